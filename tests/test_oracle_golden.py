@@ -65,6 +65,6 @@ def test_decode_window_matches_sequenceprovider_rules():
     n = len(ref)
     assert port.decode_window(packed, n, 0, 10) == b"ACGTTGCA\0\0"
     assert port.decode_window(packed, n, 1, 10) == b"CGTTGCANA\0"          # odd offset decodes len+1 bases
-    assert port.decode_window(packed, n, 2, 9) == b"GTTGCAx\0\0"            # odd len: last decoded char -> 'x'
+    assert port.decode_window(packed, n, 2, 9) == b"GTTGCANx\0"            # odd len 7: 8 chars decoded, last -> 'x'
     assert port.decode_window(packed, n, 20, 10) == b"ACCAxxxx\0\0"         # past the concatenated end -> 'x'
     assert port.decode_window(packed, n, n, 10) is None                      # offset >= length -> failure
