@@ -1,0 +1,175 @@
+/* ngm_b200.h -- C ABI of the B200 (sm_100a) alignment backend for NextGenMap.
+ *
+ * This is the drop-in boundary for NGM's seed-and-extend hot path: everything
+ * NGM's ScoreBuffer / AlignmentBuffer reach through the IAlignment plugin
+ * interface (reference: include/IAlignment.h:48-69) plus the descriptor fast
+ * path that replaces their per-pair host-side window decoding
+ * (reference: src/ScoreBuffer.cpp:87-127, src/AlignmentBuffer.cpp:73-115,
+ * src/SequenceProvider.cpp:382-441).  Plain pointers and sizes only; no C++,
+ * CUDA or torch types cross this boundary.  Every entry point returns >= 0 on
+ * success and a negative NGM_B200_E* code on failure; ngm_b200_last_error()
+ * gives the text.  There is NO CPU fallback behind any of these calls.
+ *
+ * C++ plugin exports layered on top (nextgenmap_b200/csrc/plugin.cpp) mirror the
+ * reference's historical DLL surface (lib/mason/opencl/SWOcl_export.cpp:20-83):
+ * Cookie, SetLog, SetConfig, IsAvailable, CreateAlignment, DeleteAlignment,
+ * ExternalDeleteString.
+ */
+#ifndef NGM_B200_H
+#define NGM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library itself is built with -fvisibility=hidden */
+#endif
+
+#define NGM_B200_ABI_VERSION 1
+
+enum {
+	NGM_B200_OK = 0,
+	NGM_B200_EINVAL = -1,   /* bad argument / unsupported parameter combination */
+	NGM_B200_ECUDA = -2,    /* CUDA runtime error (no device, launch failure, OOM) */
+	NGM_B200_ERANGE = -3,   /* scoring parameters outside the exact-integer range of the kernels */
+	NGM_B200_ESTATE = -4    /* call sequence error (e.g. descriptor call before set_reference) */
+};
+
+/* Alignment modes: `mode & 0xFF` of IAlignment::BatchScore/BatchAlign
+ * (reference: SWOcl.cpp:85-102, SWOclCigar.cpp:196-211). */
+enum { NGM_B200_MODE_LOCAL = 0, NGM_B200_MODE_ENDFREE = 1 };
+
+/* The Config keys the reference backend reads (SWOcl.cpp:165-166,208-242,328-348;
+ * SWOclCigar.cpp:450-454).  Penalties are positive, as in the config file. */
+typedef struct ngm_b200_params {
+	int32_t qry_max_len;        /* "qry_max_len"  -> read_length                     */
+	int32_t corridor;           /* "corridor"     -> band width in cells per row     */
+	float match_bonus;          /* "match_bonus"                                      */
+	float mismatch_penalty;     /* "mismatch_penalty"                                 */
+	float gap_read_penalty;     /* "gap_read_penalty"                                 */
+	float gap_ref_penalty;      /* "gap_ref_penalty"                                  */
+	float match_bonus_tt;       /* "match_bonus_tt" (bs-mapping / SLAMseq)            */
+	float match_bonus_tc;       /* "match_bonus_tc"                                   */
+	int32_t bs_mapping;         /* "bs_mapping"                                       */
+	int32_t slam_seq;           /* "slam_seq"                                         */
+	int32_t hard_clip;          /* "hard_clip"                                        */
+	int32_t silent_clip;        /* "silent_clip"                                      */
+	int32_t device;             /* CUDA device ordinal (low byte of CreateAlignment's mode, NGM.cpp:405) */
+	int32_t score_batch;        /* 0 = default; value returned by GetScoreBatchSize() */
+	int32_t align_batch;        /* 0 = default; value returned by GetAlignBatchSize() */
+	int32_t lane_mode;          /* 0 = auto, 1 = force int32 lanes, 2 = force s16x2 lanes (testing) */
+} ngm_b200_params;
+
+/* Layout-compatible with the reference's `struct Align` (IAlignment.h:14-28):
+ * caller-owned CIGAR / MD buffers of at least 4*max(1,qry_max_len) bytes each
+ * (AlignmentBuffer.cpp:106-107). */
+typedef struct ngm_b200_align {
+	char *cigar;                /* Align::pBuffer1 */
+	char *md;                   /* Align::pBuffer2 */
+	void *extended;             /* Align::ExtendedData (left untouched) */
+	int32_t position_offset;    /* Align::PositionOffset */
+	int32_t qstart;             /* Align::QStart */
+	int32_t qend;               /* Align::QEnd */
+	float score;                /* Align::Score (read_index hack, SWOclCigar.cpp:612-613; -1 = failed) */
+	float identity;             /* Align::Identity */
+	int32_t nm;                 /* Align::NM */
+} ngm_b200_align;
+
+/* Fixed-size per-alignment record of the descriptor / device paths. */
+typedef struct ngm_b200_align_rec {
+	int32_t position_offset;
+	int32_t qstart;
+	int32_t qend;
+	int32_t nm;
+	float identity;
+	float score;
+	uint32_t str_off;           /* offset of the CIGAR bytes in the string heap; MD follows the CIGAR */
+	uint16_t cigar_len;
+	uint16_t md_len;            /* bytes written incl. embedded NULs (SURVEY 8a note 9) */
+} ngm_b200_align_rec;
+
+/* One (read, candidate window) pair of the descriptor fast path: what
+ * ScoreBuffer::DoRun derives per pair before decoding the window on the host
+ * (ScoreBuffer.cpp:92-118). */
+typedef struct ngm_b200_pair {
+	uint64_t window_start;      /* concatenated-reference position of the window: loc - corridor/2 */
+	uint32_t read_index;        /* row in the uploaded read batch */
+	uint32_t flags;             /* bit0: use the reverse-complement read (RevSeq); bit1: direction flag (extData) */
+} ngm_b200_pair;
+
+#define NGM_B200_PAIR_REVERSE 1u   /* use RevSeq */
+#define NGM_B200_PAIR_DIR 2u       /* extData direction flag */
+#define NGM_B200_PAIR_SKIP 4u      /* do not evaluate (score -1 / -16000, alignment record score -1) */
+
+typedef struct ngm_b200_ctx ngm_b200_ctx;
+
+/* -- lifetime ------------------------------------------------------------ */
+int ngm_b200_abi_version(void);
+int ngm_b200_device_count(void);
+const char *ngm_b200_last_error(void);
+ngm_b200_ctx *ngm_b200_create(const ngm_b200_params *params);
+void ngm_b200_destroy(ngm_b200_ctx *ctx);
+/* IAlignment::GetScoreBatchSize / GetAlignBatchSize (IAlignment.h:53-54) */
+int ngm_b200_score_batch_size(const ngm_b200_ctx *ctx);
+int ngm_b200_align_batch_size(const ngm_b200_ctx *ctx);
+
+/* -- strict IAlignment path (host ASCII buffers) ------------------------- */
+/* IAlignment::BatchScore (IAlignment.h:56-60; reference impl SWOcl.cpp:33-162).
+ * ref[i]: >= qry_max_len+corridor readable bytes; qry[i]: >= qry_max_len bytes,
+ * NUL padded; dir: n direction flags or NULL.  Writes n floats; returns n. */
+int ngm_b200_batch_score(ngm_b200_ctx *ctx, int mode, int n, const char *const *ref, const char *const *qry,
+		float *scores, const char *dir);
+/* IAlignment::BatchAlign (IAlignment.h:62-66; reference impl SWOclCigar.cpp:104-370). */
+int ngm_b200_batch_align(ngm_b200_ctx *ctx, int mode, int n, const char *const *ref, const char *const *qry,
+		const char *const *qal, ngm_b200_align *results, const char *dir);
+
+/* -- descriptor fast path (reference resident in HBM) -------------------- */
+/* Upload the concatenated reference in NGM's own packing: 4 bit/base, high nibble
+ * first, A0 T1 G2 C3 N4 (SequenceProvider.cpp:72-109; body of <ref>-enc.2.ngm).
+ * concat_len = number of bases (GetConcatRefLen()). */
+int ngm_b200_set_reference(ngm_b200_ctx *ctx, const uint8_t *packed, uint64_t concat_len);
+/* Upload a batch of reads: n_reads rows of `stride` ASCII bytes (NUL padded, like
+ * MappedRead::Seq, MappedRead.cpp:25-29).  Reverse complements are derived on device
+ * (MappedRead::computeReverseSeq, MappedRead.cpp:53-67). */
+int ngm_b200_set_reads(ngm_b200_ctx *ctx, const char *reads, int n_reads, int stride);
+/* Score n pairs (ScoreBuffer::DoRun + BatchScore). */
+int ngm_b200_score_pairs(ngm_b200_ctx *ctx, int mode, int n, const ngm_b200_pair *pairs, float *scores);
+/* Align n pairs (AlignmentBuffer::DoRun + BatchAlign).  recs: n records; strings:
+ * heap of str_capacity bytes; *str_used receives the bytes needed (if it exceeds
+ * str_capacity the call returns NGM_B200_ERANGE and must be repeated with a larger heap). */
+int ngm_b200_align_pairs(ngm_b200_ctx *ctx, int mode, int n, const ngm_b200_pair *pairs, ngm_b200_align_rec *recs,
+		char *strings, size_t str_capacity, size_t *str_used);
+
+/* -- device-pointer entry points (resident pipelines, bench.py `value`) --- */
+/* All pointers are device pointers on ctx's device; work is enqueued on `stream`
+ * (a cudaStream_t passed as void*) and NOT synchronised.  d_pairs as above;
+ * d_scores: n floats; d_recs: n records; d_strings/d_str_cursor: heap + 1 uint32 cursor
+ * (zeroed by the caller before the call). */
+int ngm_b200_dev_set_reference(ngm_b200_ctx *ctx, const void *d_packed, uint64_t concat_len, void *stream);
+int ngm_b200_dev_set_reads(ngm_b200_ctx *ctx, const void *d_ascii_reads, int n_reads, int stride, void *stream);
+/* Winner gather between scoring and alignment (what ScoreBuffer::top1SE hands to
+ * AlignmentBuffer::addRead, ScoreBuffer.cpp:259-276): out[r] = pairs[best_pair[r]], or a pair
+ * flagged NGM_B200_PAIR_SKIP when read r has no candidate (its record comes back with score -1). */
+int ngm_b200_dev_gather_winners(ngm_b200_ctx *ctx, int n_reads, const void *d_pairs, const void *d_best_pair, void *d_out_pairs,
+		void *stream);
+int ngm_b200_dev_score_pairs(ngm_b200_ctx *ctx, int mode, int n, const void *d_pairs, void *d_scores, void *stream);
+int ngm_b200_dev_align_pairs(ngm_b200_ctx *ctx, int mode, int n, const void *d_pairs, void *d_recs, void *d_strings,
+		uint32_t str_capacity, void *d_str_cursor, void *stream);
+/* Per-read top-1 selection over scored candidates (ScoreBuffer::top1SE + computeMQ,
+ * ScoreBuffer.cpp:34-40,228-277).  cand_begin: n_reads+1 offsets into the pair/score arrays.
+ * best_pair[r] = index of the winning pair or -1; mapq[r]. */
+int ngm_b200_dev_select_top1(ngm_b200_ctx *ctx, int n_reads, const void *d_cand_begin, const void *d_scores,
+		void *d_best_pair, void *d_mapq, void *stream);
+/* Number of kernels this context has launched since creation (bench.py gpu_launches). */
+uint64_t ngm_b200_launch_count(const ngm_b200_ctx *ctx);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,57 @@
+// ngm_launch.h -- host-callable launchers of the templated DP kernels.  Each
+// kernel family lives in its own translation unit so nvcc can build them in parallel.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "ngm_common.cuh"
+#include "../../include/ngm_b200.h"
+
+namespace ngm {
+
+// Band capacities compiled into the library: X(capacity, smallest corridor served).
+// A corridor c is served by the smallest capacity >= c; slots >= c are pinned to the
+// sentinel at run time (only slots >= LO carry that select).
+#define NGM_BAND_LIST(X) \
+	X(12, 1) X(16, 13) X(20, 17) X(24, 21) X(28, 25) X(32, 29) X(36, 33) X(40, 37) X(44, 41) X(48, 45) \
+	X(56, 49) X(64, 57) X(72, 65) X(80, 73) X(96, 81) X(112, 97) X(128, 113) X(160, 129)
+
+constexpr int kMaxCorridor = 160;
+
+int band_capacity(int corridor);          // 0 if unsupported
+int ptr_words_for(int capacity);          // 32-bit pointer words per DP row
+
+struct ScoreArgs {
+	DevParams P;
+	const PairDesc *pairs;
+	int n;
+	const uint32_t *reads_fwd, *reads_rev;
+	const uint16_t *rlen;
+	const uint32_t *ref4;
+	float *out;
+};
+
+struct AlignArgs {
+	DevParams P;
+	const PairDesc *pairs;
+	int n;
+	const uint32_t *reads_fwd, *reads_rev;
+	const uint16_t *rlen;
+	const uint32_t *ref4;
+	uint32_t *ptr_scratch;
+	uint16_t *ops_scratch;
+	int stride, ops_cap;
+	ngm_b200_align_rec *recs;
+	char *strings;
+	uint32_t str_cap;
+	uint32_t *cursor;
+};
+
+// int32 lanes, one pair per thread
+cudaError_t launch_score_i32(int capacity, int mode, const ScoreArgs &a, cudaStream_t st);
+cudaError_t launch_align_i32(int capacity, int mode, const AlignArgs &a, cudaStream_t st);
+// s16x2 lanes, two pairs per thread
+cudaError_t launch_score_s16(int capacity, int mode, const ScoreArgs &a, cudaStream_t st);
+
+}  // namespace ngm

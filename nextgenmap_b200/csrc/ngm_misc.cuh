@@ -1,0 +1,178 @@
+// ngm_misc.cuh -- small non-templated kernels: ASCII packers, reference transcoder,
+// pair resolution, top-1 selection.  Included by exactly one translation unit (ngm_b200.cu).
+#pragma once
+
+#include "ngm_common.cuh"
+#include "../../include/ngm_b200.h"
+
+namespace ngm {
+
+// ---------------------------------------------------------------------------
+// packers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ascii_code(uint32_t ch) {
+	// oclDefines.cl:64-80
+	switch (ch) {
+	case 'A': case 'a': return 0;
+	case 'C': case 'c': return 1;
+	case 'G': case 'g': return 2;
+	case 'T': case 't': return 3;
+	case 'N': case 'n': return 5;
+	case 0: return 6;
+	default: return 4;
+	}
+}
+
+// ASCII rows -> packed code words.  One thread per output word; bytes past `width`
+// or rows >= src_rows read as NUL.  If rlen32 != nullptr, rlen32[row] = index of the last non-NUL byte + 1;
+// if noncanon != nullptr, noncanon[row] = 1 when the row holds a byte outside "ACGTNx\\0".
+__global__ void pack_ascii_kernel(const uint8_t *__restrict__ src, int src_rows, int rows, int width, int src_stride, uint32_t *__restrict__ dst,
+		int dst_words, unsigned int *__restrict__ rlen32, uint8_t *__restrict__ noncanon) {
+	const long long gid = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (gid >= (long long) rows * dst_words) return;
+	const int row = (int) (gid / dst_words), w = (int) (gid % dst_words);
+	const uint8_t *s = src + (size_t) row * src_stride;
+	uint32_t word = 0;
+	int last = 0;
+	bool odd = false;
+#pragma unroll
+	for (int k = 0; k < 8; ++k) {
+		const int i = 8 * w + k;
+		const uint32_t ch = (i < width && row < src_rows) ? s[i] : 0u;
+		word |= ascii_code(ch) << (4 * k);
+		if (ch != 0) last = i + 1;
+		// bytes the code -> char table of the formatter cannot reproduce (lower case, IUPAC, ...)
+		odd |= !(ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T' || ch == 'N' || ch == 'x' || ch == 0);
+	}
+	dst[(size_t) row * dst_words + w] = word;
+	if (noncanon != nullptr && odd && row < src_rows) noncanon[row] = 1;
+	if (rlen32 != nullptr && last > 0) atomicMax(rlen32 + row, (unsigned int) last);
+}
+
+__global__ void narrow_rlen_kernel(const unsigned int *__restrict__ rlen32, uint16_t *__restrict__ rlen, int rows) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < rows) rlen[i] = (uint16_t) rlen32[i];
+}
+
+// strict path: pair i uses read row i and the window packed at word i * win_words
+__global__ void strict_pairs_kernel(PairDesc *__restrict__ pairs, const uint8_t *__restrict__ flags, int n, int win_words) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	PairDesc d;
+	d.win_nib = (uint64_t) i * (uint64_t) win_words * 8ull;
+	d.read_idx = (uint32_t) i;
+	d.flags = flags[i];
+	pairs[i] = d;
+}
+
+// reverse complement of packed reads (MappedRead::computeReverseSeq, MappedRead.cpp:36-67):
+// rev[k] = cpl(fwd[len-1-k]) for k < len, NUL beyond; only A<->T and C<->G are complemented.
+__global__ void revcomp_kernel(const uint32_t *__restrict__ fwd, const uint16_t *__restrict__ rlen, int rows, int words,
+		uint32_t *__restrict__ rev) {
+	const long long gid = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (gid >= (long long) rows * words) return;
+	const int row = (int) (gid / words), w = (int) (gid % words);
+	const int len = rlen[row];
+	const uint32_t *f = fwd + (size_t) row * words;
+	uint32_t word = 0;
+#pragma unroll
+	for (int k = 0; k < 8; ++k) {
+		const int i = 8 * w + k;
+		uint32_t code = kCodeNul;
+		if (i < len) {
+			code = code_at(f, len - 1 - i);
+			if (code < 4) code = 3 - code;
+		}
+		word |= code << (4 * k);
+	}
+	rev[(size_t) row * words + w] = word;
+}
+
+// NGM reference packing (4 bit/base, high nibble first, A0 T1 G2 C3 N4,
+// SequenceProvider.cpp:72-109) -> device code words.  Positions >= concat_len become
+// 'x' (code 4) like DecodeRefSequence's overhang (SequenceProvider.cpp:427-429); the
+// region [n_region, n_region + n_len) is filled with 'N' (ScoreBuffer.cpp:117).
+__global__ void transcode_ref_kernel(const uint8_t *__restrict__ packed, unsigned long long concat_len, uint32_t *__restrict__ dst,
+		unsigned long long total_words, unsigned long long n_region_word) {
+	const unsigned long long w = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= total_words) return;
+	uint32_t word = 0;
+	if (w >= n_region_word) {
+		word = 0x55555555u;
+	} else {
+#pragma unroll
+		for (int k = 0; k < 8; ++k) {
+			const unsigned long long pos = 8ull * w + k;
+			uint32_t code = 4;
+			if (pos < concat_len) {
+				const uint32_t b = packed[pos >> 1];
+				const uint32_t v = (pos & 1) ? (b & 0xF) : (b >> 4);
+				code = v == 0 ? 0u : v == 1 ? 3u : v == 2 ? 2u : v == 3 ? 1u : v == 4 ? 5u : 4u;
+			}
+			word |= code << (4 * k);
+		}
+	}
+	dst[w] = word;
+}
+
+// descriptor path: translate ngm_b200_pair::window_start into a nibble index of the
+// resident reference; starts >= concat_len (incl. the unsigned underflow of
+// loc - corridor/2) select the all-'N' region (ScoreBuffer.cpp:113-118).
+__global__ void resolve_pairs_kernel(const ngm_b200_pair *__restrict__ in, PairDesc *__restrict__ out, int n, unsigned long long concat_len,
+		unsigned long long n_region_nib, const uint16_t *__restrict__ rlen) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const ngm_b200_pair p = in[i];
+	PairDesc d;
+	d.win_nib = p.window_start < concat_len ? p.window_start : n_region_nib;
+	d.read_idx = p.read_index;
+	d.flags = p.flags & (PF_REVERSE | PF_DIR | PF_INACTIVE);
+	if (rlen[p.read_index] == 0) d.flags |= PF_INACTIVE;      // an empty read is its own quad leader
+	out[i] = d;
+}
+
+__global__ void gather_winners_kernel(int n_reads, const ngm_b200_pair *__restrict__ pairs, const int *__restrict__ best_pair,
+		ngm_b200_pair *__restrict__ out) {
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const int b = best_pair[r];
+	ngm_b200_pair p;
+	if (b >= 0) {
+		p = pairs[b];
+	} else {
+		p.window_start = 0;
+		p.read_index = (uint32_t) r;
+		p.flags = PF_INACTIVE;
+	}
+	out[r] = p;
+}
+
+// ScoreBuffer::top1SE + computeMQ (ScoreBuffer.cpp:34-40,228-277); one thread per read.
+__global__ void select_top1_kernel(int n_reads, const int *__restrict__ cand_begin, const float *__restrict__ scores,
+		int *__restrict__ best_pair, int *__restrict__ mapq) {
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const int b = cand_begin[r], e = cand_begin[r + 1];
+	float best = 0.0f, second = 0.0f;
+	int besti = 0;
+	for (int j = b; j < e; ++j) {
+		const float s = scores[j];
+		if (s > second) {
+			if (s > best) {
+				second = best;
+				best = s;
+				besti = j - b;
+			} else if (s == best) {
+				second = best;
+			} else {
+				second = s;
+			}
+		}
+	}
+	int mq = 0;
+	if (best > 0.0f && second >= 0.0f) mq = (int) ceilf(60.0f * (best - second) / best);
+	best_pair[r] = e > b ? b + besti : -1;
+	mapq[r] = mq;
+}
+
+}  // namespace ngm

@@ -1,0 +1,1 @@
+from .cuda_sw import CudaSW, Align, Params, load_library, NgmB200Error  # noqa: F401

@@ -1,0 +1,234 @@
+"""Host-side mirror of the reference's alignment plugin interface on top of the C ABI.
+
+``CudaSW`` has the surface of the reference's ``IAlignment`` (include/IAlignment.h:48-69)
+as implemented by ``SWOclCigar`` (lib/mason/opencl/SWOclCigar.h:17-42): ``GetScoreBatchSize``,
+``GetAlignBatchSize``, ``BatchScore``, ``BatchAlign`` -- same argument meaning, same result
+fields (``Align``: pBuffer1 = CIGAR, pBuffer2 = MD, PositionOffset, QStart, QEnd, Score,
+Identity, NM) -- plus the descriptor fast path.  Everything is computed by
+``libngm_b200.so`` (hand-written sm_100a CUDA); there is no CPU fallback: if the library or a
+CUDA device is missing, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from pathlib import Path
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parents[1]
+LIB_PATH = PKG / "libngm_b200.so"
+
+
+class NgmB200Error(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    """ngm_b200_params (include/ngm_b200.h); defaults = Config.cpp:440-447."""
+    _fields_ = [("qry_max_len", C.c_int32), ("corridor", C.c_int32), ("match_bonus", C.c_float),
+                ("mismatch_penalty", C.c_float), ("gap_read_penalty", C.c_float), ("gap_ref_penalty", C.c_float),
+                ("match_bonus_tt", C.c_float), ("match_bonus_tc", C.c_float), ("bs_mapping", C.c_int32),
+                ("slam_seq", C.c_int32), ("hard_clip", C.c_int32), ("silent_clip", C.c_int32), ("device", C.c_int32),
+                ("score_batch", C.c_int32), ("align_batch", C.c_int32), ("lane_mode", C.c_int32)]
+
+
+class _CAlign(C.Structure):
+    _fields_ = [("cigar", C.c_void_p), ("md", C.c_void_p), ("extended", C.c_void_p), ("position_offset", C.c_int32),
+                ("qstart", C.c_int32), ("qend", C.c_int32), ("score", C.c_float), ("identity", C.c_float), ("nm", C.c_int32)]
+
+
+ALIGN_REC = np.dtype([("position_offset", "<i4"), ("qstart", "<i4"), ("qend", "<i4"), ("nm", "<i4"), ("identity", "<f4"),
+                      ("score", "<f4"), ("str_off", "<u4"), ("cigar_len", "<u2"), ("md_len", "<u2")])
+PAIR = np.dtype([("window_start", "<u8"), ("read_index", "<u4"), ("flags", "<u4")])
+PF_REVERSE, PF_DIR, PF_SKIP = 1, 2, 4
+
+
+@dataclass
+class Align:
+    """The reference's ``struct Align`` (IAlignment.h:14-28)."""
+    pBuffer1: bytes      # CIGAR
+    pBuffer2: bytes      # MD
+    PositionOffset: int
+    QStart: int
+    QEnd: int
+    Score: float
+    Identity: float
+    NM: int
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load the in-tree CUDA library; fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise NgmB200Error(f"{LIB_PATH} not built: run `python -m nextgenmap_b200.build` (there is no CPU fallback)")
+    lib = C.CDLL(str(LIB_PATH))
+    lib.ngm_b200_last_error.restype = C.c_char_p
+    lib.ngm_b200_create.restype = C.c_void_p
+    lib.ngm_b200_create.argtypes = [C.POINTER(Params)]
+    lib.ngm_b200_destroy.argtypes = [C.c_void_p]
+    lib.ngm_b200_launch_count.restype = C.c_uint64
+    lib.ngm_b200_launch_count.argtypes = [C.c_void_p]
+    for name in ("ngm_b200_score_batch_size", "ngm_b200_align_batch_size"):
+        getattr(lib, name).argtypes = [C.c_void_p]
+    lib.ngm_b200_batch_score.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ngm_b200_batch_align.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ngm_b200_set_reference.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.ngm_b200_set_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.ngm_b200_score_pairs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.ngm_b200_align_pairs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.ngm_b200_dev_set_reference.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.ngm_b200_dev_gather_winners.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ngm_b200_dev_set_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.ngm_b200_dev_score_pairs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ngm_b200_dev_align_pairs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.ngm_b200_dev_select_top1.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def _row_pointers(a: np.ndarray) -> np.ndarray:
+    """char** for a C-contiguous uint8 [n, w] array."""
+    return a.ctypes.data + np.arange(a.shape[0], dtype=np.uint64) * np.uint64(a.strides[0])
+
+
+class CudaSW:
+    """B200 implementation of the reference's IAlignment plugin (SWOclCigar equivalent)."""
+
+    def __init__(self, qry_max_len: int, corridor: int, match_bonus: float = 10, mismatch_penalty: float = 15,
+                 gap_read_penalty: float = 20, gap_ref_penalty: float = 20, match_bonus_tt: float = 0,
+                 match_bonus_tc: float = 0, bs_mapping: int = 0, slam_seq: int = 0, hard_clip: int = 0,
+                 silent_clip: int = 0, device: int = 0, score_batch: int = 0, align_batch: int = 0, lane_mode: int = 0):
+        self.lib = load_library()
+        self.params = Params(qry_max_len, corridor, match_bonus, mismatch_penalty, gap_read_penalty, gap_ref_penalty,
+                             match_bonus_tt, match_bonus_tc, bs_mapping, slam_seq, hard_clip, silent_clip, device,
+                             score_batch, align_batch, lane_mode)
+        self.qml, self.corridor = qry_max_len, corridor
+        self.ctx = self.lib.ngm_b200_create(C.byref(self.params))
+        if not self.ctx:
+            raise NgmB200Error(self._err())
+
+    def _err(self) -> str:
+        return self.lib.ngm_b200_last_error().decode(errors="replace")
+
+    def _check(self, rc: int) -> int:
+        if rc < 0:
+            raise NgmB200Error(f"ngm_b200 error {rc}: {self._err()}")
+        return rc
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.ngm_b200_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- IAlignment ---------------------------------------------------------
+    def GetScoreBatchSize(self) -> int:
+        return self.lib.ngm_b200_score_batch_size(self.ctx)
+
+    def GetAlignBatchSize(self) -> int:
+        return self.lib.ngm_b200_align_batch_size(self.ctx)
+
+    def launch_count(self) -> int:
+        return int(self.lib.ngm_b200_launch_count(self.ctx))
+
+    def _rows(self, refSeqList, qrySeqList):
+        refs = np.ascontiguousarray(refSeqList, dtype=np.uint8)
+        qrys = np.ascontiguousarray(qrySeqList, dtype=np.uint8)
+        if refs.ndim != 2 or qrys.ndim != 2 or refs.shape[0] != qrys.shape[0]:
+            raise ValueError("refSeqList / qrySeqList must be [n, width] byte arrays of equal n")
+        if refs.shape[1] < self.qml + self.corridor or qrys.shape[1] < self.qml:
+            raise ValueError("rows shorter than qry_max_len+corridor / qry_max_len")
+        return refs, qrys
+
+    def BatchScore(self, mode: int, refSeqList, qrySeqList, extData: Optional[Sequence[int]] = None) -> np.ndarray:
+        """IAlignment::BatchScore -> float32 scores (SWOcl.cpp:33-162)."""
+        refs, qrys = self._rows(refSeqList, qrySeqList)
+        n = refs.shape[0]
+        out = np.full(n, np.nan, dtype=np.float32)
+        if n == 0:
+            return out
+        rp, qp = _row_pointers(refs), _row_pointers(qrys)
+        d = None if extData is None else np.ascontiguousarray(extData, dtype=np.uint8)
+        got = self._check(self.lib.ngm_b200_batch_score(self.ctx, mode, n, rp.ctypes.data, qp.ctypes.data, out.ctypes.data,
+                                                        None if d is None else d.ctypes.data))
+        assert got == n
+        return out
+
+    def BatchAlign(self, mode: int, refSeqList, qrySeqList, qalSeqList=None, extData: Optional[Sequence[int]] = None) -> List[Align]:
+        """IAlignment::BatchAlign -> list of Align (SWOclCigar.cpp:104-370)."""
+        refs, qrys = self._rows(refSeqList, qrySeqList)
+        n = refs.shape[0]
+        if n == 0:
+            return []
+        stride = 4 * max(1, self.qml) + 2 * self.corridor + 64
+        cig = np.zeros((n, stride), np.uint8)
+        md = np.zeros((n, stride), np.uint8)
+        cig[:, :3] = 0x21                      # AlignmentBuffer.cpp:108-109
+        md[:, :3] = 0x21
+        res = (_CAlign * n)()
+        cp, mp = _row_pointers(cig), _row_pointers(md)
+        for i in range(n):
+            res[i].cigar = int(cp[i])
+            res[i].md = int(mp[i])
+        rp, qp = _row_pointers(refs), _row_pointers(qrys)
+        d = None if extData is None else np.ascontiguousarray(extData, dtype=np.uint8)
+        got = self._check(self.lib.ngm_b200_batch_align(self.ctx, mode, n, rp.ctypes.data, qp.ctypes.data, qp.ctypes.data,
+                                                        C.addressof(res), None if d is None else d.ctypes.data))
+        assert got == n
+        out = []
+        for i in range(n):
+            r = res[i]
+            out.append(Align(cig[i].tobytes().split(b"\0")[0], md[i].tobytes().split(b"\0")[0], r.position_offset, r.qstart,
+                             r.qend, r.score, r.identity, r.nm))
+        return out
+
+    # -- descriptor fast path -----------------------------------------------
+    def set_reference(self, packed: np.ndarray, concat_len: int) -> None:
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        self._check(self.lib.ngm_b200_set_reference(self.ctx, packed.ctypes.data, concat_len))
+
+    def set_reads(self, reads: np.ndarray) -> None:
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        self._check(self.lib.ngm_b200_set_reads(self.ctx, reads.ctypes.data, reads.shape[0], reads.shape[1]))
+
+    def score_pairs(self, mode: int, pairs: np.ndarray) -> np.ndarray:
+        pairs = np.ascontiguousarray(pairs, dtype=PAIR)
+        out = np.full(len(pairs), np.nan, dtype=np.float32)
+        if len(pairs):
+            self._check(self.lib.ngm_b200_score_pairs(self.ctx, mode, len(pairs), pairs.ctypes.data, out.ctypes.data))
+        return out
+
+    def align_pairs(self, mode: int, pairs: np.ndarray, str_capacity: Optional[int] = None):
+        pairs = np.ascontiguousarray(pairs, dtype=PAIR)
+        n = len(pairs)
+        recs = np.zeros(n, dtype=ALIGN_REC)
+        cap = str_capacity or max(4096, 64 * n)
+        used = C.c_size_t(0)
+        for _ in range(2):
+            heap = np.zeros(cap, dtype=np.uint8)
+            rc = self.lib.ngm_b200_align_pairs(self.ctx, mode, n, pairs.ctypes.data, recs.ctypes.data, heap.ctypes.data, cap, C.byref(used))
+            if rc == -3 and used.value > cap:
+                cap = used.value + 64
+                continue
+            self._check(rc)
+            break
+        return recs, heap[: used.value]
+
+    @staticmethod
+    def strings_of(recs: np.ndarray, heap: np.ndarray, i: int):
+        r = recs[i]
+        o = int(r["str_off"])
+        raw = heap.tobytes()
+        return raw[o: o + int(r["cigar_len"])], raw[o + int(r["cigar_len"]): o + int(r["cigar_len"]) + int(r["md_len"])]
