@@ -1,0 +1,510 @@
+#!/usr/bin/env python
+"""bench.py -- reads/s of NGM's seed-and-extend hot path (BatchScore -> top-1 -> BatchAlign).
+
+Workload (BASELINE.json configs[1]): 10 M x 150 bp single-end synthetic reads against a 3 Gbp
+synthetic reference (24 x 125 Mbp contigs), ~1.5 candidate windows per read, local alignment,
+default scoring (10/-15/-20/-20), qry_max_len 152, corridor 27.  One "step" = one pass of the hot
+path over the whole read set of this rank:
+
+    pack reads (+ reverse complements) -> score every (read, window) pair -> top-1 selection + MAPQ
+    -> banded alignment with backtrace of the winner -> CIGAR / MD / NM / identity records
+
+* ``value``  : device-resident throughput -- reads, descriptors and the packed reference are in
+               HBM when the timed region starts; results stay in HBM.
+* ``e2e``    : the same pipeline through the C ABI with HOST (pinned) inputs and outputs: every
+               step copies reads + descriptors host->device and records + strings device->host,
+               sub-batches ping-pong over two streams.
+* ``--impl reference`` : the reference's own CPU implementation of the path (oracle/_ref: its
+               unmodified OpenCL kernels on the vendored AMD CPU runtime, one instance per host
+               core like ``ngm -t``), on a bounded sample of the same workload.
+
+Multi-GPU (torchrun): reads shard across ranks (weak scaling: every rank owns a full-size read
+set), each rank holds the whole reference; NCCL only broadcasts the packed reference at start-up
+and reduces the mapping counters at the end.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+READ_LEN = 150
+MODE_LOCAL = 0
+ALG_BYTES_SCORE = 180          # ceil(L/2) + ceil((L+corridor)/2) + 12 + 4 at 150 bp
+CELLS_PER_PAIR = 150 * 27      # L x corridor
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--reads", type=int, default=int(os.environ.get("NGM_BENCH_READS", 10_000_000)))
+    ap.add_argument("--contigs", type=int, default=int(os.environ.get("NGM_BENCH_CONTIGS", 24)))
+    ap.add_argument("--contig-len", type=int, default=int(os.environ.get("NGM_BENCH_CONTIG_LEN", 125_000_000)))
+    ap.add_argument("--sub-batch", type=int, default=1_000_000, help="reads per e2e sub-batch")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------
+# CPU baseline sample (shared by cpu_baseline and --impl reference)
+# ---------------------------------------------------------------------------
+def cpu_sample_windows(packed_host: np.ndarray, concat_len: int, reads: np.ndarray, pairs: np.ndarray, cand_begin: np.ndarray,
+                       n_sample: int, qml: int, corridor: int):
+    """Decode the sample's windows the way ScoreBuffer does (ScoreBuffer.cpp:113-118) and order the pairs
+    so that each read's first candidate (the true locus) comes first: those are the ones aligned."""
+    from oracle import port
+    buf_len = ((qml + corridor) | 1) + 1
+    comp = np.arange(256, dtype=np.uint8)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+    first, rest = [], []
+    for r in range(n_sample):
+        for k, j in enumerate(range(cand_begin[r], cand_begin[r + 1])):
+            (first if k == 0 else rest).append(j)
+    order = first + rest
+    refs = np.zeros((len(order), buf_len), np.uint8)
+    qrys = np.zeros((len(order), qml), np.uint8)
+    for i, j in enumerate(order):
+        start = int(pairs["window_start"][j])
+        w = port.decode_window(packed_host, concat_len, start, buf_len)
+        refs[i] = np.frombuffer(w, np.uint8) if w is not None else ord("N")
+        row = reads[int(pairs["read_index"][j])]
+        if int(pairs["flags"][j]) & 1:
+            L = int(np.count_nonzero(row))
+            rc = np.zeros_like(row)
+            rc[:L] = comp[row[:L][::-1]]
+            row = rc
+        qrys[i] = row
+    return refs, qrys, len(first)
+
+
+def run_cpu_reference(refs, qrys, n_align, n_reads, qml, corridor, threads, warm, passes):
+    """reads/s of the reference's own CPU path on the sample; falls back to the C port if oracle/_ref cannot run."""
+    from oracle import ref_driver as rd
+    if rd.available():
+        try:
+            r = rd.bench(refs, qrys, qml, corridor, MODE_LOCAL, n_align, threads, warm, passes)
+            return {"value": n_reads * r["passes"] / r["wall_seconds"], "kind": "reference", "cores": threads,
+                    "score_pairs_per_s": r["scored"] / max(r["score_seconds"], 1e-9), "align_pairs_per_s": r["aligned"] / max(r["align_seconds"], 1e-9),
+                    "wall_seconds": r["wall_seconds"]}
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write(f"[bench] oracle/_ref harness failed ({e}); timing the C port instead\n")
+    from oracle import port
+    t0 = time.perf_counter()
+    for _ in range(passes):
+        port.batch_score(refs, qrys, qml, corridor, MODE_LOCAL)
+        port.batch_align(refs[:n_align], qrys[:n_align], qml, corridor, MODE_LOCAL)
+    dt = time.perf_counter() - t0
+    return {"value": n_reads * passes / dt, "kind": "port", "cores": 1, "wall_seconds": dt}
+
+
+# ---------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    distributed = world > 1
+
+    if args.impl == "reference" and rank != 0:
+        return 0                                    # rank 0 alone runs the CPU arm
+
+    from nextgenmap_b200 import workload
+    qml, corridor = workload.shapes_for(READ_LEN)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the workload is generated on the GPU; the product has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if distributed and args.impl != "reference":
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- workload ---------------------------------------------------------
+    t_setup = time.perf_counter()
+    if distributed and args.impl != "reference":
+        # rank 0 builds the reference, NCCL broadcasts the packed bytes over NVLink
+        if rank == 0:
+            ref = workload.make_reference(dev, args.contigs, args.contig_len, seed=20261017)
+            meta = torch.tensor([ref.concat_len], dtype=torch.int64, device=dev)
+        else:
+            meta = torch.zeros(1, dtype=torch.int64, device=dev)
+        dist.broadcast(meta, 0)
+        if rank != 0:
+            starts = workload.SPACER + np.arange(args.contigs, dtype=np.int64) * (args.contig_len + workload.SPACER)
+            ref = workload.Reference(torch.empty(int(meta.item()) // 2, dtype=torch.uint8, device=dev), int(meta.item()), starts, args.contig_len)
+        dist.broadcast(ref.packed, 0)
+    else:
+        ref = workload.make_reference(dev, args.contigs, args.contig_len, seed=20261017)
+    n_reads = args.reads
+    if args.impl == "reference":
+        n_reads = min(n_reads, 200_000)             # only a sample is needed on the CPU arm
+    batch = workload.make_reads(ref, n_reads, READ_LEN, qml, corridor, seed=20261018 + 1 + rank)
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t_setup
+
+    cfg = {"workload": f"{args.reads} x {READ_LEN} bp SE synthetic reads vs {args.contigs} x {args.contig_len} bp synthetic reference "
+                       f"({ref.concat_len / 1e9:.2f} Gbp concatenated), ~1.5 candidates/read, local mode, qry_max_len {qml}, corridor {corridor}",
+           "reads_per_step_per_gpu": args.reads, "pairs_per_step_per_gpu": batch.n_pairs if args.impl != "reference" else None,
+           "step": "set_reads(pack+revcomp) -> score pairs -> top1+MAPQ -> gather winners -> align+backtrace+CIGAR/MD",
+           "cache": "inputs larger than L2 (1.5 GB reads + 1.5 GB packed reference, random window gathers); no flush needed",
+           "parallelism": f"read-sharded x{world}, reference replicated"}
+
+    host_threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+    # ---- reference arm ----------------------------------------------------
+    if args.impl == "reference":
+        n_sample = args.cpu_sample or min(n_reads, max(20_000, 3000 * host_threads))
+        packed_host = ref.packed.cpu().numpy()
+        reads_h = batch.reads[:n_sample].cpu().numpy()
+        cb = batch.cand_begin[: n_sample + 1].cpu().numpy()
+        pairs_h = batch.pairs[: int(cb[-1])].cpu().numpy().view(np.dtype([("window_start", "<u8"), ("read_index", "<u4"), ("flags", "<u4")])).reshape(-1)
+        refs, qrys, n_align = cpu_sample_windows(packed_host, ref.concat_len, reads_h, pairs_h, cb, n_sample, qml, corridor)
+        res = run_cpu_reference(refs, qrys, n_align, n_sample, qml, corridor, host_threads, args.warmup, args.steps)
+        sample = f"{n_sample} reads / {len(refs)} pairs of the workload per step, {res['cores']} host threads (one backend instance each, like ngm -t)"
+        line = {"impl": "reference", "metric": "reads/sec aligned (150bp SE vs 3Gbp ref)", "value": res["value"], "unit": "reads/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * res["wall_seconds"] / max(args.steps, 1), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (integer-valued)", "data": "synthetic", "config": cfg,
+                "cpu_baseline": {"value": res["value"], "unit": "reads/s", "cores": res["cores"], "kind": res["kind"], "sample": sample},
+                "e2e": {"value": res["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ---- B200 arm ---------------------------------------------------------
+    from nextgenmap_b200.host import CudaSW
+    from nextgenmap_b200.host.cuda_sw import ALIGN_REC
+    sw = CudaSW(qml, corridor, device=local_rank)
+    lib, ctx = sw.lib, sw.ctx
+    st = torch.cuda.current_stream().cuda_stream
+
+    def check(rc):
+        if rc < 0:
+            raise RuntimeError(lib.ngm_b200_last_error().decode())
+        return rc
+
+    check(lib.ngm_b200_dev_set_reference(ctx, ref.packed.data_ptr(), ref.concat_len, st))
+    n, npairs = batch.n_reads, batch.n_pairs
+    d_scores = torch.empty(npairs, dtype=torch.float32, device=dev)
+    d_best = torch.empty(n, dtype=torch.int32, device=dev)
+    d_mapq = torch.empty(n, dtype=torch.int32, device=dev)
+    d_wpairs = torch.empty((n, 16), dtype=torch.uint8, device=dev)
+    d_recs = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+    str_cap = 48 * n
+    d_strings = torch.empty(str_cap, dtype=torch.uint8, device=dev)
+    d_cursor = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def resident_step():
+        check(lib.ngm_b200_dev_set_reads(ctx, batch.reads.data_ptr(), n, qml, st))
+        check(lib.ngm_b200_dev_score_pairs(ctx, MODE_LOCAL, npairs, batch.pairs.data_ptr(), d_scores.data_ptr(), st))
+        check(lib.ngm_b200_dev_select_top1(ctx, n, batch.cand_begin.data_ptr(), d_scores.data_ptr(), d_best.data_ptr(), d_mapq.data_ptr(), st))
+        check(lib.ngm_b200_dev_gather_winners(ctx, n, batch.pairs.data_ptr(), d_best.data_ptr(), d_wpairs.data_ptr(), st))
+        d_cursor.zero_()
+        check(lib.ngm_b200_dev_align_pairs(ctx, MODE_LOCAL, n, d_wpairs.data_ptr(), d_recs.data_ptr(), d_strings.data_ptr(), str_cap, d_cursor.data_ptr(), st))
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        resident_step()
+    barrier()
+    if int(d_cursor.item()) > str_cap:
+        raise RuntimeError("string heap too small")
+
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = sw.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        resident_step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = sw.launch_count() - launches0 + args.steps      # + one memset (cursor) per step issued by torch
+    clk = clocks.stop()
+
+    # per-kernel timing of the two DP kernels on the launching stream (roofline)
+    def time_call(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    ms_score = time_call(lambda: check(lib.ngm_b200_dev_score_pairs(ctx, MODE_LOCAL, npairs, batch.pairs.data_ptr(), d_scores.data_ptr(), st)))
+
+    def align_only():
+        d_cursor.zero_()
+        check(lib.ngm_b200_dev_align_pairs(ctx, MODE_LOCAL, n, d_wpairs.data_ptr(), d_recs.data_ptr(), d_strings.data_ptr(), str_cap, d_cursor.data_ptr(), st))
+
+    ms_align = time_call(align_only)
+    ms_pack = time_call(lambda: check(lib.ngm_b200_dev_set_reads(ctx, batch.reads.data_ptr(), n, qml, st)))
+
+    recs_all = d_recs.cpu().numpy().view(ALIGN_REC).reshape(-1)
+    mapped = int(np.count_nonzero(recs_all["score"] >= 0))
+    used_strings = int(d_cursor.item())
+
+    # ---- end to end through the C ABI with host buffers ---------------------
+    e2e = None
+    if not args.no_e2e:
+        SB = min(args.sub_batch, n)
+        cb_h = batch.cand_begin.cpu().numpy()
+        h_reads = batch.reads.cpu().pin_memory()
+        # descriptors as the caller would hand them over per sub-batch: read indices and candidate
+        # offsets relative to the sub-batch (prepared once, outside the timed region)
+        pdt = np.dtype([("window_start", "<u8"), ("read_index", "<u4"), ("flags", "<u4")])
+        pairs_np = batch.pairs.cpu().numpy().view(pdt).reshape(-1).copy()
+        cb_rel = []
+        for s in range(0, n, SB):
+            m = min(SB, n - s)
+            p0, p1 = int(cb_h[s]), int(cb_h[s + m])
+            pairs_np["read_index"][p0:p1] -= np.uint32(s)
+            cb_rel.append((cb_h[s: s + m + 1] - cb_h[s]).astype(np.int32))
+        h_pairs = torch.from_numpy(pairs_np.view(np.uint8).reshape(-1, 16)).pin_memory()
+        h_cbs = [torch.from_numpy(c).pin_memory() for c in cb_rel]
+        max_pairs = int(max(cb_h[min(s + SB, n)] - cb_h[s] for s in range(0, n, SB)))
+        h_recs = torch.empty((n, 32), dtype=torch.uint8).pin_memory()
+        h_mapq = torch.empty(n, dtype=torch.int32).pin_memory()
+        h_strings = torch.empty(str_cap, dtype=torch.uint8).pin_memory()
+        h_used = torch.zeros(((n + SB - 1) // SB,), dtype=torch.int32).pin_memory()
+        lanes = []
+        for _ in range(2):
+            lane_sw = CudaSW(qml, corridor, device=local_rank)
+            s_ = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(s_):
+                check(lib.ngm_b200_dev_set_reference(lane_sw.ctx, ref.packed.data_ptr(), ref.concat_len, s_.cuda_stream))
+            lanes.append(dict(sw=lane_sw, stream=s_, reads=torch.empty((SB, qml), dtype=torch.uint8, device=dev),
+                              pairs=torch.empty((max_pairs, 16), dtype=torch.uint8, device=dev), cb=torch.empty(SB + 1, dtype=torch.int32, device=dev),
+                              scores=torch.empty(max_pairs, dtype=torch.float32, device=dev), best=torch.empty(SB, dtype=torch.int32, device=dev),
+                              mapq=torch.empty(SB, dtype=torch.int32, device=dev), wpairs=torch.empty((SB, 16), dtype=torch.uint8, device=dev),
+                              recs=torch.empty((SB, 32), dtype=torch.uint8, device=dev), strings=torch.empty(48 * SB, dtype=torch.uint8, device=dev),
+                              cursor=torch.zeros(1, dtype=torch.int32, device=dev), pending=None))
+        torch.cuda.synchronize()
+        h2d = d2h = 0
+
+        def finish(lane):
+            """copy the strings of the lane's previous sub-batch once its cursor is known"""
+            nonlocal d2h
+            p = lane["pending"]
+            if p is None:
+                return
+            lane["stream"].synchronize()
+            used = int(h_used[p["k"]].item())
+            with torch.cuda.stream(lane["stream"]):
+                h_strings[p["soff"]: p["soff"] + used].copy_(lane["strings"][:used], non_blocking=True)
+            d2h += used
+            lane["pending"] = None
+
+        def e2e_step():
+            nonlocal h2d, d2h
+            for k, s in enumerate(range(0, n, SB)):
+                lane = lanes[k % 2]
+                finish(lane)
+                m = min(SB, n - s)
+                p0, p1 = int(cb_h[s]), int(cb_h[s + m])
+                mp = p1 - p0
+                c_, q_ = lane["sw"].ctx, lane["stream"].cuda_stream
+                with torch.cuda.stream(lane["stream"]):
+                    lane["reads"][:m].copy_(h_reads[s: s + m], non_blocking=True)
+                    lane["pairs"][:mp].copy_(h_pairs[p0:p1], non_blocking=True)
+                    lane["cb"][: m + 1].copy_(h_cbs[k], non_blocking=True)
+                    check(lib.ngm_b200_dev_set_reads(c_, lane["reads"].data_ptr(), m, qml, q_))
+                    check(lib.ngm_b200_dev_score_pairs(c_, MODE_LOCAL, mp, lane["pairs"].data_ptr(), lane["scores"].data_ptr(), q_))
+                    check(lib.ngm_b200_dev_select_top1(c_, m, lane["cb"].data_ptr(), lane["scores"].data_ptr(), lane["best"].data_ptr(), lane["mapq"].data_ptr(), q_))
+                    check(lib.ngm_b200_dev_gather_winners(c_, m, lane["pairs"].data_ptr(), lane["best"].data_ptr(), lane["wpairs"].data_ptr(), q_))
+                    lane["cursor"].zero_()
+                    check(lib.ngm_b200_dev_align_pairs(c_, MODE_LOCAL, m, lane["wpairs"].data_ptr(), lane["recs"].data_ptr(), lane["strings"].data_ptr(),
+                                                       48 * SB, lane["cursor"].data_ptr(), q_))
+                    h_recs[s: s + m].copy_(lane["recs"][:m], non_blocking=True)
+                    h_mapq[s: s + m].copy_(lane["mapq"][:m], non_blocking=True)
+                    h_used[k: k + 1].copy_(lane["cursor"], non_blocking=True)
+                h2d += m * qml + mp * 16 + (m + 1) * 4
+                d2h += m * 32 + m * 4 + 4
+                lane["pending"] = dict(k=k, soff=48 * s)
+            for lane in lanes:
+                finish(lane)
+            for lane in lanes:
+                lane["stream"].synchronize()
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        h2d = d2h = 0
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        e2e_launch = sum(l["sw"].launch_count() for l in lanes)
+        e2e_ms = torch.tensor([e2e_s * 1e3], dtype=torch.float64, device=dev)
+        if distributed:
+            dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n * args.steps / (float(e2e_ms.item()) / 1e3), "unit": "reads/s", "h2d_bytes_per_step": h2d // args.steps,
+               "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": float(e2e_ms.item()) / args.steps, "sub_batch_reads": SB, "streams": 2,
+               "timer": "host wall clock around K steps (barrier + synchronize both sides), max over ranks"}
+        # the e2e path must reproduce the resident results bit for bit
+        h_view = h_recs.numpy().view(ALIGN_REC).reshape(-1)
+        fields = ["position_offset", "qstart", "qend", "nm", "identity", "score", "cigar_len", "md_len"]
+        e2e["matches_resident"] = bool(all(np.array_equal(h_view[f], recs_all[f]) for f in fields))
+        for lane in lanes:
+            lane["sw"].close()
+
+    # ---- reductions over ranks ----------------------------------------------
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    counters = torch.tensor([n, mapped, npairs], dtype=torch.int64, device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM)      # mapping counters (NGM.cpp:172-201)
+    ms_max = float(t.item())
+    total_reads = int(counters[0].item())
+
+    if rank != 0:
+        if distributed:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- parity spot check + CPU baseline (rank 0, outside the timed regions) ----
+    parity = None
+    cpu_baseline = None
+    try:
+        from oracle import port
+        n_s = args.cpu_sample or min(n, max(20_000, 3000 * host_threads))
+        packed_host = ref.packed.cpu().numpy()
+        reads_h = batch.reads[:n_s].cpu().numpy()
+        cb = batch.cand_begin[: n_s + 1].cpu().numpy()
+        pdt = np.dtype([("window_start", "<u8"), ("read_index", "<u4"), ("flags", "<u4")])
+        pairs_h = batch.pairs[: int(cb[-1])].cpu().numpy().view(pdt).reshape(-1)
+        refs_s, qrys_s, n_align = cpu_sample_windows(packed_host, ref.concat_len, reads_h, pairs_h, cb, n_s, qml, corridor)
+        # order used by cpu_sample_windows: first candidates of every read, then the rest
+        first = [int(cb[r]) for r in range(n_s)]
+        rest = [j for r in range(n_s) for j in range(int(cb[r]) + 1, int(cb[r + 1]))]
+        order = np.array(first + rest)
+        want = port.batch_score(refs_s, qrys_s, qml, corridor, MODE_LOCAL)
+        got = d_scores[: int(cb[-1])].cpu().numpy()[order]
+        parity = {"score_pairs_checked": int(len(order)), "score_mismatches": int(np.count_nonzero(want != got))}
+        if not args.no_cpu_baseline:
+            res = run_cpu_reference(refs_s, qrys_s, n_align, n_s, qml, corridor, host_threads, 1, 3)
+            cpu_baseline = {"value": res["value"], "unit": "reads/s", "cores": res["cores"], "kind": res["kind"],
+                            "sample": f"{n_s} reads / {len(refs_s)} pairs of the same workload, 3 timed passes after 1 warm pass",
+                            "score_pairs_per_s": res.get("score_pairs_per_s"), "align_pairs_per_s": res.get("align_pairs_per_s")}
+    except Exception as e:  # noqa: BLE001
+        parity = {"error": str(e)}
+
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    sm_mhz = clk.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+    dominant = "score" if ms_score >= ms_align else "align"
+    dom_ms = max(ms_score, ms_align)
+    dom_units = npairs if dominant == "score" else n
+    alg_bytes = ALG_BYTES_SCORE * dom_units if dominant == "score" else (ALG_BYTES_SCORE + 8 + 2 * 4) * dom_units
+    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    # integer-ALU roofline: SMs x 128 lanes x clock / 5 instr per cell, x2 for s16x2 lanes
+    alu_peak_gcups = sm_count * 128 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 5 / 1e9
+    score_gcups = npairs * CELLS_PER_PAIR / (ms_score * 1e-3) / 1e9
+    align_gcups = n * CELLS_PER_PAIR / (ms_align * 1e-3) / 1e9
+    line = {
+        "metric": "reads/sec aligned (150bp SE vs 3Gbp ref)", "value": total_reads * args.steps / (ms_max * 1e-3), "unit": "reads/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int16x2 (score) / int32 (align)", "data": "synthetic", "config": cfg,
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+        "roofline": {"kernel": f"{dominant}_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": None, "peak_source": peak_src, "ms_per_launch_set": dom_ms, "units_per_launch_set": dom_units,
+                     "algorithmic_bytes_per_unit": alg_bytes / dom_units,
+                     "note": "integer DP: ~22 cells per algorithmic byte, so the HBM fraction is small by construction; the binding roofline is roofline_alu"},
+        "roofline_alu": {"bound": "int-alu issue", "score_gcups": score_gcups, "align_gcups": align_gcups, "peak_gcups_int32": alu_peak_gcups,
+                         "peak_gcups_s16x2": 2 * alu_peak_gcups, "score_frac_of_s16x2_peak": score_gcups / (2 * alu_peak_gcups),
+                         "align_frac_of_int32_peak": align_gcups / alu_peak_gcups, "sm_count": sm_count, "sm_mhz_under_load": sm_mhz,
+                         "definition": "cells = L x corridor = 4050 per pair; peak = SMs x 128 lanes x max clock / 5 instr per cell (SURVEY 8d)"},
+        "kernel_ms": {"set_reads": ms_pack, "score": ms_score, "align": ms_align, "score_share": ms_score / (ms_max / args.steps),
+                      "align_share": ms_align / (ms_max / args.steps)},
+        "cpu_baseline": cpu_baseline, "parity_sample": parity,
+        "counters": {"reads": total_reads, "mapped": int(counters[1].item()), "pairs_scored": int(counters[2].item()), "string_bytes": used_strings},
+        "setup_seconds": setup_s, "host_threads": host_threads,
+    }
+    print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

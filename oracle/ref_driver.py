@@ -127,14 +127,16 @@ def run(refs: np.ndarray, qrys: np.ndarray, qml: int, corridor: int, mode: int,
 
 
 def bench(refs: np.ndarray, qrys: np.ndarray, qml: int, corridor: int, mode: int, n_align: int,
-          threads: int, min_seconds: float, sc: Scoring = Scoring()) -> dict:
-    """Time BatchScore over all pairs + BatchAlign over the first n_align, `threads` CS-thread equivalents."""
+          threads: int, warm_passes: int, timed_passes: int, sc: Scoring = Scoring()) -> dict:
+    """Time BatchScore over all pairs + BatchAlign over the first n_align pairs with `threads` CS-thread
+    equivalents (one SWOclCigar instance on its own 1-core OpenCL sub-device each, like `ngm -t`).
+    Instance construction (OpenCL JIT) and the warm passes are outside the reported wall time."""
     if not available():
         raise RuntimeError("oracle/_ref not built")
     with tempfile.TemporaryDirectory(prefix="ngmref_") as td:
         inp = Path(td) / "in.bin"
         write_job(inp, refs, qrys, qml, corridor, mode, sc, n_align, None)
-        p = subprocess.run([str(HARNESS), "bench", str(inp), str(threads), str(min_seconds)], env=_env(),
+        p = subprocess.run([str(HARNESS), "bench", str(inp), str(threads), str(warm_passes), str(timed_passes)], env=_env(),
                            capture_output=True, text=True)
         if p.returncode != 0:
             raise RuntimeError(f"reference harness failed ({p.returncode}): {p.stderr[-2000:]}")

@@ -8,7 +8,7 @@
 // expects (_config / _log, cf. lib/mason/opencl/SWOcl_export.cpp:19,28).
 //
 //   ngm_ref_harness run   <in.bin> <out.bin>
-//   ngm_ref_harness bench <in.bin> <threads> <min_seconds>
+//   ngm_ref_harness bench <in.bin> <threads> <warm_passes> <timed_passes>
 //
 // in.bin  : int32 hdr[16] = {magic, qml, corridor, mode, n, match, mismatch,
 //           gap_read, gap_ref, bs_mapping, slam_seq, match_tt, match_tc,
@@ -119,11 +119,13 @@ double now() {
 
 pthread_mutex_t ctorLock = PTHREAD_MUTEX_INITIALIZER;
 
+pthread_barrier_t phaseBarrier;
+
 struct Worker {
 	Job const * job;
 	int tid, threads;
-	double minSeconds;
-	double scoreSeconds, alignSeconds;
+	int warmPasses, timedPasses;
+	double scoreSeconds, alignSeconds, wallSeconds;
 	long scored, aligned;
 	pthread_t th;
 };
@@ -152,8 +154,14 @@ void * benchThread(void * arg) {
 	}
 	w->scoreSeconds = w->alignSeconds = 0;
 	w->scored = w->aligned = 0;
-	double t0 = now();
-	do {
+	pthread_barrier_wait(&phaseBarrier);          // every instance is constructed (JIT done)
+	double t0 = 0;
+	for (int pass = 0; pass < w->warmPasses + w->timedPasses; ++pass) {
+		bool const timed = pass >= w->warmPasses;
+		if (pass == w->warmPasses) {
+			pthread_barrier_wait(&phaseBarrier);  // all threads start the timed passes together
+			t0 = now();
+		}
 		double a = now();
 		for (int s = lo; s < hi; s += sb) {
 			int m = (hi - s < sb) ? hi - s : sb;
@@ -162,7 +170,7 @@ void * benchThread(void * arg) {
 				qrys[i] = &j.qry[(size_t) (s + i) * qml];
 			}
 			sw->BatchScore(mode, m, refs.data(), qrys.data(), 0, scores.data(), j.hdr[15] ? (void *) &j.dir[s] : 0);
-			w->scored += m;
+			if (timed) w->scored += m;
 		}
 		double b = now();
 		for (int s = alo; s < ahi; s += ab) {
@@ -173,12 +181,15 @@ void * benchThread(void * arg) {
 				qals[i] = qrys[i];
 			}
 			sw->BatchAlign(mode | (1 << 8), m, refs.data(), qrys.data(), qals.data(), aligns.data(), j.hdr[15] ? (void *) &j.dir[s] : 0);
-			w->aligned += m;
+			if (timed) w->aligned += m;
 		}
 		double c = now();
-		w->scoreSeconds += b - a;
-		w->alignSeconds += c - b;
-	} while (now() - t0 < w->minSeconds);
+		if (timed) {
+			w->scoreSeconds += b - a;
+			w->alignSeconds += c - b;
+		}
+	}
+	w->wallSeconds = now() - t0;
 	pthread_mutex_lock(&ctorLock);
 	delete sw;
 	delete host;
@@ -246,7 +257,7 @@ ILog const * _log = 0;
 
 int main(int argc, char ** argv) {
 	if (argc < 4) {
-		fprintf(stderr, "usage: %s run <in.bin> <out.bin> | bench <in.bin> <threads> <min_seconds>\n", argv[0]);
+		fprintf(stderr, "usage: %s run <in.bin> <out.bin> | bench <in.bin> <threads> <warm_passes> <timed_passes>\n", argv[0]);
 		return 64;
 	}
 	static MapConfig cfg;
@@ -267,27 +278,30 @@ int main(int argc, char ** argv) {
 		int threads = atoi(argv[3]);
 		if (threads < 1) threads = 1;
 		configure(cfg, job, threads);
+		int warm = atoi(argv[4]), timed = argc >= 6 ? atoi(argv[5]) : 1;
+		if (timed < 1) timed = 1;
 		std::vector<Worker> ws(threads);
-		double t0 = now();
+		pthread_barrier_init(&phaseBarrier, 0, threads);
 		for (int t = 0; t < threads; ++t) {
 			ws[t].job = &job;
 			ws[t].tid = t;
 			ws[t].threads = threads;
-			ws[t].minSeconds = atof(argv[4]);
+			ws[t].warmPasses = warm;
+			ws[t].timedPasses = timed;
 			pthread_create(&ws[t].th, 0, benchThread, &ws[t]);
 		}
 		long scored = 0, aligned = 0;
-		double sSec = 0, aSec = 0;
+		double sSec = 0, aSec = 0, wall = 0;
 		for (int t = 0; t < threads; ++t) {
 			pthread_join(ws[t].th, 0);
 			scored += ws[t].scored;
 			aligned += ws[t].aligned;
 			if (ws[t].scoreSeconds > sSec) sSec = ws[t].scoreSeconds;
 			if (ws[t].alignSeconds > aSec) aSec = ws[t].alignSeconds;
+			if (ws[t].wallSeconds > wall) wall = ws[t].wallSeconds;
 		}
-		double wall = now() - t0;
-		printf("{\"threads\": %d, \"scored\": %ld, \"aligned\": %ld, \"score_seconds\": %.6f, \"align_seconds\": %.6f, \"wall_seconds\": %.6f}\n",
-				threads, scored, aligned, sSec, aSec, wall);
+		printf("{\"threads\": %d, \"passes\": %d, \"scored\": %ld, \"aligned\": %ld, \"score_seconds\": %.6f, \"align_seconds\": %.6f, \"wall_seconds\": %.6f}\n",
+				threads, timed, scored, aligned, sSec, aSec, wall);
 		return 0;
 	}
 	return 64;

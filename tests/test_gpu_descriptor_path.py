@@ -96,15 +96,21 @@ def test_descriptor_scores_and_alignments(qml, cor, lane_mode):
     sw.set_reads(reads)
     score_buf = ((qml + cor) | 1) + 1            # ScoreBuffer.h:112
     align_buf = (qml + cor) | 2                  # AlignmentBuffer.h:67 (operator precedence: | 1 + 1)
+    # For an odd offset DecodeRefSequence decodes one nibble more than asked for
+    # (SequenceProvider.cpp:417-423); when the window also runs past the end of the concatenated
+    # reference that nibble lies beyond the encoded array (uninitialised memory in the reference).
+    # The device defines every position >= concat_len as 'x'; such pairs are left out of the comparison.
+    starts = pairs["window_start"].astype(np.uint64)
+    undefined = ((starts & np.uint64(1)) == 1) & (starts < len(concat)) & (starts + np.uint64(score_buf - 2) >= len(concat))
     for mode in (0, 1):
         refs, qrys = host_windows(packed, len(concat), reads, pairs, qml, cor, score_buf, True)
         want = port.batch_score(refs, qrys, qml, cor, mode)
         got = sw.score_pairs(mode, pairs)
         # the oracle models the CPU device's quad-granular empty-read rule; no read is empty here
-        np.testing.assert_array_equal(util.bits(got), util.bits(want), err_msg=f"mode {mode}")
+        np.testing.assert_array_equal(util.bits(got[~undefined]), util.bits(want[~undefined]), err_msg=f"mode {mode}")
         # alignments: windows as AlignmentBuffer decodes them; pairs whose decode fails keep stale
         # buffers in the reference (AlignmentBuffer.cpp:101 ignores the return value) -> excluded
-        ok = np.array([int(p["window_start"]) < len(concat) for p in pairs])
+        ok = np.array([int(p["window_start"]) < len(concat) for p in pairs]) & ~undefined
         refs, qrys = host_windows(packed, len(concat), reads, pairs, qml, cor, align_buf, False)
         wa = port.batch_align(refs[ok], qrys[ok], qml, cor, mode)
         recs, heap = sw.align_pairs(mode, pairs[ok])
