@@ -189,18 +189,16 @@ def main():
 
     # ---- workload ---------------------------------------------------------
     t_setup = time.perf_counter()
+    from nextgenmap_b200 import sharding
     if distributed and args.impl != "reference":
         # rank 0 builds the reference, NCCL broadcasts the packed bytes over NVLink
         if rank == 0:
             ref = workload.make_reference(dev, args.contigs, args.contig_len, seed=20261017)
-            meta = torch.tensor([ref.concat_len], dtype=torch.int64, device=dev)
+            packed, concat_len = sharding.broadcast_reference(ref.packed, ref.concat_len, src=0)
         else:
-            meta = torch.zeros(1, dtype=torch.int64, device=dev)
-        dist.broadcast(meta, 0)
-        if rank != 0:
+            packed, concat_len = sharding.broadcast_reference(torch.empty(0, dtype=torch.uint8, device=dev), 0, src=0)
             starts = workload.SPACER + np.arange(args.contigs, dtype=np.int64) * (args.contig_len + workload.SPACER)
-            ref = workload.Reference(torch.empty(int(meta.item()) // 2, dtype=torch.uint8, device=dev), int(meta.item()), starts, args.contig_len)
-        dist.broadcast(ref.packed, 0)
+            ref = workload.Reference(packed, concat_len, starts, args.contig_len)
     else:
         ref = workload.make_reference(dev, args.contigs, args.contig_len, seed=20261017)
     n_reads = args.reads
@@ -410,11 +408,9 @@ def main():
         barrier()
         e2e_s = time.perf_counter() - t0
         e2e_launch = sum(l["sw"].launch_count() for l in lanes)
-        e2e_ms = torch.tensor([e2e_s * 1e3], dtype=torch.float64, device=dev)
-        if distributed:
-            dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * n * args.steps / (float(e2e_ms.item()) / 1e3), "unit": "reads/s", "h2d_bytes_per_step": h2d // args.steps,
-               "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": float(e2e_ms.item()) / args.steps, "sub_batch_reads": SB, "streams": 2,
+        e2e_ms = sharding.max_over_ranks(e2e_s * 1e3, dev)
+        e2e = {"value": world * n * args.steps / (e2e_ms / 1e3), "unit": "reads/s", "h2d_bytes_per_step": h2d // args.steps,
+               "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_ms / args.steps, "sub_batch_reads": SB, "streams": 2,
                "timer": "host wall clock around K steps (barrier + synchronize both sides), max over ranks"}
         # the e2e path must reproduce the resident results bit for bit
         h_view = h_recs.numpy().view(ALIGN_REC).reshape(-1)
@@ -424,13 +420,9 @@ def main():
             lane["sw"].close()
 
     # ---- reductions over ranks ----------------------------------------------
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    counters = torch.tensor([n, mapped, npairs], dtype=torch.int64, device=dev)
-    if distributed:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(counters, op=dist.ReduceOp.SUM)      # mapping counters (NGM.cpp:172-201)
-    ms_max = float(t.item())
-    total_reads = int(counters[0].item())
+    ms_max = sharding.max_over_ranks(ms, dev)
+    ctr = sharding.reduce_counters({"reads": n, "mapped": mapped, "pairs_scored": npairs}, dev)      # NGM.cpp:172-201
+    total_reads = ctr["reads"]
 
     if rank != 0:
         if distributed:
@@ -497,7 +489,7 @@ def main():
         "kernel_ms": {"set_reads": ms_pack, "score": ms_score, "align": ms_align, "score_share": ms_score / (ms_max / args.steps),
                       "align_share": ms_align / (ms_max / args.steps)},
         "cpu_baseline": cpu_baseline, "parity_sample": parity,
-        "counters": {"reads": total_reads, "mapped": int(counters[1].item()), "pairs_scored": int(counters[2].item()), "string_bytes": used_strings},
+        "counters": {"reads": total_reads, "mapped": ctr["mapped"], "pairs_scored": ctr["pairs_scored"], "string_bytes": used_strings},
         "setup_seconds": setup_s, "host_threads": host_threads,
     }
     print(json.dumps(line))
