@@ -1,0 +1,45 @@
+// k_align_s16.cu -- instantiations + launcher of the tagged s16x2 align path:
+// forward kernel (two alignments per thread) + backtrace/format kernel (one alignment per thread).
+#include "ngm_launch.h"
+#include "ngm_align_s16.cuh"
+
+namespace ngm {
+
+cudaError_t launch_align_s16(int capacity, int mode, const AlignArgs &a, cudaStream_t st) {
+	if (a.n <= 0) return cudaSuccess;
+	const int threads = (a.n + 1) / 2;
+	const dim3 block(128), grid((threads + 127) / 128);
+	bool launched = false;
+#define X(W, LO) \
+	if (capacity == W) { \
+		if constexpr (W <= kAlignS16MaxLocal) { \
+			if (mode == 0) { \
+				align_s16_fwd_kernel<W, LO, 0><<<grid, block, 0, st>>>(a.P, a.pairs, a.n, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, \
+						a.ptr_scratch, a.stride, a.best_scratch); \
+				launched = true; \
+			} \
+		} \
+		if constexpr (W <= kAlignS16MaxEndFree) { \
+			if (mode == 1) { \
+				align_s16_fwd_kernel<W, LO, 1><<<grid, block, 0, st>>>(a.P, a.pairs, a.n, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, \
+						a.ptr_scratch, a.stride, a.best_scratch); \
+				launched = true; \
+			} \
+		} \
+	}
+	NGM_BAND_LIST(X)
+#undef X
+	if (!launched) return cudaErrorInvalidValue;
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return e;
+	const dim3 b2(256), g2((a.n + 255) / 256);
+	if (mode == 0)
+		backtrace_format_kernel<0><<<g2, b2, 0, st>>>(a.P, a.pairs, a.n, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, a.ptr_scratch, capacity,
+				a.best_scratch, a.ops_scratch, a.stride, a.ops_cap, a.recs, a.strings, a.str_cap, a.cursor);
+	else
+		backtrace_format_kernel<1><<<g2, b2, 0, st>>>(a.P, a.pairs, a.n, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, a.ptr_scratch, capacity,
+				a.best_scratch, a.ops_scratch, a.stride, a.ops_cap, a.recs, a.strings, a.str_cap, a.cursor);
+	return cudaGetLastError();
+}
+
+}  // namespace ngm

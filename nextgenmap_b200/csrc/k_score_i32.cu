@@ -12,7 +12,7 @@ int band_capacity(int corridor) {
 	return 0;
 }
 
-int ptr_words_for(int capacity) { return (capacity + 15) / 16; }
+int ptr_words_for(int capacity) { return (capacity + 7) / 8; }
 
 cudaError_t launch_score_i32(int capacity, int mode, const ScoreArgs &a, cudaStream_t st) {
 	if (a.n <= 0) return cudaSuccess;

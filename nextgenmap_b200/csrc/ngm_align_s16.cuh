@@ -1,0 +1,408 @@
+// ngm_align_s16.cuh -- forward pass with pointers + backtrace + CIGAR/MD for TWO alignments per
+// thread on s16x2 lanes (pair A = low half, pair B = high half).
+//
+// Direction tags.  All scores are kept scaled by 4; the three candidates of a cell carry their
+// direction in the two low bits:
+//     diag : 4*(H_diag + S)        + 2      (the LUT bytes already hold 4*S + 2)
+//     up   : 4*(H_up   + gap_read) + 1
+//     left : 4*(H_left + gap_ref)  + 0
+// One packed max therefore yields score AND pointer, with the reference's tie order
+// diag > I > D (oclSwScore.cl:80-83) for free, because true scores differ by >= 1, i.e. >= 4 scaled:
+//     d = VIADD.16x2(line[j], s)   u = VIADDMNMX.S16x2(line[j+1], 4*gr+1, d)
+//     h = VIADDMNMX.S16x2[.RELU](left, 4*gf, u)   clean = h & 0xFFFCFFFC   tag = h - clean
+// and the 2-bit tags of eight cells are accumulated on the FMA pipe (pw = pw*4 + tag): one 32-bit
+// pointer word = eight cells of A (low 16 bits) and of B (high 16 bits).
+//
+// Best cell (local mode, oclSwScore.cl:88-91: first strict maximum in row-major order): per row a
+// VIMNMX3 tree gives the row maximum; when a half's running maximum strictly improves, that half of
+// the band is copied into a snapshot (one PRMT per register, selector chosen per row).  After the
+// last row the snapshot holds, per half, the row in which the final maximum first appeared; its
+// first slot equal to the maximum is the best cell.
+//
+// Exactness needs 4*score to fit int16 and 4*S+2 to fit int8; build_params() decides
+// (DevParams::align_s16), otherwise align_i32_kernel is used.  End-free mode uses the sentinel
+// -7900 (scaled -31600) instead of -16000: under the same host-side range check the sentinel can
+// never win a maximum, so its exact value is immaterial.
+#pragma once
+
+#include "ngm_common.cuh"
+#include "ngm_dp_i32.cuh"
+#include "ngm_dp_s16.cuh"
+#include "ngm_format.cuh"
+#include "../../include/ngm_b200.h"
+
+namespace ngm {
+
+constexpr int kEndFreeMinS16 = -7900;
+
+template <int W>
+struct TagGeom {
+	static constexpr int kWords = (W + 7) / 8;     // pointer words per row per thread (8 cells x 2 pairs each)
+};
+
+struct HalfBest {
+	int best_read, best_ref, best_score, read_count;
+};
+
+// ---------------------------------------------------------------------------
+// backtrace + CIGAR/MD: a separate, register-light kernel (one alignment per thread, high
+// occupancy).  The walk is a chain of dependent loads (pointer word -> next cell); the first
+// version ran it inside the forward kernel at 3 warps/SMSP and spent 2/3 of the kernel's time
+// stalled on those loads (profiles/r1_v2_*).  Here the words of the next four rows are
+// prefetched into a register ring (the walk moves up one row per step except on deletions), and
+// match cells carry their own tag (3 = diag & EQ, 2 = diag & X), so the common step needs no
+// sequence lookup at all.
+// ---------------------------------------------------------------------------
+struct BandRt {
+	int words;       // pointer words per row per thread slot = ceil(W / 8)
+	int cap;         // band capacity W
+};
+
+__device__ __forceinline__ uint32_t tagged_code(uint32_t w, int col, int cap, int half) {
+	const int g = col >> 3;
+	const int cnt = min(8, cap - 8 * g);
+	return (w >> (2 * (cnt - 1 - (col & 7)) + 16 * half)) & 3u;
+}
+
+template <int MODE>
+__device__ __forceinline__ TraceOut backtrace_tagged(const DevParams &P, const uint2 *s_lut, const PairCtx &c, const uint32_t *__restrict__ pbase,
+		size_t row_stride, BandRt geo, int half, uint16_t *__restrict__ ops, int ops_stride, int ops_cap, const int4 b) {
+	TraceOut o;
+	o.qstart = 0;
+	o.qend = 0;
+	o.sp = 0;
+	const int best_read = b.x, best_ref = b.y, best_score = b.z, read_count = b.w;
+	if (best_read <= 0) {                                         // oclSwCigar.cl:78
+		o.ok = 0;
+		o.pos = best_read;
+		return o;
+	}
+	o.ok = 1;
+	const int corridor = P.corridor;
+	int row = best_read, col = best_ref, abs_ref = best_ref + best_read;
+	int h = best_score;
+	const int qend = MODE == 0 ? read_count - best_read - 1 : 0;
+	int elem = OP_S, len = qend, sp = 0;
+	// register ring: words of rows row, row-1, row-2, row-3 at column group g
+	int g = col >> 3;
+	const uint32_t *p0 = pbase + (size_t) (row + c.sub) * row_stride + g;
+	uint32_t w0 = p0[0];
+	uint32_t w1 = row >= 1 ? *(p0 - row_stride) : 0u;
+	uint32_t w2 = row >= 2 ? *(p0 - 2 * row_stride) : 0u;
+	uint32_t w3 = row >= 3 ? *(p0 - 3 * row_stride) : 0u;
+	while (true) {
+		if (row < 0) break;
+		const bool border = col < 0 || col >= corridor;
+		int op;
+		bool up_row = false;
+		if (border) {
+			if (MODE == 0) break;
+			op = OP_X;
+			row -= 1;
+			abs_ref -= 1;
+			up_row = true;
+		} else {
+			if (MODE == 0 && h <= 0) break;
+			const uint32_t p = tagged_code(w0, col, geo.cap, half);
+			if (p >= 2u) {
+				if (p == 3u && !P.alt) {
+					op = OP_EQ;
+					h -= P.match;
+				} else {
+					const int rc = code_at(c.rp, row) & 7;
+					const int fc = code_at(c.wp, (int64_t) c.sub + row + col) & 7;
+					op = p == 3u ? OP_EQ : OP_X;
+					h -= lut_score(s_lut, c.dir, rc, fc);
+				}
+				row -= 1;
+				abs_ref -= 1;
+				up_row = true;
+			} else if (p == 1u) {
+				op = OP_I;
+				h -= P.gap_read;
+				row -= 1;
+				col += 1;
+				up_row = true;
+			} else {
+				op = OP_D;
+				h -= P.gap_ref;
+				col -= 1;
+				abs_ref -= 1;
+			}
+		}
+		if (op == elem) {
+			len += 1;
+		} else {
+			if (sp < ops_cap) ops[(size_t) sp * ops_stride] = (uint16_t) (len << 4 | elem);
+			sp += 1;
+			elem = op;
+			len = 1;
+		}
+		// advance the ring
+		const int ng = (col < 0 ? 0 : col) >> 3;
+		if (ng != g && row >= 0 && col >= 0 && col < corridor) {
+			g = ng;                                               // column group changed (indel): refill
+			p0 = pbase + (size_t) (row + c.sub) * row_stride + g;
+			w0 = p0[0];
+			w1 = row >= 1 ? *(p0 - row_stride) : 0u;
+			w2 = row >= 2 ? *(p0 - 2 * row_stride) : 0u;
+			w3 = row >= 3 ? *(p0 - 3 * row_stride) : 0u;
+		} else if (up_row) {
+			p0 -= row_stride;
+			w0 = w1;
+			w1 = w2;
+			w2 = w3;
+			w3 = row >= 3 ? *(p0 - 3 * row_stride) : 0u;
+		}
+	}
+	if (sp < ops_cap) ops[(size_t) sp * ops_stride] = (uint16_t) (len << 4 | elem);
+	sp += 1;
+	o.sp = sp;
+	o.pos = abs_ref + 1;
+	o.qstart = row + 1;
+	o.qend = qend;
+	return o;
+}
+
+__device__ __forceinline__ void fill_record(ngm_b200_align_rec &r, const TraceOut &t, const FormatOut &f, uint32_t off) {
+	r.position_offset = t.pos;
+	r.qstart = t.qstart;
+	r.qend = t.qend > 0 ? t.qend : 0;
+	r.str_off = off;
+	if (t.ok) {
+		r.nm = f.mismatch;
+		r.identity = (float) f.match * 1.0f / (float) f.total;       // SWOclCigar.cpp:609
+		r.score = (float) f.read_index;                              // SWOclCigar.cpp:613
+		r.cigar_len = (uint16_t) f.cigar_len;
+		r.md_len = (uint16_t) f.md_len;
+	} else {
+		r.nm = 0;                                                    // failure convention, DESIGN.md section 5
+		r.identity = 0.0f;
+		r.score = -1.0f;
+		r.cigar_len = 0;
+		r.md_len = 0;
+	}
+}
+
+__device__ __forceinline__ void store_record(ngm_b200_align_rec *recs, int idx, const ngm_b200_align_rec &r) {
+	reinterpret_cast<uint4 *>(recs)[2 * (size_t) idx] = *reinterpret_cast<const uint4 *>(&r);
+	reinterpret_cast<uint4 *>(recs)[2 * (size_t) idx + 1] = *(reinterpret_cast<const uint4 *>(&r) + 1);
+}
+
+template <int W, int LO, int MODE>
+__global__ void __launch_bounds__(128) align_s16_fwd_kernel(const __grid_constant__ DevParams P, const PairDesc *__restrict__ pairs, int n,
+		const uint32_t *__restrict__ reads_fwd, const uint32_t *__restrict__ reads_rev, const uint16_t *__restrict__ rlen,
+		const uint32_t *__restrict__ ref4, uint32_t *__restrict__ ptr_scratch, int stride, int4 *__restrict__ best_out) {
+	using G = BandGeom<W>;
+	using T = TagGeom<W>;
+	__shared__ uint2 s_lut4[16];
+	if (threadIdx.x < 16) s_lut4[threadIdx.x] = P.lut4[threadIdx.x];
+	__syncthreads();
+	const int t2 = blockIdx.x * blockDim.x + threadIdx.x;        // thread slot: pairs 2*t2, 2*t2 + 1
+	const int ia = 2 * t2;
+	if (ia >= n) return;
+	const bool va = true, vb = ia + 1 < n;
+	const int ib = vb ? ia + 1 : (va ? ia : 0);
+	const int ja = va ? ia : 0;
+	constexpr int SENT = MODE == 0 ? 0 : 4 * kEndFreeMinS16;
+	const uint32_t SENT2 = pack2(SENT, SENT);
+	PairCtx ca, cb;
+	uint32_t fa, fb;
+	bool act_a = load_pair(P, pairs, ja, reads_fwd, reads_rev, rlen, ref4, ca, fa) && va;
+	bool act_b = load_pair(P, pairs, ib, reads_fwd, reads_rev, rlen, ref4, cb, fb) && vb;
+	const int corridor = P.corridor;
+	const uint32_t gr2 = pack2(4 * P.gap_read + 1, 4 * P.gap_read + 1), gf2 = pack2(4 * P.gap_ref, 4 * P.gap_ref);
+	const int tstride = stride >> 1;                             // thread slots per launch
+	const size_t row_stride = (size_t) tstride * T::kWords;
+	uint32_t *pbase = ptr_scratch + (size_t) t2 * T::kWords;
+	HalfBest ba, bb;
+	{
+		uint32_t line[W + 1], snap[W];
+#pragma unroll
+		for (int j = 0; j <= W; ++j) line[j] = (j < corridor) ? 0u : SENT2;
+#pragma unroll
+		for (int j = 0; j < W; ++j) snap[j] = 0u;
+		uint32_t best = 0;
+		int brow_a = 0, brow_b = 0, rc_a = 0, rc_b = 0;
+		uint32_t wa[G::kWin], wb[G::kWin];
+#pragma unroll
+		for (int k = 0; k < G::kWin; ++k) {
+			wa[k] = __ldg(ca.wp + k);
+			wb[k] = __ldg(cb.wp + k);
+		}
+		const int nqw = max(act_a ? (ca.sub + ca.len + 7) >> 3 : 0, act_b ? (cb.sub + cb.len + 7) >> 3 : 0);
+		const uint2 *luta = s_lut4 + ca.dir * 8, *lutb = s_lut4 + cb.dir * 8;
+		uint32_t prev_a = kNulWord, prev_b = kNulWord;
+		uint32_t *prow = pbase;
+		for (int qw = 0; qw < nqw; ++qw) {
+			const uint32_t cur_a = __ldg(ca.rp + qw), cur_b = __ldg(cb.rp + qw);
+			const uint32_t rda = __funnelshift_l(prev_a, cur_a, 4 * ca.sub);
+			const uint32_t rdb = __funnelshift_l(prev_b, cur_b, 4 * cb.sub);
+			prev_a = cur_a;
+			prev_b = cur_b;
+			const uint32_t next_a = __ldg(ca.wp + qw + G::kWin), next_b = __ldg(cb.wp + qw + G::kWin);
+#pragma unroll
+			for (int t = 0; t < 8; ++t) {
+				const int rca = (rda >> (4 * t)) & 7, rcb = (rdb >> (4 * t)) & 7;
+				const uint2 ta = luta[rca];
+				const uint2 tb = lutb[rcb];
+				uint32_t ala[G::kAligned], alb[G::kAligned];
+#pragma unroll
+				for (int k = 0; k < G::kAligned; ++k) {
+					ala[k] = t == 0 ? wa[k] : __funnelshift_r(wa[k], wa[k + 1], 4 * t);
+					alb[k] = t == 0 ? wb[k] : __funnelshift_r(wb[k], wb[k + 1], 4 * t);
+				}
+				uint32_t left = SENT2;
+				uint32_t pw[T::kWords];
+#pragma unroll
+				for (int k = 0; k < T::kWords; ++k) pw[k] = 0;
+#pragma unroll
+				for (int m = 0; m < G::kGroups; ++m) {
+					const uint32_t sa = prmt(ta.x, ta.y, (m & 1) ? (ala[m >> 1] >> 16) : ala[m >> 1]);
+					const uint32_t sb = prmt(tb.x, tb.y, (m & 1) ? (alb[m >> 1] >> 16) : alb[m >> 1]);
+#pragma unroll
+					for (int i = 0; i < 4; ++i) {
+						const int j = 4 * m + i;
+						const uint32_t s2 = i == 0 ? sbyte2<0>(sa, sb) : i == 1 ? sbyte2<1>(sa, sb) : i == 2 ? sbyte2<2>(sa, sb) : sbyte2<3>(sa, sb);
+						const uint32_t d = __vadd2(line[j], s2);
+						const uint32_t u = __viaddmax_s16x2(line[j + 1], gr2, d);
+						uint32_t h = MODE == 0 ? __viaddmax_s16x2_relu(left, gf2, u) : __viaddmax_s16x2(left, gf2, u);
+						if (j >= LO) h = (j < corridor) ? h : SENT2;
+						const uint32_t clean = h & 0xFFFCFFFCu;
+						pw[j >> 3] = pw[j >> 3] * 4u + (h - clean);
+						left = clean;
+						line[j] = clean;
+					}
+				}
+				if (T::kWords == 4) {
+					*reinterpret_cast<uint4 *>(prow) = make_uint4(pw[0], pw[1], pw[2 % T::kWords], pw[3 % T::kWords]);
+				} else {
+#pragma unroll
+					for (int k = 0; k < T::kWords; ++k) prow[k] = pw[k];
+				}
+				prow += row_stride;
+				if (MODE == 0) {
+					uint32_t mx = line[0];
+#pragma unroll
+					for (int j = 1; j + 1 < W; j += 2) mx = __vimax3_s16x2(mx, line[j], line[j + 1]);
+					if ((W & 1) == 0) mx = __vmaxs2(mx, line[W - 1]);
+					const uint32_t nb = __vmaxs2(best, mx);
+					const uint32_t imp = nb ^ best;
+					best = nb;
+					const bool imp_a = (imp & 0xFFFFu) != 0, imp_b = (imp >> 16) != 0;
+					const uint32_t sel = (imp_a ? 0x0054u : 0x0010u) | (imp_b ? 0x7600u : 0x3200u);
+#pragma unroll
+					for (int j = 0; j < W; ++j) snap[j] = prmt(snap[j], line[j], sel);
+					brow_a = imp_a ? rc_a : brow_a;
+					brow_b = imp_b ? rc_b : brow_b;
+				}
+				rc_a += (rca != kCodeNul);
+				rc_b += (rcb != kCodeNul);
+			}
+#pragma unroll
+			for (int k = 0; k + 1 < G::kWin; ++k) {
+				wa[k] = wa[k + 1];
+				wb[k] = wb[k + 1];
+			}
+			wa[G::kWin - 1] = next_a;
+			wb[G::kWin - 1] = next_b;
+		}
+		ba.read_count = rc_a;
+		bb.read_count = rc_b;
+		if (MODE == 0) {
+			const int ma = (int) (short) (best & 0xFFFFu), mb = (int) (short) (best >> 16);
+			int ra = 0, rb = 0;
+			bool fa_ = false, fb_ = false;
+#pragma unroll
+			for (int j = 0; j < W; ++j) {
+				const bool ha = !fa_ && j < corridor && (int) (short) (snap[j] & 0xFFFFu) == ma;
+				const bool hb = !fb_ && j < corridor && (int) (short) (snap[j] >> 16) == mb;
+				ra = ha ? j : ra;
+				rb = hb ? j : rb;
+				fa_ = fa_ || ha;
+				fb_ = fb_ || hb;
+			}
+			// nothing ever exceeded 0: the reference's first cell (0, 0) holds the maximum (oclSwScore.cl:48,88)
+			ba.best_read = ma > 0 ? brow_a : 0;
+			ba.best_ref = ma > 0 ? ra : 0;
+			ba.best_score = ma >> 2;
+			bb.best_read = mb > 0 ? brow_b : 0;
+			bb.best_ref = mb > 0 ? rb : 0;
+			bb.best_score = mb >> 2;
+		} else {
+			int cma = 4 * kEndFreeMinS16, cmb = 4 * kEndFreeMinS16, ra = 0, rb = 0;
+#pragma unroll
+			for (int j = 0; j < W; ++j) {                 // first strict maximum of the final row (oclEndFreeScore.cl:135-140)
+				const int va_ = (int) (short) (line[j] & 0xFFFFu), vb_ = (int) (short) (line[j] >> 16);
+				const bool ga = j < corridor && va_ > cma, gb = j < corridor && vb_ > cmb;
+				cma = ga ? va_ : cma;
+				ra = ga ? j : ra;
+				cmb = gb ? vb_ : cmb;
+				rb = gb ? j : rb;
+			}
+			ba.best_read = rc_a - 1;
+			ba.best_ref = ra;
+			ba.best_score = cma >> 2;
+			bb.best_read = rc_b - 1;
+			bb.best_ref = rb;
+			bb.best_score = cmb >> 2;
+		}
+	}
+	// quad-skipped pairs: what the reference's forward kernel leaves behind (oclSwScore.cl:16-18,104-106)
+	if (!act_a) { ba.best_read = MODE == 0 ? 0 : -1; ba.best_ref = 0; ba.best_score = 0; ba.read_count = 0; }
+	if (!act_b) { bb.best_read = MODE == 0 ? 0 : -1; bb.best_ref = 0; bb.best_score = 0; bb.read_count = 0; }
+	best_out[ia] = make_int4(ba.best_read, ba.best_ref, ba.best_score, ba.read_count);
+	if (vb) best_out[ia + 1] = make_int4(bb.best_read, bb.best_ref, bb.best_score, bb.read_count);
+}
+
+// One alignment per thread: pointer walk (oclSW_Backtracking, oclSwCigar.cl:60-124), RLE op stack,
+// CIGAR / MD / NM / identity (computeCigarMD, SWOclCigar.cpp:430-615), compact string heap.
+template <int MODE>
+__global__ void __launch_bounds__(256) backtrace_format_kernel(const __grid_constant__ DevParams P, const PairDesc *__restrict__ pairs, int n,
+		const uint32_t *__restrict__ reads_fwd, const uint32_t *__restrict__ reads_rev, const uint16_t *__restrict__ rlen,
+		const uint32_t *__restrict__ ref4, const uint32_t *__restrict__ ptr_scratch, int capacity, const int4 *__restrict__ best_in,
+		uint16_t *__restrict__ ops_scratch, int stride, int ops_cap, ngm_b200_align_rec *__restrict__ recs, char *__restrict__ strings,
+		uint32_t str_cap, uint32_t *__restrict__ cursor) {
+	__shared__ uint2 s_lut[16];
+	if (threadIdx.x < 16) s_lut[threadIdx.x] = P.lut[threadIdx.x];
+	__syncthreads();
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool valid = idx < n;
+	const int id = valid ? idx : 0;
+	PairCtx c;
+	uint32_t flags;
+	load_pair(P, pairs, id, reads_fwd, reads_rev, rlen, ref4, c, flags);
+	BandRt geo;
+	geo.cap = capacity;
+	geo.words = (capacity + 7) / 8;
+	const size_t row_stride = (size_t) (stride >> 1) * geo.words;
+	const uint32_t *pbase = ptr_scratch + (size_t) (id >> 1) * geo.words;
+	uint16_t *ops = ops_scratch + id;
+	TraceOut t;
+	t.ok = 0;
+	t.pos = 0;
+	t.qstart = t.qend = t.sp = 0;
+	if (valid) t = backtrace_tagged<MODE>(P, s_lut, c, pbase, row_stride, geo, id & 1, ops, stride, ops_cap, best_in[id]);
+	FormatOut f;
+	f.cigar_len = f.md_len = f.match = f.mismatch = f.total = f.read_index = 0;
+	if (t.ok) f = format_cigar_md<false>(P, c, ops, stride, t, nullptr, nullptr);
+	const uint32_t need = t.ok ? (uint32_t) (f.cigar_len + f.md_len) : 0u;
+	const int lane = threadIdx.x & 31;
+	uint32_t incl = need;
+#pragma unroll
+	for (int dlt = 1; dlt < 32; dlt <<= 1) {
+		const uint32_t v = __shfl_up_sync(0xffffffffu, incl, dlt);
+		if (lane >= dlt) incl += v;
+	}
+	uint32_t base = 0;
+	if (lane == 31 && incl) base = atomicAdd(cursor, incl);      // one atomic per warp
+	base = __shfl_sync(0xffffffffu, base, 31);
+	const uint32_t off = base + incl - need;
+	if (!valid) return;
+	if (t.ok && (uint64_t) off + need <= (uint64_t) str_cap) format_cigar_md<true>(P, c, ops, stride, t, strings + off, strings + off + f.cigar_len);
+	ngm_b200_align_rec r;
+	fill_record(r, t, f, off);
+	store_record(recs, idx, r);
+}
+
+}  // namespace ngm

@@ -89,6 +89,7 @@ struct ngm_b200_ctx {
 	int device = 0;
 	int capacity = 0;          // band capacity W
 	int use_s16 = 0;           // s16x2 lanes allowed for the score kernels
+	int align_s16[2] = {0, 0}; // tagged s16x2 align kernel usable in local / end-free mode
 	int score_batch = 0, align_batch = 0;
 	int strict_chunk = 0;      // pairs per strict-path launch
 	int align_chunk = 0;       // alignments per launch (bounded by scratch memory)
@@ -100,7 +101,7 @@ struct ngm_b200_ctx {
 	HostBuf h_reads, h_refs, h_flags, h_scores, h_recs, h_strings, h_cursor, h_noncanon;
 	DevBuf d_areads, d_arefs, d_flags, d_reads4, d_rlen32, d_rlen, d_wins4, d_pairs, d_scores, d_recs, d_strings, d_cursor, d_noncanon;
 	// align scratch
-	DevBuf d_ptr, d_ops;
+	DevBuf d_ptr, d_ops, d_best;
 	// descriptor path
 	DevBuf d_ref4, d_rfwd, d_rrev, d_rrlen32, d_rrlen, d_rascii, d_upairs, d_rpairs;
 	uint64_t concat_len = 0, n_region_nib = 0;
@@ -111,7 +112,7 @@ struct ngm_b200_ctx {
 namespace {
 
 // Build the row LUTs from the reference's 7x7 score matrices (oclDefines.cl:85-128).
-int build_params(const ngm_b200_params &hp, DevParams &dp, int &use_s16) {
+int build_params(const ngm_b200_params &hp, DevParams &dp, int &use_s16, int *align_s16) {
 	if (hp.qry_max_len < 1 || hp.qry_max_len > 4000) return fail(NGM_B200_EINVAL, "qry_max_len %d out of range", hp.qry_max_len);
 	if (hp.corridor < 1 || hp.corridor > kMaxCorridor) return fail(NGM_B200_EINVAL, "corridor %d not in [1, %d]", hp.corridor, kMaxCorridor);
 	const float fl[6] = { hp.match_bonus, hp.mismatch_penalty, hp.gap_read_penalty, hp.gap_ref_penalty, hp.match_bonus_tt, hp.match_bonus_tc };
@@ -183,6 +184,23 @@ int build_params(const ngm_b200_params &hp, DevParams &dp, int &use_s16) {
 	// [0, smax*qml]; end-free values are bounded below by the -16000 sentinel plus one gap step
 	// as long as a full-length mismatch path stays above the sentinel.
 	use_s16 = (span * std::max(smax, 1) <= 30000) && (span * std::max(-smin, 1) <= 15000) && gr >= -700 && gf >= -700;
+	// tagged align kernel: scores scaled by 4 must fit int16 and 4*S+2 must fit int8; in end-free mode a
+	// full-length worst-case path must stay above its (smaller) sentinel so that the sentinel never wins
+	const bool lut4_ok = 4 * smin + 2 >= -128 && 4 * smax + 3 <= 127 && gr >= -250 && gf >= -250;
+	align_s16[0] = lut4_ok && 4 * span * std::max(smax, 1) <= 32000;
+	align_s16[1] = lut4_ok && 4 * span * std::max(smax, 1) <= 30000 && span * std::max(-smin, 1) <= 7500;
+	for (int d = 0; d < 2; ++d)
+		for (int r = 0; r < 8; ++r) {
+			uint32_t lo = 0, hi = 0;
+			for (int c = 0; c < 4; ++c) {
+				// diag candidate: 4*S + 2, +1 more when the cell is an EQ op (oclSwScore.cl:64,69)
+				const int e0 = alt ? (r == c && r < 7) : (tab[d][r][c] == match);
+				const int e1 = alt ? (r == c + 4 && r < 7) : (tab[d][r][c + 4] == match);
+				lo |= (uint32_t) (uint8_t) (int8_t) (lut4_ok ? 4 * tab[d][r][c] + 2 + e0 : 0) << (8 * c);
+				hi |= (uint32_t) (uint8_t) (int8_t) (lut4_ok ? 4 * tab[d][r][c + 4] + 2 + e1 : 0) << (8 * c);
+			}
+			dp.lut4[d * 8 + r] = make_uint2(lo, hi);
+		}
 	return NGM_B200_OK;
 }
 
@@ -277,6 +295,7 @@ int ensure_align_scratch(ngm_b200_ctx *c, int stride) {
 	CU(c->d_ptr.ensure((size_t) c->dp.rows_cap * stride * pw * sizeof(uint32_t)));
 	const size_t ops_cap = 2 * (size_t) c->dp.qml + c->dp.corridor + 2;
 	CU(c->d_ops.ensure(ops_cap * stride * sizeof(uint16_t)));
+	CU(c->d_best.ensure((size_t) stride * sizeof(int4)));
 	return NGM_B200_OK;
 }
 
@@ -298,13 +317,21 @@ int run_align(ngm_b200_ctx *c, int mode, const PairDesc *pairs, int n, const uin
 		a.ref4 = ref4;
 		a.ptr_scratch = c->d_ptr.as<uint32_t>();
 		a.ops_scratch = c->d_ops.as<uint16_t>();
+		a.best_scratch = c->d_best.as<int4>();
 		a.stride = stride_pad;
 		a.ops_cap = 2 * c->dp.qml + c->dp.corridor + 2;
 		a.recs = recs + s;
 		a.strings = strings;
 		a.str_cap = str_cap;
 		a.cursor = cursor;
-		cudaError_t e = launch_align_i32(c->capacity, mode, a, st);
+		cudaError_t e;
+#ifdef NGM_HAVE_S16
+		if (c->align_s16[mode]) {
+			e = launch_align_s16(c->capacity, mode, a, st);
+			c->launches += 1;                                      // forward + backtrace/format
+		} else
+#endif
+		e = launch_align_i32(c->capacity, mode, a, st);
 		c->launches += 1;
 		if (e != cudaSuccess) return fail(NGM_B200_ECUDA, "align kernel launch: %s", cudaGetErrorString(e));
 	}
@@ -384,8 +411,8 @@ ngm_b200_ctx *ngm_b200_create(const ngm_b200_params *params) {
 		return nullptr;
 	}
 	DevParams dp;
-	int use_s16 = 0;
-	if (build_params(*params, dp, use_s16) != NGM_B200_OK) return nullptr;
+	int use_s16 = 0, align_s16[2] = {0, 0};
+	if (build_params(*params, dp, use_s16, align_s16) != NGM_B200_OK) return nullptr;
 	int ndev = 0;
 	cudaError_t e = cudaGetDeviceCount(&ndev);
 	if (e != cudaSuccess || ndev == 0) {
@@ -404,8 +431,12 @@ ngm_b200_ctx *ngm_b200_create(const ngm_b200_params *params) {
 	c->device = params->device;
 	c->capacity = band_capacity(dp.corridor);
 	c->use_s16 = params->lane_mode == 1 ? 0 : (params->lane_mode == 2 ? 1 : use_s16);
+	for (int m = 0; m < 2; ++m) c->align_s16[m] = params->lane_mode == 1 ? 0 : align_s16[m];
+	if (c->capacity > kAlignS16MaxLocal) c->align_s16[0] = 0;
+	if (c->capacity > kAlignS16MaxEndFree) c->align_s16[1] = 0;
 #ifndef NGM_HAVE_S16
 	c->use_s16 = 0;
+	c->align_s16[0] = c->align_s16[1] = 0;
 #endif
 	if (params->lane_mode == 2 && !use_s16) {
 		fail(NGM_B200_ERANGE, "s16x2 lanes forced but the scoring range does not fit int16");
@@ -438,7 +469,7 @@ void ngm_b200_destroy(ngm_b200_ctx *c) {
 	HostBuf *hb[] = { &c->h_reads, &c->h_refs, &c->h_flags, &c->h_scores, &c->h_recs, &c->h_strings, &c->h_cursor, &c->h_noncanon };
 	for (HostBuf *b : hb) b->release();
 	DevBuf *db[] = { &c->d_areads, &c->d_arefs, &c->d_flags, &c->d_reads4, &c->d_rlen32, &c->d_rlen, &c->d_wins4, &c->d_pairs, &c->d_scores,
-			&c->d_recs, &c->d_strings, &c->d_cursor, &c->d_ptr, &c->d_ops, &c->d_ref4, &c->d_rfwd, &c->d_rrev, &c->d_rrlen32, &c->d_rrlen,
+			&c->d_recs, &c->d_strings, &c->d_cursor, &c->d_ptr, &c->d_ops, &c->d_best, &c->d_ref4, &c->d_rfwd, &c->d_rrev, &c->d_rrlen32, &c->d_rrlen,
 			&c->d_rascii, &c->d_upairs, &c->d_rpairs, &c->d_noncanon };
 	for (DevBuf *b : db) b->release();
 	delete c;

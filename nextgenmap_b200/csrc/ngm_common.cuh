@@ -50,6 +50,7 @@ struct DevParams {
 	int read_words;        // words per packed read row
 	int rows_cap;          // pointer rows per alignment in the scratch matrix
 	uint2 lut[16];         // [dir * 8 + rc] -> signed score bytes for fc = 0..7
+	uint2 lut4[16];        // same rows holding 4*S + 2 (diag candidate of the tagged s16x2 align kernel)
 };
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {

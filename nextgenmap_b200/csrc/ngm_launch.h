@@ -18,9 +18,12 @@ namespace ngm {
 	X(56, 49) X(64, 57) X(72, 65) X(80, 73) X(96, 81) X(112, 97) X(128, 113) X(160, 129)
 
 constexpr int kMaxCorridor = 160;
+// the tagged s16x2 align kernel keeps band + snapshot in registers: beyond these capacities it would spill
+constexpr int kAlignS16MaxLocal = 48;
+constexpr int kAlignS16MaxEndFree = 96;
 
 int band_capacity(int corridor);          // 0 if unsupported
-int ptr_words_for(int capacity);          // 32-bit pointer words per DP row
+int ptr_words_for(int capacity);          // 32-bit pointer words per DP row and alignment to allocate (covers both kernels' layouts)
 
 struct ScoreArgs {
 	DevParams P;
@@ -41,6 +44,7 @@ struct AlignArgs {
 	const uint32_t *ref4;
 	uint32_t *ptr_scratch;
 	uint16_t *ops_scratch;
+	int4 *best_scratch;          // per alignment {best_read, best_ref, best_score, read_count} (s16 path)
 	int stride, ops_cap;
 	ngm_b200_align_rec *recs;
 	char *strings;
@@ -53,5 +57,6 @@ cudaError_t launch_score_i32(int capacity, int mode, const ScoreArgs &a, cudaStr
 cudaError_t launch_align_i32(int capacity, int mode, const AlignArgs &a, cudaStream_t st);
 // s16x2 lanes, two pairs per thread
 cudaError_t launch_score_s16(int capacity, int mode, const ScoreArgs &a, cudaStream_t st);
+cudaError_t launch_align_s16(int capacity, int mode, const AlignArgs &a, cudaStream_t st);
 
 }  // namespace ngm
