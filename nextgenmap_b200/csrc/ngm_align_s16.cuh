@@ -53,6 +53,15 @@ struct HalfBest {
 // match cells carry their own tag (3 = diag & EQ, 2 = diag & X), so the common step needs no
 // sequence lookup at all.
 // ---------------------------------------------------------------------------
+constexpr int kRing = 16;       // rows in flight per thread (power of two)
+
+__device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const uint32_t *gmem_src) {
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t) __cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 struct BandRt {
 	int words;       // pointer words per row per thread slot = ceil(W / 8)
 	int cap;         // band capacity W
@@ -66,7 +75,8 @@ __device__ __forceinline__ uint32_t tagged_code(uint32_t w, int col, int cap, in
 
 template <int MODE>
 __device__ __forceinline__ TraceOut backtrace_tagged(const DevParams &P, const uint2 *s_lut, const PairCtx &c, const uint32_t *__restrict__ pbase,
-		size_t row_stride, BandRt geo, int half, uint16_t *__restrict__ ops, int ops_stride, int ops_cap, const int4 b) {
+		size_t row_stride, BandRt geo, int half, uint16_t *__restrict__ ops, int ops_stride, int ops_cap, const int4 b, uint32_t *ring,
+		int ring_stride) {
 	TraceOut o;
 	o.qstart = 0;
 	o.qend = 0;
@@ -83,51 +93,77 @@ __device__ __forceinline__ TraceOut backtrace_tagged(const DevParams &P, const u
 	int h = best_score;
 	const int qend = MODE == 0 ? read_count - best_read - 1 : 0;
 	int elem = OP_S, len = qend, sp = 0;
-	// register ring: words of rows row, row-1, row-2, row-3 at column group g
+	// Shared-memory ring fed by cp.async (LDGSTS): slot (r & 15) of this thread's column holds the pointer
+	// word of row r at column group g; the copies for the next 15 rows are in flight while the current one
+	// is consumed, so the dependent-load latency of the walk (the scratch matrix of a launch is larger
+	// than L2) is overlapped instead of paid per step.  One loop iteration = one step for every lane; the
+	// common step (tag 3: diag & EQ) touches registers + one LDS, the rare ones (X, I, D, band border)
+	// take a short divergent branch.
+	const long long rs = (long long) row_stride;
 	int g = col >> 3;
-	const uint32_t *p0 = pbase + (size_t) (row + c.sub) * row_stride + g;
-	uint32_t w0 = p0[0];
-	uint32_t w1 = row >= 1 ? *(p0 - row_stride) : 0u;
-	uint32_t w2 = row >= 2 ? *(p0 - 2 * row_stride) : 0u;
-	uint32_t w3 = row >= 3 ? *(p0 - 3 * row_stride) : 0u;
-	while (true) {
-		if (row < 0) break;
-		const bool border = col < 0 || col >= corridor;
+	int sh = 2 * (min(8, geo.cap - 8 * g) - 1 - (col & 7)) + 16 * half;
+	const uint32_t *pg = pbase + (size_t) (row + c.sub) * row_stride + g;        // word of the current row
+	auto fill = [&](int r, const uint32_t *src) {                                 // async copy of row r's word (or an empty group)
+		if (r >= 0) cp_async4(ring + (r & (kRing - 1)) * ring_stride, src);
+		cp_async_commit();
+	};
+#pragma unroll
+	for (int k = 0; k < kRing; ++k) fill(row - k, pg - k * rs);
+	const uint32_t *pf = pg - (long long) kRing * rs;                             // next row to fetch: row - kRing
+	cp_async_wait<kRing - 1>();
+	uint32_t w0 = ring[(row & (kRing - 1)) * ring_stride];
+	const bool fast_eq = !P.alt;                                  // tag 3 == EQ with score `match`
+	bool border = col < 0 || col >= corridor;
+	while (row >= 0) {
 		int op;
-		bool up_row = false;
-		if (border) {
+		bool up_row = true;
+		const uint32_t p = (w0 >> sh) & 3u;
+		if (!border && (MODE != 0 || h > 0) && p == 3u && fast_eq) {
+			op = OP_EQ;
+			h -= P.match;
+			row -= 1;
+			abs_ref -= 1;
+		} else if (border) {
 			if (MODE == 0) break;
 			op = OP_X;
 			row -= 1;
 			abs_ref -= 1;
-			up_row = true;
 		} else {
 			if (MODE == 0 && h <= 0) break;
-			const uint32_t p = tagged_code(w0, col, geo.cap, half);
 			if (p >= 2u) {
-				if (p == 3u && !P.alt) {
-					op = OP_EQ;
-					h -= P.match;
-				} else {
-					const int rc = code_at(c.rp, row) & 7;
-					const int fc = code_at(c.wp, (int64_t) c.sub + row + col) & 7;
-					op = p == 3u ? OP_EQ : OP_X;
-					h -= lut_score(s_lut, c.dir, rc, fc);
-				}
+				const int rc = code_at(c.rp, row) & 7;
+				const int fc = code_at(c.wp, (int64_t) c.sub + row + col) & 7;
+				op = p == 3u ? OP_EQ : OP_X;
+				h -= lut_score(s_lut, c.dir, rc, fc);
 				row -= 1;
 				abs_ref -= 1;
-				up_row = true;
-			} else if (p == 1u) {
-				op = OP_I;
-				h -= P.gap_read;
-				row -= 1;
-				col += 1;
-				up_row = true;
 			} else {
-				op = OP_D;
-				h -= P.gap_ref;
-				col -= 1;
-				abs_ref -= 1;
+				if (p == 1u) {
+					op = OP_I;
+					h -= P.gap_read;
+					row -= 1;
+					col += 1;
+				} else {
+					op = OP_D;
+					h -= P.gap_ref;
+					col -= 1;
+					abs_ref -= 1;
+					up_row = false;
+				}
+				border = col < 0 || col >= corridor;
+				const int ng = (col < 0 ? 0 : col) >> 3;
+				sh = 2 * (min(8, geo.cap - 8 * ng) - 1 - (col & 7)) + 16 * half;
+				if (ng != g && !border && row >= 0) {             // column group changed: restart the ring there
+					g = ng;
+					cp_async_wait<0>();
+					pg = pbase + (size_t) (row + c.sub) * row_stride + g;
+#pragma unroll
+					for (int k = 0; k < kRing; ++k) fill(row - k, pg - k * rs);
+					pf = pg - (long long) kRing * rs;
+					cp_async_wait<kRing - 1>();
+					w0 = ring[(row & (kRing - 1)) * ring_stride];
+					up_row = false;                               // ring already positioned on `row`
+				}
 			}
 		}
 		if (op == elem) {
@@ -138,23 +174,14 @@ __device__ __forceinline__ TraceOut backtrace_tagged(const DevParams &P, const u
 			elem = op;
 			len = 1;
 		}
-		// advance the ring
-		const int ng = (col < 0 ? 0 : col) >> 3;
-		if (ng != g && row >= 0 && col >= 0 && col < corridor) {
-			g = ng;                                               // column group changed (indel): refill
-			p0 = pbase + (size_t) (row + c.sub) * row_stride + g;
-			w0 = p0[0];
-			w1 = row >= 1 ? *(p0 - row_stride) : 0u;
-			w2 = row >= 2 ? *(p0 - 2 * row_stride) : 0u;
-			w3 = row >= 3 ? *(p0 - 3 * row_stride) : 0u;
-		} else if (up_row) {
-			p0 -= row_stride;
-			w0 = w1;
-			w1 = w2;
-			w2 = w3;
-			w3 = row >= 3 ? *(p0 - 3 * row_stride) : 0u;
+		if (up_row && row >= 0) {
+			fill(row - (kRing - 1), pf);                          // reuses the slot of the row just left
+			pf -= rs;
+			cp_async_wait<kRing - 1>();
+			w0 = ring[(row & (kRing - 1)) * ring_stride];
 		}
 	}
+	cp_async_wait<0>();
 	if (sp < ops_cap) ops[(size_t) sp * ops_stride] = (uint16_t) (len << 4 | elem);
 	sp += 1;
 	o.sp = sp;
@@ -364,6 +391,7 @@ __global__ void __launch_bounds__(256) backtrace_format_kernel(const __grid_cons
 		uint16_t *__restrict__ ops_scratch, int stride, int ops_cap, ngm_b200_align_rec *__restrict__ recs, char *__restrict__ strings,
 		uint32_t str_cap, uint32_t *__restrict__ cursor) {
 	__shared__ uint2 s_lut[16];
+	__shared__ uint32_t s_ring[kRing][256];
 	if (threadIdx.x < 16) s_lut[threadIdx.x] = P.lut[threadIdx.x];
 	__syncthreads();
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -382,7 +410,7 @@ __global__ void __launch_bounds__(256) backtrace_format_kernel(const __grid_cons
 	t.ok = 0;
 	t.pos = 0;
 	t.qstart = t.qend = t.sp = 0;
-	if (valid) t = backtrace_tagged<MODE>(P, s_lut, c, pbase, row_stride, geo, id & 1, ops, stride, ops_cap, best_in[id]);
+	if (valid) t = backtrace_tagged<MODE>(P, s_lut, c, pbase, row_stride, geo, id & 1, ops, stride, ops_cap, best_in[id], &s_ring[0][threadIdx.x], 256);
 	FormatOut f;
 	f.cigar_len = f.md_len = f.match = f.mismatch = f.total = f.read_index = 0;
 	if (t.ok) f = format_cigar_md<false>(P, c, ops, stride, t, nullptr, nullptr);

@@ -651,17 +651,16 @@ static int pack_reads_device(ngm_b200_ctx *c, const uint8_t *d_ascii, int n_read
 	const int RW = c->dp.read_words;
 	CU(c->d_rfwd.ensure((size_t) n_reads * RW * 4));
 	CU(c->d_rrev.ensure((size_t) n_reads * RW * 4));
-	CU(c->d_rrlen32.ensure((size_t) n_reads * 4));
 	CU(c->d_rrlen.ensure((size_t) n_reads * 2));
-	CU(cudaMemsetAsync(c->d_rrlen32.p, 0, (size_t) n_reads * 4, st));
-	const long long tot = (long long) n_reads * RW;
 	const int width = std::min(stride, c->dp.qml);
-	pack_ascii_kernel<<<(unsigned) ((tot + 255) / 256), 256, 0, st>>>(d_ascii, n_reads, n_reads, width, stride, c->d_rfwd.as<uint32_t>(), RW,
-			c->d_rrlen32.as<unsigned int>(), nullptr);
-	narrow_rlen_kernel<<<(n_reads + 255) / 256, 256, 0, st>>>(c->d_rrlen32.as<unsigned int>(), c->d_rrlen.as<uint16_t>(), n_reads);
-	revcomp_kernel<<<(unsigned) ((tot + 255) / 256), 256, 0, st>>>(c->d_rfwd.as<uint32_t>(), c->d_rrlen.as<uint16_t>(), n_reads, RW,
-			c->d_rrev.as<uint32_t>());
-	c->launches += 3;
+	const unsigned blocks = (unsigned) ((n_reads + 7) / 8);
+	if (RW <= 64)
+		pack_reads_kernel<64><<<blocks, 256, 0, st>>>(d_ascii, n_reads, width, stride, c->d_rfwd.as<uint32_t>(), c->d_rrev.as<uint32_t>(),
+				c->d_rrlen.as<uint16_t>(), RW);
+	else
+		pack_reads_kernel<512><<<blocks, 256, 0, st>>>(d_ascii, n_reads, width, stride, c->d_rfwd.as<uint32_t>(), c->d_rrev.as<uint32_t>(),
+				c->d_rrlen.as<uint16_t>(), RW);
+	c->launches += 1;
 	CU(cudaGetLastError());
 	c->n_reads = n_reads;
 	return NGM_B200_OK;

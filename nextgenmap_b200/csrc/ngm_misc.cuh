@@ -11,16 +11,16 @@ namespace ngm {
 // packers
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t ascii_code(uint32_t ch) {
-	// oclDefines.cl:64-80
-	switch (ch) {
-	case 'A': case 'a': return 0;
-	case 'C': case 'c': return 1;
-	case 'G': case 'g': return 2;
-	case 'T': case 't': return 3;
-	case 'N': case 'n': return 5;
-	case 0: return 6;
-	default: return 4;
-	}
+	// oclDefines.cl:64-80, branch-free (a switch on per-lane data diverges on every byte)
+	const uint32_t u = ch & 0xDFu;                 // 'a'..'z' -> 'A'..'Z'; nothing else maps onto a letter
+	uint32_t code = 4;
+	code = u == 'A' ? 0u : code;
+	code = u == 'C' ? 1u : code;
+	code = u == 'G' ? 2u : code;
+	code = u == 'T' ? 3u : code;
+	code = u == 'N' ? 5u : code;
+	code = ch == 0 ? 6u : code;
+	return code;
 }
 
 // ASCII rows -> packed code words.  One thread per output word; bytes past `width`
@@ -52,6 +52,64 @@ __global__ void pack_ascii_kernel(const uint8_t *__restrict__ src, int src_rows,
 __global__ void narrow_rlen_kernel(const unsigned int *__restrict__ rlen32, uint16_t *__restrict__ rlen, int rows) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < rows) rlen[i] = (uint16_t) rlen32[i];
+}
+
+// Read upload of the descriptor path in one pass: one warp per read row.  ASCII -> code words (fwd),
+// rlen, and the reverse complement (MappedRead::computeReverseSeq, MappedRead.cpp:36-67) built from a
+// per-warp shared-memory copy of the forward words.  8-byte loads when the row stride allows it.
+template <int MAXW>
+__global__ void __launch_bounds__(256) pack_reads_kernel(const uint8_t *__restrict__ src, int rows, int width, int src_stride,
+		uint32_t *__restrict__ fwd, uint32_t *__restrict__ rev, uint16_t *__restrict__ rlen, int words) {
+	__shared__ uint32_t s_words[8][MAXW];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int row = blockIdx.x * 8 + warp;
+	if (row >= rows) return;
+	const uint8_t *s = src + (size_t) row * src_stride;
+	const bool vec = ((src_stride & 7) == 0) && ((reinterpret_cast<uintptr_t>(src) & 7) == 0);
+	int last = 0;
+	for (int w = lane; w < words; w += 32) {
+		uint32_t word = 0;
+		const int i0 = 8 * w;
+		if (vec && i0 + 8 <= width) {
+			const uint2 v = *reinterpret_cast<const uint2 *>(s + i0);
+#pragma unroll
+			for (int k = 0; k < 8; ++k) {
+				const uint32_t ch = ((k < 4 ? v.x : v.y) >> (8 * (k & 3))) & 0xFFu;
+				word |= ascii_code(ch) << (4 * k);
+				if (ch != 0) last = i0 + k + 1;
+			}
+		} else {
+#pragma unroll
+			for (int k = 0; k < 8; ++k) {
+				const int i = i0 + k;
+				const uint32_t ch = i < width ? s[i] : 0u;
+				word |= ascii_code(ch) << (4 * k);
+				if (ch != 0) last = i + 1;
+			}
+		}
+		s_words[warp][w] = word;
+		fwd[(size_t) row * words + w] = word;
+	}
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, d));
+	__syncwarp();
+	if (lane == 0) rlen[row] = (uint16_t) last;
+	const int len = last;
+	for (int w = lane; w < words; w += 32) {
+		uint32_t word = 0;
+#pragma unroll
+		for (int k = 0; k < 8; ++k) {
+			const int i = 8 * w + k;
+			uint32_t code = kCodeNul;
+			if (i < len) {
+				const int srcn = len - 1 - i;
+				code = (s_words[warp][srcn >> 3] >> (4 * (srcn & 7))) & 0xFu;
+				if (code < 4) code = 3 - code;
+			}
+			word |= code << (4 * k);
+		}
+		rev[(size_t) row * words + w] = word;
+	}
 }
 
 // strict path: pair i uses read row i and the window packed at word i * win_words
