@@ -653,13 +653,12 @@ static int pack_reads_device(ngm_b200_ctx *c, const uint8_t *d_ascii, int n_read
 	CU(c->d_rrev.ensure((size_t) n_reads * RW * 4));
 	CU(c->d_rrlen.ensure((size_t) n_reads * 2));
 	const int width = std::min(stride, c->dp.qml);
-	const unsigned blocks = (unsigned) ((n_reads + 7) / 8);
-	if (RW <= 64)
-		pack_reads_kernel<64><<<blocks, 256, 0, st>>>(d_ascii, n_reads, width, stride, c->d_rfwd.as<uint32_t>(), c->d_rrev.as<uint32_t>(),
-				c->d_rrlen.as<uint16_t>(), RW);
-	else
-		pack_reads_kernel<512><<<blocks, 256, 0, st>>>(d_ascii, n_reads, width, stride, c->d_rfwd.as<uint32_t>(), c->d_rrev.as<uint32_t>(),
-				c->d_rrlen.as<uint16_t>(), RW);
+	const long long tot = (long long) n_reads * RW;
+	pack_words_kernel<<<(unsigned) ((tot + 255) / 256), 256, 0, st>>>(d_ascii, n_reads, width, stride, c->d_rfwd.as<uint32_t>(), RW);
+	read_len_kernel<<<(n_reads + 255) / 256, 256, 0, st>>>(c->d_rfwd.as<uint32_t>(), n_reads, RW, c->d_rrlen.as<uint16_t>());
+	revcomp_words_kernel<<<(unsigned) ((tot + 255) / 256), 256, 0, st>>>(c->d_rfwd.as<uint32_t>(), c->d_rrlen.as<uint16_t>(), n_reads, RW,
+			c->d_rrev.as<uint32_t>());
+	c->launches += 2;
 	c->launches += 1;
 	CU(cudaGetLastError());
 	c->n_reads = n_reads;

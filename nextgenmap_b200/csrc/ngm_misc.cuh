@@ -54,62 +54,74 @@ __global__ void narrow_rlen_kernel(const unsigned int *__restrict__ rlen32, uint
 	if (i < rows) rlen[i] = (uint16_t) rlen32[i];
 }
 
-// Read upload of the descriptor path in one pass: one warp per read row.  ASCII -> code words (fwd),
-// rlen, and the reverse complement (MappedRead::computeReverseSeq, MappedRead.cpp:36-67) built from a
-// per-warp shared-memory copy of the forward words.  8-byte loads when the row stride allows it.
-template <int MAXW>
-__global__ void __launch_bounds__(256) pack_reads_kernel(const uint8_t *__restrict__ src, int rows, int width, int src_stride,
-		uint32_t *__restrict__ fwd, uint32_t *__restrict__ rev, uint16_t *__restrict__ rlen, int words) {
-	__shared__ uint32_t s_words[8][MAXW];
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int row = blockIdx.x * 8 + warp;
-	if (row >= rows) return;
+// Read upload of the descriptor path (HBM-bound byte shuffling, three small kernels):
+//   pack_words_kernel   one thread per 8 bytes: one 64-bit load, eight lookups in a 256-byte shared table
+//                       of the reference's trans classes (oclDefines.cl:64-80), one word store
+//   read_len_kernel     one thread per read: index of the last non-NUL code + 1
+//   revcomp_words_kernel one thread per output word, nibble reversal + complement by bit tricks
+//                       (MappedRead::computeReverseSeq, MappedRead.cpp:36-67: only A<->T, C<->G change)
+__global__ void __launch_bounds__(256) pack_words_kernel(const uint8_t *__restrict__ src, int rows, int width, int src_stride,
+		uint32_t *__restrict__ dst, int words) {
+	__shared__ uint8_t s_code[256];
+	s_code[threadIdx.x] = (uint8_t) ascii_code(threadIdx.x);
+	__syncthreads();
+	const long long gid = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (gid >= (long long) rows * words) return;
+	const int row = (int) (gid / words), w = (int) (gid - (long long) row * words);
 	const uint8_t *s = src + (size_t) row * src_stride;
-	const bool vec = ((src_stride & 7) == 0) && ((reinterpret_cast<uintptr_t>(src) & 7) == 0);
-	int last = 0;
-	for (int w = lane; w < words; w += 32) {
-		uint32_t word = 0;
-		const int i0 = 8 * w;
-		if (vec && i0 + 8 <= width) {
-			const uint2 v = *reinterpret_cast<const uint2 *>(s + i0);
-#pragma unroll
-			for (int k = 0; k < 8; ++k) {
-				const uint32_t ch = ((k < 4 ? v.x : v.y) >> (8 * (k & 3))) & 0xFFu;
-				word |= ascii_code(ch) << (4 * k);
-				if (ch != 0) last = i0 + k + 1;
-			}
-		} else {
-#pragma unroll
-			for (int k = 0; k < 8; ++k) {
-				const int i = i0 + k;
-				const uint32_t ch = i < width ? s[i] : 0u;
-				word |= ascii_code(ch) << (4 * k);
-				if (ch != 0) last = i + 1;
-			}
-		}
-		s_words[warp][w] = word;
-		fwd[(size_t) row * words + w] = word;
-	}
-#pragma unroll
-	for (int d = 16; d > 0; d >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, d));
-	__syncwarp();
-	if (lane == 0) rlen[row] = (uint16_t) last;
-	const int len = last;
-	for (int w = lane; w < words; w += 32) {
-		uint32_t word = 0;
+	const int i0 = 8 * w;
+	uint32_t word;
+	if (((src_stride & 7) == 0) && ((reinterpret_cast<uintptr_t>(src) & 7) == 0) && i0 + 8 <= width) {
+		const uint2 v = *reinterpret_cast<const uint2 *>(s + i0);
+		word = (uint32_t) s_code[v.x & 0xFF] | (uint32_t) s_code[(v.x >> 8) & 0xFF] << 4 | (uint32_t) s_code[(v.x >> 16) & 0xFF] << 8 |
+				(uint32_t) s_code[v.x >> 24] << 12 | (uint32_t) s_code[v.y & 0xFF] << 16 | (uint32_t) s_code[(v.y >> 8) & 0xFF] << 20 |
+				(uint32_t) s_code[(v.y >> 16) & 0xFF] << 24 | (uint32_t) s_code[v.y >> 24] << 28;
+	} else {
+		word = 0;
 #pragma unroll
 		for (int k = 0; k < 8; ++k) {
-			const int i = 8 * w + k;
-			uint32_t code = kCodeNul;
-			if (i < len) {
-				const int srcn = len - 1 - i;
-				code = (s_words[warp][srcn >> 3] >> (4 * (srcn & 7))) & 0xFu;
-				if (code < 4) code = 3 - code;
-			}
-			word |= code << (4 * k);
+			const int i = i0 + k;
+			word |= (uint32_t) s_code[i < width ? s[i] : 0] << (4 * k);
 		}
-		rev[(size_t) row * words + w] = word;
 	}
+	dst[gid] = word;
+}
+
+__global__ void read_len_kernel(const uint32_t *__restrict__ fwd, int rows, int words, uint16_t *__restrict__ rlen) {
+	const int row = blockIdx.x * blockDim.x + threadIdx.x;
+	if (row >= rows) return;
+	const uint32_t *f = fwd + (size_t) row * words;
+	int len = 0;
+	for (int w = words - 1; w >= 0; --w) {
+		const uint32_t x = f[w] ^ kNulWord;           // non-zero nibble <=> code != NUL
+		if (x != 0) {
+			len = 8 * w + (31 - __clz(x)) / 4 + 1;
+			break;
+		}
+	}
+	rlen[row] = (uint16_t) len;
+}
+
+__global__ void __launch_bounds__(256) revcomp_words_kernel(const uint32_t *__restrict__ fwd, const uint16_t *__restrict__ rlen, int rows, int words,
+		uint32_t *__restrict__ rev) {
+	const long long gid = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (gid >= (long long) rows * words) return;
+	const int row = (int) (gid / words), w = (int) (gid - (long long) row * words);
+	const int hi = (int) rlen[row] - 1 - 8 * w;        // source index of output nibble 0; nibble k reads hi - k
+	uint32_t out = kNulWord;
+	if (hi >= 0) {
+		const uint32_t *f = fwd + (size_t) row * words;
+		const int wi = hi >> 3;
+		const uint32_t a = f[wi];
+		const uint32_t b = wi > 0 ? f[wi - 1] : kNulWord;            // indices < 0 read as NUL
+		// 16 nibbles: b = indices 8wi-8 .. 8wi-1, a = 8wi .. 8wi+7; take the 8 ending at `hi`
+		const uint32_t x = __funnelshift_rc(b, a, 4 * ((hi & 7) + 1));   // nibble 7 = index hi ... nibble 0 = hi - 7
+		uint32_t y = __byte_perm(x, 0, 0x0123);
+		y = ((y >> 4) & 0x0F0F0F0Fu) | ((y & 0x0F0F0F0Fu) << 4);       // nibble order reversed: nibble k = index hi - k
+		const uint32_t m = (~y >> 2) & 0x11111111u;                    // codes 0..3 (A C G T): complement = code ^ 3
+		out = y ^ (m * 3u);
+	}
+	rev[gid] = out;
 }
 
 // strict path: pair i uses read row i and the window packed at word i * win_words
