@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--contigs", type=int, default=int(os.environ.get("NGM_BENCH_CONTIGS", 24)))
     ap.add_argument("--contig-len", type=int, default=int(os.environ.get("NGM_BENCH_CONTIG_LEN", 125_000_000)))
     ap.add_argument("--sub-batch", type=int, default=1_000_000, help="reads per e2e sub-batch")
+    ap.add_argument("--lanes", type=int, default=3, help="e2e: contexts/streams the sub-batches rotate over")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -67,13 +68,16 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    # started a little before the timed region (nvidia-smi needs ~0.2 s to produce its first line); only
+    # samples whose arrival time falls inside [mark_begin, mark_end] are used
 
     def __init__(self, index: int):
         self.index, self.proc, self.lines = index, None, []
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -82,7 +86,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def stop(self) -> dict:
         if self.proc is None:
@@ -94,7 +104,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        inside = [ln for (t, ln) in self.lines if self.t_begin is None or (self.t_begin <= t <= (self.t_end or t) + 0.15)]
+        if not inside:
+            inside = [ln for (_, ln) in self.lines[-3:]]
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -169,6 +182,8 @@ def main():
     import torch
     import torch.distributed as dist
 
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version banner on stdout otherwise; stdout carries ONE JSON line
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -271,22 +286,24 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     for _ in range(max(args.warmup, 3)):
         resident_step()
     barrier()
     if int(d_cursor.item()) > str_cap:
         raise RuntimeError("string heap too small")
 
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     launches0 = sw.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    clocks.mark_begin()
     e0.record()
     for _ in range(args.steps):
         resident_step()
     e1.record()
     barrier()
+    clocks.mark_end()
     ms = e0.elapsed_time(e1)
     launches = sw.launch_count() - launches0 + args.steps      # + one memset (cursor) per step issued by torch
     clk = clocks.stop()
@@ -340,7 +357,7 @@ def main():
         h_strings = torch.empty(str_cap, dtype=torch.uint8).pin_memory()
         h_used = torch.zeros(((n + SB - 1) // SB,), dtype=torch.int32).pin_memory()
         lanes = []
-        for _ in range(2):
+        for _ in range(max(1, args.lanes)):
             lane_sw = CudaSW(qml, corridor, device=local_rank)
             s_ = torch.cuda.Stream(device=dev)
             with torch.cuda.stream(s_):
@@ -370,7 +387,7 @@ def main():
         def e2e_step():
             nonlocal h2d, d2h
             for k, s in enumerate(range(0, n, SB)):
-                lane = lanes[k % 2]
+                lane = lanes[k % len(lanes)]
                 finish(lane)
                 m = min(SB, n - s)
                 p0, p1 = int(cb_h[s]), int(cb_h[s + m])
@@ -410,7 +427,7 @@ def main():
         e2e_launch = sum(l["sw"].launch_count() for l in lanes)
         e2e_ms = sharding.max_over_ranks(e2e_s * 1e3, dev)
         e2e = {"value": world * n * args.steps / (e2e_ms / 1e3), "unit": "reads/s", "h2d_bytes_per_step": h2d // args.steps,
-               "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_ms / args.steps, "sub_batch_reads": SB, "streams": 2,
+               "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_ms / args.steps, "sub_batch_reads": SB, "streams": len(lanes),
                "timer": "host wall clock around K steps (barrier + synchronize both sides), max over ranks"}
         # the e2e path must reproduce the resident results bit for bit
         h_view = h_recs.numpy().view(ALIGN_REC).reshape(-1)
@@ -456,6 +473,47 @@ def main():
     except Exception as e:  # noqa: BLE001
         parity = {"error": str(e)}
 
+    # ---- strict IAlignment path (char** in, struct Align out), one host thread, for the record ----
+    strict = None
+    try:
+        n_sp = min(262144, npairs)
+        pv = batch.pairs[:n_sp]
+        starts = pv[:, 0:8].contiguous().view(torch.int64).reshape(-1)
+        ridx = pv[:, 8:12].contiguous().view(torch.int32).reshape(-1).long()
+        rev = (pv[:, 12:16].contiguous().view(torch.int32).reshape(-1) & 1).bool()
+        width = ((qml + corridor) | 1) + 1
+        pos = starts[:, None] + torch.arange(width - 2, device=dev)[None, :]
+        b = ref.packed[pos >> 1]
+        codes = torch.where((pos & 1) == 1, b & 0xF, b >> 4).long()
+        lut = workload.ASCII_OF_NGM.to(dev)
+        win = torch.zeros((n_sp, width), dtype=torch.uint8, device=dev)
+        win[:, : width - 2] = lut[codes]
+        rd = batch.reads[ridx]
+        comp = torch.arange(256, dtype=torch.uint8, device=dev)
+        for a_, b_ in zip(b"ACGT", b"TGCA"):
+            comp[a_] = b_
+        rc = torch.zeros_like(rd)
+        rc[:, :READ_LEN] = comp[torch.flip(rd[:, :READ_LEN], dims=[1]).long()]
+        rd = torch.where(rev[:, None], rc, rd)
+        refs_h, qrys_h = win.cpu().numpy(), rd.cpu().numpy()
+        ssw = CudaSW(qml, corridor, device=local_rank)
+        ssw.BatchScore(MODE_LOCAL, refs_h[:4096], qrys_h[:4096])
+        t0 = time.perf_counter()
+        sc_strict = ssw.BatchScore(MODE_LOCAL, refs_h, qrys_h)
+        t1 = time.perf_counter()
+        n_al = n_sp // 2
+        ssw.batch_align_raw(MODE_LOCAL, refs_h[:4096], qrys_h[:4096])
+        t2 = time.perf_counter()
+        ssw.batch_align_raw(MODE_LOCAL, refs_h[:n_al], qrys_h[:n_al])
+        t3 = time.perf_counter()
+        same = bool(np.array_equal(sc_strict, d_scores[:n_sp].cpu().numpy()))
+        strict = {"score_pairs_per_s": n_sp / (t1 - t0), "align_pairs_per_s": n_al / (t3 - t2), "host_threads": 1,
+                  "pairs": n_sp, "scores_equal_descriptor_path": same,
+                  "note": "drop-in IAlignment::BatchScore/BatchAlign with host char** buffers; host gather + PCIe bound"}
+        ssw.close()
+    except Exception as e:  # noqa: BLE001
+        strict = {"error": str(e)}
+
     peaks = {}
     pk = ROOT / "MEASURED_PEAKS.json"
     if pk.exists():
@@ -488,7 +546,7 @@ def main():
                          "definition": "cells = L x corridor = 4050 per pair; peak = SMs x 128 lanes x max clock / 5 instr per cell (SURVEY 8d)"},
         "kernel_ms": {"set_reads": ms_pack, "score": ms_score, "align": ms_align, "score_share": ms_score / (ms_max / args.steps),
                       "align_share": ms_align / (ms_max / args.steps)},
-        "cpu_baseline": cpu_baseline, "parity_sample": parity,
+        "cpu_baseline": cpu_baseline, "parity_sample": parity, "strict_path": strict,
         "counters": {"reads": total_reads, "mapped": ctr["mapped"], "pairs_scored": ctr["pairs_scored"], "string_bytes": used_strings},
         "setup_seconds": setup_s, "host_threads": host_threads,
     }

@@ -42,6 +42,10 @@ class _CAlign(C.Structure):
 ALIGN_REC = np.dtype([("position_offset", "<i4"), ("qstart", "<i4"), ("qend", "<i4"), ("nm", "<i4"), ("identity", "<f4"),
                       ("score", "<f4"), ("str_off", "<u4"), ("cigar_len", "<u2"), ("md_len", "<u2")])
 PAIR = np.dtype([("window_start", "<u8"), ("read_index", "<u4"), ("flags", "<u4")])
+# ngm_b200_align == the reference's struct Align (IAlignment.h:14-28) on LP64
+ALIGN_C = np.dtype([("cigar", "<u8"), ("md", "<u8"), ("extended", "<u8"), ("position_offset", "<i4"), ("qstart", "<i4"), ("qend", "<i4"),
+                    ("score", "<f4"), ("identity", "<f4"), ("nm", "<i4")])
+assert ALIGN_C.itemsize == C.sizeof(_CAlign)
 PF_REVERSE, PF_DIR, PF_SKIP = 1, 2, 4
 
 
@@ -172,27 +176,32 @@ class CudaSW:
         n = refs.shape[0]
         if n == 0:
             return []
-        stride = 4 * max(1, self.qml) + 2 * self.corridor + 64
-        cig = np.zeros((n, stride), np.uint8)
-        md = np.zeros((n, stride), np.uint8)
-        cig[:, :3] = 0x21                      # AlignmentBuffer.cpp:108-109
-        md[:, :3] = 0x21
-        res = (_CAlign * n)()
-        cp, mp = _row_pointers(cig), _row_pointers(md)
-        for i in range(n):
-            res[i].cigar = int(cp[i])
-            res[i].md = int(mp[i])
-        rp, qp = _row_pointers(refs), _row_pointers(qrys)
-        d = None if extData is None else np.ascontiguousarray(extData, dtype=np.uint8)
-        got = self._check(self.lib.ngm_b200_batch_align(self.ctx, mode, n, rp.ctypes.data, qp.ctypes.data, qp.ctypes.data,
-                                                        C.addressof(res), None if d is None else d.ctypes.data))
-        assert got == n
+        res, cig, md = self.batch_align_raw(mode, refs, qrys, extData)
         out = []
         for i in range(n):
             r = res[i]
-            out.append(Align(cig[i].tobytes().split(b"\0")[0], md[i].tobytes().split(b"\0")[0], r.position_offset, r.qstart,
-                             r.qend, r.score, r.identity, r.nm))
+            out.append(Align(cig[i].tobytes().split(b"\0")[0], md[i].tobytes().split(b"\0")[0], int(r["position_offset"]), int(r["qstart"]),
+                             int(r["qend"]), float(r["score"]), float(r["identity"]), int(r["nm"])))
         return out
+
+    def batch_align_raw(self, mode: int, refs: np.ndarray, qrys: np.ndarray, extData=None):
+        """BatchAlign into numpy buffers: (struct Align array, CIGAR rows, MD rows); rows are 4*qry_max_len+ bytes
+        pre-filled with "!!!" like AlignmentBuffer.cpp:108-109."""
+        n = refs.shape[0]
+        stride = 4 * max(1, self.qml) + 2 * self.corridor + 64
+        cig = np.zeros((n, stride), np.uint8)
+        md = np.zeros((n, stride), np.uint8)
+        cig[:, :3] = 0x21
+        md[:, :3] = 0x21
+        res = np.zeros(n, dtype=ALIGN_C)
+        res["cigar"] = _row_pointers(cig)
+        res["md"] = _row_pointers(md)
+        rp, qp = _row_pointers(refs), _row_pointers(qrys)
+        d = None if extData is None else np.ascontiguousarray(extData, dtype=np.uint8)
+        got = self._check(self.lib.ngm_b200_batch_align(self.ctx, mode, n, rp.ctypes.data, qp.ctypes.data, qp.ctypes.data,
+                                                        res.ctypes.data, None if d is None else d.ctypes.data))
+        assert got == n
+        return res, cig, md
 
     # -- descriptor fast path -----------------------------------------------
     def set_reference(self, packed: np.ndarray, concat_len: int) -> None:
