@@ -54,6 +54,7 @@ struct HalfBest {
 // sequence lookup at all.
 // ---------------------------------------------------------------------------
 constexpr int kRing = 16;       // rows in flight per thread (power of two)
+constexpr int kSpecialFlag = 1 << 30;   // in HalfBest::read_count: sequences hold codes other than A/C/G/T
 
 __device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const uint32_t *gmem_src) {
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t) __cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
@@ -65,6 +66,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 struct BandRt {
 	int words;       // pointer words per row per thread slot = ceil(W / 8)
 	int cap;         // band capacity W
+	int tstride;     // thread slots per launch (distance between column groups of one row)
 };
 
 __device__ __forceinline__ uint32_t tagged_code(uint32_t w, int col, int cap, int half) {
@@ -81,7 +83,8 @@ __device__ __forceinline__ TraceOut backtrace_tagged(const DevParams &P, const u
 	o.qstart = 0;
 	o.qend = 0;
 	o.sp = 0;
-	const int best_read = b.x, best_ref = b.y, best_score = b.z, read_count = b.w;
+	const int best_read = b.x, best_ref = b.y, best_score = b.z, read_count = b.w & (kSpecialFlag - 1);
+	const bool plain = !P.alt && !(b.w & kSpecialFlag);            // every diag step scores `match` or `mismatch`
 	if (best_read <= 0) {                                         // oclSwCigar.cl:78
 		o.ok = 0;
 		o.pos = best_read;
@@ -102,7 +105,7 @@ __device__ __forceinline__ TraceOut backtrace_tagged(const DevParams &P, const u
 	const long long rs = (long long) row_stride;
 	int g = col >> 3;
 	int sh = 2 * (min(8, geo.cap - 8 * g) - 1 - (col & 7)) + 16 * half;
-	const uint32_t *pg = pbase + (size_t) (row + c.sub) * row_stride + g;        // word of the current row
+	const uint32_t *pg = pbase + (size_t) (row + c.sub) * row_stride + (size_t) g * geo.tstride;   // word of the current row
 	auto fill = [&](int r, const uint32_t *src) {                                 // async copy of row r's word (or an empty group)
 		if (r >= 0) cp_async4(ring + (r & (kRing - 1)) * ring_stride, src);
 		cp_async_commit();
@@ -131,10 +134,14 @@ __device__ __forceinline__ TraceOut backtrace_tagged(const DevParams &P, const u
 		} else {
 			if (MODE == 0 && h <= 0) break;
 			if (p >= 2u) {
-				const int rc = code_at(c.rp, row) & 7;
-				const int fc = code_at(c.wp, (int64_t) c.sub + row + col) & 7;
 				op = p == 3u ? OP_EQ : OP_X;
-				h -= lut_score(s_lut, c.dir, rc, fc);
+				if (plain) {
+					h -= P.mismatch;                              // tag 2 between plain codes (tag 3 took the fast path)
+				} else {
+					const int rc = code_at(c.rp, row) & 7;
+					const int fc = code_at(c.wp, (int64_t) c.sub + row + col) & 7;
+					h -= lut_score(s_lut, c.dir, rc, fc);
+				}
 				row -= 1;
 				abs_ref -= 1;
 			} else {
@@ -156,7 +163,7 @@ __device__ __forceinline__ TraceOut backtrace_tagged(const DevParams &P, const u
 				if (ng != g && !border && row >= 0) {             // column group changed: restart the ring there
 					g = ng;
 					cp_async_wait<0>();
-					pg = pbase + (size_t) (row + c.sub) * row_stride + g;
+					pg = pbase + (size_t) (row + c.sub) * row_stride + (size_t) g * geo.tstride;
 #pragma unroll
 					for (int k = 0; k < kRing; ++k) fill(row - k, pg - k * rs);
 					pf = pg - (long long) kRing * rs;
@@ -240,8 +247,10 @@ __global__ void __launch_bounds__(128) align_s16_fwd_kernel(const __grid_constan
 	const int corridor = P.corridor;
 	const uint32_t gr2 = pack2(4 * P.gap_read + 1, 4 * P.gap_read + 1), gf2 = pack2(4 * P.gap_ref, 4 * P.gap_ref);
 	const int tstride = stride >> 1;                             // thread slots per launch
+	// pointer matrix layout [row q][column group][thread slot]: the words of one group and row are contiguous
+	// over thread slots, so the forward stores and the backtrace loads of a warp are both fully coalesced
 	const size_t row_stride = (size_t) tstride * T::kWords;
-	uint32_t *pbase = ptr_scratch + (size_t) t2 * T::kWords;
+	uint32_t *pbase = ptr_scratch + (size_t) t2;
 	HalfBest ba, bb;
 	{
 		uint32_t line[W + 1], snap[W];
@@ -252,10 +261,18 @@ __global__ void __launch_bounds__(128) align_s16_fwd_kernel(const __grid_constan
 		uint32_t best = 0;
 		int brow_a = 0, brow_b = 0, rc_a = 0, rc_b = 0;
 		uint32_t wa[G::kWin], wb[G::kWin];
+		// "special" = a code other than A/C/G/T inside the read or inside the part of the window the band can
+		// touch: only then does a non-EQ diagonal step score something else than `mismatch`, and only then
+		// does the backtrace have to look at the sequences (bit 2 of a nibble <=> code >= 4)
+		const int wend_a = ca.sub + ca.len + corridor - 1, wend_b = cb.sub + cb.len + corridor - 1;
+		auto nib_mask = [](int valid) { return valid >= 8 ? 0xFFFFFFFFu : (valid <= 0 ? 0u : ((1u << (4 * valid)) - 1u)); };
+		uint32_t spec_a = 0, spec_b = 0;
 #pragma unroll
 		for (int k = 0; k < G::kWin; ++k) {
 			wa[k] = __ldg(ca.wp + k);
 			wb[k] = __ldg(cb.wp + k);
+			spec_a |= wa[k] & nib_mask(wend_a - 8 * k);
+			spec_b |= wb[k] & nib_mask(wend_b - 8 * k);
 		}
 		const int nqw = max(act_a ? (ca.sub + ca.len + 7) >> 3 : 0, act_b ? (cb.sub + cb.len + 7) >> 3 : 0);
 		const uint2 *luta = s_lut4 + ca.dir * 8, *lutb = s_lut4 + cb.dir * 8;
@@ -268,6 +285,8 @@ __global__ void __launch_bounds__(128) align_s16_fwd_kernel(const __grid_constan
 			prev_a = cur_a;
 			prev_b = cur_b;
 			const uint32_t next_a = __ldg(ca.wp + qw + G::kWin), next_b = __ldg(cb.wp + qw + G::kWin);
+			spec_a |= (next_a & nib_mask(wend_a - 8 * (qw + G::kWin))) | (cur_a & nib_mask(ca.len - 8 * qw));
+			spec_b |= (next_b & nib_mask(wend_b - 8 * (qw + G::kWin))) | (cur_b & nib_mask(cb.len - 8 * qw));
 #pragma unroll
 			for (int t = 0; t < 8; ++t) {
 				const int rca = (rda >> (4 * t)) & 7, rcb = (rdb >> (4 * t)) & 7;
@@ -301,12 +320,8 @@ __global__ void __launch_bounds__(128) align_s16_fwd_kernel(const __grid_constan
 						line[j] = clean;
 					}
 				}
-				if (T::kWords == 4) {
-					*reinterpret_cast<uint4 *>(prow) = make_uint4(pw[0], pw[1], pw[2 % T::kWords], pw[3 % T::kWords]);
-				} else {
 #pragma unroll
-					for (int k = 0; k < T::kWords; ++k) prow[k] = pw[k];
-				}
+				for (int k = 0; k < T::kWords; ++k) prow[(size_t) k * tstride] = pw[k];
 				prow += row_stride;
 				if (MODE == 0) {
 					uint32_t mx = line[0];
@@ -334,8 +349,8 @@ __global__ void __launch_bounds__(128) align_s16_fwd_kernel(const __grid_constan
 			wa[G::kWin - 1] = next_a;
 			wb[G::kWin - 1] = next_b;
 		}
-		ba.read_count = rc_a;
-		bb.read_count = rc_b;
+		ba.read_count = rc_a | ((spec_a & 0x44444444u) ? kSpecialFlag : 0);
+		bb.read_count = rc_b | ((spec_b & 0x44444444u) ? kSpecialFlag : 0);
 		if (MODE == 0) {
 			const int ma = (int) (short) (best & 0xFFFFu), mb = (int) (short) (best >> 16);
 			int ra = 0, rb = 0;
@@ -403,8 +418,9 @@ __global__ void __launch_bounds__(256) backtrace_format_kernel(const __grid_cons
 	BandRt geo;
 	geo.cap = capacity;
 	geo.words = (capacity + 7) / 8;
-	const size_t row_stride = (size_t) (stride >> 1) * geo.words;
-	const uint32_t *pbase = ptr_scratch + (size_t) (id >> 1) * geo.words;
+	geo.tstride = stride >> 1;
+	const size_t row_stride = (size_t) geo.tstride * geo.words;
+	const uint32_t *pbase = ptr_scratch + (size_t) (id >> 1);
 	uint16_t *ops = ops_scratch + id;
 	TraceOut t;
 	t.ok = 0;

@@ -164,6 +164,7 @@ int build_params(const ngm_b200_params &hp, DevParams &dp, int &use_s16, int *al
 	dp.gap_read = gr;
 	dp.gap_ref = gf;
 	dp.match = match;
+	dp.mismatch = mism;
 	dp.alt = alt != 0;
 	dp.acct_alt = (hp.bs_mapping == 1 || hp.slam_seq != 0) ? 1 : 0;
 	dp.acct_slam = hp.slam_seq != 0;

@@ -42,6 +42,7 @@ struct DevParams {
 	int gap_read;          // negative
 	int gap_ref;           // negative
 	int match;             // match score, EQ test of the non-ALT kernels (oclSwScore.cl:64)
+	int mismatch;          // -mismatch_penalty: score of every non-EQ diag step between plain A/C/G/T codes
 	int alt;               // ALT scoring compiled in: EQ iff codes equal (oclSwScore.cl:69)
 	int acct_alt;          // bs_mapping == 1 || slam_seq != 0 : X-op accounting (SWOclCigar.cpp:500-514)
 	int acct_slam;         // slam_seq != 0 (bsFrom/bsTo choice, SWOclCigar.cpp:312-320)

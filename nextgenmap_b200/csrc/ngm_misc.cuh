@@ -92,7 +92,8 @@ __global__ void read_len_kernel(const uint32_t *__restrict__ fwd, int rows, int 
 	if (row >= rows) return;
 	const uint32_t *f = fwd + (size_t) row * words;
 	int len = 0;
-	for (int w = words - 1; w >= 0; --w) {
+	int w = words - 1;
+	for (; w >= 0; --w) {
 		const uint32_t x = f[w] ^ kNulWord;           // non-zero nibble <=> code != NUL
 		if (x != 0) {
 			len = 8 * w + (31 - __clz(x)) / 4 + 1;
@@ -100,6 +101,7 @@ __global__ void read_len_kernel(const uint32_t *__restrict__ fwd, int rows, int 
 		}
 	}
 	rlen[row] = (uint16_t) len;
+
 }
 
 __global__ void __launch_bounds__(256) revcomp_words_kernel(const uint32_t *__restrict__ fwd, const uint16_t *__restrict__ rlen, int rows, int words,
