@@ -1,0 +1,74 @@
+"""oracle/ngm_e2e.py -- TEST INFRASTRUCTURE ONLY.
+
+End-to-end runs of the UNMODIFIED NextGenMap built by oracle/Makefile.ngm:
+``ngm_ref`` (reference OpenCL backend on the vendored CPU runtime) and ``ngm_cuda`` (same NGM objects, CUDA
+backend through the link seam).  BASELINE configs[0]: 10 k x 100 bp single-end synthetic reads vs a 5 Mbp
+synthetic reference, ``-t 4``; compare sorted SAM bodies (thread interleaving only permutes lines).
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+from pathlib import Path
+from typing import List, Sequence
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+NGM_DIR = HERE / "_ref" / "ngm"
+COMP = bytes.maketrans(b"ACGT", b"TGCA")
+
+
+def binary(which: str) -> Path:
+    return NGM_DIR / f"ngm_{which}"
+
+
+def available(which: str) -> bool:
+    return binary(which).exists()
+
+
+def write_inputs(d: Path, ref_len: int = 5_000_000, n_reads: int = 10_000, read_len: int = 100, seed: int = 20261017,
+                 sub_rate: float = 0.02, indel_reads: float = 0.05) -> None:
+    """Seeded synthetic reference (one contig) + reads: uniform start, both strands, 2 % substitutions,
+    a 1-3 bp indel in 5 % of the reads, constant qualities; truth in the read name."""
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    ref = acgt[rng.integers(0, 4, ref_len)]
+    with open(d / "ref.fa", "wb") as f:
+        f.write(b">chr1 synthetic\n")
+        for i in range(0, ref_len, 60):
+            f.write(ref[i: i + 60].tobytes() + b"\n")
+    with open(d / "reads.fq", "wb") as f:
+        for r in range(n_reads):
+            pos = int(rng.integers(0, ref_len - read_len - 8))
+            seq = ref[pos: pos + read_len + 4].copy()
+            if rng.random() < indel_reads:
+                at, k = int(rng.integers(10, read_len - 10)), int(rng.integers(1, 4))
+                if rng.random() < 0.5:
+                    seq = np.concatenate([seq[:at], seq[at + k:]])
+                else:
+                    seq = np.concatenate([seq[:at], acgt[rng.integers(0, 4, k)], seq[at:]])
+            seq = seq[:read_len]
+            sub = rng.random(read_len) < sub_rate
+            seq[sub] = acgt[rng.integers(0, 4, int(sub.sum()))]
+            s = seq.tobytes()
+            strand = "+"
+            if rng.random() < 0.5:
+                s = s.translate(COMP)[::-1]
+                strand = "-"
+            f.write(f"@r{r}_{pos}_{strand}\n".encode() + s + b"\n+\n" + b"I" * read_len + b"\n")
+
+
+def run(which: str, d: Path, threads: int = 4, extra: Sequence[str] = (), out_name: str = "out.sam") -> List[str]:
+    """Run one NGM binary; return the sorted SAM body without @PG (command line differs)."""
+    env = dict(os.environ)
+    ocl = HERE / "_ref" / "ocl"
+    env["OPENCL_VENDOR_PATH"] = str(ocl / "vendor")
+    env["LD_LIBRARY_PATH"] = str(ocl / "lib") + os.pathsep + env.get("LD_LIBRARY_PATH", "")
+    out = d / out_name
+    cmd = [str(binary(which)), "-r", str(d / "ref.fa"), "-q", str(d / "reads.fq"), "-o", str(out), "-t", str(threads), "--no-progress", *extra]
+    p = subprocess.run(cmd, env=env, capture_output=True, text=True, cwd=d)
+    if p.returncode != 0 or not out.exists():
+        raise RuntimeError(f"{which} failed ({p.returncode}):\n{p.stdout[-1500:]}\n{p.stderr[-1500:]}")
+    lines = [ln for ln in out.read_text().splitlines() if not ln.startswith("@PG")]
+    return sorted(lines)

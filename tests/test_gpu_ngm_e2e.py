@@ -1,0 +1,41 @@
+"""BASELINE configs[0] end to end: the UNMODIFIED NextGenMap, once with its own OpenCL backend (CPU device) and
+once with the CUDA backend swapped in at link time (nextgenmap_b200/link_seam, zero source changes), must write
+the same SAM: same positions, MAPQ, CIGAR, AS / NM / XI / MD tags for every read.
+
+Both binaries are built by oracle/Makefile.ngm where /root/reference exists and travel to the GPU box in
+oracle/_ref/ (git-ignored); the test is skipped when they are absent.
+"""
+import tempfile
+from pathlib import Path
+
+import pytest
+
+from oracle import ngm_e2e as e2e
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not (e2e.available("ref") and e2e.available("cuda")), reason="oracle/_ref/ngm not built")]
+
+
+def compare(extra, n_reads=10_000, read_len=100, threads=4):
+    with tempfile.TemporaryDirectory(prefix="ngm_e2e_") as td:
+        d = Path(td)
+        e2e.write_inputs(d, ref_len=5_000_000, n_reads=n_reads, read_len=read_len)
+        want = e2e.run("ref", d, threads=threads, extra=extra, out_name="ref.sam")
+        got = e2e.run("cuda", d, threads=threads, extra=extra, out_name="cuda.sam")
+    assert len(want) == n_reads + 2                      # @HD, @SQ + one record per read
+    mapped = sum(1 for ln in want if not ln.startswith("@") and ln.split("\t")[2] != "*")
+    assert mapped > 0.98 * n_reads
+    diff = [(a, b) for a, b in zip(want, got) if a != b]
+    assert len(want) == len(got) and not diff, f"{len(diff)} SAM lines differ, first:\n{diff[0][0]}\n{diff[0][1]}"
+
+
+def test_config0_local_mode_sam_identical():
+    """10 k x 100 bp SE vs 5 Mbp, -t 4 (BASELINE.json configs[0])."""
+    compare(extra=())
+
+
+def test_config0_end_to_end_mode_sam_identical():
+    compare(extra=("-e",), n_reads=4000)
+
+
+def test_150bp_single_thread_sam_identical():
+    compare(extra=(), n_reads=4000, read_len=150, threads=1)
