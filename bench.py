@@ -55,6 +55,10 @@ def parse_args():
     ap.add_argument("--contig-len", type=int, default=int(os.environ.get("NGM_BENCH_CONTIG_LEN", 125_000_000)))
     ap.add_argument("--sub-batch", type=int, default=1_000_000, help="reads per e2e sub-batch")
     ap.add_argument("--lanes", type=int, default=3, help="e2e: contexts/streams the sub-batches rotate over")
+    ap.add_argument("--read-len", type=int, default=READ_LEN, help="read length (BASELINE configs[4] sweep: 75/100/150/250/400); default 150")
+    ap.add_argument("--corridor", type=int, default=0, help="override the band width (NGM -C n => 2n); 0 = int(5 + 0.15 L)")
+    ap.add_argument("--sub-rate", type=float, default=0.01)
+    ap.add_argument("--indel-rate", type=float, default=0.0005)
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -193,7 +197,13 @@ def main():
         return 0                                    # rank 0 alone runs the CPU arm
 
     from nextgenmap_b200 import workload
-    qml, corridor = workload.shapes_for(READ_LEN)
+    L = args.read_len
+    qml, corridor = workload.shapes_for(L)
+    if args.corridor:
+        corridor = args.corridor
+    global ALG_BYTES_SCORE, CELLS_PER_PAIR
+    ALG_BYTES_SCORE = (L + 1) // 2 + (L + corridor + 1) // 2 + 12 + 4
+    CELLS_PER_PAIR = L * corridor
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the workload is generated on the GPU; the product has no CPU path)")
@@ -219,11 +229,11 @@ def main():
     n_reads = args.reads
     if args.impl == "reference":
         n_reads = min(n_reads, 200_000)             # only a sample is needed on the CPU arm
-    batch = workload.make_reads(ref, n_reads, READ_LEN, qml, corridor, seed=20261018 + 1 + rank)
+    batch = workload.make_reads(ref, n_reads, L, qml, corridor, seed=20261018 + 1 + rank, sub_rate=args.sub_rate, indel_rate=args.indel_rate)
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t_setup
 
-    cfg = {"workload": f"{args.reads} x {READ_LEN} bp SE synthetic reads vs {args.contigs} x {args.contig_len} bp synthetic reference "
+    cfg = {"workload": f"{args.reads} x {L} bp SE synthetic reads vs {args.contigs} x {args.contig_len} bp synthetic reference "
                        f"({ref.concat_len / 1e9:.2f} Gbp concatenated), ~1.5 candidates/read, local mode, qry_max_len {qml}, corridor {corridor}",
            "reads_per_step_per_gpu": args.reads, "pairs_per_step_per_gpu": batch.n_pairs if args.impl != "reference" else None,
            "step": "set_reads(pack+revcomp) -> score pairs -> top1+MAPQ -> gather winners -> align+backtrace+CIGAR/MD",
@@ -269,7 +279,8 @@ def main():
     d_mapq = torch.empty(n, dtype=torch.int32, device=dev)
     d_wpairs = torch.empty((n, 16), dtype=torch.uint8, device=dev)
     d_recs = torch.empty((n, 32), dtype=torch.uint8, device=dev)
-    str_cap = 48 * n
+    STR_PER = 48 + int(L * args.sub_rate * 5) + (64 if args.indel_rate > 0.001 else 0)      # string-heap bytes per read
+    str_cap = STR_PER * n
     d_strings = torch.empty(str_cap, dtype=torch.uint8, device=dev)
     d_cursor = torch.zeros(1, dtype=torch.int32, device=dev)
 
@@ -366,7 +377,7 @@ def main():
                               pairs=torch.empty((max_pairs, 16), dtype=torch.uint8, device=dev), cb=torch.empty(SB + 1, dtype=torch.int32, device=dev),
                               scores=torch.empty(max_pairs, dtype=torch.float32, device=dev), best=torch.empty(SB, dtype=torch.int32, device=dev),
                               mapq=torch.empty(SB, dtype=torch.int32, device=dev), wpairs=torch.empty((SB, 16), dtype=torch.uint8, device=dev),
-                              recs=torch.empty((SB, 32), dtype=torch.uint8, device=dev), strings=torch.empty(48 * SB, dtype=torch.uint8, device=dev),
+                              recs=torch.empty((SB, 32), dtype=torch.uint8, device=dev), strings=torch.empty(STR_PER * SB, dtype=torch.uint8, device=dev),
                               cursor=torch.zeros(1, dtype=torch.int32, device=dev), pending=None))
         torch.cuda.synchronize()
         h2d = d2h = 0
@@ -403,13 +414,13 @@ def main():
                     check(lib.ngm_b200_dev_gather_winners(c_, m, lane["pairs"].data_ptr(), lane["best"].data_ptr(), lane["wpairs"].data_ptr(), q_))
                     lane["cursor"].zero_()
                     check(lib.ngm_b200_dev_align_pairs(c_, MODE_LOCAL, m, lane["wpairs"].data_ptr(), lane["recs"].data_ptr(), lane["strings"].data_ptr(),
-                                                       48 * SB, lane["cursor"].data_ptr(), q_))
+                                                       STR_PER * SB, lane["cursor"].data_ptr(), q_))
                     h_recs[s: s + m].copy_(lane["recs"][:m], non_blocking=True)
                     h_mapq[s: s + m].copy_(lane["mapq"][:m], non_blocking=True)
                     h_used[k: k + 1].copy_(lane["cursor"], non_blocking=True)
                 h2d += m * qml + mp * 16 + (m + 1) * 4
                 d2h += m * 32 + m * 4 + 4
-                lane["pending"] = dict(k=k, soff=48 * s)
+                lane["pending"] = dict(k=k, soff=STR_PER * s)
             for lane in lanes:
                 finish(lane)
             for lane in lanes:
@@ -493,7 +504,7 @@ def main():
         for a_, b_ in zip(b"ACGT", b"TGCA"):
             comp[a_] = b_
         rc = torch.zeros_like(rd)
-        rc[:, :READ_LEN] = comp[torch.flip(rd[:, :READ_LEN], dims=[1]).long()]
+        rc[:, :L] = comp[torch.flip(rd[:, :L], dims=[1]).long()]
         rd = torch.where(rev[:, None], rc, rd)
         refs_h, qrys_h = win.cpu().numpy(), rd.cpu().numpy()
         ssw = CudaSW(qml, corridor, device=local_rank)
@@ -543,7 +554,7 @@ def main():
         "roofline_alu": {"bound": "int-alu issue", "score_gcups": score_gcups, "align_gcups": align_gcups, "peak_gcups_int32": alu_peak_gcups,
                          "peak_gcups_s16x2": 2 * alu_peak_gcups, "score_frac_of_s16x2_peak": score_gcups / (2 * alu_peak_gcups),
                          "align_frac_of_int32_peak": align_gcups / alu_peak_gcups, "sm_count": sm_count, "sm_mhz_under_load": sm_mhz,
-                         "definition": "cells = L x corridor = 4050 per pair; peak = SMs x 128 lanes x max clock / 5 instr per cell (SURVEY 8d)"},
+                         "definition": f"cells = L x corridor = {CELLS_PER_PAIR} per pair; peak = SMs x 128 lanes x max clock / 5 instr per cell (SURVEY 8d)"},
         "kernel_ms": {"set_reads": ms_pack, "score": ms_score, "align": ms_align, "score_share": ms_score / (ms_max / args.steps),
                       "align_share": ms_align / (ms_max / args.steps)},
         "cpu_baseline": cpu_baseline, "parity_sample": parity, "strict_path": strict,

@@ -143,6 +143,32 @@ int ngm_b200_score_pairs(ngm_b200_ctx *ctx, int mode, int n, const ngm_b200_pair
 int ngm_b200_align_pairs(ngm_b200_ctx *ctx, int mode, int n, const ngm_b200_pair *pairs, ngm_b200_align_rec *recs,
 		char *strings, size_t str_capacity, size_t *str_used);
 
+/* -- reference cache file of NGM ---------------------------- */
+/* One contig of the concatenated reference: RefIdx of SequenceProvider.h:45-52. */
+typedef struct ngm_b200_contig {
+	uint64_t start;             /* SeqStart: concatenated coordinate of the first base */
+	uint32_t length;            /* SeqLen */
+	uint32_t name_len;
+	char name[100];             /* not NUL terminated when name_len == 100 */
+} ngm_b200_contig;
+
+typedef struct ngm_b200_encref {
+	uint64_t concat_len;        /* GetConcatRefLen() = binRefIndex - 1 (SequenceProvider.cpp:454-456) */
+	uint64_t packed_bytes;      /* encRefSize */
+	uint32_t n_contigs;
+	uint8_t *packed;            /* binRef: 4 bit/base, high nibble first, A0 T1 G2 C3 N4 */
+	ngm_b200_contig *contigs;
+} ngm_b200_encref;
+
+/* Read `<ref>-enc.2.ngm` as written by _SequenceProvider::writeEncRefToFile (SequenceProvider.cpp:189-208;
+ * cookie 0x74656).  Host only (no CUDA call).  Free with ngm_b200_free_enc_ref. */
+int ngm_b200_read_enc_ref(const char *path, ngm_b200_encref *out);
+void ngm_b200_free_enc_ref(ngm_b200_encref *ref);
+/* _SequenceProvider::convert (SequenceProvider.cpp:111-141): concatenated position -> (contig, position).
+ * Returns 1, or 0 when the position lies in the 1000-N spacer in front of the next contig (reported as
+ * unmapped by NGM). */
+int ngm_b200_convert(const ngm_b200_encref *ref, uint64_t concat_pos, uint32_t *contig, uint64_t *pos);
+
 /* -- device-pointer entry points (resident pipelines, bench.py `value`) --- */
 /* All pointers are device pointers on ctx's device; work is enqueued on `stream`
  * (a cudaStream_t passed as void*) and NOT synchronised.  d_pairs as above;

@@ -241,3 +241,40 @@ class CudaSW:
         o = int(r["str_off"])
         raw = heap.tobytes()
         return raw[o: o + int(r["cigar_len"])], raw[o + int(r["cigar_len"]): o + int(r["cigar_len"]) + int(r["md_len"])]
+
+
+# -- NGM's encoded-reference cache file --------------------------------------------------
+class _CContig(C.Structure):
+    _fields_ = [("start", C.c_uint64), ("length", C.c_uint32), ("name_len", C.c_uint32), ("name", C.c_char * 100)]
+
+
+class _CEncRef(C.Structure):
+    _fields_ = [("concat_len", C.c_uint64), ("packed_bytes", C.c_uint64), ("n_contigs", C.c_uint32), ("packed", C.POINTER(C.c_uint8)),
+                ("contigs", C.POINTER(_CContig))]
+
+
+class EncodedReference:
+    """`<ref>-enc.2.ngm` (SequenceProvider.cpp:189-208) + convert() (SequenceProvider.cpp:111-141).  Host only."""
+
+    def __init__(self, path: str):
+        self.lib = load_library()
+        self.lib.ngm_b200_read_enc_ref.argtypes = [C.c_char_p, C.POINTER(_CEncRef)]
+        self.lib.ngm_b200_free_enc_ref.argtypes = [C.POINTER(_CEncRef)]
+        self.lib.ngm_b200_convert.argtypes = [C.POINTER(_CEncRef), C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+        self.c = _CEncRef()
+        rc = self.lib.ngm_b200_read_enc_ref(str(path).encode(), C.byref(self.c))
+        if rc != 0:
+            raise NgmB200Error(f"cannot read encoded reference {path} (rc {rc})")
+        self.concat_len = int(self.c.concat_len)
+        self.packed = np.ctypeslib.as_array(self.c.packed, shape=(int(self.c.packed_bytes),)).copy()
+        self.contigs = [(self.c.contigs[i].name[: self.c.contigs[i].name_len].decode(), int(self.c.contigs[i].start), int(self.c.contigs[i].length))
+                        for i in range(int(self.c.n_contigs))]
+
+    def convert(self, concat_pos: int):
+        contig, pos = C.c_uint32(0), C.c_uint64(0)
+        ok = self.lib.ngm_b200_convert(C.byref(self.c), concat_pos, C.byref(contig), C.byref(pos))
+        return (int(contig.value), int(pos.value)) if ok else None
+
+    def close(self):
+        if self.c.packed:
+            self.lib.ngm_b200_free_enc_ref(C.byref(self.c))
