@@ -14,15 +14,21 @@ cudaError_t launch_align_s16(int capacity, int mode, const AlignArgs &a, cudaStr
 	if (capacity == W) { \
 		if constexpr (W <= kAlignS16MaxLocal) { \
 			if (mode == 0) { \
-				align_s16_fwd_kernel<W, LO, 0><<<grid, block, 0, st>>>(a.P, a.pairs, a.n, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, \
-						a.ptr_scratch, a.stride, a.best_scratch); \
+				align_s16_fwd_kernel<W, LO, 0, false><<<grid, block, 0, st>>>(a.P, a.pairs, a.n, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, \
+						a.ptr_scratch, a.stride, a.best_scratch, nullptr); \
+				launched = true; \
+			} \
+		} else if constexpr (W <= kAlignS16MaxKnown) { \
+			if (mode == 0 && a.known != nullptr) { \
+				align_s16_fwd_kernel<W, LO, 0, true><<<grid, block, 0, st>>>(a.P, a.pairs, a.n, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, \
+						a.ptr_scratch, a.stride, a.best_scratch, a.known); \
 				launched = true; \
 			} \
 		} \
 		if constexpr (W <= kAlignS16MaxEndFree) { \
 			if (mode == 1) { \
-				align_s16_fwd_kernel<W, LO, 1><<<grid, block, 0, st>>>(a.P, a.pairs, a.n, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, \
-						a.ptr_scratch, a.stride, a.best_scratch); \
+				align_s16_fwd_kernel<W, LO, 1, false><<<grid, block, 0, st>>>(a.P, a.pairs, a.n, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, \
+						a.ptr_scratch, a.stride, a.best_scratch, nullptr); \
 				launched = true; \
 			} \
 		} \

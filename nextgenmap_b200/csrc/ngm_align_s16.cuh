@@ -223,10 +223,15 @@ __device__ __forceinline__ void store_record(ngm_b200_align_rec *recs, int idx, 
 	reinterpret_cast<uint4 *>(recs)[2 * (size_t) idx + 1] = *(reinterpret_cast<const uint4 *>(&r) + 1);
 }
 
-template <int W, int LO, int MODE>
+// KNOWN = the local maximum of every pair is already known (`known`, the score kernel's output): the best
+// cell is then found by comparing each row's maximum with it and scanning the band once, in the first row that
+// reaches it; no band snapshot is kept, which halves the register footprint and lets wide bands (capacity
+// 56..96: `-C 40`, 400 bp reads) stay on the s16x2 path.
+template <int W, int LO, int MODE, bool KNOWN>
 __global__ void __launch_bounds__(128) align_s16_fwd_kernel(const __grid_constant__ DevParams P, const PairDesc *__restrict__ pairs, int n,
 		const uint32_t *__restrict__ reads_fwd, const uint32_t *__restrict__ reads_rev, const uint16_t *__restrict__ rlen,
-		const uint32_t *__restrict__ ref4, uint32_t *__restrict__ ptr_scratch, int stride, int4 *__restrict__ best_out) {
+		const uint32_t *__restrict__ ref4, uint32_t *__restrict__ ptr_scratch, int stride, int4 *__restrict__ best_out,
+		const float *__restrict__ known) {
 	using G = BandGeom<W>;
 	using T = TagGeom<W>;
 	__shared__ uint2 s_lut4[16];
@@ -253,13 +258,21 @@ __global__ void __launch_bounds__(128) align_s16_fwd_kernel(const __grid_constan
 	uint32_t *pbase = ptr_scratch + (size_t) t2;
 	HalfBest ba, bb;
 	{
-		uint32_t line[W + 1], snap[W];
+		uint32_t line[W + 1], snap[(MODE == 0 && !KNOWN) ? W : 1];
 #pragma unroll
 		for (int j = 0; j <= W; ++j) line[j] = (j < corridor) ? 0u : SENT2;
+		if (MODE == 0 && !KNOWN) {
 #pragma unroll
-		for (int j = 0; j < W; ++j) snap[j] = 0u;
+			for (int j = 0; j < W; ++j) snap[j] = 0u;
+		}
 		uint32_t best = 0;
 		int brow_a = 0, brow_b = 0, rc_a = 0, rc_b = 0;
+		int tgt_a = 0, tgt_b = 0, col_a = 0, col_b = 0;
+		bool found_a = false, found_b = false;
+		if (MODE == 0 && KNOWN) {
+			tgt_a = 4 * (int) known[ja];
+			tgt_b = 4 * (int) known[ib];
+		}
 		uint32_t wa[G::kWin], wb[G::kWin];
 		// "special" = a code other than A/C/G/T inside the read or inside the part of the window the band can
 		// touch: only then does a non-EQ diagonal step score something else than `mismatch`, and only then
@@ -323,7 +336,29 @@ __global__ void __launch_bounds__(128) align_s16_fwd_kernel(const __grid_constan
 #pragma unroll
 				for (int k = 0; k < T::kWords; ++k) prow[(size_t) k * tstride] = pw[k];
 				prow += row_stride;
-				if (MODE == 0) {
+				if (MODE == 0 && KNOWN) {
+					uint32_t mx = line[0];
+#pragma unroll
+					for (int j = 1; j + 1 < W; j += 2) mx = __vimax3_s16x2(mx, line[j], line[j + 1]);
+					if ((W & 1) == 0) mx = __vmaxs2(mx, line[W - 1]);
+					const bool hit_a = !found_a && tgt_a > 0 && (int) (short) (mx & 0xFFFFu) == tgt_a;
+					const bool hit_b = !found_b && tgt_b > 0 && (int) (short) (mx >> 16) == tgt_b;
+					if (hit_a || hit_b) {                             // once per alignment: first slot holding the maximum
+						bool fa_ = false, fb_ = false;
+#pragma unroll
+						for (int j = 0; j < W; ++j) {
+							const bool ha = hit_a && !fa_ && j < corridor && (int) (short) (line[j] & 0xFFFFu) == tgt_a;
+							const bool hb = hit_b && !fb_ && j < corridor && (int) (short) (line[j] >> 16) == tgt_b;
+							col_a = ha ? j : col_a;
+							col_b = hb ? j : col_b;
+							fa_ = fa_ || ha;
+							fb_ = fb_ || hb;
+						}
+						if (hit_a) { found_a = true; brow_a = rc_a; }
+						if (hit_b) { found_b = true; brow_b = rc_b; }
+					}
+				}
+				if (MODE == 0 && !KNOWN) {
 					uint32_t mx = line[0];
 #pragma unroll
 					for (int j = 1; j + 1 < W; j += 2) mx = __vimax3_s16x2(mx, line[j], line[j + 1]);
@@ -351,7 +386,14 @@ __global__ void __launch_bounds__(128) align_s16_fwd_kernel(const __grid_constan
 		}
 		ba.read_count = rc_a | ((spec_a & 0x44444444u) ? kSpecialFlag : 0);
 		bb.read_count = rc_b | ((spec_b & 0x44444444u) ? kSpecialFlag : 0);
-		if (MODE == 0) {
+		if (MODE == 0 && KNOWN) {
+			ba.best_read = found_a ? brow_a : 0;
+			ba.best_ref = found_a ? col_a : 0;
+			ba.best_score = found_a ? (tgt_a >> 2) : 0;
+			bb.best_read = found_b ? brow_b : 0;
+			bb.best_ref = found_b ? col_b : 0;
+			bb.best_score = found_b ? (tgt_b >> 2) : 0;
+		} else if (MODE == 0) {
 			const int ma = (int) (short) (best & 0xFFFFu), mb = (int) (short) (best >> 16);
 			int ra = 0, rb = 0;
 			bool fa_ = false, fb_ = false;

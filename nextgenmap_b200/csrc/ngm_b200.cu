@@ -101,7 +101,7 @@ struct ngm_b200_ctx {
 	HostBuf h_reads, h_refs, h_flags, h_scores, h_recs, h_strings, h_cursor, h_noncanon;
 	DevBuf d_areads, d_arefs, d_flags, d_reads4, d_rlen32, d_rlen, d_wins4, d_pairs, d_scores, d_recs, d_strings, d_cursor, d_noncanon;
 	// align scratch
-	DevBuf d_ptr, d_ops, d_best;
+	DevBuf d_ptr, d_ops, d_best, d_known;
 	// descriptor path
 	DevBuf d_ref4, d_rfwd, d_rrev, d_rrlen32, d_rrlen, d_rascii, d_upairs, d_rpairs;
 	uint64_t concat_len = 0, n_region_nib = 0;
@@ -297,6 +297,7 @@ int ensure_align_scratch(ngm_b200_ctx *c, int stride) {
 	const size_t ops_cap = 2 * (size_t) c->dp.qml + c->dp.corridor + 2;
 	CU(c->d_ops.ensure(ops_cap * stride * sizeof(uint16_t)));
 	CU(c->d_best.ensure((size_t) stride * sizeof(int4)));
+	CU(c->d_known.ensure((size_t) stride * sizeof(float)));
 	return NGM_B200_OK;
 }
 
@@ -319,6 +320,14 @@ int run_align(ngm_b200_ctx *c, int mode, const PairDesc *pairs, int n, const uin
 		a.ptr_scratch = c->d_ptr.as<uint32_t>();
 		a.ops_scratch = c->d_ops.as<uint16_t>();
 		a.best_scratch = c->d_best.as<int4>();
+		a.known = nullptr;
+		if (mode == 0 && c->align_s16[0] && c->capacity > kAlignS16MaxLocal) {
+			// wide band: get the local maxima from the (cheap) score kernel first, then run the snapshot-free forward pass
+			ScoreArgs sa = score_args(c, a.pairs, a.n, rf, rr, rl, ref4, c->d_known.as<float>());
+			int rc2 = run_score(c, 0, sa, st);
+			if (rc2) return rc2;
+			a.known = c->d_known.as<float>();
+		}
 		a.stride = stride_pad;
 		a.ops_cap = 2 * c->dp.qml + c->dp.corridor + 2;
 		a.recs = recs + s;
@@ -433,7 +442,7 @@ ngm_b200_ctx *ngm_b200_create(const ngm_b200_params *params) {
 	c->capacity = band_capacity(dp.corridor);
 	c->use_s16 = params->lane_mode == 1 ? 0 : (params->lane_mode == 2 ? 1 : use_s16);
 	for (int m = 0; m < 2; ++m) c->align_s16[m] = params->lane_mode == 1 ? 0 : align_s16[m];
-	if (c->capacity > kAlignS16MaxLocal) c->align_s16[0] = 0;
+	if (c->capacity > kAlignS16MaxKnown) c->align_s16[0] = 0;
 	if (c->capacity > kAlignS16MaxEndFree) c->align_s16[1] = 0;
 #ifndef NGM_HAVE_S16
 	c->use_s16 = 0;
@@ -470,7 +479,7 @@ void ngm_b200_destroy(ngm_b200_ctx *c) {
 	HostBuf *hb[] = { &c->h_reads, &c->h_refs, &c->h_flags, &c->h_scores, &c->h_recs, &c->h_strings, &c->h_cursor, &c->h_noncanon };
 	for (HostBuf *b : hb) b->release();
 	DevBuf *db[] = { &c->d_areads, &c->d_arefs, &c->d_flags, &c->d_reads4, &c->d_rlen32, &c->d_rlen, &c->d_wins4, &c->d_pairs, &c->d_scores,
-			&c->d_recs, &c->d_strings, &c->d_cursor, &c->d_ptr, &c->d_ops, &c->d_best, &c->d_ref4, &c->d_rfwd, &c->d_rrev, &c->d_rrlen32, &c->d_rrlen,
+			&c->d_recs, &c->d_strings, &c->d_cursor, &c->d_ptr, &c->d_ops, &c->d_best, &c->d_known, &c->d_ref4, &c->d_rfwd, &c->d_rrev, &c->d_rrlen32, &c->d_rrlen,
 			&c->d_rascii, &c->d_upairs, &c->d_rpairs, &c->d_noncanon };
 	for (DevBuf *b : db) b->release();
 	delete c;

@@ -20,6 +20,7 @@ namespace ngm {
 constexpr int kMaxCorridor = 160;
 // the tagged s16x2 align kernel keeps band + snapshot in registers: beyond these capacities it would spill
 constexpr int kAlignS16MaxLocal = 48;
+constexpr int kAlignS16MaxKnown = 96;     // local mode with the maximum known in advance (no snapshot)
 constexpr int kAlignS16MaxEndFree = 96;
 
 int band_capacity(int corridor);          // 0 if unsupported
@@ -45,6 +46,7 @@ struct AlignArgs {
 	uint32_t *ptr_scratch;
 	uint16_t *ops_scratch;
 	int4 *best_scratch;          // per alignment {best_read, best_ref, best_score, read_count} (s16 path)
+	const float *known;          // local maxima of the pairs (score kernel output) or nullptr
 	int stride, ops_cap;
 	ngm_b200_align_rec *recs;
 	char *strings;
