@@ -538,6 +538,14 @@ def main():
     dom_units = npairs if dominant == "score" else n
     alg_bytes = ALG_BYTES_SCORE * dom_units if dominant == "score" else (ALG_BYTES_SCORE + 8 + 2 * 4) * dom_units
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    # DRAM traffic of the dominant launch set from the committed ncu capture (bytes per unit x units of this run)
+    traffic = None
+    tf = ROOT / "profiles" / "traffic_r1.json"
+    if tf.exists() and L == READ_LEN and not args.corridor:
+        tj = json.loads(tf.read_text())
+        per_unit = tj["score_s16_kernel"]["dram_bytes_per_unit"] if dominant == "score" else (
+            tj["align_s16_fwd_kernel"]["dram_bytes_per_unit"] + tj["backtrace_format_kernel"]["dram_bytes_per_unit"])
+        traffic = per_unit * dom_units
     # integer-ALU roofline: SMs x 128 lanes x clock / 5 instr per cell, x2 for s16x2 lanes
     alu_peak_gcups = sm_count * 128 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 5 / 1e9
     score_gcups = npairs * CELLS_PER_PAIR / (ms_score * 1e-3) / 1e9
@@ -545,10 +553,12 @@ def main():
     line = {
         "metric": "reads/sec aligned (150bp SE vs 3Gbp ref)", "value": total_reads * args.steps / (ms_max * 1e-3), "unit": "reads/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "int16x2 (score) / int32 (align)", "data": "synthetic", "config": cfg,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int16x2", "data": "synthetic", "config": cfg,
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
-        "roofline": {"kernel": f"{dominant}_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "peak_source": peak_src, "ms_per_launch_set": dom_ms, "units_per_launch_set": dom_units,
+        "roofline": {"kernel": "score_s16_kernel" if dominant == "score" else "align_s16_fwd_kernel + backtrace_format_kernel (one launch set per 262144 alignments)",
+                     "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": traffic, "traffic_note": "dram bytes for the units of one step, from the ncu capture in profiles/traffic_r1.json; the pointer matrix (1.3 KB/alignment) makes it ~11x the algorithmic bytes and still only ~12 % of HBM peak",
+                     "peak_source": peak_src, "ms_per_launch_set": dom_ms, "units_per_launch_set": dom_units,
                      "algorithmic_bytes_per_unit": alg_bytes / dom_units,
                      "note": "integer DP: ~22 cells per algorithmic byte, so the HBM fraction is small by construction; the binding roofline is roofline_alu"},
         "roofline_alu": {"bound": "int-alu issue", "score_gcups": score_gcups, "align_gcups": align_gcups, "peak_gcups_int32": alu_peak_gcups,
