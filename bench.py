@@ -278,6 +278,7 @@ def main():
     d_best = torch.empty(n, dtype=torch.int32, device=dev)
     d_mapq = torch.empty(n, dtype=torch.int32, device=dev)
     d_wpairs = torch.empty((n, 16), dtype=torch.uint8, device=dev)
+    d_wscores = torch.empty(n, dtype=torch.float32, device=dev)
     d_recs = torch.empty((n, 32), dtype=torch.uint8, device=dev)
     STR_PER = 48 + int(L * args.sub_rate * 5) + (64 if args.indel_rate > 0.001 else 0)      # string-heap bytes per read
     str_cap = STR_PER * n
@@ -288,9 +289,11 @@ def main():
         check(lib.ngm_b200_dev_set_reads(ctx, batch.reads.data_ptr(), n, qml, st))
         check(lib.ngm_b200_dev_score_pairs(ctx, MODE_LOCAL, npairs, batch.pairs.data_ptr(), d_scores.data_ptr(), st))
         check(lib.ngm_b200_dev_select_top1(ctx, n, batch.cand_begin.data_ptr(), d_scores.data_ptr(), d_best.data_ptr(), d_mapq.data_ptr(), st))
-        check(lib.ngm_b200_dev_gather_winners(ctx, n, batch.pairs.data_ptr(), d_best.data_ptr(), d_wpairs.data_ptr(), st))
+        check(lib.ngm_b200_dev_gather_winners_scored(ctx, n, batch.pairs.data_ptr(), d_scores.data_ptr(), d_best.data_ptr(), d_wpairs.data_ptr(),
+                                                     d_wscores.data_ptr(), st))
         d_cursor.zero_()
-        check(lib.ngm_b200_dev_align_pairs(ctx, MODE_LOCAL, n, d_wpairs.data_ptr(), d_recs.data_ptr(), d_strings.data_ptr(), str_cap, d_cursor.data_ptr(), st))
+        check(lib.ngm_b200_dev_align_pairs_scored(ctx, MODE_LOCAL, n, d_wpairs.data_ptr(), d_wscores.data_ptr(), d_recs.data_ptr(), d_strings.data_ptr(),
+                                                  str_cap, d_cursor.data_ptr(), st))
 
     def barrier():
         if distributed:
@@ -335,7 +338,14 @@ def main():
 
     def align_only():
         d_cursor.zero_()
+        check(lib.ngm_b200_dev_align_pairs_scored(ctx, MODE_LOCAL, n, d_wpairs.data_ptr(), d_wscores.data_ptr(), d_recs.data_ptr(), d_strings.data_ptr(),
+                                                  str_cap, d_cursor.data_ptr(), st))
+
+    def align_unscored():
+        d_cursor.zero_()
         check(lib.ngm_b200_dev_align_pairs(ctx, MODE_LOCAL, n, d_wpairs.data_ptr(), d_recs.data_ptr(), d_strings.data_ptr(), str_cap, d_cursor.data_ptr(), st))
+
+    ms_align_unscored = time_call(align_unscored, reps=2)
 
     ms_align = time_call(align_only)
     ms_pack = time_call(lambda: check(lib.ngm_b200_dev_set_reads(ctx, batch.reads.data_ptr(), n, qml, st)))
@@ -377,6 +387,7 @@ def main():
                               pairs=torch.empty((max_pairs, 16), dtype=torch.uint8, device=dev), cb=torch.empty(SB + 1, dtype=torch.int32, device=dev),
                               scores=torch.empty(max_pairs, dtype=torch.float32, device=dev), best=torch.empty(SB, dtype=torch.int32, device=dev),
                               mapq=torch.empty(SB, dtype=torch.int32, device=dev), wpairs=torch.empty((SB, 16), dtype=torch.uint8, device=dev),
+                              wscores=torch.empty(SB, dtype=torch.float32, device=dev),
                               recs=torch.empty((SB, 32), dtype=torch.uint8, device=dev), strings=torch.empty(STR_PER * SB, dtype=torch.uint8, device=dev),
                               cursor=torch.zeros(1, dtype=torch.int32, device=dev), pending=None))
         torch.cuda.synchronize()
@@ -411,10 +422,11 @@ def main():
                     check(lib.ngm_b200_dev_set_reads(c_, lane["reads"].data_ptr(), m, qml, q_))
                     check(lib.ngm_b200_dev_score_pairs(c_, MODE_LOCAL, mp, lane["pairs"].data_ptr(), lane["scores"].data_ptr(), q_))
                     check(lib.ngm_b200_dev_select_top1(c_, m, lane["cb"].data_ptr(), lane["scores"].data_ptr(), lane["best"].data_ptr(), lane["mapq"].data_ptr(), q_))
-                    check(lib.ngm_b200_dev_gather_winners(c_, m, lane["pairs"].data_ptr(), lane["best"].data_ptr(), lane["wpairs"].data_ptr(), q_))
+                    check(lib.ngm_b200_dev_gather_winners_scored(c_, m, lane["pairs"].data_ptr(), lane["scores"].data_ptr(), lane["best"].data_ptr(),
+                                                                 lane["wpairs"].data_ptr(), lane["wscores"].data_ptr(), q_))
                     lane["cursor"].zero_()
-                    check(lib.ngm_b200_dev_align_pairs(c_, MODE_LOCAL, m, lane["wpairs"].data_ptr(), lane["recs"].data_ptr(), lane["strings"].data_ptr(),
-                                                       STR_PER * SB, lane["cursor"].data_ptr(), q_))
+                    check(lib.ngm_b200_dev_align_pairs_scored(c_, MODE_LOCAL, m, lane["wpairs"].data_ptr(), lane["wscores"].data_ptr(), lane["recs"].data_ptr(),
+                                                              lane["strings"].data_ptr(), STR_PER * SB, lane["cursor"].data_ptr(), q_))
                     h_recs[s: s + m].copy_(lane["recs"][:m], non_blocking=True)
                     h_mapq[s: s + m].copy_(lane["mapq"][:m], non_blocking=True)
                     h_used[k: k + 1].copy_(lane["cursor"], non_blocking=True)
@@ -565,7 +577,7 @@ def main():
                          "peak_gcups_s16x2": 2 * alu_peak_gcups, "score_frac_of_s16x2_peak": score_gcups / (2 * alu_peak_gcups),
                          "align_frac_of_int32_peak": align_gcups / alu_peak_gcups, "sm_count": sm_count, "sm_mhz_under_load": sm_mhz,
                          "definition": f"cells = L x corridor = {CELLS_PER_PAIR} per pair; peak = SMs x 128 lanes x max clock / 5 instr per cell (SURVEY 8d)"},
-        "kernel_ms": {"set_reads": ms_pack, "score": ms_score, "align": ms_align, "score_share": ms_score / (ms_max / args.steps),
+        "kernel_ms": {"set_reads": ms_pack, "score": ms_score, "align": ms_align, "align_without_known_scores": ms_align_unscored, "score_share": ms_score / (ms_max / args.steps),
                       "align_share": ms_align / (ms_max / args.steps)},
         "cpu_baseline": cpu_baseline, "parity_sample": parity, "strict_path": strict,
         "counters": {"reads": total_reads, "mapped": ctr["mapped"], "pairs_scored": ctr["pairs_scored"], "string_bytes": used_strings},

@@ -181,9 +181,21 @@ int ngm_b200_dev_set_reads(ngm_b200_ctx *ctx, const void *d_ascii_reads, int n_r
  * flagged NGM_B200_PAIR_SKIP when read r has no candidate (its record comes back with score -1). */
 int ngm_b200_dev_gather_winners(ngm_b200_ctx *ctx, int n_reads, const void *d_pairs, const void *d_best_pair, void *d_out_pairs,
 		void *stream);
+/* Same, and out_scores[r] = scores[best_pair[r]] (0 when read r has no candidate): the winners' BatchScore results,
+ * which ScoreBuffer keeps in LocationScore::Score.f (ScoreBuffer.cpp:151-153) and which
+ * ngm_b200_dev_align_pairs_scored takes back. */
+int ngm_b200_dev_gather_winners_scored(ngm_b200_ctx *ctx, int n_reads, const void *d_pairs, const void *d_scores,
+		const void *d_best_pair, void *d_out_pairs, void *d_out_scores, void *stream);
 int ngm_b200_dev_score_pairs(ngm_b200_ctx *ctx, int mode, int n, const void *d_pairs, void *d_scores, void *stream);
 int ngm_b200_dev_align_pairs(ngm_b200_ctx *ctx, int mode, int n, const void *d_pairs, void *d_recs, void *d_strings,
 		uint32_t str_capacity, void *d_str_cursor, void *stream);
+/* BatchAlign of pairs whose BatchScore result in the SAME mode is already known (d_pair_scores[i] = the float
+ * ngm_b200_dev_score_pairs returned for d_pairs[i]).  Wide bands (capacity > 48: `-C 40`, 400 bp reads) locate the
+ * best cell by comparing against that maximum and so skip their internal score pass; narrow bands ignore it (their
+ * snapshot kernel is faster).  Results are identical to ngm_b200_dev_align_pairs; on the wide-band path a score that
+ * is NOT the pair's true local maximum yields a failed record (score -1). */
+int ngm_b200_dev_align_pairs_scored(ngm_b200_ctx *ctx, int mode, int n, const void *d_pairs, const void *d_pair_scores,
+		void *d_recs, void *d_strings, uint32_t str_capacity, void *d_str_cursor, void *stream);
 /* Per-read top-1 selection over scored candidates (ScoreBuffer::top1SE + computeMQ,
  * ScoreBuffer.cpp:34-40,228-277).  cand_begin: n_reads+1 offsets into the pair/score arrays.
  * best_pair[r] = index of the winning pair or -1; mapq[r]. */

@@ -303,7 +303,8 @@ int ensure_align_scratch(ngm_b200_ctx *c, int stride) {
 
 // Launch the align kernel over n resolved pairs in slices of align_chunk.
 int run_align(ngm_b200_ctx *c, int mode, const PairDesc *pairs, int n, const uint32_t *rf, const uint32_t *rr, const uint16_t *rl,
-		const uint32_t *ref4, ngm_b200_align_rec *recs, char *strings, uint32_t str_cap, uint32_t *cursor, cudaStream_t st) {
+		const uint32_t *ref4, ngm_b200_align_rec *recs, char *strings, uint32_t str_cap, uint32_t *cursor, cudaStream_t st,
+		const float *known_user = nullptr) {
 	const int stride = std::min(std::max(n, 1), c->align_chunk);
 	const int stride_pad = (stride + 127) / 128 * 128;
 	int rc = ensure_align_scratch(c, stride_pad);
@@ -321,7 +322,11 @@ int run_align(ngm_b200_ctx *c, int mode, const PairDesc *pairs, int n, const uin
 		a.ops_scratch = c->d_ops.as<uint16_t>();
 		a.best_scratch = c->d_best.as<int4>();
 		a.known = nullptr;
-		if (mode == 0 && c->align_s16[0] && c->capacity > kAlignS16MaxLocal) {
+		if (mode == 0 && c->align_s16[0] && c->capacity > kAlignS16MaxLocal && known_user != nullptr) {
+			// wide band and the caller already holds the pairs' local maxima (the resident pipeline: BatchScore ran first).
+			// Narrow bands keep the snapshot kernel: measured faster there (19.5 vs 17.8 ms per 10 M x 150 bp, profiles/r1b).
+			a.known = known_user + s;
+		} else if (mode == 0 && c->align_s16[0] && c->capacity > kAlignS16MaxLocal) {
 			// wide band: get the local maxima from the (cheap) score kernel first, then run the snapshot-free forward pass
 			ScoreArgs sa = score_args(c, a.pairs, a.n, rf, rr, rl, ref4, c->d_known.as<float>());
 			int rc2 = run_score(c, 0, sa, st);
@@ -631,15 +636,28 @@ int ngm_b200_dev_set_reference(ngm_b200_ctx *c, const void *d_packed, uint64_t c
 	return transcode_reference(c, static_cast<const uint8_t *>(d_packed), concat_len, static_cast<cudaStream_t>(stream));
 }
 
-int ngm_b200_dev_gather_winners(ngm_b200_ctx *c, int n_reads, const void *d_pairs, const void *d_best_pair, void *d_out_pairs, void *stream) {
+static int gather_winners(ngm_b200_ctx *c, int n_reads, const void *d_pairs, const void *d_scores, const void *d_best_pair, void *d_out_pairs,
+		void *d_out_scores, void *stream) {
 	if (c == nullptr || d_pairs == nullptr || d_best_pair == nullptr || d_out_pairs == nullptr) return fail(NGM_B200_EINVAL, "NULL argument");
+	if ((d_scores == nullptr) != (d_out_scores == nullptr)) return fail(NGM_B200_EINVAL, "d_scores and d_out_scores go together");
 	if (n_reads <= 0) return 0;
 	CU(cudaSetDevice(c->device));
 	gather_winners_kernel<<<(n_reads + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(n_reads, static_cast<const ngm_b200_pair *>(d_pairs),
-			static_cast<const int *>(d_best_pair), static_cast<ngm_b200_pair *>(d_out_pairs));
+			static_cast<const int *>(d_best_pair), static_cast<ngm_b200_pair *>(d_out_pairs), static_cast<const float *>(d_scores),
+			static_cast<float *>(d_out_scores));
 	c->launches += 1;
 	CU(cudaGetLastError());
 	return n_reads;
+}
+
+int ngm_b200_dev_gather_winners(ngm_b200_ctx *c, int n_reads, const void *d_pairs, const void *d_best_pair, void *d_out_pairs, void *stream) {
+	return gather_winners(c, n_reads, d_pairs, nullptr, d_best_pair, d_out_pairs, nullptr, stream);
+}
+
+int ngm_b200_dev_gather_winners_scored(ngm_b200_ctx *c, int n_reads, const void *d_pairs, const void *d_scores, const void *d_best_pair,
+		void *d_out_pairs, void *d_out_scores, void *stream) {
+	if (d_scores == nullptr || d_out_scores == nullptr) return fail(NGM_B200_EINVAL, "NULL argument");
+	return gather_winners(c, n_reads, d_pairs, d_scores, d_best_pair, d_out_pairs, d_out_scores, stream);
 }
 
 int ngm_b200_set_reference(ngm_b200_ctx *c, const uint8_t *packed, uint64_t concat_len) {
@@ -717,8 +735,8 @@ int ngm_b200_dev_score_pairs(ngm_b200_ctx *c, int mode, int n, const void *d_pai
 	return rc ? rc : n;
 }
 
-int ngm_b200_dev_align_pairs(ngm_b200_ctx *c, int mode, int n, const void *d_pairs, void *d_recs, void *d_strings, uint32_t str_capacity,
-		void *d_str_cursor, void *stream) {
+static int dev_align_pairs(ngm_b200_ctx *c, int mode, int n, const void *d_pairs, const void *d_pair_scores, void *d_recs, void *d_strings,
+		uint32_t str_capacity, void *d_str_cursor, void *stream) {
 	if (c == nullptr || d_pairs == nullptr || d_recs == nullptr || d_strings == nullptr || d_str_cursor == nullptr)
 		return fail(NGM_B200_EINVAL, "NULL argument");
 	if (n <= 0) return 0;
@@ -730,8 +748,19 @@ int ngm_b200_dev_align_pairs(ngm_b200_ctx *c, int mode, int n, const void *d_pai
 	if (rc) return rc;
 	rc = run_align(c, m0, c->d_rpairs.as<PairDesc>(), n, c->d_rfwd.as<uint32_t>(), c->d_rrev.as<uint32_t>(), c->d_rrlen.as<uint16_t>(),
 			c->d_ref4.as<uint32_t>(), static_cast<ngm_b200_align_rec *>(d_recs), static_cast<char *>(d_strings), str_capacity,
-			static_cast<uint32_t *>(d_str_cursor), st);
+			static_cast<uint32_t *>(d_str_cursor), st, static_cast<const float *>(d_pair_scores));
 	return rc ? rc : n;
+}
+
+int ngm_b200_dev_align_pairs(ngm_b200_ctx *c, int mode, int n, const void *d_pairs, void *d_recs, void *d_strings, uint32_t str_capacity,
+		void *d_str_cursor, void *stream) {
+	return dev_align_pairs(c, mode, n, d_pairs, nullptr, d_recs, d_strings, str_capacity, d_str_cursor, stream);
+}
+
+int ngm_b200_dev_align_pairs_scored(ngm_b200_ctx *c, int mode, int n, const void *d_pairs, const void *d_pair_scores, void *d_recs,
+		void *d_strings, uint32_t str_capacity, void *d_str_cursor, void *stream) {
+	if (d_pair_scores == nullptr) return fail(NGM_B200_EINVAL, "NULL argument");
+	return dev_align_pairs(c, mode, n, d_pairs, d_pair_scores, d_recs, d_strings, str_capacity, d_str_cursor, stream);
 }
 
 int ngm_b200_dev_select_top1(ngm_b200_ctx *c, int n_reads, const void *d_cand_begin, const void *d_scores, void *d_best_pair, void *d_mapq,

@@ -204,19 +204,22 @@ __global__ void resolve_pairs_kernel(const ngm_b200_pair *__restrict__ in, PairD
 }
 
 __global__ void gather_winners_kernel(int n_reads, const ngm_b200_pair *__restrict__ pairs, const int *__restrict__ best_pair,
-		ngm_b200_pair *__restrict__ out) {
+		ngm_b200_pair *__restrict__ out, const float *__restrict__ scores, float *__restrict__ out_scores) {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= n_reads) return;
 	const int b = best_pair[r];
 	ngm_b200_pair p;
+	float s = 0.0f;
 	if (b >= 0) {
 		p = pairs[b];
+		if (scores != nullptr) s = scores[b];
 	} else {
 		p.window_start = 0;
 		p.read_index = (uint32_t) r;
 		p.flags = PF_INACTIVE;
 	}
 	out[r] = p;
+	if (out_scores != nullptr) out_scores[r] = s;
 }
 
 // ScoreBuffer::top1SE + computeMQ (ScoreBuffer.cpp:34-40,228-277); one thread per read.

@@ -161,3 +161,58 @@ def test_select_top1_matches_host_rule():
         want_best = begin[r] + bi if counts[r] else -1
         assert (best[r], mq[r]) == (want_best, want_mq), r
     sw.close()
+
+
+@pytest.mark.parametrize("qml,cor", [(152, 27), (76, 16), (252, 42), (402, 65)])
+def test_scored_align_equals_plain_align(qml, cor):
+    """Resident pipeline: score -> top1 -> gather_winners_scored -> align_pairs_scored (the winners' known local maxima
+    steer the forward pass) must give the records and strings of the plain align_pairs call."""
+    import torch
+    from nextgenmap_b200.host import CudaSW
+    from nextgenmap_b200.host.cuda_sw import ALIGN_REC
+    concat, packed, reads, pairs = build_case(99 + qml, 3000, qml, cor)
+    sw = CudaSW(qml, cor)
+    sw.set_reference(packed, len(concat))
+    sw.set_reads(reads)
+    n_reads = len(reads)
+    begin = np.searchsorted(pairs["read_index"], np.arange(n_reads + 1)).astype(np.int32)
+    dev = torch.device("cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    d_pairs = torch.from_numpy(pairs.view(np.uint8).reshape(-1, 16)).to(dev)
+    d_begin = torch.from_numpy(begin).to(dev)
+    d_scores = torch.empty(len(pairs), dtype=torch.float32, device=dev)
+    d_best = torch.empty(n_reads, dtype=torch.int32, device=dev)
+    d_mq = torch.empty(n_reads, dtype=torch.int32, device=dev)
+    d_wp = torch.empty((n_reads, 16), dtype=torch.uint8, device=dev)
+    d_ws = torch.empty(n_reads, dtype=torch.float32, device=dev)
+    lib, ctx = sw.lib, sw.ctx
+    assert lib.ngm_b200_dev_score_pairs(ctx, 0, len(pairs), d_pairs.data_ptr(), d_scores.data_ptr(), st) == len(pairs)
+    assert lib.ngm_b200_dev_select_top1(ctx, n_reads, d_begin.data_ptr(), d_scores.data_ptr(), d_best.data_ptr(), d_mq.data_ptr(), st) == n_reads
+    assert lib.ngm_b200_dev_gather_winners_scored(ctx, n_reads, d_pairs.data_ptr(), d_scores.data_ptr(), d_best.data_ptr(), d_wp.data_ptr(),
+                                                  d_ws.data_ptr(), st) == n_reads
+    out = []
+    for scored in (False, True):
+        d_recs = torch.zeros((n_reads, 32), dtype=torch.uint8, device=dev)
+        cap = 256 * n_reads
+        d_str = torch.zeros(cap, dtype=torch.uint8, device=dev)
+        d_cur = torch.zeros(1, dtype=torch.int32, device=dev)
+        if scored:
+            rc = lib.ngm_b200_dev_align_pairs_scored(ctx, 0, n_reads, d_wp.data_ptr(), d_ws.data_ptr(), d_recs.data_ptr(), d_str.data_ptr(), cap,
+                                                     d_cur.data_ptr(), st)
+        else:
+            rc = lib.ngm_b200_dev_align_pairs(ctx, 0, n_reads, d_wp.data_ptr(), d_recs.data_ptr(), d_str.data_ptr(), cap, d_cur.data_ptr(), st)
+        assert rc == n_reads, sw._err()
+        torch.cuda.synchronize()
+        assert int(d_cur.item()) <= cap
+        recs = d_recs.cpu().numpy().view(ALIGN_REC).reshape(-1)
+        heap = d_str.cpu().numpy()
+        out.append([(int(r["position_offset"]), int(r["qstart"]), int(r["qend"]), int(r["nm"]), util.bits(np.array([r["identity"]]))[0],
+                     float(r["score"])) + sw.strings_of(recs, heap, i) for i, r in enumerate(recs)])
+    ws = d_ws.cpu().numpy()
+    best = d_best.cpu().numpy()
+    sc = d_scores.cpu().numpy()
+    assert np.array_equal(ws[best >= 0], sc[best[best >= 0]])
+    bad = [(i, a, b) for i, (a, b) in enumerate(zip(*out)) if a != b]
+    assert not bad, f"{len(bad)} differ, first {bad[0]}"
+    assert sum(1 for a in out[0] if a[5] >= 0) > n_reads // 2
+    sw.close()
