@@ -1,0 +1,87 @@
+"""Candidate search: the C restatement (oracle/cs_oracle.c) against what the UNMODIFIED reference produced --
+committed fixtures (tests/golden/cs, made by tests/golden/make_cs_golden.py) and, where oracle/_ref/ngm/ngm_cs_probe
+exists, a fresh differential run."""
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import cs_port, port
+from tests import cs_cases
+
+GOLD = Path(__file__).resolve().parent / "golden" / "cs"
+NAMES = sorted(p.stem for p in GOLD.glob("*.npz"))
+
+
+def load(name):
+    with np.load(GOLD / f"{name}.npz") as z:
+        return {k: z[k] for k in z.files}
+
+
+def golden_lists(g):
+    out = {}
+    for i, r in enumerate(g["read_index"]):
+        b, e = int(g["cand_begin"][i]), int(g["cand_begin"][i + 1])
+        out[int(r)] = (float(g["max_hit"][i]), [(int(g["cand_loc"][j]), int(g["cand_rev"][j]), float(g["cand_votes"][j])) for j in range(b, e)])
+    return out
+
+
+def oracle_lists(ix, reads, sens, max_kfreq):
+    begin, cands, mh = ix.search(reads, sens, max_kfreq=max_kfreq)
+    return {r: (float(mh[r]), [(int(c["location"]), int(c["reverse"]), float(c["score"])) for c in cands[begin[r]: begin[r + 1]]])
+            for r in range(reads.shape[0])}
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_index_and_candidates_match_reference_fixture(name):
+    g = load(name)
+    k = int(g["k"])
+    concat = g["concat"].tobytes()
+    ctg = [(int(a), int(b)) for a, b in g["contigs"]]
+    ix = cs_port.Index(port.pack_ref(concat), len(concat) - 1, ctg, k=k)
+    # the prefix table the reference wrote: used prefixes, their weights, list lengths and the whole position table
+    used = np.nonzero(ix.weight != 0)[0].astype(np.uint32)
+    np.testing.assert_array_equal(used, g["ht_used_prefix"])
+    np.testing.assert_array_equal(ix.weight[used], g["ht_used_weight"])
+    np.testing.assert_array_equal(ix.tab[used + 1] - ix.tab[used], g["ht_used_count"])
+    assert ix.table_len == int(g["ht_table_len"]) and ix.max_kfreq == int(g["max_kfreq"])
+    np.testing.assert_array_equal(ix.table, g["ht_table"])
+    want = golden_lists(g)
+    got = oracle_lists(ix, g["reads"], float(g["sensitivity"]), int(g["max_kfreq"]))
+    bad = [(r, want[r], got[r]) for r in want if want[r] != got[r]]
+    assert not bad, f"{len(bad)} reads differ, first {bad[0]}"
+    assert sum(1 for r in want if len(want[r][1]) > 1) > 10       # the order of multi-candidate lists is part of the check
+    ix.close()
+
+
+@pytest.mark.skipif(not cs_port.probe_available(), reason="oracle/_ref/ngm/ngm_cs_probe not built")
+@pytest.mark.parametrize("seed,k,read_len,sens", [(7, 10, 75, 0.5), (8, 11, 120, 0.9)])
+def test_fresh_differential_run_against_reference(seed, k, read_len, sens):
+    contigs = cs_cases.make_reference(seed)
+    concat, ctg, concat_len = cs_port.layout(contigs)
+    reads = cs_cases.make_reads(seed + 1, concat, ctg, 600, read_len, (read_len | 1) + 1)
+    with tempfile.TemporaryDirectory(prefix="csdiff_") as td:
+        d = Path(td)
+        cs_cases.write_fasta(d / "ref.fa", contigs)
+        cs_cases.write_fastq(d / "reads.fq", reads)
+        head, rows = cs_port.run_probe(d, "ref.fa", "reads.fq", sens, k=k)
+        ht = cs_port.read_ht_file(d / f"ref.fa-ht-{k}-2.3.ngm")
+    ix = cs_port.Index(port.pack_ref(concat), concat_len, ctg, k=k)
+    np.testing.assert_array_equal(ix.tab, ht["tab"])
+    np.testing.assert_array_equal(ix.weight, ht["weight"])
+    np.testing.assert_array_equal(ix.table, ht["table"])
+    assert ix.max_kfreq == head["max_kfreq"]
+    got = oracle_lists(ix, reads, sens, head["max_kfreq"])
+    for (rid, name, ln, mh, cl) in rows:
+        r = int(name[1:])
+        assert got[r] == (mh, cl), (r, got[r], (mh, cl))
+    ix.close()
+
+
+def test_revcomp_prefix():
+    # A0 C1 T2 G3: ACGTT -> revcomp AACGT
+    enc = {"A": 0, "C": 1, "T": 2, "G": 3}
+    code = lambda s: sum(enc[c] << (2 * (len(s) - 1 - i)) for i, c in enumerate(s))
+    assert cs_port.revcomp_prefix(code("ACGTT"), 5) == code("AACGT")
+    assert cs_port.revcomp_prefix(code("ACGTTGCATGCAA"), 13) == code("TTGCATGCAACGT")
