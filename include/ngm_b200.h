@@ -169,6 +169,55 @@ void ngm_b200_free_enc_ref(ngm_b200_encref *ref);
  * unmapped by NGM). */
 int ngm_b200_convert(const ngm_b200_encref *ref, uint64_t concat_pos, uint32_t *contig, uint64_t *pos);
 
+/* -- candidate search: k-mer index + per-read vote --------------------------------- */
+/* The Config keys CS / CompactPrefixTable read (src/config/Config.cpp:383-390,512-518; CS.cpp:476-481,563-570). */
+typedef struct ngm_b200_cs_params {
+	int32_t kmer;               /* "kmer" (13); 8..14 */
+	int32_t kmer_skip;          /* "kmer_skip" (2): every (kmer_skip+1)-th reference position is indexed */
+	int32_t bin_size;           /* "bin_size" (2): votes are collected per 2^bin_size reference positions */
+	int32_t skip_rep;           /* CompactPrefixTable(dualStrand, skip = true): drop repeated k-mers inside one bin (1) */
+	float sensitivity;          /* "sensitivity" (-s; estimated or 0.5): threshold = sensitivity x best vote */
+	float kmer_min;             /* "kmer_min" (0) */
+	int32_t max_kfreq;          /* "max_kfreq": 0 = derive like CompactPrefixTable::stats (ceil(max(100, mean + 5 sd))) */
+	int32_t max_cmrs;           /* "max_cmrs": 0 = INT_MAX; reads with that many candidates keep none */
+} ngm_b200_cs_params;
+
+/* Build the prefix table of CompactPrefixTable (PrefixTable.cpp:196-245,357-498,577-738) on the device from the
+ * reference given to ngm_b200_set_reference / ngm_b200_dev_set_reference.  contigs: host array (SeqStart, SeqLen) as in
+ * <ref>-enc.2.ngm.  Synchronous.  Single table unit: the concatenated reference must be shorter than 2^32 - 1. */
+int ngm_b200_cs_build_index(ngm_b200_ctx *ctx, const ngm_b200_cs_params *params, const ngm_b200_contig *contigs, uint32_t n_contigs);
+/* Upload a prefix table read from NGM's cache file `<ref>-ht-<kmer>-<kmer_skip>.3.ngm` (see ngm_b200_read_ht_file):
+ * tab = Index::m_TabIndex, weight = Index::m_RevCompIndex (index_len = 4^kmer + 1 entries), table = Location::m_Location. */
+int ngm_b200_cs_load_index(ngm_b200_ctx *ctx, const ngm_b200_cs_params *params, const uint32_t *tab, const int8_t *weight,
+		uint32_t index_len, const uint32_t *table, uint32_t table_len);
+int ngm_b200_cs_index_info(const ngm_b200_ctx *ctx, uint32_t *index_len, uint32_t *table_len, int32_t *max_kfreq);
+/* Copy the device index back in the file's representation (tab: index_len entries, weight: index_len, table: table_len). */
+int ngm_b200_cs_export_index(ngm_b200_ctx *ctx, uint32_t *tab, int8_t *weight, uint32_t *table);
+
+/* NGM's prefix-table cache file (CompactPrefixTable::saveToFile / readFromFile, PrefixTable.cpp:819-921). Host only. */
+typedef struct ngm_b200_htfile {
+	uint32_t kmer, kmer_skip, index_len, table_len;
+	uint32_t *tab;              /* index_len entries */
+	int8_t *weight;             /* index_len entries */
+	uint32_t *table;            /* table_len entries */
+	uint64_t unit_offset;
+} ngm_b200_htfile;
+int ngm_b200_read_ht_file(const char *path, ngm_b200_htfile *out);
+void ngm_b200_free_ht_file(ngm_b200_htfile *ht);
+int ngm_b200_write_ht_file(const char *path, const ngm_b200_htfile *ht);
+
+/* Candidate search for n_reads rows of `stride` ASCII bytes (NUL padded, like MappedRead::Seq): CS::RunBatch without
+ * the bs-mapping k-mer mutation (CS.cpp:340-436).  cand_begin: n_reads + 1 offsets; pairs[cand_begin[r] .. cand_begin[r+1])
+ * are read r's candidates in the reference's order as descriptors for ngm_b200_score_pairs (window_start =
+ * Location - corridor/2, flags = REVERSE|DIR for minus-strand candidates, ScoreBuffer.cpp:92-114); votes = LocationScore
+ * Score.f; max_hit (optional) = MappedRead::s.  *total receives the number of candidates; if it exceeds `capacity` the
+ * call returns NGM_B200_ERANGE and must be repeated with larger buffers.  mode_flags bit 0: use only the sequential
+ * exact kernel (testing). */
+int ngm_b200_cs_search(ngm_b200_ctx *ctx, const char *reads, int n_reads, int stride, int mode_flags, int32_t *cand_begin,
+		ngm_b200_pair *pairs, float *votes, size_t capacity, size_t *total, float *max_hit);
+/* Reads the last ngm_b200_cs_search call routed to the exact kernel. */
+uint64_t ngm_b200_cs_exact_reads(const ngm_b200_ctx *ctx);
+
 /* -- device-pointer entry points (resident pipelines, bench.py `value`) --- */
 /* All pointers are device pointers on ctx's device; work is enqueued on `stream`
  * (a cudaStream_t passed as void*) and NOT synchronised.  d_pairs as above;
@@ -201,6 +250,10 @@ int ngm_b200_dev_align_pairs_scored(ngm_b200_ctx *ctx, int mode, int n, const vo
  * best_pair[r] = index of the winning pair or -1; mapq[r]. */
 int ngm_b200_dev_select_top1(ngm_b200_ctx *ctx, int n_reads, const void *d_cand_begin, const void *d_scores,
 		void *d_best_pair, void *d_mapq, void *stream);
+/* Device-pointer form of ngm_b200_cs_search: enqueued on `stream`, not synchronised; the caller checks
+ * cand_begin[n_reads] <= capacity afterwards.  d_votes / d_max_hit may be NULL. */
+int ngm_b200_dev_cs_search(ngm_b200_ctx *ctx, const void *d_ascii_reads, int n_reads, int stride, int mode_flags, void *d_cand_begin,
+		void *d_pairs, void *d_votes, uint32_t capacity, void *d_max_hit, void *stream);
 /* Number of kernels this context has launched since creation (bench.py gpu_launches). */
 uint64_t ngm_b200_launch_count(const ngm_b200_ctx *ctx);
 

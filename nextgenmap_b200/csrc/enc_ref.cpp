@@ -88,3 +88,76 @@ extern "C" __attribute__((visibility("default"))) int ngm_b200_convert(const ngm
 	if (pos) *pos = concat_pos - ref->contigs[upper - 1].start;
 	return 1;
 }
+
+// ---- prefix-table cache file `<ref>-ht-<k>-<skip>.3.ngm` (PrefixTable.cpp:819-921) --------------------
+// layout: cookie 0x74656, kmer, kmer_skip, unit count, index size; per unit: cRefTableLen, Index[index size] (packed
+// {uint32 m_TabIndex; char m_RevCompIndex}, PrefixTable.h:17-33), Location[cRefTableLen], uint64 Offset; then the
+// signature cookie + kmer + kmer_skip + units + index size.
+extern "C" __attribute__((visibility("default"))) int ngm_b200_read_ht_file(const char *path, ngm_b200_htfile *out) {
+	if (path == nullptr || out == nullptr) return NGM_B200_EINVAL;
+	memset(out, 0, sizeof(*out));
+	FILE *fp = fopen(path, "rb");
+	if (fp == nullptr) return NGM_B200_EINVAL;
+	uint32_t hdr[5];
+	int rc = NGM_B200_EINVAL;
+	uint8_t *raw = nullptr;
+	do {
+		if (fread(hdr, 4, 5, fp) != 5 || hdr[0] != kRefEncCookie || hdr[3] != 1) break;      // one table unit (< 4 Gbp)
+		out->kmer = hdr[1];
+		out->kmer_skip = hdr[2];
+		out->index_len = hdr[4];
+		if (fread(&out->table_len, 4, 1, fp) != 1) break;
+		const size_t n = out->index_len;
+		raw = (uint8_t *) malloc(n * 5);
+		out->tab = (uint32_t *) malloc(n * 4);
+		out->weight = (int8_t *) malloc(n);
+		out->table = (uint32_t *) malloc((size_t) out->table_len * 4 + 4);
+		if (!raw || !out->tab || !out->weight || !out->table) break;
+		if (fread(raw, 5, n, fp) != n) break;
+		for (size_t i = 0; i < n; ++i) {
+			memcpy(&out->tab[i], raw + 5 * i, 4);
+			out->weight[i] = (int8_t) raw[5 * i + 4];
+		}
+		if (fread(out->table, 4, out->table_len, fp) != out->table_len) break;
+		uint32_t sig = 0;
+		if (fread(&out->unit_offset, 8, 1, fp) != 1 || fread(&sig, 4, 1, fp) != 1) break;
+		if (sig != hdr[0] + hdr[1] + hdr[2] + hdr[3] + hdr[4]) break;
+		rc = NGM_B200_OK;
+	} while (false);
+	free(raw);
+	fclose(fp);
+	if (rc != NGM_B200_OK) ngm_b200_free_ht_file(out);
+	return rc;
+}
+
+extern "C" __attribute__((visibility("default"))) void ngm_b200_free_ht_file(ngm_b200_htfile *ht) {
+	if (ht == nullptr) return;
+	free(ht->tab);
+	free(ht->weight);
+	free(ht->table);
+	memset(ht, 0, sizeof(*ht));
+}
+
+extern "C" __attribute__((visibility("default"))) int ngm_b200_write_ht_file(const char *path, const ngm_b200_htfile *ht) {
+	if (path == nullptr || ht == nullptr || ht->tab == nullptr || ht->weight == nullptr) return NGM_B200_EINVAL;
+	FILE *fp = fopen(path, "wb");
+	if (fp == nullptr) return NGM_B200_EINVAL;
+	const uint32_t hdr[5] = { kRefEncCookie, ht->kmer, ht->kmer_skip, 1u, ht->index_len };
+	bool ok = fwrite(hdr, 4, 5, fp) == 5 && fwrite(&ht->table_len, 4, 1, fp) == 1;
+	const size_t n = ht->index_len;
+	uint8_t *raw = (uint8_t *) malloc(n * 5);
+	ok = ok && raw != nullptr;
+	if (ok) {
+		for (size_t i = 0; i < n; ++i) {
+			memcpy(raw + 5 * i, &ht->tab[i], 4);
+			raw[5 * i + 4] = (uint8_t) ht->weight[i];
+		}
+		ok = fwrite(raw, 5, n, fp) == n;
+	}
+	free(raw);
+	ok = ok && (ht->table_len == 0 || fwrite(ht->table, 4, ht->table_len, fp) == ht->table_len);
+	const uint32_t sig = hdr[0] + hdr[1] + hdr[2] + hdr[3] + hdr[4];
+	ok = ok && fwrite(&ht->unit_offset, 8, 1, fp) == 1 && fwrite(&sig, 4, 1, fp) == 1;
+	fclose(fp);
+	return ok ? NGM_B200_OK : NGM_B200_EINVAL;
+}

@@ -14,14 +14,15 @@
 #include <new>
 #include <vector>
 
+#include "ngm_ctx.h"
 #include "ngm_launch.h"
 #include "ngm_misc.cuh"
 
 using namespace ngm;
 
-namespace {
+namespace ngm {
 
-thread_local char g_err[512] = "";
+static thread_local char g_err[512] = "";
 
 int fail(int code, const char *fmt, ...) {
 	va_list ap;
@@ -31,83 +32,15 @@ int fail(int code, const char *fmt, ...) {
 	return code;
 }
 
-#define CU(call) \
-	do { \
-		cudaError_t e_ = (call); \
-		if (e_ != cudaSuccess) return fail(NGM_B200_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-	} while (0)
+const char *last_error_text() { return g_err; }
 
-struct DevBuf {
-	void *p = nullptr;
-	size_t cap = 0;
-	cudaError_t ensure(size_t bytes) {
-		if (bytes <= cap) return cudaSuccess;
-		if (p) cudaFree(p);
-		p = nullptr;
-		cap = 0;
-		size_t want = bytes + bytes / 8 + 256;
-		cudaError_t e = cudaMalloc(&p, want);
-		if (e == cudaSuccess) cap = want;
-		return e;
-	}
-	void release() {
-		if (p) cudaFree(p);
-		p = nullptr;
-		cap = 0;
-	}
-	template <typename T> T *as() const { return static_cast<T *>(p); }
-};
+}  // namespace ngm
 
-struct HostBuf {   // pinned
-	void *p = nullptr;
-	size_t cap = 0;
-	cudaError_t ensure(size_t bytes) {
-		if (bytes <= cap) return cudaSuccess;
-		if (p) cudaFreeHost(p);
-		p = nullptr;
-		cap = 0;
-		size_t want = bytes + bytes / 8 + 256;
-		cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
-		if (e == cudaSuccess) cap = want;
-		return e;
-	}
-	void release() {
-		if (p) cudaFreeHost(p);
-		p = nullptr;
-		cap = 0;
-	}
-	template <typename T> T *as() const { return static_cast<T *>(p); }
-};
+namespace {
 
 bool is_int(float v) { return std::floor(v) == v && std::fabs(v) < 1e6f; }
 
 }  // namespace
-
-struct ngm_b200_ctx {
-	ngm_b200_params hp;
-	DevParams dp;
-	int device = 0;
-	int capacity = 0;          // band capacity W
-	int use_s16 = 0;           // s16x2 lanes allowed for the score kernels
-	int align_s16[2] = {0, 0}; // tagged s16x2 align kernel usable in local / end-free mode
-	int score_batch = 0, align_batch = 0;
-	int strict_chunk = 0;      // pairs per strict-path launch
-	int align_chunk = 0;       // alignments per launch (bounded by scratch memory)
-	int win_words = 0;         // strict path: packed words per window
-	int ref_width = 0;         // qml + corridor bytes copied per window (SWOcl.cpp:546)
-	cudaStream_t stream = nullptr;
-	uint64_t launches = 0;
-	// strict-path staging
-	HostBuf h_reads, h_refs, h_flags, h_scores, h_recs, h_strings, h_cursor, h_noncanon;
-	DevBuf d_areads, d_arefs, d_flags, d_reads4, d_rlen32, d_rlen, d_wins4, d_pairs, d_scores, d_recs, d_strings, d_cursor, d_noncanon;
-	// align scratch
-	DevBuf d_ptr, d_ops, d_best, d_known;
-	// descriptor path
-	DevBuf d_ref4, d_rfwd, d_rrev, d_rrlen32, d_rrlen, d_rascii, d_upairs, d_rpairs;
-	uint64_t concat_len = 0, n_region_nib = 0;
-	int n_reads = 0;
-	bool have_ref = false;
-};
 
 namespace {
 
@@ -409,7 +342,7 @@ extern "C" {
 
 int ngm_b200_abi_version(void) { return NGM_B200_ABI_VERSION; }
 
-const char *ngm_b200_last_error(void) { return g_err; }
+const char *ngm_b200_last_error(void) { return ngm::last_error_text(); }
 
 int ngm_b200_device_count(void) {
 	int n = 0;
@@ -487,6 +420,7 @@ void ngm_b200_destroy(ngm_b200_ctx *c) {
 			&c->d_recs, &c->d_strings, &c->d_cursor, &c->d_ptr, &c->d_ops, &c->d_best, &c->d_known, &c->d_ref4, &c->d_rfwd, &c->d_rrev, &c->d_rrlen32, &c->d_rrlen,
 			&c->d_rascii, &c->d_upairs, &c->d_rpairs, &c->d_noncanon };
 	for (DevBuf *b : db) b->release();
+	if (c->cs) cs_release(c->cs);
 	delete c;
 }
 
@@ -700,6 +634,7 @@ int ngm_b200_set_reads(ngm_b200_ctx *c, const char *reads, int n_reads, int stri
 	CU(cudaMemcpyAsync(c->d_rascii.p, reads, (size_t) n_reads * stride, cudaMemcpyHostToDevice, c->stream));
 	int rc = pack_reads_device(c, c->d_rascii.as<uint8_t>(), n_reads, stride, c->stream);
 	if (rc) return rc;
+	c->reads_stride = stride;
 	CU(cudaStreamSynchronize(c->stream));
 	return NGM_B200_OK;
 }

@@ -1,0 +1,439 @@
+// ngm_cs.cu -- host side of the candidate-search entry points of include/ngm_b200.h.
+//
+// Index construction follows CompactPrefixTable (src/PrefixTable.cpp:196-245,357-498,577-690) for one table unit:
+// the k-mer walk of CS::PrefixIteration (src/CSstatic.cpp:26-76) is resolved on the host into "runs" of emitted
+// k-mers (it only depends on where the N's are), the k-mers themselves are extracted, de-duplicated, counted, scanned
+// and sorted on the device.  CUB's radix sort / scan are used for this one-off start-up step only; the search path is
+// made of the kernels in ngm_cs.cuh.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include <cub/cub.cuh>
+
+#include "ngm_ctx.h"
+#include "ngm_cs.cuh"
+
+using namespace ngm;
+
+namespace ngm {
+
+struct CsState {
+	ngm_b200_cs_params hp;
+	int k = 0, step = 0, bin_shift = 0;
+	uint32_t n_prefix = 0, table_len = 0;
+	int max_kfreq = 0;
+	bool ready = false;
+	DevBuf d_tabu, d_table, d_weight;
+	// search scratch
+	DevBuf d_meta, d_heap, d_cursor, d_slow_list, d_slow_count, d_counts, d_begin, d_scan_tmp, d_pairs, d_votes;
+	DevBuf d_ex_tables, d_ex_rlists, d_ex_gens;
+	HostBuf h_total;
+	int ex_blocks = 0;
+	uint64_t exact_reads = 0;      // reads the last search sent to the exact kernel
+};
+
+void cs_release(CsState *cs) {
+	if (cs == nullptr) return;
+	DevBuf *db[] = { &cs->d_tabu, &cs->d_table, &cs->d_weight, &cs->d_meta, &cs->d_heap, &cs->d_cursor, &cs->d_slow_list, &cs->d_slow_count,
+			&cs->d_counts, &cs->d_begin, &cs->d_scan_tmp, &cs->d_pairs, &cs->d_votes, &cs->d_ex_tables, &cs->d_ex_rlists, &cs->d_ex_gens };
+	for (DevBuf *b : db) b->release();
+	cs->h_total.release();
+	delete cs;
+}
+
+}  // namespace ngm
+
+namespace {
+
+int check_params(const ngm_b200_cs_params *p) {
+	if (p == nullptr) return fail(NGM_B200_EINVAL, "cs params == NULL");
+	if (p->kmer < 8 || p->kmer > 14) return fail(NGM_B200_EINVAL, "kmer %d not in [8, 14]", p->kmer);
+	if (p->kmer_skip < 0 || p->kmer_skip > 64) return fail(NGM_B200_EINVAL, "kmer_skip %d out of range", p->kmer_skip);
+	if (p->bin_size < 0 || p->bin_size > 8) return fail(NGM_B200_EINVAL, "bin_size %d out of range", p->bin_size);
+	if (!(p->sensitivity >= 0.0f && p->sensitivity <= 1.0f)) return fail(NGM_B200_EINVAL, "sensitivity %g not in [0, 1]", p->sensitivity);
+	return NGM_B200_OK;
+}
+
+CsState *fresh_state(ngm_b200_ctx *c, const ngm_b200_cs_params *p) {
+	if (c->cs) cs_release(c->cs);
+	c->cs = new CsState();
+	c->cs->hp = *p;
+	c->cs->k = p->kmer;
+	c->cs->step = p->kmer_skip + 1;
+	c->cs->bin_shift = p->bin_size;
+	c->cs->n_prefix = 1u << (2 * p->kmer);
+	return c->cs;
+}
+
+// CompactPrefixTable::stats (PrefixTable.cpp:151-194): ceil(max(100, avg + 5 sd)) over the per-k-mer list lengths
+int max_kfreq_from_sums(uint32_t n_prefix, unsigned long long s1, unsigned long long s2) {
+	const double il = (double) n_prefix, sum = (double) s1, sum2 = (double) s2;
+	const double avg = sum / il;
+	const double sd = std::sqrt(sum2 / (il - 1) - 2.0 * avg * (sum / (il - 1)) + ((il * std::pow(avg, 2.0)) / (il - 1)));
+	return (int) std::ceil(std::max(100.0, avg + 5 * sd));
+}
+
+struct NRun {
+	uint64_t s, e;             // inclusive
+};
+
+// CS::PrefixIteration (CSstatic.cpp:26-76) over one contig at the level of N-free stretches.  The contig buffer the
+// reference iterates has `len` characters of which only the first `real` are decoded bases (DecodeRefSequence is
+// given the contig length as buffer length and decodes two less, SequenceProvider.cpp:384); the rest reads as code 0.
+void contig_runs(uint64_t start, uint64_t len, uint64_t real, const std::vector<NRun> &nruns, int k, int step, std::vector<CsRun> &out,
+		uint64_t &emit_total) {
+	const uint64_t contig_base = emit_total;
+	// N runs clipped to the decoded part of this contig, relative coordinates
+	std::vector<NRun> nr;
+	auto it = std::lower_bound(nruns.begin(), nruns.end(), start, [](const NRun &a, uint64_t v) { return a.e < v; });
+	for (; it != nruns.end() && it->s < start + real; ++it) {
+		const uint64_t s = std::max(it->s, start) - start, e = std::min(it->e, start + real - 1) - start;
+		nr.push_back({s, e});
+	}
+	size_t ni = 0;
+	uint64_t pos = 0, length = len;
+	auto is_n = [&](uint64_t p) {
+		while (ni < nr.size() && nr[ni].e < p) ++ni;
+		return ni < nr.size() && nr[ni].s <= p;
+	};
+	for (;;) {
+		if (length < (uint64_t) k) break;                          // :27-28
+		if (is_n(pos)) {                                           // :30-41
+			const uint64_t n_skip = nr[ni].e - pos + 1;
+			pos += n_skip;
+			if (n_skip >= length - (uint64_t) k) break;
+			length -= n_skip;
+		}
+		while (ni < nr.size() && nr[ni].e < pos) ++ni;
+		const uint64_t end = pos + length;                        // one past the last character of the buffer
+		const uint64_t q = ni < nr.size() ? nr[ni].s : end;        // next N (or the end)
+		if (q - pos >= (uint64_t) k) {
+			CsRun r;
+			r.start = start + pos;
+			r.tail_start = start + real;
+			r.emit_base = emit_total;
+			r.contig_base = contig_base;
+			r.n_emit = (uint32_t) ((q - pos - (uint64_t) k) / (uint64_t) step + 1);
+			r.pad = 0;
+			out.push_back(r);
+			emit_total += r.n_emit;
+		}
+		if (q == end) break;
+		length -= q - pos + 1;                                     // restart behind the N (:48-50,60-62)
+		pos = q + 1;
+	}
+}
+
+int finish_index(ngm_b200_ctx *c, CsState *cs, unsigned long long s1, unsigned long long s2) {
+	cs->max_kfreq = cs->hp.max_kfreq > 0 ? cs->hp.max_kfreq : max_kfreq_from_sums(cs->n_prefix, s1, s2);
+	cs->ready = true;
+	(void) c;
+	return NGM_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ngm_b200_cs_build_index(ngm_b200_ctx *c, const ngm_b200_cs_params *params, const ngm_b200_contig *contigs, uint32_t n_contigs) {
+	if (c == nullptr || contigs == nullptr || n_contigs == 0) return fail(NGM_B200_EINVAL, "NULL argument");
+	int rc = check_params(params);
+	if (rc) return rc;
+	if (!c->have_ref) return fail(NGM_B200_ESTATE, "set_reference must precede cs_build_index");
+	if (c->concat_len >= 0xFFFFFFFFull) return fail(NGM_B200_ERANGE, "references of 2^32 - 1 bases or more need several table units (not supported)");
+	CU(cudaSetDevice(c->device));
+	CsState *cs = fresh_state(c, params);
+	cudaStream_t st = c->stream;
+	const int k = cs->k;
+	const uint32_t *ref4 = c->d_ref4.as<uint32_t>();
+
+	// 1. where are the N's (device) -> runs of emitted k-mers (host)
+	const uint64_t n_words = (c->concat_len + 7) / 8;
+	const uint32_t cap = 8u << 20;
+	DevBuf d_list, d_cnt;
+	CU(d_list.ensure((size_t) cap * 8));
+	CU(d_cnt.ensure(4));
+	CU(cudaMemsetAsync(d_cnt.p, 0, 4, st));
+	cs_find_n_kernel<<<(unsigned) ((n_words + 255) / 256), 256, 0, st>>>(ref4, n_words, c->concat_len, d_list.as<unsigned long long>(), cap,
+			d_cnt.as<uint32_t>());
+	c->launches += 1;
+	uint32_t n_bound = 0;
+	CU(cudaMemcpyAsync(&n_bound, d_cnt.p, 4, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	if (n_bound > cap) {
+		d_list.release();
+		d_cnt.release();
+		return fail(NGM_B200_ERANGE, "reference holds more than %u N-run boundaries", cap);
+	}
+	std::vector<unsigned long long> bounds(n_bound);
+	if (n_bound) CU(cudaMemcpy(bounds.data(), d_list.p, (size_t) n_bound * 8, cudaMemcpyDeviceToHost));
+	d_list.release();
+	d_cnt.release();
+	std::sort(bounds.begin(), bounds.end());
+	std::vector<NRun> nruns;
+	for (size_t i = 0; i < bounds.size();) {                       // (start, end) pairs; a single N is both
+		const uint64_t s = bounds[i] >> 1;
+		if (bounds[i] & 1ull) return fail(NGM_B200_ECUDA, "inconsistent N-run list");
+		size_t j = i + 1;
+		if (j >= bounds.size() || !(bounds[j] & 1ull)) return fail(NGM_B200_ECUDA, "inconsistent N-run list");
+		nruns.push_back({s, (uint64_t) (bounds[j] >> 1)});
+		i = j + 1;
+	}
+	std::vector<CsRun> runs;
+	uint64_t n_emit = 0;
+	for (uint32_t i = 0; i < n_contigs; ++i) {
+		const uint64_t start = contigs[i].start, len = contigs[i].length;
+		if (start + len > c->concat_len + 1) return fail(NGM_B200_EINVAL, "contig %u lies outside the reference", i);
+		if (len < 2) continue;
+		const uint64_t real = (start & 1) ? len - 1 : len - 2;     // SequenceProvider.cpp:384,416-426
+		contig_runs(start, len, real, nruns, k, cs->step, runs, n_emit);
+	}
+	if (n_emit >= 0x7FFFFFF0ull) return fail(NGM_B200_ERANGE, "too many indexed positions (%llu)", (unsigned long long) n_emit);
+
+	// 2. k-mers, counts
+	const uint32_t NP = cs->n_prefix;
+	DevBuf d_runs, d_freq, d_keys, d_vals, d_keys2, d_sums, d_tmp, d_off;
+	CU(d_freq.ensure(((size_t) NP + 1) * 4));
+	CU(cudaMemsetAsync(d_freq.p, 0, ((size_t) NP + 1) * 4, st));
+	CU(d_sums.ensure(16));
+	CU(cudaMemsetAsync(d_sums.p, 0, 16, st));
+	const size_t ne = (size_t) std::max<uint64_t>(n_emit, 1);
+	CU(d_keys.ensure(ne * 4));
+	CU(d_vals.ensure(ne * 4));
+	if (n_emit) {
+		CU(d_runs.ensure(runs.size() * sizeof(CsRun)));
+		CU(cudaMemcpyAsync(d_runs.p, runs.data(), runs.size() * sizeof(CsRun), cudaMemcpyHostToDevice, st));
+		cs_emit_kernel<<<(unsigned) ((n_emit + 255) / 256), 256, 0, st>>>(ref4, d_runs.as<CsRun>(), (int) runs.size(), n_emit, k, cs->step, cs->bin_shift,
+				params->skip_rep ? 1 : 0, NP, d_keys.as<uint32_t>(), d_vals.as<uint32_t>(), d_freq.as<uint32_t>());
+		c->launches += 1;
+	}
+	CU(cs->d_weight.ensure((size_t) NP + 1));
+	CU(cudaMemsetAsync(cs->d_weight.p, 0, (size_t) NP + 1, st));
+	cs_weight_kernel<<<(NP + 255) / 256, 256, 0, st>>>(d_freq.as<uint32_t>(), NP, k, cs->d_weight.as<int8_t>(), d_sums.as<unsigned long long>());
+	c->launches += 1;
+	// 3. offsets
+	CU(d_off.ensure(((size_t) NP + 1) * 4));
+	size_t tmp_bytes = 0;
+	CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_freq.as<uint32_t>(), d_off.as<uint32_t>(), (int) (NP + 1), st));
+	CU(d_tmp.ensure(tmp_bytes));
+	CU(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, d_freq.as<uint32_t>(), d_off.as<uint32_t>(), (int) (NP + 1), st));
+	CU(cs->d_tabu.ensure(((size_t) NP + 1) * 4));
+	cs_tabu_kernel<<<(NP + 1 + 255) / 256, 256, 0, st>>>(d_off.as<uint32_t>(), cs->d_weight.as<int8_t>(), NP, cs->d_tabu.as<uint32_t>());
+	c->launches += 1;
+	uint32_t total = 0;
+	unsigned long long sums[2] = {0, 0};
+	CU(cudaMemcpyAsync(&total, d_off.as<uint32_t>() + NP, 4, cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(sums, d_sums.p, 16, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	d_freq.release();
+	d_off.release();
+	cs->table_len = total;
+	// 4. positions grouped by k-mer: stable sort of (k-mer, position) in emission order keeps positions ascending
+	CU(cs->d_table.ensure(ne * 4 + 4));
+	if (n_emit) {
+		CU(d_keys2.ensure(ne * 4));
+		tmp_bytes = 0;
+		CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys.as<uint32_t>(), d_keys2.as<uint32_t>(), d_vals.as<uint32_t>(),
+				cs->d_table.as<uint32_t>(), (int) n_emit, 0, 2 * k + 1, st));
+		CU(d_tmp.ensure(tmp_bytes));
+		CU(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, d_keys.as<uint32_t>(), d_keys2.as<uint32_t>(), d_vals.as<uint32_t>(),
+				cs->d_table.as<uint32_t>(), (int) n_emit, 0, 2 * k + 1, st));
+		cs_zero_unused_kernel<<<(NP + 255) / 256, 256, 0, st>>>(cs->d_tabu.as<uint32_t>(), NP, cs->d_table.as<uint32_t>());
+		c->launches += 1;
+	}
+	CU(cudaStreamSynchronize(st));
+	CU(cudaGetLastError());
+	d_keys.release();
+	d_keys2.release();
+	d_vals.release();
+	d_tmp.release();
+	d_runs.release();
+	d_sums.release();
+	return finish_index(c, cs, sums[0], sums[1]);
+}
+
+int ngm_b200_cs_load_index(ngm_b200_ctx *c, const ngm_b200_cs_params *params, const uint32_t *tab, const int8_t *weight, uint32_t index_len,
+		const uint32_t *table, uint32_t table_len) {
+	if (c == nullptr || tab == nullptr || weight == nullptr || (table == nullptr && table_len)) return fail(NGM_B200_EINVAL, "NULL argument");
+	int rc = check_params(params);
+	if (rc) return rc;
+	const uint32_t NP = 1u << (2 * params->kmer);
+	if (index_len != NP + 1) return fail(NGM_B200_EINVAL, "index length %u does not belong to kmer %d", index_len, params->kmer);
+	CU(cudaSetDevice(c->device));
+	CsState *cs = fresh_state(c, params);
+	cudaStream_t st = c->stream;
+	DevBuf d_tab;
+	CU(d_tab.ensure((size_t) index_len * 4));
+	CU(cs->d_weight.ensure((size_t) index_len));
+	CU(cs->d_tabu.ensure((size_t) index_len * 4));
+	CU(cs->d_table.ensure((size_t) table_len * 4 + 4));
+	CU(cudaMemcpyAsync(d_tab.p, tab, (size_t) index_len * 4, cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(cs->d_weight.p, weight, (size_t) index_len, cudaMemcpyHostToDevice, st));
+	if (table_len) CU(cudaMemcpyAsync(cs->d_table.p, table, (size_t) table_len * 4, cudaMemcpyHostToDevice, st));
+	cs_tabu_from_file_kernel<<<(NP + 1 + 255) / 256, 256, 0, st>>>(d_tab.as<uint32_t>(), cs->d_weight.as<int8_t>(), NP, cs->d_tabu.as<uint32_t>());
+	c->launches += 1;
+	CU(cudaStreamSynchronize(st));
+	CU(cudaGetLastError());
+	d_tab.release();
+	cs->table_len = table_len;
+	// stats() over the file's index (PrefixTable.cpp:160-176)
+	unsigned long long s1 = 0, s2 = 0;
+	for (uint32_t j = 0; j < NP; ++j) {
+		const unsigned long long cnt = tab[j + 1] - tab[j];
+		s1 += cnt;
+		s2 += cnt * cnt;
+	}
+	return finish_index(c, cs, s1, s2);
+}
+
+int ngm_b200_cs_index_info(const ngm_b200_ctx *c, uint32_t *index_len, uint32_t *table_len, int32_t *max_kfreq) {
+	if (c == nullptr || c->cs == nullptr || !c->cs->ready) return fail(NGM_B200_ESTATE, "no candidate-search index");
+	if (index_len) *index_len = c->cs->n_prefix + 1;
+	if (table_len) *table_len = c->cs->table_len;
+	if (max_kfreq) *max_kfreq = c->cs->max_kfreq;
+	return NGM_B200_OK;
+}
+
+int ngm_b200_cs_export_index(ngm_b200_ctx *c, uint32_t *tab, int8_t *weight, uint32_t *table) {
+	if (c == nullptr || c->cs == nullptr || !c->cs->ready) return fail(NGM_B200_ESTATE, "no candidate-search index");
+	CU(cudaSetDevice(c->device));
+	CsState *cs = c->cs;
+	const uint32_t NP = cs->n_prefix;
+	if (tab) {
+		DevBuf d_tab;
+		CU(d_tab.ensure(((size_t) NP + 1) * 4));
+		cs_export_tab_kernel<<<(NP + 1 + 255) / 256, 256, 0, c->stream>>>(cs->d_tabu.as<uint32_t>(), NP, d_tab.as<uint32_t>());
+		c->launches += 1;
+		CU(cudaMemcpyAsync(tab, d_tab.p, ((size_t) NP + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+		CU(cudaStreamSynchronize(c->stream));
+		d_tab.release();
+	}
+	if (weight) CU(cudaMemcpy(weight, cs->d_weight.p, (size_t) NP + 1, cudaMemcpyDeviceToHost));
+	if (table && cs->table_len) CU(cudaMemcpy(table, cs->d_table.p, (size_t) cs->table_len * 4, cudaMemcpyDeviceToHost));
+	return NGM_B200_OK;
+}
+
+int ngm_b200_dev_cs_search(ngm_b200_ctx *c, const void *d_ascii_reads, int n_reads, int stride, int mode_flags, void *d_cand_begin, void *d_pairs,
+		void *d_votes, uint32_t capacity, void *d_max_hit, void *stream) {
+	if (c == nullptr || d_ascii_reads == nullptr || d_cand_begin == nullptr || d_pairs == nullptr) return fail(NGM_B200_EINVAL, "NULL argument");
+	if (c->cs == nullptr || !c->cs->ready) return fail(NGM_B200_ESTATE, "cs_build_index / cs_load_index must precede cs_search");
+	if (n_reads <= 0) return 0;
+	if (stride <= 0 || stride > kCsMaxStride) return fail(NGM_B200_EINVAL, "read stride %d not in [1, %d]", stride, kCsMaxStride);
+	CU(cudaSetDevice(c->device));
+	CsState *cs = c->cs;
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	CsDev P;
+	P.tabu = cs->d_tabu.as<uint32_t>();
+	P.table = cs->d_table.as<uint32_t>();
+	P.k = cs->k;
+	P.bin_shift = cs->bin_shift;
+	P.max_kfreq = cs->max_kfreq;
+	P.max_cmrs = cs->hp.max_cmrs > 0 ? cs->hp.max_cmrs : 0x7FFFFFFF;
+	P.sensitivity = cs->hp.sensitivity;
+	P.kmer_min = cs->hp.kmer_min;
+	CU(cs->d_meta.ensure((size_t) n_reads * sizeof(CsMeta)));
+	CU(cs->d_heap.ensure((size_t) capacity * sizeof(CsCand) + 8));
+	CU(cs->d_cursor.ensure(4));
+	CU(cs->d_slow_count.ensure(4));
+	CU(cs->d_slow_list.ensure((size_t) n_reads * 4));
+	CU(cs->d_counts.ensure(((size_t) n_reads + 1) * 4));
+	CU(cudaMemsetAsync(cs->d_cursor.p, 0, 4, st));
+	CU(cudaMemsetAsync(cs->d_slow_count.p, 0, 4, st));
+	if (cs->ex_blocks == 0) {
+		int sms = 0;
+		CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+		cs->ex_blocks = std::max(8, 2 * sms);
+		const size_t tl = (size_t) 1 << kCsExactBits;
+		CU(cs->d_ex_tables.ensure(tl * sizeof(CsExactEntry) * cs->ex_blocks));
+		CU(cs->d_ex_rlists.ensure(tl * 4 * cs->ex_blocks));
+		CU(cs->d_ex_gens.ensure((size_t) cs->ex_blocks * 4));
+		CU(cudaMemsetAsync(cs->d_ex_tables.p, 0xFF, tl * sizeof(CsExactEntry) * cs->ex_blocks, st));
+		CU(cudaMemsetAsync(cs->d_ex_gens.p, 0, (size_t) cs->ex_blocks * 4, st));
+	}
+	const uint8_t *reads = static_cast<const uint8_t *>(d_ascii_reads);
+	CsMeta *meta = cs->d_meta.as<CsMeta>();
+	CsCand *heap = cs->d_heap.as<CsCand>();
+	uint32_t *cursor = cs->d_cursor.as<uint32_t>();
+	float *max_hit = static_cast<float *>(d_max_hit);
+	const bool exact_only = (mode_flags & 1) != 0;
+	if (!exact_only) {
+		// expected distinct bins per read ~ (L - k + 1) x 2 lists x mean list length; 8192 slots serve <= ~170 bp
+		const bool big = stride > 176;
+		if (big) {
+			CU(cudaFuncSetAttribute(cs_search_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 * 4));
+			cs_search_kernel<14><<<n_reads, 128, 2 * 16384 * 4, st>>>(P, reads, n_reads, stride, meta, heap, capacity, cursor, cs->d_slow_list.as<uint32_t>(),
+					cs->d_slow_count.as<uint32_t>(), max_hit);
+		} else {
+			CU(cudaFuncSetAttribute(cs_search_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4));
+			cs_search_kernel<13><<<n_reads, 128, 2 * 8192 * 4, st>>>(P, reads, n_reads, stride, meta, heap, capacity, cursor, cs->d_slow_list.as<uint32_t>(),
+					cs->d_slow_count.as<uint32_t>(), max_hit);
+		}
+		c->launches += 1;
+		CU(cudaGetLastError());
+	}
+	cs_search_exact_kernel<<<cs->ex_blocks, 32, 0, st>>>(P, reads, n_reads, stride, meta, heap, capacity, cursor,
+			exact_only ? nullptr : cs->d_slow_list.as<uint32_t>(), cs->d_slow_count.as<uint32_t>(), cs->d_ex_tables.as<CsExactEntry>(),
+			cs->d_ex_rlists.as<uint32_t>(), cs->d_ex_gens.as<uint32_t>(), max_hit);
+	c->launches += 1;
+	CU(cudaGetLastError());
+	// CSR
+	cs_counts_kernel<<<(n_reads + 1 + 255) / 256, 256, 0, st>>>(meta, n_reads, cs->d_counts.as<int>());
+	size_t tmp_bytes = 0;
+	CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cs->d_counts.as<int>(), static_cast<int *>(d_cand_begin), n_reads + 1, st));
+	CU(cs->d_scan_tmp.ensure(tmp_bytes));
+	CU(cub::DeviceScan::ExclusiveSum(cs->d_scan_tmp.p, tmp_bytes, cs->d_counts.as<int>(), static_cast<int *>(d_cand_begin), n_reads + 1, st));
+	cs_gather_kernel<<<(n_reads + 255) / 256, 256, 0, st>>>(meta, heap, capacity, static_cast<const int *>(d_cand_begin), n_reads, cs->bin_shift,
+			c->dp.corridor, capacity, static_cast<ngm_b200_pair *>(d_pairs), static_cast<float *>(d_votes));
+	c->launches += 3;
+	CU(cudaGetLastError());
+	return n_reads;
+}
+
+int ngm_b200_cs_search(ngm_b200_ctx *c, const char *reads, int n_reads, int stride, int mode_flags, int32_t *cand_begin, ngm_b200_pair *pairs,
+		float *votes, size_t capacity, size_t *total, float *max_hit) {
+	if (c == nullptr || reads == nullptr || cand_begin == nullptr || (pairs == nullptr && capacity)) return fail(NGM_B200_EINVAL, "NULL argument");
+	if (c->cs == nullptr || !c->cs->ready) return fail(NGM_B200_ESTATE, "cs_build_index / cs_load_index must precede cs_search");
+	if (n_reads <= 0) return 0;
+	if (capacity > 0x7FFFFFFFull) capacity = 0x7FFFFFFFull;
+	CU(cudaSetDevice(c->device));
+	CsState *cs = c->cs;
+	cudaStream_t st = c->stream;
+	DevBuf d_reads, d_mh;
+	CU(d_reads.ensure((size_t) n_reads * stride));
+	CU(cs->d_begin.ensure(((size_t) n_reads + 1) * 4));
+	CU(cs->d_pairs.ensure(std::max<size_t>(capacity, 1) * sizeof(ngm_b200_pair)));
+	CU(cs->d_votes.ensure(std::max<size_t>(capacity, 1) * 4));
+	if (max_hit) CU(d_mh.ensure((size_t) n_reads * 4));
+	CU(cudaMemcpyAsync(d_reads.p, reads, (size_t) n_reads * stride, cudaMemcpyHostToDevice, st));
+	int rc = ngm_b200_dev_cs_search(c, d_reads.p, n_reads, stride, mode_flags, cs->d_begin.p, cs->d_pairs.p, cs->d_votes.p, (uint32_t) capacity,
+			max_hit ? d_mh.p : nullptr, st);
+	if (rc < 0) {
+		d_reads.release();
+		d_mh.release();
+		return rc;
+	}
+	CU(cudaMemcpyAsync(cand_begin, cs->d_begin.p, ((size_t) n_reads + 1) * 4, cudaMemcpyDeviceToHost, st));
+	if (max_hit) CU(cudaMemcpyAsync(max_hit, d_mh.p, (size_t) n_reads * 4, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	d_reads.release();
+	d_mh.release();
+	const size_t tot = (size_t) cand_begin[n_reads];
+	if (total) *total = tot;
+	uint32_t slow = 0;
+	CU(cudaMemcpy(&slow, cs->d_slow_count.p, 4, cudaMemcpyDeviceToHost));
+	cs->exact_reads = (mode_flags & 1) ? (uint64_t) n_reads : slow;
+	if (tot > capacity) return fail(NGM_B200_ERANGE, "candidate buffer too small: %zu entries needed", tot);
+	if (tot) {
+		CU(cudaMemcpy(pairs, cs->d_pairs.p, tot * sizeof(ngm_b200_pair), cudaMemcpyDeviceToHost));
+		if (votes) CU(cudaMemcpy(votes, cs->d_votes.p, tot * 4, cudaMemcpyDeviceToHost));
+	}
+	return n_reads;
+}
+
+uint64_t ngm_b200_cs_exact_reads(const ngm_b200_ctx *c) { return (c && c->cs) ? c->cs->exact_reads : 0; }
+
+}  // extern "C"

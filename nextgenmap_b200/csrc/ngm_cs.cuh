@@ -1,0 +1,648 @@
+// ngm_cs.cuh -- candidate search on the device: NextGenMap's k-mer index ("prefix table") and
+// the per-read vote that turns k-mer hits into candidate reference windows for BatchScore.
+//
+// Reference: src/CSstatic.cpp:20-76 (k-mer iteration), src/PrefixTable.cpp:357-498,577-738 (index construction),
+// :750-817 (lookup), src/CS.cpp:114-213 (PrefixSearch + AddLocationStd), :263-313 (CollectResultsStd),
+// src/CS.h:164-175 (bins).  The results -- candidate set, votes AND the order of every read's list (which decides
+// ties in ScoreBuffer::top1SE) -- are identical to the reference's.
+//
+// Index in HBM:  tabu[p] = (exclusive prefix sum of the k-mer counts) | used(p) << 31 for p in [0, 4^k], and
+// table[] = reference positions grouped by k-mer, ascending inside a group (the order the reference's sequential
+// fill produces).  3 Gbp, k 13, every 3rd position: 268 MB + 4.1 GB.
+//
+// Search: one 128-thread block per read.  Every thread takes one k-mer of the read, looks up the forward and the
+// reverse-complement list and votes for bin (position - offset) >> bin_size in an open-addressed table in shared
+// memory (64 or 128 KB: 8192 / 16384 slots of {bin, fwd votes | rev votes << 16}).  The reference's result only
+// depends on the final votes, except for the ORDER of a read's candidates, which is the order in which entries first
+// reached the running threshold sensitivity x max-votes-so-far while hits arrive in k-mer order.  That order is
+// reconstructed exactly for the few reads that need it (more than one accepted entry): the hits of all entries that
+// can influence the running maximum (>= 2 votes) or are accepted are collected with their sequence number, sorted,
+// and replayed.  Reads that do not fit the fast path (table overflow, too many relevant hits, > 64 accepted entries,
+// 64-bit bin arithmetic) go to cs_search_exact_kernel, a one-lane sequential restatement on a table in global memory.
+#pragma once
+
+#include "ngm_common.cuh"
+
+namespace ngm {
+
+struct CsDev {
+	const uint32_t *tabu;     // [4^k + 1]
+	const uint32_t *table;
+	int k, bin_shift, max_kfreq, max_cmrs;
+	float sensitivity, kmer_min;
+};
+
+struct CsRun {                // one N-free stretch of a contig as CS::PrefixIteration walks it
+	uint64_t start;           // concatenated position of the first emitted k-mer
+	uint64_t tail_start;      // positions >= tail_start read as code 0 (the two undecoded bases at a contig's end)
+	uint64_t emit_base;       // emission index of this run's first k-mer
+	uint64_t contig_base;     // emission index of the contig's first k-mer
+	uint32_t n_emit;
+	uint32_t pad;
+};
+
+struct CsMeta {               // per read: where its candidates sit in the heap
+	uint32_t off;
+	uint32_t count;           // kPending while the read waits for the exact kernel
+};
+
+struct CsCand {               // 8 bytes
+	uint32_t bin;
+	uint16_t votes;
+	uint16_t rev;
+};
+
+constexpr uint32_t kCsPending = 0xFFFFFFFFu;
+constexpr uint32_t kCsEmpty = 0xFFFFFFFFu;
+constexpr int kCsMaxItems = 512;           // relevant hits replayed for the order
+constexpr int kCsMaxAccepted = 64;
+constexpr int kCsMaxStride = 1024;         // NGM's maximum read length (ReadProvider.cpp:42)
+constexpr int kCsExactBits = 17;           // slots of the exact kernel's table (reads <= 1000 bp x max_kfreq hits)
+
+__host__ __device__ __forceinline__ uint32_t cs_revcomp(uint32_t prefix, int k) {      // PrefixTable.cpp:93-108
+	uint32_t c = (prefix ^ 0xAAAAAAAAu) << (32 - 2 * k);
+	c = (c & 0xFFFF0000u) >> 16 | (c & 0x0000FFFFu) << 16;
+	c = (c & 0xFF00FF00u) >> 8 | (c & 0x00FF00FFu) << 8;
+	c = (c & 0xF0F0F0F0u) >> 4 | (c & 0x0F0F0F0Fu) << 4;
+	c = (c & 0xCCCCCCCCu) >> 2 | (c & 0x33333333u) << 2;
+	return c;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// index construction
+// ---------------------------------------------------------------------------------------------------------
+// boundaries of the N runs of the whole concatenated reference (code 5 in the device packing): entry = pos << 1 | is_end
+__global__ void cs_find_n_kernel(const uint32_t *__restrict__ ref4, uint64_t n_words, uint64_t concat_len, unsigned long long *__restrict__ list,
+		uint32_t cap, uint32_t *__restrict__ count) {
+	const uint64_t wi = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (wi >= n_words) return;
+	const uint32_t w = ref4[wi];
+	// nibble == 5  <=>  (nibble ^ 5) == 0
+	const uint32_t x = w ^ 0x55555555u;
+	const uint32_t z = ~(x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u;     // bit 4i set iff nibble i is N
+	if (z == 0) return;
+	uint32_t nm = 0;
+#pragma unroll
+	for (int i = 0; i < 8; ++i) nm |= ((z >> (4 * i)) & 1u) << i;
+	for (int i = 0; i < 8; ++i)
+		if (wi * 8 + i >= concat_len) nm &= ~(1u << i);
+	if (nm == 0) return;
+	const uint32_t prev = wi > 0 ? ((ref4[wi - 1] >> 28) == 5u) : 0u;
+	const uint32_t next = (wi + 1 < n_words && (wi + 1) * 8 < concat_len) ? ((ref4[wi + 1] & 0xFu) == 5u) : 0u;
+	const uint32_t starts = nm & ~((nm << 1) | prev);
+	const uint32_t ends = nm & ~((nm >> 1) | (next << 7));
+	for (int i = 0; i < 8; ++i) {
+		if ((starts >> i) & 1u) {
+			const uint32_t at = atomicAdd(count, 1u);
+			if (at < cap) list[at] = (unsigned long long) (wi * 8 + i) << 1;
+		}
+		if ((ends >> i) & 1u) {
+			const uint32_t at = atomicAdd(count, 1u);
+			if (at < cap) list[at] = ((unsigned long long) (wi * 8 + i) << 1) | 1ull;
+		}
+	}
+}
+
+__device__ __forceinline__ int cs_find_run(const CsRun *__restrict__ runs, int n_runs, uint64_t e) {
+	int lo = 0, hi = n_runs - 1;
+	while (lo < hi) {                                      // last run with emit_base <= e
+		const int mid = (lo + hi + 1) >> 1;
+		if (runs[mid].emit_base <= e) lo = mid; else hi = mid - 1;
+	}
+	return lo;
+}
+
+// k-mer code (A0 C1 T2 G3, CSstatic.cpp:19-22) of the k bases at concatenated position x
+__device__ __forceinline__ uint32_t cs_ref_kmer(const uint32_t *__restrict__ ref4, uint64_t x, int k, uint64_t tail_start) {
+	uint32_t p = 0;
+	uint64_t wi = x >> 3;
+	int sh = 4 * (int) (x & 7);
+	uint32_t w = ref4[wi];
+	for (int i = 0; i < k; ++i) {
+		uint32_t c = (w >> sh) & 0xFu;
+		if (x + i >= tail_start) c = 0;
+		p = (p << 2) | ((c ^ (c >> 1)) & 3u);
+		sh += 4;
+		if (sh == 32) {
+			sh = 0;
+			w = ref4[++wi];
+		}
+	}
+	return p;
+}
+
+// One thread per emitted reference k-mer: CountKmer's de-duplication (PrefixTable.cpp:632-655) written as a local rule,
+//   counted(e) = !same(e) || !same(e-1) || bin(x_e) != bin(x_{e-1}),  same(e) = prefix(e) == prefix(e-1),
+// with prefix(-1) = 111111 and same(-1) = false at the start of every contig (PrefixTable.cpp:363-365).
+__global__ void cs_emit_kernel(const uint32_t *__restrict__ ref4, const CsRun *__restrict__ runs, int n_runs, uint64_t n_emit, int k, int step,
+		int bin_shift, int skip_rep, uint32_t sentinel, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ freq) {
+	const uint64_t e = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= n_emit) return;
+	const int r = cs_find_run(runs, n_runs, e);
+	const CsRun run = runs[r];
+	const uint64_t x = run.start + (e - run.emit_base) * (uint64_t) step;
+	const uint32_t p = cs_ref_kmer(ref4, x, k, run.tail_start);
+	bool counted = true;
+	if (skip_rep) {
+		uint32_t p1 = 111111u, p2 = 111111u;
+		uint64_t x1 = 0;
+		bool have1 = e > run.contig_base, have2 = e > run.contig_base + 1;
+		if (have1) {
+			const int r1 = (e - 1 >= run.emit_base) ? r : cs_find_run(runs, n_runs, e - 1);
+			const CsRun q = runs[r1];
+			x1 = q.start + (e - 1 - q.emit_base) * (uint64_t) step;
+			p1 = cs_ref_kmer(ref4, x1, k, q.tail_start);
+		}
+		if (have2) {
+			const int r2 = (e - 2 >= run.emit_base) ? r : cs_find_run(runs, n_runs, e - 2);
+			const CsRun q = runs[r2];
+			p2 = cs_ref_kmer(ref4, q.start + (e - 2 - q.emit_base) * (uint64_t) step, k, q.tail_start);
+		}
+		const bool same0 = p == p1;
+		const bool same1 = have1 && p1 == p2;
+		counted = !same0 || !same1 || ((x >> bin_shift) != (x1 >> bin_shift));
+	}
+	if (counted) atomicAdd(&freq[p], 1u);
+	keys[e] = counted ? p : sentinel;
+	vals[e] = (uint32_t) x;
+}
+
+// createRefTableIndex (PrefixTable.cpp:436-498): weight / used flag per k-mer, and the sums stats() needs (:151-194)
+__global__ void cs_weight_kernel(const uint32_t *__restrict__ freq, uint32_t n_prefix, int k, int8_t *__restrict__ weight,
+		unsigned long long *__restrict__ sums) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long s1 = 0, s2 = 0;
+	if (i < n_prefix) {
+		const uint32_t f = freq[i];
+		int8_t w = 0;
+		if (f > 0) {
+			const uint32_t tot = f + freq[cs_revcomp(i, k)];
+			const int dummy = 10000;
+			w = (int8_t) (int) ((float) (dummy - (int) min(tot, (uint32_t) dummy)) * 100.0f / (float) dummy);
+		}
+		weight[i] = w;
+		s1 = f;
+		s2 = (unsigned long long) f * f;
+	}
+	for (int d = 16; d > 0; d >>= 1) {
+		s1 += __shfl_down_sync(0xffffffffu, s1, d);
+		s2 += __shfl_down_sync(0xffffffffu, s2, d);
+	}
+	if ((threadIdx.x & 31) == 0 && (s1 | s2)) {
+		atomicAdd(&sums[0], s1);
+		atomicAdd(&sums[1], s2);
+	}
+}
+
+__global__ void cs_tabu_kernel(const uint32_t *__restrict__ off, const int8_t *__restrict__ weight, uint32_t n_prefix, uint32_t *__restrict__ tabu) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i > n_prefix) return;
+	tabu[i] = off[i] | ((i < n_prefix && weight[i] != 0) ? 0x80000000u : 0u);
+}
+
+// k-mers that were counted but are not "used" (>= 9901 occurrences incl. reverse complement) keep zeroed slots
+// (BuildPrefixTable only stores for used() k-mers, PrefixTable.cpp:677-690)
+__global__ void cs_zero_unused_kernel(const uint32_t *__restrict__ tabu, uint32_t n_prefix, uint32_t *__restrict__ table) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_prefix) return;
+	const uint32_t a = tabu[i];
+	if (a >> 31) return;
+	const uint32_t b = tabu[i + 1] & 0x7FFFFFFFu;
+	for (uint32_t j = a; j < b; ++j) table[j] = 0;
+}
+
+// index loaded from a `<ref>-ht-<k>-<skip>.3.ngm` file (Index::m_TabIndex is 1-based)
+__global__ void cs_tabu_from_file_kernel(const uint32_t *__restrict__ tab, const int8_t *__restrict__ weight, uint32_t n_prefix, uint32_t *__restrict__ tabu) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i > n_prefix) return;
+	tabu[i] = (tab[i] - 1u) | ((i < n_prefix && weight[i] != 0) ? 0x80000000u : 0u);
+}
+
+__global__ void cs_export_tab_kernel(const uint32_t *__restrict__ tabu, uint32_t n_prefix, uint32_t *__restrict__ tab) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i > n_prefix) return;
+	tab[i] = (tabu[i] & 0x7FFFFFFFu) + 1u;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// search: shared helpers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cs_enc2(uint8_t c) { return ((uint32_t) c >> 1) & 3u; }      // CSstatic.cpp:19-22
+
+// Is the k-mer starting at o one that CS::PrefixIteration emits?  No 'N' inside, and not the k-mer the N-skip path
+// drops: the last k-mer of the read when it directly follows an N run entered through CSstatic.cpp:30-41.
+__device__ __forceinline__ bool cs_read_kmer(const uint8_t *seq, int len, int o, int k, uint32_t &prefix) {
+	uint32_t p = 0;
+	bool ok = true;
+	for (int i = 0; i < k; ++i) {
+		const uint8_t c = seq[o + i];
+		ok = ok && (c != 'N');
+		p = (p << 2) | cs_enc2(c);
+	}
+	if (ok && o + k == len && o >= 1 && seq[o - 1] == 'N' && (o == 1 || seq[o - 2] == 'N')) ok = false;
+	prefix = p;
+	return ok;
+}
+
+struct CsLists {
+	uint32_t fs, fc, rs, rc;
+};
+
+__device__ __forceinline__ bool cs_lookup(const CsDev &P, uint32_t prefix, CsLists &L) {      // GetRefEntry, PrefixTable.cpp:750-817
+	const uint32_t rcp = cs_revcomp(prefix, P.k);
+	const uint32_t a0 = __ldg(P.tabu + prefix), a1 = __ldg(P.tabu + prefix + 1);
+	const uint32_t b0 = __ldg(P.tabu + rcp), b1 = __ldg(P.tabu + rcp + 1);
+	L.fs = a0 & 0x7FFFFFFFu;
+	L.fc = (a0 >> 31) ? (a1 & 0x7FFFFFFFu) - L.fs : 0u;
+	L.rs = b0 & 0x7FFFFFFFu;
+	L.rc = (b0 >> 31) ? (b1 & 0x7FFFFFFFu) - L.rs : 0u;
+	return (int) (L.fc + L.rc) < P.max_kfreq;              // cur->refTotal < maxPrefixFreq, CS.cpp:122
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// search: fast path, one block per read
+// ---------------------------------------------------------------------------------------------------------
+template <int TS_LOG>
+__global__ void __launch_bounds__(128) cs_search_kernel(const CsDev P, const uint8_t *__restrict__ reads, int n_reads, int stride,
+		CsMeta *__restrict__ meta, CsCand *__restrict__ heap, uint32_t heap_cap, uint32_t *__restrict__ cursor, uint32_t *__restrict__ slow_list,
+		uint32_t *__restrict__ slow_count, float *__restrict__ max_hit) {
+	constexpr int TS = 1 << TS_LOG;
+	constexpr uint32_t MASK = TS - 1;
+	extern __shared__ uint32_t s_dyn[];
+	uint32_t *keys = s_dyn, *cnts = s_dyn + TS;
+	__shared__ uint8_t s_read[kCsMaxStride + 16];
+	__shared__ uint32_t s_items_t[kCsMaxItems], s_items_s[kCsMaxItems];
+	__shared__ uint16_t s_items_c[kCsMaxItems];
+	__shared__ uint32_t s_acc[kCsMaxAccepted];
+	__shared__ int s_len;
+	__shared__ uint32_t s_max, s_any, s_distinct, s_slow, s_nacc, s_ncand, s_nitems, s_nord;
+	const int tid = threadIdx.x;
+	const int r = blockIdx.x;
+	if (r >= n_reads) return;
+	if (tid == 0) {
+		s_len = stride;
+		s_max = s_any = s_distinct = s_slow = s_nacc = s_ncand = s_nitems = s_nord = 0;
+	}
+	{
+		uint4 *k4 = reinterpret_cast<uint4 *>(keys), *c4 = reinterpret_cast<uint4 *>(cnts);
+		for (int i = tid; i < TS / 4; i += 128) {
+			k4[i] = make_uint4(kCsEmpty, kCsEmpty, kCsEmpty, kCsEmpty);
+			c4[i] = make_uint4(0, 0, 0, 0);
+		}
+	}
+	__syncthreads();
+	const uint8_t *src = reads + (size_t) r * stride;
+	for (int i = tid; i < stride; i += 128) {
+		const uint8_t c = src[i];
+		s_read[i] = c;
+		if (c == 0) atomicMin(&s_len, i);                  // MappedRead::length
+	}
+	__syncthreads();
+	const int len = s_len;
+	const int k = P.k;
+	const int n_kmers = len - k + 1;
+
+	// ---- vote -------------------------------------------------------------------------------------------
+	for (int o = tid; o < n_kmers; o += 128) {
+		uint32_t prefix;
+		if (!cs_read_kmer(s_read, len, o, k, prefix)) continue;
+		CsLists L;
+		if (!cs_lookup(P, prefix, L)) continue;
+		const uint32_t corr_r = (uint32_t) (len - (o + k));
+		const uint32_t total = L.fc + L.rc;
+		for (uint32_t i = 0; i < total; ++i) {
+			const bool rev = i >= L.fc;
+			const uint32_t loc = __ldg(P.table + (rev ? L.rs + (i - L.fc) : L.fs + i));
+			const uint32_t corr = rev ? corr_r : (uint32_t) o;
+			if (loc < corr) {                              // the reference's 64-bit wrap-around: exact kernel
+				s_slow = 1;
+				continue;
+			}
+			const uint32_t bin = (loc - corr) >> P.bin_shift;
+			uint32_t slot = (bin * 2654435761u) >> (32 - TS_LOG);
+			for (int probe = 0; probe < TS; ++probe) {
+				const uint32_t old = atomicCAS(&keys[slot], kCsEmpty, bin);
+				if (old == kCsEmpty || old == bin) {
+					if (old == kCsEmpty) atomicAdd(&s_distinct, 1u);
+					const uint32_t before = atomicAdd(&cnts[slot], rev ? 0x10000u : 1u);
+					const uint32_t now = ((before >> (rev ? 16 : 0)) & 0x7FFFu) + 1u;
+					if (now > 1u) atomicMax(&s_max, now);
+					break;
+				}
+				slot = (slot + 1) & MASK;
+				if (probe == TS - 1) s_slow = 1;
+			}
+			if (s_distinct > (uint32_t) (TS - TS / 8)) {       // table (nearly) full: give up on the fast path
+				s_slow = 1;
+				break;
+			}
+		}
+		s_any = 1;
+	}
+	__syncthreads();
+	auto to_exact = [&]() {
+		if (tid == 0) {
+			meta[r].off = 0;
+			meta[r].count = kCsPending;
+			slow_list[atomicAdd(slow_count, 1u)] = (uint32_t) r;
+		}
+	};
+	if (s_slow) {
+		to_exact();
+		return;
+	}
+	// hits of k-mers whose lists were empty still leave s_any == 1 with no entry; the maximum then stays 0
+	const uint32_t M = s_max > 0 ? s_max : (s_distinct > 0 ? 1u : 0u);
+	if (max_hit != nullptr && tid == 0) max_hit[r] = (float) M;
+	if (M == 0) {
+		if (tid == 0) {
+			meta[r].off = 0;
+			meta[r].count = 0;
+		}
+		return;
+	}
+	const float thr = fmaxf(P.kmer_min, __fmul_rn((float) M, P.sensitivity));      // CS.cpp:193-196,271
+
+	// ---- accepted entries -------------------------------------------------------------------------------
+	for (int s = tid; s < TS; s += 128) {
+		if (keys[s] == kCsEmpty) continue;
+		const uint32_t c = cnts[s];
+		const uint32_t a = ((float) (c & 0x7FFFu) >= thr ? 1u : 0u) + ((float) ((c >> 16) & 0x7FFFu) >= thr ? 1u : 0u);
+		if (a) {
+			const uint32_t at = atomicAdd(&s_nacc, 1u);
+			if (at < kCsMaxAccepted) s_acc[at] = (uint32_t) s;
+			atomicAdd(&s_ncand, a);
+			cnts[s] = c | 0x8000u;                         // accepted flag
+		}
+	}
+	__syncthreads();
+	const uint32_t nacc = s_nacc, ncand = s_ncand;
+	if (nacc > kCsMaxAccepted) {
+		to_exact();
+		return;
+	}
+	if (!((long long) ncand < (long long) P.max_cmrs)) {      // CS.cpp:308-310
+		if (tid == 0) {
+			meta[r].off = 0;
+			meta[r].count = 0;
+		}
+		return;
+	}
+	if (nacc > 1) {
+		// ---- order of the list: replay the relevant hits in sequence ---------------------------------------
+		for (int o = tid; o < n_kmers; o += 128) {
+			uint32_t prefix;
+			if (!cs_read_kmer(s_read, len, o, k, prefix)) continue;
+			CsLists L;
+			if (!cs_lookup(P, prefix, L)) continue;
+			const uint32_t corr_r = (uint32_t) (len - (o + k));
+			const uint32_t total = L.fc + L.rc;
+			for (uint32_t i = 0; i < total; ++i) {
+				const bool rev = i >= L.fc;
+				const uint32_t idx = rev ? i - L.fc : i;
+				const uint32_t loc = __ldg(P.table + (rev ? L.rs + idx : L.fs + idx));
+				const uint32_t bin = (loc - (rev ? corr_r : (uint32_t) o)) >> P.bin_shift;
+				uint32_t slot = (bin * 2654435761u) >> (32 - TS_LOG);
+				while (keys[slot] != bin) slot = (slot + 1) & MASK;
+				const uint32_t c = cnts[slot];
+				if ((c & 0x8000u) || (c & 0x7FFFu) >= 2u || ((c >> 16) & 0x7FFFu) >= 2u) {
+					const uint32_t at = atomicAdd(&s_nitems, 1u);
+					if (at < kCsMaxItems) {
+						s_items_t[at] = ((uint32_t) o << 17) | (rev ? 0x10000u : 0u) | idx;      // sequence number of the hit
+						s_items_s[at] = (uint32_t) slot | (rev ? 0x80000000u : 0u);
+					}
+				}
+			}
+		}
+		__syncthreads();
+		const int n_items = (int) s_nitems;
+		if (n_items > kCsMaxItems) {
+			to_exact();
+			return;
+		}
+		int n2 = 1;
+		while (n2 < n_items) n2 <<= 1;
+		for (int i = n_items + tid; i < n2; i += 128) {
+			s_items_t[i] = 0xFFFFFFFFu;
+			s_items_s[i] = 0;
+		}
+		__syncthreads();
+		for (int size = 2; size <= n2; size <<= 1) {           // bitonic sort by sequence number
+			for (int st = size >> 1; st > 0; st >>= 1) {
+				for (int i = tid; i < n2; i += 128) {
+					const int j = i ^ st;
+					if (j > i) {
+						const bool up = (i & size) == 0;
+						const uint32_t a = s_items_t[i], b = s_items_t[j];
+						if ((a > b) == up) {
+							s_items_t[i] = b;
+							s_items_t[j] = a;
+							const uint32_t sa = s_items_s[i];
+							s_items_s[i] = s_items_s[j];
+							s_items_s[j] = sa;
+						}
+					}
+				}
+				__syncthreads();
+			}
+		}
+		// votes of the hit's (entry, strand) right after this hit
+		for (int i = tid; i < n_items; i += 128) {
+			const uint32_t me = s_items_s[i];
+			uint32_t c = 1;
+			for (int j = 0; j < i; ++j) c += (s_items_s[j] == me);
+			s_items_c[i] = (uint16_t) c;
+		}
+		__syncthreads();
+		if (tid == 0) {
+			uint32_t run_max = 0, nord = 0;
+			for (int i = 0; i < n_items; ++i) {
+				const uint32_t c = s_items_c[i];
+				run_max = max(run_max, c);                     // CS.cpp:193-196
+				const uint32_t slot = s_items_s[i] & 0x7FFFFFFFu;
+				const uint32_t cc = cnts[slot];
+				// CS.cpp:199-202: enters rList the first time a hit lifts it to the running threshold
+				if ((cc & 0x8000u) && !(cc & 0x80000000u) && (float) c >= __fmul_rn((float) run_max, P.sensitivity)) {
+					cnts[slot] = cc | 0x80000000u;
+					s_acc[nord++] = slot;
+				}
+			}
+			s_nord = nord;
+		}
+		__syncthreads();
+		if (s_nord != nacc) {                                  // cannot happen; be loud rather than wrong
+			to_exact();
+			return;
+		}
+	}
+	// ---- emit (CollectResultsStd, CS.cpp:286-305) -------------------------------------------------------------
+	if (tid == 0) {
+		const uint32_t off = atomicAdd(cursor, ncand);
+		meta[r].off = off;
+		meta[r].count = ncand;
+		if ((unsigned long long) off + ncand <= heap_cap) {
+			uint32_t w = off;
+			for (uint32_t a = 0; a < nacc; ++a) {
+				const uint32_t slot = s_acc[a];
+				const uint32_t c = cnts[slot];
+				const uint32_t f = c & 0x7FFFu, rv = (c >> 16) & 0x7FFFu;
+				if ((float) f >= thr) {
+					CsCand cd;
+					cd.bin = keys[slot];
+					cd.votes = (uint16_t) f;
+					cd.rev = 0;
+					heap[w++] = cd;
+				}
+				if ((float) rv >= thr) {
+					CsCand cd;
+					cd.bin = keys[slot];
+					cd.votes = (uint16_t) rv;
+					cd.rev = 1;
+					heap[w++] = cd;
+				}
+			}
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// search: exact sequential path (one lane per read, table in global memory)
+// ---------------------------------------------------------------------------------------------------------
+struct CsExactEntry {         // CSTableEntry (LocationScore.h:9-14)
+	uint32_t loc;
+	uint32_t state;
+	float fscore, rscore;
+};
+
+__global__ void __launch_bounds__(32) cs_search_exact_kernel(const CsDev P, const uint8_t *__restrict__ reads, int n_reads, int stride,
+		CsMeta *__restrict__ meta, CsCand *__restrict__ heap, uint32_t heap_cap, uint32_t *__restrict__ cursor, const uint32_t *__restrict__ work_list,
+		const uint32_t *__restrict__ work_count, CsExactEntry *__restrict__ tables, uint32_t *__restrict__ rlists, uint32_t *__restrict__ gens,
+		float *__restrict__ max_hit) {
+	if (threadIdx.x != 0) return;
+	constexpr uint32_t TLEN = 1u << kCsExactBits;
+	CsExactEntry *tab = tables + (size_t) blockIdx.x * TLEN;
+	uint32_t *rlist = rlists + (size_t) blockIdx.x * TLEN;
+	uint32_t gen = gens[blockIdx.x];
+	const uint32_t n_work = work_list != nullptr ? *work_count : (uint32_t) n_reads;
+	for (uint32_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+		const int r = work_list != nullptr ? (int) work_list[w] : (int) w;
+		const uint8_t *seq = reads + (size_t) r * stride;
+		int len = 0;
+		while (len < stride && seq[len] != 0) ++len;
+		gen = (gen + 1) & 0x7FFFFFFFu;                         // CS::RunBatch, CS.cpp:351-356
+		if (gen == 0x7FFFFFFFu) gen = 1;
+		uint32_t rlen = 0;
+		float maxhit = 0.0f, thresh = 0.0f;
+		bool overflow = false;
+		for (int o = 0; o + P.k <= len && !overflow; ++o) {
+			uint32_t prefix;
+			if (!cs_read_kmer(seq, len, o, P.k, prefix)) continue;
+			CsLists L;
+			if (!cs_lookup(P, prefix, L)) continue;
+			const uint64_t corr_r = (uint64_t) len - ((uint64_t) o + (uint64_t) P.k);
+			const uint32_t total = L.fc + L.rc;
+			for (uint32_t i = 0; i < total; ++i) {
+				const bool rev = i >= L.fc;
+				const uint64_t loc = P.table[rev ? L.rs + (i - L.fc) : L.fs + i];
+				const uint64_t bin = (loc - (rev ? corr_r : (uint64_t) o)) >> P.bin_shift;      // GetBin on 64 bits
+				uint32_t e = (uint32_t) ((bin * 11400714819323199488ull) >> (64 - kCsExactBits));      // CS::Hash
+				bool found;
+				uint32_t probes = 0;
+				while ((found = ((tab[e].state & 0x7FFFFFFFu) == gen)) && !((uint64_t) tab[e].loc == bin)) {
+					e = (e + 1) & (TLEN - 1);
+					if (++probes >= TLEN) {
+						overflow = true;
+						break;
+					}
+				}
+				if (overflow) break;
+				float score = 1.0f;
+				if (!found) {
+					tab[e].loc = (uint32_t) bin;
+					tab[e].state = gen;
+					tab[e].fscore = rev ? 0.0f : 1.0f;
+					tab[e].rscore = rev ? 1.0f : 0.0f;
+				} else if (rev) {
+					score = (tab[e].rscore += 1.0f);
+				} else {
+					score = (tab[e].fscore += 1.0f);
+				}
+				if (score > maxhit) {
+					maxhit = score;
+					thresh = __fmul_rn(maxhit, P.sensitivity);
+				}
+				if (!(tab[e].state & 0x80000000u) && score >= thresh) {
+					tab[e].state |= 0x80000000u;
+					rlist[rlen++] = e;
+				}
+			}
+		}
+		if (max_hit != nullptr) max_hit[r] = maxhit;
+		const float thr = fmaxf(P.kmer_min, thresh);
+		uint32_t n = 0;
+		for (uint32_t i = 0; i < rlen && !overflow; ++i) {
+			const CsExactEntry t = tab[rlist[i]];
+			n += (t.fscore >= thr) + (t.rscore >= thr);
+		}
+		if (overflow || !((long long) n < (long long) P.max_cmrs)) n = 0;
+		uint32_t off = 0;
+		if (n) {
+			off = atomicAdd(cursor, n);
+			if ((unsigned long long) off + n <= heap_cap) {
+				uint32_t at = off;
+				for (uint32_t i = 0; i < rlen; ++i) {
+					const CsExactEntry t = tab[rlist[i]];
+					if (t.fscore >= thr) {
+						CsCand cd;
+						cd.bin = t.loc;
+						cd.votes = (uint16_t) t.fscore;
+						cd.rev = 0;
+						heap[at++] = cd;
+					}
+					if (t.rscore >= thr) {
+						CsCand cd;
+						cd.bin = t.loc;
+						cd.votes = (uint16_t) t.rscore;
+						cd.rev = 1;
+						heap[at++] = cd;
+					}
+				}
+			}
+		}
+		meta[r].off = off;
+		meta[r].count = overflow ? 0u : n;
+	}
+	gens[blockIdx.x] = gen;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// CSR assembly: counts -> (exclusive scan on the host side of this file's launcher) -> pairs
+// ---------------------------------------------------------------------------------------------------------
+__global__ void cs_counts_kernel(const CsMeta *__restrict__ meta, int n_reads, int *__restrict__ counts) {
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r > n_reads) return;
+	counts[r] = r < n_reads ? (int) meta[r].count : 0;
+}
+
+// LocationScore -> (read, window) descriptor: Location = ResolveBin(bin) (CS.h:170-175); ScoreBuffer fetches the
+// window at Location - corridor/2 and uses RevSeq for reverse candidates (ScoreBuffer.cpp:92-114)
+__global__ void cs_gather_kernel(const CsMeta *__restrict__ meta, const CsCand *__restrict__ heap, uint32_t heap_cap, const int *__restrict__ begin,
+		int n_reads, int bin_shift, int corridor, uint32_t out_cap, ngm_b200_pair *__restrict__ pairs, float *__restrict__ votes) {
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const CsMeta m = meta[r];
+	const uint32_t b = (uint32_t) begin[r];
+	const unsigned long long half = bin_shift > 0 ? 1ull << (bin_shift - 1) : 0ull;
+	for (uint32_t i = 0; i < m.count; ++i) {
+		if ((unsigned long long) m.off + i >= heap_cap || b + i >= out_cap) break;
+		const CsCand c = heap[m.off + i];
+		ngm_b200_pair p;
+		p.window_start = (((unsigned long long) c.bin << bin_shift) + half) - (unsigned long long) (corridor >> 1);
+		p.read_index = (uint32_t) r;
+		p.flags = c.rev ? (NGM_B200_PAIR_REVERSE | NGM_B200_PAIR_DIR) : 0u;
+		pairs[b + i] = p;
+		if (votes != nullptr) votes[b + i] = (float) c.votes;
+	}
+}
+
+}  // namespace ngm

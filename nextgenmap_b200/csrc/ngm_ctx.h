@@ -1,0 +1,95 @@
+// ngm_ctx.h -- internal: the context behind the C ABI and small host helpers shared by the translation units
+// that implement it (ngm_b200.cu: alignment path, ngm_cs.cu: candidate search).
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "ngm_common.cuh"
+#include "../../include/ngm_b200.h"
+
+namespace ngm {
+
+int fail(int code, const char *fmt, ...);      // records the message for ngm_b200_last_error() and returns `code`
+
+#define CU(call) \
+	do { \
+		cudaError_t e_ = (call); \
+		if (e_ != cudaSuccess) return ngm::fail(NGM_B200_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+
+struct DevBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	cudaError_t ensure(size_t bytes) {
+		if (bytes <= cap) return cudaSuccess;
+		if (p) cudaFree(p);
+		p = nullptr;
+		cap = 0;
+		size_t want = bytes + bytes / 8 + 256;
+		cudaError_t e = cudaMalloc(&p, want);
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release() {
+		if (p) cudaFree(p);
+		p = nullptr;
+		cap = 0;
+	}
+	template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct HostBuf {   // pinned
+	void *p = nullptr;
+	size_t cap = 0;
+	cudaError_t ensure(size_t bytes) {
+		if (bytes <= cap) return cudaSuccess;
+		if (p) cudaFreeHost(p);
+		p = nullptr;
+		cap = 0;
+		size_t want = bytes + bytes / 8 + 256;
+		cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release() {
+		if (p) cudaFreeHost(p);
+		p = nullptr;
+		cap = 0;
+	}
+	template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct CsState;                                 // candidate search: index + scratch (ngm_cs.cu)
+void cs_release(CsState *cs);
+
+}  // namespace ngm
+
+struct ngm_b200_ctx {
+	ngm_b200_params hp;
+	ngm::DevParams dp;
+	int device = 0;
+	int capacity = 0;          // band capacity W
+	int use_s16 = 0;           // s16x2 lanes allowed for the score kernels
+	int align_s16[2] = {0, 0}; // tagged s16x2 align kernel usable in local / end-free mode
+	int score_batch = 0, align_batch = 0;
+	int strict_chunk = 0;      // pairs per strict-path launch
+	int align_chunk = 0;       // alignments per launch (bounded by scratch memory)
+	int win_words = 0;         // strict path: packed words per window
+	int ref_width = 0;         // qml + corridor bytes copied per window (SWOcl.cpp:546)
+	cudaStream_t stream = nullptr;
+	uint64_t launches = 0;
+	// strict-path staging
+	ngm::HostBuf h_reads, h_refs, h_flags, h_scores, h_recs, h_strings, h_cursor, h_noncanon;
+	ngm::DevBuf d_areads, d_arefs, d_flags, d_reads4, d_rlen32, d_rlen, d_wins4, d_pairs, d_scores, d_recs, d_strings, d_cursor, d_noncanon;
+	// align scratch
+	ngm::DevBuf d_ptr, d_ops, d_best, d_known;
+	// descriptor path
+	ngm::DevBuf d_ref4, d_rfwd, d_rrev, d_rrlen32, d_rrlen, d_rascii, d_upairs, d_rpairs;
+	uint64_t concat_len = 0, n_region_nib = 0;
+	int n_reads = 0;
+	int reads_stride = 0;      // bytes per row of d_rascii (set_reads)
+	bool have_ref = false;
+	ngm::CsState *cs = nullptr;
+};

@@ -34,6 +34,21 @@ class Params(C.Structure):
                 ("score_batch", C.c_int32), ("align_batch", C.c_int32), ("lane_mode", C.c_int32)]
 
 
+class CsParams(C.Structure):
+    """ngm_b200_cs_params (include/ngm_b200.h); defaults = src/config/Config.cpp:383-390,512."""
+    _fields_ = [("kmer", C.c_int32), ("kmer_skip", C.c_int32), ("bin_size", C.c_int32), ("skip_rep", C.c_int32), ("sensitivity", C.c_float),
+                ("kmer_min", C.c_float), ("max_kfreq", C.c_int32), ("max_cmrs", C.c_int32)]
+
+
+class _CContigRec(C.Structure):
+    _fields_ = [("start", C.c_uint64), ("length", C.c_uint32), ("name_len", C.c_uint32), ("name", C.c_char * 100)]
+
+
+class _CHtFile(C.Structure):
+    _fields_ = [("kmer", C.c_uint32), ("kmer_skip", C.c_uint32), ("index_len", C.c_uint32), ("table_len", C.c_uint32), ("tab", C.POINTER(C.c_uint32)),
+                ("weight", C.POINTER(C.c_int8)), ("table", C.POINTER(C.c_uint32)), ("unit_offset", C.c_uint64)]
+
+
 class _CAlign(C.Structure):
     _fields_ = [("cigar", C.c_void_p), ("md", C.c_void_p), ("extended", C.c_void_p), ("position_offset", C.c_int32),
                 ("qstart", C.c_int32), ("qend", C.c_int32), ("score", C.c_float), ("identity", C.c_float), ("nm", C.c_int32)]
@@ -94,6 +109,19 @@ def load_library() -> C.CDLL:
     lib.ngm_b200_dev_align_pairs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     lib.ngm_b200_dev_gather_winners_scored.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ngm_b200_dev_align_pairs_scored.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.ngm_b200_cs_build_index.argtypes = [C.c_void_p, C.POINTER(CsParams), C.c_void_p, C.c_uint32]
+    lib.ngm_b200_cs_load_index.argtypes = [C.c_void_p, C.POINTER(CsParams), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+    lib.ngm_b200_cs_index_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
+    lib.ngm_b200_cs_export_index.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ngm_b200_cs_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                       C.POINTER(C.c_size_t), C.c_void_p]
+    lib.ngm_b200_cs_exact_reads.restype = C.c_uint64
+    lib.ngm_b200_cs_exact_reads.argtypes = [C.c_void_p]
+    lib.ngm_b200_dev_cs_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                           C.c_void_p, C.c_void_p]
+    lib.ngm_b200_read_ht_file.argtypes = [C.c_char_p, C.POINTER(_CHtFile)]
+    lib.ngm_b200_free_ht_file.argtypes = [C.POINTER(_CHtFile)]
+    lib.ngm_b200_write_ht_file.argtypes = [C.c_char_p, C.POINTER(_CHtFile)]
     lib.ngm_b200_dev_select_top1.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
@@ -237,6 +265,65 @@ class CudaSW:
             break
         return recs, heap[: used.value]
 
+    # -- candidate search (CS / CompactPrefixTable) ---------------
+    @staticmethod
+    def cs_params(kmer: int = 13, kmer_skip: int = 2, bin_size: int = 2, skip_rep: int = 1, sensitivity: float = 0.5, kmer_min: float = 0.0,
+                  max_kfreq: int = 0, max_cmrs: int = 0) -> CsParams:
+        return CsParams(kmer, kmer_skip, bin_size, skip_rep, sensitivity, kmer_min, max_kfreq, max_cmrs)
+
+    def cs_build_index(self, contigs, params: Optional[CsParams] = None) -> dict:
+        """contigs: [(start, length)] in concatenated coordinates (SeqStart, SeqLen).  Needs set_reference first."""
+        params = params or self.cs_params()
+        arr = (_CContigRec * len(contigs))()
+        for i, (st, ln) in enumerate(contigs):
+            arr[i].start, arr[i].length, arr[i].name_len = st, ln, 0
+        self._check(self.lib.ngm_b200_cs_build_index(self.ctx, C.byref(params), arr, len(contigs)))
+        return self.cs_index_info()
+
+    def cs_load_index(self, tab: np.ndarray, weight: np.ndarray, table: np.ndarray, params: Optional[CsParams] = None) -> dict:
+        params = params or self.cs_params()
+        tab = np.ascontiguousarray(tab, dtype=np.uint32)
+        weight = np.ascontiguousarray(weight, dtype=np.int8)
+        table = np.ascontiguousarray(table, dtype=np.uint32)
+        self._check(self.lib.ngm_b200_cs_load_index(self.ctx, C.byref(params), tab.ctypes.data, weight.ctypes.data, len(tab), table.ctypes.data, len(table)))
+        return self.cs_index_info()
+
+    def cs_index_info(self) -> dict:
+        il, tl, mk = C.c_uint32(0), C.c_uint32(0), C.c_int32(0)
+        self._check(self.lib.ngm_b200_cs_index_info(self.ctx, C.byref(il), C.byref(tl), C.byref(mk)))
+        return {"index_len": il.value, "table_len": tl.value, "max_kfreq": mk.value}
+
+    def cs_export_index(self):
+        info = self.cs_index_info()
+        tab = np.zeros(info["index_len"], np.uint32)
+        weight = np.zeros(info["index_len"], np.int8)
+        table = np.zeros(max(info["table_len"], 1), np.uint32)
+        self._check(self.lib.ngm_b200_cs_export_index(self.ctx, tab.ctypes.data, weight.ctypes.data, table.ctypes.data))
+        return tab, weight, table[: info["table_len"]]
+
+    def cs_search(self, reads: np.ndarray, exact_only: bool = False, capacity: Optional[int] = None):
+        """-> (cand_begin int32 [n+1], pairs PAIR [total], votes float32 [total], max_hit float32 [n])"""
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        n, stride = reads.shape
+        begin = np.zeros(n + 1, np.int32)
+        mh = np.zeros(n, np.float32)
+        cap = capacity or max(1024, 8 * n)
+        total = C.c_size_t(0)
+        for _ in range(2):
+            pairs = np.zeros(cap, dtype=PAIR)
+            votes = np.zeros(cap, np.float32)
+            rc = self.lib.ngm_b200_cs_search(self.ctx, reads.ctypes.data, n, stride, 1 if exact_only else 0, begin.ctypes.data, pairs.ctypes.data,
+                                             votes.ctypes.data, cap, C.byref(total), mh.ctypes.data)
+            if rc == -3 and total.value > cap:
+                cap = total.value + 16
+                continue
+            self._check(rc)
+            break
+        return begin, pairs[: total.value], votes[: total.value], mh
+
+    def cs_exact_reads(self) -> int:
+        return int(self.lib.ngm_b200_cs_exact_reads(self.ctx))
+
     @staticmethod
     def strings_of(recs: np.ndarray, heap: np.ndarray, i: int):
         r = recs[i]
@@ -280,3 +367,31 @@ class EncodedReference:
     def close(self):
         if self.c.packed:
             self.lib.ngm_b200_free_enc_ref(C.byref(self.c))
+
+
+class PrefixTableFile:
+    """`<ref>-ht-<k>-<skip>.3.ngm` (CompactPrefixTable::saveToFile / readFromFile, PrefixTable.cpp:819-921).  Host only."""
+
+    def __init__(self, path: str):
+        self.lib = load_library()
+        c = _CHtFile()
+        rc = self.lib.ngm_b200_read_ht_file(str(path).encode(), C.byref(c))
+        if rc != 0:
+            raise NgmB200Error(f"cannot read prefix table file {path} (rc {rc})")
+        self.kmer, self.kmer_skip, self.index_len, self.table_len = int(c.kmer), int(c.kmer_skip), int(c.index_len), int(c.table_len)
+        self.unit_offset = int(c.unit_offset)
+        self.tab = np.ctypeslib.as_array(c.tab, shape=(self.index_len,)).copy()
+        self.weight = np.ctypeslib.as_array(c.weight, shape=(self.index_len,)).copy()
+        self.table = np.ctypeslib.as_array(c.table, shape=(max(self.table_len, 1),)).copy()[: self.table_len]
+        self.lib.ngm_b200_free_ht_file(C.byref(c))
+
+    @staticmethod
+    def write(path: str, kmer: int, kmer_skip: int, tab: np.ndarray, weight: np.ndarray, table: np.ndarray) -> None:
+        lib = load_library()
+        tab = np.ascontiguousarray(tab, dtype=np.uint32)
+        weight = np.ascontiguousarray(weight, dtype=np.int8)
+        table = np.ascontiguousarray(table, dtype=np.uint32)
+        c = _CHtFile(kmer, kmer_skip, len(tab), len(table), tab.ctypes.data_as(C.POINTER(C.c_uint32)), weight.ctypes.data_as(C.POINTER(C.c_int8)),
+                     table.ctypes.data_as(C.POINTER(C.c_uint32)), 0)
+        if lib.ngm_b200_write_ht_file(str(path).encode(), C.byref(c)) != 0:
+            raise NgmB200Error(f"cannot write {path}")

@@ -1,0 +1,149 @@
+"""Candidate search on the device against the oracle pinned to the reference (oracle/cs_oracle.c) and
+against the fixtures the reference's own code produced (tests/golden/cs): prefix table (index, weights, position table,
+max_kfreq) and per-read candidate lists -- set, votes, ORDER -- through both the block-per-read kernel and the
+sequential exact kernel."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import cs_port, port
+from tests import cs_cases
+
+pytestmark = pytest.mark.gpu
+
+GOLD = Path(__file__).resolve().parent / "golden" / "cs"
+NAMES = sorted(p.stem for p in GOLD.glob("*.npz"))
+
+
+def load(name):
+    with np.load(GOLD / f"{name}.npz") as z:
+        return {k: z[k] for k in z.files}
+
+
+def lists_from_device(begin, pairs, votes, mh, corridor):
+    out = {}
+    for r in range(len(begin) - 1):
+        b, e = int(begin[r]), int(begin[r + 1])
+        out[r] = (float(mh[r]), [((int(pairs["window_start"][j]) + (corridor >> 1)) & (2 ** 64 - 1), int(pairs["flags"][j]) & 1, float(votes[j]))
+                                 for j in range(b, e)])
+    return out
+
+
+def shapes_for(read_len):
+    return (read_len | 1) + 1, int(5 + 0.15 * read_len)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_index_and_candidates_match_reference_fixture(name):
+    from nextgenmap_b200.host import CudaSW
+    g = load(name)
+    k, read_len = int(g["k"]), int(g["read_len"])
+    concat = g["concat"].tobytes()
+    ctg = [(int(a), int(b)) for a, b in g["contigs"]]
+    qml, cor = shapes_for(read_len)
+    sw = CudaSW(qml, cor)
+    sw.set_reference(port.pack_ref(concat), len(concat) - 1)
+    info = sw.cs_build_index(ctg, sw.cs_params(kmer=k, sensitivity=float(g["sensitivity"])))
+    assert info["table_len"] == int(g["ht_table_len"]) and info["max_kfreq"] == int(g["max_kfreq"])
+    tab, weight, table = sw.cs_export_index()
+    used = np.nonzero(weight != 0)[0].astype(np.uint32)
+    np.testing.assert_array_equal(used, g["ht_used_prefix"])
+    np.testing.assert_array_equal(weight[used], g["ht_used_weight"])
+    np.testing.assert_array_equal(tab[used + 1] - tab[used], g["ht_used_count"])
+    np.testing.assert_array_equal(table, g["ht_table"])
+    want = {}
+    for i, r in enumerate(g["read_index"]):
+        b, e = int(g["cand_begin"][i]), int(g["cand_begin"][i + 1])
+        want[int(r)] = (float(g["max_hit"][i]), [(int(g["cand_loc"][j]), int(g["cand_rev"][j]), float(g["cand_votes"][j])) for j in range(b, e)])
+    for exact in (False, True):
+        got = lists_from_device(*sw.cs_search(g["reads"], exact_only=exact), cor)
+        bad = [(r, want[r], got[r]) for r in want if want[r] != got[r]]
+        assert not bad, f"exact={exact}: {len(bad)} reads differ, first {bad[0]}"
+        if not exact:
+            assert sw.cs_exact_reads() < len(want)            # the block-per-read kernel did the bulk of the work
+    sw.close()
+
+
+@pytest.mark.parametrize("seed,k,read_len,sens,scale", [(51, 13, 150, 0.5, 4), (52, 12, 100, 0.3, 2), (53, 13, 250, 0.8, 3), (54, 11, 400, 0.5, 1),
+                                                        (55, 10, 36, 0.5, 1), (56, 13, 1000, 0.5, 2)])
+def test_fresh_cases_against_oracle(seed, k, read_len, sens, scale):
+    from nextgenmap_b200.host import CudaSW
+    contigs = cs_cases.make_reference(seed, scale)
+    concat, ctg, concat_len = cs_port.layout(contigs)
+    qml, cor = shapes_for(read_len)
+    reads = cs_cases.make_reads(seed + 1, concat, ctg, 700, read_len, qml)
+    ix = cs_port.Index(port.pack_ref(concat), concat_len, ctg, k=k)
+    sw = CudaSW(qml, min(cor, 155))
+    sw.set_reference(port.pack_ref(concat), concat_len)
+    info = sw.cs_build_index(ctg, sw.cs_params(kmer=k, sensitivity=sens))
+    assert info["table_len"] == ix.table_len and info["max_kfreq"] == ix.max_kfreq
+    tab, weight, table = sw.cs_export_index()
+    np.testing.assert_array_equal(tab, ix.tab)
+    np.testing.assert_array_equal(weight, ix.weight)
+    np.testing.assert_array_equal(table, ix.table)
+    begin, cands, mh = ix.search(reads, sens)
+    want = {r: (float(mh[r]), [(int(c["location"]), int(c["reverse"]), float(c["score"])) for c in cands[begin[r]: begin[r + 1]]])
+            for r in range(reads.shape[0])}
+    for exact in (False, True):
+        got = lists_from_device(*sw.cs_search(reads, exact_only=exact), min(cor, 155))
+        bad = [(r, want[r], got[r]) for r in want if want[r] != got[r]]
+        assert not bad, f"exact={exact}: {len(bad)} reads differ, first {bad[0]}"
+    ix.close()
+    sw.close()
+
+
+def test_index_loaded_from_file_arrays_equals_built_index():
+    """cs_load_index with the oracle's arrays (= what NGM's ht file holds) searches like the built index."""
+    from nextgenmap_b200.host import CudaSW
+    contigs = cs_cases.make_reference(77)
+    concat, ctg, concat_len = cs_port.layout(contigs)
+    reads = cs_cases.make_reads(78, concat, ctg, 500, 100, 102)
+    ix = cs_port.Index(port.pack_ref(concat), concat_len, ctg, k=11)
+    a, b = CudaSW(102, 20), CudaSW(102, 20)
+    a.set_reference(port.pack_ref(concat), concat_len)
+    a.cs_build_index(ctg, a.cs_params(kmer=11))
+    info = b.cs_load_index(ix.tab, ix.weight, ix.table, b.cs_params(kmer=11))
+    assert info["max_kfreq"] == ix.max_kfreq
+    ra, rb = a.cs_search(reads), b.cs_search(reads)
+    for x, y in zip(ra, rb):
+        np.testing.assert_array_equal(x, y)
+    a.close()
+    b.close()
+
+
+def test_candidates_feed_the_alignment_path():
+    """reads -> cs_search -> score_pairs -> top-1: the true locus wins for clean reads (pipeline plumbing)."""
+    from nextgenmap_b200.host import CudaSW
+    rng = np.random.default_rng(3)
+    seq = cs_cases.ACGT[rng.integers(0, 4, 400_000)].tobytes()
+    concat, ctg, concat_len = cs_port.layout([seq])
+    L, qml, cor = 150, 152, 27
+    n = 2000
+    reads = np.zeros((n, qml), np.uint8)
+    truth = np.zeros(n, np.int64)
+    for r in range(n):
+        pos = int(rng.integers(0, len(seq) - L))
+        s = np.frombuffer(seq[pos: pos + L], np.uint8).copy()
+        mut = rng.random(L) < 0.02
+        s[mut] = cs_cases.ACGT[rng.integers(0, 4, int(mut.sum()))]
+        b = s.tobytes()
+        if r & 1:
+            b = b.translate(cs_cases.COMP)[::-1]
+        reads[r, :L] = np.frombuffer(b, np.uint8)
+        truth[r] = 1000 + pos
+    sw = CudaSW(qml, cor)
+    sw.set_reference(port.pack_ref(concat), concat_len)
+    sw.cs_build_index(ctg, sw.cs_params(kmer=13))
+    begin, pairs, votes, mh = sw.cs_search(reads)
+    sw.set_reads(reads)
+    scores = sw.score_pairs(0, pairs)
+    hit = 0
+    for r in range(n):
+        b, e = begin[r], begin[r + 1]
+        if e > b:
+            j = b + int(np.argmax(scores[b:e]))
+            loc = int(pairs["window_start"][j]) + (cor >> 1)
+            hit += abs(loc - truth[r]) <= 8 and (int(pairs["flags"][j]) & 1) == (r & 1)
+    assert hit >= 0.99 * n, hit
+    sw.close()
