@@ -62,6 +62,8 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cs", action="store_true", help="skip the candidate-search section (index build + k-mer vote on device)")
+    ap.add_argument("--sensitivity", type=float, default=0.5, help="CS sensitivity (NGM -s; its own default when not estimated)")
     return ap.parse_args()
 
 
@@ -459,6 +461,81 @@ def main():
         for lane in lanes:
             lane["sw"].close()
 
+    # ---- candidate search on device: reads -> k-mer vote -> candidates -> score -> top1 -> align ----
+    cs_info = None
+    if not args.no_cs:
+        try:
+            from nextgenmap_b200.host.cuda_sw import CsParams, _CContigRec
+            import ctypes as C
+            K_MER, K_SKIP, BIN = 13, 2, 2
+            contig_arr = (_CContigRec * args.contigs)()
+            for i, s0 in enumerate(ref.contig_start):
+                contig_arr[i].start, contig_arr[i].length, contig_arr[i].name_len = int(s0), int(ref.contig_len), 0
+            csp = CsParams(K_MER, K_SKIP, BIN, 1, args.sensitivity, 0.0, 0, 0)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            check(lib.ngm_b200_cs_build_index(ctx, C.byref(csp), contig_arr, args.contigs))
+            torch.cuda.synchronize()
+            build_s = time.perf_counter() - t0
+            info = sw.cs_index_info()
+            cap = 3 * n + 1024
+            d_cb = torch.empty(n + 1, dtype=torch.int32, device=dev)
+            d_cpairs = torch.empty((cap, 16), dtype=torch.uint8, device=dev)
+            d_cvotes = torch.empty(cap, dtype=torch.float32, device=dev)
+            d_cscores = torch.empty(cap, dtype=torch.float32, device=dev)
+
+            def cs_only():
+                check(lib.ngm_b200_dev_cs_search(ctx, batch.reads.data_ptr(), n, qml, 0, d_cb.data_ptr(), d_cpairs.data_ptr(), d_cvotes.data_ptr(), cap, None, st))
+
+            def cs_pipeline_step():
+                check(lib.ngm_b200_dev_set_reads(ctx, batch.reads.data_ptr(), n, qml, st))
+                cs_only()
+                total = int(d_cb[n].item())                      # the one host sync of the step: number of candidates
+                if total > cap:
+                    raise RuntimeError(f"candidate buffer too small ({total} > {cap})")
+                check(lib.ngm_b200_dev_score_pairs(ctx, MODE_LOCAL, total, d_cpairs.data_ptr(), d_cscores.data_ptr(), st))
+                check(lib.ngm_b200_dev_select_top1(ctx, n, d_cb.data_ptr(), d_cscores.data_ptr(), d_best.data_ptr(), d_mapq.data_ptr(), st))
+                check(lib.ngm_b200_dev_gather_winners_scored(ctx, n, d_cpairs.data_ptr(), d_cscores.data_ptr(), d_best.data_ptr(), d_wpairs.data_ptr(),
+                                                             d_wscores.data_ptr(), st))
+                d_cursor.zero_()
+                check(lib.ngm_b200_dev_align_pairs_scored(ctx, MODE_LOCAL, n, d_wpairs.data_ptr(), d_wscores.data_ptr(), d_recs.data_ptr(),
+                                                          d_strings.data_ptr(), str_cap, d_cursor.data_ptr(), st))
+                return total
+
+            ms_cs = time_call(cs_only, reps=3)
+            total_c = cs_pipeline_step()
+            torch.cuda.synchronize()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            a_.record()
+            reps = max(2, min(args.steps, 5))
+            for _ in range(reps):
+                cs_pipeline_step()
+            b_.record()
+            barrier()
+            ms_pipe = sharding.max_over_ranks(a_.elapsed_time(b_) / reps, dev)
+            # sanity against the generator's truth: the winner of every read sits at the locus the read was drawn from
+            wp = d_wpairs.view(torch.int64).view(n, 2)
+            loc = wp[:, 0] + (corridor >> 1)
+            wflags = (wp[:, 1] >> 32) & 0xFFFFFFFF
+            ok_pos = ((loc - batch.true_pos).abs() <= corridor) & ((wflags & 1).bool() == batch.reverse) & ((wflags & 4) == 0)
+            recs_cs = d_recs.cpu().numpy().view(ALIGN_REC).reshape(-1)
+            n_kmers = L - K_MER + 1
+            mean_list = info["table_len"] / float(4 ** K_MER)
+            alg_bytes_read = n_kmers * 2 * 8 + n_kmers * 2 * mean_list * 4 + L
+            cs_info = {"kmer": K_MER, "kmer_skip": K_SKIP, "bin_size": BIN, "sensitivity": args.sensitivity, "max_kfreq": info["max_kfreq"],
+                       "index_positions": info["table_len"], "index_build_seconds": build_s, "index_bytes": 4 * (4 ** K_MER + 1) + 4 * info["table_len"],
+                       "cs_ms": ms_cs, "cs_reads_per_s": n / (ms_cs * 1e-3), "candidates": int(total_c), "candidates_per_read": total_c / n,
+                       "pipeline_step": "set_reads -> cs_search (k-mer vote) -> score all candidates -> top1+MAPQ -> gather -> align+backtrace+CIGAR/MD",
+                       "pipeline_ms": ms_pipe, "pipeline_reads_per_s": world * n / (ms_pipe * 1e-3),
+                       "winner_at_true_locus": float(ok_pos.float().mean().item()), "mapped": int(np.count_nonzero(recs_cs["score"] >= 0)),
+                       "roofline": {"kernel": "cs_search_kernel", "bound": "hbm", "algorithmic_bytes_per_read": alg_bytes_read,
+                                    "achieved": alg_bytes_read * n / (ms_cs * 1e-3) / 1e9, "unit": "GB/s",
+                                    "note": "2 index lookups of 8 B and 2 position lists of ~%.1f x 4 B per k-mer, %d k-mers per read" % (mean_list, n_kmers)}}
+            del d_cpairs, d_cvotes, d_cscores, d_cb
+        except Exception as e:  # noqa: BLE001
+            cs_info = {"error": str(e)}
+
     # ---- reductions over ranks ----------------------------------------------
     ms_max = sharding.max_over_ranks(ms, dev)
     ctr = sharding.reduce_counters({"reads": n, "mapped": mapped, "pairs_scored": npairs}, dev)      # NGM.cpp:172-201
@@ -543,6 +620,9 @@ def main():
         peaks = json.loads(pk.read_text())
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    if cs_info and "roofline" in cs_info:
+        cs_info["roofline"]["peak"] = hbm_peak
+        cs_info["roofline"]["frac"] = cs_info["roofline"]["achieved"] / hbm_peak
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
     sm_mhz = clk.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
     dominant = "score" if ms_score >= ms_align else "align"
@@ -579,6 +659,7 @@ def main():
                          "definition": f"cells = L x corridor = {CELLS_PER_PAIR} per pair; peak = SMs x 128 lanes x max clock / 5 instr per cell (SURVEY 8d)"},
         "kernel_ms": {"set_reads": ms_pack, "score": ms_score, "align": ms_align, "align_without_known_scores": ms_align_unscored, "score_share": ms_score / (ms_max / args.steps),
                       "align_share": ms_align / (ms_max / args.steps)},
+        "candidate_search": cs_info,
         "cpu_baseline": cpu_baseline, "parity_sample": parity, "strict_path": strict,
         "counters": {"reads": total_reads, "mapped": ctr["mapped"], "pairs_scored": ctr["pairs_scored"], "string_bytes": used_strings},
         "setup_seconds": setup_s, "host_threads": host_threads,

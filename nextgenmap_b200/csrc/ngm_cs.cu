@@ -34,6 +34,7 @@ struct CsState {
 	HostBuf h_total;
 	int ex_blocks = 0;
 	uint64_t exact_reads = 0;      // reads the last search sent to the exact kernel
+	bool exact_all = false;
 };
 
 void cs_release(CsState *cs) {
@@ -360,23 +361,35 @@ int ngm_b200_dev_cs_search(ngm_b200_ctx *c, const void *d_ascii_reads, int n_rea
 	uint32_t *cursor = cs->d_cursor.as<uint32_t>();
 	float *max_hit = static_cast<float *>(d_max_hit);
 	const bool exact_only = (mode_flags & 1) != 0;
+	bool exact_only_fallback = false;
+	cs->exact_all = exact_only;
+	cs->exact_reads = (uint64_t) n_reads;
 	if (!exact_only) {
-		// expected distinct bins per read ~ (L - k + 1) x 2 lists x mean list length; 8192 slots serve <= ~170 bp
-		const bool big = stride > 176;
-		if (big) {
-			CU(cudaFuncSetAttribute(cs_search_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 * 4));
-			cs_search_kernel<14><<<n_reads, 128, 2 * 16384 * 4, st>>>(P, reads, n_reads, stride, meta, heap, capacity, cursor, cs->d_slow_list.as<uint32_t>(),
+		// table size by the expected number of distinct bins per read: ~ (L - k + 1) k-mers x 2 lists x mean list length
+		auto launch = [&](auto kern, size_t smem) -> cudaError_t {
+			cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+			if (e != cudaSuccess) return e;
+			kern<<<n_reads, 256, smem, st>>>(P, reads, n_reads, stride, meta, heap, capacity, cursor, cs->d_slow_list.as<uint32_t>(),
 					cs->d_slow_count.as<uint32_t>(), max_hit);
+			return cudaGetLastError();
+		};
+		const double mean_list = (double) cs->table_len / (double) cs->n_prefix;
+		const double expect = (double) std::max(1, stride - cs->k + 1) * 2.0 * std::max(mean_list, 0.5);      // hits per read
+		const bool bins_fit = ((c->concat_len + 1024) >> cs->bin_shift) < (1ull << 30);      // two flag bits ride on every stored bin
+		if (!bins_fit) {
+			cs->exact_all = true;                                  // (bin_size 0/1 on > 1 Gbp: sequential kernel only)
+			exact_only_fallback = true;
+		} else if (stride - cs->k + 1 <= 256 && expect <= 4250.0) {
+			CU(launch(cs_search_kernel<11, 256, 4608>, CsSmem<11, 256, 4608>::bytes));
+		} else if (stride - cs->k + 1 <= 512 && expect <= 14000.0) {
+			CU(launch(cs_search_kernel<12, 512, 16384>, CsSmem<12, 512, 16384>::bytes));
 		} else {
-			CU(cudaFuncSetAttribute(cs_search_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4));
-			cs_search_kernel<13><<<n_reads, 128, 2 * 8192 * 4, st>>>(P, reads, n_reads, stride, meta, heap, capacity, cursor, cs->d_slow_list.as<uint32_t>(),
-					cs->d_slow_count.as<uint32_t>(), max_hit);
+			CU(launch(cs_search_kernel<12, 1024, 36864>, CsSmem<12, 1024, 36864>::bytes));
 		}
 		c->launches += 1;
-		CU(cudaGetLastError());
 	}
 	cs_search_exact_kernel<<<cs->ex_blocks, 32, 0, st>>>(P, reads, n_reads, stride, meta, heap, capacity, cursor,
-			exact_only ? nullptr : cs->d_slow_list.as<uint32_t>(), cs->d_slow_count.as<uint32_t>(), cs->d_ex_tables.as<CsExactEntry>(),
+			(exact_only || exact_only_fallback) ? nullptr : cs->d_slow_list.as<uint32_t>(), cs->d_slow_count.as<uint32_t>(), cs->d_ex_tables.as<CsExactEntry>(),
 			cs->d_ex_rlists.as<uint32_t>(), cs->d_ex_gens.as<uint32_t>(), max_hit);
 	c->launches += 1;
 	CU(cudaGetLastError());
@@ -423,9 +436,6 @@ int ngm_b200_cs_search(ngm_b200_ctx *c, const char *reads, int n_reads, int stri
 	d_mh.release();
 	const size_t tot = (size_t) cand_begin[n_reads];
 	if (total) *total = tot;
-	uint32_t slow = 0;
-	CU(cudaMemcpy(&slow, cs->d_slow_count.p, 4, cudaMemcpyDeviceToHost));
-	cs->exact_reads = (mode_flags & 1) ? (uint64_t) n_reads : slow;
 	if (tot > capacity) return fail(NGM_B200_ERANGE, "candidate buffer too small: %zu entries needed", tot);
 	if (tot) {
 		CU(cudaMemcpy(pairs, cs->d_pairs.p, tot * sizeof(ngm_b200_pair), cudaMemcpyDeviceToHost));
@@ -434,6 +444,14 @@ int ngm_b200_cs_search(ngm_b200_ctx *c, const char *reads, int n_reads, int stri
 	return n_reads;
 }
 
-uint64_t ngm_b200_cs_exact_reads(const ngm_b200_ctx *c) { return (c && c->cs) ? c->cs->exact_reads : 0; }
+uint64_t ngm_b200_cs_exact_reads(const ngm_b200_ctx *c) {
+	if (c == nullptr || c->cs == nullptr) return 0;
+	if (c->cs->exact_all) return c->cs->exact_reads;
+	uint32_t slow = 0;                                         // counter of the last search (synchronises the device)
+	if (c->cs->d_slow_count.p == nullptr || cudaSetDevice(c->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+			cudaMemcpy(&slow, c->cs->d_slow_count.p, 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+		return 0;
+	return slow;
+}
 
 }  // extern "C"

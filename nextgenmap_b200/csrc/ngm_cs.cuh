@@ -10,9 +10,9 @@
 // table[] = reference positions grouped by k-mer, ascending inside a group (the order the reference's sequential
 // fill produces).  3 Gbp, k 13, every 3rd position: 268 MB + 4.1 GB.
 //
-// Search: one 128-thread block per read.  Every thread takes one k-mer of the read, looks up the forward and the
-// reverse-complement list and votes for bin (position - offset) >> bin_size in an open-addressed table in shared
-// memory (64 or 128 KB: 8192 / 16384 slots of {bin, fwd votes | rev votes << 16}).  The reference's result only
+// Search: one 256-thread block per read (details above cs_search_kernel): every k-mer of the read is looked up
+// (forward and reverse-complement list) and every hit votes for bin (position - offset) >> bin_size; votes are
+// counted exactly in shared memory behind a "seen" bitmap that filters the single-vote noise.  The reference's result only
 // depends on the final votes, except for the ORDER of a read's candidates, which is the order in which entries first
 // reached the running threshold sensitivity x max-votes-so-far while hits arrive in k-mer order.  That order is
 // reconstructed exactly for the few reads that need it (more than one accepted entry): the hits of all entries that
@@ -260,39 +260,77 @@ __device__ __forceinline__ bool cs_lookup(const CsDev &P, uint32_t prefix, CsLis
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// search: fast path, one block per read
+// search: fast path, one 256-thread block per read
+//
+// Almost all hits of a read are noise: bins that are hit exactly once (~4100 of ~4150 at 150 bp on 3 Gbp).  Only
+// bins hit at least twice can reach a threshold above one vote, so the hits are first run through a 64 Kbit
+// "seen" bitmap (one ATOMS.OR each, no probing); only hits that find their bit already set (true repeats plus ~3 %
+// false positives) enter a small exact table (double hashing, load < 0.2).  A second sweep over the hits -- kept
+// in shared memory as 32-bit bins -- adds the one hit per repeated bin that set the bit and was therefore not counted.
+//
+//   A  every thread takes one k-mer of the read: validity, code, the two index lookups -> list descriptors in
+//      shared memory; block-wide exclusive scan of the list lengths = sequence number of every hit
+//   B  every warp takes a k-mer: lanes load one position each (fwd list then rev list: one coalesced ~60-byte
+//      read per list), eight k-mers in flight per warp; bitmap test, insert of repeats, bins[] <- hit
+//   C  second sweep: first hits of the table's bins
+//   D  maximum, threshold, accepted entries (table scan: 2048 slots)
+//   E  only if more than one entry is accepted: the order of the list (see the header of this file)
+// Reads whose single-vote bins can pass (threshold <= 1: nothing aligns well), with more hits than MAXH or a crowded
+// table go to the exact kernel.
 // ---------------------------------------------------------------------------------------------------------
-template <int TS_LOG>
-__global__ void __launch_bounds__(128) cs_search_kernel(const CsDev P, const uint8_t *__restrict__ reads, int n_reads, int stride,
+constexpr int kCsBitmapWords = 1024;                           // 32768 bits each: "seen" and "repeated"
+constexpr int kCsQueue = 768;                                  // hits per read that find their bit set (repeats + false positives)
+constexpr uint32_t kHitInserted = 0x80000000u, kHitRev = 0x40000000u, kHitBin = 0x3FFFFFFFu;
+
+template <int T2_LOG, int MAXK, int MAXH>
+struct CsSmem {
+	static constexpr int T2 = 1 << T2_LOG;
+	static constexpr size_t bytes = (size_t) kCsBitmapWords * 8 + (size_t) T2 * 8 + (size_t) MAXH * 4 + (size_t) MAXK * 8 + ((size_t) MAXK + 4) * 4 +
+			(size_t) MAXK * 4 + (size_t) MAXK + 32;
+};
+
+template <int T2_LOG, int MAXK, int MAXH>
+__global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uint8_t *__restrict__ reads, int n_reads, int stride,
 		CsMeta *__restrict__ meta, CsCand *__restrict__ heap, uint32_t heap_cap, uint32_t *__restrict__ cursor, uint32_t *__restrict__ slow_list,
 		uint32_t *__restrict__ slow_count, float *__restrict__ max_hit) {
-	constexpr int TS = 1 << TS_LOG;
-	constexpr uint32_t MASK = TS - 1;
+	constexpr int T2 = 1 << T2_LOG;
+	constexpr uint32_t MASK = T2 - 1;
+	constexpr int NT = 256;
+	constexpr int IPT = MAXK / NT;                             // list descriptors per thread in the scan
+	static_assert(MAXK % NT == 0, "MAXK must be a multiple of the block size");
 	extern __shared__ uint32_t s_dyn[];
-	uint32_t *keys = s_dyn, *cnts = s_dyn + TS;
-	__shared__ uint8_t s_read[kCsMaxStride + 16];
-	__shared__ uint32_t s_items_t[kCsMaxItems], s_items_s[kCsMaxItems];
+	uint32_t *seen = s_dyn, *rep = seen + kCsBitmapWords, *keys = rep + kCsBitmapWords, *cnts = keys + T2, *bins = cnts + T2;
+	uint32_t *kfs = bins + MAXH, *krs = kfs + MAXK, *kbase = krs + MAXK;      // kbase: MAXK + 4 entries
+	uint16_t *kfc = reinterpret_cast<uint16_t *>(kbase + MAXK + 4), *krc = kfc + MAXK;
+	uint8_t *s_read = reinterpret_cast<uint8_t *>(krc + MAXK);            // MAXK + 32 bytes >= stride (stride - k + 1 <= MAXK, k <= 14)
+	__shared__ uint32_t s_items_s[kCsMaxItems];
 	__shared__ uint16_t s_items_c[kCsMaxItems];
 	__shared__ uint32_t s_acc[kCsMaxAccepted];
+	__shared__ uint32_t s_warp[NT / 32];
 	__shared__ int s_len;
-	__shared__ uint32_t s_max, s_any, s_distinct, s_slow, s_nacc, s_ncand, s_nitems, s_nord;
-	const int tid = threadIdx.x;
+	__shared__ uint32_t s_queue[kCsQueue];
+	uint32_t *s_items_t = s_queue;                             // the queue is dead by the time the order is worked out
+	static_assert(kCsQueue >= kCsMaxItems, "items reuse the queue");
+	__shared__ uint32_t s_max, s_slow, s_nent, s_nacc, s_ncand, s_nitems, s_nord, s_nq;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int r = blockIdx.x;
 	if (r >= n_reads) return;
 	if (tid == 0) {
 		s_len = stride;
-		s_max = s_any = s_distinct = s_slow = s_nacc = s_ncand = s_nitems = s_nord = 0;
+		s_max = s_slow = s_nent = s_nacc = s_ncand = s_nitems = s_nord = s_nq = 0;
 	}
 	{
+		uint4 *z4 = reinterpret_cast<uint4 *>(seen);               // both bitmaps
+		for (int i = tid; i < 2 * kCsBitmapWords / 4; i += NT) z4[i] = make_uint4(0, 0, 0, 0);
 		uint4 *k4 = reinterpret_cast<uint4 *>(keys), *c4 = reinterpret_cast<uint4 *>(cnts);
-		for (int i = tid; i < TS / 4; i += 128) {
+		for (int i = tid; i < T2 / 4; i += NT) {
 			k4[i] = make_uint4(kCsEmpty, kCsEmpty, kCsEmpty, kCsEmpty);
 			c4[i] = make_uint4(0, 0, 0, 0);
 		}
 	}
-	__syncthreads();
 	const uint8_t *src = reads + (size_t) r * stride;
-	for (int i = tid; i < stride; i += 128) {
+	__syncthreads();
+	for (int i = tid; i < stride; i += NT) {
 		const uint8_t c = src[i];
 		s_read[i] = c;
 		if (c == 0) atomicMin(&s_len, i);                  // MappedRead::length
@@ -300,46 +338,55 @@ __global__ void __launch_bounds__(128) cs_search_kernel(const CsDev P, const uin
 	__syncthreads();
 	const int len = s_len;
 	const int k = P.k;
-	const int n_kmers = len - k + 1;
+	const int n_kmers = max(0, len - k + 1);                   // <= MAXK (checked by the launcher: stride - k + 1 <= MAXK)
 
-	// ---- vote -------------------------------------------------------------------------------------------
-	for (int o = tid; o < n_kmers; o += 128) {
-		uint32_t prefix;
-		if (!cs_read_kmer(s_read, len, o, k, prefix)) continue;
-		CsLists L;
-		if (!cs_lookup(P, prefix, L)) continue;
-		const uint32_t corr_r = (uint32_t) (len - (o + k));
-		const uint32_t total = L.fc + L.rc;
-		for (uint32_t i = 0; i < total; ++i) {
-			const bool rev = i >= L.fc;
-			const uint32_t loc = __ldg(P.table + (rev ? L.rs + (i - L.fc) : L.fs + i));
-			const uint32_t corr = rev ? corr_r : (uint32_t) o;
-			if (loc < corr) {                              // the reference's 64-bit wrap-around: exact kernel
-				s_slow = 1;
-				continue;
-			}
-			const uint32_t bin = (loc - corr) >> P.bin_shift;
-			uint32_t slot = (bin * 2654435761u) >> (32 - TS_LOG);
-			for (int probe = 0; probe < TS; ++probe) {
-				const uint32_t old = atomicCAS(&keys[slot], kCsEmpty, bin);
-				if (old == kCsEmpty || old == bin) {
-					if (old == kCsEmpty) atomicAdd(&s_distinct, 1u);
-					const uint32_t before = atomicAdd(&cnts[slot], rev ? 0x10000u : 1u);
-					const uint32_t now = ((before >> (rev ? 16 : 0)) & 0x7FFFu) + 1u;
-					if (now > 1u) atomicMax(&s_max, now);
-					break;
+	// ---- A: list descriptors + sequence numbers -----------------------------------------------------------
+	uint32_t mine[IPT];
+#pragma unroll
+	for (int q = 0; q < IPT; ++q) {
+		const int o = tid * IPT + q;                           // blocked layout so that the scan below is a plain prefix sum
+		uint32_t fc = 0, rc = 0, fs = 0, rs = 0;
+		if (o < n_kmers) {
+			uint32_t prefix;
+			if (cs_read_kmer(s_read, len, o, k, prefix)) {
+				CsLists L;
+				if (cs_lookup(P, prefix, L)) {
+					fc = L.fc;
+					rc = L.rc;
+					fs = L.fs;
+					rs = L.rs;
 				}
-				slot = (slot + 1) & MASK;
-				if (probe == TS - 1) s_slow = 1;
-			}
-			if (s_distinct > (uint32_t) (TS - TS / 8)) {       // table (nearly) full: give up on the fast path
-				s_slow = 1;
-				break;
 			}
 		}
-		s_any = 1;
+		kfs[o] = fs;
+		krs[o] = rs;
+		kfc[o] = (uint16_t) fc;
+		krc[o] = (uint16_t) rc;
+		mine[q] = fc + rc;
 	}
+	uint32_t tsum = 0;
+#pragma unroll
+	for (int q = 0; q < IPT; ++q) tsum += mine[q];
+	uint32_t incl = tsum;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+		if (lane >= d) incl += v;
+	}
+	if (lane == 31) s_warp[warp] = incl;
 	__syncthreads();
+	uint32_t wbase = 0;
+#pragma unroll
+	for (int w = 0; w < NT / 32; ++w) wbase += (w < warp) ? s_warp[w] : 0u;
+	uint32_t run = wbase + incl - tsum;
+#pragma unroll
+	for (int q = 0; q < IPT; ++q) {
+		kbase[tid * IPT + q] = run;
+		run += mine[q];
+	}
+	if (tid == NT - 1) kbase[MAXK] = run;
+	__syncthreads();
+	const uint32_t n_hits = kbase[MAXK];
 	auto to_exact = [&]() {
 		if (tid == 0) {
 			meta[r].off = 0;
@@ -347,24 +394,151 @@ __global__ void __launch_bounds__(128) cs_search_kernel(const CsDev P, const uin
 			slow_list[atomicAdd(slow_count, 1u)] = (uint32_t) r;
 		}
 	};
+	if (n_hits > (uint32_t) MAXH) {
+		to_exact();
+		return;
+	}
+	if (n_hits == 0) {
+		if (tid == 0) {
+			meta[r].off = 0;
+			meta[r].count = 0;
+			if (max_hit != nullptr) max_hit[r] = 0.0f;
+		}
+		return;
+	}
+
+	// double hashing in the small table
+	auto slot0 = [&](uint32_t bin) { return (bin * 2654435761u) >> (32 - T2_LOG); };
+	auto step_of = [&](uint32_t bin) { return ((bin * 0x9E3779B1u) >> (32 - T2_LOG)) | 1u; };
+
+	// ---- B: bitmap sweep; hits that find their bit set are queued for the table --------------------------------
+	auto hash_bit = [&](uint32_t bin, uint32_t &word, uint32_t &bit) {
+		const uint32_t hb = (bin * 0x85EBCA6Bu) >> 17;         // 15 bits -> one of 32768 bits
+		word = hb >> 5;
+		bit = 1u << (hb & 31);
+	};
+	auto first_sweep = [&](bool valid, uint32_t loc, bool rev, uint32_t corr, uint32_t h) {
+		if (!valid) return;
+		if (loc < corr) {                                      // the reference's 64-bit wrap-around: exact kernel
+			s_slow = 1;
+			loc = corr;
+		}
+		const uint32_t bin = (loc - corr) >> P.bin_shift;
+		uint32_t word, bit;
+		hash_bit(bin, word, bit);
+		const uint32_t old = atomicOr(&seen[word], bit);
+		uint32_t tag = bin | (rev ? kHitRev : 0u);
+		if (old & bit) {                                       // seen before (or a colliding bin): to be counted exactly
+			tag |= kHitInserted;
+			const uint32_t q = atomicAdd(&s_nq, 1u);
+			if (q < kCsQueue) s_queue[q] = h;
+		}
+		bins[h] = tag;
+	};
+	constexpr int U = 8;
+	for (int j0 = warp; j0 < n_kmers; j0 += (NT / 32) * U) {
+		uint32_t loc[U];
+#pragma unroll
+		for (int u = 0; u < U; ++u) {
+			const int j = j0 + u * (NT / 32);
+			loc[u] = 0;
+			if (j < n_kmers) {
+				const uint32_t fc = kfc[j], tot = fc + krc[j];
+				if ((uint32_t) lane < tot) loc[u] = __ldg(P.table + ((uint32_t) lane < fc ? kfs[j] + lane : krs[j] + (lane - fc)));
+			}
+		}
+#pragma unroll 1
+		for (int u = 0; u < U; ++u) {                              // rolled on purpose: keeps the kernel inside the instruction cache
+			const int j = j0 + u * (NT / 32);
+			if (j >= n_kmers) break;
+			const uint32_t fc = kfc[j], tot = fc + krc[j];
+			const uint32_t corr_f = (uint32_t) j, corr_r = (uint32_t) (len - (j + k));
+			uint32_t v = loc[0];
+#pragma unroll
+			for (int q = 1; q < U; ++q) v = (u == q) ? loc[q] : v;
+			first_sweep((uint32_t) lane < tot, v, (uint32_t) lane >= fc, (uint32_t) lane >= fc ? corr_r : corr_f, kbase[j] + lane);
+			for (uint32_t l = 32 + lane; l < tot; l += 32) {       // lists longer than a warp
+				const uint32_t w = __ldg(P.table + (l < fc ? kfs[j] + l : krs[j] + (l - fc)));
+				first_sweep(true, w, l >= fc, l >= fc ? corr_r : corr_f, kbase[j] + l);
+			}
+		}
+	}
+	__syncthreads();
+	if (s_slow || s_nq > (uint32_t) kCsQueue || s_nq > (uint32_t) (T2 / 2)) {
+		to_exact();
+		return;
+	}
+	// ---- B2: the queued hits enter the exact table (dense: one hit per thread) -----------------------------------
+	for (uint32_t q = tid; q < s_nq; q += NT) {
+		const uint32_t t = bins[s_queue[q]];
+		const uint32_t bin = t & kHitBin;
+		uint32_t slot = slot0(bin);
+		const uint32_t st = step_of(bin);
+		bool done = false;
+		for (int probe = 0; probe < 64; ++probe) {
+			const uint32_t was = atomicCAS(&keys[slot], kCsEmpty, bin);
+			if (was == kCsEmpty || was == bin) {
+				atomicAdd(&cnts[slot], (t & kHitRev) ? 0x10000u : 1u);
+				done = true;
+				break;
+			}
+			slot = (slot + st) & MASK;
+		}
+		if (!done) s_slow = 1;
+		uint32_t word, bit;
+		hash_bit(bin, word, bit);
+		atomicOr(&rep[word], bit);
+	}
+	__syncthreads();
 	if (s_slow) {
 		to_exact();
 		return;
 	}
-	// hits of k-mers whose lists were empty still leave s_any == 1 with no entry; the maximum then stays 0
-	const uint32_t M = s_max > 0 ? s_max : (s_distinct > 0 ? 1u : 0u);
-	if (max_hit != nullptr && tid == 0) max_hit[r] = (float) M;
-	if (M == 0) {
-		if (tid == 0) {
-			meta[r].off = 0;
-			meta[r].count = 0;
+	// read-only lookup (the table is complete as far as keys go)
+	auto find = [&](uint32_t bin) -> int {
+		uint32_t slot = slot0(bin);
+		const uint32_t st = step_of(bin);
+		for (int probe = 0; probe < 64; ++probe) {
+			const uint32_t kk = keys[slot];
+			if (kk == bin) return (int) slot;
+			if (kk == kCsEmpty) return -1;
+			slot = (slot + st) & MASK;
 		}
+		return -1;
+	};
+	// ---- C: the hit that set the bit of a repeated bin (the "repeated" bitmap spares the lookup for ~97 % of the hits)
+	for (uint32_t h = tid; h < n_hits; h += NT) {
+		const uint32_t t = bins[h];
+		if (t & kHitInserted) continue;
+		uint32_t word, bit;
+		hash_bit(t & kHitBin, word, bit);
+		if (!(rep[word] & bit)) continue;
+		const int slot = find(t & kHitBin);
+		if (slot >= 0) {
+			atomicAdd(&cnts[slot], (t & kHitRev) ? 0x10000u : 1u);
+			bins[h] = t | kHitInserted;
+		}
+	}
+	__syncthreads();
+	// ---- D: maximum, threshold, accepted entries -----------------------------------------------------------------
+	{
+		uint32_t m = 1;                                        // n_hits > 0: some bin has one vote
+		for (int s = tid; s < T2; s += NT) {
+			const uint32_t c = cnts[s];
+			m = max(m, max(c & 0x7FFFu, (c >> 16) & 0x7FFFu));
+		}
+		for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+		if (lane == 0) atomicMax(&s_max, m);
+	}
+	__syncthreads();
+	const uint32_t M = s_max;
+	if (max_hit != nullptr && tid == 0) max_hit[r] = (float) M;
+	const float thr = fmaxf(P.kmer_min, __fmul_rn((float) M, P.sensitivity));      // CS.cpp:193-196,271
+	if (!(thr > 1.0f)) {                                       // single-vote bins pass: not a case for the bitmap filter
+		to_exact();
 		return;
 	}
-	const float thr = fmaxf(P.kmer_min, __fmul_rn((float) M, P.sensitivity));      // CS.cpp:193-196,271
-
-	// ---- accepted entries -------------------------------------------------------------------------------
-	for (int s = tid; s < TS; s += 128) {
+	for (int s = tid; s < T2; s += NT) {
 		if (keys[s] == kCsEmpty) continue;
 		const uint32_t c = cnts[s];
 		const uint32_t a = ((float) (c & 0x7FFFu) >= thr ? 1u : 0u) + ((float) ((c >> 16) & 0x7FFFu) >= thr ? 1u : 0u);
@@ -372,7 +546,7 @@ __global__ void __launch_bounds__(128) cs_search_kernel(const CsDev P, const uin
 			const uint32_t at = atomicAdd(&s_nacc, 1u);
 			if (at < kCsMaxAccepted) s_acc[at] = (uint32_t) s;
 			atomicAdd(&s_ncand, a);
-			cnts[s] = c | 0x8000u;                         // accepted flag
+			cnts[s] = c | 0x8000u;                             // bit 15: accepted
 		}
 	}
 	__syncthreads();
@@ -389,28 +563,17 @@ __global__ void __launch_bounds__(128) cs_search_kernel(const CsDev P, const uin
 		return;
 	}
 	if (nacc > 1) {
-		// ---- order of the list: replay the relevant hits in sequence ---------------------------------------
-		for (int o = tid; o < n_kmers; o += 128) {
-			uint32_t prefix;
-			if (!cs_read_kmer(s_read, len, o, k, prefix)) continue;
-			CsLists L;
-			if (!cs_lookup(P, prefix, L)) continue;
-			const uint32_t corr_r = (uint32_t) (len - (o + k));
-			const uint32_t total = L.fc + L.rc;
-			for (uint32_t i = 0; i < total; ++i) {
-				const bool rev = i >= L.fc;
-				const uint32_t idx = rev ? i - L.fc : i;
-				const uint32_t loc = __ldg(P.table + (rev ? L.rs + idx : L.fs + idx));
-				const uint32_t bin = (loc - (rev ? corr_r : (uint32_t) o)) >> P.bin_shift;
-				uint32_t slot = (bin * 2654435761u) >> (32 - TS_LOG);
-				while (keys[slot] != bin) slot = (slot + 1) & MASK;
-				const uint32_t c = cnts[slot];
-				if ((c & 0x8000u) || (c & 0x7FFFu) >= 2u || ((c >> 16) & 0x7FFFu) >= 2u) {
-					const uint32_t at = atomicAdd(&s_nitems, 1u);
-					if (at < kCsMaxItems) {
-						s_items_t[at] = ((uint32_t) o << 17) | (rev ? 0x10000u : 0u) | idx;      // sequence number of the hit
-						s_items_s[at] = (uint32_t) slot | (rev ? 0x80000000u : 0u);
-					}
+		// ---- E: order of the list: replay the relevant hits in sequence ---------------------------------------
+		for (uint32_t h = tid; h < n_hits; h += NT) {
+			const uint32_t t = bins[h];
+			if (!(t & kHitInserted)) continue;                 // not in the table: a single-vote bin
+			const int slot = find(t & kHitBin);
+			const uint32_t c = cnts[slot];
+			if ((c & 0x8000u) || (c & 0x7FFFu) >= 2u || ((c >> 16) & 0x7FFFu) >= 2u) {
+				const uint32_t at = atomicAdd(&s_nitems, 1u);
+				if (at < kCsMaxItems) {
+					s_items_t[at] = h;                             // sequence number of the hit
+					s_items_s[at] = (uint32_t) slot | ((t & kHitRev) ? 0x80000000u : 0u);
 				}
 			}
 		}
@@ -422,14 +585,14 @@ __global__ void __launch_bounds__(128) cs_search_kernel(const CsDev P, const uin
 		}
 		int n2 = 1;
 		while (n2 < n_items) n2 <<= 1;
-		for (int i = n_items + tid; i < n2; i += 128) {
+		for (int i = n_items + tid; i < n2; i += NT) {
 			s_items_t[i] = 0xFFFFFFFFu;
 			s_items_s[i] = 0;
 		}
 		__syncthreads();
 		for (int size = 2; size <= n2; size <<= 1) {           // bitonic sort by sequence number
 			for (int st = size >> 1; st > 0; st >>= 1) {
-				for (int i = tid; i < n2; i += 128) {
+				for (int i = tid; i < n2; i += NT) {
 					const int j = i ^ st;
 					if (j > i) {
 						const bool up = (i & size) == 0;
@@ -447,7 +610,7 @@ __global__ void __launch_bounds__(128) cs_search_kernel(const CsDev P, const uin
 			}
 		}
 		// votes of the hit's (entry, strand) right after this hit
-		for (int i = tid; i < n_items; i += 128) {
+		for (int i = tid; i < n_items; i += NT) {
 			const uint32_t me = s_items_s[i];
 			uint32_t c = 1;
 			for (int j = 0; j < i; ++j) c += (s_items_s[j] == me);
