@@ -529,6 +529,7 @@ def main():
                        "pipeline_step": "set_reads -> cs_search (k-mer vote) -> score all candidates -> top1+MAPQ -> gather -> align+backtrace+CIGAR/MD",
                        "pipeline_ms": ms_pipe, "pipeline_reads_per_s": world * n / (ms_pipe * 1e-3),
                        "winner_at_true_locus": float(ok_pos.float().mean().item()), "mapped": int(np.count_nonzero(recs_cs["score"] >= 0)),
+                       "reads_on_sequential_exact_kernel": sw.cs_exact_reads(), "exact_kernel_reasons": sw.cs_exact_reasons(),
                        "roofline": {"kernel": "cs_search_kernel", "bound": "hbm", "algorithmic_bytes_per_read": alg_bytes_read,
                                     "achieved": alg_bytes_read * n / (ms_cs * 1e-3) / 1e9, "unit": "GB/s",
                                     "note": "2 index lookups of 8 B and 2 position lists of ~%.1f x 4 B per k-mer, %d k-mers per read" % (mean_list, n_kmers)}}

@@ -217,6 +217,10 @@ int ngm_b200_cs_search(ngm_b200_ctx *ctx, const char *reads, int n_reads, int st
 		ngm_b200_pair *pairs, float *votes, size_t capacity, size_t *total, float *max_hit);
 /* Reads the last ngm_b200_cs_search call routed to the exact kernel. */
 uint64_t ngm_b200_cs_exact_reads(const ngm_b200_ctx *ctx);
+/* Why they left the block-per-read kernel (diagnostics): out[0..n) = counts per reason -- 0 more hits than the kernel's
+ * hit buffer, 1 64-bit bin wrap-around, 2 repeat queue full, 3 table crowded, 4 too many two-vote entries, 5 zero threshold,
+ * 6 more than 192 accepted entries, 7 too many hits to replay for the order, 8 order check failed.  Returns the number of reasons. */
+int ngm_b200_cs_exact_reasons(const ngm_b200_ctx *ctx, uint32_t *out, int n);
 
 /* -- device-pointer entry points (resident pipelines, bench.py `value`) --- */
 /* All pointers are device pointers on ctx's device; work is enqueued on `stream`

@@ -339,11 +339,11 @@ int ngm_b200_dev_cs_search(ngm_b200_ctx *c, const void *d_ascii_reads, int n_rea
 	CU(cs->d_meta.ensure((size_t) n_reads * sizeof(CsMeta)));
 	CU(cs->d_heap.ensure((size_t) capacity * sizeof(CsCand) + 8));
 	CU(cs->d_cursor.ensure(4));
-	CU(cs->d_slow_count.ensure(4));
+	CU(cs->d_slow_count.ensure(64));
 	CU(cs->d_slow_list.ensure((size_t) n_reads * 4));
 	CU(cs->d_counts.ensure(((size_t) n_reads + 1) * 4));
 	CU(cudaMemsetAsync(cs->d_cursor.p, 0, 4, st));
-	CU(cudaMemsetAsync(cs->d_slow_count.p, 0, 4, st));
+	CU(cudaMemsetAsync(cs->d_slow_count.p, 0, 64, st));
 	if (cs->ex_blocks == 0) {
 		int sms = 0;
 		CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
@@ -452,6 +452,16 @@ uint64_t ngm_b200_cs_exact_reads(const ngm_b200_ctx *c) {
 			cudaMemcpy(&slow, c->cs->d_slow_count.p, 4, cudaMemcpyDeviceToHost) != cudaSuccess)
 		return 0;
 	return slow;
+}
+
+int ngm_b200_cs_exact_reasons(const ngm_b200_ctx *c, uint32_t *out, int n) {
+	if (c == nullptr || c->cs == nullptr || out == nullptr || c->cs->d_slow_count.p == nullptr) return fail(NGM_B200_ESTATE, "no candidate search yet");
+	uint32_t tmp[16] = {0};
+	if (cudaSetDevice(c->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+			cudaMemcpy(tmp, c->cs->d_slow_count.p, 64, cudaMemcpyDeviceToHost) != cudaSuccess)
+		return fail(NGM_B200_ECUDA, "cannot read the counters");
+	for (int i = 0; i < n && i < (int) kCsWhyCount; ++i) out[i] = tmp[1 + i];
+	return (int) kCsWhyCount;
 }
 
 }  // extern "C"

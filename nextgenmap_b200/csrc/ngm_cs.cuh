@@ -55,7 +55,7 @@ struct CsCand {               // 8 bytes
 constexpr uint32_t kCsPending = 0xFFFFFFFFu;
 constexpr uint32_t kCsEmpty = 0xFFFFFFFFu;
 constexpr int kCsMaxItems = 512;           // relevant hits replayed for the order
-constexpr int kCsMaxAccepted = 64;
+constexpr int kCsMaxAccepted = 192;        // noise bins collect two votes at a rate of ~1.5 % of the hits (a random 13-mer hit extends to the next indexed position with p = 1/64): ~100 per 250 bp read, all accepted when the best bin has <= 4 votes
 constexpr int kCsMaxStride = 1024;         // NGM's maximum read length (ReadProvider.cpp:42)
 constexpr int kCsExactBits = 17;           // slots of the exact kernel's table (reads <= 1000 bp x max_kfreq hits)
 
@@ -278,14 +278,17 @@ __device__ __forceinline__ bool cs_lookup(const CsDev &P, uint32_t prefix, CsLis
 // Reads whose single-vote bins can pass (threshold <= 1: nothing aligns well), with more hits than MAXH or a crowded
 // table go to the exact kernel.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kCsBitmapWords = 1024;                           // 32768 bits each: "seen" and "repeated"
-constexpr int kCsQueue = 768;                                  // hits per read that find their bit set (repeats + false positives)
+enum CsExactReason { kCsWhyHits = 0, kCsWhyWrap, kCsWhyQueue, kCsWhyTable, kCsWhyMulti, kCsWhyZeroThr, kCsWhyAccepted, kCsWhyItems, kCsWhyOrder, kCsWhyCount };
+constexpr int kCsRepWords = 512;                               // 16384 "repeated" bits; the "seen" bitmap has max(65536, 32 x T2) bits
+constexpr int kCsMaxMulti = 256;                               // (entry, strand) pairs with two or more votes
+constexpr int kCsQueue = 512;                                  // hits per read that find their bit set (repeats + false positives)
 constexpr uint32_t kHitInserted = 0x80000000u, kHitRev = 0x40000000u, kHitBin = 0x3FFFFFFFu;
 
 template <int T2_LOG, int MAXK, int MAXH>
 struct CsSmem {
 	static constexpr int T2 = 1 << T2_LOG;
-	static constexpr size_t bytes = (size_t) kCsBitmapWords * 8 + (size_t) T2 * 8 + (size_t) MAXH * 4 + (size_t) MAXK * 8 + ((size_t) MAXK + 4) * 4 +
+	static constexpr int SEENW = T2 > 2048 ? T2 : 2048;        // words of the "seen" bitmap (reused as per-slot first-hit array)
+	static constexpr size_t bytes = (size_t) (SEENW + kCsRepWords) * 4 + (size_t) T2 * 8 + (size_t) MAXH * 4 + (size_t) MAXK * 8 + ((size_t) MAXK + 4) * 4 +
 			(size_t) MAXK * 4 + (size_t) MAXK + 32;
 };
 
@@ -293,13 +296,17 @@ template <int T2_LOG, int MAXK, int MAXH>
 __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uint8_t *__restrict__ reads, int n_reads, int stride,
 		CsMeta *__restrict__ meta, CsCand *__restrict__ heap, uint32_t heap_cap, uint32_t *__restrict__ cursor, uint32_t *__restrict__ slow_list,
 		uint32_t *__restrict__ slow_count, float *__restrict__ max_hit) {
+	// slow_count[1 + reason]: why reads left the fast path (diagnostics, see CsExactReason)
 	constexpr int T2 = 1 << T2_LOG;
 	constexpr uint32_t MASK = T2 - 1;
 	constexpr int NT = 256;
 	constexpr int IPT = MAXK / NT;                             // list descriptors per thread in the scan
 	static_assert(MAXK % NT == 0, "MAXK must be a multiple of the block size");
 	extern __shared__ uint32_t s_dyn[];
-	uint32_t *seen = s_dyn, *rep = seen + kCsBitmapWords, *keys = rep + kCsBitmapWords, *cnts = keys + T2, *bins = cnts + T2;
+	constexpr int SEENW = CsSmem<T2_LOG, MAXK, MAXH>::SEENW;
+	constexpr int SEEN_SHIFT = SEENW == 2048 ? 16 : (SEENW == 4096 ? 15 : 14);      // 32 - log2(32 x SEENW)
+	static_assert(SEENW == 2048 || SEENW == 4096 || SEENW == 8192, "seen bitmap size");
+	uint32_t *seen = s_dyn, *rep = seen + SEENW, *keys = rep + kCsRepWords, *cnts = keys + T2, *bins = cnts + T2;
 	uint32_t *kfs = bins + MAXH, *krs = kfs + MAXK, *kbase = krs + MAXK;      // kbase: MAXK + 4 entries
 	uint16_t *kfc = reinterpret_cast<uint16_t *>(kbase + MAXK + 4), *krc = kfc + MAXK;
 	uint8_t *s_read = reinterpret_cast<uint8_t *>(krc + MAXK);            // MAXK + 32 bytes >= stride (stride - k + 1 <= MAXK, k <= 14)
@@ -311,17 +318,18 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 	__shared__ uint32_t s_queue[kCsQueue];
 	uint32_t *s_items_t = s_queue;                             // the queue is dead by the time the order is worked out
 	static_assert(kCsQueue >= kCsMaxItems, "items reuse the queue");
-	__shared__ uint32_t s_max, s_slow, s_nent, s_nacc, s_ncand, s_nitems, s_nord, s_nq;
+	__shared__ uint16_t s_multi[kCsMaxMulti];
+	__shared__ uint32_t s_max, s_slow, s_nmulti, s_nacc, s_ncand, s_nitems, s_nord, s_nq;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int r = blockIdx.x;
 	if (r >= n_reads) return;
 	if (tid == 0) {
 		s_len = stride;
-		s_max = s_slow = s_nent = s_nacc = s_ncand = s_nitems = s_nord = s_nq = 0;
+		s_max = s_slow = s_nmulti = s_nacc = s_ncand = s_nitems = s_nord = s_nq = 0;
 	}
 	{
 		uint4 *z4 = reinterpret_cast<uint4 *>(seen);               // both bitmaps
-		for (int i = tid; i < 2 * kCsBitmapWords / 4; i += NT) z4[i] = make_uint4(0, 0, 0, 0);
+		for (int i = tid; i < (SEENW + kCsRepWords) / 4; i += NT) z4[i] = make_uint4(0, 0, 0, 0);
 		uint4 *k4 = reinterpret_cast<uint4 *>(keys), *c4 = reinterpret_cast<uint4 *>(cnts);
 		for (int i = tid; i < T2 / 4; i += NT) {
 			k4[i] = make_uint4(kCsEmpty, kCsEmpty, kCsEmpty, kCsEmpty);
@@ -387,15 +395,16 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 	if (tid == NT - 1) kbase[MAXK] = run;
 	__syncthreads();
 	const uint32_t n_hits = kbase[MAXK];
-	auto to_exact = [&]() {
+	auto to_exact = [&](int reason) {
 		if (tid == 0) {
 			meta[r].off = 0;
 			meta[r].count = kCsPending;
 			slow_list[atomicAdd(slow_count, 1u)] = (uint32_t) r;
+			atomicAdd(slow_count + 1 + reason, 1u);
 		}
 	};
 	if (n_hits > (uint32_t) MAXH) {
-		to_exact();
+		to_exact(kCsWhyHits);
 		return;
 	}
 	if (n_hits == 0) {
@@ -413,7 +422,12 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 
 	// ---- B: bitmap sweep; hits that find their bit set are queued for the table --------------------------------
 	auto hash_bit = [&](uint32_t bin, uint32_t &word, uint32_t &bit) {
-		const uint32_t hb = (bin * 0x85EBCA6Bu) >> 17;         // 15 bits -> one of 32768 bits
+		const uint32_t hb = (bin * 0x85EBCA6Bu) >> SEEN_SHIFT; // one of the "seen" bits
+		word = hb >> 5;
+		bit = 1u << (hb & 31);
+	};
+	auto rep_bit = [&](uint32_t bin, uint32_t &word, uint32_t &bit) {
+		const uint32_t hb = (bin * 0xC2B2AE35u) >> 18;         // one of 16384 "repeated" bits, independent of the hash above
 		word = hb >> 5;
 		bit = 1u << (hb & 31);
 	};
@@ -435,7 +449,7 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 		}
 		bins[h] = tag;
 	};
-	constexpr int U = 8;
+	constexpr int U = 9;
 	for (int j0 = warp; j0 < n_kmers; j0 += (NT / 32) * U) {
 		uint32_t loc[U];
 #pragma unroll
@@ -447,27 +461,39 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 				if ((uint32_t) lane < tot) loc[u] = __ldg(P.table + ((uint32_t) lane < fc ? kfs[j] + lane : krs[j] + (lane - fc)));
 			}
 		}
-#pragma unroll 1
-		for (int u = 0; u < U; ++u) {                              // rolled on purpose: keeps the kernel inside the instruction cache
-			const int j = j0 + u * (NT / 32);
-			if (j >= n_kmers) break;
-			const uint32_t fc = kfc[j], tot = fc + krc[j];
-			const uint32_t corr_f = (uint32_t) j, corr_r = (uint32_t) (len - (j + k));
-			uint32_t v = loc[0];
 #pragma unroll
-			for (int q = 1; q < U; ++q) v = (u == q) ? loc[q] : v;
-			first_sweep((uint32_t) lane < tot, v, (uint32_t) lane >= fc, (uint32_t) lane >= fc ? corr_r : corr_f, kbase[j] + lane);
-			for (uint32_t l = 32 + lane; l < tot; l += 32) {       // lists longer than a warp
-				const uint32_t w = __ldg(P.table + (l < fc ? kfs[j] + l : krs[j] + (l - fc)));
-				first_sweep(true, w, l >= fc, l >= fc ? corr_r : corr_f, kbase[j] + l);
+		for (int u = 0; u < U; ++u) {
+			const int j = j0 + u * (NT / 32);
+			if (j < n_kmers) {
+				const uint32_t fc = kfc[j], tot = fc + krc[j];
+				const uint32_t corr_f = (uint32_t) j, corr_r = (uint32_t) (len - (j + k));
+				first_sweep((uint32_t) lane < tot, loc[u], (uint32_t) lane >= fc, (uint32_t) lane >= fc ? corr_r : corr_f, kbase[j] + lane);
+				if (tot > 32u) {                                   // warp-uniform: the part of the two lists beyond 32 hits
+					for (uint32_t l = 32 + lane; l < tot; l += 32) {
+						const uint32_t w = __ldg(P.table + (l < fc ? kfs[j] + l : krs[j] + (l - fc)));
+						first_sweep(true, w, l >= fc, l >= fc ? corr_r : corr_f, kbase[j] + l);
+					}
+				}
 			}
 		}
 	}
 	__syncthreads();
 	if (s_slow || s_nq > (uint32_t) kCsQueue || s_nq > (uint32_t) (T2 / 2)) {
-		to_exact();
+		to_exact(s_slow ? kCsWhyWrap : kCsWhyQueue);
 		return;
 	}
+	// one more vote for (slot, strand); remembers the running maximum and every (entry, strand) that reaches two votes
+	auto bump = [&](uint32_t slot, bool rev) {
+		const uint32_t before = atomicAdd(&cnts[slot], rev ? 0x10000u : 1u);
+		const uint32_t now = ((before >> (rev ? 16 : 0)) & 0x7FFFu) + 1u;
+		if (now >= 2u) {
+			atomicMax(&s_max, now);
+			if (now == 2u) {
+				const uint32_t at = atomicAdd(&s_nmulti, 1u);
+				if (at < kCsMaxMulti) s_multi[at] = (uint16_t) slot;
+			}
+		}
+	};
 	// ---- B2: the queued hits enter the exact table (dense: one hit per thread) -----------------------------------
 	for (uint32_t q = tid; q < s_nq; q += NT) {
 		const uint32_t t = bins[s_queue[q]];
@@ -478,7 +504,7 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 		for (int probe = 0; probe < 64; ++probe) {
 			const uint32_t was = atomicCAS(&keys[slot], kCsEmpty, bin);
 			if (was == kCsEmpty || was == bin) {
-				atomicAdd(&cnts[slot], (t & kHitRev) ? 0x10000u : 1u);
+				bump(slot, (t & kHitRev) != 0);
 				done = true;
 				break;
 			}
@@ -486,12 +512,12 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 		}
 		if (!done) s_slow = 1;
 		uint32_t word, bit;
-		hash_bit(bin, word, bit);
+		rep_bit(bin, word, bit);
 		atomicOr(&rep[word], bit);
 	}
 	__syncthreads();
 	if (s_slow) {
-		to_exact();
+		to_exact(kCsWhyTable);
 		return;
 	}
 	// read-only lookup (the table is complete as far as keys go)
@@ -507,52 +533,125 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 		return -1;
 	};
 	// ---- C: the hit that set the bit of a repeated bin (the "repeated" bitmap spares the lookup for ~97 % of the hits)
-	for (uint32_t h = tid; h < n_hits; h += NT) {
-		const uint32_t t = bins[h];
-		if (t & kHitInserted) continue;
-		uint32_t word, bit;
-		hash_bit(t & kHitBin, word, bit);
-		if (!(rep[word] & bit)) continue;
-		const int slot = find(t & kHitBin);
-		if (slot >= 0) {
-			atomicAdd(&cnts[slot], (t & kHitRev) ? 0x10000u : 1u);
-			bins[h] = t | kHitInserted;
+	for (uint32_t h4 = 4 * tid; h4 < n_hits; h4 += 4 * NT) {       // four hits per thread and step (bins[] is 16-byte aligned)
+		const uint4 q4 = *reinterpret_cast<const uint4 *>(bins + h4);
+		const uint32_t tt[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+		for (int e = 0; e < 4; ++e) {
+			const uint32_t t = tt[e];
+			if (h4 + e >= n_hits || (t & kHitInserted)) continue;
+			uint32_t word, bit;
+			rep_bit(t & kHitBin, word, bit);
+			if (!(rep[word] & bit)) continue;
+			const int slot = find(t & kHitBin);
+			if (slot >= 0) {
+				bump((uint32_t) slot, (t & kHitRev) != 0);
+				bins[h4 + e] = t | kHitInserted;
+			}
 		}
 	}
 	__syncthreads();
 	// ---- D: maximum, threshold, accepted entries -----------------------------------------------------------------
-	{
-		uint32_t m = 1;                                        // n_hits > 0: some bin has one vote
-		for (int s = tid; s < T2; s += NT) {
-			const uint32_t c = cnts[s];
-			m = max(m, max(c & 0x7FFFu, (c >> 16) & 0x7FFFu));
-		}
-		for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
-		if (lane == 0) atomicMax(&s_max, m);
-	}
-	__syncthreads();
-	const uint32_t M = s_max;
+	const uint32_t M = max(s_max, 1u);                         // n_hits > 0: some bin has one vote
 	if (max_hit != nullptr && tid == 0) max_hit[r] = (float) M;
 	const float thr = fmaxf(P.kmer_min, __fmul_rn((float) M, P.sensitivity));      // CS.cpp:193-196,271
-	if (!(thr > 1.0f)) {                                       // single-vote bins pass: not a case for the bitmap filter
-		to_exact();
+	if (!(thr > 0.0f) || s_nmulti > (uint32_t) kCsMaxMulti) {      // zero threshold (strands without a vote pass): exact kernel
+		to_exact(thr > 0.0f ? kCsWhyMulti : kCsWhyZeroThr);
 		return;
 	}
-	for (int s = tid; s < T2; s += NT) {
-		if (keys[s] == kCsEmpty) continue;
-		const uint32_t c = cnts[s];
+	if (!(thr > 1.0f)) {
+		// ---- J: nothing stands out (threshold <= 1): EVERY bin with a vote is a candidate (CS.cpp:286-305), and as the
+		// running threshold never exceeded one vote, every entry entered rList at its first hit (CS.cpp:199-202): the
+		// list is the bins in the order of their first hit, forward strand before reverse strand.
+		uint32_t *firsth = seen;                               // the bitmap is no longer needed: first hit per table slot
+		for (int sl = tid; sl < T2; sl += NT) firsth[sl] = 0xFFFFFFFFu;
+		__syncthreads();
+		for (uint32_t h = tid; h < n_hits; h += NT) {
+			const uint32_t t = bins[h];
+			if (t & kHitInserted) atomicMin(&firsth[find(t & kHitBin)], h);
+		}
+		__syncthreads();
+		const uint32_t chunk = (n_hits + NT - 1) / NT;
+		const uint32_t h0 = min(n_hits, tid * chunk), h1 = min(n_hits, h0 + chunk);
+		auto emits = [&](uint32_t h, uint32_t &f, uint32_t &rv, uint32_t &bin) -> uint32_t {
+			const uint32_t t = bins[h];
+			bin = t & kHitBin;
+			if (!(t & kHitInserted)) {                             // a bin with exactly one vote
+				f = (t & kHitRev) ? 0u : 1u;
+				rv = 1u - f;
+				return 1u;
+			}
+			const int sl = find(bin);
+			if (firsth[sl] != h) return 0u;
+			const uint32_t c = cnts[sl];
+			f = c & 0x7FFFu;
+			rv = (c >> 16) & 0x7FFFu;
+			return (f ? 1u : 0u) + (rv ? 1u : 0u);
+		};
+		uint32_t mine_n = 0;
+		for (uint32_t h = h0; h < h1; ++h) {
+			uint32_t f, rv, bin;
+			mine_n += emits(h, f, rv, bin);
+		}
+		uint32_t inc2 = mine_n;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t v = __shfl_up_sync(0xffffffffu, inc2, d);
+			if (lane >= d) inc2 += v;
+		}
+		if (lane == 31) s_warp[warp] = inc2;
+		__syncthreads();
+		uint32_t before = inc2 - mine_n, total_c = 0;
+#pragma unroll
+		for (int w = 0; w < NT / 32; ++w) {
+			before += (w < warp) ? s_warp[w] : 0u;
+			total_c += s_warp[w];
+		}
+		if (!((long long) total_c < (long long) P.max_cmrs)) total_c = 0;      // CS.cpp:308-310
+		if (tid == 0) {
+			s_nord = total_c ? atomicAdd(cursor, total_c) : 0u;
+			meta[r].off = s_nord;
+			meta[r].count = total_c;
+		}
+		__syncthreads();
+		const uint32_t off = s_nord;
+		if (total_c && (unsigned long long) off + total_c <= heap_cap) {
+			uint32_t w = off + before;
+			for (uint32_t h = h0; h < h1; ++h) {
+				uint32_t f = 0, rv = 0, bin = 0;
+				if (emits(h, f, rv, bin) == 0) continue;
+				if (f) {
+					CsCand cd;
+					cd.bin = bin;
+					cd.votes = (uint16_t) f;
+					cd.rev = 0;
+					heap[w++] = cd;
+				}
+				if (rv) {
+					CsCand cd;
+					cd.bin = bin;
+					cd.votes = (uint16_t) rv;
+					cd.rev = 1;
+					heap[w++] = cd;
+				}
+			}
+		}
+		return;
+	}
+	for (uint32_t i = tid; i < s_nmulti; i += NT) {            // only entries with two votes on a strand can pass thr > 1
+		const uint32_t sl = s_multi[i];
+		const uint32_t c = cnts[sl];
 		const uint32_t a = ((float) (c & 0x7FFFu) >= thr ? 1u : 0u) + ((float) ((c >> 16) & 0x7FFFu) >= thr ? 1u : 0u);
-		if (a) {
+		if (a && !(atomicOr(&cnts[sl], 0x8000u) & 0x8000u)) {      // bit 15: accepted (an entry can be listed once per strand)
 			const uint32_t at = atomicAdd(&s_nacc, 1u);
-			if (at < kCsMaxAccepted) s_acc[at] = (uint32_t) s;
+			if (at < kCsMaxAccepted) s_acc[at] = sl;
 			atomicAdd(&s_ncand, a);
-			cnts[s] = c | 0x8000u;                             // bit 15: accepted
 		}
 	}
 	__syncthreads();
 	const uint32_t nacc = s_nacc, ncand = s_ncand;
 	if (nacc > kCsMaxAccepted) {
-		to_exact();
+		to_exact(kCsWhyAccepted);
 		return;
 	}
 	if (!((long long) ncand < (long long) P.max_cmrs)) {      // CS.cpp:308-310
@@ -580,7 +679,7 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 		__syncthreads();
 		const int n_items = (int) s_nitems;
 		if (n_items > kCsMaxItems) {
-			to_exact();
+			to_exact(kCsWhyItems);
 			return;
 		}
 		int n2 = 1;
@@ -634,7 +733,7 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 		}
 		__syncthreads();
 		if (s_nord != nacc) {                                  // cannot happen; be loud rather than wrong
-			to_exact();
+			to_exact(kCsWhyOrder);
 			return;
 		}
 	}

@@ -324,6 +324,13 @@ class CudaSW:
     def cs_exact_reads(self) -> int:
         return int(self.lib.ngm_b200_cs_exact_reads(self.ctx))
 
+    def cs_exact_reasons(self) -> dict:
+        names = ["hits", "wrap", "queue", "table", "multi", "zero_threshold", "accepted", "items", "order"]
+        out = (C.c_uint32 * len(names))()
+        self.lib.ngm_b200_cs_exact_reasons.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        self._check(self.lib.ngm_b200_cs_exact_reasons(self.ctx, out, len(names)))
+        return {k: int(v) for k, v in zip(names, out)}
+
     @staticmethod
     def strings_of(recs: np.ndarray, heap: np.ndarray, i: int):
         r = recs[i]

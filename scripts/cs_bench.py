@@ -75,7 +75,7 @@ def main():
     has = d_cb[1:] > d_cb[:-1]
     near = ((first_loc - batch.true_pos).abs() <= corridor + 8) & has
     print(json.dumps({"reads": n, "read_len": L, "index_build_s": build_s, "index_positions": info["table_len"], "max_kfreq": info["max_kfreq"],
-                      "cs_ms": ms, "cs_reads_per_s": n / (ms * 1e-3), "candidates_per_read": total / n, "exact_reads": sw.cs_exact_reads(),
+                      "cs_ms": ms, "cs_reads_per_s": n / (ms * 1e-3), "candidates_per_read": total / n, "exact_reads": sw.cs_exact_reads(), "exact_reasons": sw.cs_exact_reasons(),
                       "first_candidate_at_truth": float(near.float().mean().item())}))
 
 
