@@ -183,8 +183,25 @@ def run_cpu_reference(refs, qrys, n_align, n_reads, qml, corridor, threads, warm
 
 
 # ---------------------------------------------------------------------------
+_JSON_FD = None
+
+
+def emit_json(line: dict) -> None:
+    """The ONE line of stdout.  Everything else this process (or a library in it: NCCL's version banner) prints goes to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
     args = parse_args()
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)            # keep the real stdout for the JSON line ...
+    os.dup2(2, 1)                   # ... and send every other write to fd 1 (C libraries included) to stderr
     import torch
     import torch.distributed as dist
 
@@ -259,7 +276,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 (integer-valued)", "data": "synthetic", "config": cfg,
                 "cpu_baseline": {"value": res["value"], "unit": "reads/s", "cores": res["cores"], "kind": res["kind"], "sample": sample},
                 "e2e": {"value": res["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        emit_json(line)
         return 0
 
     # ---- B200 arm ---------------------------------------------------------
@@ -533,6 +550,29 @@ def main():
                        "roofline": {"kernel": "cs_search_kernel", "bound": "hbm", "algorithmic_bytes_per_read": alg_bytes_read,
                                     "achieved": alg_bytes_read * n / (ms_cs * 1e-3) / 1e9, "unit": "GB/s",
                                     "note": "2 index lookups of 8 B and 2 position lists of ~%.1f x 4 B per k-mer, %d k-mers per read" % (mean_list, n_kmers)}}
+            # parity at full scale + CPU beside it (rank 0): the oracle restatement of CS.cpp searches a sample of the reads in
+            # the SAME 3 Gbp prefix table (exported from the device); lists must agree entry by entry, order included
+            if rank == 0 and not args.no_cpu_baseline:
+                try:
+                    from oracle import cs_port
+                    n_cs = min(n, 20_000)
+                    tab_h, weight_h, table_h = sw.cs_export_index()
+                    oix = cs_port.Index.from_arrays(tab_h, weight_h, table_h, K_MER, K_SKIP, BIN, info["max_kfreq"])
+                    reads_cs = batch.reads[:n_cs].cpu().numpy()
+                    t0 = time.perf_counter()
+                    wb, wc, wm = oix.search(reads_cs, args.sensitivity)
+                    cpu_s = time.perf_counter() - t0
+                    gb = d_cb[: n_cs + 1].cpu().numpy()
+                    gp = d_cpairs[: int(gb[-1])].cpu().numpy().view(np.dtype([("window_start", "<u8"), ("read_index", "<u4"), ("flags", "<u4")])).reshape(-1)
+                    gv = d_cvotes[: int(gb[-1])].cpu().numpy()
+                    same = (np.array_equal(gb, wb) and np.array_equal((gp["window_start"] + np.uint64(corridor >> 1)).astype(np.uint64), wc["location"])
+                            and np.array_equal(gp["flags"] & 1, wc["reverse"].astype(np.uint32)) and np.array_equal(gv, wc["score"]))
+                    cs_info["parity_sample"] = {"reads_checked": n_cs, "candidates_checked": int(wb[-1]), "identical_to_oracle": bool(same)}
+                    cs_info["cpu_baseline"] = {"value": n_cs / cpu_s, "unit": "reads/s", "cores": 1, "kind": "port",
+                                               "sample": f"{n_cs} reads of the same workload searched by oracle/cs_oracle.c (restatement of CS.cpp) in the same prefix table"}
+                    del tab_h, weight_h, table_h, oix
+                except Exception as e:  # noqa: BLE001
+                    cs_info["parity_sample"] = {"error": str(e)}
             del d_cpairs, d_cvotes, d_cscores, d_cb
         except Exception as e:  # noqa: BLE001
             cs_info = {"error": str(e)}
@@ -665,7 +705,7 @@ def main():
         "counters": {"reads": total_reads, "mapped": ctr["mapped"], "pairs_scored": ctr["pairs_scored"], "string_bytes": used_strings},
         "setup_seconds": setup_s, "host_threads": host_threads,
     }
-    print(json.dumps(line))
+    emit_json(line)
     if distributed:
         dist.destroy_process_group()
     return 0

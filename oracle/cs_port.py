@@ -59,6 +59,21 @@ class Index:
         self.weight = np.ctypeslib.as_array(self.c.weight, shape=(self.index_len,)).copy()
         self.table = np.ctypeslib.as_array(self.c.table, shape=(max(self.table_len, 1),)).copy()[: self.table_len]
 
+    @classmethod
+    def from_arrays(cls, tab: np.ndarray, weight: np.ndarray, table: np.ndarray, k: int, ref_skip: int = 2, bin_shift: int = 2, max_kfreq: int = 100):
+        """Wrap an existing prefix table (e.g. read from an ht file or exported from the device) for `search`."""
+        self = cls.__new__(cls)
+        self.lib = _lib()
+        self.tab = np.ascontiguousarray(tab, dtype=np.uint32)
+        self.weight = np.ascontiguousarray(weight, dtype=np.int8)
+        self.table = np.ascontiguousarray(table, dtype=np.uint32)
+        self.k, self.ref_skip, self.bin_shift = k, ref_skip, bin_shift
+        self.index_len, self.table_len, self.max_kfreq = len(self.tab), len(self.table), max_kfreq
+        self.c = _Index(k, ref_skip, bin_shift, self.index_len, self.table_len, self.tab.ctypes.data_as(C.POINTER(C.c_uint32)),
+                        self.weight.ctypes.data_as(C.POINTER(C.c_int8)), self.table.ctypes.data_as(C.POINTER(C.c_uint32)), max_kfreq)
+        self._borrowed = True
+        return self
+
     def search(self, reads: np.ndarray, sensitivity: float, kmer_min: float = 0.0, max_kfreq: int = 0, max_cmrs: int = 2 ** 31 - 1):
         """reads uint8 [n, stride] NUL padded -> (cand_begin int32 [n+1], candidates CAND [total], max_hit float32 [n])."""
         reads = np.ascontiguousarray(reads, dtype=np.uint8)
@@ -76,6 +91,8 @@ class Index:
             cap = int(total) + 16
 
     def close(self):
+        if getattr(self, "_borrowed", False):
+            return
         if self.c.tab:
             self.lib.cs_oracle_free_index(C.byref(self.c))
 
