@@ -254,6 +254,10 @@ int ngm_b200_dev_align_pairs_scored(ngm_b200_ctx *ctx, int mode, int n, const vo
  * best_pair[r] = index of the winning pair or -1; mapq[r]. */
 int ngm_b200_dev_select_top1(ngm_b200_ctx *ctx, int n_reads, const void *d_cand_begin, const void *d_scores,
 		void *d_best_pair, void *d_mapq, void *stream);
+/* Same, and num_top[r] = number of candidates sharing the best score (top1SE's numBestScore -> MappedRead::numTopScores,
+ * ScoreBuffer.cpp:236-251; SAM tags NH / X0, SAMWriter.cpp:171,191). */
+int ngm_b200_dev_select_top1_ex(ngm_b200_ctx *ctx, int n_reads, const void *d_cand_begin, const void *d_scores,
+		void *d_best_pair, void *d_mapq, void *d_num_top, void *stream);
 /* Device-pointer form of ngm_b200_cs_search: enqueued on `stream`, not synchronised; the caller checks
  * cand_begin[n_reads] <= capacity afterwards.  d_votes / d_max_hit may be NULL. */
 int ngm_b200_dev_cs_search(ngm_b200_ctx *ctx, const void *d_ascii_reads, int n_reads, int stride, int mode_flags, void *d_cand_begin,

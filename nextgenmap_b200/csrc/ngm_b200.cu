@@ -698,17 +698,28 @@ int ngm_b200_dev_align_pairs_scored(ngm_b200_ctx *c, int mode, int n, const void
 	return dev_align_pairs(c, mode, n, d_pairs, d_pair_scores, d_recs, d_strings, str_capacity, d_str_cursor, stream);
 }
 
-int ngm_b200_dev_select_top1(ngm_b200_ctx *c, int n_reads, const void *d_cand_begin, const void *d_scores, void *d_best_pair, void *d_mapq,
-		void *stream) {
+static int select_top1(ngm_b200_ctx *c, int n_reads, const void *d_cand_begin, const void *d_scores, void *d_best_pair, void *d_mapq,
+		void *d_num_top, void *stream) {
 	if (c == nullptr || d_cand_begin == nullptr || d_scores == nullptr || d_best_pair == nullptr || d_mapq == nullptr)
 		return fail(NGM_B200_EINVAL, "NULL argument");
 	if (n_reads <= 0) return 0;
 	CU(cudaSetDevice(c->device));
 	select_top1_kernel<<<(n_reads + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(n_reads, static_cast<const int *>(d_cand_begin),
-			static_cast<const float *>(d_scores), static_cast<int *>(d_best_pair), static_cast<int *>(d_mapq));
+			static_cast<const float *>(d_scores), static_cast<int *>(d_best_pair), static_cast<int *>(d_mapq), static_cast<int *>(d_num_top));
 	c->launches += 1;
 	CU(cudaGetLastError());
 	return n_reads;
+}
+
+int ngm_b200_dev_select_top1(ngm_b200_ctx *c, int n_reads, const void *d_cand_begin, const void *d_scores, void *d_best_pair, void *d_mapq,
+		void *stream) {
+	return select_top1(c, n_reads, d_cand_begin, d_scores, d_best_pair, d_mapq, nullptr, stream);
+}
+
+int ngm_b200_dev_select_top1_ex(ngm_b200_ctx *c, int n_reads, const void *d_cand_begin, const void *d_scores, void *d_best_pair, void *d_mapq,
+		void *d_num_top, void *stream) {
+	if (d_num_top == nullptr) return fail(NGM_B200_EINVAL, "NULL argument");
+	return select_top1(c, n_reads, d_cand_begin, d_scores, d_best_pair, d_mapq, d_num_top, stream);
 }
 
 int ngm_b200_score_pairs(ngm_b200_ctx *c, int mode, int n, const ngm_b200_pair *pairs, float *scores) {

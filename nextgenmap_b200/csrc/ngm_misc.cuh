@@ -224,12 +224,12 @@ __global__ void gather_winners_kernel(int n_reads, const ngm_b200_pair *__restri
 
 // ScoreBuffer::top1SE + computeMQ (ScoreBuffer.cpp:34-40,228-277); one thread per read.
 __global__ void select_top1_kernel(int n_reads, const int *__restrict__ cand_begin, const float *__restrict__ scores,
-		int *__restrict__ best_pair, int *__restrict__ mapq) {
+		int *__restrict__ best_pair, int *__restrict__ mapq, int *__restrict__ num_top) {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= n_reads) return;
 	const int b = cand_begin[r], e = cand_begin[r + 1];
 	float best = 0.0f, second = 0.0f;
-	int besti = 0;
+	int besti = 0, nbest = 0;                                  // numBestScore -> MappedRead::numTopScores (SAM NH / X0)
 	for (int j = b; j < e; ++j) {
 		const float s = scores[j];
 		if (s > second) {
@@ -237,13 +237,18 @@ __global__ void select_top1_kernel(int n_reads, const int *__restrict__ cand_beg
 				second = best;
 				best = s;
 				besti = j - b;
+				nbest = 1;
 			} else if (s == best) {
+				++nbest;
 				second = best;
 			} else {
 				second = s;
 			}
+		} else if (s == best) {
+			++nbest;
 		}
 	}
+	if (num_top != nullptr) num_top[r] = nbest;
 	int mq = 0;
 	if (best > 0.0f && second >= 0.0f) mq = (int) ceilf(60.0f * (best - second) / best);
 	best_pair[r] = e > b ? b + besti : -1;

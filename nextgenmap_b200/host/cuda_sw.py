@@ -109,6 +109,7 @@ def load_library() -> C.CDLL:
     lib.ngm_b200_dev_align_pairs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     lib.ngm_b200_dev_gather_winners_scored.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ngm_b200_dev_align_pairs_scored.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.ngm_b200_dev_select_top1_ex.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ngm_b200_cs_build_index.argtypes = [C.c_void_p, C.POINTER(CsParams), C.c_void_p, C.c_uint32]
     lib.ngm_b200_cs_load_index.argtypes = [C.c_void_p, C.POINTER(CsParams), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
     lib.ngm_b200_cs_index_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]

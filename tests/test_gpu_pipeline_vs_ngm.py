@@ -1,0 +1,56 @@
+"""The whole single-end mapping run on the device against the UNMODIFIED NextGenMap (oracle/_ref/ngm/ngm_ref: its own CS, its own
+OpenCL kernels on the CPU, its own selection and SAM writer): BASELINE configs[0]-shaped input (100 bp reads vs a 5 Mbp contig), and a
+two-contig / indel-rich / 150 bp variant.  The device side: prefix table built on the device from the reference file NGM wrote, k-mer vote
+(cs_search), BatchScore of every candidate, top-1 + MAPQ + NH, BatchAlign, rendered by the host mirror of SAMWriter.  Sorted SAM bodies
+must be byte-identical: POS, FLAG, MAPQ, CIGAR, AS, NM, NH/X0, XI, XE (= the best k-mer vote), XR, MD -- for every read."""
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import cs_port, ngm_e2e as e2e
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not e2e.available("ref"), reason="oracle/_ref/ngm/ngm_ref not built")]
+
+
+def read_fastq(path):
+    names, seqs, quals = [], [], []
+    with open(path, "rb") as f:
+        lines = f.read().split(b"\n")
+    for i in range(0, len(lines) - 3, 4):
+        names.append(lines[i][1:].decode().split()[0])
+        seqs.append(lines[i + 1])
+        quals.append(lines[i + 3])
+    return names, seqs, quals
+
+
+@pytest.mark.parametrize("ref_len,n_reads,read_len,extra", [(5_000_000, 10_000, 100, []), (1_200_000, 4_000, 150, ["-e"]), (800_000, 3_000, 75, ["-s", "0.8"])])
+def test_sam_identical_to_ngm(ref_len, n_reads, read_len, extra):
+    from nextgenmap_b200.host import CudaSW, EncodedReference
+    from nextgenmap_b200.host import pipeline
+    sens = float(extra[extra.index("-s") + 1]) if "-s" in extra else 0.5
+    mode = 1 if "-e" in extra else 0
+    with tempfile.TemporaryDirectory(prefix="pipe_") as td:
+        d = Path(td)
+        e2e.write_inputs(d, ref_len=ref_len, n_reads=n_reads, read_len=read_len, seed=4242 + read_len, indel_reads=0.15)
+        args = [a for a in extra if a not in ("-s", str(sens))] + ["-s", str(sens)]
+        want = [ln for ln in e2e.run("ref", d, threads=4, extra=args) if not ln.startswith("@")]
+        ref = EncodedReference(str(d / "ref.fa-enc.2.ngm"))
+        names, seqs, quals = read_fastq(d / "reads.fq")
+    qml = (read_len | 1) + 1                         # ReadProvider.cpp:288
+    cor = int(5 + 0.15 * read_len)                   # ReadProvider.cpp:304
+    reads = np.zeros((len(seqs), qml), np.uint8)
+    for i, s in enumerate(seqs):
+        reads[i, : len(s)] = np.frombuffer(s, np.uint8)
+    sw = CudaSW(qml, cor)
+    sw.set_reference(ref.packed, ref.concat_len)
+    sw.cs_build_index([(c[1], c[2]) for c in ref.contigs], sw.cs_params(kmer=13, sensitivity=sens))
+    batch = pipeline.map_reads(sw, reads, mode)
+    got = sorted(pipeline.sam_lines(sw, batch, reads, names, quals, ref, cor))
+    assert len(got) == len(want)
+    bad = [(g, w) for g, w in zip(got, want) if g != w]
+    assert not bad, f"{len(bad)} of {len(want)} SAM lines differ, first:\n{bad[0][0]}\n{bad[0][1]}"
+    assert sum(1 for ln in want if ln.split("\t")[1] != "4") > 0.95 * len(want)
+    sw.close()
+    ref.close()
