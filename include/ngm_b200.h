@@ -215,6 +215,13 @@ int ngm_b200_write_ht_file(const char *path, const ngm_b200_htfile *ht);
  * exact kernel (testing). */
 int ngm_b200_cs_search(ngm_b200_ctx *ctx, const char *reads, int n_reads, int stride, int mode_flags, int32_t *cand_begin,
 		ngm_b200_pair *pairs, float *votes, size_t capacity, size_t *total, float *max_hit);
+/* The sensitivity NGM estimates when -s is not given (ReadProvider::init, ReadProvider.cpp:236-251,310-325,53-79): pass the
+ * reads number 1000, 2000, ... (1-based) of the input as `sampled_reads` (ReadProvider samples every 1000th of the first 10 M, and
+ * only estimates from inputs of >= 1000 reads); *sensitivity = clamp(mean(best vote / possible votes), 0.3, 0.9), without the
+ * --fast / --sensitive modifiers.  Returns the number of reads that contributed.  ngm_b200_cs_set_sensitivity installs a value.
+ * mode_flags bit 1 of the search calls selects the vote count used here (both strands added) for max_hit[]. */
+int ngm_b200_cs_estimate_sensitivity(ngm_b200_ctx *ctx, const char *sampled_reads, int n, int stride, float *sensitivity);
+int ngm_b200_cs_set_sensitivity(ngm_b200_ctx *ctx, float sensitivity);
 /* Reads the last ngm_b200_cs_search call routed to the exact kernel. */
 uint64_t ngm_b200_cs_exact_reads(const ngm_b200_ctx *ctx);
 /* Why they left the block-per-read kernel (diagnostics): out[0..n) = counts per reason -- 0 more hits than the kernel's

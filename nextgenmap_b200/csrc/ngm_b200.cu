@@ -6,6 +6,7 @@
 // difference is what travels and where it is processed: ASCII is packed to 4-bit codes
 // on the device, the pointer matrix never leaves the GPU, and CIGAR/MD come back as
 // compact strings.  There is no CPU implementation of the DP in this library.
+#include <cstdlib>
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>

@@ -336,6 +336,7 @@ int ngm_b200_dev_cs_search(ngm_b200_ctx *c, const void *d_ascii_reads, int n_rea
 	P.max_cmrs = cs->hp.max_cmrs > 0 ? cs->hp.max_cmrs : 0x7FFFFFFF;
 	P.sensitivity = cs->hp.sensitivity;
 	P.kmer_min = cs->hp.kmer_min;
+	P.merged = (mode_flags & 2) ? 1 : 0;
 	CU(cs->d_meta.ensure((size_t) n_reads * sizeof(CsMeta)));
 	CU(cs->d_heap.ensure((size_t) capacity * sizeof(CsCand) + 8));
 	CU(cs->d_cursor.ensure(4));
@@ -452,6 +453,44 @@ uint64_t ngm_b200_cs_exact_reads(const ngm_b200_ctx *c) {
 			cudaMemcpy(&slow, c->cs->d_slow_count.p, 4, cudaMemcpyDeviceToHost) != cudaSuccess)
 		return 0;
 	return slow;
+}
+
+int ngm_b200_cs_set_sensitivity(ngm_b200_ctx *c, float sensitivity) {
+	if (c == nullptr || c->cs == nullptr || !c->cs->ready) return fail(NGM_B200_ESTATE, "no candidate-search index");
+	if (!(sensitivity >= 0.0f && sensitivity <= 1.0f)) return fail(NGM_B200_EINVAL, "sensitivity %g not in [0, 1]", sensitivity);
+	c->cs->hp.sensitivity = sensitivity;
+	return NGM_B200_OK;
+}
+
+// ReadProvider::init (ReadProvider.cpp:236-251,310-325) with CollectResultsFallback (:53-79): every sampled read contributes
+// best-vote / possible-votes, votes counted with both strands added; the estimate is the mean clamped to [0.3, 0.9].
+int ngm_b200_cs_estimate_sensitivity(ngm_b200_ctx *c, const char *sampled_reads, int n, int stride, float *sensitivity) {
+	if (c == nullptr || sampled_reads == nullptr || sensitivity == nullptr) return fail(NGM_B200_EINVAL, "NULL argument");
+	if (c->cs == nullptr || !c->cs->ready) return fail(NGM_B200_ESTATE, "cs_build_index / cs_load_index must precede the estimate");
+	if (n <= 0) return fail(NGM_B200_EINVAL, "no sampled reads");
+	std::vector<int32_t> begin((size_t) n + 1);
+	std::vector<float> best((size_t) n);
+	ngm_b200_pair dummy;
+	size_t total = 0;
+	int rc = ngm_b200_cs_search(c, sampled_reads, n, stride, 2, begin.data(), &dummy, nullptr, 0, &total, best.data());
+	if (rc < 0 && rc != NGM_B200_ERANGE) return rc;                 // the candidates themselves are not wanted
+	const int skip = c->cs->step;
+	float sum = 0.0f;
+	int count = 0;
+	for (int r = 0; r < n; ++r) {
+		const char *row = sampled_reads + (size_t) r * stride;
+		int len = 0;
+		while (len < stride && row[len] != 0) ++len;
+		const int max = (int) std::ceil((double) ((len - c->cs->k + 1) / skip) * 1.0);
+		const float cur = best[r];
+		if ((float) max > 1.0f && cur <= (float) max) {
+			sum += cur / (float) max;
+			count += 1;
+		}
+	}
+	float avg = sum / (float) count * 1.0f;                         // NaN when nothing qualified, like the reference
+	*sensitivity = std::min(std::max(0.3f, avg), 0.9f);
+	return count;
 }
 
 int ngm_b200_cs_exact_reasons(const ngm_b200_ctx *c, uint32_t *out, int n) {

@@ -30,6 +30,7 @@ struct CsDev {
 	const uint32_t *table;
 	int k, bin_shift, max_kfreq, max_cmrs;
 	float sensitivity, kmer_min;
+	int merged;               // max_hit[] receives the best vote with both strands added (ReadProvider's estimate) instead of MappedRead::s
 };
 
 struct CsRun {                // one N-free stretch of a contig as CS::PrefixIteration walks it
@@ -319,13 +320,13 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 	uint32_t *s_items_t = s_queue;                             // the queue is dead by the time the order is worked out
 	static_assert(kCsQueue >= kCsMaxItems, "items reuse the queue");
 	__shared__ uint16_t s_multi[kCsMaxMulti];
-	__shared__ uint32_t s_max, s_slow, s_nmulti, s_nacc, s_ncand, s_nitems, s_nord, s_nq;
+	__shared__ uint32_t s_max, s_maxm, s_slow, s_nmulti, s_nacc, s_ncand, s_nitems, s_nord, s_nq;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int r = blockIdx.x;
 	if (r >= n_reads) return;
 	if (tid == 0) {
 		s_len = stride;
-		s_max = s_slow = s_nmulti = s_nacc = s_ncand = s_nitems = s_nord = s_nq = 0;
+		s_max = s_maxm = s_slow = s_nmulti = s_nacc = s_ncand = s_nitems = s_nord = s_nq = 0;
 	}
 	{
 		uint4 *z4 = reinterpret_cast<uint4 *>(seen);               // both bitmaps
@@ -486,6 +487,7 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 	auto bump = [&](uint32_t slot, bool rev) {
 		const uint32_t before = atomicAdd(&cnts[slot], rev ? 0x10000u : 1u);
 		const uint32_t now = ((before >> (rev ? 16 : 0)) & 0x7FFFu) + 1u;
+		if (P.merged) atomicMax(&s_maxm, (before & 0x7FFFu) + ((before >> 16) & 0x7FFFu) + 1u);
 		if (now >= 2u) {
 			atomicMax(&s_max, now);
 			if (now == 2u) {
@@ -553,7 +555,7 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 	__syncthreads();
 	// ---- D: maximum, threshold, accepted entries -----------------------------------------------------------------
 	const uint32_t M = max(s_max, 1u);                         // n_hits > 0: some bin has one vote
-	if (max_hit != nullptr && tid == 0) max_hit[r] = (float) M;
+	if (max_hit != nullptr && tid == 0) max_hit[r] = P.merged ? (float) max(s_maxm, 1u) : (float) M;
 	const float thr = fmaxf(P.kmer_min, __fmul_rn((float) M, P.sensitivity));      // CS.cpp:193-196,271
 	if (!(thr > 0.0f) || s_nmulti > (uint32_t) kCsMaxMulti) {      // zero threshold (strands without a vote pass): exact kernel
 		to_exact(thr > 0.0f ? kCsWhyMulti : kCsWhyZeroThr);
@@ -794,7 +796,7 @@ __global__ void __launch_bounds__(32) cs_search_exact_kernel(const CsDev P, cons
 		gen = (gen + 1) & 0x7FFFFFFFu;                         // CS::RunBatch, CS.cpp:351-356
 		if (gen == 0x7FFFFFFFu) gen = 1;
 		uint32_t rlen = 0;
-		float maxhit = 0.0f, thresh = 0.0f;
+		float maxhit = 0.0f, thresh = 0.0f, maxmerged = 0.0f;
 		bool overflow = false;
 		for (int o = 0; o + P.k <= len && !overflow; ++o) {
 			uint32_t prefix;
@@ -833,13 +835,14 @@ __global__ void __launch_bounds__(32) cs_search_exact_kernel(const CsDev P, cons
 					maxhit = score;
 					thresh = __fmul_rn(maxhit, P.sensitivity);
 				}
+				maxmerged = fmaxf(maxmerged, tab[e].fscore + tab[e].rscore);
 				if (!(tab[e].state & 0x80000000u) && score >= thresh) {
 					tab[e].state |= 0x80000000u;
 					rlist[rlen++] = e;
 				}
 			}
 		}
-		if (max_hit != nullptr) max_hit[r] = maxhit;
+		if (max_hit != nullptr) max_hit[r] = P.merged ? maxmerged : maxhit;
 		const float thr = fmaxf(P.kmer_min, thresh);
 		uint32_t n = 0;
 		for (uint32_t i = 0; i < rlen && !overflow; ++i) {

@@ -118,6 +118,8 @@ def load_library() -> C.CDLL:
                                        C.POINTER(C.c_size_t), C.c_void_p]
     lib.ngm_b200_cs_exact_reads.restype = C.c_uint64
     lib.ngm_b200_cs_exact_reads.argtypes = [C.c_void_p]
+    lib.ngm_b200_cs_estimate_sensitivity.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
+    lib.ngm_b200_cs_set_sensitivity.argtypes = [C.c_void_p, C.c_float]
     lib.ngm_b200_dev_cs_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                            C.c_void_p, C.c_void_p]
     lib.ngm_b200_read_ht_file.argtypes = [C.c_char_p, C.POINTER(_CHtFile)]
@@ -321,6 +323,18 @@ class CudaSW:
             self._check(rc)
             break
         return begin, pairs[: total.value], votes[: total.value], mh
+
+    def cs_estimate_sensitivity(self, reads: np.ndarray, install: bool = True) -> float:
+        """ReadProvider::init's estimate from the whole read set (every 1000th read, ReadProvider.cpp:240); 0.5 for < 1000 reads."""
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        n = reads.shape[0]
+        sens = C.c_float(0.5)
+        if n >= 1000:
+            sample = np.ascontiguousarray(reads[999:min(n, 10_000_000 - 1):1000])
+            self._check(self.lib.ngm_b200_cs_estimate_sensitivity(self.ctx, sample.ctypes.data, sample.shape[0], sample.shape[1], C.byref(sens)))
+        if install:
+            self._check(self.lib.ngm_b200_cs_set_sensitivity(self.ctx, sens))
+        return float(sens.value)
 
     def cs_exact_reads(self) -> int:
         return int(self.lib.ngm_b200_cs_exact_reads(self.ctx))

@@ -395,3 +395,86 @@ long long cs_oracle_search_batch(const cs_oracle_index *ix, const char *reads, i
 	free(s.rlist);
 	return total;
 }
+
+/* ---- sensitivity estimate (ReadProvider::init) -------------------------------------------------------- */
+typedef struct {
+	const cs_oracle_index *ix;
+	int read_len, max_kfreq;
+	uint64_t *bins;             /* stands in for iTable (std::map<uloc, float>, ReadProvider.cpp:34): every vote has weight 1 */
+	size_t n, cap;
+} estimate_state;
+
+static void estimate_vote(estimate_state *s, uint64_t bin) {
+	if (s->n == s->cap) {
+		s->cap = s->cap ? 2 * s->cap : 4096;
+		s->bins = (uint64_t *) realloc(s->bins, s->cap * sizeof(uint64_t));
+	}
+	s->bins[s->n++] = bin;
+}
+
+static void estimate_prefix_search(uint64_t prefix, uint64_t pos, void *data) {        /* ReadProvider.cpp:81-123 (static PrefixSearch) */
+	estimate_state *s = (estimate_state *) data;
+	const cs_oracle_index *ix = s->ix;
+	const uint32_t rc = cs_oracle_revcomp((uint32_t) prefix, ix->k);
+	uint32_t fstart = 0, fcount = 0, rstart = 0, rcount = 0;
+	if (ix->weight[prefix] != 0) {
+		fstart = ix->tab[prefix] - 1;
+		fcount = ix->tab[prefix + 1] - 1 - fstart;
+	}
+	if (ix->weight[rc] != 0) {
+		rstart = ix->tab[rc] - 1;
+		rcount = ix->tab[rc + 1] - 1 - rstart;
+	}
+	if (!((int) (fcount + rcount) < s->max_kfreq)) return;         /* :87 */
+	for (uint32_t i = 0; i < fcount; ++i) estimate_vote(s, ((uint64_t) ix->table[fstart + i] - pos) >> ix->bin_shift);        /* :111-112 */
+	const uint64_t corr = (uint64_t) s->read_len - (pos + (uint64_t) ix->k);                                                   /* :97-100 */
+	for (uint32_t i = 0; i < rcount; ++i) estimate_vote(s, ((uint64_t) ix->table[rstart + i] - corr) >> ix->bin_shift);
+}
+
+static int cmp_u64(const void *a, const void *b) {
+	const uint64_t x = *(const uint64_t *) a, y = *(const uint64_t *) b;
+	return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+/* ReadProvider::init (ReadProvider.cpp:236-251,310-325) + CollectResultsFallback (:53-79): `sampled` are the reads number 1000, 2000, ...
+ * of the input (the caller samples).  Both strands vote into ONE map keyed by the bin, so the best vote here is not MappedRead::s. */
+int cs_oracle_estimate_sensitivity(const cs_oracle_index *ix, const char *sampled, int n_reads, int stride, int max_kfreq, float *sensitivity) {
+	estimate_state s;
+	memset(&s, 0, sizeof(s));
+	s.ix = ix;
+	s.max_kfreq = max_kfreq;
+	const int skip = ix->ref_skip + 1;
+	float sum = 0.0f;
+	int count = 0;
+	for (int r = 0; r < n_reads; ++r) {
+		const char *read = sampled + (size_t) r * stride;
+		int len = 0;
+		while (len < stride && read[len] != '\0') ++len;
+		s.read_len = len;
+		s.n = 0;
+		prefix_iteration(read, (uint64_t) len, estimate_prefix_search, &s, 0, 0, (unsigned) ix->k);
+		float max_current = 0.0f;
+		if (s.n > 0) {
+			qsort(s.bins, s.n, sizeof(uint64_t), cmp_u64);
+			size_t run = 1;
+			for (size_t i = 1; i <= s.n; ++i) {
+				if (i < s.n && s.bins[i] == s.bins[i - 1]) {
+					++run;
+					continue;
+				}
+				if ((float) run > max_current) max_current = (float) run;
+				run = 1;
+			}
+		}
+		const int max = (int) ceil((double) ((len - ix->k + 1) / skip) * 1.0);         /* :68: integer division, then ceil of an int */
+		if ((float) max > 1.0f && max_current <= (float) max) {
+			sum += max_current / (float) max;
+			count += 1;
+		}
+	}
+	free(s.bins);
+	const float avg = sum / (float) count * 1.0f;                   /* :319; 0/0 when nothing qualified */
+	const float lo = 0.3f > avg ? 0.3f : avg;                       /* std::max(0.3f, avg): NaN avg -> 0.3f?  std::max(a,b) = (a<b)?b:a */
+	*sensitivity = lo < 0.9f ? lo : 0.9f;                           /* std::min(x, 0.9f) = (0.9f<x)?0.9f:x */
+	return count;
+}

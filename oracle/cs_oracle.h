@@ -49,6 +49,11 @@ int cs_oracle_search(const cs_oracle_index *ix, const char *read, int read_len, 
 long long cs_oracle_search_batch(const cs_oracle_index *ix, const char *reads, int n_reads, int stride, float sensitivity, float kmer_min,
 		int max_kfreq, int max_cmrs, int *cand_begin, cs_oracle_cand *out, long long out_cap, float *max_hit);
 
+/* The sensitivity NGM estimates when -s is absent (ReadProvider::init, ReadProvider.cpp:236-251,310-325 with the static PrefixSearch
+ * :81-123 and CollectResultsFallback :53-79).  `sampled`: the reads number 1000, 2000, ... of the input.  Returns the number of reads
+ * that contributed; *sensitivity = min(max(0.3, mean), 0.9) (no --fast / --sensitive modifier). */
+int cs_oracle_estimate_sensitivity(const cs_oracle_index *ix, const char *sampled, int n_reads, int stride, int max_kfreq, float *sensitivity);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,6 +90,20 @@ class Index:
                 return begin, out[:total], mh
             cap = int(total) + 16
 
+    def estimate_sensitivity(self, reads: np.ndarray, max_kfreq: int = 0):
+        """ReadProvider::init's estimate over the whole input (every 1000th read of the first 10 M) -> (sensitivity, contributing reads);
+        (0.5, 0) for fewer than 1000 reads (ReadProvider.cpp:310,372-379)."""
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        n = reads.shape[0]
+        if n < 1000:
+            return 0.5, 0
+        sample = np.ascontiguousarray(reads[999:min(n, 10_000_000 - 1):1000])
+        out = C.c_float(0.0)
+        self.lib.cs_oracle_estimate_sensitivity.restype = C.c_int
+        cnt = self.lib.cs_oracle_estimate_sensitivity(C.byref(self.c), sample.ctypes.data_as(C.c_void_p), sample.shape[0], sample.shape[1],
+                                                      max_kfreq or self.max_kfreq, C.byref(out))
+        return float(out.value), int(cnt)
+
     def close(self):
         if getattr(self, "_borrowed", False):
             return

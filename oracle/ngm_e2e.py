@@ -70,5 +70,19 @@ def run(which: str, d: Path, threads: int = 4, extra: Sequence[str] = (), out_na
     p = subprocess.run(cmd, env=env, capture_output=True, text=True, cwd=d)
     if p.returncode != 0 or not out.exists():
         raise RuntimeError(f"{which} failed ({p.returncode}):\n{p.stdout[-1500:]}\n{p.stderr[-1500:]}")
+    global last_log
+    last_log = p.stdout + p.stderr
     lines = [ln for ln in out.read_text().splitlines() if not ln.startswith("@PG")]
     return sorted(lines)
+
+
+last_log = ""
+
+
+def logged_sensitivity() -> float:
+    """'Estimated sensitivity: %f' of the last run (ReadProvider.cpp:357)."""
+    import re
+    m = re.search(r"Estimated sensitivity: ([0-9.]+)", last_log)
+    if m is None:
+        raise RuntimeError("no sensitivity estimate in the log:\n" + last_log[-1500:])
+    return float(m.group(1))

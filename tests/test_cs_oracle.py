@@ -85,3 +85,26 @@ def test_revcomp_prefix():
     code = lambda s: sum(enc[c] << (2 * (len(s) - 1 - i)) for i, c in enumerate(s))
     assert cs_port.revcomp_prefix(code("ACGTT"), 5) == code("AACGT")
     assert cs_port.revcomp_prefix(code("ACGTTGCATGCAA"), 13) == code("TTGCATGCAACGT")
+
+
+SENS = Path(__file__).resolve().parent / "golden" / "cs_sensitivity.json"
+
+
+@pytest.mark.parametrize("case", __import__("json").loads(SENS.read_text()), ids=lambda c: f"seed{c['seed']}_l{c['read_len']}")
+def test_sensitivity_estimate_matches_ngm_log(case):
+    """ReadProvider::init's estimate (no -s): the restatement against the value the unmodified NGM logged (tests/golden/make_cs_sensitivity_golden.py)."""
+    contigs = cs_cases.make_reference(case["seed"], case["scale"])
+    concat, ctg, concat_len = cs_port.layout(contigs)
+    reads = cs_cases.make_reads(case["seed"] + 1, concat, ctg, case["n_reads"], case["read_len"], (case["read_len"] | 1) + 1)
+    ix = cs_port.Index(port.pack_ref(concat), concat_len, ctg, k=13)
+    sens, used = ix.estimate_sensitivity(reads)
+    assert "%f" % sens == case["ngm_logged"] and used > 0
+    ix.close()
+
+
+def test_sensitivity_estimate_needs_1000_reads():
+    contigs = cs_cases.make_reference(5)
+    concat, ctg, concat_len = cs_port.layout(contigs)
+    ix = cs_port.Index(port.pack_ref(concat), concat_len, ctg, k=13)
+    assert ix.estimate_sensitivity(cs_cases.make_reads(6, concat, ctg, 999, 100, 102)) == (0.5, 0)
+    ix.close()

@@ -150,3 +150,43 @@ def test_candidates_feed_the_alignment_path():
             hit += abs(loc - truth[r]) <= 8 and (int(pairs["flags"][j]) & 1) == (r & 1)
     assert hit >= 0.99 * n, hit
     sw.close()
+
+
+@pytest.mark.parametrize("case", __import__("json").loads((GOLD.parent / "cs_sensitivity.json").read_text()), ids=lambda c: f"seed{c['seed']}_l{c['read_len']}")
+def test_sensitivity_estimate_matches_ngm_log_and_oracle(case):
+    """ReadProvider::init's estimate (NGM run without -s): device == oracle == the value the unmodified NGM logged; the per-read best
+    vote with both strands added is the same through the block-per-read kernel and the sequential exact kernel."""
+    import ctypes as C
+    from nextgenmap_b200.host import CudaSW
+    from nextgenmap_b200.host.cuda_sw import PAIR
+    L = case["read_len"]
+    contigs = cs_cases.make_reference(case["seed"], case["scale"])
+    concat, ctg, concat_len = cs_port.layout(contigs)
+    qml, cor = shapes_for(L)
+    reads = cs_cases.make_reads(case["seed"] + 1, concat, ctg, case["n_reads"], L, qml)
+    ix = cs_port.Index(port.pack_ref(concat), concat_len, ctg, k=13)
+    want, used = ix.estimate_sensitivity(reads)
+    sw = CudaSW(qml, cor)
+    sw.set_reference(port.pack_ref(concat), concat_len)
+    sw.cs_build_index(ctg, sw.cs_params(kmer=13))
+    got = sw.cs_estimate_sensitivity(reads)
+    assert np.float32(got) == np.float32(want) and "%f" % got == case["ngm_logged"]
+    sample = np.ascontiguousarray(reads[999::1000])
+    merged = []
+    for flags in (2, 3):
+        begin = np.zeros(len(sample) + 1, np.int32)
+        mh = np.zeros(len(sample), np.float32)
+        total = C.c_size_t(0)
+        pairs = np.zeros(1 << 16, dtype=PAIR)
+        rc = sw.lib.ngm_b200_cs_search(sw.ctx, sample.ctypes.data, len(sample), sample.shape[1], flags, begin.ctypes.data, pairs.ctypes.data, None, 1 << 16,
+                                       C.byref(total), mh.ctypes.data)
+        assert rc == len(sample)
+        merged.append(mh.copy())
+    np.testing.assert_array_equal(merged[0], merged[1])
+    # the installed estimate is what the searches now use
+    begin, cands, mh = ix.search(reads[:300], want)
+    b2, pairs, votes, mh2 = sw.cs_search(reads[:300])
+    np.testing.assert_array_equal(begin, b2)
+    np.testing.assert_array_equal(mh, mh2)
+    ix.close()
+    sw.close()

@@ -25,17 +25,20 @@ def read_fastq(path):
     return names, seqs, quals
 
 
-@pytest.mark.parametrize("ref_len,n_reads,read_len,extra", [(5_000_000, 10_000, 100, []), (1_200_000, 4_000, 150, ["-e"]), (800_000, 3_000, 75, ["-s", "0.8"])])
+@pytest.mark.parametrize("ref_len,n_reads,read_len,extra", [(5_000_000, 10_000, 100, []), (1_200_000, 4_000, 150, ["-e"]), (800_000, 3_000, 75, ["-s", "0.8"]),
+                                                             (900_000, 5_000, 120, ["--estimate"])])
 def test_sam_identical_to_ngm(ref_len, n_reads, read_len, extra):
     from nextgenmap_b200.host import CudaSW, EncodedReference
     from nextgenmap_b200.host import pipeline
+    estimate = "--estimate" in extra                # no -s: NGM estimates the sensitivity from every 1000th read (ReadProvider.cpp:236-325)
     sens = float(extra[extra.index("-s") + 1]) if "-s" in extra else 0.5
     mode = 1 if "-e" in extra else 0
     with tempfile.TemporaryDirectory(prefix="pipe_") as td:
         d = Path(td)
         e2e.write_inputs(d, ref_len=ref_len, n_reads=n_reads, read_len=read_len, seed=4242 + read_len, indel_reads=0.15)
-        args = [a for a in extra if a not in ("-s", str(sens))] + ["-s", str(sens)]
+        args = [a for a in extra if a not in ("-s", str(sens), "--estimate")] + ([] if estimate else ["-s", str(sens)])
         want = [ln for ln in e2e.run("ref", d, threads=4, extra=args) if not ln.startswith("@")]
+        logged = e2e.logged_sensitivity() if estimate else None
         ref = EncodedReference(str(d / "ref.fa-enc.2.ngm"))
         names, seqs, quals = read_fastq(d / "reads.fq")
     qml = (read_len | 1) + 1                         # ReadProvider.cpp:288
@@ -46,6 +49,9 @@ def test_sam_identical_to_ngm(ref_len, n_reads, read_len, extra):
     sw = CudaSW(qml, cor)
     sw.set_reference(ref.packed, ref.concat_len)
     sw.cs_build_index([(c[1], c[2]) for c in ref.contigs], sw.cs_params(kmer=13, sensitivity=sens))
+    if estimate:
+        got_sens = sw.cs_estimate_sensitivity(reads)            # installs it for the searches below
+        assert "%f" % got_sens == "%f" % logged and 0.3 < got_sens < 0.9
     batch = pipeline.map_reads(sw, reads, mode)
     got = sorted(pipeline.sam_lines(sw, batch, reads, names, quals, ref, cor))
     assert len(got) == len(want)
