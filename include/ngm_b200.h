@@ -265,6 +265,31 @@ int ngm_b200_dev_select_top1(ngm_b200_ctx *ctx, int n_reads, const void *d_cand_
  * ScoreBuffer.cpp:236-251; SAM tags NH / X0, SAMWriter.cpp:171,191). */
 int ngm_b200_dev_select_top1_ex(ngm_b200_ctx *ctx, int n_reads, const void *d_cand_begin, const void *d_scores,
 		void *d_best_pair, void *d_mapq, void *d_num_top, void *stream);
+/* -- paired-end selection (BASELINE configs[2]) ------------------------------------------- */
+/* The Config keys ScoreBuffer / NGM read for pairs (src/config/Config.cpp:393-406, ScoreBuffer.h:90-91, NGM.cpp:38-41). */
+typedef struct ngm_b200_pe_params {
+	float pair_score_cutoff;    /* "pair_score_cutoff" (0.9): candidates below cutoff x best score do not take part in pairing */
+	int32_t min_insert_size;    /* "min_insert_size" (0), exclusive */
+	int32_t max_insert_size;    /* "max_insert_size" (1000), exclusive; <= 0 = INT_MAX */
+	int32_t strata;             /* "strata" (0) */
+	int32_t fast_pairing;       /* "fast_pairing" (0): both mates are selected single-end */
+} ngm_b200_pe_params;
+/* Installs the parameters and resets the running insert-size sums (ScoreBuffer's pairDistSum = 0, pairDistCount = 1): call once per
+ * mapping run, before the first batch. */
+int ngm_b200_pe_configure(ngm_b200_ctx *ctx, const ngm_b200_pe_params *params);
+/* pairDistSum / pairDistCount after the batches selected so far (synchronises the device). */
+int ngm_b200_pe_insert_stats(ngm_b200_ctx *ctx, int64_t *dist_sum, int64_t *dist_count);
+/* What ScoreBuffer::DoRun does once both mates of a fragment are scored (ScoreBuffer.cpp:196-215): top1PE + CheckPairs (:365-502), or
+ * top1SE (:228-277) for a mate whose partner has no candidate, under fast_pairing, and as the fallback when no combination has an
+ * insert size inside the limits (both mates then carry NGMNames::PairedFail).  Rows 2f and 2f + 1 of the read batch given to
+ * ngm_b200_set_reads / ngm_b200_dev_set_reads are the mates of fragment f (ReadId & 1 = second mate); n_reads is even.
+ * cand_begin / pairs / scores as for ngm_b200_dev_select_top1 (pairs: n_pairs descriptors as ngm_b200_cs_search emits them, the
+ * candidate's Location is window_start + corridor / 2).  Per read: best_pair = index of the candidate handed to alignment or -1,
+ * mapq, num_top = MappedRead::numTopScores (NH / X0: top1PE stores the number of equally good pairs there, 0 for a unique pair),
+ * pair_fail.  Equal pair scores are broken by the distance to the mean insert size of the pairs accepted before, in input order over
+ * all batches since ngm_b200_pe_configure -- the reference's result with one CS thread.  Enqueued on `stream`, not synchronised. */
+int ngm_b200_dev_select_pairs(ngm_b200_ctx *ctx, int n_reads, const void *d_cand_begin, const void *d_pairs, const void *d_scores, uint32_t n_pairs,
+		void *d_best_pair, void *d_mapq, void *d_num_top, void *d_pair_fail, void *stream);
 /* Device-pointer form of ngm_b200_cs_search: enqueued on `stream`, not synchronised; the caller checks
  * cand_begin[n_reads] <= capacity afterwards.  d_votes / d_max_hit may be NULL. */
 int ngm_b200_dev_cs_search(ngm_b200_ctx *ctx, const void *d_ascii_reads, int n_reads, int stride, int mode_flags, void *d_cand_begin,

@@ -422,6 +422,7 @@ void ngm_b200_destroy(ngm_b200_ctx *c) {
 			&c->d_rascii, &c->d_upairs, &c->d_rpairs, &c->d_noncanon };
 	for (DevBuf *b : db) b->release();
 	if (c->cs) cs_release(c->cs);
+	if (c->pe) pe_release(c->pe);
 	delete c;
 }
 

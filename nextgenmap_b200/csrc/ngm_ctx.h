@@ -63,6 +63,8 @@ struct HostBuf {   // pinned
 
 struct CsState;                                 // candidate search: index + scratch (ngm_cs.cu)
 void cs_release(CsState *cs);
+struct PeState;                                 // paired-end selection: parameters, running insert-size sums, scratch (ngm_select.cu)
+void pe_release(PeState *pe);
 
 }  // namespace ngm
 
@@ -92,4 +94,5 @@ struct ngm_b200_ctx {
 	int reads_stride = 0;      // bytes per row of d_rascii (set_reads)
 	bool have_ref = false;
 	ngm::CsState *cs = nullptr;
+	ngm::PeState *pe = nullptr;
 };

@@ -40,6 +40,12 @@ class CsParams(C.Structure):
                 ("kmer_min", C.c_float), ("max_kfreq", C.c_int32), ("max_cmrs", C.c_int32)]
 
 
+class PeParams(C.Structure):
+    """ngm_b200_pe_params (include/ngm_b200.h); defaults = src/config/Config.cpp:393-406."""
+    _fields_ = [("pair_score_cutoff", C.c_float), ("min_insert_size", C.c_int32), ("max_insert_size", C.c_int32), ("strata", C.c_int32),
+                ("fast_pairing", C.c_int32)]
+
+
 class _CContigRec(C.Structure):
     _fields_ = [("start", C.c_uint64), ("length", C.c_uint32), ("name_len", C.c_uint32), ("name", C.c_char * 100)]
 
@@ -118,6 +124,10 @@ def load_library() -> C.CDLL:
                                        C.POINTER(C.c_size_t), C.c_void_p]
     lib.ngm_b200_cs_exact_reads.restype = C.c_uint64
     lib.ngm_b200_cs_exact_reads.argtypes = [C.c_void_p]
+    lib.ngm_b200_pe_configure.argtypes = [C.c_void_p, C.POINTER(PeParams)]
+    lib.ngm_b200_pe_insert_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.ngm_b200_dev_select_pairs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p]
     lib.ngm_b200_cs_estimate_sensitivity.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
     lib.ngm_b200_cs_set_sensitivity.argtypes = [C.c_void_p, C.c_float]
     lib.ngm_b200_dev_cs_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
@@ -335,6 +345,18 @@ class CudaSW:
         if install:
             self._check(self.lib.ngm_b200_cs_set_sensitivity(self.ctx, sens))
         return float(sens.value)
+
+    def pe_configure(self, pair_score_cutoff: float = 0.9, min_insert_size: int = 0, max_insert_size: int = 1000, strata: int = 0,
+                     fast_pairing: int = 0) -> None:
+        """Paired-end selection parameters (Config.cpp:393-406); resets the running insert-size sums of ScoreBuffer (ScoreBuffer.h:90)."""
+        p = PeParams(pair_score_cutoff, min_insert_size, max_insert_size, strata, fast_pairing)
+        self._check(self.lib.ngm_b200_pe_configure(self.ctx, C.byref(p)))
+
+    def pe_insert_stats(self):
+        """-> (pairDistSum, pairDistCount) of ScoreBuffer (ScoreBuffer.cpp:420-422)."""
+        s, n = C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.ngm_b200_pe_insert_stats(self.ctx, C.byref(s), C.byref(n)))
+        return int(s.value), int(n.value)
 
     def cs_exact_reads(self) -> int:
         return int(self.lib.ngm_b200_cs_exact_reads(self.ctx))

@@ -1,26 +1,29 @@
-"""Host-side mirror of NextGenMap's single-end mapping run on top of the device library:
+"""Host-side mirror of NextGenMap's mapping run on top of the device library:
 
-    reads -> CS (k-mer vote, CS.cpp) -> ScoreBuffer (BatchScore of every candidate, top1SE + computeMQ)
+    reads -> CS (k-mer vote, CS.cpp) -> ScoreBuffer (BatchScore of every candidate; top1SE + computeMQ, or top1PE for pairs)
           -> AlignmentBuffer (BatchAlign of the winner) -> GenericReadWriter filters -> SAMWriter lines
 
 Everything numeric runs in ``libngm_b200.so`` (there is no CPU path); this module only strings the device calls together
-and renders the records the way ``SAMWriter::DoWriteReadGeneric`` / ``DoWriteUnmappedReadGeneric`` do
-(src/writer/SAMWriter.cpp:98-228,312-365), after the post-processing of ``AlignmentBuffer::DoRun`` / ``WriteRead``
-(src/AlignmentBuffer.cpp:121-135,166-176) and the output filters of ``GenericReadWriter::WriteRead``
-(src/writer/GenericReadWriter.h:190-256).  Single-end, ``topn`` 1, no bs-mapping -- what BASELINE configs[0]/[1] run.
+and renders the records the way ``SAMWriter::DoWriteReadGeneric`` / ``DoWriteUnmappedReadGeneric`` / ``DoWritePair`` do
+(src/writer/SAMWriter.cpp:98-228,230-310,312-365), after the post-processing of ``AlignmentBuffer::DoRun`` / ``WriteRead``
+(src/AlignmentBuffer.cpp:121-135,166-208) and the output filters of ``GenericReadWriter::WriteRead`` / ``WritePair``
+(src/writer/GenericReadWriter.h:190-312).  ``topn`` 1, no bs-mapping -- what BASELINE configs[0]-[2] run.
+
+The renderers take any object with the fields of ``MappedBatch`` (the tests also feed them from the CPU oracles to pin those against
+the unmodified NextGenMap).
 """
 from __future__ import annotations
 
-import ctypes as C
 import math
 from dataclasses import dataclass
-from typing import List, Optional, Sequence, Tuple
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .cuda_sw import ALIGN_REC, PAIR, CudaSW
+from .cuda_sw import PAIR, CudaSW
 
 COMP = bytes.maketrans(b"ACGT", b"TGCA")
+U64 = 2 ** 64 - 1
 
 
 @dataclass
@@ -30,21 +33,43 @@ class MappedBatch:
     pairs: np.ndarray           # PAIR [total]  candidates in the reference's order
     scores: np.ndarray          # float32 [total]  BatchScore
     max_hit: np.ndarray         # float32  MappedRead::s
-    best_pair: np.ndarray       # int32  index into pairs, -1 = no candidate
+    best_pair: np.ndarray       # int32  index into pairs, -1 = no candidate handed to alignment
     mapq: np.ndarray            # int32
     num_top: np.ndarray         # int32  MappedRead::numTopScores
-    recs: np.ndarray            # ALIGN_REC
-    heap: np.ndarray            # uint8 string heap (CIGAR, MD)
+    recs: np.ndarray            # ALIGN_REC fields position_offset, qstart, qend, nm, identity, score
+    heap: Optional[np.ndarray]  # uint8 string heap (CIGAR, MD)
+    strings: Callable[[int], Tuple[bytes, bytes]] = None      # read -> (CIGAR, MD bytes as written)
+    pair_fail: Optional[np.ndarray] = None                    # int32  NGMNames::PairedFail set by top1PE (paired runs)
 
 
-def map_reads(sw: CudaSW, reads: np.ndarray, mode: int = 0) -> MappedBatch:
-    """One batch through candidate search, scoring, top-1 selection and alignment.  Needs set_reference + a prefix table."""
-    import torch
+def _search_and_score(sw: CudaSW, reads: np.ndarray, mode: int):
     reads = np.ascontiguousarray(reads, dtype=np.uint8)
-    n = reads.shape[0]
     begin, pairs, votes, max_hit = sw.cs_search(reads)
     sw.set_reads(reads)
     scores = sw.score_pairs(mode, pairs)
+    return reads, begin, pairs, scores, max_hit
+
+
+def _align_winners(sw: CudaSW, mode: int, n: int, pairs: np.ndarray, best: np.ndarray):
+    winners = np.zeros(n, dtype=PAIR)
+    has = best >= 0
+    winners[has] = pairs[best[has]]
+    winners["read_index"] = np.arange(n, dtype=np.uint32)
+    winners["flags"][~has] = 4                     # NGM_B200_PAIR_SKIP
+    recs, heap = sw.align_pairs(mode, winners)
+    raw = heap.tobytes()
+
+    def strings(r: int):
+        o, cl, ml = int(recs[r]["str_off"]), int(recs[r]["cigar_len"]), int(recs[r]["md_len"])
+        return raw[o: o + cl], raw[o + cl: o + cl + ml]
+    return recs, heap, strings
+
+
+def map_reads(sw: CudaSW, reads: np.ndarray, mode: int = 0) -> MappedBatch:
+    """One single-end batch through candidate search, scoring, top-1 selection and alignment.  Needs set_reference + a prefix table."""
+    import torch
+    reads, begin, pairs, scores, max_hit = _search_and_score(sw, reads, mode)
+    n = reads.shape[0]
     dev = torch.device("cuda", sw.params.device)
     st = torch.cuda.current_stream(dev).cuda_stream
     d_begin = torch.from_numpy(begin).to(dev)
@@ -55,13 +80,28 @@ def map_reads(sw: CudaSW, reads: np.ndarray, mode: int = 0) -> MappedBatch:
     sw._check(sw.lib.ngm_b200_dev_select_top1_ex(sw.ctx, n, d_begin.data_ptr(), d_scores.data_ptr(), d_best.data_ptr(), d_mq.data_ptr(), d_nt.data_ptr(), st))
     torch.cuda.synchronize(dev)
     best = d_best.cpu().numpy()
-    winners = np.zeros(n, dtype=PAIR)
-    has = best >= 0
-    winners[has] = pairs[best[has]]
-    winners["read_index"] = np.arange(n, dtype=np.uint32)
-    winners["flags"][~has] = 4                     # NGM_B200_PAIR_SKIP
-    recs, heap = sw.align_pairs(mode, winners)
-    return MappedBatch(begin, pairs, scores, max_hit, best, d_mq.cpu().numpy(), d_nt.cpu().numpy(), recs, heap)
+    recs, heap, strings = _align_winners(sw, mode, n, pairs, best)
+    return MappedBatch(begin, pairs, scores, max_hit, best, d_mq.cpu().numpy(), d_nt.cpu().numpy(), recs, heap, strings)
+
+
+def map_pairs(sw: CudaSW, reads: np.ndarray, mode: int = 0) -> MappedBatch:
+    """One paired-end batch (rows 2f, 2f + 1 = the mates of fragment f; ``sw.pe_configure`` once per run before the first batch):
+    candidate search and scoring per mate, top1PE / top1SE on the device, alignment of every selected candidate."""
+    import torch
+    reads, begin, pairs, scores, max_hit = _search_and_score(sw, reads, mode)
+    n = reads.shape[0]
+    dev = torch.device("cuda", sw.params.device)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    d_begin = torch.from_numpy(begin).to(dev)
+    d_scores = torch.from_numpy(scores).to(dev) if len(scores) else torch.zeros(1, dtype=torch.float32, device=dev)
+    d_pairs = torch.from_numpy(pairs.view(np.uint8).reshape(-1, 16)).to(dev) if len(pairs) else torch.zeros((1, 16), dtype=torch.uint8, device=dev)
+    out = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(4)]
+    sw._check(sw.lib.ngm_b200_dev_select_pairs(sw.ctx, n, d_begin.data_ptr(), d_pairs.data_ptr(), d_scores.data_ptr(), len(pairs), out[0].data_ptr(),
+                                               out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), st))
+    torch.cuda.synchronize(dev)
+    best, mq, nt, pf = (t.cpu().numpy() for t in out)
+    recs, heap, strings = _align_winners(sw, mode, n, pairs, best)
+    return MappedBatch(begin, pairs, scores, max_hit, best, mq, nt, recs, heap, strings, pf)
 
 
 def _xi(identity: float) -> str:
@@ -71,42 +111,128 @@ def _xi(identity: float) -> str:
     return "%g" % float(np.float32(r / 10000.0))
 
 
-def sam_lines(sw: CudaSW, batch: MappedBatch, reads: np.ndarray, names: Sequence[str], quals: Sequence[bytes], encref, corridor: int,
-              min_identity: float = 0.65, min_residues: float = 0.5) -> List[str]:
-    """SAM body lines of a single-end batch (no header), one per read, in read order."""
+@dataclass
+class _Read:
+    """One read after AlignmentBuffer::DoRun: what WriteRead / WritePair look at."""
+    name: str
+    seq: bytes
+    qual: bytes
+    length: int
+    has: bool = False           # hasCandidates() with a usable alignment
+    reverse: bool = False
+    loc: int = 0                # Location.m_Location (concatenated until convert() succeeds)
+    contig: int = 0             # Location.getrefId()
+    converted: bool = False
+    bp: int = -1
+    r: int = -1
+
+
+def _collect(batch, reads: np.ndarray, names, quals, encref) -> List[_Read]:
     out = []
     for r in range(reads.shape[0]):
         seq = reads[r].tobytes().split(b"\0")[0]
-        length = len(seq)
-        qual = quals[r]
-        name = names[r]
-        line = None
+        rd = _Read(names[r], seq, quals[r], len(seq), r=r)
         bp = int(batch.best_pair[r])
-        rec = batch.recs[r]
-        if bp >= 0 and float(rec["score"]) >= 0.0:
+        if bp >= 0 and float(batch.recs[r]["score"]) >= 0.0:
             p = batch.pairs[bp]
-            reverse = bool(int(p["flags"]) & 1)
+            rd.has, rd.bp = True, bp
+            rd.reverse = bool(int(p["flags"]) & 1)
             # AlignmentBuffer.cpp:129: Location += PositionOffset - (corridor >> 1); window_start is Location - corridor/2 already
-            loc = (int(p["window_start"]) + int(rec["position_offset"])) & (2 ** 64 - 1)
-            conv = encref.convert(loc)              # AlignmentBuffer.cpp:171-175
-            qstart, qend = int(rec["qstart"]), int(rec["qend"])
-            mres = length * min_residues if min_residues <= 1.0 else min_residues      # GenericReadWriter.h:206-210
-            mapped = conv is not None and float(rec["identity"]) >= np.float32(min_identity) and float(length - qstart - qend) >= np.float32(mres)
-            if mapped:
-                contig, pos = conv
-                cigar, md = sw.strings_of(batch.recs, batch.heap, r)
-                s, q = seq, qual
-                flags = 0
-                if reverse:
-                    s = seq.translate(COMP)[::-1]
-                    q = qual[::-1]
-                    flags |= 0x10
-                ntop = int(batch.num_top[r])
-                line = "\t".join([name, str(flags), encref.contigs[contig][0], str((pos + 1) & 0xFFFFFFFF), str(int(batch.mapq[r])), cigar.decode(), "*", "0", "0",
-                                  s.decode(), q.decode(), "AS:i:%d" % int(batch.scores[bp]), "NM:i:%d" % int(rec["nm"]), "NH:i:%d" % ntop,
-                                  "XI:f:" + _xi(float(rec["identity"])), "X0:i:%d" % ntop, "XE:i:%d" % int(batch.max_hit[r]),
-                                  "XR:i:%d" % (length - qstart - qend), "MD:Z:" + md.split(b"\0")[0].decode()])
-        if line is None:                            # SAMWriter.cpp:312-365
-            line = "\t".join([name, "4", "*", "0", "0", "*", "*", "0", "0", seq.decode(), qual.decode()])
-        out.append(line)
+            rd.loc = (int(p["window_start"]) + int(batch.recs[r]["position_offset"])) & U64
+            conv = encref.convert(rd.loc)               # AlignmentBuffer.cpp:171-175
+            if conv is not None:
+                rd.contig, rd.loc, rd.converted = conv[0], conv[1], True
+        out.append(rd)
+    return out
+
+
+def _passes(batch, rd: _Read, min_identity: float, min_residues: float) -> bool:
+    rec = batch.recs[rd.r]
+    mres = rd.length * min_residues if min_residues <= 1.0 else min_residues      # GenericReadWriter.h:206-210,273-278
+    return bool(float(rec["identity"]) >= np.float32(min_identity)
+                and float(rd.length - int(rec["qstart"]) - int(rec["qend"])) >= np.float32(mres))
+
+
+def _mapped_line(batch, rd: _Read, encref, flags: int, rnext: str, pnext: int, tlen: int) -> str:
+    """SAMWriter::DoWriteReadGeneric (SAMWriter.cpp:98-228)."""
+    rec = batch.recs[rd.r]
+    cigar, md = batch.strings(rd.r)
+    s, q = rd.seq, rd.qual
+    if rd.reverse:
+        s = rd.seq.translate(COMP)[::-1]
+        q = rd.qual[::-1]
+        flags |= 0x10
+    ntop = int(batch.num_top[rd.r])
+    qstart, qend = int(rec["qstart"]), int(rec["qend"])
+    return "\t".join([rd.name, str(flags), encref.contigs[rd.contig][0], str((rd.loc + 1) & 0xFFFFFFFF), str(int(batch.mapq[rd.r])), cigar.decode(),
+                      rnext, str((pnext + 1) & 0xFFFFFFFF), str(tlen), s.decode(), q.decode(), "AS:i:%d" % int(batch.scores[rd.bp]),
+                      "NM:i:%d" % int(rec["nm"]), "NH:i:%d" % ntop, "XI:f:" + _xi(float(rec["identity"])), "X0:i:%d" % ntop,
+                      "XE:i:%d" % int(batch.max_hit[rd.r]), "XR:i:%d" % (rd.length - qstart - qend), "MD:Z:" + md.split(b"\0")[0].decode()])
+
+
+def _i32(v: int) -> int:
+    v &= 0xFFFFFFFF
+    return v - (1 << 32) if v & 0x80000000 else v
+
+
+def _unmapped_line(rd: _Read, flags: int, rname: str = "*", loc: int = -1, rnext: str = "*", pnext: int = -1) -> str:
+    """SAMWriter::DoWriteUnmappedReadGeneric (SAMWriter.cpp:312-365)."""
+    return "\t".join([rd.name, str(flags | 0x4), rname, str(_i32(loc + 1)), "0", "*", rnext, str(_i32(pnext + 1)), "0", rd.seq.decode(), rd.qual.decode()])
+
+
+def sam_lines(sw: Optional[CudaSW], batch, reads: np.ndarray, names: Sequence[str], quals: Sequence[bytes], encref, corridor: int,
+              min_identity: float = 0.65, min_residues: float = 0.5) -> List[str]:
+    """SAM body lines of a single-end batch (no header), one per read, in read order."""
+    out = []
+    for rd in _collect(batch, reads, names, quals, encref):
+        if rd.has and rd.converted and _passes(batch, rd, min_identity, min_residues):
+            out.append(_mapped_line(batch, rd, encref, 0, "*", -1, 0))
+        else:
+            out.append(_unmapped_line(rd, 0))
+    return out
+
+
+def sam_lines_paired(batch, reads: np.ndarray, names: Sequence[str], quals: Sequence[bytes], encref, corridor: int, min_identity: float = 0.65,
+                     min_residues: float = 0.5, min_mq: int = 0, min_insert_size: int = 0, max_insert_size: int = 1000) -> List[str]:
+    """SAM body lines of a paired batch, two per fragment: AlignmentBuffer::WriteRead's pair check (AlignmentBuffer.cpp:176-200),
+    GenericReadWriter::WritePair's filters (GenericReadWriter.h:258-312) and SAMWriter::DoWritePair (SAMWriter.cpp:230-310)."""
+    rds = _collect(batch, reads, names, quals, encref)
+    if max_insert_size <= 0:
+        max_insert_size = 2 ** 31 - 1
+    out = []
+    for f in range(0, len(rds) - 1, 2):
+        a, b = rds[f], rds[f + 1]                       # a: first mate (ReadId even), b: second mate
+        fail = bool(batch.pair_fail[a.r]) or bool(batch.pair_fail[b.r])
+        # WriteRead: the mate that arrives second does the check; with both aligned that is the first mate (top1PE submits read = second
+        # mate first), so read = a, read->Paired = b
+        if a.has and b.has:
+            d = (b.loc - a.loc + a.length) if b.loc > a.loc else (a.loc - b.loc + b.length)
+            d = _i32(d)
+            if a.contig != b.contig or d < min_insert_size or d > max_insert_size or a.reverse == b.reverse:
+                fail = True
+        for rd in (a, b):                               # WritePair: mapped1 / mapped2, clearScores() otherwise
+            if rd.has and not (int(batch.mapq[rd.r]) >= min_mq and _passes(batch, rd, min_identity, min_residues)):
+                rd.has = False
+        fa, fb = 0x1 | 0x40, 0x1 | 0x80
+        ra, rb = encref.contigs[a.contig][0], encref.contigs[b.contig][0]
+        if not a.has and not b.has:
+            out += [_unmapped_line(b, fb | 0x8), _unmapped_line(a, fa | 0x8)]
+        elif not a.has:
+            out += [_mapped_line(batch, b, encref, fb | 0x8, "=", b.loc, 0), _unmapped_line(a, fa, rb, b.loc, "=", b.loc)]
+        elif not b.has:
+            out += [_unmapped_line(b, fb, ra, a.loc, "=", a.loc), _mapped_line(batch, a, encref, fa | 0x8, "=", a.loc, 0)]
+        elif not fail:
+            fa |= 0x2
+            fb |= 0x2
+            fwd, rev = (a, b) if not a.reverse else (b, a)          # after the check above exactly one mate is on the minus strand
+            rec = batch.recs[rev.r]
+            dist = _i32((rev.loc + rev.length - int(rec["qstart"]) - int(rec["qend"])) - fwd.loc)
+            ffwd, frev = (fa, fb) if fwd is a else (fb, fa)
+            out += [_mapped_line(batch, rev, encref, frev, "=", fwd.loc, -dist), _mapped_line(batch, fwd, encref, ffwd | 0x20, "=", rev.loc, dist)]
+        else:
+            if a.reverse:
+                fb |= 0x20
+            if b.reverse:
+                fa |= 0x20
+            out += [_mapped_line(batch, b, encref, fb, ra, a.loc, 0), _mapped_line(batch, a, encref, fa, rb, b.loc, 0)]
     return out

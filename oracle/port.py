@@ -45,7 +45,7 @@ class Scoring:
 
 
 def build(force: bool = False) -> Path:
-    if force or not LIB.exists() or LIB.stat().st_mtime < (HERE / "ngm_oracle.c").stat().st_mtime:
+    if force or not LIB.exists() or LIB.stat().st_mtime < max(f.stat().st_mtime for f in HERE.glob("*_oracle.[ch]")):
         subprocess.run(["make", "-C", str(HERE), "port"], check=True, capture_output=True)
     return LIB
 

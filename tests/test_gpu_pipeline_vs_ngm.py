@@ -60,3 +60,42 @@ def test_sam_identical_to_ngm(ref_len, n_reads, read_len, extra):
     assert sum(1 for ln in want if ln.split("\t")[1] != "4") > 0.95 * len(want)
     sw.close()
     ref.close()
+
+
+@pytest.mark.parametrize("ref_len,n_frags,read_len,seed,extra", [(600_000, 2000, 100, 31, []), (500_000, 1200, 150, 32, ["-e"]),
+                                                                 (400_000, 1000, 75, 33, ["--fast-pairing"])])
+def test_paired_sam_identical_to_ngm(ref_len, n_frags, read_len, seed, extra):
+    """BASELINE configs[2] shape: interleaved mates, `ngm -p -t 1` (one CS thread: the insert-size mean that breaks ties between equally
+    scoring pairs runs through the reads in input order).  Device: cs_search + BatchScore per mate, ngm_b200_dev_select_pairs (top1PE),
+    BatchAlign; pair check, filters and SAM flags / RNEXT / PNEXT / TLEN by the host mirror of WriteRead / WritePair / DoWritePair.  The
+    reads go through in three batches."""
+    from nextgenmap_b200.host import CudaSW, EncodedReference
+    from nextgenmap_b200.host import pipeline
+    from tests.test_mapper_oracle import read_fastq as read_fastq_pe, rows
+    mode = 1 if "-e" in extra else 0
+    with tempfile.TemporaryDirectory(prefix="pipe_pe_") as td:
+        d = Path(td)
+        e2e.write_paired_inputs(d, ref_len=ref_len, n_frags=n_frags, read_len=read_len, seed=seed)
+        want = [ln for ln in e2e.run("ref", d, threads=1, extra=["-p", "-s", "0.5", *extra]) if not ln.startswith("@")]
+        ref = EncodedReference(str(d / "ref.fa-enc.2.ngm"))
+        names, seqs, quals = read_fastq_pe(d / "reads.fq", True)
+    qml, cor = (read_len | 1) + 1, int(5 + 0.15 * read_len)
+    reads = rows(seqs, qml)
+    sw = CudaSW(qml, cor)
+    sw.set_reference(ref.packed, ref.concat_len)
+    sw.cs_build_index([(c[1], c[2]) for c in ref.contigs], sw.cs_params(kmer=13, sensitivity=0.5))
+    sw.pe_configure(fast_pairing=1 if "--fast-pairing" in extra else 0)
+    got, n = [], len(names)
+    step = (n // 3 + 1) & ~1
+    for lo in range(0, n, step):
+        hi = min(n, lo + step)
+        batch = pipeline.map_pairs(sw, reads[lo:hi], mode)
+        got += pipeline.sam_lines_paired(batch, reads[lo:hi], names[lo:hi], quals[lo:hi], ref, cor)
+    got.sort()
+    assert len(got) == len(want)
+    bad = [(g, w) for g, w in zip(got, want) if g != w]
+    assert not bad, f"{len(bad)} of {len(want)} SAM lines differ, first:\n{bad[0][0]}\n{bad[0][1]}"
+    flags = {ln.split("\t")[1] for ln in want}
+    assert {"99", "147", "83", "163"} <= flags and len(flags) >= 10
+    sw.close()
+    ref.close()

@@ -1,0 +1,92 @@
+"""Paired-end selection on the device (ngm_b200_dev_select_pairs: ScoreBuffer::top1PE + CheckPairs + the top1SE fallbacks,
+ScoreBuffer.cpp:196-215,228-277,365-502) against oracle/select_oracle.c, which is pinned to the unmodified NextGenMap through whole
+runs (tests/test_mapper_oracle.py).  Random candidate lists with many equal scores (the order std::sort leaves them in decides the
+winner), lists longer than 16 (introsort instead of insertion sort), equal pair scores (running insert-size mean, carried over
+batches), mates without candidates, strata and fast pairing."""
+import numpy as np
+import pytest
+
+from oracle import mapper_port
+
+pytestmark = pytest.mark.gpu
+
+
+def make_case(seed, n_frag, max_cands, score_values):
+    rng = np.random.default_rng(seed)
+    n = 2 * n_frag
+    counts = rng.integers(0, max_cands + 1, n)
+    counts[rng.random(n) < 0.08] = 0
+    big = rng.random(n) < 0.03
+    counts[big] = rng.integers(17, 90, int(big.sum()))                 # beyond std::sort's insertion-sort threshold
+    begin = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    total = int(begin[-1])
+    scores = rng.choice(score_values, total).astype(np.float32)
+    frag_pos = rng.integers(5_000, 2_000_000, n_frag)
+    loc = np.zeros(total, np.uint64)
+    for r in range(n):
+        b, e = begin[r], begin[r + 1]
+        base = frag_pos[r // 2] + (0 if r % 2 == 0 else int(rng.integers(150, 700)))
+        jitter = rng.choice([0, 0, 0, 4, -4, 8, 300, -300, 5000, 40_000], e - b)
+        loc[b:e] = (base + jitter).astype(np.uint64)
+    lens = rng.choice([100, 100, 100, 97, 64], n).astype(np.int32)
+    return begin, scores, loc, lens
+
+
+@pytest.mark.parametrize("seed,max_cands,values,kw", [
+    (1, 4, [0.0, 400.0, 850.0, 900.0, 950.0, 1000.0], {}),
+    (2, 8, [900.0, 1000.0], {}),                                       # ties everywhere
+    (3, 12, [0.0, 10.0, 700.0, 990.0, 1000.0], {"strata": 1}),
+    (4, 6, [500.0, 800.0, 1000.0], {"fast_pairing": 1}),
+    (5, 5, [-1.0, 0.0, 300.0, 1000.0], {"min_insert_size": 200, "max_insert_size": 450}),
+    (6, 3, [1000.0], {"pair_score_cutoff": 0.5, "max_insert_size": 0}),
+])
+def test_select_pairs_matches_oracle(seed, max_cands, values, kw):
+    import torch
+    from nextgenmap_b200.host import CudaSW
+    from nextgenmap_b200.host.cuda_sw import PAIR
+    qml, cor = 102, 20
+    sw = CudaSW(qml, cor)
+    sw.pe_configure(**kw)
+    okw = dict(kw)
+    sel = mapper_port.Selector(**okw)
+    st = torch.cuda.current_stream().cuda_stream
+    for batch in range(3):                                             # pairDistSum / pairDistCount carry over the batches
+        begin, scores, loc, lens = make_case(100 * seed + batch, 3000, max_cands, values)
+        n = len(lens)
+        reads = np.zeros((n, qml), np.uint8)
+        for r in range(n):
+            reads[r, : lens[r]] = ord("A")
+        sw.set_reads(reads)
+        want = sel.select_pairs(begin, loc, scores, lens)
+        pairs = np.zeros(max(len(scores), 1), dtype=PAIR)
+        pairs["window_start"][: len(scores)] = loc - np.uint64(cor >> 1)
+        d_begin = torch.from_numpy(begin).cuda()
+        d_scores = torch.from_numpy(np.concatenate([scores, np.zeros(1, np.float32)])).cuda()
+        d_pairs = torch.from_numpy(pairs.view(np.uint8).reshape(-1, 16)).cuda()
+        out = [torch.full((n,), -7, dtype=torch.int32, device="cuda") for _ in range(4)]
+        rc = sw.lib.ngm_b200_dev_select_pairs(sw.ctx, n, d_begin.data_ptr(), d_pairs.data_ptr(), d_scores.data_ptr(), len(scores), out[0].data_ptr(),
+                                              out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), st)
+        assert rc == n, sw._err()
+        torch.cuda.synchronize()
+        best, mq, nt, pf = (t.cpu().numpy() for t in out)
+        np.testing.assert_array_equal(best, want["best"], err_msg=f"batch {batch}: best")
+        np.testing.assert_array_equal(mq, want["mapq"], err_msg=f"batch {batch}: mapq")
+        has = want["best"] >= 0
+        np.testing.assert_array_equal(nt[has], want["num_top"][has], err_msg=f"batch {batch}: num_top")
+        np.testing.assert_array_equal(pf, want["paired_fail"], err_msg=f"batch {batch}: pair_fail")
+        assert sw.pe_insert_stats() == (sel.state.dist_sum, sel.state.dist_count)
+    assert sel.state.dist_count > 100 or kw.get("fast_pairing")
+    sw.close()
+
+
+def test_select_pairs_argument_checks():
+    import torch
+    from nextgenmap_b200.host import CudaSW
+    sw = CudaSW(102, 20)
+    z = torch.zeros(64, dtype=torch.int32, device="cuda")
+    args = (z.data_ptr(),) * 3 + (0,) + (z.data_ptr(),) * 4 + (None,)
+    assert sw.lib.ngm_b200_dev_select_pairs(sw.ctx, 2, *args) == -4              # pe_configure missing
+    sw.pe_configure()
+    assert sw.lib.ngm_b200_dev_select_pairs(sw.ctx, 3, *args) == -1              # odd number of reads
+    assert sw.lib.ngm_b200_dev_select_pairs(sw.ctx, 2, *args) == -4              # no read batch
+    sw.close()

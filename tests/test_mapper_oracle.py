@@ -1,0 +1,132 @@
+"""Whole mapping runs on the CPU restatements (oracle/mapper_port.py: candidate search -> scores -> selection -> alignments, rendered by
+the host mirror of SAMWriter) against the UNMODIFIED NextGenMap: single-end and paired-end (`-p -t 1`; BASELINE configs[2] shape).
+This is what pins oracle/select_oracle.c -- ScoreBuffer::top1SE / top1PE / CheckPairs incl. the order std::sort leaves equal scores in
+and the running insert-size mean that breaks ties between equally scoring pairs (the paired inputs hold repeated segments for that).
+
+The golden SAM (tests/golden/pe_l100.sam.gz, made by tests/golden/make_pe_golden.py from the reference binary) is checked always; the
+live runs need oracle/_ref/ngm/ngm_ref."""
+import gzip
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import cs_port, mapper_port, ngm_e2e as e2e
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def read_fastq(path, paired):
+    names, seqs, quals = [], [], []
+    with open(path, "rb") as f:
+        lines = f.read().split(b"\n")
+    for i in range(0, len(lines) - 3, 4):
+        nm = lines[i][1:].decode().split()[0]
+        if paired and len(nm) > 2 and nm[-2] == "/":        # ReadProvider::NextRead strips the mate suffix (ReadProvider.cpp:417-420)
+            nm = nm[:-2]
+        names.append(nm)
+        seqs.append(lines[i + 1])
+        quals.append(lines[i + 3])
+    return names, seqs, quals
+
+
+def rows(seqs, qml):
+    reads = np.zeros((len(seqs), qml), np.uint8)
+    for i, s in enumerate(seqs):
+        reads[i, : len(s)] = np.frombuffer(s, np.uint8)
+    return reads
+
+
+class LaidOutReference:
+    """The concatenated reference as SequenceProvider::Init lays it out (SequenceProvider.cpp:289-330) from a FASTA file, with convert()
+    (SequenceProvider.cpp:111-141) -- stands in for NGM's `<ref>-enc.2.ngm` where the reference binary is not available."""
+
+    def __init__(self, fasta: Path):
+        from oracle import port
+        names, seqs = [], []
+        for ln in open(fasta, "rb").read().split(b"\n"):
+            if ln.startswith(b">"):
+                names.append(ln[1:].split()[0].decode())
+                seqs.append([])
+            elif ln:
+                seqs[-1].append(ln)
+        concat, ctg, self.concat_len = cs_port.layout([b"".join(s) for s in seqs])
+        self.packed = port.pack_ref(concat)
+        self.contigs = [(nm, st, ln) for nm, (st, ln) in zip(names, ctg)]
+        self.starts = [st for _, st, _ in self.contigs] + [len(concat) + 1000]
+
+    def convert(self, pos: int):
+        import bisect
+        i = bisect.bisect_right(self.starts, pos)            # std::upper_bound over refStartPos
+        if i >= len(self.starts) or self.starts[i] - pos < 1000 or i == 0:
+            return None
+        return i - 1, pos - self.starts[i - 1]
+
+    def close(self):
+        pass
+
+
+def oracle_sam(d: Path, read_len: int, mode: int, sens: float, paired: bool, batches: int = 1, sel=None):
+    from nextgenmap_b200.host import EncodedReference        # host-only reader of <ref>-enc.2.ngm (no CUDA call)
+    from nextgenmap_b200.host import pipeline
+    enc = d / "ref.fa-enc.2.ngm"
+    ref = EncodedReference(str(enc)) if enc.exists() else LaidOutReference(d / "ref.fa")
+    names, seqs, quals = read_fastq(d / "reads.fq", paired)
+    qml, cor = (read_len | 1) + 1, int(5 + 0.15 * read_len)
+    reads = rows(seqs, qml)
+    ix = cs_port.Index(ref.packed, ref.concat_len, [(c[1], c[2]) for c in ref.contigs], k=13)
+    sel = sel or mapper_port.Selector()
+    got, n = [], len(names)
+    step = (n // batches + 1) & ~1
+    for lo in range(0, n, step):                             # the insert-size sums carry over the batches
+        hi = min(n, lo + step)
+        batch = mapper_port.map_batch(ref.packed, ref.concat_len, ix, reads[lo:hi], qml, cor, mode, sens, sel, paired=paired)
+        if paired:
+            got += pipeline.sam_lines_paired(batch, reads[lo:hi], names[lo:hi], quals[lo:hi], ref, cor)
+        else:
+            got += pipeline.sam_lines(None, batch, reads[lo:hi], names[lo:hi], quals[lo:hi], ref, cor)
+    ix.close()
+    ref.close()
+    return sorted(got), sel
+
+
+def diff(got, want):
+    assert len(got) == len(want)
+    bad = [(g, w) for g, w in zip(got, want) if g != w]
+    assert not bad, f"{len(bad)} of {len(want)} SAM lines differ, first:\n{bad[0][0]}\n{bad[0][1]}"
+
+
+def test_paired_golden_sam():
+    """Inputs regenerated from the seed; NGM's answer from the committed fixture."""
+    with tempfile.TemporaryDirectory(prefix="pegold_") as td:
+        d = Path(td)
+        e2e.write_paired_inputs(d, ref_len=300_000, n_frags=600, read_len=100, seed=77)
+        got, sel = oracle_sam(d, 100, 0, 0.5, True, batches=3)
+    want = gzip.open(GOLD / "pe_l100.sam.gz", "rt").read().splitlines()
+    diff(got, want)
+    flags = {ln.split("\t")[1] for ln in want}
+    assert {"99", "147", "83", "163"} <= flags and len(flags) >= 12          # proper pairs, broken pairs, unmapped mates
+    assert sel.state.dist_count > 300
+
+
+@pytest.mark.skipif(not e2e.available("ref"), reason="oracle/_ref/ngm/ngm_ref not built")
+@pytest.mark.parametrize("ref_len,n_frags,read_len,seed,extra", [(600_000, 1500, 100, 5, []), (500_000, 1000, 150, 6, ["-e"]), (400_000, 800, 75, 7, ["--fast-pairing"])])
+def test_paired_sam_identical_to_ngm(ref_len, n_frags, read_len, seed, extra):
+    with tempfile.TemporaryDirectory(prefix="pe_") as td:
+        d = Path(td)
+        e2e.write_paired_inputs(d, ref_len=ref_len, n_frags=n_frags, read_len=read_len, seed=seed)
+        want = [ln for ln in e2e.run("ref", d, threads=1, extra=["-p", "-s", "0.5", *extra]) if not ln.startswith("@")]
+        sel = mapper_port.Selector(fast_pairing=1 if "--fast-pairing" in extra else 0)
+        got, _ = oracle_sam(d, read_len, 1 if "-e" in extra else 0, 0.5, True, batches=2, sel=sel)
+    diff(got, want)
+
+
+@pytest.mark.skipif(not e2e.available("ref"), reason="oracle/_ref/ngm/ngm_ref not built")
+def test_single_end_sam_identical_to_ngm():
+    with tempfile.TemporaryDirectory(prefix="se_") as td:
+        d = Path(td)
+        e2e.write_inputs(d, ref_len=500_000, n_reads=1500, read_len=100, seed=99, indel_reads=0.15)
+        want = [ln for ln in e2e.run("ref", d, threads=2, extra=["-s", "0.5"]) if not ln.startswith("@")]
+        got, _ = oracle_sam(d, 100, 0, 0.5, False)
+    diff(got, want)
