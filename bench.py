@@ -63,6 +63,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cs", action="store_true", help="skip the candidate-search section (index build + k-mer vote on device)")
+    ap.add_argument("--no-pe", action="store_true", help="skip the paired-end section (needs the candidate-search section)")
     ap.add_argument("--sensitivity", type=float, default=0.5, help="CS sensitivity (NGM -s; its own default when not estimated)")
     return ap.parse_args()
 
@@ -573,6 +574,88 @@ def main():
                     del tab_h, weight_h, table_h, oix
                 except Exception as e:  # noqa: BLE001
                     cs_info["parity_sample"] = {"error": str(e)}
+            # ---- paired-end (BASELINE configs[2] shape, per-GPU shard): the same run with mates in rows 2f / 2f + 1 and
+            # ScoreBuffer::top1PE on the device (ngm_b200_dev_select_pairs) between scoring and alignment
+            if not args.no_pe:
+                try:
+                    from nextgenmap_b200.host.cuda_sw import PeParams
+                    pbatch = workload.make_reads(ref, n, L, qml, corridor, seed=20261018 + 2 + 16 * rank, sub_rate=args.sub_rate, indel_rate=args.indel_rate,
+                                                 paired=True)
+                    d_nt, d_pf = torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, dtype=torch.int32, device=dev)
+                    pep = PeParams(0.9, 0, 1000, 0, 0)
+
+                    def pe_select(total):
+                        check(lib.ngm_b200_dev_select_pairs(ctx, n, d_cb.data_ptr(), d_cpairs.data_ptr(), d_cscores.data_ptr(), total, d_best.data_ptr(),
+                                                            d_mapq.data_ptr(), d_nt.data_ptr(), d_pf.data_ptr(), st))
+
+                    def pe_pipeline_step():
+                        check(lib.ngm_b200_dev_set_reads(ctx, pbatch.reads.data_ptr(), n, qml, st))
+                        check(lib.ngm_b200_dev_cs_search(ctx, pbatch.reads.data_ptr(), n, qml, 0, d_cb.data_ptr(), d_cpairs.data_ptr(), d_cvotes.data_ptr(), cap, None, st))
+                        total = int(d_cb[n].item())
+                        if total > cap:
+                            raise RuntimeError(f"candidate buffer too small ({total} > {cap})")
+                        check(lib.ngm_b200_dev_score_pairs(ctx, MODE_LOCAL, total, d_cpairs.data_ptr(), d_cscores.data_ptr(), st))
+                        pe_select(total)
+                        check(lib.ngm_b200_dev_gather_winners_scored(ctx, n, d_cpairs.data_ptr(), d_cscores.data_ptr(), d_best.data_ptr(), d_wpairs.data_ptr(),
+                                                                     d_wscores.data_ptr(), st))
+                        d_cursor.zero_()
+                        check(lib.ngm_b200_dev_align_pairs_scored(ctx, MODE_LOCAL, n, d_wpairs.data_ptr(), d_wscores.data_ptr(), d_recs.data_ptr(),
+                                                                  d_strings.data_ptr(), str_cap, d_cursor.data_ptr(), st))
+                        return total
+
+                    check(lib.ngm_b200_pe_configure(ctx, C.byref(pep)))
+                    total_p = pe_pipeline_step()                         # first batch after configure: checked against the oracle below
+                    torch.cuda.synchronize()
+                    first = {"begin": d_cb.cpu().numpy(), "best": d_best.cpu().numpy(), "mapq": d_mapq.cpu().numpy(), "nt": d_nt.cpu().numpy(), "pf": d_pf.cpu().numpy()}
+                    sum1, cnt1 = sw.pe_insert_stats()
+                    deferred1 = sw.pe_deferred_fragments()
+                    wp = d_wpairs.view(torch.int64).view(n, 2)
+                    wflags = (wp[:, 1] >> 32) & 0xFFFFFFFF
+                    ok_pe = (((wp[:, 0] + (corridor >> 1)) - pbatch.true_pos).abs() <= corridor) & ((wflags & 1).bool() == pbatch.reverse) & ((wflags & 4) == 0)
+                    ms_sel = time_call(lambda: pe_select(total_p), reps=3)
+                    a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    barrier()
+                    a_.record()
+                    for _ in range(reps):
+                        pe_pipeline_step()
+                    b_.record()
+                    barrier()
+                    ms_pe = sharding.max_over_ranks(a_.elapsed_time(b_) / reps, dev)
+                    pe_info = {"workload": f"{n // 2} fragments x 2 x {L} bp per GPU, insert ~ N(400, 40), FR, same reference and index",
+                               "pipeline_step": "set_reads -> cs_search -> score all candidates -> top1PE (select_pairs) -> gather -> align+backtrace+CIGAR/MD",
+                               "candidates_per_read": total_p / n, "select_pairs_ms": ms_sel, "pipeline_ms": ms_pe, "pipeline_reads_per_s": world * n / (ms_pe * 1e-3),
+                               "proper_pair_fraction": float(((first["pf"] == 0) & (first["best"] >= 0)).mean()), "winner_at_true_locus": float(ok_pe.float().mean().item()),
+                               "mean_insert_size": sum1 / max(cnt1, 1), "pairs_accepted": cnt1 - 1,
+                               "fragments_decided_sequentially": deferred1}
+                    if rank == 0 and not args.no_cpu_baseline:
+                        try:
+                            from oracle import mapper_port
+                            n_pe = min(n, 20_000)
+                            e_pe = int(first["begin"][n_pe])
+                            pdt = np.dtype([("window_start", "<u8"), ("read_index", "<u4"), ("flags", "<u4")])
+                            # candidates and scores of the first batch: recompute them (the buffers were overwritten by the timed steps)
+                            check(lib.ngm_b200_dev_set_reads(ctx, pbatch.reads.data_ptr(), n, qml, st))
+                            check(lib.ngm_b200_dev_cs_search(ctx, pbatch.reads.data_ptr(), n, qml, 0, d_cb.data_ptr(), d_cpairs.data_ptr(), d_cvotes.data_ptr(), cap, None, st))
+                            check(lib.ngm_b200_dev_score_pairs(ctx, MODE_LOCAL, total_p, d_cpairs.data_ptr(), d_cscores.data_ptr(), st))
+                            torch.cuda.synchronize()
+                            hp = d_cpairs[:e_pe].cpu().numpy().view(pdt).reshape(-1)
+                            hs = d_cscores[:e_pe].cpu().numpy()
+                            lens = np.full(n_pe, L, np.int32)
+                            t0 = time.perf_counter()
+                            want = mapper_port.Selector().select_pairs(first["begin"][: n_pe + 1], hp["window_start"] + np.uint64(corridor >> 1), hs, lens)
+                            cpu_s = time.perf_counter() - t0
+                            has = want["best"] >= 0
+                            same = (np.array_equal(first["best"][:n_pe], want["best"]) and np.array_equal(first["mapq"][:n_pe], want["mapq"])
+                                    and np.array_equal(first["nt"][:n_pe][has], want["num_top"][has]) and np.array_equal(first["pf"][:n_pe], want["paired_fail"]))
+                            pe_info["parity_sample"] = {"reads_checked": n_pe, "identical_to_oracle": bool(same)}
+                            pe_info["cpu_baseline"] = {"value": n_pe / cpu_s, "unit": "reads/s", "cores": 1, "kind": "port",
+                                                       "sample": f"selection only (oracle/select_oracle.c) of {n_pe} reads with the device's scores"}
+                        except Exception as e:  # noqa: BLE001
+                            pe_info["parity_sample"] = {"error": str(e)}
+                    cs_info["paired_end"] = pe_info
+                    del pbatch
+                except Exception as e:  # noqa: BLE001
+                    cs_info["paired_end"] = {"error": str(e)}
             del d_cpairs, d_cvotes, d_cscores, d_cb
         except Exception as e:  # noqa: BLE001
             cs_info = {"error": str(e)}

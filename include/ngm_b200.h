@@ -279,6 +279,9 @@ typedef struct ngm_b200_pe_params {
 int ngm_b200_pe_configure(ngm_b200_ctx *ctx, const ngm_b200_pe_params *params);
 /* pairDistSum / pairDistCount after the batches selected so far (synchronises the device). */
 int ngm_b200_pe_insert_stats(ngm_b200_ctx *ctx, int64_t *dist_sum, int64_t *dist_count);
+/* Fragments of the last ngm_b200_dev_select_pairs call that met equal pair scores and were therefore decided one after the other
+ * (diagnostics; synchronises the device). */
+int64_t ngm_b200_pe_deferred_fragments(ngm_b200_ctx *ctx);
 /* What ScoreBuffer::DoRun does once both mates of a fragment are scored (ScoreBuffer.cpp:196-215): top1PE + CheckPairs (:365-502), or
  * top1SE (:228-277) for a mate whose partner has no candidate, under fast_pairing, and as the fallback when no combination has an
  * insert size inside the limits (both mates then carry NGMNames::PairedFail).  Rows 2f and 2f + 1 of the read batch given to

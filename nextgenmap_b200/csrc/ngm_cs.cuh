@@ -290,7 +290,7 @@ struct CsSmem {
 	static constexpr int T2 = 1 << T2_LOG;
 	static constexpr int SEENW = T2 > 2048 ? T2 : 2048;        // words of the "seen" bitmap (reused as per-slot first-hit array)
 	static constexpr size_t bytes = (size_t) (SEENW + kCsRepWords) * 4 + (size_t) T2 * 8 + (size_t) MAXH * 4 + (size_t) MAXK * 8 + ((size_t) MAXK + 4) * 4 +
-			(size_t) MAXK * 4 + (size_t) MAXK + 32;
+			(size_t) MAXK * 4 + (size_t) MAXK + 32 + ((size_t) MAXH / 32 + 2) * 2;
 };
 
 template <int T2_LOG, int MAXK, int MAXH>
@@ -311,6 +311,8 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 	uint32_t *kfs = bins + MAXH, *krs = kfs + MAXK, *kbase = krs + MAXK;      // kbase: MAXK + 4 entries
 	uint16_t *kfc = reinterpret_cast<uint16_t *>(kbase + MAXK + 4), *krc = kfc + MAXK;
 	uint8_t *s_read = reinterpret_cast<uint8_t *>(krc + MAXK);            // MAXK + 32 bytes >= stride (stride - k + 1 <= MAXK, k <= 14)
+	uint16_t *cstart = reinterpret_cast<uint16_t *>(s_read + MAXK + 32);  // k-mer that holds hit 32 c, for every chunk c of 32 hits
+	static_assert(MAXK % 2 == 0 && MAXH % 32 == 0, "alignment of cstart / whole chunks");
 	__shared__ uint32_t s_items_s[kCsMaxItems];
 	__shared__ uint16_t s_items_c[kCsMaxItems];
 	__shared__ uint32_t s_acc[kCsMaxAccepted];
@@ -391,6 +393,8 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 #pragma unroll
 	for (int q = 0; q < IPT; ++q) {
 		kbase[tid * IPT + q] = run;
+		if (run + mine[q] <= (uint32_t) MAXH)                   // (reads with more hits leave for the exact kernel below)
+			for (uint32_t ch = (run + 31u) >> 5; (ch << 5) < run + mine[q]; ++ch) cstart[ch] = (uint16_t) (tid * IPT + q);
 		run += mine[q];
 	}
 	if (tid == NT - 1) kbase[MAXK] = run;
@@ -450,32 +454,34 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 		}
 		bins[h] = tag;
 	};
-	constexpr int U = 9;
-	for (int j0 = warp; j0 < n_kmers; j0 += (NT / 32) * U) {
-		uint32_t loc[U];
+	// The hits are numbered in the reference's order (k-mer by k-mer, forward list then reverse list); a warp takes 32 consecutive
+	// hits whatever k-mers they belong to, so every lane carries a hit and no list has a tail.  U chunks in flight per warp.
+	constexpr int U = 8;
+	const uint32_t n_chunks = (n_hits + 31u) >> 5;
+	for (uint32_t c0 = warp; c0 < n_chunks; c0 += (NT / 32) * U) {
+		uint32_t loc[U], meta_j[U];
 #pragma unroll
 		for (int u = 0; u < U; ++u) {
-			const int j = j0 + u * (NT / 32);
+			const uint32_t ch = c0 + u * (NT / 32);
+			const uint32_t h = (ch << 5) + lane;
 			loc[u] = 0;
-			if (j < n_kmers) {
-				const uint32_t fc = kfc[j], tot = fc + krc[j];
-				if ((uint32_t) lane < tot) loc[u] = __ldg(P.table + ((uint32_t) lane < fc ? kfs[j] + lane : krs[j] + (lane - fc)));
+			meta_j[u] = 0xFFFFFFFFu;
+			if (ch < n_chunks && h < n_hits) {
+				uint32_t j = cstart[ch];
+				while (h >= kbase[j + 1]) ++j;                      // at most a few k-mers per chunk
+				const uint32_t o = h - kbase[j], fc = kfc[j];
+				const bool rv = o >= fc;
+				loc[u] = __ldg(P.table + (rv ? krs[j] + (o - fc) : kfs[j] + o));
+				meta_j[u] = j | (rv ? 0x80000000u : 0u);
 			}
 		}
 #pragma unroll
 		for (int u = 0; u < U; ++u) {
-			const int j = j0 + u * (NT / 32);
-			if (j < n_kmers) {
-				const uint32_t fc = kfc[j], tot = fc + krc[j];
-				const uint32_t corr_f = (uint32_t) j, corr_r = (uint32_t) (len - (j + k));
-				first_sweep((uint32_t) lane < tot, loc[u], (uint32_t) lane >= fc, (uint32_t) lane >= fc ? corr_r : corr_f, kbase[j] + lane);
-				if (tot > 32u) {                                   // warp-uniform: the part of the two lists beyond 32 hits
-					for (uint32_t l = 32 + lane; l < tot; l += 32) {
-						const uint32_t w = __ldg(P.table + (l < fc ? kfs[j] + l : krs[j] + (l - fc)));
-						first_sweep(true, w, l >= fc, l >= fc ? corr_r : corr_f, kbase[j] + l);
-					}
-				}
-			}
+			const uint32_t ch = c0 + u * (NT / 32);
+			const uint32_t m = meta_j[u];
+			const bool rv = (m >> 31) != 0;
+			const uint32_t j = m & 0x7FFFFFFFu;
+			first_sweep(m != 0xFFFFFFFFu, loc[u], rv, rv ? (uint32_t) (len - ((int) j + k)) : j, (ch << 5) + lane);
 		}
 	}
 	__syncthreads();

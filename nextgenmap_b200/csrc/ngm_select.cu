@@ -12,7 +12,9 @@
 // reference's own result depends on how reads were dealt to threads.
 #include <cub/cub.cuh>
 
+#include <algorithm>
 #include <climits>
+#include <cstdlib>
 #include <cstdint>
 
 #include "ngm_ctx.h"
@@ -307,13 +309,49 @@ struct Sum2 {
 	__device__ __forceinline__ longlong2 operator()(const longlong2 &x, const longlong2 &y) const { return make_longlong2(x.x + y.x, x.y + y.y); }
 };
 
-// The deferred fragments in input order; prefix[f] = inclusive sums of the contributions of the fragments decided in parallel.
+// One relaxation step over the deferred fragments, all at once: every deferred fragment is decided with the mean that the CURRENT
+// contributions of all earlier fragments give (prefix = inclusive scan of contrib, which holds the deferred fragments' previous
+// decisions, (0, 0) at first).  The dependency is strictly from earlier to later fragments, so a step that changes nothing has reached
+// the sequential result; the mean moves by a fraction of a base per pair, so that is the case after two or three steps.
+__global__ void relax_deferred_kernel(const int *__restrict__ list, const int *__restrict__ n_list, const int *__restrict__ cand_begin,
+		const ngm_b200_pair *__restrict__ pairs, const uint16_t *__restrict__ rlen, const PeDev P, const SelItem *__restrict__ items,
+		const longlong2 *__restrict__ prefix, longlong2 *__restrict__ contrib, int *__restrict__ best_pair, int *__restrict__ mapq,
+		int *__restrict__ num_top, int *__restrict__ pflags, const long long *__restrict__ state, int *__restrict__ changed) {
+	const int d = blockIdx.x * blockDim.x + threadIdx.x;
+	if (d >= *n_list) return;
+	const int f = list[d];
+	const int a = 2 * f, b = a + 1;
+	const int ba = cand_begin[a], bb = cand_begin[b], eb = cand_begin[b + 1];
+	const longlong2 incl = prefix[f], own = contrib[f];
+	const long long sum = state[0] + incl.x - own.x, cnt = state[1] + incl.y - own.y;
+	SelOut oa, ob;
+	int pf = 0, distance = 0;
+	sel_top1_pe(items + bb, eb - bb, (int) rlen[b], items + ba, bb - ba, (int) rlen[a], pairs, P, true, (int) (sum / cnt), ob, oa, pf, distance);
+	const longlong2 now = (!pf && ob.best >= 0) ? make_longlong2(distance, 1) : make_longlong2(0, 0);
+	if (now.x != own.x || now.y != own.y) {
+		contrib[f] = now;
+		*changed = 1;
+	}
+	sel_store(a, oa, pf, best_pair, mapq, num_top, pflags);
+	sel_store(b, ob, pf, best_pair, mapq, num_top, pflags);
+}
+
+// pairDistSum / pairDistCount after the batch, when the last relaxation step changed nothing (prefix is then exact).
+__global__ void commit_state_kernel(int n_frag, const longlong2 *__restrict__ prefix, const int *__restrict__ changed, long long *__restrict__ state) {
+	if (blockIdx.x != 0 || threadIdx.x != 0 || *changed || n_frag <= 0) return;
+	const longlong2 all = prefix[n_frag - 1];
+	state[0] += all.x;
+	state[1] += all.y;
+}
+
+// Safety net, runs only if the relaxation has not settled (`changed` still set): the deferred fragments in input order, one after the
+// other.  prefix0[f] = inclusive sums of the contributions of the fragments decided in parallel (deferred ones count (0, 0) there).
 // state[0..1] = pairDistSum, pairDistCount carried between batches.
 __global__ void resolve_deferred_kernel(int n_frag, const int *__restrict__ list, const int *__restrict__ n_list, const int *__restrict__ cand_begin,
 		const ngm_b200_pair *__restrict__ pairs, const uint16_t *__restrict__ rlen, const PeDev P, const SelItem *__restrict__ items,
 		const longlong2 *__restrict__ prefix, int *__restrict__ best_pair, int *__restrict__ mapq, int *__restrict__ num_top,
-		int *__restrict__ pflags, long long *__restrict__ state) {
-	if (blockIdx.x != 0 || threadIdx.x != 0) return;
+		int *__restrict__ pflags, long long *__restrict__ state, const int *__restrict__ changed) {
+	if (blockIdx.x != 0 || threadIdx.x != 0 || !*changed) return;
 	long long extra_sum = 0, extra_cnt = 0;
 	const int n = *n_list;
 	for (int d = 0; d < n; ++d) {
@@ -341,7 +379,7 @@ __global__ void resolve_deferred_kernel(int n_frag, const int *__restrict__ list
 
 struct PeState {
 	ngm_b200_pe_params hp;
-	DevBuf d_items, d_contrib, d_prefix, d_deferred, d_list, d_nlist, d_state, d_tmp;
+	DevBuf d_items, d_contrib, d_prefix, d_prefix0, d_deferred, d_list, d_nlist, d_state, d_tmp, d_changed;
 	bool have_state = false;
 };
 
@@ -350,6 +388,8 @@ void pe_release(PeState *pe) {
 	pe->d_items.release();
 	pe->d_contrib.release();
 	pe->d_prefix.release();
+	pe->d_prefix0.release();
+	pe->d_changed.release();
 	pe->d_deferred.release();
 	pe->d_list.release();
 	pe->d_nlist.release();
@@ -387,6 +427,15 @@ int ngm_b200_pe_insert_stats(ngm_b200_ctx *c, int64_t *dist_sum, int64_t *dist_c
 	return NGM_B200_OK;
 }
 
+int64_t ngm_b200_pe_deferred_fragments(ngm_b200_ctx *c) {
+	if (c == nullptr || c->pe == nullptr || c->pe->d_nlist.p == nullptr) return fail(NGM_B200_ESTATE, "no paired selection yet");
+	CU(cudaSetDevice(c->device));
+	CU(cudaDeviceSynchronize());
+	int n = 0;
+	CU(cudaMemcpy(&n, c->pe->d_nlist.p, 4, cudaMemcpyDeviceToHost));
+	return n;
+}
+
 int ngm_b200_dev_select_pairs(ngm_b200_ctx *c, int n_reads, const void *d_cand_begin, const void *d_pairs, const void *d_scores, uint32_t n_pairs,
 		void *d_best_pair, void *d_mapq, void *d_num_top, void *d_pair_fail, void *stream) {
 	if (c == nullptr || d_cand_begin == nullptr || d_pairs == nullptr || d_scores == nullptr || d_best_pair == nullptr || d_mapq == nullptr ||
@@ -403,6 +452,8 @@ int ngm_b200_dev_select_pairs(ngm_b200_ctx *c, int n_reads, const void *d_cand_b
 	CU(pe->d_items.ensure(std::max<size_t>(n_pairs, 1) * sizeof(SelItem)));
 	CU(pe->d_contrib.ensure((size_t) n_frag * sizeof(longlong2)));
 	CU(pe->d_prefix.ensure((size_t) n_frag * sizeof(longlong2)));
+	CU(pe->d_prefix0.ensure((size_t) n_frag * sizeof(longlong2)));
+	CU(pe->d_changed.ensure(4));
 	CU(pe->d_deferred.ensure((size_t) n_frag));
 	CU(pe->d_list.ensure((size_t) n_frag * 4));
 	CU(pe->d_nlist.ensure(4));
@@ -424,12 +475,30 @@ int ngm_b200_dev_select_pairs(ngm_b200_ctx *c, int n_reads, const void *d_cand_b
 	CU(cub::DeviceScan::InclusiveScan(nullptr, t1, pe->d_contrib.as<longlong2>(), pe->d_prefix.as<longlong2>(), Sum2(), n_frag, st));
 	CU(cub::DeviceSelect::Flagged(nullptr, t2, ids, pe->d_deferred.as<uint8_t>(), pe->d_list.as<int>(), pe->d_nlist.as<int>(), n_frag, st));
 	CU(pe->d_tmp.ensure(std::max(t1, t2)));
-	CU(cub::DeviceScan::InclusiveScan(pe->d_tmp.p, t1, pe->d_contrib.as<longlong2>(), pe->d_prefix.as<longlong2>(), Sum2(), n_frag, st));
+	CU(cub::DeviceScan::InclusiveScan(pe->d_tmp.p, t1, pe->d_contrib.as<longlong2>(), pe->d_prefix0.as<longlong2>(), Sum2(), n_frag, st));
 	CU(cub::DeviceSelect::Flagged(pe->d_tmp.p, t2, ids, pe->d_deferred.as<uint8_t>(), pe->d_list.as<int>(), pe->d_nlist.as<int>(), n_frag, st));
+	int n_deferred_bound = n_frag;                              // the count stays on the device: size the grid for the worst case
+	int kRelaxSteps = 4;
+	if (const char *e = getenv("NGM_B200_PE_RELAX_STEPS")) kRelaxSteps = std::max(0, std::min(16, atoi(e)));      // testing hook: 0 = sequential replay only
+	const longlong2 *last_prefix = pe->d_prefix0.as<longlong2>();
+	CU(cudaMemsetAsync(pe->d_changed.p, kRelaxSteps == 0 ? 1 : 0, 4, st));
+	for (int it = 0; it < kRelaxSteps; ++it) {
+		const longlong2 *prefix = it == 0 ? pe->d_prefix0.as<longlong2>() : pe->d_prefix.as<longlong2>();
+		if (it > 0) CU(cub::DeviceScan::InclusiveScan(pe->d_tmp.p, t1, pe->d_contrib.as<longlong2>(), pe->d_prefix.as<longlong2>(), Sum2(), n_frag, st));
+		last_prefix = prefix;
+		CU(cudaMemsetAsync(pe->d_changed.p, 0, 4, st));
+		relax_deferred_kernel<<<(n_deferred_bound + 127) / 128, 128, 0, st>>>(pe->d_list.as<int>(), pe->d_nlist.as<int>(), begin, pairs,
+				c->d_rrlen.as<uint16_t>(), P, pe->d_items.as<SelItem>(), prefix, pe->d_contrib.as<longlong2>(), static_cast<int *>(d_best_pair),
+				static_cast<int *>(d_mapq), static_cast<int *>(d_num_top), static_cast<int *>(d_pair_fail), pe->d_state.as<long long>(),
+				pe->d_changed.as<int>());
+	}
+	// the last step changed nothing: its prefix is exact; otherwise replay the deferred fragments one by one (contributions of the
+	// fragments decided in parallel: prefix0)
 	resolve_deferred_kernel<<<1, 32, 0, st>>>(n_frag, pe->d_list.as<int>(), pe->d_nlist.as<int>(), begin, pairs, c->d_rrlen.as<uint16_t>(), P,
-			pe->d_items.as<SelItem>(), pe->d_prefix.as<longlong2>(), static_cast<int *>(d_best_pair), static_cast<int *>(d_mapq),
-			static_cast<int *>(d_num_top), static_cast<int *>(d_pair_fail), pe->d_state.as<long long>());
-	c->launches += 4;
+			pe->d_items.as<SelItem>(), pe->d_prefix0.as<longlong2>(), static_cast<int *>(d_best_pair), static_cast<int *>(d_mapq),
+			static_cast<int *>(d_num_top), static_cast<int *>(d_pair_fail), pe->d_state.as<long long>(), pe->d_changed.as<int>());
+	commit_state_kernel<<<1, 32, 0, st>>>(n_frag, last_prefix, pe->d_changed.as<int>(), pe->d_state.as<long long>());
+	c->launches += 3 + 2 * kRelaxSteps + 2;
 	CU(cudaGetLastError());
 	return n_reads;
 }

@@ -126,6 +126,8 @@ def load_library() -> C.CDLL:
     lib.ngm_b200_cs_exact_reads.argtypes = [C.c_void_p]
     lib.ngm_b200_pe_configure.argtypes = [C.c_void_p, C.POINTER(PeParams)]
     lib.ngm_b200_pe_insert_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.ngm_b200_pe_deferred_fragments.argtypes = [C.c_void_p]
+    lib.ngm_b200_pe_deferred_fragments.restype = C.c_int64
     lib.ngm_b200_dev_select_pairs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_void_p]
     lib.ngm_b200_cs_estimate_sensitivity.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
@@ -357,6 +359,9 @@ class CudaSW:
         s, n = C.c_int64(0), C.c_int64(0)
         self._check(self.lib.ngm_b200_pe_insert_stats(self.ctx, C.byref(s), C.byref(n)))
         return int(s.value), int(n.value)
+
+    def pe_deferred_fragments(self) -> int:
+        return int(self.lib.ngm_b200_pe_deferred_fragments(self.ctx))
 
     def cs_exact_reads(self) -> int:
         return int(self.lib.ngm_b200_cs_exact_reads(self.ctx))

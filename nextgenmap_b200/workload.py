@@ -76,8 +76,12 @@ def _base_codes(ref: Reference, pos: torch.Tensor) -> torch.Tensor:
 
 
 def make_reads(ref: Reference, n: int, read_len: int, qml: int, corridor: int, seed: int, sub_rate: float = 0.01,
-               indel_rate: float = 0.0005, decoy_fraction: float = 0.5, chunk: int = 1 << 20) -> ReadBatch:
+               indel_rate: float = 0.0005, decoy_fraction: float = 0.5, chunk: int = 1 << 20, paired: bool = False, insert_mean: float = 400.0,
+               insert_sd: float = 40.0) -> ReadBatch:
+    """paired: rows 2f, 2f + 1 are the mates of fragment f (BASELINE configs[2]; SURVEY 8d: insert ~ N(400, 40), FR orientation, the
+    fragment on either strand); true_pos / reverse describe each mate."""
     dev = ref.packed.device
+    assert not paired or (n % 2 == 0 and chunk % 2 == 0)
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
     n_contigs = len(ref.contig_start)
@@ -93,6 +97,17 @@ def make_reads(ref: Reference, n: int, read_len: int, qml: int, corridor: int, s
         contig = torch.randint(0, n_contigs, (m,), device=dev, generator=g)
         local = torch.randint(0, ref.contig_len - read_len - 8, (m,), device=dev, generator=g)
         pos = cstart[contig] + local
+        pair_rev = None
+        if paired:
+            fcontig = contig[0::2]
+            ins = (torch.randn(m // 2, device=dev, generator=g) * insert_sd + insert_mean).long().clamp(min=read_len + 5, max=4 * int(insert_mean))
+            flocal = torch.minimum(local[0::2], ref.contig_len - 8 - ins)
+            fpos = cstart[fcontig] + flocal
+            flip = torch.rand(m // 2, device=dev, generator=g) < 0.5          # fragment from the minus strand: the mates swap ends
+            mate = torch.arange(m, device=dev) & 1
+            left_end = mate == flip.repeat_interleave(2).long()
+            pos = torch.where(left_end, fpos.repeat_interleave(2), (fpos + ins - read_len).repeat_interleave(2))
+            pair_rev = ~left_end
         # at most one 1-3 bp indel per read (0.05 % per base)
         ev = torch.rand(m, device=dev, generator=g) < p_event
         is_ins = torch.rand(m, device=dev, generator=g) < 0.5
@@ -111,6 +126,8 @@ def make_reads(ref: Reference, n: int, read_len: int, qml: int, corridor: int, s
         step = torch.randint(1, 4, (m, read_len), dtype=torch.uint8, device=dev, generator=g)
         codes = torch.where(sub & (codes < 4), (codes + step) & 3, codes)
         rev = torch.rand(m, device=dev, generator=g) < 0.5
+        if pair_rev is not None:
+            rev = pair_rev
         # minus strand: reverse complement; in NGM's code space A0<->T1, G2<->C3 is code ^ 1
         rc = torch.flip(torch.where(codes < 4, codes ^ 1, codes), dims=[1])
         codes = torch.where(rev[:, None], rc, codes)

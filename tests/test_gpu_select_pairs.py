@@ -40,8 +40,15 @@ def make_case(seed, n_frag, max_cands, score_values):
     (5, 5, [-1.0, 0.0, 300.0, 1000.0], {"min_insert_size": 200, "max_insert_size": 450}),
     (6, 3, [1000.0], {"pair_score_cutoff": 0.5, "max_insert_size": 0}),
 ])
-def test_select_pairs_matches_oracle(seed, max_cands, values, kw):
+@pytest.mark.parametrize("relax_steps", [None, "0", "1"])
+def test_select_pairs_matches_oracle(seed, max_cands, values, kw, relax_steps, monkeypatch):
+    """relax_steps: the library's testing hook -- None = default (parallel relaxation of the fragments that need the insert-size mean),
+    "0" = only the sequential replay (the safety net), "1" = one relaxation step, then the safety net if that step changed anything."""
     import torch
+    if relax_steps is not None:
+        if seed > 3:
+            pytest.skip("hook variants on three cases")
+        monkeypatch.setenv("NGM_B200_PE_RELAX_STEPS", relax_steps)
     from nextgenmap_b200.host import CudaSW
     from nextgenmap_b200.host.cuda_sw import PAIR
     qml, cor = 102, 20
