@@ -370,6 +370,8 @@ int ngm_b200_dev_cs_search(ngm_b200_ctx *c, const void *d_ascii_reads, int n_rea
 		auto launch = [&](auto kern, size_t smem) -> cudaError_t {
 			cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 			if (e != cudaSuccess) return e;
+			e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+			if (e != cudaSuccess) return e;
 			kern<<<n_reads, 256, smem, st>>>(P, reads, n_reads, stride, meta, heap, capacity, cursor, cs->d_slow_list.as<uint32_t>(),
 					cs->d_slow_count.as<uint32_t>(), max_hit);
 			return cudaGetLastError();
@@ -377,11 +379,14 @@ int ngm_b200_dev_cs_search(ngm_b200_ctx *c, const void *d_ascii_reads, int n_rea
 		const double mean_list = (double) cs->table_len / (double) cs->n_prefix;
 		const double expect = (double) std::max(1, stride - cs->k + 1) * 2.0 * std::max(mean_list, 0.5);      // hits per read
 		const bool bins_fit = ((c->concat_len + 1024) >> cs->bin_shift) < (1ull << 30);      // two flag bits ride on every stored bin
-		if (!bins_fit) {
+		const bool scan_fits = (uint64_t) std::max(1, stride - cs->k + 1) * (uint64_t) P.max_kfreq < (1ull << 20);      // packed scan: hits in 20 bits
+		if (!bins_fit || !scan_fits) {
 			cs->exact_all = true;                                  // (bin_size 0/1 on > 1 Gbp: sequential kernel only)
 			exact_only_fallback = true;
 		} else if (stride - cs->k + 1 <= 256 && expect <= 4250.0) {
-			CU(launch(cs_search_kernel<11, 256, 4608>, CsSmem<11, 256, 4608>::bytes));
+			CU(launch(cs_search_kernel<10, 256, 4608>, CsSmem<10, 256, 4608>::bytes));
+		} else if (stride - cs->k + 1 <= 256 && expect <= 7700.0) {
+			CU(launch(cs_search_kernel<11, 256, 8192, 4096>, CsSmem<11, 256, 8192, 4096>::bytes));      // 250 bp on 3 Gbp: 3 blocks / SM
 		} else if (stride - cs->k + 1 <= 512 && expect <= 14000.0) {
 			CU(launch(cs_search_kernel<12, 512, 16384>, CsSmem<12, 512, 16384>::bytes));
 		} else {

@@ -23,6 +23,11 @@
 
 #include "ngm_common.cuh"
 
+// index / position-table loads of the search kernels: random, no reuse inside a block
+#ifndef NGM_CS_LD
+#define NGM_CS_LD(p) __ldg(p)          /* ld.global.cg measured 16 % slower: the 18 % L1 hits are worth keeping */
+#endif
+
 namespace ngm {
 
 struct CsDev {
@@ -251,8 +256,8 @@ struct CsLists {
 
 __device__ __forceinline__ bool cs_lookup(const CsDev &P, uint32_t prefix, CsLists &L) {      // GetRefEntry, PrefixTable.cpp:750-817
 	const uint32_t rcp = cs_revcomp(prefix, P.k);
-	const uint32_t a0 = __ldg(P.tabu + prefix), a1 = __ldg(P.tabu + prefix + 1);
-	const uint32_t b0 = __ldg(P.tabu + rcp), b1 = __ldg(P.tabu + rcp + 1);
+	const uint32_t a0 = NGM_CS_LD(P.tabu + prefix), a1 = NGM_CS_LD(P.tabu + prefix + 1);
+	const uint32_t b0 = NGM_CS_LD(P.tabu + rcp), b1 = NGM_CS_LD(P.tabu + rcp + 1);
 	L.fs = a0 & 0x7FFFFFFFu;
 	L.fc = (a0 >> 31) ? (a1 & 0x7FFFFFFFu) - L.fs : 0u;
 	L.rs = b0 & 0x7FFFFFFFu;
@@ -285,15 +290,16 @@ constexpr int kCsMaxMulti = 256;                               // (entry, strand
 constexpr int kCsQueue = 512;                                  // hits per read that find their bit set (repeats + false positives)
 constexpr uint32_t kHitInserted = 0x80000000u, kHitRev = 0x40000000u, kHitBin = 0x3FFFFFFFu;
 
-template <int T2_LOG, int MAXK, int MAXH>
+template <int T2_LOG, int MAXK, int MAXH, int SEENW_ = 0>
 struct CsSmem {
 	static constexpr int T2 = 1 << T2_LOG;
-	static constexpr int SEENW = T2 > 2048 ? T2 : 2048;        // words of the "seen" bitmap (reused as per-slot first-hit array)
+	static constexpr int SEENW = SEENW_ ? SEENW_ : (T2 > 2048 ? T2 : 2048);        // words of the "seen" bitmap (reused as per-slot first-hit array, >= T2)
+	static_assert(SEENW >= T2, "the first-hit array of path J lives in the bitmap");
 	static constexpr size_t bytes = (size_t) (SEENW + kCsRepWords) * 4 + (size_t) T2 * 8 + (size_t) MAXH * 4 + (size_t) MAXK * 8 + ((size_t) MAXK + 4) * 4 +
-			(size_t) MAXK * 4 + (size_t) MAXK + 32 + ((size_t) MAXH / 32 + 2) * 2;
+			(size_t) MAXK * 4 + (size_t) MAXK + 32 + ((size_t) MAXH / 32 + 2) * 2 + ((size_t) MAXH / 32 + 1) * 4 + (size_t) MAXK * 2;
 };
 
-template <int T2_LOG, int MAXK, int MAXH>
+template <int T2_LOG, int MAXK, int MAXH, int SEENW_ = 0>
 __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uint8_t *__restrict__ reads, int n_reads, int stride,
 		CsMeta *__restrict__ meta, CsCand *__restrict__ heap, uint32_t heap_cap, uint32_t *__restrict__ cursor, uint32_t *__restrict__ slow_list,
 		uint32_t *__restrict__ slow_count, float *__restrict__ max_hit) {
@@ -304,23 +310,29 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 	constexpr int IPT = MAXK / NT;                             // list descriptors per thread in the scan
 	static_assert(MAXK % NT == 0, "MAXK must be a multiple of the block size");
 	extern __shared__ uint32_t s_dyn[];
-	constexpr int SEENW = CsSmem<T2_LOG, MAXK, MAXH>::SEENW;
+	constexpr int SEENW = CsSmem<T2_LOG, MAXK, MAXH, SEENW_>::SEENW;
 	constexpr int SEEN_SHIFT = SEENW == 2048 ? 16 : (SEENW == 4096 ? 15 : 14);      // 32 - log2(32 x SEENW)
 	static_assert(SEENW == 2048 || SEENW == 4096 || SEENW == 8192, "seen bitmap size");
 	uint32_t *seen = s_dyn, *rep = seen + SEENW, *keys = rep + kCsRepWords, *cnts = keys + T2, *bins = cnts + T2;
 	uint32_t *kfs = bins + MAXH, *krs = kfs + MAXK, *kbase = krs + MAXK;      // kbase: MAXK + 4 entries
 	uint16_t *kfc = reinterpret_cast<uint16_t *>(kbase + MAXK + 4), *krc = kfc + MAXK;
 	uint8_t *s_read = reinterpret_cast<uint8_t *>(krc + MAXK);            // MAXK + 32 bytes >= stride (stride - k + 1 <= MAXK, k <= 14)
-	uint16_t *cstart = reinterpret_cast<uint16_t *>(s_read + MAXK + 32);  // k-mer that holds hit 32 c, for every chunk c of 32 hits
-	static_assert(MAXK % 2 == 0 && MAXH % 32 == 0, "alignment of cstart / whole chunks");
-	__shared__ uint32_t s_items_s[kCsMaxItems];
-	__shared__ uint16_t s_items_c[kCsMaxItems];
-	__shared__ uint32_t s_acc[kCsMaxAccepted];
+	// hit -> k-mer map of sweep B: per chunk c of 32 hits, rbase[c] = rank (among the k-mers with hits) of the k-mer that holds hit 32 c
+	// and bstart[c] = the hits of the chunk that begin a k-mer (bit 0 left out: that is rbase's); nzmap[rank] = k-mer
+	uint16_t *rbase = reinterpret_cast<uint16_t *>(s_read + MAXK + 32);
+	uint32_t *bstart = reinterpret_cast<uint32_t *>(rbase + (MAXH / 32 + 2));
+	uint16_t *nzmap = reinterpret_cast<uint16_t *>(bstart + (MAXH / 32 + 1));
+	static_assert(MAXK % 4 == 0 && MAXH % 64 == 0 && MAXK < 4096 && MAXH < (1 << 20), "alignment of the chunk maps; packing of the scan");
+	// dead while the "seen" bitmap is in use (sweep B), needed only from phase D on: they live in the bitmap's words
+	uint32_t *s_items_s = seen;                                           // kCsMaxItems words
+	uint16_t *s_items_c = reinterpret_cast<uint16_t *>(seen + kCsMaxItems);      // kCsMaxItems halves
+	uint32_t *s_acc = seen + kCsMaxItems + kCsMaxItems / 2;               // kCsMaxAccepted words
+	uint32_t *s_items_t = s_acc + kCsMaxAccepted;                         // kCsMaxItems words
+	static_assert(2 * kCsMaxItems + kCsMaxItems / 2 + kCsMaxAccepted <= SEENW, "phase D/E scratch must fit into the seen bitmap");
 	__shared__ uint32_t s_warp[NT / 32];
 	__shared__ int s_len;
-	__shared__ uint32_t s_queue[kCsQueue];
-	uint32_t *s_items_t = s_queue;                             // the queue is dead by the time the order is worked out
-	static_assert(kCsQueue >= kCsMaxItems, "items reuse the queue");
+	__shared__ uint16_t s_queue[kCsQueue];                     // hit numbers (< MAXH)
+	static_assert(MAXH <= 65536, "queue entries are 16 bits wide");
 	__shared__ uint16_t s_multi[kCsMaxMulti];
 	__shared__ uint32_t s_max, s_maxm, s_slow, s_nmulti, s_nacc, s_ncand, s_nitems, s_nord, s_nq;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -333,6 +345,7 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 	{
 		uint4 *z4 = reinterpret_cast<uint4 *>(seen);               // both bitmaps
 		for (int i = tid; i < (SEENW + kCsRepWords) / 4; i += NT) z4[i] = make_uint4(0, 0, 0, 0);
+		for (int i = tid; i < MAXH / 32 + 1; i += NT) bstart[i] = 0;
 		uint4 *k4 = reinterpret_cast<uint4 *>(keys), *c4 = reinterpret_cast<uint4 *>(cnts);
 		for (int i = tid; i < T2 / 4; i += NT) {
 			k4[i] = make_uint4(kCsEmpty, kCsEmpty, kCsEmpty, kCsEmpty);
@@ -373,7 +386,7 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 		krs[o] = rs;
 		kfc[o] = (uint16_t) fc;
 		krc[o] = (uint16_t) rc;
-		mine[q] = fc + rc;
+		mine[q] = (fc + rc) | ((fc + rc) ? (1u << 20) : 0u);      // hits in bits 0..19, "has hits" counted in bits 20..31
 	}
 	uint32_t tsum = 0;
 #pragma unroll
@@ -392,12 +405,16 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 	uint32_t run = wbase + incl - tsum;
 #pragma unroll
 	for (int q = 0; q < IPT; ++q) {
-		kbase[tid * IPT + q] = run;
-		if (run + mine[q] <= (uint32_t) MAXH)                   // (reads with more hits leave for the exact kernel below)
-			for (uint32_t ch = (run + 31u) >> 5; (ch << 5) < run + mine[q]; ++ch) cstart[ch] = (uint16_t) (tid * IPT + q);
+		const uint32_t start = run & 0xFFFFFu, cnt = mine[q] & 0xFFFFFu, rank = run >> 20;
+		kbase[tid * IPT + q] = start;
+		if (cnt && start + cnt <= (uint32_t) MAXH) {            // (reads with more hits leave for the exact kernel below)
+			nzmap[rank] = (uint16_t) (tid * IPT + q);
+			if (start & 31u) atomicOr(&bstart[start >> 5], 1u << (start & 31u));
+			for (uint32_t ch = (start + 31u) >> 5; (ch << 5) < start + cnt; ++ch) rbase[ch] = (uint16_t) rank;
+		}
 		run += mine[q];
 	}
-	if (tid == NT - 1) kbase[MAXK] = run;
+	if (tid == NT - 1) kbase[MAXK] = run & 0xFFFFFu;
 	__syncthreads();
 	const uint32_t n_hits = kbase[MAXK];
 	auto to_exact = [&](int reason) {
@@ -436,8 +453,9 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 		word = hb >> 5;
 		bit = 1u << (hb & 31);
 	};
-	auto first_sweep = [&](bool valid, uint32_t loc, bool rev, uint32_t corr, uint32_t h) {
-		if (!valid) return;
+	// -> true if the hit found its bit set (to be queued for the exact table)
+	auto first_sweep = [&](bool valid, uint32_t loc, bool rev, uint32_t corr, uint32_t h) -> bool {
+		if (!valid) return false;
 		if (loc < corr) {                                      // the reference's 64-bit wrap-around: exact kernel
 			s_slow = 1;
 			loc = corr;
@@ -446,18 +464,16 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 		uint32_t word, bit;
 		hash_bit(bin, word, bit);
 		const uint32_t old = atomicOr(&seen[word], bit);
-		uint32_t tag = bin | (rev ? kHitRev : 0u);
-		if (old & bit) {                                       // seen before (or a colliding bin): to be counted exactly
-			tag |= kHitInserted;
-			const uint32_t q = atomicAdd(&s_nq, 1u);
-			if (q < kCsQueue) s_queue[q] = h;
-		}
-		bins[h] = tag;
+		const bool again = (old & bit) != 0;                   // seen before (or a colliding bin): to be counted exactly
+		bins[h] = bin | (rev ? kHitRev : 0u) | (again ? kHitInserted : 0u);
+		return again;
 	};
 	// The hits are numbered in the reference's order (k-mer by k-mer, forward list then reverse list); a warp takes 32 consecutive
-	// hits whatever k-mers they belong to, so every lane carries a hit and no list has a tail.  U chunks in flight per warp.
+	// hits whatever k-mers they belong to, so every lane carries a hit and no list has a tail.  U chunks in flight per warp; the
+	// hits of a batch that have to be queued take one slot reservation per warp (the order inside the queue does not matter).
 	constexpr int U = 8;
 	const uint32_t n_chunks = (n_hits + 31u) >> 5;
+	const uint32_t lane_le = (2u << lane) - 1u;
 	for (uint32_t c0 = warp; c0 < n_chunks; c0 += (NT / 32) * U) {
 		uint32_t loc[U], meta_j[U];
 #pragma unroll
@@ -466,22 +482,41 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 			const uint32_t h = (ch << 5) + lane;
 			loc[u] = 0;
 			meta_j[u] = 0xFFFFFFFFu;
-			if (ch < n_chunks && h < n_hits) {
-				uint32_t j = cstart[ch];
-				while (h >= kbase[j + 1]) ++j;                      // at most a few k-mers per chunk
+			if (h < n_hits) {                                       // implies ch < n_chunks
+				const uint32_t j = nzmap[rbase[ch] + __popc(bstart[ch] & lane_le)];
 				const uint32_t o = h - kbase[j], fc = kfc[j];
 				const bool rv = o >= fc;
-				loc[u] = __ldg(P.table + (rv ? krs[j] + (o - fc) : kfs[j] + o));
+				loc[u] = NGM_CS_LD(P.table + (rv ? krs[j] + (o - fc) : kfs[j] + o));
 				meta_j[u] = j | (rv ? 0x80000000u : 0u);
 			}
 		}
+		uint32_t again = 0;
 #pragma unroll
 		for (int u = 0; u < U; ++u) {
 			const uint32_t ch = c0 + u * (NT / 32);
 			const uint32_t m = meta_j[u];
 			const bool rv = (m >> 31) != 0;
 			const uint32_t j = m & 0x7FFFFFFFu;
-			first_sweep(m != 0xFFFFFFFFu, loc[u], rv, rv ? (uint32_t) (len - ((int) j + k)) : j, (ch << 5) + lane);
+			if (first_sweep(m != 0xFFFFFFFFu, loc[u], rv, rv ? (uint32_t) (len - ((int) j + k)) : j, (ch << 5) + lane)) again |= 1u << u;
+		}
+		if (__any_sync(0xffffffffu, again != 0)) {
+			const uint32_t mine_q = __popc(again);
+			uint32_t incl_q = mine_q;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint32_t v = __shfl_up_sync(0xffffffffu, incl_q, d);
+				if (lane >= d) incl_q += v;
+			}
+			uint32_t base_q = 0;
+			if (lane == 31) base_q = atomicAdd(&s_nq, incl_q);
+			base_q = __shfl_sync(0xffffffffu, base_q, 31);
+			uint32_t at = base_q + incl_q - mine_q;
+			while (again) {
+				const int u = __ffs(again) - 1;
+				again &= again - 1;
+				if (at < (uint32_t) kCsQueue) s_queue[at] = (uint16_t) (((c0 + u * (NT / 32)) << 5) + lane);
+				++at;
+			}
 		}
 	}
 	__syncthreads();
@@ -493,9 +528,12 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 	auto bump = [&](uint32_t slot, bool rev) {
 		const uint32_t before = atomicAdd(&cnts[slot], rev ? 0x10000u : 1u);
 		const uint32_t now = ((before >> (rev ? 16 : 0)) & 0x7FFFu) + 1u;
-		if (P.merged) atomicMax(&s_maxm, (before & 0x7FFFu) + ((before >> 16) & 0x7FFFu) + 1u);
+		if (P.merged) {
+			const uint32_t both = (before & 0x7FFFu) + ((before >> 16) & 0x7FFFu) + 1u;
+			if (both > *(volatile uint32_t *) &s_maxm) atomicMax(&s_maxm, both);
+		}
 		if (now >= 2u) {
-			atomicMax(&s_max, now);
+			if (now > *(volatile uint32_t *) &s_max) atomicMax(&s_max, now);       // (a stale value only costs a redundant atomic)
 			if (now == 2u) {
 				const uint32_t at = atomicAdd(&s_nmulti, 1u);
 				if (at < kCsMaxMulti) s_multi[at] = (uint16_t) slot;

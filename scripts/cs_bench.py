@@ -24,12 +24,21 @@ def main():
     ap.add_argument("--sub-rate", type=float, default=0.01)
     ap.add_argument("--indel-rate", type=float, default=0.0005)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--l2-fetch", type=int, default=0, help="experiment: cudaLimitMaxL2FetchGranularity (32 / 64 / 128)")
     args = ap.parse_args()
     import torch
     from nextgenmap_b200 import workload
     from nextgenmap_b200.host import CudaSW
     from nextgenmap_b200.host.cuda_sw import CsParams, _CContigRec
     dev = torch.device("cuda", 0)
+    if args.l2_fetch:
+        import glob
+        torch.zeros(1, device=dev)
+        rt = C.CDLL(sorted(glob.glob(str(Path(torch.__file__).parents[1] / "nvidia" / "cuda_runtime" / "lib" / "libcudart.so*")))[0])
+        rc = rt.cudaDeviceSetLimit(5, C.c_size_t(args.l2_fetch))          # cudaLimitMaxL2FetchGranularity
+        got = C.c_size_t(0)
+        rt.cudaDeviceGetLimit(C.byref(got), 5)
+        print(f"cudaLimitMaxL2FetchGranularity: rc {rc}, now {got.value}", file=sys.stderr)
     L = args.read_len
     qml, corridor = workload.shapes_for(L)
     ref = workload.make_reference(dev, args.contigs, args.contig_len, seed=20261017)
