@@ -47,6 +47,11 @@ def compile_one(src: Path, force: bool) -> Path:
 def build(force: bool = False, verbose: bool = False) -> Path:
     OBJ.mkdir(exist_ok=True)
     srcs = sources()
+    deps = srcs + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list((PKG.parent / "include").glob("*.h"))
+    if not force and not stale(LIB, deps):          # up to date (the object files do not travel to the GPU box)
+        if verbose:
+            print(f"up to date: {LIB}")
+        return LIB
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(lambda s: compile_one(s, force), srcs))
     if force or stale(LIB, objs):

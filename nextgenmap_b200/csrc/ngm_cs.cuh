@@ -32,6 +32,7 @@ namespace ngm {
 
 struct CsDev {
 	const uint32_t *tabu;     // [4^k + 1]
+	const uint4 *both;        // [4^k] {forward list start, length, reverse-complement list start, length}: one 16-byte load per k-mer
 	const uint32_t *table;
 	int k, bin_shift, max_kfreq, max_cmrs;
 	float sensitivity, kmer_min;
@@ -255,14 +256,27 @@ struct CsLists {
 };
 
 __device__ __forceinline__ bool cs_lookup(const CsDev &P, uint32_t prefix, CsLists &L) {      // GetRefEntry, PrefixTable.cpp:750-817
-	const uint32_t rcp = cs_revcomp(prefix, P.k);
-	const uint32_t a0 = NGM_CS_LD(P.tabu + prefix), a1 = NGM_CS_LD(P.tabu + prefix + 1);
-	const uint32_t b0 = NGM_CS_LD(P.tabu + rcp), b1 = NGM_CS_LD(P.tabu + rcp + 1);
-	L.fs = a0 & 0x7FFFFFFFu;
-	L.fc = (a0 >> 31) ? (a1 & 0x7FFFFFFFu) - L.fs : 0u;
-	L.rs = b0 & 0x7FFFFFFFu;
-	L.rc = (b0 >> 31) ? (b1 & 0x7FFFFFFFu) - L.rs : 0u;
+	const uint4 e = NGM_CS_LD(P.both + prefix);
+	L.fs = e.x;
+	L.fc = e.y;
+	L.rs = e.z;
+	L.rc = e.w;
 	return (int) (L.fc + L.rc) < P.max_kfreq;              // cur->refTotal < maxPrefixFreq, CS.cpp:122
+}
+
+// both[p] from tabu: what GetRefEntry assembles from Index[p], Index[p + 1], Index[rc(p)], Index[rc(p) + 1] (two random 8-byte reads per
+// k-mer of every read) is laid down once per index, so that the search reads one aligned 16-byte entry per k-mer.
+__global__ void cs_both_kernel(const uint32_t *__restrict__ tabu, uint32_t n_prefix, int k, uint4 *__restrict__ both) {
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= n_prefix) return;
+	const uint32_t rcp = cs_revcomp(p, k);
+	const uint32_t a0 = tabu[p], a1 = tabu[p + 1], b0 = tabu[rcp], b1 = tabu[rcp + 1];
+	uint4 e;
+	e.x = a0 & 0x7FFFFFFFu;
+	e.y = (a0 >> 31) ? (a1 & 0x7FFFFFFFu) - e.x : 0u;
+	e.z = b0 & 0x7FFFFFFFu;
+	e.w = (b0 >> 31) ? (b1 & 0x7FFFFFFFu) - e.z : 0u;
+	both[p] = e;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -287,6 +301,7 @@ __device__ __forceinline__ bool cs_lookup(const CsDev &P, uint32_t prefix, CsLis
 enum CsExactReason { kCsWhyHits = 0, kCsWhyWrap, kCsWhyQueue, kCsWhyTable, kCsWhyMulti, kCsWhyZeroThr, kCsWhyAccepted, kCsWhyItems, kCsWhyOrder, kCsWhyCount };
 constexpr int kCsRepWords = 512;                               // 16384 "repeated" bits; the "seen" bitmap has max(65536, 32 x T2) bits
 constexpr int kCsMaxMulti = 256;                               // (entry, strand) pairs with two or more votes
+constexpr int kCsMaxRes = 4;                                   // entries that can still reach the threshold after the queue is counted
 constexpr int kCsQueue = 512;                                  // hits per read that find their bit set (repeats + false positives)
 constexpr uint32_t kHitInserted = 0x80000000u, kHitRev = 0x40000000u, kHitBin = 0x3FFFFFFFu;
 
@@ -334,13 +349,14 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 	__shared__ uint16_t s_queue[kCsQueue];                     // hit numbers (< MAXH)
 	static_assert(MAXH <= 65536, "queue entries are 16 bits wide");
 	__shared__ uint16_t s_multi[kCsMaxMulti];
-	__shared__ uint32_t s_max, s_maxm, s_slow, s_nmulti, s_nacc, s_ncand, s_nitems, s_nord, s_nq;
+	__shared__ uint32_t s_max, s_maxm, s_slow, s_nmulti, s_nacc, s_ncand, s_nitems, s_nord, s_nq, s_nres;
+	__shared__ uint32_t s_res[2 * kCsMaxRes];                  // bins whose first vote is looked for (see sweep C)
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int r = blockIdx.x;
 	if (r >= n_reads) return;
 	if (tid == 0) {
 		s_len = stride;
-		s_max = s_maxm = s_slow = s_nmulti = s_nacc = s_ncand = s_nitems = s_nord = s_nq = 0;
+		s_max = s_maxm = s_slow = s_nmulti = s_nacc = s_ncand = s_nitems = s_nord = s_nq = s_nres = 0;
 	}
 	{
 		uint4 *z4 = reinterpret_cast<uint4 *>(seen);               // both bitmaps
@@ -579,20 +595,82 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 		return -1;
 	};
 	// ---- C: the hit that set the bit of a repeated bin (the "repeated" bitmap spares the lookup for ~97 % of the hits)
-	for (uint32_t h4 = 4 * tid; h4 < n_hits; h4 += 4 * NT) {       // four hits per thread and step (bins[] is 16-byte aligned)
-		const uint4 q4 = *reinterpret_cast<const uint4 *>(bins + h4);
-		const uint32_t tt[4] = {q4.x, q4.y, q4.z, q4.w};
+	auto sweep_c = [&]() {
+		for (uint32_t h4 = 4 * tid; h4 < n_hits; h4 += 4 * NT) {   // four hits per thread and step (bins[] is 16-byte aligned)
+			const uint4 q4 = *reinterpret_cast<const uint4 *>(bins + h4);
+			const uint32_t tt[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
-		for (int e = 0; e < 4; ++e) {
-			const uint32_t t = tt[e];
-			if (h4 + e >= n_hits || (t & kHitInserted)) continue;
-			uint32_t word, bit;
-			rep_bit(t & kHitBin, word, bit);
-			if (!(rep[word] & bit)) continue;
-			const int slot = find(t & kHitBin);
-			if (slot >= 0) {
-				bump((uint32_t) slot, (t & kHitRev) != 0);
-				bins[h4 + e] = t | kHitInserted;
+			for (int e = 0; e < 4; ++e) {
+				const uint32_t t = tt[e];
+				if (h4 + e >= n_hits || (t & kHitInserted)) continue;
+				uint32_t word, bit;
+				rep_bit(t & kHitBin, word, bit);
+				if (!(rep[word] & bit)) continue;
+				const int slot = find(t & kHitBin);
+				if (slot >= 0) {
+					bump((uint32_t) slot, (t & kHitRev) != 0);
+					bins[h4 + e] = t | kHitInserted;
+				}
+			}
+		}
+	};
+	// Only entries that can still reach the threshold need their missing first vote: with Mq the best count so far (queued hits
+	// only), the final threshold is at least thr_lb = max(kmer_min, sensitivity x Mq), and an entry whose count + 1 stays below it can
+	// neither pass nor be the maximum.  When thr_lb > 2 those entries are few (the true locus and its neighbours): the sweep then
+	// compares every hit with up to kCsMaxRes bins held in registers instead of hashing it into the "repeated" bitmap.  The complete
+	// sweep still runs when the order of the list has to be worked out (phase E), when every bin is a candidate (path J), for the
+	// both-strand maximum of the sensitivity estimate, and when more entries qualify than the registers hold.
+	bool full_c = P.merged != 0 || s_nmulti > (uint32_t) kCsMaxMulti;
+	const float thr_lb = fmaxf(P.kmer_min, __fmul_rn((float) s_max, P.sensitivity));
+	if (!(thr_lb > 2.0f)) full_c = true;
+	if (!full_c) {
+		for (uint32_t i = tid; i < s_nmulti; i += NT) {
+			const uint32_t sl = s_multi[i];
+			const uint32_t c = cnts[sl];
+			if ((float) (max(c & 0x7FFFu, (c >> 16) & 0x7FFFu) + 1u) >= thr_lb) {
+				const uint32_t at = atomicAdd(&s_nres, 1u);
+				if (at < 2u * kCsMaxRes) s_res[at] = keys[sl];
+			}
+		}
+		__syncthreads();
+		if (tid == 0) {                                         // an entry is listed once per strand that reached two votes
+			const uint32_t listed = min(s_nres, 2u * (uint32_t) kCsMaxRes);
+			uint32_t n = 0;
+			for (uint32_t i = 0; i < listed; ++i) {                 // compaction in place (n <= i)
+				const uint32_t v = s_res[i];
+				bool dup = false;
+				for (uint32_t j = 0; j < n; ++j) dup = dup || s_res[j] == v;
+				if (!dup) s_res[n++] = v;
+			}
+			const bool over = s_nres > 2u * (uint32_t) kCsMaxRes || n > (uint32_t) kCsMaxRes;
+			for (uint32_t j = n; j < (uint32_t) kCsMaxRes; ++j) s_res[j] = 0xFFFFFFFFu;
+			s_nres = over ? 0xFFFFFFFFu : n;
+		}
+		__syncthreads();
+		if (s_nres == 0xFFFFFFFFu) full_c = true;
+	}
+	if (full_c) {
+		sweep_c();
+	} else if (s_nres > 0) {
+		uint32_t key[kCsMaxRes];
+#pragma unroll
+		for (int j = 0; j < kCsMaxRes; ++j) key[j] = s_res[j];
+		for (uint32_t h4 = 4 * tid; h4 < n_hits; h4 += 4 * NT) {
+			const uint4 q4 = *reinterpret_cast<const uint4 *>(bins + h4);
+			const uint32_t tt[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+			for (int e = 0; e < 4; ++e) {
+				const uint32_t b = tt[e] & ~kHitRev;               // equals a key only if kHitInserted is clear: a first hit
+				bool hit = false;
+#pragma unroll
+				for (int j = 0; j < kCsMaxRes; ++j) hit = hit || b == key[j];
+				if (hit && h4 + e < n_hits) {
+					const int slot = find(b);
+					if (slot >= 0) {
+						bump((uint32_t) slot, (tt[e] & kHitRev) != 0);
+						bins[h4 + e] = tt[e] | kHitInserted;
+					}
+				}
 			}
 		}
 	}
@@ -708,6 +786,10 @@ __global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uin
 		return;
 	}
 	if (nacc > 1) {
+		if (!full_c) {                                             // the replay needs every entry's votes and first hit
+			sweep_c();
+			__syncthreads();
+		}
 		// ---- E: order of the list: replay the relevant hits in sequence ---------------------------------------
 		for (uint32_t h = tid; h < n_hits; h += NT) {
 			const uint32_t t = bins[h];
