@@ -550,7 +550,12 @@ def main():
                        "reads_on_sequential_exact_kernel": sw.cs_exact_reads(), "exact_kernel_reasons": sw.cs_exact_reasons(),
                        "roofline": {"kernel": "cs_search_kernel", "bound": "hbm", "algorithmic_bytes_per_read": alg_bytes_read,
                                     "achieved": alg_bytes_read * n / (ms_cs * 1e-3) / 1e9, "unit": "GB/s",
-                                    "note": "2 index lookups of 8 B and 2 position lists of ~%.1f x 4 B per k-mer, %d k-mers per read" % (mean_list, n_kmers)}}
+                                    "note": "one 16-byte index entry and 2 position lists of ~%.1f x 4 B per k-mer, %d k-mers per read" % (mean_list, n_kmers)}}
+            cs_info["roofline"]["peak"] = hbm_peak_cs = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text()).get("hbm_gbs", 6542.0)) if (ROOT / "MEASURED_PEAKS.json").exists() else 6542.0
+            cs_info["roofline"]["frac"] = cs_info["roofline"]["achieved"] / hbm_peak_cs
+            tfc = ROOT / "profiles" / "traffic_r1.json"
+            if tfc.exists() and L == READ_LEN:
+                cs_info["roofline"]["traffic"] = json.loads(tfc.read_text())["cs_search_kernel"]["dram_bytes_per_unit"] * n
             # parity at full scale + CPU beside it (rank 0): the oracle restatement of CS.cpp searches a sample of the reads in
             # the SAME 3 Gbp prefix table (exported from the device); lists must agree entry by entry, order included
             if rank == 0 and not args.no_cpu_baseline:
@@ -626,7 +631,7 @@ def main():
                                "candidates_per_read": total_p / n, "select_pairs_ms": ms_sel, "pipeline_ms": ms_pe, "pipeline_reads_per_s": world * n / (ms_pe * 1e-3),
                                "proper_pair_fraction": float(((first["pf"] == 0) & (first["best"] >= 0)).mean()), "winner_at_true_locus": float(ok_pe.float().mean().item()),
                                "mean_insert_size": sum1 / max(cnt1, 1), "pairs_accepted": cnt1 - 1,
-                               "fragments_decided_sequentially": deferred1}
+                               "fragments_needing_insert_mean": deferred1}
                     if rank == 0 and not args.no_cpu_baseline:
                         try:
                             from oracle import mapper_port

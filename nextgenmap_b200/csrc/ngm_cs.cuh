@@ -28,6 +28,10 @@
 #define NGM_CS_LD(p) __ldg(p)          /* ld.global.cg measured 16 % slower: the 18 % L1 hits are worth keeping */
 #endif
 
+#ifndef NGM_CS_MIN_BLOCKS
+#define NGM_CS_MIN_BLOCKS 5            /* resident blocks the register allocation must allow (5 x 256 threads: <= 51 registers) */
+#endif
+
 namespace ngm {
 
 struct CsDev {
@@ -315,7 +319,7 @@ struct CsSmem {
 };
 
 template <int T2_LOG, int MAXK, int MAXH, int SEENW_ = 0>
-__global__ void __launch_bounds__(256) cs_search_kernel(const CsDev P, const uint8_t *__restrict__ reads, int n_reads, int stride,
+__global__ void __launch_bounds__(256, NGM_CS_MIN_BLOCKS) cs_search_kernel(const CsDev P, const uint8_t *__restrict__ reads, int n_reads, int stride,
 		CsMeta *__restrict__ meta, CsCand *__restrict__ heap, uint32_t heap_cap, uint32_t *__restrict__ cursor, uint32_t *__restrict__ slow_list,
 		uint32_t *__restrict__ slow_count, float *__restrict__ max_hit) {
 	// slow_count[1 + reason]: why reads left the fast path (diagnostics, see CsExactReason)

@@ -1,7 +1,2 @@
-python -m pytest tests/test_gpu_cs.py tests/test_gpu_pipeline_vs_ngm.py -x -q 2>&1 | tail -4 > gpurun_out/r1w_tests.log
-python scripts/cs_bench.py --reads 2000000 > gpurun_out/r1w_cs.json 2> gpurun_out/r1w_cs.err
-python scripts/cs_bench.py --reads 500000 --read-len 250 > gpurun_out/r1w_cs250.json 2>> gpurun_out/r1w_cs.err
-python scripts/cs_bench.py --reads 500000 --read-len 250 --sub-rate 0.12 --indel-rate 0.004 > gpurun_out/r1w_cs250d.json 2>> gpurun_out/r1w_cs.err
-M=gpu__time_duration.sum,dram__bytes_read.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active
-ncu --metrics $M --clock-control none -k regex:cs_search_kernel -c 1 --csv --log-file gpurun_out/r1w_ncu.csv python scripts/cs_bench.py --reads 1000000 --reps 1 > /dev/null 2>&1
-cat gpurun_out/r1w_tests.log gpurun_out/r1w_cs.json gpurun_out/r1w_cs250.json gpurun_out/r1w_cs250d.json; tail -3 gpurun_out/r1w_cs.err; grep -v "^==" gpurun_out/r1w_ncu.csv | cut -d, -f 21- | tail -4
+ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:ngm:: -c 4000 --csv --log-file gpurun_out/r1z_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/r1z_ncu_bench.log 2>&1
+grep -c ngm gpurun_out/r1z_launches.csv; tail -2 gpurun_out/r1z_ncu_bench.log | cut -c1-200
