@@ -384,7 +384,7 @@ int ngm_b200_dev_cs_search(ngm_b200_ctx *c, const void *d_ascii_reads, int n_rea
 		const double mean_list = (double) cs->table_len / (double) cs->n_prefix;
 		const double expect = (double) std::max(1, stride - cs->k + 1) * 2.0 * std::max(mean_list, 0.5);      // hits per read
 		const bool bins_fit = ((c->concat_len + 1024) >> cs->bin_shift) < (1ull << 30);      // two flag bits ride on every stored bin
-		const bool scan_fits = (uint64_t) std::max(1, stride - cs->k + 1) * (uint64_t) P.max_kfreq < (1ull << 20);      // packed scan: hits in 20 bits
+		const bool scan_fits = (uint64_t) std::max(1, stride - cs->k + 1) * (uint64_t) P.max_kfreq < (1ull << 20) && P.max_kfreq <= 65535;      // packed scan: hits in 20 bits; list lengths in 16
 		if (!bins_fit || !scan_fits) {
 			cs->exact_all = true;                                  // (bin_size 0/1 on > 1 Gbp: sequential kernel only)
 			exact_only_fallback = true;

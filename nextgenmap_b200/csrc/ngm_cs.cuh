@@ -314,8 +314,8 @@ struct CsSmem {
 	static constexpr int T2 = 1 << T2_LOG;
 	static constexpr int SEENW = SEENW_ ? SEENW_ : (T2 > 2048 ? T2 : 2048);        // words of the "seen" bitmap (reused as per-slot first-hit array, >= T2)
 	static_assert(SEENW >= T2, "the first-hit array of path J lives in the bitmap");
-	static constexpr size_t bytes = (size_t) (SEENW + kCsRepWords) * 4 + (size_t) T2 * 8 + (size_t) MAXH * 4 + (size_t) MAXK * 8 + ((size_t) MAXK + 4) * 4 +
-			(size_t) MAXK * 4 + (size_t) MAXK + 32 + ((size_t) MAXH / 32 + 2) * 2 + ((size_t) MAXH / 32 + 1) * 4 + (size_t) MAXK * 2;
+	static constexpr size_t bytes = (size_t) (SEENW + kCsRepWords) * 4 + (size_t) T2 * 8 + (size_t) MAXH * 4 + (size_t) MAXK * 16 +
+			(size_t) MAXK + 32 + ((size_t) MAXH / 32 + 2) * 2 + ((size_t) MAXH / 32 + 1) * 4;
 };
 
 template <int T2_LOG, int MAXK, int MAXH, int SEENW_ = 0>
@@ -333,14 +333,13 @@ __global__ void __launch_bounds__(256, NGM_CS_MIN_BLOCKS) cs_search_kernel(const
 	constexpr int SEEN_SHIFT = SEENW == 2048 ? 16 : (SEENW == 4096 ? 15 : 14);      // 32 - log2(32 x SEENW)
 	static_assert(SEENW == 2048 || SEENW == 4096 || SEENW == 8192, "seen bitmap size");
 	uint32_t *seen = s_dyn, *rep = seen + SEENW, *keys = rep + kCsRepWords, *cnts = keys + T2, *bins = cnts + T2;
-	uint32_t *kfs = bins + MAXH, *krs = kfs + MAXK, *kbase = krs + MAXK;      // kbase: MAXK + 4 entries
-	uint16_t *kfc = reinterpret_cast<uint16_t *>(kbase + MAXK + 4), *krc = kfc + MAXK;
-	uint8_t *s_read = reinterpret_cast<uint8_t *>(krc + MAXK);            // MAXK + 32 bytes >= stride (stride - k + 1 <= MAXK, k <= 14)
-	// hit -> k-mer map of sweep B: per chunk c of 32 hits, rbase[c] = rank (among the k-mers with hits) of the k-mer that holds hit 32 c
-	// and bstart[c] = the hits of the chunk that begin a k-mer (bit 0 left out: that is rbase's); nzmap[rank] = k-mer
+	// the k-mers that have hits, by rank: {number of the k-mer's first hit, forward list start, reverse list start, forward length | k-mer << 16}
+	uint4 *km = reinterpret_cast<uint4 *>(bins + MAXH);
+	uint8_t *s_read = reinterpret_cast<uint8_t *>(km + MAXK);             // MAXK + 32 bytes >= stride (stride - k + 1 <= MAXK, k <= 14)
+	// hit -> k-mer map of sweep B: per chunk c of 32 hits, rbase[c] = rank of the k-mer that holds hit 32 c and bstart[c] = the hits of
+	// the chunk that begin a k-mer (bit 0 left out: that is rbase's)
 	uint16_t *rbase = reinterpret_cast<uint16_t *>(s_read + MAXK + 32);
 	uint32_t *bstart = reinterpret_cast<uint32_t *>(rbase + (MAXH / 32 + 2));
-	uint16_t *nzmap = reinterpret_cast<uint16_t *>(bstart + (MAXH / 32 + 1));
 	static_assert(MAXK % 4 == 0 && MAXH % 64 == 0 && MAXK < 4096 && MAXH < (1 << 20), "alignment of the chunk maps; packing of the scan");
 	// dead while the "seen" bitmap is in use (sweep B), needed only from phase D on: they live in the bitmap's words
 	uint32_t *s_items_s = seen;                                           // kCsMaxItems words
@@ -353,6 +352,7 @@ __global__ void __launch_bounds__(256, NGM_CS_MIN_BLOCKS) cs_search_kernel(const
 	__shared__ uint16_t s_queue[kCsQueue];                     // hit numbers (< MAXH)
 	static_assert(MAXH <= 65536, "queue entries are 16 bits wide");
 	__shared__ uint16_t s_multi[kCsMaxMulti];
+	__shared__ uint32_t s_nhits;
 	__shared__ uint32_t s_max, s_maxm, s_slow, s_nmulti, s_nacc, s_ncand, s_nitems, s_nord, s_nq, s_nres;
 	__shared__ uint32_t s_res[2 * kCsMaxRes];                  // bins whose first vote is looked for (see sweep C)
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(256, NGM_CS_MIN_BLOCKS) cs_search_kernel(const
 	const int n_kmers = max(0, len - k + 1);                   // <= MAXK (checked by the launcher: stride - k + 1 <= MAXK)
 
 	// ---- A: list descriptors + sequence numbers -----------------------------------------------------------
-	uint32_t mine[IPT];
+	uint32_t mine[IPT], m_fs[IPT], m_rs[IPT], m_fc[IPT];
 #pragma unroll
 	for (int q = 0; q < IPT; ++q) {
 		const int o = tid * IPT + q;                           // blocked layout so that the scan below is a plain prefix sum
@@ -402,10 +402,9 @@ __global__ void __launch_bounds__(256, NGM_CS_MIN_BLOCKS) cs_search_kernel(const
 				}
 			}
 		}
-		kfs[o] = fs;
-		krs[o] = rs;
-		kfc[o] = (uint16_t) fc;
-		krc[o] = (uint16_t) rc;
+		m_fs[q] = fs;
+		m_rs[q] = rs;
+		m_fc[q] = fc;
 		mine[q] = (fc + rc) | ((fc + rc) ? (1u << 20) : 0u);      // hits in bits 0..19, "has hits" counted in bits 20..31
 	}
 	uint32_t tsum = 0;
@@ -426,17 +425,16 @@ __global__ void __launch_bounds__(256, NGM_CS_MIN_BLOCKS) cs_search_kernel(const
 #pragma unroll
 	for (int q = 0; q < IPT; ++q) {
 		const uint32_t start = run & 0xFFFFFu, cnt = mine[q] & 0xFFFFFu, rank = run >> 20;
-		kbase[tid * IPT + q] = start;
 		if (cnt && start + cnt <= (uint32_t) MAXH) {            // (reads with more hits leave for the exact kernel below)
-			nzmap[rank] = (uint16_t) (tid * IPT + q);
+			km[rank] = make_uint4(start, m_fs[q], m_rs[q], m_fc[q] | ((uint32_t) (tid * IPT + q) << 16));      // list lengths < max_kfreq <= 65535
 			if (start & 31u) atomicOr(&bstart[start >> 5], 1u << (start & 31u));
 			for (uint32_t ch = (start + 31u) >> 5; (ch << 5) < start + cnt; ++ch) rbase[ch] = (uint16_t) rank;
 		}
 		run += mine[q];
 	}
-	if (tid == NT - 1) kbase[MAXK] = run & 0xFFFFFu;
+	if (tid == NT - 1) s_nhits = run & 0xFFFFFu;
 	__syncthreads();
-	const uint32_t n_hits = kbase[MAXK];
+	const uint32_t n_hits = s_nhits;
 	auto to_exact = [&](int reason) {
 		if (tid == 0) {
 			meta[r].off = 0;
@@ -503,11 +501,11 @@ __global__ void __launch_bounds__(256, NGM_CS_MIN_BLOCKS) cs_search_kernel(const
 			loc[u] = 0;
 			meta_j[u] = 0xFFFFFFFFu;
 			if (h < n_hits) {                                       // implies ch < n_chunks
-				const uint32_t j = nzmap[rbase[ch] + __popc(bstart[ch] & lane_le)];
-				const uint32_t o = h - kbase[j], fc = kfc[j];
+				const uint4 e = km[rbase[ch] + __popc(bstart[ch] & lane_le)];
+				const uint32_t o = h - e.x, fc = e.w & 0xFFFFu;
 				const bool rv = o >= fc;
-				loc[u] = NGM_CS_LD(P.table + (rv ? krs[j] + (o - fc) : kfs[j] + o));
-				meta_j[u] = j | (rv ? 0x80000000u : 0u);
+				loc[u] = NGM_CS_LD(P.table + (rv ? e.z + (o - fc) : e.y + o));
+				meta_j[u] = (e.w >> 16) | (rv ? 0x80000000u : 0u);
 			}
 		}
 		uint32_t again = 0;

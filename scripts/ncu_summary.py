@@ -17,6 +17,8 @@ for row in csv.DictReader(rows):
     agg.setdefault(row["Kernel Name"].split("(")[0][:90], []).append(float(row["Metric Value"].replace(",", "")))
 tot = sum(sum(v) for v in agg.values())
 mine = {k: v for k, v in agg.items() if "ngm::" in k}
+if not mine:            # launch list taken with `--kernel-name-base demangled -k regex:ngm::` : only this library's kernels, namespace stripped
+    mine = {k: v for k, v in agg.items() if "cub::" not in k}
 tot_mine = sum(sum(v) for v in mine.values())
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1]))[:14]:
     lines.append(f"| {sum(v) / 1e6:.3f} | {100 * sum(v) / tot:.1f}% | {len(v)} | `{k}` |")
