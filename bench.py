@@ -520,6 +520,14 @@ def main():
                                                           d_strings.data_ptr(), str_cap, d_cursor.data_ptr(), st))
                 return total
 
+            cs_only()                                               # size the candidate buffers for this workload (divergent reads: ~20 per read)
+            need = int(d_cb[n].item())
+            if need > cap:
+                cap = int(need * 1.05) + 1024
+                del d_cpairs, d_cvotes, d_cscores
+                d_cpairs = torch.empty((cap, 16), dtype=torch.uint8, device=dev)
+                d_cvotes = torch.empty(cap, dtype=torch.float32, device=dev)
+                d_cscores = torch.empty(cap, dtype=torch.float32, device=dev)
             ms_cs = time_call(cs_only, reps=3)
             total_c = cs_pipeline_step()
             torch.cuda.synchronize()

@@ -385,14 +385,20 @@ int ngm_b200_dev_cs_search(ngm_b200_ctx *c, const void *d_ascii_reads, int n_rea
 		const double expect = (double) std::max(1, stride - cs->k + 1) * 2.0 * std::max(mean_list, 0.5);      // hits per read
 		const bool bins_fit = ((c->concat_len + 1024) >> cs->bin_shift) < (1ull << 30);      // two flag bits ride on every stored bin
 		const bool scan_fits = (uint64_t) std::max(1, stride - cs->k + 1) * (uint64_t) P.max_kfreq < (1ull << 20) && P.max_kfreq <= 65535;      // packed scan: hits in 20 bits; list lengths in 16
+		const int n_kmers_max = stride - cs->k + 1;
+		int config = (n_kmers_max <= 256 && expect <= 4250.0) ? 1 : (n_kmers_max <= 256 && expect <= 7700.0) ? 2 : (n_kmers_max <= 512 && expect <= 14000.0) ? 3 : 4;
+		if (const char *e = getenv("NGM_B200_CS_CONFIG")) {        // testing hook: run a small case through a larger configuration
+			const int want = atoi(e);
+			if (want > config && want <= 4) config = want;
+		}
 		if (!bins_fit || !scan_fits) {
 			cs->exact_all = true;                                  // (bin_size 0/1 on > 1 Gbp: sequential kernel only)
 			exact_only_fallback = true;
-		} else if (stride - cs->k + 1 <= 256 && expect <= 4250.0) {
-			CU(launch(cs_search_kernel<10, 256, 4608>, CsSmem<10, 256, 4608>::bytes));
-		} else if (stride - cs->k + 1 <= 256 && expect <= 7700.0) {
+		} else if (config == 1) {
+			CU(launch(cs_search_kernel<10, 256, 4608>, CsSmem<10, 256, 4608>::bytes));                  // 150 bp on 3 Gbp: 5 blocks / SM
+		} else if (config == 2) {
 			CU(launch(cs_search_kernel<11, 256, 8192, 4096>, CsSmem<11, 256, 8192, 4096>::bytes));      // 250 bp on 3 Gbp: 3 blocks / SM
-		} else if (stride - cs->k + 1 <= 512 && expect <= 14000.0) {
+		} else if (config == 3) {
 			CU(launch(cs_search_kernel<12, 512, 16384>, CsSmem<12, 512, 16384>::bytes));
 		} else {
 			CU(launch(cs_search_kernel<12, 1024, 36864>, CsSmem<12, 1024, 36864>::bytes));

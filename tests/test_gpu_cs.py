@@ -67,8 +67,15 @@ def test_index_and_candidates_match_reference_fixture(name):
 
 @pytest.mark.parametrize("seed,k,read_len,sens,scale", [(51, 13, 150, 0.5, 4), (52, 12, 100, 0.3, 2), (53, 13, 250, 0.8, 3), (54, 11, 400, 0.5, 1),
                                                         (55, 10, 36, 0.5, 1), (56, 13, 1000, 0.5, 2)])
-def test_fresh_cases_against_oracle(seed, k, read_len, sens, scale):
+@pytest.mark.parametrize("config", [0, 2, 3, 4])
+def test_fresh_cases_against_oracle(seed, k, read_len, sens, scale, config, monkeypatch):
+    """config: the library's testing hook NGM_B200_CS_CONFIG -- the small references here would always take the smallest kernel
+    configuration their read length allows; 2..4 push the same cases through the configurations that long reads / large genomes use."""
     from nextgenmap_b200.host import CudaSW
+    if config:
+        if read_len > 250 and config < 4 or seed in (52, 55):
+            pytest.skip("covered by the default configuration")
+        monkeypatch.setenv("NGM_B200_CS_CONFIG", str(config))
     contigs = cs_cases.make_reference(seed, scale)
     concat, ctg, concat_len = cs_port.layout(contigs)
     qml, cor = shapes_for(read_len)
