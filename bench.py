@@ -564,6 +564,37 @@ def main():
             tfc = ROOT / "profiles" / "traffic_r1.json"
             if tfc.exists() and L == READ_LEN:
                 cs_info["roofline"]["traffic"] = json.loads(tfc.read_text())["cs_search_kernel"]["dram_bytes_per_unit"] * n
+            # SAM records of the single-end run on the host threads (ngm_b200_format_sam): 1 M reads of the step above
+            if rank == 0:
+                try:
+                    from nextgenmap_b200.host.cuda_sw import SamBatch, SamOpts, _CContig, _CEncRef
+                    n_f = min(n, 1_000_000)
+                    e_f = int(d_cb[n_f].item())
+                    h_reads = batch.reads[:n_f].cpu().numpy()
+                    h_quals = np.where(h_reads != 0, ord("I"), 0).astype(np.uint8)
+                    name_arr = (C.c_char_p * n_f)(*[b"r%d" % i for i in range(n_f)])
+                    hk = [d_cpairs[:e_f].cpu().numpy(), d_cscores[:e_f].cpu().numpy(), d_best[:n_f].cpu().numpy(), d_mapq[:n_f].cpu().numpy(),
+                          np.ones(n_f, np.int32), np.zeros(n_f, np.float32), d_recs.cpu().numpy().view(np.uint8).reshape(n, -1)[:n_f].copy(), d_strings.cpu().numpy()]
+                    ctg = (_CContig * args.contigs)()
+                    for i, s0 in enumerate(ref.contig_start):
+                        ctg[i].start, ctg[i].length, ctg[i].name_len, ctg[i].name = int(s0), int(ref.contig_len), len("chr%d" % (i + 1)), b"chr%d" % (i + 1)
+                    enc = _CEncRef()
+                    enc.concat_len, enc.packed_bytes, enc.n_contigs = ref.concat_len, 0, args.contigs
+                    enc.contigs = C.cast(ctg, type(enc.contigs))
+                    sb = SamBatch(n_f, qml, h_reads.ctypes.data, h_quals.ctypes.data, name_arr, hk[0].ctypes.data, hk[1].ctypes.data, hk[2].ctypes.data, hk[3].ctypes.data,
+                                  hk[4].ctypes.data, None, hk[5].ctypes.data, hk[6].ctypes.data, hk[7].ctypes.data)
+                    so = SamOpts(0.65, 0.5, 0, 1000, 0)
+                    out_f = np.zeros(n_f * (2 * qml + 256), np.uint8)
+                    used = C.c_size_t(0)
+                    t0 = time.perf_counter()
+                    rc_f = lib.ngm_b200_format_sam(C.byref(enc), C.byref(so), C.byref(sb), out_f.ctypes.data, out_f.size, C.byref(used))
+                    fmt_s = time.perf_counter() - t0
+                    cs_info["sam_format"] = {"reads": n_f, "host_threads": host_threads, "reads_per_s": n_f / fmt_s, "bytes": int(used.value), "rc": int(rc_f),
+                                             "mapped_lines": int(out_f[: used.value].tobytes().count(b"\tAS:i:")),
+                                             "note": "ngm_b200_format_sam on the host: AlignmentBuffer::WriteRead + GenericReadWriter filters + SAMWriter lines"}
+                    del out_f, hk, h_reads, h_quals
+                except Exception as e:  # noqa: BLE001
+                    cs_info["sam_format"] = {"error": str(e)}
             # parity at full scale + CPU beside it (rank 0): the oracle restatement of CS.cpp searches a sample of the reads in
             # the SAME 3 Gbp prefix table (exported from the device); lists must agree entry by entry, order included
             if rank == 0 and not args.no_cpu_baseline:

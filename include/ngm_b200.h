@@ -293,6 +293,37 @@ int64_t ngm_b200_pe_deferred_fragments(ngm_b200_ctx *ctx);
  * all batches since ngm_b200_pe_configure -- the reference's result with one CS thread.  Enqueued on `stream`, not synchronised. */
 int ngm_b200_dev_select_pairs(ngm_b200_ctx *ctx, int n_reads, const void *d_cand_begin, const void *d_pairs, const void *d_scores, uint32_t n_pairs,
 		void *d_best_pair, void *d_mapq, void *d_num_top, void *d_pair_fail, void *stream);
+/* -- SAM records of a batch ------------------------------------------------------------------ */
+/* Output filters and pair limits (src/config/Config.cpp:405-410,430-431; GenericReadWriter.h:204-214,263-283). */
+typedef struct ngm_b200_sam_opts {
+	float min_identity;         /* "min_identity" (0.65) */
+	float min_residues;         /* "min_residues" (0.5): <= 1 = fraction of the read length */
+	int32_t min_insert_size;    /* "min_insert_size" (0), inclusive in the check of the aligned mates */
+	int32_t max_insert_size;    /* "max_insert_size" (1000); <= 0 = INT_MAX */
+	int32_t threads;            /* host threads; 0 = all */
+} ngm_b200_sam_opts;
+/* One batch as the calls above leave it, all host pointers.  Paired runs: rows 2f / 2f + 1 are mates and pair_fail != NULL. */
+typedef struct ngm_b200_sam_batch {
+	int32_t n_reads, stride;
+	const char *reads;              /* n_reads rows of `stride` bytes, NUL padded (MappedRead::Seq) */
+	const char *quals;              /* same shape (MappedRead::qlty) */
+	const char *const *names;       /* NUL-terminated read names, mate suffix stripped (ReadProvider.cpp:417-420) */
+	const ngm_b200_pair *pairs;     /* candidates (ngm_b200_cs_search) */
+	const float *scores;            /* BatchScore of every candidate -> AS:i */
+	const int32_t *best_pair;       /* selection: index into pairs or -1 */
+	const int32_t *mapq;
+	const int32_t *num_top;         /* NH:i / X0:i */
+	const int32_t *pair_fail;       /* NULL = single-end */
+	const float *max_hit;           /* MappedRead::s -> XE:i */
+	const ngm_b200_align_rec *recs; /* alignment of read r's selected candidate (ngm_b200_align_pairs with read_index = r) */
+	const char *strings;            /* its string heap */
+} ngm_b200_sam_batch;
+/* SAM body lines (no header) of the batch in read order, what AlignmentBuffer::WriteRead (AlignmentBuffer.cpp:166-200),
+ * GenericReadWriter::WriteRead / WritePair (GenericReadWriter.h:190-312) and SAMWriter::DoWriteReadGeneric / DoWriteUnmappedReadGeneric /
+ * DoWritePair (SAMWriter.cpp:98-228,230-365) produce for topn 1 without bs-mapping, clipping options or read group.  Host only,
+ * multi-threaded.  *out_used receives the bytes needed; NGM_B200_ERANGE if that exceeds out_capacity (nothing is written then). */
+int ngm_b200_format_sam(const ngm_b200_encref *ref, const ngm_b200_sam_opts *opts, const ngm_b200_sam_batch *batch, char *out, size_t out_capacity,
+		size_t *out_used);
 /* Device-pointer form of ngm_b200_cs_search: enqueued on `stream`, not synchronised; the caller checks
  * cand_begin[n_reads] <= capacity afterwards.  d_votes / d_max_hit may be NULL. */
 int ngm_b200_dev_cs_search(ngm_b200_ctx *ctx, const void *d_ascii_reads, int n_reads, int stride, int mode_flags, void *d_cand_begin,

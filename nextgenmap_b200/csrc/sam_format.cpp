@@ -1,0 +1,315 @@
+// sam_format.cpp -- SAM body lines from the records of the device path ("multi-thread SAM formatting so the host keeps up").
+// Host only, no CUDA call.
+//
+// What NextGenMap does per read after BatchAlign: AlignmentBuffer::DoRun's `Location += PositionOffset - corridor / 2`
+// (src/AlignmentBuffer.cpp:129), AlignmentBuffer::WriteRead (convert() to contig coordinates :166-176; for pairs the check of the
+// aligned positions :176-200), the output filters of GenericReadWriter::WriteRead / WritePair (src/writer/GenericReadWriter.h:190-312:
+// min_identity, min_residues) and SAMWriter::DoWriteReadGeneric / DoWriteUnmappedReadGeneric / DoWritePair
+// (src/writer/SAMWriter.cpp:98-228,230-310,312-365).  topn 1, no bs-mapping, no hard / silent clipping of SEQ, no read group.
+// Lines come out in read order (mates: second mate's line first, like DoWritePair); NGM's own order depends on its thread timing.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/ngm_b200.h"
+
+namespace {
+
+struct ReadView {          // one read after AlignmentBuffer::DoRun: what WriteRead / WritePair look at
+	int r = 0;
+	const char *name = nullptr;
+	const char *seq = nullptr;
+	const char *qual = nullptr;
+	int length = 0;
+	bool has = false;      // hasCandidates() with a usable alignment
+	bool reverse = false;
+	uint64_t loc = 0;      // Location.m_Location (contig-relative once convert() succeeded)
+	uint32_t contig = 0;
+	bool converted = false;
+	int bp = -1;
+};
+
+struct Job {
+	const ngm_b200_encref *ref;
+	const ngm_b200_sam_opts *o;
+	const ngm_b200_sam_batch *b;
+};
+
+inline char comp(char c) {     // MappedRead.cpp:36-47
+	switch (c) {
+	case 'A': return 'T';
+	case 'T': return 'A';
+	case 'C': return 'G';
+	case 'G': return 'C';
+	default: return c;
+	}
+}
+
+void collect(const Job &j, int r, ReadView &v) {
+	const ngm_b200_sam_batch &b = *j.b;
+	v.r = r;
+	v.name = b.names[r];
+	v.seq = b.reads + (size_t) r * b.stride;
+	v.qual = b.quals + (size_t) r * b.stride;
+	v.length = (int) strnlen(v.seq, (size_t) b.stride);
+	const int bp = b.best_pair[r];
+	if (bp >= 0 && b.recs[r].score >= 0.0f) {
+		const ngm_b200_pair &p = b.pairs[bp];
+		v.has = true;
+		v.bp = bp;
+		v.reverse = (p.flags & NGM_B200_PAIR_REVERSE) != 0;
+		v.loc = p.window_start + (uint64_t) (int64_t) b.recs[r].position_offset;      // window_start is Location - corridor / 2 already
+		uint32_t contig = 0;
+		uint64_t pos = 0;
+		if (ngm_b200_convert(j.ref, v.loc, &contig, &pos)) {
+			v.contig = contig;
+			v.loc = pos;
+			v.converted = true;
+		}
+	}
+}
+
+bool passes(const Job &j, const ReadView &v) {     // GenericReadWriter.h:206-214,273-283
+	const ngm_b200_align_rec &rec = j.b->recs[v.r];
+	const float mres = j.o->min_residues <= 1.0f ? (float) v.length * j.o->min_residues : j.o->min_residues;
+	return rec.identity >= j.o->min_identity && (float) (v.length - rec.qstart - rec.qend) >= mres;
+}
+
+struct Line {              // one output line is assembled in a scratch buffer that is large enough by construction (line_bound)
+	char *p;
+	void push_back(char c) { *p++ = c; }
+	void append(const char *s, size_t n) {
+		memcpy(p, s, n);
+		p += n;
+	}
+	void append(const char *s) { append(s, strlen(s)); }
+};
+
+size_t line_bound(const Job &j, int r) {       // name + FLAG..TLEN + SEQ + QUAL + tags + CIGAR + MD
+	const ngm_b200_align_rec &rec = j.b->recs[r];
+	return strlen(j.b->names[r]) + 2 * (size_t) j.b->stride + (j.b->best_pair[r] >= 0 ? (size_t) rec.cigar_len + rec.md_len : 0) + 2 * 100 + 320;
+}
+
+void put_name(Line &out, const ngm_b200_contig &c) { out.append(c.name, c.name_len); }
+
+inline void put_u64(Line &out, unsigned long long v) {       // what Print("%u") / Print("%d") produce, without the printf machinery
+	char buf[24];
+	int n = 0;
+	do {
+		buf[n++] = (char) ('0' + v % 10);
+		v /= 10;
+	} while (v);
+	while (n) out.push_back(buf[--n]);
+}
+
+inline void put_int(Line &out, long long v) {
+	if (v < 0) {
+		out.push_back('-');
+		put_u64(out, (unsigned long long) (-v));
+	} else {
+		put_u64(out, (unsigned long long) v);
+	}
+}
+
+inline void tag_int(Line &out, const char *tag, long long v) {
+	out.append(tag);
+	put_int(out, v);
+}
+
+// Print("XI:f:%g", round(Identity * 10000.0f) / 10000.0f) (SAMWriter.cpp:188-189): the value is k / 10000 with k = 0 .. 10000, which %g
+// prints as 0, 1 or 0.dddd without trailing zeros; anything else (NaN of an empty alignment) goes through printf itself.
+inline void put_xi(Line &out, float raw_identity) {
+	const float scaled = roundf(raw_identity * 10000.0f);
+	if (scaled >= 0.0f && scaled <= 10000.0f) {
+		int kk = (int) scaled;
+		if (kk == 0 || kk == 10000) {
+			out.push_back(kk ? '1' : '0');
+			return;
+		}
+		char d[4] = { (char) ('0' + kk / 1000), (char) ('0' + kk / 100 % 10), (char) ('0' + kk / 10 % 10), (char) ('0' + kk % 10) };
+		int n = 4;
+		while (d[n - 1] == '0') --n;
+		out.push_back('0');
+		out.push_back('.');
+		out.append(d, (size_t) n);
+		return;
+	}
+	char num[48];
+	snprintf(num, sizeof num, "%g", (float) ((double) scaled / 10000.0));
+	out.append(num);
+}
+
+void mapped_line(const Job &j, const ReadView &v, int flags, const char *rnext, const ngm_b200_contig *rnext_contig, int64_t pnext, int tlen,
+		Line &out) {                                        // SAMWriter::DoWriteReadGeneric
+	const ngm_b200_sam_batch &b = *j.b;
+	const ngm_b200_align_rec &rec = b.recs[v.r];
+	if (v.reverse) flags |= 0x10;
+	out.append(v.name);
+	out.push_back('\t');
+	put_int(out, flags);
+	out.push_back('\t');
+	put_name(out, j.ref->contigs[v.contig]);
+	out.push_back('\t');
+	put_u64(out, (unsigned) (v.loc + 1));
+	out.push_back('\t');
+	put_int(out, b.mapq[v.r]);
+	out.push_back('\t');
+	out.append(b.strings + rec.str_off, rec.cigar_len);
+	out.push_back('\t');
+	if (rnext_contig) put_name(out, *rnext_contig);
+	else out.append(rnext);
+	out.push_back('\t');
+	put_u64(out, (unsigned) (pnext + 1));
+	out.push_back('\t');
+	put_int(out, tlen);
+	out.push_back('\t');
+	char *dst = out.p;
+	out.p += 2 * (size_t) v.length + 1;
+	if (v.reverse) {                                            // RevSeq, reversed qualities (SAMWriter.cpp:120-126)
+		for (int i = 0; i < v.length; ++i) dst[i] = comp(v.seq[v.length - 1 - i]);
+		dst[v.length] = '\t';
+		for (int i = 0; i < v.length; ++i) dst[v.length + 1 + i] = v.qual[v.length - 1 - i];
+	} else {
+		memcpy(dst, v.seq, (size_t) v.length);
+		dst[v.length] = '\t';
+		memcpy(dst + v.length + 1, v.qual, (size_t) v.length);
+	}
+	const int ntop = b.num_top[v.r];
+	tag_int(out, "\tAS:i:", (int) b.scores[v.bp]);
+	tag_int(out, "\tNM:i:", rec.nm);
+	tag_int(out, "\tNH:i:", ntop);
+	out.append("\tXI:f:");
+	put_xi(out, rec.identity);
+	tag_int(out, "\tX0:i:", ntop);
+	tag_int(out, "\tXE:i:", (int) b.max_hit[v.r]);
+	tag_int(out, "\tXR:i:", v.length - rec.qstart - rec.qend);
+	out.append("\tMD:Z:");
+	const char *md = b.strings + rec.str_off + rec.cigar_len;
+	out.append(md, strnlen(md, rec.md_len));                    // printed with %s: stops at an embedded NUL (SURVEY 8a note 9)
+	out.push_back('\n');
+}
+
+void unmapped_line(const ReadView &v, int flags, const ngm_b200_contig *rname, int64_t loc, char rnext, int64_t pnext, Line &out) {
+	out.append(v.name);                                         // SAMWriter::DoWriteUnmappedReadGeneric
+	out.push_back('\t');
+	put_int(out, flags | 0x4);
+	out.push_back('\t');
+	if (rname) put_name(out, *rname);
+	else out.push_back('*');
+	out.push_back('\t');
+	put_int(out, (int) (loc + 1));
+	out.append("\t0\t*\t");
+	out.push_back(rnext);
+	out.push_back('\t');
+	put_int(out, (int) (pnext + 1));
+	out.append("\t0\t");
+	out.append(v.seq, (size_t) v.length);
+	out.push_back('\t');
+	out.append(v.qual, (size_t) v.length);
+	out.push_back('\n');
+}
+
+void single(const Job &j, int r, std::string &text, std::vector<char> &scratch) {
+	ReadView v;
+	collect(j, r, v);
+	scratch.resize(std::max(scratch.size(), line_bound(j, r)));
+	Line out = { scratch.data() };
+	if (v.has && v.converted && passes(j, v)) mapped_line(j, v, 0, "*", nullptr, -1, 0, out);
+	else unmapped_line(v, 0, nullptr, -1, '*', -1, out);
+	text.append(scratch.data(), (size_t) (out.p - scratch.data()));
+}
+
+void fragment(const Job &j, int f, std::string &text, std::vector<char> &scratch) {
+	const ngm_b200_sam_batch &bt = *j.b;
+	ReadView a, b;                                              // a: first mate (ReadId even), b: second mate
+	collect(j, 2 * f, a);
+	collect(j, 2 * f + 1, b);
+	scratch.resize(std::max(scratch.size(), line_bound(j, 2 * f) + line_bound(j, 2 * f + 1)));
+	Line out = { scratch.data() };
+	const int max_insert = j.o->max_insert_size > 0 ? j.o->max_insert_size : 0x7FFFFFFF;
+	bool fail = bt.pair_fail[a.r] != 0 || bt.pair_fail[b.r] != 0;
+	if (a.has && b.has) {                                       // AlignmentBuffer::WriteRead: read = first mate (it arrives second)
+		const int d = (int) (b.loc > a.loc ? b.loc - a.loc + (uint64_t) a.length : a.loc - b.loc + (uint64_t) b.length);
+		if (a.contig != b.contig || d < j.o->min_insert_size || d > max_insert || a.reverse == b.reverse) fail = true;
+	}
+	if (a.has && !passes(j, a)) a.has = false;                  // WritePair: mapped1 / mapped2, clearScores() otherwise
+	if (b.has && !passes(j, b)) b.has = false;
+	int fa = 0x1 | 0x40, fb = 0x1 | 0x80;
+	const ngm_b200_contig *ca = &j.ref->contigs[a.contig], *cb = &j.ref->contigs[b.contig];
+	if (!a.has && !b.has) {
+		unmapped_line(b, fb | 0x8, nullptr, -1, '*', -1, out);
+		unmapped_line(a, fa | 0x8, nullptr, -1, '*', -1, out);
+	} else if (!a.has) {
+		mapped_line(j, b, fb | 0x8, "=", nullptr, (int64_t) b.loc, 0, out);
+		unmapped_line(a, fa, cb, (int64_t) b.loc, '=', (int64_t) b.loc, out);
+	} else if (!b.has) {
+		unmapped_line(b, fb, ca, (int64_t) a.loc, '=', (int64_t) a.loc, out);
+		mapped_line(j, a, fa | 0x8, "=", nullptr, (int64_t) a.loc, 0, out);
+	} else if (!fail) {
+		fa |= 0x2;
+		fb |= 0x2;
+		const ReadView &fwd = a.reverse ? b : a, &rev = a.reverse ? a : b;      // exactly one mate is on the minus strand here
+		const ngm_b200_align_rec &rec = bt.recs[rev.r];
+		const int dist = (int) ((rev.loc + (uint64_t) rev.length - (uint64_t) rec.qstart - (uint64_t) rec.qend) - fwd.loc);
+		const int ffwd = (&fwd == &a) ? fa : fb, frev = (&fwd == &a) ? fb : fa;
+		mapped_line(j, rev, frev, "=", nullptr, (int64_t) fwd.loc, -dist, out);
+		mapped_line(j, fwd, ffwd | 0x20, "=", nullptr, (int64_t) rev.loc, dist, out);
+	} else {
+		if (a.reverse) fb |= 0x20;
+		if (b.reverse) fa |= 0x20;
+		mapped_line(j, b, fb, nullptr, ca, (int64_t) a.loc, 0, out);
+		mapped_line(j, a, fa, nullptr, cb, (int64_t) b.loc, 0, out);
+	}
+	text.append(scratch.data(), (size_t) (out.p - scratch.data()));
+}
+
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) int ngm_b200_format_sam(const ngm_b200_encref *ref, const ngm_b200_sam_opts *opts,
+		const ngm_b200_sam_batch *batch, char *out, size_t out_capacity, size_t *out_used) {
+	if (ref == nullptr || opts == nullptr || batch == nullptr || out_used == nullptr || (out == nullptr && out_capacity)) return NGM_B200_EINVAL;
+	const ngm_b200_sam_batch &b = *batch;
+	if (b.n_reads < 0 || (b.n_reads && (b.reads == nullptr || b.quals == nullptr || b.names == nullptr || b.best_pair == nullptr || b.mapq == nullptr ||
+			b.num_top == nullptr || b.max_hit == nullptr || b.recs == nullptr))) return NGM_B200_EINVAL;
+	const bool paired = b.pair_fail != nullptr;
+	if (paired && (b.n_reads & 1)) return NGM_B200_EINVAL;
+	const int units = paired ? b.n_reads / 2 : b.n_reads;
+	int threads = opts->threads > 0 ? opts->threads : (int) std::thread::hardware_concurrency();
+	threads = std::max(1, std::min(threads, std::max(1, units / 256)));
+	std::vector<std::string> parts((size_t) threads);
+	const Job job = { ref, opts, batch };
+	auto work = [&](int t) {
+		const int lo = (int) ((long long) units * t / threads), hi = (int) ((long long) units * (t + 1) / threads);
+		std::string &s = parts[(size_t) t];
+		s.reserve((size_t) (hi - lo) * (paired ? 2 : 1) * (size_t) (2 * b.stride + 160));
+		std::vector<char> scratch(4096);
+		for (int u = lo; u < hi; ++u) {
+			if (paired) fragment(job, u, s, scratch);
+			else single(job, u, s, scratch);
+		}
+	};
+	auto run_all = [&](auto fn) {
+		if (threads == 1) {
+			fn(0);
+		} else {
+			std::vector<std::thread> pool;
+			for (int t = 0; t < threads; ++t) pool.emplace_back(fn, t);
+			for (std::thread &t : pool) t.join();
+		}
+	};
+	run_all(work);
+	size_t total = 0;
+	std::vector<size_t> at((size_t) threads);
+	for (int t = 0; t < threads; ++t) {
+		at[(size_t) t] = total;
+		total += parts[(size_t) t].size();
+	}
+	*out_used = total;
+	if (total > out_capacity) return NGM_B200_ERANGE;
+	run_all([&](int t) { memcpy(out + at[(size_t) t], parts[(size_t) t].data(), parts[(size_t) t].size()); });      // every thread places (and first-touches) its own part
+	return b.n_reads;
+}

@@ -46,6 +46,18 @@ class PeParams(C.Structure):
                 ("fast_pairing", C.c_int32)]
 
 
+class SamOpts(C.Structure):
+    """ngm_b200_sam_opts (include/ngm_b200.h); defaults = src/config/Config.cpp:405-410,430-431."""
+    _fields_ = [("min_identity", C.c_float), ("min_residues", C.c_float), ("min_insert_size", C.c_int32), ("max_insert_size", C.c_int32), ("threads", C.c_int32)]
+
+
+class SamBatch(C.Structure):
+    """ngm_b200_sam_batch (include/ngm_b200.h)."""
+    _fields_ = [("n_reads", C.c_int32), ("stride", C.c_int32), ("reads", C.c_void_p), ("quals", C.c_void_p), ("names", C.POINTER(C.c_char_p)), ("pairs", C.c_void_p),
+                ("scores", C.c_void_p), ("best_pair", C.c_void_p), ("mapq", C.c_void_p), ("num_top", C.c_void_p), ("pair_fail", C.c_void_p), ("max_hit", C.c_void_p),
+                ("recs", C.c_void_p), ("strings", C.c_void_p)]
+
+
 class _CContigRec(C.Structure):
     _fields_ = [("start", C.c_uint64), ("length", C.c_uint32), ("name_len", C.c_uint32), ("name", C.c_char * 100)]
 
@@ -124,6 +136,7 @@ def load_library() -> C.CDLL:
                                        C.POINTER(C.c_size_t), C.c_void_p]
     lib.ngm_b200_cs_exact_reads.restype = C.c_uint64
     lib.ngm_b200_cs_exact_reads.argtypes = [C.c_void_p]
+    lib.ngm_b200_format_sam.argtypes = [C.c_void_p, C.POINTER(SamOpts), C.POINTER(SamBatch), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.ngm_b200_pe_configure.argtypes = [C.c_void_p, C.POINTER(PeParams)]
     lib.ngm_b200_pe_insert_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.ngm_b200_pe_deferred_fragments.argtypes = [C.c_void_p]

@@ -20,7 +20,9 @@ from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .cuda_sw import PAIR, CudaSW
+import ctypes as C
+
+from .cuda_sw import ALIGN_REC, PAIR, CudaSW, SamBatch, SamOpts, load_library
 
 COMP = bytes.maketrans(b"ACGT", b"TGCA")
 U64 = 2 ** 64 - 1
@@ -236,3 +238,38 @@ def sam_lines_paired(batch, reads: np.ndarray, names: Sequence[str], quals: Sequ
                 fa |= 0x20
             out += [_mapped_line(batch, b, encref, fb, ra, a.loc, 0), _mapped_line(batch, a, encref, fa, rb, b.loc, 0)]
     return out
+
+
+def format_sam(batch, reads: np.ndarray, names: Sequence[str], quals: Sequence[bytes], encref, paired: bool, min_identity: float = 0.65,
+               min_residues: float = 0.5, min_insert_size: int = 0, max_insert_size: int = 1000, threads: int = 0) -> bytes:
+    """The same lines as ``sam_lines`` / ``sam_lines_paired`` from the library's multi-threaded formatter (``ngm_b200_format_sam``): what a
+    C / C++ host calls.  ``encref``: an ``EncodedReference`` (the C struct is handed over as it is).  ``batch.recs`` / ``batch.heap`` as
+    ``ngm_b200_align_pairs`` returned them."""
+    lib = load_library()
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    n, stride = reads.shape
+    q = np.zeros((n, stride), np.uint8)
+    for i, ql in enumerate(quals):
+        q[i, : len(ql)] = np.frombuffer(ql, np.uint8)
+    name_arr = (C.c_char_p * n)(*[nm.encode() for nm in names])
+    keep = [np.ascontiguousarray(batch.pairs), np.ascontiguousarray(batch.scores, dtype=np.float32), np.ascontiguousarray(batch.best_pair, dtype=np.int32),
+            np.ascontiguousarray(batch.mapq, dtype=np.int32), np.ascontiguousarray(batch.num_top, dtype=np.int32),
+            np.ascontiguousarray(batch.pair_fail, dtype=np.int32) if paired else None, np.ascontiguousarray(batch.max_hit, dtype=np.float32),
+            np.ascontiguousarray(batch.recs), np.ascontiguousarray(batch.heap)]
+    assert keep[7].dtype == ALIGN_REC
+    ptr = lambda a: None if a is None else a.ctypes.data
+    sb = SamBatch(n, stride, reads.ctypes.data, q.ctypes.data, name_arr, ptr(keep[0]), ptr(keep[1]), ptr(keep[2]), ptr(keep[3]), ptr(keep[4]), ptr(keep[5]),
+                  ptr(keep[6]), ptr(keep[7]), ptr(keep[8]))
+    so = SamOpts(min_identity, min_residues, min_insert_size, max_insert_size, threads)
+    used = C.c_size_t(0)
+    cap = n * (2 * stride + 256) + 4096
+    for _ in range(2):
+        out = np.zeros(cap, np.uint8)
+        rc = lib.ngm_b200_format_sam(C.byref(encref.c), C.byref(so), C.byref(sb), out.ctypes.data, cap, C.byref(used))
+        if rc == -3:
+            cap = used.value + 16
+            continue
+        if rc < 0:
+            raise RuntimeError(f"ngm_b200_format_sam failed ({rc})")
+        return out[: used.value].tobytes()
+    raise RuntimeError("ngm_b200_format_sam: buffer sizing failed")

@@ -1,10 +1,8 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2d_bench_n2.json 2> gpurun_out/r2d_bench_n2.err
-tail -c 400 gpurun_out/r2d_bench_n2.err; python - <<'PY'
+python -m pytest tests/test_gpu_pipeline_vs_ngm.py -x -q 2>&1 | tail -5 > gpurun_out/r2e_tests.log
+python bench.py --steps 5 --no-e2e > gpurun_out/r2e_bench.json 2> gpurun_out/r2e_bench.err
+cat gpurun_out/r2e_tests.log; tail -c 300 gpurun_out/r2e_bench.err; python - <<'PY'
 import json
-d = json.load(open("gpurun_out/r2d_bench_n2.json"))
-print(d["value"], d["n_gpus"], d["ms_per_step"], d["e2e"]["value"], d["scaling"])
+d = json.load(open("gpurun_out/r2e_bench.json"))
 cs = d["candidate_search"]
-print({k: cs.get(k) for k in ("cs_reads_per_s", "pipeline_reads_per_s", "parity_sample", "error")})
-pe = cs.get("paired_end")
-print({k: pe.get(k) for k in ("pipeline_reads_per_s", "select_pairs_ms", "parity_sample", "error")} if pe else None)
+print(d["value"], cs["cs_reads_per_s"], cs["pipeline_reads_per_s"], cs.get("sam_format"), cs["roofline"])
 PY

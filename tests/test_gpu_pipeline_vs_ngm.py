@@ -54,6 +54,8 @@ def test_sam_identical_to_ngm(ref_len, n_reads, read_len, extra):
         assert "%f" % got_sens == "%f" % logged and 0.3 < got_sens < 0.9
     batch = pipeline.map_reads(sw, reads, mode)
     got = sorted(pipeline.sam_lines(sw, batch, reads, names, quals, ref, cor))
+    native = sorted(pipeline.format_sam(batch, reads, names, quals, ref, False).decode().splitlines())      # ngm_b200_format_sam (C++, threads)
+    assert native == got
     assert len(got) == len(want)
     bad = [(g, w) for g, w in zip(got, want) if g != w]
     assert not bad, f"{len(bad)} of {len(want)} SAM lines differ, first:\n{bad[0][0]}\n{bad[0][1]}"
@@ -85,12 +87,14 @@ def test_paired_sam_identical_to_ngm(ref_len, n_frags, read_len, seed, extra):
     sw.set_reference(ref.packed, ref.concat_len)
     sw.cs_build_index([(c[1], c[2]) for c in ref.contigs], sw.cs_params(kmer=13, sensitivity=0.5))
     sw.pe_configure(fast_pairing=1 if "--fast-pairing" in extra else 0)
-    got, n = [], len(names)
+    got, native, n = [], [], len(names)
     step = (n // 3 + 1) & ~1
     for lo in range(0, n, step):
         hi = min(n, lo + step)
         batch = pipeline.map_pairs(sw, reads[lo:hi], mode)
         got += pipeline.sam_lines_paired(batch, reads[lo:hi], names[lo:hi], quals[lo:hi], ref, cor)
+        native += pipeline.format_sam(batch, reads[lo:hi], names[lo:hi], quals[lo:hi], ref, True).decode().splitlines()
+    assert native == got                                # ngm_b200_format_sam (C++, threads): same lines, same order
     got.sort()
     assert len(got) == len(want)
     bad = [(g, w) for g, w in zip(got, want) if g != w]

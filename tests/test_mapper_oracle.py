@@ -63,6 +63,20 @@ class LaidOutReference:
             return None
         return i - 1, pos - self.starts[i - 1]
 
+    def as_encoded_reference(self):
+        """The same reference as the C struct ngm_b200_format_sam takes (ngm_b200_encref)."""
+        import ctypes as C
+        from types import SimpleNamespace
+        from nextgenmap_b200.host.cuda_sw import _CContig, _CEncRef
+        arr = (_CContig * len(self.contigs))()
+        for i, (nm, st, ln) in enumerate(self.contigs):
+            arr[i].start, arr[i].length, arr[i].name_len, arr[i].name = st, ln, len(nm), nm.encode()
+        c = _CEncRef()
+        c.concat_len, c.packed_bytes, c.n_contigs = self.concat_len, len(self.packed), len(self.contigs)
+        c.packed = self.packed.ctypes.data_as(type(c.packed))
+        c.contigs = C.cast(arr, type(c.contigs))
+        return SimpleNamespace(c=c, _keep=(arr, self.packed))
+
     def close(self):
         pass
 
@@ -130,3 +144,45 @@ def test_single_end_sam_identical_to_ngm():
         want = [ln for ln in e2e.run("ref", d, threads=2, extra=["-s", "0.5"]) if not ln.startswith("@")]
         got, _ = oracle_sam(d, 100, 0, 0.5, False)
     diff(got, want)
+
+
+def with_heap(batch):
+    """The oracle batch in the layout ngm_b200_align_pairs returns: ALIGN_REC records + one string heap (CIGAR then MD per read)."""
+    from nextgenmap_b200.host.cuda_sw import ALIGN_REC
+    n = len(batch.best_pair)
+    recs = np.zeros(n, dtype=ALIGN_REC)
+    heap = bytearray()
+    for r in range(n):
+        for f in ("position_offset", "qstart", "qend", "nm", "identity", "score"):
+            recs[r][f] = batch.recs[r][f]
+        if batch.best_pair[r] >= 0:
+            cig, md = batch.strings(r)
+            recs[r]["str_off"], recs[r]["cigar_len"], recs[r]["md_len"] = len(heap), len(cig), len(md)
+            heap += cig + md
+    batch.recs = recs
+    batch.heap = np.frombuffer(bytes(heap) + b"\0", np.uint8)
+    return batch
+
+
+@pytest.mark.parametrize("paired", [False, True])
+def test_native_sam_formatter_equals_host_mirror(paired):
+    """ngm_b200_format_sam (C++, multi-threaded; host only) against the Python mirror that is checked against NGM's own SAM above."""
+    from nextgenmap_b200.host import pipeline
+    with tempfile.TemporaryDirectory(prefix="fmt_") as td:
+        d = Path(td)
+        if paired:
+            e2e.write_paired_inputs(d, ref_len=300_000, n_frags=600, read_len=100, seed=77)
+        else:
+            e2e.write_inputs(d, ref_len=300_000, n_reads=1200, read_len=100, seed=78, indel_reads=0.2)
+        ref = LaidOutReference(d / "ref.fa")
+        names, seqs, quals = read_fastq(d / "reads.fq", paired)
+    reads = rows(seqs, 102)
+    ix = cs_port.Index(ref.packed, ref.concat_len, [(c[1], c[2]) for c in ref.contigs], k=13)
+    batch = with_heap(mapper_port.map_batch(ref.packed, ref.concat_len, ix, reads, 102, 20, 0, 0.5, mapper_port.Selector(), paired=paired))
+    ix.close()
+    want = pipeline.sam_lines_paired(batch, reads, names, quals, ref, 20) if paired else pipeline.sam_lines(None, batch, reads, names, quals, ref, 20)
+    for threads in (1, 3):
+        got = pipeline.format_sam(batch, reads, names, quals, ref.as_encoded_reference(), paired, threads=threads).decode().splitlines()
+        assert got == want
+    if paired:
+        assert sorted(want) == gzip.open(GOLD / "pe_l100.sam.gz", "rt").read().splitlines()
