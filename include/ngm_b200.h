@@ -293,6 +293,30 @@ int64_t ngm_b200_pe_deferred_fragments(ngm_b200_ctx *ctx);
  * all batches since ngm_b200_pe_configure -- the reference's result with one CS thread.  Enqueued on `stream`, not synchronised. */
 int ngm_b200_dev_select_pairs(ngm_b200_ctx *ctx, int n_reads, const void *d_cand_begin, const void *d_pairs, const void *d_scores, uint32_t n_pairs,
 		void *d_best_pair, void *d_mapq, void *d_num_top, void *d_pair_fail, void *stream);
+/* -- a whole batch in one call ------------------------------------------------------------------------------ */
+/* Host arrays the caller owns; n = rows of the batch. */
+typedef struct ngm_b200_map_result {
+	int32_t *cand_begin;        /* n + 1 offsets into pairs / scores */
+	ngm_b200_pair *pairs;       /* `capacity` candidates in the reference's order (ngm_b200_cs_search) */
+	float *scores;              /* `capacity` BatchScore results */
+	size_t capacity;
+	size_t n_candidates;        /* out: candidates found (> capacity: NGM_B200_ERANGE, repeat with larger arrays) */
+	int32_t *best_pair;         /* n: the candidate handed to alignment or -1 */
+	int32_t *mapq;              /* n */
+	int32_t *num_top;           /* n: MappedRead::numTopScores */
+	int32_t *pair_fail;         /* n, paired batches only */
+	float *max_hit;             /* n: MappedRead::s */
+	ngm_b200_align_rec *recs;   /* n: alignment of read r's selected candidate (score -1 when there is none) */
+	char *strings;              /* string heap of `str_capacity` bytes */
+	size_t str_capacity;
+	size_t str_used;            /* out: bytes needed (> str_capacity: NGM_B200_ERANGE) */
+} ngm_b200_map_result;
+/* CS::RunBatch -> ScoreBuffer::DoRun (BatchScore, top1SE or top1PE) -> AlignmentBuffer::DoRun (BatchAlign) for one batch of reads, from
+ * host buffers to host buffers (CS.cpp:340-436, ScoreBuffer.cpp:80-277,365-502, AlignmentBuffer.cpp:64-147).  Needs ngm_b200_set_reference
+ * and a prefix table (ngm_b200_cs_build_index / cs_load_index); paired != 0 additionally ngm_b200_pe_configure, rows 2f / 2f + 1 = mates.
+ * Synchronous.  The result feeds ngm_b200_format_sam (its ngm_b200_sam_batch takes the same arrays). */
+int ngm_b200_map_batch(ngm_b200_ctx *ctx, const char *reads, int n_reads, int stride, int mode, int paired, ngm_b200_map_result *result);
+
 /* -- SAM records of a batch ------------------------------------------------------------------ */
 /* Output filters and pair limits (src/config/Config.cpp:405-410,430-431; GenericReadWriter.h:204-214,263-283). */
 typedef struct ngm_b200_sam_opts {

@@ -65,6 +65,8 @@ struct CsState;                                 // candidate search: index + scr
 void cs_release(CsState *cs);
 struct PeState;                                 // paired-end selection: parameters, running insert-size sums, scratch (ngm_select.cu)
 void pe_release(PeState *pe);
+struct MapState;                                // scratch of ngm_b200_map_batch (ngm_map.cu)
+void map_release(MapState *m);
 
 }  // namespace ngm
 
@@ -95,4 +97,5 @@ struct ngm_b200_ctx {
 	bool have_ref = false;
 	ngm::CsState *cs = nullptr;
 	ngm::PeState *pe = nullptr;
+	ngm::MapState *map = nullptr;
 };

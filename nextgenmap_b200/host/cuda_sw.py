@@ -58,6 +58,13 @@ class SamBatch(C.Structure):
                 ("recs", C.c_void_p), ("strings", C.c_void_p)]
 
 
+class MapResult(C.Structure):
+    """ngm_b200_map_result (include/ngm_b200.h)."""
+    _fields_ = [("cand_begin", C.c_void_p), ("pairs", C.c_void_p), ("scores", C.c_void_p), ("capacity", C.c_size_t), ("n_candidates", C.c_size_t),
+                ("best_pair", C.c_void_p), ("mapq", C.c_void_p), ("num_top", C.c_void_p), ("pair_fail", C.c_void_p), ("max_hit", C.c_void_p),
+                ("recs", C.c_void_p), ("strings", C.c_void_p), ("str_capacity", C.c_size_t), ("str_used", C.c_size_t)]
+
+
 class _CContigRec(C.Structure):
     _fields_ = [("start", C.c_uint64), ("length", C.c_uint32), ("name_len", C.c_uint32), ("name", C.c_char * 100)]
 
@@ -136,6 +143,7 @@ def load_library() -> C.CDLL:
                                        C.POINTER(C.c_size_t), C.c_void_p]
     lib.ngm_b200_cs_exact_reads.restype = C.c_uint64
     lib.ngm_b200_cs_exact_reads.argtypes = [C.c_void_p]
+    lib.ngm_b200_map_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(MapResult)]
     lib.ngm_b200_format_sam.argtypes = [C.c_void_p, C.POINTER(SamOpts), C.POINTER(SamBatch), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.ngm_b200_pe_configure.argtypes = [C.c_void_p, C.POINTER(PeParams)]
     lib.ngm_b200_pe_insert_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]

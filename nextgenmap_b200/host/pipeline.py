@@ -22,7 +22,7 @@ import numpy as np
 
 import ctypes as C
 
-from .cuda_sw import ALIGN_REC, PAIR, CudaSW, SamBatch, SamOpts, load_library
+from .cuda_sw import ALIGN_REC, PAIR, CudaSW, MapResult, SamBatch, SamOpts, load_library
 
 COMP = bytes.maketrans(b"ACGT", b"TGCA")
 U64 = 2 ** 64 - 1
@@ -104,6 +104,35 @@ def map_pairs(sw: CudaSW, reads: np.ndarray, mode: int = 0) -> MappedBatch:
     best, mq, nt, pf = (t.cpu().numpy() for t in out)
     recs, heap, strings = _align_winners(sw, mode, n, pairs, best)
     return MappedBatch(begin, pairs, scores, max_hit, best, mq, nt, recs, heap, strings, pf)
+
+
+def map_batch(sw: CudaSW, reads: np.ndarray, mode: int = 0, paired: bool = False) -> MappedBatch:
+    """The same as ``map_reads`` / ``map_pairs`` through the one-call entry point ``ngm_b200_map_batch`` (host buffers in, host buffers
+    out; candidates, scores and winners never leave the device in between)."""
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    n, stride = reads.shape
+    cap, scap = max(1024, 4 * n), n * 64 + 4096
+    for _ in range(3):
+        begin = np.zeros(n + 1, np.int32)
+        pairs, scores = np.zeros(cap, dtype=PAIR), np.zeros(cap, np.float32)
+        best, mq, nt, pf = (np.zeros(n, np.int32) for _ in range(4))
+        mh = np.zeros(n, np.float32)
+        recs, heap = np.zeros(n, dtype=ALIGN_REC), np.zeros(scap, np.uint8)
+        res = MapResult(begin.ctypes.data, pairs.ctypes.data, scores.ctypes.data, cap, 0, best.ctypes.data, mq.ctypes.data, nt.ctypes.data,
+                        pf.ctypes.data if paired else None, mh.ctypes.data, recs.ctypes.data, heap.ctypes.data, scap, 0)
+        rc = sw.lib.ngm_b200_map_batch(sw.ctx, reads.ctypes.data, n, stride, mode, 1 if paired else 0, C.byref(res))
+        if rc == -3:                                 # a paired batch that is repeated must start from the same insert-size sums: callers
+            cap = max(cap, int(res.n_candidates) + 16)          # size generously or reconfigure (pe_configure) before repeating
+            scap = max(scap, int(res.str_used) + 16)
+            continue
+        sw._check(rc)
+        total, raw = int(res.n_candidates), heap[: int(res.str_used)].tobytes()
+
+        def strings(r: int):
+            o, cl, ml = int(recs[r]["str_off"]), int(recs[r]["cigar_len"]), int(recs[r]["md_len"])
+            return raw[o: o + cl], raw[o + cl: o + cl + ml]
+        return MappedBatch(begin, pairs[:total], scores[:total], mh, best, mq, nt, recs, heap[: int(res.str_used) + 1], strings, pf if paired else None)
+    raise RuntimeError("ngm_b200_map_batch: buffer sizing failed")
 
 
 def _xi(identity: float) -> str:

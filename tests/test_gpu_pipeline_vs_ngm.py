@@ -56,6 +56,8 @@ def test_sam_identical_to_ngm(ref_len, n_reads, read_len, extra):
     got = sorted(pipeline.sam_lines(sw, batch, reads, names, quals, ref, cor))
     native = sorted(pipeline.format_sam(batch, reads, names, quals, ref, False).decode().splitlines())      # ngm_b200_format_sam (C++, threads)
     assert native == got
+    one_call = pipeline.map_batch(sw, reads, mode)                 # ngm_b200_map_batch: the whole batch in one C call
+    assert sorted(pipeline.format_sam(one_call, reads, names, quals, ref, False).decode().splitlines()) == got
     assert len(got) == len(want)
     bad = [(g, w) for g, w in zip(got, want) if g != w]
     assert not bad, f"{len(bad)} of {len(want)} SAM lines differ, first:\n{bad[0][0]}\n{bad[0][1]}"
@@ -95,6 +97,12 @@ def test_paired_sam_identical_to_ngm(ref_len, n_frags, read_len, seed, extra):
         got += pipeline.sam_lines_paired(batch, reads[lo:hi], names[lo:hi], quals[lo:hi], ref, cor)
         native += pipeline.format_sam(batch, reads[lo:hi], names[lo:hi], quals[lo:hi], ref, True).decode().splitlines()
     assert native == got                                # ngm_b200_format_sam (C++, threads): same lines, same order
+    sw.pe_configure(fast_pairing=1 if "--fast-pairing" in extra else 0)        # again from the start, through ngm_b200_map_batch
+    one_call = []
+    for lo in range(0, n, step):
+        hi = min(n, lo + step)
+        one_call += pipeline.format_sam(pipeline.map_batch(sw, reads[lo:hi], mode, paired=True), reads[lo:hi], names[lo:hi], quals[lo:hi], ref, True).decode().splitlines()
+    assert one_call == got
     got.sort()
     assert len(got) == len(want)
     bad = [(g, w) for g, w in zip(got, want) if g != w]
