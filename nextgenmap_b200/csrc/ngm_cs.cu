@@ -27,7 +27,7 @@ struct CsState {
 	uint32_t n_prefix = 0, table_len = 0;
 	int max_kfreq = 0;
 	bool ready = false;
-	DevBuf d_tabu, d_table, d_weight, d_both;
+	DevBuf d_tabu, d_table, d_weight, d_both, d_table2;
 	// search scratch
 	DevBuf d_meta, d_heap, d_cursor, d_slow_list, d_slow_count, d_counts, d_begin, d_scan_tmp, d_pairs, d_votes;
 	DevBuf d_ex_tables, d_ex_rlists, d_ex_gens;
@@ -39,7 +39,7 @@ struct CsState {
 
 void cs_release(CsState *cs) {
 	if (cs == nullptr) return;
-	DevBuf *db[] = { &cs->d_tabu, &cs->d_table, &cs->d_weight, &cs->d_both, &cs->d_meta, &cs->d_heap, &cs->d_cursor, &cs->d_slow_list, &cs->d_slow_count,
+	DevBuf *db[] = { &cs->d_tabu, &cs->d_table, &cs->d_weight, &cs->d_both, &cs->d_table2, &cs->d_meta, &cs->d_heap, &cs->d_cursor, &cs->d_slow_list, &cs->d_slow_count,
 			&cs->d_counts, &cs->d_begin, &cs->d_scan_tmp, &cs->d_pairs, &cs->d_votes, &cs->d_ex_tables, &cs->d_ex_rlists, &cs->d_ex_gens };
 	for (DevBuf *b : db) b->release();
 	cs->h_total.release();
@@ -131,11 +131,27 @@ void contig_runs(uint64_t start, uint64_t len, uint64_t real, const std::vector<
 
 int finish_index(ngm_b200_ctx *c, CsState *cs, unsigned long long s1, unsigned long long s2) {
 	cs->max_kfreq = cs->hp.max_kfreq > 0 ? cs->hp.max_kfreq : max_kfreq_from_sums(cs->n_prefix, s1, s2);
-	CU(cs->d_both.ensure((size_t) cs->n_prefix * sizeof(uint4)));
-	cs_both_kernel<<<(cs->n_prefix + 255) / 256, 256, 0, c->stream>>>(cs->d_tabu.as<uint32_t>(), cs->n_prefix, cs->k, cs->d_both.as<uint4>());
-	c->launches += 1;
+	// the search's copy: 16-byte entries + positions ordered by k-mer pair (cs_pair_copy_kernel)
+	const uint32_t NP = cs->n_prefix;
+	cudaStream_t st = c->stream;
+	DevBuf d_size, d_off2, d_tmp;
+	CU(cs->d_both.ensure((size_t) NP * sizeof(uint4)));
+	CU(cs->d_table2.ensure((size_t) cs->table_len * 4 + 4));
+	CU(d_size.ensure((size_t) NP * 4));
+	CU(d_off2.ensure((size_t) NP * 4));
+	cs_pair_size_kernel<<<(NP + 255) / 256, 256, 0, st>>>(cs->d_tabu.as<uint32_t>(), NP, cs->k, d_size.as<uint32_t>());
+	size_t tmp_bytes = 0;
+	CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_size.as<uint32_t>(), d_off2.as<uint32_t>(), (int) NP, st));
+	CU(d_tmp.ensure(tmp_bytes));
+	CU(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, d_size.as<uint32_t>(), d_off2.as<uint32_t>(), (int) NP, st));
+	cs_pair_copy_kernel<<<(NP + 255) / 256, 256, 0, st>>>(cs->d_tabu.as<uint32_t>(), NP, cs->k, d_off2.as<uint32_t>(), cs->d_table.as<uint32_t>(),
+			cs->d_table2.as<uint32_t>(), cs->d_both.as<uint4>());
+	c->launches += 4;
 	CU(cudaGetLastError());
-	CU(cudaStreamSynchronize(c->stream));
+	CU(cudaStreamSynchronize(st));
+	d_size.release();
+	d_off2.release();
+	d_tmp.release();
 	cs->ready = true;
 	return NGM_B200_OK;
 }
@@ -334,7 +350,7 @@ int ngm_b200_dev_cs_search(ngm_b200_ctx *c, const void *d_ascii_reads, int n_rea
 	CsDev P;
 	P.tabu = cs->d_tabu.as<uint32_t>();
 	P.both = cs->d_both.as<uint4>();
-	P.table = cs->d_table.as<uint32_t>();
+	P.table = cs->d_table2.as<uint32_t>();
 	P.k = cs->k;
 	P.bin_shift = cs->bin_shift;
 	P.max_kfreq = cs->max_kfreq;

@@ -36,7 +36,8 @@ namespace ngm {
 
 struct CsDev {
 	const uint32_t *tabu;     // [4^k + 1]
-	const uint4 *both;        // [4^k] {forward list start, length, reverse-complement list start, length}: one 16-byte load per k-mer
+	const uint4 *both;        // [4^k] {forward list start, length, reverse-complement list start, length} in `table`: one 16-byte load per k-mer
+	                          // (`table` here is the search's pair-ordered copy, see cs_pair_copy_kernel)
 	const uint32_t *table;
 	int k, bin_shift, max_kfreq, max_cmrs;
 	float sensitivity, kmer_min;
@@ -268,19 +269,40 @@ __device__ __forceinline__ bool cs_lookup(const CsDev &P, uint32_t prefix, CsLis
 	return (int) (L.fc + L.rc) < P.max_kfreq;              // cur->refTotal < maxPrefixFreq, CS.cpp:122
 }
 
-// both[p] from tabu: what GetRefEntry assembles from Index[p], Index[p + 1], Index[rc(p)], Index[rc(p) + 1] (two random 8-byte reads per
-// k-mer of every read) is laid down once per index, so that the search reads one aligned 16-byte entry per k-mer.
-__global__ void cs_both_kernel(const uint32_t *__restrict__ tabu, uint32_t n_prefix, int k, uint4 *__restrict__ both) {
+// The search's own copy of the index.  GetRefEntry assembles a k-mer's two lists from Index[p], Index[p + 1], Index[rc(p)], Index[rc(p) + 1]
+// (two random 8-byte reads per k-mer of every read) and the lists of p and rc(p) lie wherever their prefixes put them.  Laid down once per
+// index: table2 holds, for every pair {p, rc(p)}, the list of the smaller prefix followed by the list of the larger one, and both[p] =
+// {start of p's list, length, start of rc(p)'s list, length} in table2 -- one aligned 16-byte entry and ONE contiguous range of positions
+// per k-mer of a read.  tabu / table keep the reference's layout (export, file format).
+__device__ __forceinline__ uint32_t cs_list_len(const uint32_t *__restrict__ tabu, uint32_t p) {
+	const uint32_t a0 = tabu[p];
+	return (a0 >> 31) ? (tabu[p + 1] & 0x7FFFFFFFu) - (a0 & 0x7FFFFFFFu) : 0u;
+}
+
+__global__ void cs_pair_size_kernel(const uint32_t *__restrict__ tabu, uint32_t n_prefix, int k, uint32_t *__restrict__ size) {
 	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= n_prefix) return;
-	const uint32_t rcp = cs_revcomp(p, k);
-	const uint32_t a0 = tabu[p], a1 = tabu[p + 1], b0 = tabu[rcp], b1 = tabu[rcp + 1];
-	uint4 e;
-	e.x = a0 & 0x7FFFFFFFu;
-	e.y = (a0 >> 31) ? (a1 & 0x7FFFFFFFu) - e.x : 0u;
-	e.z = b0 & 0x7FFFFFFFu;
-	e.w = (b0 >> 31) ? (b1 & 0x7FFFFFFFu) - e.z : 0u;
-	both[p] = e;
+	const uint32_t c = cs_revcomp(p, k);
+	size[p] = p <= c ? cs_list_len(tabu, p) + (c != p ? cs_list_len(tabu, c) : 0u) : 0u;
+}
+
+__global__ void cs_pair_copy_kernel(const uint32_t *__restrict__ tabu, uint32_t n_prefix, int k, const uint32_t *__restrict__ off2,
+		const uint32_t *__restrict__ table, uint32_t *__restrict__ table2, uint4 *__restrict__ both) {
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= n_prefix) return;
+	const uint32_t c = cs_revcomp(p, k);
+	const uint32_t n = cs_list_len(tabu, p), nc = cs_list_len(tabu, c);
+	uint32_t dest_p, dest_c;
+	if (p <= c) {
+		dest_p = off2[p];
+		dest_c = c != p ? dest_p + n : dest_p;
+	} else {
+		dest_c = off2[c];
+		dest_p = dest_c + nc;
+	}
+	const uint32_t src = tabu[p] & 0x7FFFFFFFu;
+	for (uint32_t i = 0; i < n; ++i) table2[dest_p + i] = table[src + i];
+	both[p] = make_uint4(dest_p, n, dest_c, nc);
 }
 
 // ---------------------------------------------------------------------------------------------------------
