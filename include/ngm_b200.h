@@ -279,6 +279,8 @@ typedef struct ngm_b200_pe_params {
 int ngm_b200_pe_configure(ngm_b200_ctx *ctx, const ngm_b200_pe_params *params);
 /* pairDistSum / pairDistCount after the batches selected so far (synchronises the device). */
 int ngm_b200_pe_insert_stats(ngm_b200_ctx *ctx, int64_t *dist_sum, int64_t *dist_count);
+/* Installs sums read earlier (a batch that has to be repeated, a run that is resumed). */
+int ngm_b200_pe_set_insert_stats(ngm_b200_ctx *ctx, int64_t dist_sum, int64_t dist_count);
 /* Fragments of the last ngm_b200_dev_select_pairs call that met equal pair scores and were therefore decided one after the other
  * (diagnostics; synchronises the device). */
 int64_t ngm_b200_pe_deferred_fragments(ngm_b200_ctx *ctx);

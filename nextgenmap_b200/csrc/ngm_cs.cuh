@@ -314,15 +314,19 @@ __global__ void cs_pair_copy_kernel(const uint32_t *__restrict__ tabu, uint32_t 
 // false positives) enter a small exact table (double hashing, load < 0.2).  A second sweep over the hits -- kept
 // in shared memory as 32-bit bins -- adds the one hit per repeated bin that set the bit and was therefore not counted.
 //
-//   A  every thread takes one k-mer of the read: validity, code, the two index lookups -> list descriptors in
-//      shared memory; block-wide exclusive scan of the list lengths = sequence number of every hit
-//   B  every warp takes a k-mer: lanes load one position each (fwd list then rev list: one coalesced ~60-byte
-//      read per list), eight k-mers in flight per warp; bitmap test, insert of repeats, bins[] <- hit
-//   C  second sweep: first hits of the table's bins
-//   D  maximum, threshold, accepted entries (table scan: 2048 slots)
+//   A  every thread takes one k-mer of the read: validity, code, ONE 16-byte index entry (both strands' lists); block-wide scan over
+//      (list length | "has hits" << 20) = number of every hit in the reference's order + rank of every k-mer that has hits;
+//      km[rank] = {first hit number, list starts, forward length | k-mer}, rbase / bstart = chunk -> rank maps
+//   B  the hits are swept in flat chunks of 32 consecutive hit numbers, eight chunks in flight per warp: a lane's k-mer is
+//      km[rbase[chunk] + popc(bstart[chunk] & lanes_below)]; position load, bitmap test, bins[] <- hit; the hits that found their bit
+//      set are queued (one slot reservation per warp and batch)
+//   B2 the queue enters the exact table, one hit per thread
+//   C  the vote that set the bit is missing from every table entry: looked up only for the entries that can still reach the
+//      threshold (<= kCsMaxRes bins in registers), or for all of them where that is needed (phase E, path J, sensitivity estimate)
+//   D  maximum, threshold, accepted entries
 //   E  only if more than one entry is accepted: the order of the list (see the header of this file)
-// Reads whose single-vote bins can pass (threshold <= 1: nothing aligns well), with more hits than MAXH or a crowded
-// table go to the exact kernel.
+//   J  threshold <= 1 (every bin is a candidate): the bins in first-hit order
+// Reads with more hits than MAXH, a crowded queue / table, a zero threshold or a 64-bit wrap-around go to the exact kernel.
 // ---------------------------------------------------------------------------------------------------------
 enum CsExactReason { kCsWhyHits = 0, kCsWhyWrap, kCsWhyQueue, kCsWhyTable, kCsWhyMulti, kCsWhyZeroThr, kCsWhyAccepted, kCsWhyItems, kCsWhyOrder, kCsWhyCount };
 constexpr int kCsRepWords = 512;                               // 16384 "repeated" bits; the "seen" bitmap has max(65536, 32 x T2) bits

@@ -71,6 +71,8 @@ int ngm_b200_map_batch(ngm_b200_ctx *c, const char *reads, int n_reads, int stri
 		rc = ngm_b200_dev_score_pairs(c, mode, (int) total, m->d_pairs.p, m->d_scores.p, st);
 		if (rc < 0) return rc;
 	}
+	int64_t pe_sum = 0, pe_count = 0;                          // a batch that has to be repeated must start from the same insert-size sums
+	if (paired && (rc = ngm_b200_pe_insert_stats(c, &pe_sum, &pe_count)) < 0) return rc;
 	if (paired) rc = ngm_b200_dev_select_pairs(c, n_reads, m->d_begin.p, m->d_pairs.p, m->d_scores.p, (uint32_t) total, m->d_best.p, m->d_mapq.p, m->d_ntop.p, m->d_pfail.p, st);
 	else rc = ngm_b200_dev_select_top1_ex(c, n_reads, m->d_begin.p, m->d_scores.p, m->d_best.p, m->d_mapq.p, m->d_ntop.p, st);
 	if (rc < 0) return rc;
@@ -93,7 +95,10 @@ int ngm_b200_map_batch(ngm_b200_ctx *c, const char *reads, int n_reads, int stri
 	CU(cudaMemcpyAsync(res->recs, m->d_recs.p, n * sizeof(ngm_b200_align_rec), cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
 	res->str_used = used;
-	if ((size_t) used > res->str_capacity) return fail(NGM_B200_ERANGE, "string heap too small: %u bytes needed", used);
+	if ((size_t) used > res->str_capacity) {
+		if (paired) ngm_b200_pe_set_insert_stats(c, pe_sum, pe_count);
+		return fail(NGM_B200_ERANGE, "string heap too small: %u bytes needed", used);
+	}
 	if (used) CU(cudaMemcpy(res->strings, m->d_strings.p, used, cudaMemcpyDeviceToHost));
 	return n_reads;
 }

@@ -427,6 +427,16 @@ int ngm_b200_pe_insert_stats(ngm_b200_ctx *c, int64_t *dist_sum, int64_t *dist_c
 	return NGM_B200_OK;
 }
 
+int ngm_b200_pe_set_insert_stats(ngm_b200_ctx *c, int64_t dist_sum, int64_t dist_count) {
+	if (c == nullptr || c->pe == nullptr || !c->pe->have_state) return fail(NGM_B200_ESTATE, "ngm_b200_pe_configure must come first");
+	if (dist_count <= 0) return fail(NGM_B200_EINVAL, "pairDistCount starts at 1");
+	CU(cudaSetDevice(c->device));
+	CU(cudaDeviceSynchronize());
+	const long long st[2] = { (long long) dist_sum, (long long) dist_count };
+	CU(cudaMemcpy(c->pe->d_state.p, st, sizeof(st), cudaMemcpyHostToDevice));
+	return NGM_B200_OK;
+}
+
 int64_t ngm_b200_pe_deferred_fragments(ngm_b200_ctx *c) {
 	if (c == nullptr || c->pe == nullptr || c->pe->d_nlist.p == nullptr) return fail(NGM_B200_ESTATE, "no paired selection yet");
 	CU(cudaSetDevice(c->device));

@@ -106,13 +106,13 @@ def map_pairs(sw: CudaSW, reads: np.ndarray, mode: int = 0) -> MappedBatch:
     return MappedBatch(begin, pairs, scores, max_hit, best, mq, nt, recs, heap, strings, pf)
 
 
-def map_batch(sw: CudaSW, reads: np.ndarray, mode: int = 0, paired: bool = False) -> MappedBatch:
+def map_batch(sw: CudaSW, reads: np.ndarray, mode: int = 0, paired: bool = False, capacity: int = 0, heap_bytes: int = 0) -> MappedBatch:
     """The same as ``map_reads`` / ``map_pairs`` through the one-call entry point ``ngm_b200_map_batch`` (host buffers in, host buffers
     out; candidates, scores and winners never leave the device in between)."""
     reads = np.ascontiguousarray(reads, dtype=np.uint8)
     n, stride = reads.shape
-    cap, scap = max(1024, 4 * n), n * 64 + 4096
-    for _ in range(3):
+    cap, scap = capacity or max(1024, 4 * n), heap_bytes or n * 64 + 4096
+    for _ in range(4):
         begin = np.zeros(n + 1, np.int32)
         pairs, scores = np.zeros(cap, dtype=PAIR), np.zeros(cap, np.float32)
         best, mq, nt, pf = (np.zeros(n, np.int32) for _ in range(4))
@@ -121,8 +121,8 @@ def map_batch(sw: CudaSW, reads: np.ndarray, mode: int = 0, paired: bool = False
         res = MapResult(begin.ctypes.data, pairs.ctypes.data, scores.ctypes.data, cap, 0, best.ctypes.data, mq.ctypes.data, nt.ctypes.data,
                         pf.ctypes.data if paired else None, mh.ctypes.data, recs.ctypes.data, heap.ctypes.data, scap, 0)
         rc = sw.lib.ngm_b200_map_batch(sw.ctx, reads.ctypes.data, n, stride, mode, 1 if paired else 0, C.byref(res))
-        if rc == -3:                                 # a paired batch that is repeated must start from the same insert-size sums: callers
-            cap = max(cap, int(res.n_candidates) + 16)          # size generously or reconfigure (pe_configure) before repeating
+        if rc == -3:                                 # (the library puts the insert-size sums of a paired run back before it reports this)
+            cap = max(cap, int(res.n_candidates) + 16)
             scap = max(scap, int(res.str_used) + 16)
             continue
         sw._check(rc)
