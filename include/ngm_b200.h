@@ -350,6 +350,12 @@ typedef struct ngm_b200_sam_batch {
  * multi-threaded.  *out_used receives the bytes needed; NGM_B200_ERANGE if that exceeds out_capacity (nothing is written then). */
 int ngm_b200_format_sam(const ngm_b200_encref *ref, const ngm_b200_sam_opts *opts, const ngm_b200_sam_batch *batch, char *out, size_t out_capacity,
 		size_t *out_used);
+/* Single-end selection with "topn" > 1 (ScoreBuffer::topNSE, ScoreBuffer.cpp:279-330; `-n`, `--strata`): the candidates are sorted by score
+ * (std::sort's order of equal scores included); sel[r * topn + j], j < n_sel[r], = the candidates handed to alignment, best first (-1 beyond
+ * n_sel[r]); mapq from the two best scores; num_top = candidates sharing the best score.  Under strata a read with more than topn equally
+ * good candidates keeps none.  topn = 1 runs take ngm_b200_dev_select_top1 (the reference's top1SE differs: no sort, first of equals). */
+int ngm_b200_dev_select_topn(ngm_b200_ctx *ctx, int n_reads, const void *d_cand_begin, const void *d_scores, uint32_t n_pairs, int topn, int strata,
+		void *d_sel, void *d_n_sel, void *d_mapq, void *d_num_top, void *stream);
 /* Device-pointer form of ngm_b200_cs_search: enqueued on `stream`, not synchronised; the caller checks
  * cand_begin[n_reads] <= capacity afterwards.  d_votes / d_max_hit may be NULL. */
 int ngm_b200_dev_cs_search(ngm_b200_ctx *ctx, const void *d_ascii_reads, int n_reads, int stride, int mode_flags, void *d_cand_begin,

@@ -305,6 +305,35 @@ __global__ void select_pairs_kernel(int n_frag, const int *__restrict__ cand_beg
 	}
 }
 
+// ScoreBuffer::topNSE (ScoreBuffer.cpp:279-330), topn > 1; one thread per read.  sel[r * topn + j] = the candidates handed to alignment in
+// the order of the sorted list (std::sort's order of equal scores included), -1 beyond n_sel[r].
+__global__ void select_topn_kernel(int n_reads, const int *__restrict__ cand_begin, const float *__restrict__ scores, int topn, int strata,
+		SelItem *__restrict__ items, int *__restrict__ sel, int *__restrict__ n_sel, int *__restrict__ mapq, int *__restrict__ num_top) {
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const int b = cand_begin[r], e = cand_begin[r + 1], n = e - b;
+	for (int j = 0; j < topn; ++j) sel[(size_t) r * topn + j] = -1;
+	int ns = 0, mq = 0, nt = 1;                                 // MappedRead ctor: numTopScores 1
+	if (n > 0) {
+		SelItem *s = items + b;
+		for (int j = 0; j < n; ++j) {
+			s[j].score = scores[b + j];
+			s[j].orig = b + j;
+		}
+		sel_sort(s, n);
+		nt = 1;
+		while (nt < n && s[0].score == s[nt].score) ++nt;
+		if (nt <= topn || !strata) {
+			ns = strata ? nt : min(n, topn);
+			mq = n > 1 ? sel_mq(s[0].score, s[1].score) : 60;
+			for (int j = 0; j < ns; ++j) sel[(size_t) r * topn + j] = s[j].orig;
+		}
+	}
+	n_sel[r] = ns;
+	mapq[r] = mq;
+	num_top[r] = nt;
+}
+
 struct Sum2 {
 	__device__ __forceinline__ longlong2 operator()(const longlong2 &x, const longlong2 &y) const { return make_longlong2(x.x + y.x, x.y + y.y); }
 };
@@ -425,6 +454,23 @@ int ngm_b200_pe_insert_stats(ngm_b200_ctx *c, int64_t *dist_sum, int64_t *dist_c
 	if (dist_sum) *dist_sum = st[0];
 	if (dist_count) *dist_count = st[1];
 	return NGM_B200_OK;
+}
+
+int ngm_b200_dev_select_topn(ngm_b200_ctx *c, int n_reads, const void *d_cand_begin, const void *d_scores, uint32_t n_pairs, int topn, int strata,
+		void *d_sel, void *d_n_sel, void *d_mapq, void *d_num_top, void *stream) {
+	if (c == nullptr || d_cand_begin == nullptr || d_scores == nullptr || d_sel == nullptr || d_n_sel == nullptr || d_mapq == nullptr || d_num_top == nullptr)
+		return fail(NGM_B200_EINVAL, "NULL argument");
+	if (topn < 1 || topn > 1000) return fail(NGM_B200_EINVAL, "topn %d not in [1, 1000]", topn);      // GenericReadWriter.h:79 MAX_PASSED
+	if (n_reads <= 0) return 0;
+	CU(cudaSetDevice(c->device));
+	if (c->pe == nullptr) c->pe = new PeState();
+	CU(c->pe->d_items.ensure(std::max<size_t>(n_pairs, 1) * sizeof(SelItem)));
+	select_topn_kernel<<<(n_reads + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(n_reads, static_cast<const int *>(d_cand_begin),
+			static_cast<const float *>(d_scores), topn, strata, c->pe->d_items.as<SelItem>(), static_cast<int *>(d_sel), static_cast<int *>(d_n_sel),
+			static_cast<int *>(d_mapq), static_cast<int *>(d_num_top));
+	c->launches += 1;
+	CU(cudaGetLastError());
+	return n_reads;
 }
 
 int ngm_b200_pe_set_insert_stats(ngm_b200_ctx *c, int64_t dist_sum, int64_t dist_count) {

@@ -143,6 +143,8 @@ def load_library() -> C.CDLL:
                                        C.POINTER(C.c_size_t), C.c_void_p]
     lib.ngm_b200_cs_exact_reads.restype = C.c_uint64
     lib.ngm_b200_cs_exact_reads.argtypes = [C.c_void_p]
+    lib.ngm_b200_dev_select_topn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p]
     lib.ngm_b200_map_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(MapResult)]
     lib.ngm_b200_format_sam.argtypes = [C.c_void_p, C.POINTER(SamOpts), C.POINTER(SamBatch), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.ngm_b200_pe_configure.argtypes = [C.c_void_p, C.POINTER(PeParams)]

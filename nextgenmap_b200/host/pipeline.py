@@ -106,6 +106,40 @@ def map_pairs(sw: CudaSW, reads: np.ndarray, mode: int = 0) -> MappedBatch:
     return MappedBatch(begin, pairs, scores, max_hit, best, mq, nt, recs, heap, strings, pf)
 
 
+def map_reads_topn(sw: CudaSW, reads: np.ndarray, topn: int, strata: bool = False, mode: int = 0):
+    """Single-end batch with ``topn`` > 1 (NGM ``-n``): candidate search, scores, ScoreBuffer::topNSE on the device, up to topn alignments
+    per read.  -> the batch ``sam_lines_topn`` takes."""
+    import torch
+    from types import SimpleNamespace
+    reads, begin, pairs, scores, max_hit = _search_and_score(sw, reads, mode)
+    n = reads.shape[0]
+    dev = torch.device("cuda", sw.params.device)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    d_begin = torch.from_numpy(begin).to(dev)
+    d_scores = torch.from_numpy(scores).to(dev) if len(scores) else torch.zeros(1, dtype=torch.float32, device=dev)
+    d_sel = torch.empty((n, topn), dtype=torch.int32, device=dev)
+    d_ns, d_mq, d_nt = (torch.empty(n, dtype=torch.int32, device=dev) for _ in range(3))
+    sw._check(sw.lib.ngm_b200_dev_select_topn(sw.ctx, n, d_begin.data_ptr(), d_scores.data_ptr(), len(scores), topn, 1 if strata else 0, d_sel.data_ptr(),
+                                              d_ns.data_ptr(), d_mq.data_ptr(), d_nt.data_ptr(), st))
+    torch.cuda.synchronize(dev)
+    sel = d_sel.cpu().numpy()
+    rr, jj = np.nonzero(sel >= 0)
+    winners = pairs[sel[rr, jj]].copy()
+    recs = np.zeros((n, topn), dtype=ALIGN_REC)
+    recs["score"] = -1.0
+    raw = b""
+    if len(rr):
+        flat, heap = sw.align_pairs(mode, winners)
+        recs[rr, jj] = flat
+        raw = heap.tobytes()
+
+    def strings(r: int, j: int):
+        o, cl, ml = int(recs[r, j]["str_off"]), int(recs[r, j]["cigar_len"]), int(recs[r, j]["md_len"])
+        return raw[o: o + cl], raw[o + cl: o + cl + ml]
+    return SimpleNamespace(cand_begin=begin, pairs=pairs, scores=scores, max_hit=max_hit, sel=sel, n_sel=d_ns.cpu().numpy(), mapq=d_mq.cpu().numpy(),
+                           num_top=d_nt.cpu().numpy(), recs=recs, strings=strings)
+
+
 def map_batch(sw: CudaSW, reads: np.ndarray, mode: int = 0, paired: bool = False, capacity: int = 0, heap_bytes: int = 0) -> MappedBatch:
     """The same as ``map_reads`` / ``map_pairs`` through the one-call entry point ``ngm_b200_map_batch`` (host buffers in, host buffers
     out; candidates, scores and winners never leave the device in between)."""
@@ -221,6 +255,52 @@ def sam_lines(sw: Optional[CudaSW], batch, reads: np.ndarray, names: Sequence[st
         else:
             out.append(_unmapped_line(rd, 0))
     return out
+
+
+def sam_lines_topn(batch, reads: np.ndarray, names: Sequence[str], quals: Sequence[bytes], encref, corridor: int, min_identity: float = 0.65,
+                   min_residues: float = 0.5) -> List[str]:
+    """Single-end run with ``topn`` > 1: up to topn lines per read.  ``batch``: sel [n, topn] (candidate indices in the order of
+    ScoreBuffer::topNSE, -1 padded), n_sel, mapq, num_top, recs [n, topn], strings(r, j).  AlignmentBuffer::WriteRead converts every
+    location and keeps the LAST result (AlignmentBuffer.cpp:169-175); GenericReadWriter::WriteRead (GenericReadWriter.h:200-248) stops
+    accepting alignments after the first one that fails a filter, drops repeated locations, and writes the unmapped record when nothing
+    passed; every line after the best candidate's carries 0x100 (SAMWriter.cpp:116-118)."""
+    out = []
+    for r in range(reads.shape[0]):
+        seq = reads[r].tobytes().split(b"\0")[0]
+        length, ns = len(seq), int(batch.n_sel[r])
+        lines, mapped, seen, views = [], ns > 0, set(), []
+        for j in range(ns):
+            p = batch.pairs[int(batch.sel[r, j])]
+            rec = batch.recs[r, j]
+            rd = _Read(names[r], seq, quals[r], length, has=True, reverse=bool(int(p["flags"]) & 1), bp=int(batch.sel[r, j]), r=r)
+            rd.loc = (int(p["window_start"]) + int(rec["position_offset"])) & U64
+            conv = encref.convert(rd.loc)
+            if conv is not None:
+                rd.contig, rd.loc, rd.converted = conv[0], conv[1], True
+            mapped = conv is not None                      # the last convert() decides
+            views.append((rd, rec))
+        if any(float(rec["score"]) < 0.0 for _, rec in views):
+            mapped = False
+        for j, (rd, rec) in enumerate(views):
+            mres = length * min_residues if min_residues <= 1.0 else min_residues
+            mapped = mapped and bool(float(rec["identity"]) >= np.float32(min_identity)) and bool(float(length - int(rec["qstart"]) - int(rec["qend"])) >= np.float32(mres))
+            if mapped:
+                key = (rd.loc, rd.contig, rd.reverse)
+                if key not in seen:
+                    seen.add(key)
+                    one = SimpleBatch(batch, r, j)
+                    lines.append(_mapped_line(one, rd, encref, 0x100 if j else 0, "*", -1, 0))
+        out += lines if lines else [_unmapped_line(_Read(names[r], seq, quals[r], length), 0)]
+    return out
+
+
+class SimpleBatch:
+    """View of alignment j of read r in a topn batch with the field names ``_mapped_line`` reads."""
+
+    def __init__(self, batch, r: int, j: int):
+        self.recs = {r: batch.recs[r, j]}
+        self.mapq, self.num_top, self.max_hit, self.scores = batch.mapq, batch.num_top, batch.max_hit, batch.scores
+        self.strings = lambda rr: batch.strings(rr, j)
 
 
 def sam_lines_paired(batch, reads: np.ndarray, names: Sequence[str], quals: Sequence[bytes], encref, corridor: int, min_identity: float = 0.65,

@@ -68,6 +68,26 @@ class Selector:
         return out
 
 
+def select_topn(selector: Selector, cand_begin: np.ndarray, scores: np.ndarray, topn: int):
+    """ScoreBuffer::topNSE per read -> (sel int32 [n, topn] candidate indices in sorted order, -1 padded; n_sel, mapq, num_top int32 [n])."""
+    n = len(cand_begin) - 1
+    sel = np.full((n, topn), -1, np.int32)
+    n_sel, mapq, num_top = np.zeros(n, np.int32), np.zeros(n, np.int32), np.ones(n, np.int32)
+    for r in range(n):
+        b, e = int(cand_begin[r]), int(cand_begin[r + 1])
+        if e > b:
+            cands = np.zeros(e - b, dtype=SEL_CAND)
+            cands["score"] = scores[b:e]
+            cands["orig"] = np.arange(b, e)
+            row = np.zeros(max(topn, e - b), np.int32)
+            ns, mq, nt = C.c_int(0), C.c_int(0), C.c_int(0)
+            selector.lib.sel_oracle_topn_se(cands.ctypes.data_as(C.c_void_p), e - b, topn, C.byref(selector.p), row.ctypes.data_as(C.c_void_p), C.byref(ns),
+                                            C.byref(mq), C.byref(nt))
+            sel[r, : ns.value] = row[: ns.value]
+            n_sel[r], mapq[r], num_top[r] = ns.value, mq.value, nt.value
+    return sel, n_sel, mapq, num_top
+
+
 def revcomp_row(row: np.ndarray) -> np.ndarray:
     s = row.tobytes().split(b"\0")[0]
     out = np.zeros_like(row)
@@ -89,6 +109,35 @@ def _windows(packed, concat_len, reads, pairs, qml, cor, buf_len, fill_on_failur
         row = reads[int(p["read_index"])]
         qrys[i] = revcomp_row(row) if (int(p["flags"]) & 1) else row
     return refs, qrys
+
+
+def map_batch_topn(packed: np.ndarray, concat_len: int, ix: cs_port.Index, reads: np.ndarray, qml: int, corridor: int, mode: int, sensitivity: float,
+                   topn: int, selector: Optional[Selector] = None):
+    """Single-end run with topn > 1 (ScoreBuffer::topNSE): up to topn alignments per read.  -> namespace with the fields
+    nextgenmap_b200.host.pipeline.sam_lines_topn takes (sel [n, topn], n_sel, recs [n, topn], strings(r, j))."""
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    n = reads.shape[0]
+    begin, cands, max_hit = ix.search(reads, sensitivity)
+    pairs = np.zeros(len(cands), dtype=PAIR)
+    pairs["window_start"] = (cands["location"].astype(np.uint64) - np.uint64(corridor >> 1))
+    pairs["read_index"] = np.repeat(np.arange(n, dtype=np.uint32), np.diff(begin))
+    pairs["flags"] = np.where(cands["reverse"] != 0, 3, 0)
+    refs, qrys = _windows(packed, concat_len, reads, pairs, qml, corridor, ((qml + corridor) | 1) + 1, True)
+    scores = port.batch_score(refs, qrys, qml, corridor, mode) if len(pairs) else np.zeros(0, np.float32)
+    selector = selector or Selector()
+    sel, n_sel, mapq, num_top = select_topn(selector, begin, scores, topn)
+    rr, jj = np.nonzero(sel >= 0)
+    winners = pairs[sel[rr, jj]].copy()
+    recs = np.zeros((n, topn), dtype=REC)
+    recs["score"] = -1.0
+    strings = {}
+    if len(rr):
+        refs, qrys = _windows(packed, concat_len, reads, winners, qml, corridor, (qml + corridor) | 2, False)
+        for r, j, a in zip(rr, jj, port.batch_align(refs, qrys, qml, corridor, mode)):
+            recs[r, j] = (a.position_offset, a.qstart, a.qend, a.nm, a.identity, a.ascore)
+            strings[(int(r), int(j))] = (a.cigar, a.md_raw)
+    return SimpleNamespace(cand_begin=begin, pairs=pairs, scores=scores, max_hit=max_hit, sel=sel, n_sel=n_sel, mapq=mapq, num_top=num_top, recs=recs,
+                           strings=lambda r, j: strings[(int(r), int(j))])
 
 
 def map_batch(packed: np.ndarray, concat_len: int, ix: cs_port.Index, reads: np.ndarray, qml: int, corridor: int, mode: int, sensitivity: float,

@@ -287,3 +287,23 @@ void sel_oracle_select_pairs(int n_reads, const int *cand_begin, cand *cands, co
 		}
 	}
 }
+
+/* ScoreBuffer::topNSE (ScoreBuffer.cpp:279-330), topn > 1: s is sorted in place; the first *n_sel entries of the sorted list go to alignment
+ * (sel[j] = their positions in the caller's array).  Returns 0 when the read is reported unmapped (too many equal top scores under strata). */
+int sel_oracle_topn_se(cand *s, int n, int topn, const sel_oracle_params *p, int *sel, int *n_sel, int *mapq, int *num_top) {
+	sel_oracle_sort(s, n);
+	int n_scores = n, n_top = 1;
+	while (n_top < n_scores && s[0].score == s[n_top].score) n_top += 1;
+	*num_top = n_top;
+	if (n_top <= topn || !p->strata) {
+		if (p->strata) n_scores = n_top;
+		else n_scores = n_scores < topn ? n_scores : topn;
+		*mapq = mq_sorted(s, n);
+		*n_sel = n_scores;
+		for (int j = 0; j < n_scores; ++j) sel[j] = s[j].orig;
+		return 1;
+	}
+	*mapq = 0;
+	*n_sel = 0;
+	return 0;
+}

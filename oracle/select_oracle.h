@@ -49,6 +49,9 @@ void sel_oracle_top1_pe(sel_oracle_cand *s_read, int n_read, int len_read, sel_o
 void sel_oracle_select_pairs(int n_reads, const int *cand_begin, sel_oracle_cand *cands, const int *read_len, const sel_oracle_params *p,
 		sel_oracle_state *st, sel_oracle_result *out);
 
+/* ScoreBuffer::topNSE (ScoreBuffer.cpp:279-330): see select_oracle.c. */
+int sel_oracle_topn_se(sel_oracle_cand *s, int n, int topn, const sel_oracle_params *p, int *sel, int *n_sel, int *mapq, int *num_top);
+
 #ifdef __cplusplus
 }
 #endif

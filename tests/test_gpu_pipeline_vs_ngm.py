@@ -113,3 +113,29 @@ def test_paired_sam_identical_to_ngm(ref_len, n_frags, read_len, seed, extra):
     assert {"99", "147", "83", "163"} <= flags and len(flags) >= 10
     sw.close()
     ref.close()
+
+
+@pytest.mark.parametrize("extra,topn,strata,seed", [(["-n", "3"], 3, False, 51), (["-n", "2", "--strata"], 2, True, 52)])
+def test_topn_sam_identical_to_ngm(extra, topn, strata, seed):
+    """`ngm -n <topn>` (ScoreBuffer::topNSE): several alignments per read, secondary lines (0x100), repeated locations dropped."""
+    from nextgenmap_b200.host import CudaSW, EncodedReference
+    from nextgenmap_b200.host import pipeline
+    from tests.test_mapper_oracle import read_fastq as read_fastq_pe, rows
+    with tempfile.TemporaryDirectory(prefix="pipe_topn_") as td:
+        d = Path(td)
+        e2e.write_paired_inputs(d, ref_len=500_000, n_frags=900, read_len=100, seed=seed)      # repeats: several equally good candidates
+        want = [ln for ln in e2e.run("ref", d, threads=1, extra=["-s", "0.5", *extra]) if not ln.startswith("@")]
+        ref = EncodedReference(str(d / "ref.fa-enc.2.ngm"))
+        names, seqs, quals = read_fastq_pe(d / "reads.fq", False)
+    reads = rows(seqs, 102)
+    sw = CudaSW(102, 20)
+    sw.set_reference(ref.packed, ref.concat_len)
+    sw.cs_build_index([(c[1], c[2]) for c in ref.contigs], sw.cs_params(kmer=13, sensitivity=0.5))
+    batch = pipeline.map_reads_topn(sw, reads, topn, strata)
+    got = sorted(pipeline.sam_lines_topn(batch, reads, names, quals, ref, 20))
+    assert len(got) == len(want)
+    bad = [(g, w) for g, w in zip(got, want) if g != w]
+    assert not bad, f"{len(bad)} of {len(want)} SAM lines differ, first:\n{bad[0][0]}\n{bad[0][1]}"
+    assert sum(1 for ln in want if int(ln.split("\t")[1]) & 0x100) > (5 if strata else 100)
+    sw.close()
+    ref.close()

@@ -97,3 +97,31 @@ def test_select_pairs_argument_checks():
     assert sw.lib.ngm_b200_dev_select_pairs(sw.ctx, 3, *args) == -1              # odd number of reads
     assert sw.lib.ngm_b200_dev_select_pairs(sw.ctx, 2, *args) == -4              # no read batch
     sw.close()
+
+
+@pytest.mark.parametrize("seed,topn,strata,values", [(11, 3, 0, [0.0, 400.0, 900.0, 1000.0]), (12, 2, 1, [900.0, 1000.0]), (13, 8, 0, [1000.0]), (14, 4, 1, [10.0, 20.0, 30.0])])
+def test_select_topn_matches_oracle(seed, topn, strata, values):
+    """ngm_b200_dev_select_topn (ScoreBuffer::topNSE) against the oracle: which candidates, in which order (std::sort's order of equal
+    scores, lists beyond 16 entries), MAPQ, numTopScores, the strata rule."""
+    import torch
+    from nextgenmap_b200.host import CudaSW
+    begin, scores, _, _ = make_case(seed, 3000, 6, values)
+    n = len(begin) - 1
+    sel = mapper_port.Selector(strata=strata)
+    want_sel, want_ns, want_mq, want_nt = mapper_port.select_topn(sel, begin, scores, topn)
+    sw = CudaSW(102, 20)
+    d_begin = torch.from_numpy(begin).cuda()
+    d_scores = torch.from_numpy(np.concatenate([scores, np.zeros(1, np.float32)])).cuda()
+    d_sel = torch.full((n, topn), -7, dtype=torch.int32, device="cuda")
+    o = [torch.full((n,), -7, dtype=torch.int32, device="cuda") for _ in range(3)]
+    rc = sw.lib.ngm_b200_dev_select_topn(sw.ctx, n, d_begin.data_ptr(), d_scores.data_ptr(), len(scores), topn, strata, d_sel.data_ptr(), o[0].data_ptr(),
+                                         o[1].data_ptr(), o[2].data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == n, sw._err()
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(d_sel.cpu().numpy(), want_sel)
+    np.testing.assert_array_equal(o[0].cpu().numpy(), want_ns)
+    np.testing.assert_array_equal(o[1].cpu().numpy(), want_mq)
+    has = np.diff(begin) > 0
+    np.testing.assert_array_equal(o[2].cpu().numpy()[has], want_nt[has])
+    assert (want_ns > 1).sum() > 100
+    sw.close()

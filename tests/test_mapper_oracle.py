@@ -186,3 +186,41 @@ def test_native_sam_formatter_equals_host_mirror(paired):
         assert got == want
     if paired:
         assert sorted(want) == gzip.open(GOLD / "pe_l100.sam.gz", "rt").read().splitlines()
+
+
+def oracle_topn_sam(d: Path, read_len: int, mode: int, topn: int, strata: int):
+    from nextgenmap_b200.host import EncodedReference, pipeline
+    enc = d / "ref.fa-enc.2.ngm"
+    ref = EncodedReference(str(enc)) if enc.exists() else LaidOutReference(d / "ref.fa")
+    names, seqs, quals = read_fastq(d / "reads.fq", False)
+    qml, cor = (read_len | 1) + 1, int(5 + 0.15 * read_len)
+    reads = rows(seqs, qml)
+    ix = cs_port.Index(ref.packed, ref.concat_len, [(c[1], c[2]) for c in ref.contigs], k=13)
+    batch = mapper_port.map_batch_topn(ref.packed, ref.concat_len, ix, reads, qml, cor, mode, 0.5, topn, mapper_port.Selector(strata=strata))
+    ix.close()
+    got = sorted(pipeline.sam_lines_topn(batch, reads, names, quals, ref, cor))
+    ref.close()
+    return got
+
+
+def test_topn_golden_sam():
+    """`-n 3` (ScoreBuffer::topNSE, several alignments per read, 0x100 lines, the duplicate filter of GenericReadWriter::WriteRead):
+    oracle run against the committed SAM of the unmodified NGM (tests/golden/make_pe_golden.py)."""
+    with tempfile.TemporaryDirectory(prefix="topngold_") as td:
+        d = Path(td)
+        e2e.write_paired_inputs(d, ref_len=300_000, n_frags=500, read_len=100, seed=79)
+        got = oracle_topn_sam(d, 100, 0, 3, 0)
+    want = gzip.open(GOLD / "se_topn3_l100.sam.gz", "rt").read().splitlines()
+    diff(got, want)
+    assert sum(1 for ln in want if int(ln.split("\t")[1]) & 0x100) > 100
+
+
+@pytest.mark.skipif(not e2e.available("ref"), reason="oracle/_ref/ngm/ngm_ref not built")
+@pytest.mark.parametrize("extra,topn,strata,seed", [(["-n", "2", "--strata"], 2, 1, 42), (["-n", "5", "-e"], 5, 0, 43)])
+def test_topn_sam_identical_to_ngm(extra, topn, strata, seed):
+    with tempfile.TemporaryDirectory(prefix="topn_") as td:
+        d = Path(td)
+        e2e.write_paired_inputs(d, ref_len=400_000, n_frags=600, read_len=100, seed=seed)
+        want = [ln for ln in e2e.run("ref", d, threads=1, extra=["-s", "0.5", *extra]) if not ln.startswith("@")]
+        got = oracle_topn_sam(d, 100, 1 if "-e" in extra else 0, topn, strata)
+    diff(got, want)
