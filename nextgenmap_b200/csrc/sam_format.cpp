@@ -39,15 +39,17 @@ struct Job {
 	const ngm_b200_sam_batch *b;
 };
 
-inline char comp(char c) {     // MappedRead.cpp:36-47
-	switch (c) {
-	case 'A': return 'T';
-	case 'T': return 'A';
-	case 'C': return 'G';
-	case 'G': return 'C';
-	default: return c;
+struct CompTable {             // MappedRead.cpp:36-47: A <-> T, C <-> G, everything else unchanged
+	unsigned char t[256];
+	CompTable() {
+		for (int i = 0; i < 256; ++i) t[i] = (unsigned char) i;
+		t['A'] = 'T';
+		t['T'] = 'A';
+		t['C'] = 'G';
+		t['G'] = 'C';
 	}
-}
+};
+const CompTable kComp;
 
 void collect(const Job &j, int r, ReadView &v) {
 	const ngm_b200_sam_batch &b = *j.b;
@@ -170,9 +172,10 @@ void mapped_line(const Job &j, const ReadView &v, int flags, const char *rnext, 
 	char *dst = out.p;
 	out.p += 2 * (size_t) v.length + 1;
 	if (v.reverse) {                                            // RevSeq, reversed qualities (SAMWriter.cpp:120-126)
-		for (int i = 0; i < v.length; ++i) dst[i] = comp(v.seq[v.length - 1 - i]);
+		const unsigned char *sq = reinterpret_cast<const unsigned char *>(v.seq) + v.length;
+		for (int i = 0; i < v.length; ++i) dst[i] = (char) kComp.t[*--sq];
 		dst[v.length] = '\t';
-		for (int i = 0; i < v.length; ++i) dst[v.length + 1 + i] = v.qual[v.length - 1 - i];
+		std::reverse_copy(v.qual, v.qual + v.length, dst + v.length + 1);
 	} else {
 		memcpy(dst, v.seq, (size_t) v.length);
 		dst[v.length] = '\t';
