@@ -343,6 +343,11 @@ typedef struct ngm_b200_sam_batch {
 	const float *max_hit;           /* MappedRead::s -> XE:i */
 	const ngm_b200_align_rec *recs; /* alignment of read r's selected candidate (ngm_b200_align_pairs with read_index = r) */
 	const char *strings;            /* its string heap */
+	/* "topn" > 1 (single-end only, ngm_b200_dev_select_topn): recs holds n_reads x topn records, record r * topn + j belongs to candidate
+	 * sel[r * topn + j], j < n_sel[r]; best_pair is not read.  topn <= 1: leave these zero. */
+	int32_t topn;
+	const int32_t *sel;
+	const int32_t *n_sel;
 } ngm_b200_sam_batch;
 /* SAM body lines (no header) of the batch in read order, what AlignmentBuffer::WriteRead (AlignmentBuffer.cpp:166-200),
  * GenericReadWriter::WriteRead / WritePair (GenericReadWriter.h:190-312) and SAMWriter::DoWriteReadGeneric / DoWriteUnmappedReadGeneric /

@@ -31,6 +31,7 @@ struct ReadView {          // one read after AlignmentBuffer::DoRun: what WriteR
 	uint32_t contig = 0;
 	bool converted = false;
 	int bp = -1;
+	const ngm_b200_align_rec *rec = nullptr;
 };
 
 struct Job {
@@ -51,20 +52,24 @@ struct CompTable {             // MappedRead.cpp:36-47: A <-> T, C <-> G, everyt
 };
 const CompTable kComp;
 
-void collect(const Job &j, int r, ReadView &v) {
+void collect_at(const Job &j, int r, int bp, const ngm_b200_align_rec *rec, ReadView &v);
+
+void collect(const Job &j, int r, ReadView &v) { collect_at(j, r, j.b->best_pair[r], &j.b->recs[r], v); }
+
+void collect_at(const Job &j, int r, int bp, const ngm_b200_align_rec *rec, ReadView &v) {
 	const ngm_b200_sam_batch &b = *j.b;
 	v.r = r;
+	v.rec = rec;
 	v.name = b.names[r];
 	v.seq = b.reads + (size_t) r * b.stride;
 	v.qual = b.quals + (size_t) r * b.stride;
 	v.length = (int) strnlen(v.seq, (size_t) b.stride);
-	const int bp = b.best_pair[r];
-	if (bp >= 0 && b.recs[r].score >= 0.0f) {
+	if (bp >= 0 && rec->score >= 0.0f) {
 		const ngm_b200_pair &p = b.pairs[bp];
 		v.has = true;
 		v.bp = bp;
 		v.reverse = (p.flags & NGM_B200_PAIR_REVERSE) != 0;
-		v.loc = p.window_start + (uint64_t) (int64_t) b.recs[r].position_offset;      // window_start is Location - corridor / 2 already
+		v.loc = p.window_start + (uint64_t) (int64_t) rec->position_offset;      // window_start is Location - corridor / 2 already
 		uint32_t contig = 0;
 		uint64_t pos = 0;
 		if (ngm_b200_convert(j.ref, v.loc, &contig, &pos)) {
@@ -76,7 +81,7 @@ void collect(const Job &j, int r, ReadView &v) {
 }
 
 bool passes(const Job &j, const ReadView &v) {     // GenericReadWriter.h:206-214,273-283
-	const ngm_b200_align_rec &rec = j.b->recs[v.r];
+	const ngm_b200_align_rec &rec = *v.rec;
 	const float mres = j.o->min_residues <= 1.0f ? (float) v.length * j.o->min_residues : j.o->min_residues;
 	return rec.identity >= j.o->min_identity && (float) (v.length - rec.qstart - rec.qend) >= mres;
 }
@@ -91,10 +96,11 @@ struct Line {              // one output line is assembled in a scratch buffer t
 	void append(const char *s) { append(s, strlen(s)); }
 };
 
-size_t line_bound(const Job &j, int r) {       // name + FLAG..TLEN + SEQ + QUAL + tags + CIGAR + MD
-	const ngm_b200_align_rec &rec = j.b->recs[r];
-	return strlen(j.b->names[r]) + 2 * (size_t) j.b->stride + (j.b->best_pair[r] >= 0 ? (size_t) rec.cigar_len + rec.md_len : 0) + 2 * 100 + 320;
+size_t line_bound_at(const Job &j, int r, bool aligned, const ngm_b200_align_rec &rec) {       // name + FLAG..TLEN + SEQ + QUAL + tags + CIGAR + MD
+	return strlen(j.b->names[r]) + 2 * (size_t) j.b->stride + (aligned ? (size_t) rec.cigar_len + rec.md_len : 0) + 2 * 100 + 320;
 }
+
+size_t line_bound(const Job &j, int r) { return line_bound_at(j, r, j.b->best_pair[r] >= 0, j.b->recs[r]); }
 
 void put_name(Line &out, const ngm_b200_contig &c) { out.append(c.name, c.name_len); }
 
@@ -148,7 +154,7 @@ inline void put_xi(Line &out, float raw_identity) {
 void mapped_line(const Job &j, const ReadView &v, int flags, const char *rnext, const ngm_b200_contig *rnext_contig, int64_t pnext, int tlen,
 		Line &out) {                                        // SAMWriter::DoWriteReadGeneric
 	const ngm_b200_sam_batch &b = *j.b;
-	const ngm_b200_align_rec &rec = b.recs[v.r];
+	const ngm_b200_align_rec &rec = *v.rec;
 	if (v.reverse) flags |= 0x10;
 	out.append(v.name);
 	out.push_back('\t');
@@ -226,6 +232,46 @@ void single(const Job &j, int r, std::string &text, std::vector<char> &scratch) 
 	text.append(scratch.data(), (size_t) (out.p - scratch.data()));
 }
 
+// topn > 1: up to topn lines per read.  AlignmentBuffer::WriteRead converts every location and keeps the LAST result
+// (AlignmentBuffer.cpp:169-175); GenericReadWriter::WriteRead (GenericReadWriter.h:200-248) stops accepting alignments after the first one
+// that fails a filter and drops repeated locations; lines after the best candidate's carry 0x100 (SAMWriter.cpp:116-118).
+void single_topn(const Job &j, int r, std::string &text, std::vector<char> &scratch) {
+	const ngm_b200_sam_batch &b = *j.b;
+	const int topn = b.topn, ns = b.n_sel[r];
+	std::vector<ReadView> views((size_t) std::max(ns, 1));
+	size_t bound = line_bound_at(j, r, false, b.recs[(size_t) r * topn]);
+	bool mapped = ns > 0;
+	for (int k = 0; k < ns; ++k) {
+		const ngm_b200_align_rec *rec = &b.recs[(size_t) r * topn + k];
+		collect_at(j, r, b.sel[(size_t) r * topn + k], rec, views[(size_t) k]);
+		bound += line_bound_at(j, r, true, *rec);
+		mapped = views[(size_t) k].converted;                  // the last convert() decides
+	}
+	for (int k = 0; k < ns; ++k) if (!views[(size_t) k].has) mapped = false;       // a failed alignment: nothing of this read is written as mapped
+	scratch.resize(std::max(scratch.size(), bound));
+	Line out = { scratch.data() };
+	int written = 0;
+	for (int k = 0; k < ns; ++k) {
+		const ReadView &v = views[(size_t) k];
+		mapped = mapped && passes(j, v);
+		if (!mapped) continue;
+		bool dup = false;
+		for (int q = 0; q < k && !dup; ++q) {
+			const ReadView &w = views[(size_t) q];
+			dup = w.bp == -2 && w.loc == v.loc && w.contig == v.contig && w.reverse == v.reverse;      // bp == -2 marks the locations already written
+		}
+		if (dup) continue;
+		mapped_line(j, v, k ? 0x100 : 0, "*", nullptr, -1, 0, out);
+		views[(size_t) k].bp = -2;
+		++written;
+	}
+	if (written == 0) {
+		if (ns == 0) collect_at(j, r, -1, &b.recs[(size_t) r * topn], views[0]);
+		unmapped_line(views[0], 0, nullptr, -1, '*', -1, out);
+	}
+	text.append(scratch.data(), (size_t) (out.p - scratch.data()));
+}
+
 void fragment(const Job &j, int f, std::string &text, std::vector<char> &scratch) {
 	const ngm_b200_sam_batch &bt = *j.b;
 	ReadView a, b;                                              // a: first mate (ReadId even), b: second mate
@@ -276,9 +322,11 @@ extern "C" __attribute__((visibility("default"))) int ngm_b200_format_sam(const 
 		const ngm_b200_sam_batch *batch, char *out, size_t out_capacity, size_t *out_used) {
 	if (ref == nullptr || opts == nullptr || batch == nullptr || out_used == nullptr || (out == nullptr && out_capacity)) return NGM_B200_EINVAL;
 	const ngm_b200_sam_batch &b = *batch;
-	if (b.n_reads < 0 || (b.n_reads && (b.reads == nullptr || b.quals == nullptr || b.names == nullptr || b.best_pair == nullptr || b.mapq == nullptr ||
+	if (b.n_reads < 0 || (b.n_reads && (b.reads == nullptr || b.quals == nullptr || b.names == nullptr || (b.best_pair == nullptr && b.topn <= 1) || b.mapq == nullptr ||
 			b.num_top == nullptr || b.max_hit == nullptr || b.recs == nullptr))) return NGM_B200_EINVAL;
 	const bool paired = b.pair_fail != nullptr;
+	const bool multi = b.topn > 1;
+	if (multi && (paired || b.sel == nullptr || b.n_sel == nullptr)) return NGM_B200_EINVAL;      // several alignments per read: single-end only, like the reference
 	if (paired && (b.n_reads & 1)) return NGM_B200_EINVAL;
 	const int units = paired ? b.n_reads / 2 : b.n_reads;
 	int threads = opts->threads > 0 ? opts->threads : (int) std::thread::hardware_concurrency();
@@ -292,6 +340,7 @@ extern "C" __attribute__((visibility("default"))) int ngm_b200_format_sam(const 
 		std::vector<char> scratch(4096);
 		for (int u = lo; u < hi; ++u) {
 			if (paired) fragment(job, u, s, scratch);
+			else if (multi) single_topn(job, u, s, scratch);
 			else single(job, u, s, scratch);
 		}
 	};

@@ -55,7 +55,7 @@ class SamBatch(C.Structure):
     """ngm_b200_sam_batch (include/ngm_b200.h)."""
     _fields_ = [("n_reads", C.c_int32), ("stride", C.c_int32), ("reads", C.c_void_p), ("quals", C.c_void_p), ("names", C.POINTER(C.c_char_p)), ("pairs", C.c_void_p),
                 ("scores", C.c_void_p), ("best_pair", C.c_void_p), ("mapq", C.c_void_p), ("num_top", C.c_void_p), ("pair_fail", C.c_void_p), ("max_hit", C.c_void_p),
-                ("recs", C.c_void_p), ("strings", C.c_void_p)]
+                ("recs", C.c_void_p), ("strings", C.c_void_p), ("topn", C.c_int32), ("sel", C.c_void_p), ("n_sel", C.c_void_p)]
 
 
 class MapResult(C.Structure):

@@ -127,7 +127,7 @@ def map_reads_topn(sw: CudaSW, reads: np.ndarray, topn: int, strata: bool = Fals
     winners = pairs[sel[rr, jj]].copy()
     recs = np.zeros((n, topn), dtype=ALIGN_REC)
     recs["score"] = -1.0
-    raw = b""
+    raw, heap = b"", np.zeros(1, np.uint8)
     if len(rr):
         flat, heap = sw.align_pairs(mode, winners)
         recs[rr, jj] = flat
@@ -137,7 +137,7 @@ def map_reads_topn(sw: CudaSW, reads: np.ndarray, topn: int, strata: bool = Fals
         o, cl, ml = int(recs[r, j]["str_off"]), int(recs[r, j]["cigar_len"]), int(recs[r, j]["md_len"])
         return raw[o: o + cl], raw[o + cl: o + cl + ml]
     return SimpleNamespace(cand_begin=begin, pairs=pairs, scores=scores, max_hit=max_hit, sel=sel, n_sel=d_ns.cpu().numpy(), mapq=d_mq.cpu().numpy(),
-                           num_top=d_nt.cpu().numpy(), recs=recs, strings=strings)
+                           num_top=d_nt.cpu().numpy(), recs=recs, strings=strings, heap=heap)
 
 
 def map_batch(sw: CudaSW, reads: np.ndarray, mode: int = 0, paired: bool = False, capacity: int = 0, heap_bytes: int = 0) -> MappedBatch:
@@ -361,17 +361,21 @@ def format_sam(batch, reads: np.ndarray, names: Sequence[str], quals: Sequence[b
     for i, ql in enumerate(quals):
         q[i, : len(ql)] = np.frombuffer(ql, np.uint8)
     name_arr = (C.c_char_p * n)(*[nm.encode() for nm in names])
-    keep = [np.ascontiguousarray(batch.pairs), np.ascontiguousarray(batch.scores, dtype=np.float32), np.ascontiguousarray(batch.best_pair, dtype=np.int32),
+    topn = int(batch.sel.shape[1]) if hasattr(batch, "sel") else 0        # a ``map_reads_topn`` batch: recs [n, topn], sel, n_sel
+    best = batch.sel[:, 0] if topn else batch.best_pair
+    keep = [np.ascontiguousarray(batch.pairs), np.ascontiguousarray(batch.scores, dtype=np.float32), np.ascontiguousarray(best, dtype=np.int32),
             np.ascontiguousarray(batch.mapq, dtype=np.int32), np.ascontiguousarray(batch.num_top, dtype=np.int32),
             np.ascontiguousarray(batch.pair_fail, dtype=np.int32) if paired else None, np.ascontiguousarray(batch.max_hit, dtype=np.float32),
             np.ascontiguousarray(batch.recs), np.ascontiguousarray(batch.heap)]
     assert keep[7].dtype == ALIGN_REC
     ptr = lambda a: None if a is None else a.ctypes.data
+    sel = np.ascontiguousarray(batch.sel, dtype=np.int32) if topn else None
+    n_sel = np.ascontiguousarray(batch.n_sel, dtype=np.int32) if topn else None
     sb = SamBatch(n, stride, reads.ctypes.data, q.ctypes.data, name_arr, ptr(keep[0]), ptr(keep[1]), ptr(keep[2]), ptr(keep[3]), ptr(keep[4]), ptr(keep[5]),
-                  ptr(keep[6]), ptr(keep[7]), ptr(keep[8]))
+                  ptr(keep[6]), ptr(keep[7]), ptr(keep[8]), topn if topn > 1 else 0, ptr(sel), ptr(n_sel))
     so = SamOpts(min_identity, min_residues, min_insert_size, max_insert_size, threads)
     used = C.c_size_t(0)
-    cap = n * (2 * stride + 256) + 4096
+    cap = n * max(topn, 1) * (2 * stride + 256) + 4096
     for _ in range(2):
         out = np.zeros(cap, np.uint8)
         rc = lib.ngm_b200_format_sam(C.byref(encref.c), C.byref(so), C.byref(sb), out.ctypes.data, cap, C.byref(used))

@@ -133,6 +133,7 @@ def test_topn_sam_identical_to_ngm(extra, topn, strata, seed):
     sw.cs_build_index([(c[1], c[2]) for c in ref.contigs], sw.cs_params(kmer=13, sensitivity=0.5))
     batch = pipeline.map_reads_topn(sw, reads, topn, strata)
     got = sorted(pipeline.sam_lines_topn(batch, reads, names, quals, ref, 20))
+    assert sorted(pipeline.format_sam(batch, reads, names, quals, ref, False).decode().splitlines()) == got      # ngm_b200_format_sam, topn records
     assert len(got) == len(want)
     bad = [(g, w) for g, w in zip(got, want) if g != w]
     assert not bad, f"{len(bad)} of {len(want)} SAM lines differ, first:\n{bad[0][0]}\n{bad[0][1]}"

@@ -224,3 +224,33 @@ def test_topn_sam_identical_to_ngm(extra, topn, strata, seed):
         want = [ln for ln in e2e.run("ref", d, threads=1, extra=["-s", "0.5", *extra]) if not ln.startswith("@")]
         got = oracle_topn_sam(d, 100, 1 if "-e" in extra else 0, topn, strata)
     diff(got, want)
+
+
+def test_native_sam_formatter_topn_equals_host_mirror():
+    """ngm_b200_format_sam with several alignments per read (topn 3) against the Python mirror that is checked against `ngm -n 3`."""
+    from nextgenmap_b200.host import pipeline
+    from nextgenmap_b200.host.cuda_sw import ALIGN_REC
+    with tempfile.TemporaryDirectory(prefix="fmt_topn_") as td:
+        d = Path(td)
+        e2e.write_paired_inputs(d, ref_len=300_000, n_frags=500, read_len=100, seed=79)
+        ref = LaidOutReference(d / "ref.fa")
+        names, seqs, quals = read_fastq(d / "reads.fq", False)
+    reads = rows(seqs, 102)
+    ix = cs_port.Index(ref.packed, ref.concat_len, [(c[1], c[2]) for c in ref.contigs], k=13)
+    batch = mapper_port.map_batch_topn(ref.packed, ref.concat_len, ix, reads, 102, 20, 0, 0.5, 3, mapper_port.Selector())
+    ix.close()
+    want = pipeline.sam_lines_topn(batch, reads, names, quals, ref, 20)
+    n, topn = batch.sel.shape
+    recs, heap = np.zeros((n, topn), dtype=ALIGN_REC), bytearray()
+    for r in range(n):
+        for j in range(int(batch.n_sel[r])):
+            for f in ("position_offset", "qstart", "qend", "nm", "identity", "score"):
+                recs[r, j][f] = batch.recs[r, j][f]
+            cig, md = batch.strings(r, j)
+            recs[r, j]["str_off"], recs[r, j]["cigar_len"], recs[r, j]["md_len"] = len(heap), len(cig), len(md)
+            heap += cig + md
+    batch.recs, batch.heap = recs, np.frombuffer(bytes(heap) + b"\0", np.uint8)
+    for threads in (1, 3):
+        got = pipeline.format_sam(batch, reads, names, quals, ref.as_encoded_reference(), False, threads=threads).decode().splitlines()
+        assert got == want
+    assert sorted(want) == gzip.open(GOLD / "se_topn3_l100.sam.gz", "rt").read().splitlines()
