@@ -35,3 +35,38 @@ def test_top1_and_topn_rules():
     # strata: more equally best candidates than topn -> the read keeps none
     s, ns, mq, nt = mapper_port.select_topn(mapper_port.Selector(strata=1), np.array([0, 3], np.int32), np.array([5, 5, 5], np.float32), 2)
     assert ns.tolist() == [0] and mq.tolist() == [0] and nt.tolist() == [3]
+
+
+def test_format_sam_argument_checks_and_sizing():
+    """ngm_b200_format_sam is host only: NULL / shape errors are reported, an undersized buffer gets the size it needs and is left untouched."""
+    import ctypes as C
+    from nextgenmap_b200.host.cuda_sw import ALIGN_REC, PAIR, SamBatch, SamOpts, _CContig, _CEncRef, load_library
+    lib = load_library()
+    n, stride = 4, 12
+    reads = np.zeros((n, stride), np.uint8)
+    reads[:, :8] = np.frombuffer(b"ACGTACGT", np.uint8)
+    quals = np.where(reads != 0, ord("I"), 0).astype(np.uint8)
+    names = (C.c_char_p * n)(*[b"q%d" % i for i in range(n)])
+    best = np.full(n, -1, np.int32)
+    zero_i, zero_f = np.zeros(n, np.int32), np.zeros(n, np.float32)
+    recs = np.zeros(n, ALIGN_REC)
+    pairs, heap = np.zeros(1, PAIR), np.zeros(1, np.uint8)
+    ctg = (_CContig * 1)()
+    ctg[0].start, ctg[0].length, ctg[0].name_len, ctg[0].name = 1000, 5000, 4, b"chr1"
+    enc = _CEncRef()
+    enc.concat_len, enc.n_contigs, enc.contigs = 7000, 1, C.cast(ctg, type(enc.contigs))
+    so = SamOpts(0.65, 0.5, 0, 1000, 1)
+    sb = SamBatch(n, stride, reads.ctypes.data, quals.ctypes.data, names, pairs.ctypes.data, zero_f.ctypes.data, best.ctypes.data, zero_i.ctypes.data,
+                  zero_i.ctypes.data, None, zero_f.ctypes.data, recs.ctypes.data, heap.ctypes.data)
+    used = C.c_size_t(0)
+    out = np.full(4096, 0x2A, np.uint8)
+    assert lib.ngm_b200_format_sam(C.byref(enc), C.byref(so), C.byref(sb), out.ctypes.data, 8, C.byref(used)) == -3      # NGM_B200_ERANGE
+    need = used.value
+    assert need > 8 and (out == 0x2A).all()
+    assert lib.ngm_b200_format_sam(C.byref(enc), C.byref(so), C.byref(sb), out.ctypes.data, out.size, C.byref(used)) == n
+    text = out[: used.value].tobytes().decode().splitlines()
+    assert used.value == need and text == ["q%d\t4\t*\t0\t0\t*\t*\t0\t0\tACGTACGT\tIIIIIIII" % i for i in range(n)]      # SAMWriter.cpp:312-365
+    assert lib.ngm_b200_format_sam(None, C.byref(so), C.byref(sb), out.ctypes.data, out.size, C.byref(used)) == -1
+    odd = SamBatch(3, stride, reads.ctypes.data, quals.ctypes.data, names, pairs.ctypes.data, zero_f.ctypes.data, best.ctypes.data, zero_i.ctypes.data,
+                   zero_i.ctypes.data, zero_i.ctypes.data, zero_f.ctypes.data, recs.ctypes.data, heap.ctypes.data)
+    assert lib.ngm_b200_format_sam(C.byref(enc), C.byref(so), C.byref(odd), out.ctypes.data, out.size, C.byref(used)) == -1     # pairs need an even number of rows
