@@ -81,7 +81,7 @@ class LaidOutReference:
         pass
 
 
-def oracle_sam(d: Path, read_len: int, mode: int, sens: float, paired: bool, batches: int = 1, sel=None):
+def oracle_sam(d: Path, read_len: int, mode: int, sens: float, paired: bool, batches: int = 1, sel=None, limits=None):
     from nextgenmap_b200.host import EncodedReference        # host-only reader of <ref>-enc.2.ngm (no CUDA call)
     from nextgenmap_b200.host import pipeline
     enc = d / "ref.fa-enc.2.ngm"
@@ -97,7 +97,7 @@ def oracle_sam(d: Path, read_len: int, mode: int, sens: float, paired: bool, bat
         hi = min(n, lo + step)
         batch = mapper_port.map_batch(ref.packed, ref.concat_len, ix, reads[lo:hi], qml, cor, mode, sens, sel, paired=paired)
         if paired:
-            got += pipeline.sam_lines_paired(batch, reads[lo:hi], names[lo:hi], quals[lo:hi], ref, cor)
+            got += pipeline.sam_lines_paired(batch, reads[lo:hi], names[lo:hi], quals[lo:hi], ref, cor, **(limits or {}))
         else:
             got += pipeline.sam_lines(None, batch, reads[lo:hi], names[lo:hi], quals[lo:hi], ref, cor)
     ix.close()
@@ -125,14 +125,16 @@ def test_paired_golden_sam():
 
 
 @pytest.mark.skipif(not e2e.available("ref"), reason="oracle/_ref/ngm/ngm_ref not built")
-@pytest.mark.parametrize("ref_len,n_frags,read_len,seed,extra", [(600_000, 1500, 100, 5, []), (500_000, 1000, 150, 6, ["-e"]), (400_000, 800, 75, 7, ["--fast-pairing"])])
+@pytest.mark.parametrize("ref_len,n_frags,read_len,seed,extra", [(600_000, 1500, 100, 5, []), (500_000, 1000, 150, 6, ["-e"]), (400_000, 800, 75, 7, ["--fast-pairing"]),
+                                                                 (400_000, 900, 100, 61, ["-I", "250", "-X", "430"]), (400_000, 900, 100, 62, ["--strata"])])
 def test_paired_sam_identical_to_ngm(ref_len, n_frags, read_len, seed, extra):
     with tempfile.TemporaryDirectory(prefix="pe_") as td:
         d = Path(td)
         e2e.write_paired_inputs(d, ref_len=ref_len, n_frags=n_frags, read_len=read_len, seed=seed)
         want = [ln for ln in e2e.run("ref", d, threads=1, extra=["-p", "-s", "0.5", *extra]) if not ln.startswith("@")]
-        sel = mapper_port.Selector(fast_pairing=1 if "--fast-pairing" in extra else 0)
-        got, _ = oracle_sam(d, read_len, 1 if "-e" in extra else 0, 0.5, True, batches=2, sel=sel)
+        limits = {"min_insert_size": int(extra[extra.index("-I") + 1]), "max_insert_size": int(extra[extra.index("-X") + 1])} if "-I" in extra else {}
+        sel = mapper_port.Selector(fast_pairing=1 if "--fast-pairing" in extra else 0, strata=1 if "--strata" in extra else 0, **limits)
+        got, _ = oracle_sam(d, read_len, 1 if "-e" in extra else 0, 0.5, True, batches=2, sel=sel, limits=limits)
     diff(got, want)
 
 
