@@ -139,13 +139,23 @@ def test_paired_sam_identical_to_ngm(ref_len, n_frags, read_len, seed, extra):
 
 
 @pytest.mark.skipif(not e2e.available("ref"), reason="oracle/_ref/ngm/ngm_ref not built")
-def test_single_end_sam_identical_to_ngm():
+@pytest.mark.parametrize("extra,filters,sub_rate,indels", [([], {}, 0.02, 0.15), (["-i", "0.93", "-R", "0.9"], {"min_identity": 0.93, "min_residues": 0.9}, 0.06, 0.4)])
+def test_single_end_sam_identical_to_ngm(extra, filters, sub_rate, indels):
+    """The second case tightens the output filters of GenericReadWriter::WriteRead (`-i`, `-R`): 17 % of the reads come out unmapped."""
+    from nextgenmap_b200.host import pipeline
     with tempfile.TemporaryDirectory(prefix="se_") as td:
         d = Path(td)
-        e2e.write_inputs(d, ref_len=500_000, n_reads=1500, read_len=100, seed=99, indel_reads=0.15)
-        want = [ln for ln in e2e.run("ref", d, threads=2, extra=["-s", "0.5"]) if not ln.startswith("@")]
-        got, _ = oracle_sam(d, 100, 0, 0.5, False)
+        e2e.write_inputs(d, ref_len=500_000, n_reads=1500, read_len=100, seed=99, sub_rate=sub_rate, indel_reads=indels)
+        want = [ln for ln in e2e.run("ref", d, threads=2, extra=["-s", "0.5", *extra]) if not ln.startswith("@")]
+        orig = pipeline.sam_lines
+        pipeline.sam_lines = lambda *a, **k: orig(*a, **filters, **k)
+        try:
+            got, _ = oracle_sam(d, 100, 0, 0.5, False)
+        finally:
+            pipeline.sam_lines = orig
     diff(got, want)
+    if filters:
+        assert sum(1 for ln in want if ln.split("\t")[1] == "4") > 100
 
 
 def with_heap(batch):
