@@ -327,6 +327,7 @@ typedef struct ngm_b200_sam_opts {
 	int32_t min_insert_size;    /* "min_insert_size" (0), inclusive in the check of the aligned mates */
 	int32_t max_insert_size;    /* "max_insert_size" (1000); <= 0 = INT_MAX */
 	int32_t threads;            /* host threads; 0 = all */
+	int32_t min_mq;             /* "min_mq" (0): reads below it are written as unmapped (AlignmentBuffer.cpp:46-49, GenericReadWriter.h:281-284) */
 } ngm_b200_sam_opts;
 /* One batch as the calls above leave it, all host pointers.  Paired runs: rows 2f / 2f + 1 are mates and pair_fail != NULL. */
 typedef struct ngm_b200_sam_batch {

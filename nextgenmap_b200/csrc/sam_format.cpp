@@ -64,7 +64,7 @@ void collect_at(const Job &j, int r, int bp, const ngm_b200_align_rec *rec, Read
 	v.seq = b.reads + (size_t) r * b.stride;
 	v.qual = b.quals + (size_t) r * b.stride;
 	v.length = (int) strnlen(v.seq, (size_t) b.stride);
-	if (bp >= 0 && rec->score >= 0.0f) {
+	if (bp >= 0 && rec->score >= 0.0f && b.mapq[r] >= j.o->min_mq) {          // AlignmentBuffer.cpp:46-49: below min_mq = unmapped, never aligned
 		const ngm_b200_pair &p = b.pairs[bp];
 		v.has = true;
 		v.bp = bp;

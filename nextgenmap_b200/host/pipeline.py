@@ -192,13 +192,14 @@ class _Read:
     r: int = -1
 
 
-def _collect(batch, reads: np.ndarray, names, quals, encref) -> List[_Read]:
+def _collect(batch, reads: np.ndarray, names, quals, encref, min_mq: int = 0) -> List[_Read]:
     out = []
     for r in range(reads.shape[0]):
         seq = reads[r].tobytes().split(b"\0")[0]
         rd = _Read(names[r], seq, quals[r], len(seq), r=r)
         bp = int(batch.best_pair[r])
-        if bp >= 0 and float(batch.recs[r]["score"]) >= 0.0:
+        # AlignmentBuffer::addRead (AlignmentBuffer.cpp:46-49): a read below min_mq is written as unmapped without being aligned
+        if bp >= 0 and float(batch.recs[r]["score"]) >= 0.0 and int(batch.mapq[r]) >= min_mq:
             p = batch.pairs[bp]
             rd.has, rd.bp = True, bp
             rd.reverse = bool(int(p["flags"]) & 1)
@@ -246,10 +247,10 @@ def _unmapped_line(rd: _Read, flags: int, rname: str = "*", loc: int = -1, rnext
 
 
 def sam_lines(sw: Optional[CudaSW], batch, reads: np.ndarray, names: Sequence[str], quals: Sequence[bytes], encref, corridor: int,
-              min_identity: float = 0.65, min_residues: float = 0.5) -> List[str]:
+              min_identity: float = 0.65, min_residues: float = 0.5, min_mq: int = 0) -> List[str]:
     """SAM body lines of a single-end batch (no header), one per read, in read order."""
     out = []
-    for rd in _collect(batch, reads, names, quals, encref):
+    for rd in _collect(batch, reads, names, quals, encref, min_mq):
         if rd.has and rd.converted and _passes(batch, rd, min_identity, min_residues):
             out.append(_mapped_line(batch, rd, encref, 0, "*", -1, 0))
         else:
@@ -307,7 +308,7 @@ def sam_lines_paired(batch, reads: np.ndarray, names: Sequence[str], quals: Sequ
                      min_residues: float = 0.5, min_mq: int = 0, min_insert_size: int = 0, max_insert_size: int = 1000) -> List[str]:
     """SAM body lines of a paired batch, two per fragment: AlignmentBuffer::WriteRead's pair check (AlignmentBuffer.cpp:176-200),
     GenericReadWriter::WritePair's filters (GenericReadWriter.h:258-312) and SAMWriter::DoWritePair (SAMWriter.cpp:230-310)."""
-    rds = _collect(batch, reads, names, quals, encref)
+    rds = _collect(batch, reads, names, quals, encref, min_mq)
     if max_insert_size <= 0:
         max_insert_size = 2 ** 31 - 1
     out = []
@@ -322,7 +323,7 @@ def sam_lines_paired(batch, reads: np.ndarray, names: Sequence[str], quals: Sequ
             if a.contig != b.contig or d < min_insert_size or d > max_insert_size or a.reverse == b.reverse:
                 fail = True
         for rd in (a, b):                               # WritePair: mapped1 / mapped2, clearScores() otherwise
-            if rd.has and not (int(batch.mapq[rd.r]) >= min_mq and _passes(batch, rd, min_identity, min_residues)):
+            if rd.has and not _passes(batch, rd, min_identity, min_residues):
                 rd.has = False
         fa, fb = 0x1 | 0x40, 0x1 | 0x80
         ra, rb = encref.contigs[a.contig][0], encref.contigs[b.contig][0]
@@ -350,7 +351,7 @@ def sam_lines_paired(batch, reads: np.ndarray, names: Sequence[str], quals: Sequ
 
 
 def format_sam(batch, reads: np.ndarray, names: Sequence[str], quals: Sequence[bytes], encref, paired: bool, min_identity: float = 0.65,
-               min_residues: float = 0.5, min_insert_size: int = 0, max_insert_size: int = 1000, threads: int = 0) -> bytes:
+               min_residues: float = 0.5, min_insert_size: int = 0, max_insert_size: int = 1000, threads: int = 0, min_mq: int = 0) -> bytes:
     """The same lines as ``sam_lines`` / ``sam_lines_paired`` from the library's multi-threaded formatter (``ngm_b200_format_sam``): what a
     C / C++ host calls.  ``encref``: an ``EncodedReference`` (the C struct is handed over as it is).  ``batch.recs`` / ``batch.heap`` as
     ``ngm_b200_align_pairs`` returned them."""
@@ -373,7 +374,7 @@ def format_sam(batch, reads: np.ndarray, names: Sequence[str], quals: Sequence[b
     n_sel = np.ascontiguousarray(batch.n_sel, dtype=np.int32) if topn else None
     sb = SamBatch(n, stride, reads.ctypes.data, q.ctypes.data, name_arr, ptr(keep[0]), ptr(keep[1]), ptr(keep[2]), ptr(keep[3]), ptr(keep[4]), ptr(keep[5]),
                   ptr(keep[6]), ptr(keep[7]), ptr(keep[8]), topn if topn > 1 else 0, ptr(sel), ptr(n_sel))
-    so = SamOpts(min_identity, min_residues, min_insert_size, max_insert_size, threads)
+    so = SamOpts(min_identity, min_residues, min_insert_size, max_insert_size, threads, min_mq)
     used = C.c_size_t(0)
     cap = n * max(topn, 1) * (2 * stride + 256) + 4096
     for _ in range(2):

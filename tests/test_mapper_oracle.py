@@ -266,3 +266,26 @@ def test_native_sam_formatter_topn_equals_host_mirror():
         got = pipeline.format_sam(batch, reads, names, quals, ref.as_encoded_reference(), False, threads=threads).decode().splitlines()
         assert got == want
     assert sorted(want) == gzip.open(GOLD / "se_topn3_l100.sam.gz", "rt").read().splitlines()
+
+
+@pytest.mark.skipif(not e2e.available("ref"), reason="oracle/_ref/ngm/ngm_ref not built")
+@pytest.mark.parametrize("paired", [False, True])
+def test_min_mq_identical_to_ngm(paired):
+    """`-Q 20`: reads below the mapping quality are written as unmapped without being aligned (AlignmentBuffer.cpp:46-49), for pairs
+    through WritePair's mapped1 / mapped2 (GenericReadWriter.h:281-284); mirror and native formatter against NGM's SAM."""
+    from nextgenmap_b200.host import EncodedReference, pipeline
+    with tempfile.TemporaryDirectory(prefix="minmq_") as td:
+        d = Path(td)
+        e2e.write_paired_inputs(d, ref_len=400_000, n_frags=700, read_len=100, seed=81)
+        want = [ln for ln in e2e.run("ref", d, threads=1, extra=["-s", "0.5", "-Q", "20"] + (["-p"] if paired else [])) if not ln.startswith("@")]
+        ref = EncodedReference(str(d / "ref.fa-enc.2.ngm"))
+        names, seqs, quals = read_fastq(d / "reads.fq", paired)
+    reads = rows(seqs, 102)
+    ix = cs_port.Index(ref.packed, ref.concat_len, [(c[1], c[2]) for c in ref.contigs], k=13)
+    batch = with_heap(mapper_port.map_batch(ref.packed, ref.concat_len, ix, reads, 102, 20, 0, 0.5, mapper_port.Selector(), paired=paired))
+    ix.close()
+    got = pipeline.sam_lines_paired(batch, reads, names, quals, ref, 20, min_mq=20) if paired else pipeline.sam_lines(None, batch, reads, names, quals, ref, 20, min_mq=20)
+    assert pipeline.format_sam(batch, reads, names, quals, ref, paired, min_mq=20).decode().splitlines() == got
+    diff(sorted(got), want)
+    assert sum(1 for ln in want if int(ln.split("\t")[1]) & 4) > 300
+    ref.close()
