@@ -28,7 +28,7 @@ extern "C" {
 #pragma GCC visibility push(default)   /* the library itself is built with -fvisibility=hidden */
 #endif
 
-#define NGM_B200_ABI_VERSION 1
+#define NGM_B200_ABI_VERSION 1   /* round 2 only adds entry points */
 
 enum {
 	NGM_B200_OK = 0,
@@ -366,6 +366,89 @@ int ngm_b200_dev_select_topn(ngm_b200_ctx *ctx, int n_reads, const void *d_cand_
  * cand_begin[n_reads] <= capacity afterwards.  d_votes / d_max_hit may be NULL. */
 int ngm_b200_dev_cs_search(ngm_b200_ctx *ctx, const void *d_ascii_reads, int n_reads, int stride, int mode_flags, void *d_cand_begin,
 		void *d_pairs, void *d_votes, uint32_t capacity, void *d_max_hit, void *stream);
+/* -- a whole scored + aligned batch in one call, pipelined inside the library -------------------------------------
+ * ScoreBuffer::DoRun (window fetch, BatchScore, top1SE / top1PE + computeMQ; ScoreBuffer.cpp:80-277,365-502) followed by
+ * AlignmentBuffer::DoRun (BatchAlign + computeCigarMD; AlignmentBuffer.cpp:64-147) for n_reads reads whose candidate lists the
+ * caller already holds (CS::SendToBuffer, CS.cpp:320-335).  This is the entry point north_star's re-plumbed ScoreBuffer /
+ * AlignmentBuffer submit to: reads and (read x candidate) descriptors packed into pinned staging buffers.
+ *
+ * Inside, the batch is cut into sub-batches that rotate over several lanes (stream + device staging each): the host->device copy of
+ * sub-batch i+1, the kernels of sub-batch i and the device->host copy of sub-batch i-1 overlap, like the reference overlaps packing
+ * with its kernels (SWOcl.cpp:435-444).  Reads with a single candidate skip BatchScore: their score is the maximum the alignment's
+ * forward pass finds anyway (same recurrence), so results are identical.
+ *
+ * Read formats.  ASCII: n_reads rows of `read_stride` bytes, NUL padded (MappedRead::Seq).  PACKED2: rows of `read_stride` bytes
+ * (a multiple of 4) holding 2 bits per base, base i in bits [2(i & 15), +2) of little-endian word i >> 4, A0 C1 G2 T3; read_len[r] =
+ * bases in row r; every base that is not A/C/G/T is listed in `exceptions` (sorted by read, then position) with its ASCII byte.
+ * 150 bp: 40 + 2 instead of 152 bytes per read cross PCIe.
+ * Descriptor formats.  PAIR16: ngm_b200_pair (read_index is ignored: candidate lists are given by cand_begin).  U64: NGM_B200_DESC(). */
+typedef struct ngm_b200_read_exc {
+	uint32_t read_index;
+	uint16_t pos;
+	uint8_t ch;                 /* the ASCII byte ('N', IUPAC, ...) */
+	uint8_t pad;
+} ngm_b200_read_exc;
+
+enum { NGM_B200_READS_ASCII = 0, NGM_B200_READS_PACKED2 = 1 };
+enum { NGM_B200_DESC_PAIR16 = 0, NGM_B200_DESC_U64 = 1 };
+/* window_start in bits 0..55 (saturated: a start that underflowed or lies behind the reference selects the all-'N' window either way,
+ * ScoreBuffer.cpp:113-118), NGM_B200_PAIR_* flags in bits 56..63 */
+#define NGM_B200_DESC(window_start, flags) \
+	((((uint64_t) (window_start)) > 0x00FFFFFFFFFFFFFFull ? 0x00FFFFFFFFFFFFFFull : ((uint64_t) (window_start))) | ((uint64_t) (flags) << 56))
+
+typedef struct ngm_b200_batch_in {
+	int32_t n_reads;
+	int32_t mode;               /* NGM_B200_MODE_* */
+	int32_t paired;             /* rows 2f / 2f + 1 are mates; needs ngm_b200_pe_configure */
+	int32_t read_format;        /* NGM_B200_READS_* */
+	const void *reads;
+	int32_t read_stride;        /* bytes per row */
+	int32_t desc_format;        /* NGM_B200_DESC_* */
+	const uint16_t *read_len;   /* PACKED2 only */
+	const ngm_b200_read_exc *exceptions;   /* PACKED2 only; may be NULL when n_exceptions == 0 */
+	uint32_t n_exceptions;
+	uint32_t n_desc;            /* ngm_b200_dev_run_batch: number of descriptors (0 = cand_begin[n_reads] is read back: one stream synchronisation) */
+	const int32_t *cand_begin;  /* n_reads + 1 offsets into desc */
+	const void *desc;           /* cand_begin[n_reads] descriptors */
+} ngm_b200_batch_in;
+
+typedef struct ngm_b200_batch_out {
+	float *scores;              /* optional (may be NULL): cand_begin[n_reads] BatchScore results (LocationScore::Score.f) */
+	int32_t *best_pair;         /* n_reads: index of the candidate handed to alignment, or -1 */
+	int32_t *mapq;              /* n_reads */
+	int32_t *num_top;           /* n_reads, optional */
+	int32_t *pair_fail;         /* n_reads, paired batches only */
+	ngm_b200_align_rec *recs;   /* n_reads: alignment of the selected candidate (score -1 when there is none) */
+	char *strings;              /* CIGAR / MD heap; recs[].str_off are offsets into it.  The heap is filled per sub-batch, so it is sparse:
+	                             * sub-batch k owns [k * slot, (k + 1) * slot), slot = str_capacity / number of sub-batches (16-byte aligned) */
+	size_t str_capacity;
+	size_t str_used;            /* out: bytes of CIGAR / MD text.  NGM_B200_ERANGE: a sub-batch needed more than its slot; str_used then holds a
+	                             * sufficient total capacity for a repeat of the call */
+	uint32_t *d_str_cursor;     /* ngm_b200_dev_run_batch only: device word that receives the heap bytes used (dense heap, one sub-batch) */
+} ngm_b200_batch_out;
+
+/* Host buffers in, host buffers out; returns n_reads.  For copies that overlap with the kernels the buffers must be page-locked:
+ * ngm_b200_host_alloc / ngm_b200_host_register (pageable memory works, but every copy then stalls its lane). */
+int ngm_b200_run_batch(ngm_b200_ctx *ctx, const ngm_b200_batch_in *in, ngm_b200_batch_out *out);
+/* The same with every pointer of `in` / `out` on the device: one sub-batch, enqueued on `stream`, not synchronised (resident
+ * pipelines; bench.py `value`).  out->str_used is not written; out->d_str_cursor receives the bytes used. */
+int ngm_b200_dev_run_batch(ngm_b200_ctx *ctx, const ngm_b200_batch_in *in, ngm_b200_batch_out *out, void *stream);
+/* Lanes (1..8, default 3) and reads per sub-batch (default 1 << 20) of ngm_b200_run_batch / ngm_b200_map_batch. */
+int ngm_b200_set_pipeline(ngm_b200_ctx *ctx, int lanes, int sub_batch_reads);
+/* "strata" for single-end runs (ScoreBuffer::top1SE, ScoreBuffer.cpp:259-276): a read with several equally best candidates is reported
+ * unmapped (best_pair -1, mapq 0).  Applies to ngm_b200_dev_select_top1[_ex], ngm_b200_run_batch and ngm_b200_map_batch. */
+int ngm_b200_se_configure(ngm_b200_ctx *ctx, int strata);
+/* Page-locked host memory for the staging buffers (cudaHostAlloc / cudaHostRegister). */
+void *ngm_b200_host_alloc(size_t bytes);
+void ngm_b200_host_free(void *p);
+int ngm_b200_host_register(void *p, size_t bytes);
+int ngm_b200_host_unregister(void *p);
+/* ASCII rows -> PACKED2 on the host (what a re-plumbed ScoreBuffer does while it fills its staging buffer).  packed: n rows of
+ * row_bytes (>= 4 * ceil(stride / 16)); exceptions: capacity exc_cap, *n_exc receives the number needed (NGM_B200_ERANGE if larger).
+ * threads: host threads to use (0 = all). */
+int ngm_b200_pack_reads(const char *ascii, int n_reads, int stride, void *packed, int row_bytes, uint16_t *read_len, ngm_b200_read_exc *exceptions,
+		size_t exc_cap, size_t *n_exc, int threads);
+
 /* Number of kernels this context has launched since creation (bench.py gpu_launches). */
 uint64_t ngm_b200_launch_count(const ngm_b200_ctx *ctx);
 

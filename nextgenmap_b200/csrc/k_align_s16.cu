@@ -1,7 +1,10 @@
 // k_align_s16.cu -- instantiations + launcher of the tagged s16x2 align path:
 // forward kernel (two alignments per thread) + backtrace/format kernel (one alignment per thread).
 #include "ngm_launch.h"
+#include <cstdlib>
+
 #include "ngm_align_s16.cuh"
+#include "ngm_align_s16v2.cuh"
 
 namespace ngm {
 
@@ -10,8 +13,35 @@ cudaError_t launch_align_s16(int capacity, int mode, const AlignArgs &a, cudaStr
 	const int threads = (a.n + 1) / 2;
 	const dim3 block(128), grid((threads + 127) / 128);
 	bool launched = false;
+	// second-generation forward pass (ngm_align_s16v2.cuh): narrow local bands and every end-free band.  NGM_B200_FWD=1 keeps the
+	// first-generation kernel (A/B measurements, tests of both).
+	static const bool use_v1 = [] { const char *e = getenv("NGM_B200_FWD"); return e != nullptr && atoi(e) == 1; }();
+	if (!use_v1) {
 #define X(W, LO) \
-	if (capacity == W) { \
+		if (capacity == W && !launched) { \
+			if constexpr (W <= kAlignS16MaxLocal) { \
+				if (mode == 0) { \
+					constexpr int smem = 3 * W * 128 * 4; \
+					static const cudaError_t attr = cudaFuncSetAttribute(align_s16_fwd2_kernel<W, LO, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+					if (attr != cudaSuccess) return attr; \
+					align_s16_fwd2_kernel<W, LO, 0><<<grid, block, smem, st>>>(a.P, a.pairs, a.n, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, \
+							a.ptr_scratch, a.stride, a.best_scratch); \
+					launched = true; \
+				} \
+			} \
+			if constexpr (W <= kAlignS16MaxEndFree) { \
+				if (mode == 1) { \
+					align_s16_fwd2_kernel<W, LO, 1><<<grid, block, 0, st>>>(a.P, a.pairs, a.n, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, \
+							a.ptr_scratch, a.stride, a.best_scratch); \
+					launched = true; \
+				} \
+			} \
+		}
+		NGM_BAND_LIST(X)
+#undef X
+	}
+#define X(W, LO) \
+	if (capacity == W && !launched) { \
 		if constexpr (W <= kAlignS16MaxLocal) { \
 			if (mode == 0) { \
 				align_s16_fwd_kernel<W, LO, 0, false><<<grid, block, 0, st>>>(a.P, a.pairs, a.n, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, \
@@ -41,10 +71,10 @@ cudaError_t launch_align_s16(int capacity, int mode, const AlignArgs &a, cudaStr
 	const dim3 b2(256), g2((a.n + 255) / 256);
 	if (mode == 0)
 		backtrace_format_kernel<0><<<g2, b2, 0, st>>>(a.P, a.pairs, a.n, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, a.ptr_scratch, capacity,
-				a.best_scratch, a.ops_scratch, a.stride, a.ops_cap, a.recs, a.strings, a.str_cap, a.cursor);
+				a.best_scratch, a.ops_scratch, a.stride, a.ops_cap, a.recs, a.strings, a.str_cap, a.cursor, a.out_best);
 	else
 		backtrace_format_kernel<1><<<g2, b2, 0, st>>>(a.P, a.pairs, a.n, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, a.ptr_scratch, capacity,
-				a.best_scratch, a.ops_scratch, a.stride, a.ops_cap, a.recs, a.strings, a.str_cap, a.cursor);
+				a.best_scratch, a.ops_scratch, a.stride, a.ops_cap, a.recs, a.strings, a.str_cap, a.cursor, a.out_best);
 	return cudaGetLastError();
 }
 

@@ -19,8 +19,8 @@ cudaError_t launch_score_i32(int capacity, int mode, const ScoreArgs &a, cudaStr
 	const dim3 block(128), grid((a.n + 127) / 128);
 #define X(W, LO) \
 	if (capacity == W) { \
-		if (mode == 0) score_i32_kernel<W, LO, 0><<<grid, block, 0, st>>>(a.P, a.pairs, a.n, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, a.out); \
-		else score_i32_kernel<W, LO, 1><<<grid, block, 0, st>>>(a.P, a.pairs, a.n, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, a.out); \
+		if (mode == 0) score_i32_kernel<W, LO, 0><<<grid, block, 0, st>>>(a.P, a.pairs, a.n, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, a.out, a.sel, a.n_dev); \
+		else score_i32_kernel<W, LO, 1><<<grid, block, 0, st>>>(a.P, a.pairs, a.n, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, a.out, a.sel, a.n_dev); \
 		return cudaGetLastError(); \
 	}
 	NGM_BAND_LIST(X)

@@ -251,6 +251,7 @@ __global__ void __launch_bounds__(128) align_s16_fwd_kernel(const __grid_constan
 	bool act_b = load_pair(P, pairs, ib, reads_fwd, reads_rev, rlen, ref4, cb, fb) && vb;
 	const int corridor = P.corridor;
 	const uint32_t gr2 = pack2(4 * P.gap_read + 1, 4 * P.gap_read + 1), gf2 = pack2(4 * P.gap_ref, 4 * P.gap_ref);
+	const uint32_t c_four = P.c_four, c_neg1 = P.c_neg1;
 	const int tstride = stride >> 1;                             // thread slots per launch
 	// pointer matrix layout [row q][column group][thread slot]: the words of one group and row are contiguous
 	// over thread slots, so the forward stores and the backtrace loads of a warp are both fully coalesced
@@ -328,7 +329,7 @@ __global__ void __launch_bounds__(128) align_s16_fwd_kernel(const __grid_constan
 						uint32_t h = MODE == 0 ? __viaddmax_s16x2_relu(left, gf2, u) : __viaddmax_s16x2(left, gf2, u);
 						if (j >= LO) h = (j < corridor) ? h : SENT2;
 						const uint32_t clean = h & 0xFFFCFFFCu;
-						pw[j >> 3] = pw[j >> 3] * 4u + (h - clean);
+						pw[j >> 3] = imad_u32(pw[j >> 3], c_four, imad_u32(clean, c_neg1, h));      // 4 * pw + (h - clean), both on the FMA pipe
 						left = clean;
 						line[j] = clean;
 					}
@@ -446,7 +447,7 @@ __global__ void __launch_bounds__(256) backtrace_format_kernel(const __grid_cons
 		const uint32_t *__restrict__ reads_fwd, const uint32_t *__restrict__ reads_rev, const uint16_t *__restrict__ rlen,
 		const uint32_t *__restrict__ ref4, const uint32_t *__restrict__ ptr_scratch, int capacity, const int4 *__restrict__ best_in,
 		uint16_t *__restrict__ ops_scratch, int stride, int ops_cap, ngm_b200_align_rec *__restrict__ recs, char *__restrict__ strings,
-		uint32_t str_cap, uint32_t *__restrict__ cursor) {
+		uint32_t str_cap, uint32_t *__restrict__ cursor, float *__restrict__ out_best) {
 	__shared__ uint2 s_lut[16];
 	__shared__ uint32_t s_ring[kRing][256];
 	if (threadIdx.x < 16) s_lut[threadIdx.x] = P.lut[threadIdx.x];
@@ -456,7 +457,9 @@ __global__ void __launch_bounds__(256) backtrace_format_kernel(const __grid_cons
 	const int id = valid ? idx : 0;
 	PairCtx c;
 	uint32_t flags;
-	load_pair(P, pairs, id, reads_fwd, reads_rev, rlen, ref4, c, flags);
+	const bool active = load_pair(P, pairs, id, reads_fwd, reads_rev, rlen, ref4, c, flags);
+	// the forward pass's maximum is the pair's BatchScore result in this mode (oclSW / oclSW_Global compute the same recurrence)
+	if (out_best != nullptr && valid) out_best[idx] = active ? (float) best_in[id].z : (MODE == 0 ? -1.0f : (float) kEndFreeMin);
 	BandRt geo;
 	geo.cap = capacity;
 	geo.words = (capacity + 7) / 8;

@@ -1,0 +1,258 @@
+// ngm_align_s16v2.cuh -- second-generation forward pass of the tagged s16x2 align path (narrow bands).
+//
+// Same arithmetic, pointer-matrix layout and results as align_s16_fwd_kernel (ngm_align_s16.cuh); what changed
+// is where the instructions go.  The first-generation kernel is bound by the integer ALU pipe (64 lanes / clk / SM:
+// PRMT, LOP3, VIADD, VIADDMNMX, VIMNMX3, SEL all share it) while the FMA pipe idles:
+//
+//   * the tag arithmetic runs on the FMA pipe: tag = h - clean and pw = 4 * pw + tag are issued as IMADs whose
+//     multipliers (-1, 4) come from the kernel parameters, so ptxas cannot strength-reduce them back into
+//     LOP3 / LEA on the ALU pipe;
+//   * local mode no longer keeps a per-row snapshot of the band in registers (one PRMT per band register and row).
+//     Instead the band is CHECKPOINTED to shared memory once per eight rows (one STS per band register and eight
+//     rows, LSU pipe), the running maximum is tracked per block of eight rows only, and after the last row the
+//     eight rows of the block in which each half's maximum first appeared are REPLAYED from that block's checkpoint
+//     to find the best cell (first strict maximum in row-major order, oclSwScore.cl:88-91).  Three checkpoint
+//     buffers rotate per thread: one owned by each half (the block of its last improvement) and one being written.
+//
+// Reference semantics: oclSW_Score / oclSW_ScoreGlobal (oclSwScore.cl:4-107, oclEndFreeScore.cl:58-146).
+#pragma once
+
+#include "ngm_align_s16.cuh"
+
+namespace ngm {
+
+// One DP row for both halves.  PTR: accumulate + return the pointer words of the row.
+template <int W, int LO, int MODE, bool PTR>
+__device__ __forceinline__ void fwd2_row(uint32_t (&line)[W + 1], const uint32_t (&wa)[BandGeom<W>::kWin], const uint32_t (&wb)[BandGeom<W>::kWin],
+		const int t, const uint2 ta, const uint2 tb, const uint32_t gr2, const uint32_t gf2, const uint32_t SENT2, const int corridor,
+		const uint32_t c_four, const uint32_t c_neg1, uint32_t (&pw)[TagGeom<W>::kWords]) {
+	using G = BandGeom<W>;
+	uint32_t ala[G::kAligned], alb[G::kAligned];
+#pragma unroll
+	for (int k = 0; k < G::kAligned; ++k) {
+		ala[k] = t == 0 ? wa[k] : __funnelshift_r(wa[k], wa[k + 1], 4 * t);
+		alb[k] = t == 0 ? wb[k] : __funnelshift_r(wb[k], wb[k + 1], 4 * t);
+	}
+	uint32_t left = SENT2;
+	if (PTR) {
+#pragma unroll
+		for (int k = 0; k < TagGeom<W>::kWords; ++k) pw[k] = 0;
+	}
+#pragma unroll
+	for (int m = 0; m < G::kGroups; ++m) {
+		const uint32_t sa = prmt(ta.x, ta.y, (m & 1) ? (ala[m >> 1] >> 16) : ala[m >> 1]);
+		const uint32_t sb = prmt(tb.x, tb.y, (m & 1) ? (alb[m >> 1] >> 16) : alb[m >> 1]);
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			const int j = 4 * m + i;
+			const uint32_t s2 = i == 0 ? sbyte2<0>(sa, sb) : i == 1 ? sbyte2<1>(sa, sb) : i == 2 ? sbyte2<2>(sa, sb) : sbyte2<3>(sa, sb);
+			const uint32_t d = __vadd2(line[j], s2);
+			const uint32_t u = __viaddmax_s16x2(line[j + 1], gr2, d);
+			uint32_t h = MODE == 0 ? __viaddmax_s16x2_relu(left, gf2, u) : __viaddmax_s16x2(left, gf2, u);
+			if (j >= LO) h = (j < corridor) ? h : SENT2;
+			const uint32_t clean = h & 0xFFFCFFFCu;
+			if (PTR) {
+				const uint32_t tag = imad_u32(clean, c_neg1, h);          // h - clean, FMA pipe
+				pw[j >> 3] = imad_u32(pw[j >> 3], c_four, tag);           // 4 * pw + tag, FMA pipe
+			}
+			left = clean;
+			line[j] = clean;
+		}
+	}
+}
+
+template <int W>
+__device__ __forceinline__ uint32_t band_max(const uint32_t (&line)[W + 1], uint32_t acc) {
+#pragma unroll
+	for (int j = 0; j + 1 < W; j += 2) acc = __vimax3_s16x2(acc, line[j], line[j + 1]);
+	if (W & 1) acc = __vmaxs2(acc, line[W - 1]);
+	return acc;
+}
+
+template <int W, int LO, int MODE>
+__global__ void __launch_bounds__(128) align_s16_fwd2_kernel(const __grid_constant__ DevParams P, const PairDesc *__restrict__ pairs, int n,
+		const uint32_t *__restrict__ reads_fwd, const uint32_t *__restrict__ reads_rev, const uint16_t *__restrict__ rlen,
+		const uint32_t *__restrict__ ref4, uint32_t *__restrict__ ptr_scratch, int stride, int4 *__restrict__ best_out) {
+	using G = BandGeom<W>;
+	using T = TagGeom<W>;
+	extern __shared__ uint32_t s_chk[];                           // local mode: [3][W][128] checkpoint words, one column per thread
+	__shared__ uint2 s_lut4[16];
+	if (threadIdx.x < 16) s_lut4[threadIdx.x] = P.lut4[threadIdx.x];
+	__syncthreads();
+	const int t2 = blockIdx.x * blockDim.x + threadIdx.x;        // thread slot: pairs 2*t2, 2*t2 + 1
+	const int ia = 2 * t2;
+	if (ia >= n) return;
+	const bool vb = ia + 1 < n;
+	const int ib = vb ? ia + 1 : ia;
+	constexpr int SENT = MODE == 0 ? 0 : 4 * kEndFreeMinS16;
+	const uint32_t SENT2 = pack2(SENT, SENT);
+	PairCtx ca, cb;
+	uint32_t fa, fb;
+	const bool act_a = load_pair(P, pairs, ia, reads_fwd, reads_rev, rlen, ref4, ca, fa);
+	const bool act_b = load_pair(P, pairs, ib, reads_fwd, reads_rev, rlen, ref4, cb, fb) && vb;
+	const int corridor = P.corridor;
+	const uint32_t gr2 = pack2(4 * P.gap_read + 1, 4 * P.gap_read + 1), gf2 = pack2(4 * P.gap_ref, 4 * P.gap_ref);
+	const uint32_t c_four = P.c_four, c_neg1 = P.c_neg1;
+	const int tstride = stride >> 1;
+	const size_t row_stride = (size_t) tstride * T::kWords;
+	uint32_t *prow = ptr_scratch + (size_t) t2;
+	uint32_t *chk = s_chk + threadIdx.x;
+	auto chk_at = [&](int buf, int j) -> uint32_t * { return chk + (buf * W + j) * 128; };
+
+	uint32_t line[W + 1];
+#pragma unroll
+	for (int j = 0; j <= W; ++j) line[j] = (j < corridor) ? 0u : SENT2;
+	uint32_t best = 0;
+	int rc_a = 0, rc_b = 0;
+	// checkpoint bookkeeping (local mode): per half the buffer, block and row count of the block of its last improvement
+	int own_a = 0, own_b = 0, blk_a = 0, blk_b = 0, rc0_a = 0, rc0_b = 0;
+	uint32_t wa[G::kWin], wb[G::kWin];
+	const int wend_a = ca.sub + ca.len + corridor - 1, wend_b = cb.sub + cb.len + corridor - 1;
+	auto nib_mask = [](int valid) { return valid >= 8 ? 0xFFFFFFFFu : (valid <= 0 ? 0u : ((1u << (4 * valid)) - 1u)); };
+	uint32_t spec_a = 0, spec_b = 0;
+#pragma unroll
+	for (int k = 0; k < G::kWin; ++k) {
+		wa[k] = __ldg(ca.wp + k);
+		wb[k] = __ldg(cb.wp + k);
+		spec_a |= wa[k] & nib_mask(wend_a - 8 * k);
+		spec_b |= wb[k] & nib_mask(wend_b - 8 * k);
+	}
+	const int nqw = max(act_a ? (ca.sub + ca.len + 7) >> 3 : 0, act_b ? (cb.sub + cb.len + 7) >> 3 : 0);
+	const uint2 *luta = s_lut4 + ca.dir * 8, *lutb = s_lut4 + cb.dir * 8;
+	uint32_t prev_a = kNulWord, prev_b = kNulWord;
+	for (int qw = 0; qw < nqw; ++qw) {
+		const uint32_t cur_a = __ldg(ca.rp + qw), cur_b = __ldg(cb.rp + qw);
+		const uint32_t rda = __funnelshift_l(prev_a, cur_a, 4 * ca.sub);
+		const uint32_t rdb = __funnelshift_l(prev_b, cur_b, 4 * cb.sub);
+		prev_a = cur_a;
+		prev_b = cur_b;
+		const uint32_t next_a = __ldg(ca.wp + qw + G::kWin), next_b = __ldg(cb.wp + qw + G::kWin);
+		spec_a |= (next_a & nib_mask(wend_a - 8 * (qw + G::kWin))) | (cur_a & nib_mask(ca.len - 8 * qw));
+		spec_b |= (next_b & nib_mask(wend_b - 8 * (qw + G::kWin))) | (cur_b & nib_mask(cb.len - 8 * qw));
+		int cur_buf = 0;
+		const uint32_t best_before = best;
+		const int rcs_a = rc_a, rcs_b = rc_b;
+		if (MODE == 0) {
+			cur_buf = (own_a != 0 && own_b != 0) ? 0 : ((own_a != 1 && own_b != 1) ? 1 : 2);
+#pragma unroll
+			for (int j = 0; j < W; ++j) *chk_at(cur_buf, j) = line[j];
+		}
+#pragma unroll
+		for (int t = 0; t < 8; ++t) {
+			const int rca = (rda >> (4 * t)) & 7, rcb = (rdb >> (4 * t)) & 7;
+			uint32_t pw[T::kWords];
+			fwd2_row<W, LO, MODE, true>(line, wa, wb, t, luta[rca], lutb[rcb], gr2, gf2, SENT2, corridor, c_four, c_neg1, pw);
+#pragma unroll
+			for (int k = 0; k < T::kWords; ++k) prow[(size_t) k * tstride] = pw[k];
+			prow += row_stride;
+			if (MODE == 0) best = band_max<W>(line, best);
+			rc_a += (rca != kCodeNul);
+			rc_b += (rcb != kCodeNul);
+		}
+		if (MODE == 0) {
+			const uint32_t imp = best ^ best_before;
+			if (imp & 0xFFFFu) {
+				own_a = cur_buf;
+				blk_a = qw;
+				rc0_a = rcs_a;
+			}
+			if (imp >> 16) {
+				own_b = cur_buf;
+				blk_b = qw;
+				rc0_b = rcs_b;
+			}
+		}
+#pragma unroll
+		for (int k = 0; k + 1 < G::kWin; ++k) {
+			wa[k] = wa[k + 1];
+			wb[k] = wb[k + 1];
+		}
+		wa[G::kWin - 1] = next_a;
+		wb[G::kWin - 1] = next_b;
+	}
+	HalfBest ba, bb;
+	ba.read_count = rc_a | ((spec_a & 0x44444444u) ? kSpecialFlag : 0);
+	bb.read_count = rc_b | ((spec_b & 0x44444444u) ? kSpecialFlag : 0);
+	if (MODE == 0) {
+		const int ma = (int) (short) (best & 0xFFFFu), mb = (int) (short) (best >> 16);
+		// ---- replay: the block of each half's last improvement, from its checkpoint, until the half reaches its maximum ----
+#pragma unroll
+		for (int j = 0; j < W; ++j) line[j] = prmt(*chk_at(own_a, j), *chk_at(own_b, j), 0x7610u);
+#pragma unroll
+		for (int k = 0; k < G::kWin; ++k) {
+			wa[k] = __ldg(ca.wp + blk_a + k);
+			wb[k] = __ldg(cb.wp + blk_b + k);
+		}
+		const uint32_t pa = blk_a > 0 ? __ldg(ca.rp + blk_a - 1) : kNulWord, pb = blk_b > 0 ? __ldg(cb.rp + blk_b - 1) : kNulWord;
+		const uint32_t rda = __funnelshift_l(pa, __ldg(ca.rp + blk_a), 4 * ca.sub);
+		const uint32_t rdb = __funnelshift_l(pb, __ldg(cb.rp + blk_b), 4 * cb.sub);
+		bool found_a = false, found_b = false;
+		int brow_a = 0, brow_b = 0, rr_a = rc0_a, rr_b = rc0_b;
+#pragma unroll
+		for (int t = 0; t < 8; ++t) {
+			const int rca = (rda >> (4 * t)) & 7, rcb = (rdb >> (4 * t)) & 7;
+			uint32_t pw[T::kWords];
+			fwd2_row<W, LO, MODE, false>(line, wa, wb, t, luta[rca], lutb[rcb], gr2, gf2, SENT2, corridor, c_four, c_neg1, pw);
+			const uint32_t mx = band_max<W>(line, 0u);
+			const bool hit_a = !found_a && (int) (short) (mx & 0xFFFFu) == ma;
+			const bool hit_b = !found_b && (int) (short) (mx >> 16) == mb;
+			// the band of the row in which a half first reaches its maximum goes to a (by now free) checkpoint buffer
+			if (hit_a) {
+#pragma unroll
+				for (int j = 0; j < W; ++j) *chk_at(0, j) = line[j];
+				brow_a = rr_a;
+			}
+			if (hit_b) {
+#pragma unroll
+				for (int j = 0; j < W; ++j) *chk_at(1, j) = line[j];
+				brow_b = rr_b;
+			}
+			found_a = found_a || hit_a;
+			found_b = found_b || hit_b;
+			rr_a += (rca != kCodeNul);
+			rr_b += (rcb != kCodeNul);
+		}
+		int ra = 0, rb = 0;
+		bool fa_ = false, fb_ = false;
+#pragma unroll
+		for (int j = 0; j < W; ++j) {
+			const bool ha = !fa_ && j < corridor && (int) (short) (*chk_at(0, j) & 0xFFFFu) == ma;
+			const bool hb = !fb_ && j < corridor && (int) (short) (*chk_at(1, j) >> 16) == mb;
+			ra = ha ? j : ra;
+			rb = hb ? j : rb;
+			fa_ = fa_ || ha;
+			fb_ = fb_ || hb;
+		}
+		// nothing ever exceeded 0: the reference's first cell (0, 0) holds the maximum (oclSwScore.cl:48,88)
+		ba.best_read = (ma > 0 && found_a) ? brow_a : 0;
+		ba.best_ref = (ma > 0 && found_a) ? ra : 0;
+		ba.best_score = ma >> 2;
+		bb.best_read = (mb > 0 && found_b) ? brow_b : 0;
+		bb.best_ref = (mb > 0 && found_b) ? rb : 0;
+		bb.best_score = mb >> 2;
+	} else {
+		int cma = 4 * kEndFreeMinS16, cmb = 4 * kEndFreeMinS16, ra = 0, rb = 0;
+#pragma unroll
+		for (int j = 0; j < W; ++j) {                 // first strict maximum of the final row (oclEndFreeScore.cl:135-140)
+			const int va_ = (int) (short) (line[j] & 0xFFFFu), vb_ = (int) (short) (line[j] >> 16);
+			const bool ga = j < corridor && va_ > cma, gb = j < corridor && vb_ > cmb;
+			cma = ga ? va_ : cma;
+			ra = ga ? j : ra;
+			cmb = gb ? vb_ : cmb;
+			rb = gb ? j : rb;
+		}
+		ba.best_read = rc_a - 1;
+		ba.best_ref = ra;
+		ba.best_score = cma >> 2;
+		bb.best_read = rc_b - 1;
+		bb.best_ref = rb;
+		bb.best_score = cmb >> 2;
+	}
+	// quad-skipped pairs: what the reference's forward kernel leaves behind (oclSwScore.cl:16-18,104-106)
+	if (!act_a) { ba.best_read = MODE == 0 ? 0 : -1; ba.best_ref = 0; ba.best_score = 0; ba.read_count = 0; }
+	if (!act_b) { bb.best_read = MODE == 0 ? 0 : -1; bb.best_ref = 0; bb.best_score = 0; bb.read_count = 0; }
+	best_out[ia] = make_int4(ba.best_read, ba.best_ref, ba.best_score, ba.read_count);
+	if (vb) best_out[ia + 1] = make_int4(bb.best_read, bb.best_ref, bb.best_score, bb.read_count);
+}
+
+}  // namespace ngm

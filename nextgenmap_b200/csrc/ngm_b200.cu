@@ -104,6 +104,8 @@ int build_params(const ngm_b200_params &hp, DevParams &dp, int &use_s16, int *al
 	dp.acct_slam = hp.slam_seq != 0;
 	dp.hard_clip = hp.hard_clip;
 	dp.silent_clip = hp.silent_clip;
+	dp.c_four = 4u;
+	dp.c_neg1 = 0xFFFFFFFFu;
 	dp.read_words = (hp.qry_max_len + 14) / 8 + 1;
 	dp.rows_cap = 8 * ((hp.qry_max_len + 14) / 8);
 	for (int d = 0; d < 2; ++d)
@@ -194,6 +196,10 @@ void recount_alt(const char *cigar, const char *md, int md_len, const char *ref,
 	*total_out = total;
 }
 
+}  // namespace
+
+namespace ngm {
+
 int mode_of(int mode) {
 	const int m = mode & 0xFF;
 	return (m == 0 || m == 1) ? m : -1;
@@ -238,7 +244,7 @@ int ensure_align_scratch(ngm_b200_ctx *c, int stride) {
 // Launch the align kernel over n resolved pairs in slices of align_chunk.
 int run_align(ngm_b200_ctx *c, int mode, const PairDesc *pairs, int n, const uint32_t *rf, const uint32_t *rr, const uint16_t *rl,
 		const uint32_t *ref4, ngm_b200_align_rec *recs, char *strings, uint32_t str_cap, uint32_t *cursor, cudaStream_t st,
-		const float *known_user = nullptr) {
+		const float *known_user, float *out_best) {
 	const int stride = std::min(std::max(n, 1), c->align_chunk);
 	const int stride_pad = (stride + 127) / 128 * 128;
 	int rc = ensure_align_scratch(c, stride_pad);
@@ -256,6 +262,7 @@ int run_align(ngm_b200_ctx *c, int mode, const PairDesc *pairs, int n, const uin
 		a.ops_scratch = c->d_ops.as<uint16_t>();
 		a.best_scratch = c->d_best.as<int4>();
 		a.known = nullptr;
+		a.out_best = out_best != nullptr ? out_best + s : nullptr;
 		if (mode == 0 && c->align_s16[0] && c->capacity > kAlignS16MaxLocal && known_user != nullptr) {
 			// wide band and the caller already holds the pairs' local maxima (the resident pipeline: BatchScore ran first).
 			// Narrow bands keep the snapshot kernel: measured faster there (19.5 vs 17.8 ms per 10 M x 150 bp, profiles/r1b).
@@ -286,6 +293,10 @@ int run_align(ngm_b200_ctx *c, int mode, const PairDesc *pairs, int n, const uin
 	}
 	return NGM_B200_OK;
 }
+
+}  // namespace ngm
+
+namespace {
 
 // Gather + upload + pack one strict-path chunk (copySeqDataToDevice, SWOcl.cpp:534-556).
 int stage_strict(ngm_b200_ctx *c, int base, int m, const char *const *ref, const char *const *qry, const char *dir) {
@@ -411,6 +422,8 @@ ngm_b200_ctx *ngm_b200_create(const ngm_b200_params *params) {
 void ngm_b200_destroy(ngm_b200_ctx *c) {
 	if (c == nullptr) return;
 	cudaSetDevice(c->device);
+	if (c->batch) batch_release(c->batch);                 // the lanes first: they borrow this context's buffers
+	c->batch = nullptr;
 	if (c->stream) {
 		cudaStreamSynchronize(c->stream);
 		cudaStreamDestroy(c->stream);
@@ -429,7 +442,7 @@ void ngm_b200_destroy(ngm_b200_ctx *c) {
 
 int ngm_b200_score_batch_size(const ngm_b200_ctx *c) { return c ? c->score_batch : 0; }
 int ngm_b200_align_batch_size(const ngm_b200_ctx *c) { return c ? c->align_batch : 0; }
-uint64_t ngm_b200_launch_count(const ngm_b200_ctx *c) { return c ? c->launches : 0; }
+uint64_t ngm_b200_launch_count(const ngm_b200_ctx *c) { return c ? c->launches + batch_lane_launches(c) : 0; }
 
 int ngm_b200_batch_score(ngm_b200_ctx *c, int mode, int n, const char *const *ref, const char *const *qry, float *scores, const char *dir) {
 	if (c == nullptr) return fail(NGM_B200_EINVAL, "ctx == NULL");
@@ -481,7 +494,7 @@ int ngm_b200_batch_align(ngm_b200_ctx *c, int mode, int n, const char *const *re
 			CU(cudaMemsetAsync(c->d_cursor.p, 0, 4, c->stream));
 			rc = run_align(c, m0, c->d_pairs.as<PairDesc>(), m, c->d_reads4.as<uint32_t>(), c->d_reads4.as<uint32_t>(), c->d_rlen.as<uint16_t>(),
 					c->d_wins4.as<uint32_t>(), c->d_recs.as<ngm_b200_align_rec>(), c->d_strings.as<char>(), (uint32_t) str_cap,
-					c->d_cursor.as<uint32_t>(), c->stream);
+					c->d_cursor.as<uint32_t>(), c->stream, nullptr, nullptr);
 			if (rc) return rc;
 			CU(cudaMemcpyAsync(c->h_cursor.p, c->d_cursor.p, 4, cudaMemcpyDeviceToHost, c->stream));
 			CU(cudaStreamSynchronize(c->stream));
@@ -564,6 +577,7 @@ static int transcode_reference(ngm_b200_ctx *c, const uint8_t *d_packed, uint64_
 	c->concat_len = concat_len;
 	c->n_region_nib = n_region_word * 8;
 	c->have_ref = true;
+	c->epoch += 1;
 	return NGM_B200_OK;
 }
 
@@ -612,19 +626,25 @@ int ngm_b200_set_reference(ngm_b200_ctx *c, const uint8_t *packed, uint64_t conc
 	return rc;
 }
 
-static int pack_reads_device(ngm_b200_ctx *c, const uint8_t *d_ascii, int n_reads, int stride, cudaStream_t st) {
+static int pack_reads_device_impl(ngm_b200_ctx *c, const uint8_t *d_ascii, int n_reads, int stride, cudaStream_t st) {
 	const int RW = c->dp.read_words;
 	CU(c->d_rfwd.ensure((size_t) n_reads * RW * 4));
 	CU(c->d_rrev.ensure((size_t) n_reads * RW * 4));
 	CU(c->d_rrlen.ensure((size_t) n_reads * 2));
 	const int width = std::min(stride, c->dp.qml);
 	const long long tot = (long long) n_reads * RW;
-	pack_words_kernel<<<(unsigned) ((tot + 255) / 256), 256, 0, st>>>(d_ascii, n_reads, width, stride, c->d_rfwd.as<uint32_t>(), RW);
-	read_len_kernel<<<(n_reads + 255) / 256, 256, 0, st>>>(c->d_rfwd.as<uint32_t>(), n_reads, RW, c->d_rrlen.as<uint16_t>());
-	revcomp_words_kernel<<<(unsigned) ((tot + 255) / 256), 256, 0, st>>>(c->d_rfwd.as<uint32_t>(), c->d_rrlen.as<uint16_t>(), n_reads, RW,
-			c->d_rrev.as<uint32_t>());
-	c->launches += 2;
-	c->launches += 1;
+	static const bool three_pass = [] { const char *e = getenv("NGM_B200_PACK3"); return e != nullptr && atoi(e) == 1; }();      // A/B measurements
+	if (three_pass) {
+		pack_words_kernel<<<(unsigned) ((tot + 255) / 256), 256, 0, st>>>(d_ascii, n_reads, width, stride, c->d_rfwd.as<uint32_t>(), RW);
+		read_len_kernel<<<(n_reads + 255) / 256, 256, 0, st>>>(c->d_rfwd.as<uint32_t>(), n_reads, RW, c->d_rrlen.as<uint16_t>());
+		revcomp_words_kernel<<<(unsigned) ((tot + 255) / 256), 256, 0, st>>>(c->d_rfwd.as<uint32_t>(), c->d_rrlen.as<uint16_t>(), n_reads, RW,
+				c->d_rrev.as<uint32_t>());
+		c->launches += 3;
+	} else {
+		pack_reads_fused_kernel<<<(n_reads + kPackRowsPerBlock - 1) / kPackRowsPerBlock, 32 * kPackRowsPerBlock, (size_t) kPackRowsPerBlock * RW * 4, st>>>(
+				d_ascii, n_reads, width, stride, c->d_rfwd.as<uint32_t>(), c->d_rrev.as<uint32_t>(), c->d_rrlen.as<uint16_t>(), RW);
+		c->launches += 1;
+	}
 	CU(cudaGetLastError());
 	c->n_reads = n_reads;
 	return NGM_B200_OK;
@@ -635,7 +655,7 @@ int ngm_b200_set_reads(ngm_b200_ctx *c, const char *reads, int n_reads, int stri
 	CU(cudaSetDevice(c->device));
 	CU(c->d_rascii.ensure((size_t) n_reads * stride));
 	CU(cudaMemcpyAsync(c->d_rascii.p, reads, (size_t) n_reads * stride, cudaMemcpyHostToDevice, c->stream));
-	int rc = pack_reads_device(c, c->d_rascii.as<uint8_t>(), n_reads, stride, c->stream);
+	int rc = pack_reads_device_impl(c, c->d_rascii.as<uint8_t>(), n_reads, stride, c->stream);
 	if (rc) return rc;
 	c->reads_stride = stride;
 	CU(cudaStreamSynchronize(c->stream));
@@ -645,7 +665,7 @@ int ngm_b200_set_reads(ngm_b200_ctx *c, const char *reads, int n_reads, int stri
 int ngm_b200_dev_set_reads(ngm_b200_ctx *c, const void *d_ascii, int n_reads, int stride, void *stream) {
 	if (c == nullptr || d_ascii == nullptr || n_reads <= 0 || stride <= 0) return fail(NGM_B200_EINVAL, "bad read batch");
 	CU(cudaSetDevice(c->device));
-	return pack_reads_device(c, static_cast<const uint8_t *>(d_ascii), n_reads, stride, static_cast<cudaStream_t>(stream));
+	return pack_reads_device_impl(c, static_cast<const uint8_t *>(d_ascii), n_reads, stride, static_cast<cudaStream_t>(stream));
 }
 
 static int resolve_pairs(ngm_b200_ctx *c, const void *d_pairs_user, int n, cudaStream_t st) {
@@ -686,7 +706,7 @@ static int dev_align_pairs(ngm_b200_ctx *c, int mode, int n, const void *d_pairs
 	if (rc) return rc;
 	rc = run_align(c, m0, c->d_rpairs.as<PairDesc>(), n, c->d_rfwd.as<uint32_t>(), c->d_rrev.as<uint32_t>(), c->d_rrlen.as<uint16_t>(),
 			c->d_ref4.as<uint32_t>(), static_cast<ngm_b200_align_rec *>(d_recs), static_cast<char *>(d_strings), str_capacity,
-			static_cast<uint32_t *>(d_str_cursor), st, static_cast<const float *>(d_pair_scores));
+			static_cast<uint32_t *>(d_str_cursor), st, static_cast<const float *>(d_pair_scores), nullptr);
 	return rc ? rc : n;
 }
 
@@ -708,7 +728,7 @@ static int select_top1(ngm_b200_ctx *c, int n_reads, const void *d_cand_begin, c
 	if (n_reads <= 0) return 0;
 	CU(cudaSetDevice(c->device));
 	select_top1_kernel<<<(n_reads + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(n_reads, static_cast<const int *>(d_cand_begin),
-			static_cast<const float *>(d_scores), static_cast<int *>(d_best_pair), static_cast<int *>(d_mapq), static_cast<int *>(d_num_top));
+			static_cast<const float *>(d_scores), static_cast<int *>(d_best_pair), static_cast<int *>(d_mapq), static_cast<int *>(d_num_top), c->se_strata);
 	c->launches += 1;
 	CU(cudaGetLastError());
 	return n_reads;
@@ -766,3 +786,7 @@ int ngm_b200_align_pairs(ngm_b200_ctx *c, int mode, int n, const ngm_b200_pair *
 }
 
 }  // extern "C"
+
+namespace ngm {
+int pack_reads_device(ngm_b200_ctx *c, const uint8_t *d_ascii, int n_reads, int stride, cudaStream_t st) { return pack_reads_device_impl(c, d_ascii, n_reads, stride, st); }
+}  // namespace ngm

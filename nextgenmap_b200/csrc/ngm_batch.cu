@@ -1,0 +1,762 @@
+// ngm_batch.cu -- one scored + selected + aligned read batch per call, pipelined over several lanes inside the library.
+//
+// What the host side of NGM does between candidate search and the writer (src/ScoreBuffer.cpp:80-277,365-502: window fetch,
+// BatchScore, top1SE / top1PE, computeMQ; src/AlignmentBuffer.cpp:64-147: BatchAlign, computeCigarMD) for a whole batch, behind ONE
+// C-ABI call that takes host buffers: ngm_b200_run_batch.  This is the call a re-plumbed ScoreBuffer / AlignmentBuffer submits its
+// pinned staging buffers to (north_star), and the call bench.py's `e2e` times.
+//
+//   lanes       a lane is a child context: its own stream, read / pair / result staging and alignment scratch; the packed reference,
+//               the k-mer index and the paired-end running sums are borrowed from the root context.  Sub-batches rotate over the
+//               lanes, so the host->device copy of sub-batch i+1, the kernels of sub-batch i and the device->host copy of sub-batch
+//               i-1 overlap (the reference overlaps its host-side packing with the kernels the same way, SWOcl.cpp:435-444).
+//   fusion      a read with ONE candidate does not need BatchScore before its alignment: the forward pass of the alignment computes
+//               the same recurrence and its maximum IS the pair's score (oclSW vs oclSW_Score, oclSwScore.cl:4-154).  Such pairs skip
+//               the score kernel; their Score.f / MAPQ are filled in after the alignment.  Results are identical.
+//   formats     reads as NUL-padded ASCII rows or 2-bit packed + exception list (42 instead of 152 bytes per 150 bp read over PCIe);
+//               descriptors as ngm_b200_pair (16 bytes) or one 64-bit word (the read index is implicit in cand_begin).
+#include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "ngm_ctx.h"
+#include "ngm_launch.h"
+
+using namespace ngm;
+
+namespace ngm {
+
+// ---------------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t spread2to4(uint32_t x16) {      // 8 two-bit fields -> 8 nibbles (A0 C1 G2 T3 are the device codes already)
+	uint32_t y = (x16 | (x16 << 8)) & 0x00FF00FFu;
+	y = (y | (y << 4)) & 0x0F0F0F0Fu;
+	y = (y | (y << 2)) & 0x33333333u;
+	return y;
+}
+
+__device__ __forceinline__ uint32_t nib_keep(int valid) { return valid >= 8 ? 0xFFFFFFFFu : (valid <= 0 ? 0u : ((1u << (4 * valid)) - 1u)); }
+
+// forward code word w (bases 8w .. 8w+7) of a PACKED2 row; positions >= len read as NUL
+__device__ __forceinline__ uint32_t packed2_word(const uint32_t *__restrict__ in, int in_words, int len, int w) {
+	if (w < 0 || 8 * w >= len) return kNulWord;
+	const int iw = w >> 1;
+	const uint32_t x = iw < in_words ? ((__ldg(in + iw) >> (16 * (w & 1))) & 0xFFFFu) : 0u;
+	const uint32_t keep = nib_keep(len - 8 * w);
+	return (spread2to4(x) & keep) | (kNulWord & ~keep);
+}
+
+// PACKED2 rows -> forward words, reverse-complement words (MappedRead::computeReverseSeq, MappedRead.cpp:36-67) and lengths.
+// One thread per output word; the 40-byte input row stays in L1 for the 21 threads that share it.
+__global__ void __launch_bounds__(256) expand_packed2_kernel(const uint32_t *__restrict__ in, int rows, int in_words, const uint16_t *__restrict__ len_in,
+		int max_len, uint32_t *__restrict__ fwd, uint32_t *__restrict__ rev, uint16_t *__restrict__ rlen, int words) {
+	const long long gid = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (gid >= (long long) rows * words) return;
+	const int row = (int) (gid / words), w = (int) (gid - (long long) row * words);
+	const int len = min((int) len_in[row], max_len);
+	const uint32_t *r = in + (size_t) row * in_words;
+	fwd[gid] = packed2_word(r, in_words, len, w);
+	uint32_t out = kNulWord;
+	const int hi = len - 1 - 8 * w;                                // source index of output nibble 0; nibble k reads hi - k
+	if (hi >= 0) {
+		const int wi = hi >> 3;
+		const uint32_t a = packed2_word(r, in_words, len, wi), b = packed2_word(r, in_words, len, wi - 1);
+		const uint32_t x = __funnelshift_rc(b, a, 4 * ((hi & 7) + 1));
+		uint32_t y = __byte_perm(x, 0, 0x0123);
+		y = ((y >> 4) & 0x0F0F0F0Fu) | ((y & 0x0F0F0F0Fu) << 4);
+		const uint32_t m = (~y >> 2) & 0x11111111u;
+		out = y ^ (m * 3u);
+	}
+	rev[gid] = out;
+	if (w == 0) rlen[row] = (uint16_t) len;
+}
+
+// bases that are not A/C/G/T: oclDefines.cl:64-80 classes (N 5, everything else 4; a NUL inside the row ends nothing here: lengths are explicit)
+__global__ void patch_exceptions_kernel(const ngm_b200_read_exc *__restrict__ exc, uint32_t n_exc, uint32_t read_base, int rows, const uint16_t *__restrict__ rlen,
+		uint32_t *__restrict__ fwd, uint32_t *__restrict__ rev, int words) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_exc) return;
+	const ngm_b200_read_exc e = exc[i];
+	const long long row = (long long) e.read_index - (long long) read_base;
+	if (row < 0 || row >= rows) return;
+	const int len = rlen[row];
+	if ((int) e.pos >= len) return;
+	const uint32_t u = e.ch & 0xDFu;
+	const uint32_t code = u == 'A' ? 0u : u == 'C' ? 1u : u == 'G' ? 2u : u == 'T' ? 3u : u == 'N' ? 5u : (e.ch == 0 ? 6u : 4u);
+	uint32_t *f = fwd + (size_t) row * words + (e.pos >> 3);
+	const int sf = 4 * (e.pos & 7);
+	atomicAnd(f, ~(0xFu << sf));
+	atomicOr(f, code << sf);
+	const int rp = len - 1 - (int) e.pos;
+	uint32_t *rv = rev + (size_t) row * words + (rp >> 3);
+	const int sr = 4 * (rp & 7);
+	const uint32_t rcode = code < 4 ? 3u - code : code;
+	atomicAnd(rv, ~(0xFu << sr));
+	atomicOr(rv, rcode << sr);
+}
+
+// Per read: resolve its candidates' descriptors (window start -> nibble index of the resident reference; starts >= concat_len, incl. the
+// unsigned underflow of loc - corridor/2, select the all-'N' region, ScoreBuffer.cpp:113-118) and, when single-candidate reads skip the
+// score kernel, append the candidates of every other read to the score kernel's work list (one atomicAdd per warp).
+template <int FMT>
+__global__ void __launch_bounds__(256) batch_plan_kernel(int n_reads, const int *__restrict__ cb, int cb_base, const void *__restrict__ desc,
+		PairDesc *__restrict__ rp, ngm_b200_pair *__restrict__ pairs16, unsigned long long concat_len, unsigned long long n_region_nib,
+		const uint16_t *__restrict__ rlen, int fuse, int *__restrict__ sel, int *__restrict__ n_sel) {
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool valid = r < n_reads;
+	int b = 0, e = 0;
+	if (valid) {
+		b = cb[r] - cb_base;
+		e = cb[r + 1] - cb_base;
+	}
+	const int cnt = e - b;
+	const bool empty = valid && rlen[r] == 0;
+	for (int i = b; i < e; ++i) {
+		unsigned long long ws;
+		uint32_t fl;
+		if (FMT == NGM_B200_DESC_PAIR16) {
+			const ngm_b200_pair p = static_cast<const ngm_b200_pair *>(desc)[i];
+			ws = p.window_start;
+			fl = p.flags;
+		} else {
+			const unsigned long long d = static_cast<const unsigned long long *>(desc)[i];
+			ws = d & 0x00FFFFFFFFFFFFFFull;
+			fl = (uint32_t) (d >> 56);
+		}
+		PairDesc d;
+		d.win_nib = ws < concat_len ? ws : n_region_nib;
+		d.read_idx = (uint32_t) r;
+		d.flags = (fl & (PF_REVERSE | PF_DIR | PF_INACTIVE)) | (empty ? PF_INACTIVE : 0u);      // an empty read is its own quad leader
+		rp[i] = d;
+		if (pairs16 != nullptr) {
+			ngm_b200_pair p;
+			p.window_start = ws;
+			p.read_index = (uint32_t) r;
+			p.flags = fl;
+			pairs16[i] = p;
+		}
+	}
+	if (!fuse) return;
+	const int want = cnt > 1 ? cnt : 0;
+	const int lane = threadIdx.x & 31;
+	int incl = want;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const int v = __shfl_up_sync(0xffffffffu, incl, d);
+		if (lane >= d) incl += v;
+	}
+	int base = 0;
+	if (lane == 31 && incl) base = atomicAdd(n_sel, incl);
+	base = __shfl_sync(0xffffffffu, base, 31);
+	int at = base + incl - want;
+	for (int i = 0; i < want; ++i) sel[at + i] = b + i;
+}
+
+// ScoreBuffer::top1SE + computeMQ (ScoreBuffer.cpp:34-40,228-277) incl. `strata`; single-candidate reads of a fused batch only get their
+// winner here (score-dependent fields follow in batch_finalize_kernel)
+__global__ void __launch_bounds__(256) batch_select_top1_kernel(int n_reads, const int *__restrict__ cb, int cb_base, const float *__restrict__ scores,
+		int fuse, int strata, int *__restrict__ best_pair, int *__restrict__ mapq, int *__restrict__ num_top) {
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const int b = cb[r] - cb_base, e = cb[r + 1] - cb_base;
+	if (fuse && e - b == 1) {
+		best_pair[r] = b;
+		mapq[r] = 0;
+		if (num_top != nullptr) num_top[r] = 0;
+		return;
+	}
+	float best = 0.0f, second = 0.0f;
+	int besti = 0, nbest = 0;
+	for (int j = b; j < e; ++j) {
+		const float s = scores[j];
+		if (s > second) {
+			if (s > best) {
+				second = best;
+				best = s;
+				besti = j - b;
+				nbest = 1;
+			} else if (s == best) {
+				++nbest;
+				second = best;
+			} else {
+				second = s;
+			}
+		} else if (s == best) {
+			++nbest;
+		}
+	}
+	int mq = 0;
+	if (best > 0.0f && second >= 0.0f) mq = (int) ceilf(60.0f * (best - second) / best);
+	int bp = e > b ? b + besti : -1;
+	if (strata && nbest != 1 && e > b) {                           // too many equally scoring positions (ScoreBuffer.cpp:270-276)
+		bp = -1;
+		mq = 0;
+		nbest = 1;
+	}
+	best_pair[r] = bp;
+	mapq[r] = mq;
+	if (num_top != nullptr) num_top[r] = nbest;
+}
+
+__global__ void __launch_bounds__(256) batch_gather_kernel(int n_reads, const int *__restrict__ cb, int cb_base, const PairDesc *__restrict__ rp,
+		const int *__restrict__ best_pair, const float *__restrict__ scores, int fuse, PairDesc *__restrict__ wp, float *__restrict__ wscores) {
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const int bp = best_pair[r];
+	PairDesc d;
+	float s = 0.0f;
+	if (bp >= 0) {
+		d = rp[bp];
+		const bool single = fuse && (cb[r + 1] - cb[r] == 1);
+		if (!single) s = scores[bp];
+	} else {
+		d.win_nib = 0;
+		d.read_idx = (uint32_t) r;
+		d.flags = PF_INACTIVE;
+	}
+	wp[r] = d;
+	wscores[r] = s;
+}
+
+// fused batches: the score of a single-candidate read is the maximum its alignment's forward pass found; then top1SE over that one score
+__global__ void __launch_bounds__(256) batch_finalize_kernel(int n_reads, const int *__restrict__ cb, int cb_base, const float *__restrict__ out_best,
+		int strata, float *__restrict__ scores, int *__restrict__ best_pair, int *__restrict__ mapq, int *__restrict__ num_top) {
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const int b = cb[r] - cb_base, e = cb[r + 1] - cb_base;
+	if (e - b != 1) return;
+	const float s = out_best[r];
+	scores[b] = s;
+	int nbest = s >= 0.0f ? 1 : 0;                                   // s > 0: new best; s == 0: equals the initial best (ScoreBuffer.cpp:238-251)
+	int mq = s > 0.0f ? 60 : 0;                                      // computeMQ(best, 0)
+	if (strata && nbest != 1) {
+		best_pair[r] = -1;
+		mq = 0;
+		nbest = 1;
+	}
+	mapq[r] = mq;
+	if (num_top != nullptr) num_top[r] = nbest;
+}
+
+__global__ void batch_set_u32_kernel(uint32_t *p, uint32_t v, int *q) {
+	if (p != nullptr) *p = v;
+	if (q != nullptr) *q = 0;
+}
+
+__global__ void __launch_bounds__(256) batch_rebase_kernel(int n, int *__restrict__ cb, int base) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) cb[i] -= base;
+}
+
+__global__ void __launch_bounds__(256) batch_add_base_kernel(int n, int *__restrict__ best_pair, int base) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n && best_pair[i] >= 0) best_pair[i] += base;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// per-lane staging + the lanes of a root context
+// ---------------------------------------------------------------------------------------------------------
+struct LaneBuf {
+	DevBuf d_in_reads, d_in_len, d_in_exc, d_cb, d_desc, d_rp, d_pairs16, d_sel, d_nsel, d_scores, d_best, d_mapq, d_ntop, d_pfail, d_wp, d_wscores, d_obest,
+			d_recs, d_strings, d_cursor;
+	cudaEvent_t done = nullptr;
+	int pending = -1;                                              // sub-batch whose strings still have to be fetched
+	void release() {
+		DevBuf *all[] = { &d_in_reads, &d_in_len, &d_in_exc, &d_cb, &d_desc, &d_rp, &d_pairs16, &d_sel, &d_nsel, &d_scores, &d_best, &d_mapq, &d_ntop, &d_pfail,
+				&d_wp, &d_wscores, &d_obest, &d_recs, &d_strings, &d_cursor };
+		for (DevBuf *b : all) b->release();
+		if (done) cudaEventDestroy(done);
+		done = nullptr;
+	}
+};
+
+struct BatchState {
+	int n_lanes = 3;
+	int sub_batch = 1 << 20;
+	std::vector<ngm_b200_ctx *> lanes;
+	std::vector<LaneBuf> bufs;
+	LaneBuf own;                                                   // staging of ngm_b200_dev_run_batch on the root context itself
+	uint64_t synced_epoch = ~0ull;
+	HostBuf h_used;                                                // pinned: heap cursor of every sub-batch
+	cudaEvent_t pe_chain = nullptr;                                // orders the paired-end selections of consecutive sub-batches
+};
+
+void batch_release(BatchState *b) {
+	if (b == nullptr) return;
+	for (LaneBuf &l : b->bufs) l.release();
+	b->own.release();
+	for (ngm_b200_ctx *l : b->lanes) ngm_b200_destroy(l);
+	b->h_used.release();
+	if (b->pe_chain) cudaEventDestroy(b->pe_chain);
+	delete b;
+}
+
+}  // namespace ngm
+
+namespace {
+
+struct DevIn {                      // one sub-batch with every pointer on the device
+	int n_reads, mode, paired, desc_format;
+	const int *cb;                  // n_reads + 1 offsets, relative to cb_base
+	int cb_base;
+	const void *desc;               // descriptors of this sub-batch (index 0 = candidate cb_base)
+	int n_pairs;
+};
+
+struct DevOut {
+	float *scores;                  // n_pairs (always present on the device)
+	int *best_pair, *mapq, *num_top, *pair_fail;
+	ngm_b200_align_rec *recs;
+	char *strings;                  // heap pointer such that strings + offset is valid for offsets in [str_base, str_cap)
+	uint32_t str_cap;
+	uint32_t *cursor;               // already holds str_base
+};
+
+// enqueue score -> select -> align of one sub-batch whose reads are installed in `c` (d_rfwd / d_rrev / d_rrlen)
+int batch_enqueue(ngm_b200_ctx *c, LaneBuf &L, const DevIn &in, const DevOut &out, int strata, cudaStream_t st, cudaEvent_t pe_wait, cudaEvent_t pe_signal) {
+	const int n = in.n_reads, np = in.n_pairs;
+	const int m0 = mode_of(in.mode);
+	if (m0 < 0) return fail(NGM_B200_EINVAL, "unsupported alignment mode %d", in.mode & 0xFF);
+	if (!c->have_ref) return fail(NGM_B200_ESTATE, "set_reference must precede ngm_b200_run_batch");
+	// single-candidate reads skip BatchScore when the alignment kernel of this configuration reports its forward maximum and does not
+	// need the score beforehand (wide local bands locate their best cell by it)
+	const bool wide_local = m0 == 0 && c->align_s16[0] && c->capacity > kAlignS16MaxLocal;
+	static const bool no_fuse = [] { const char *e = getenv("NGM_B200_NO_FUSE"); return e != nullptr && atoi(e) == 1; }();
+	const int fuse = (!in.paired && !wide_local && !no_fuse) ? 1 : 0;
+	CU(L.d_rp.ensure(std::max<size_t>(np, 1) * sizeof(PairDesc)));
+	CU(L.d_wp.ensure((size_t) n * sizeof(PairDesc)));
+	CU(L.d_wscores.ensure((size_t) n * 4));
+	CU(L.d_obest.ensure((size_t) n * 4));
+	CU(L.d_nsel.ensure(4));
+	if (fuse) CU(L.d_sel.ensure(std::max<size_t>(np, 1) * 4));
+	if (in.paired) CU(L.d_pairs16.ensure(std::max<size_t>(np, 1) * sizeof(ngm_b200_pair)));
+	batch_set_u32_kernel<<<1, 1, 0, st>>>(nullptr, 0, L.d_nsel.as<int>());
+	const int blocks_r = (n + 255) / 256;
+	ngm_b200_pair *p16 = in.paired ? L.d_pairs16.as<ngm_b200_pair>() : nullptr;
+	if (in.desc_format == NGM_B200_DESC_PAIR16)
+		batch_plan_kernel<NGM_B200_DESC_PAIR16><<<blocks_r, 256, 0, st>>>(n, in.cb, in.cb_base, in.desc, L.d_rp.as<PairDesc>(), p16, (unsigned long long) c->concat_len,
+				(unsigned long long) c->n_region_nib, c->d_rrlen.as<uint16_t>(), fuse, L.d_sel.as<int>(), L.d_nsel.as<int>());
+	else
+		batch_plan_kernel<NGM_B200_DESC_U64><<<blocks_r, 256, 0, st>>>(n, in.cb, in.cb_base, in.desc, L.d_rp.as<PairDesc>(), p16, (unsigned long long) c->concat_len,
+				(unsigned long long) c->n_region_nib, c->d_rrlen.as<uint16_t>(), fuse, L.d_sel.as<int>(), L.d_nsel.as<int>());
+	c->launches += 2;
+	CU(cudaGetLastError());
+	const uint32_t *rf = c->d_rfwd.as<uint32_t>(), *rr = c->d_rrev.as<uint32_t>(), *ref4 = c->d_ref4.as<uint32_t>();
+	const uint16_t *rl = c->d_rrlen.as<uint16_t>();
+	if (np > 0) {
+		ScoreArgs a;
+		a.P = c->dp;
+		a.pairs = L.d_rp.as<PairDesc>();
+		a.n = np;
+		a.reads_fwd = rf;
+		a.reads_rev = rr;
+		a.rlen = rl;
+		a.ref4 = ref4;
+		a.out = out.scores;
+		if (fuse) {
+			a.sel = L.d_sel.as<int>();
+			a.n_dev = L.d_nsel.as<int>();
+		}
+		int rc = run_score(c, m0, a, st);
+		if (rc) return rc;
+	}
+	if (in.paired) {
+		if (pe_wait) CU(cudaStreamWaitEvent(st, pe_wait, 0));
+		int rc = ngm_b200_dev_select_pairs(c, n, in.cb, p16, out.scores, (uint32_t) np, out.best_pair, out.mapq, out.num_top != nullptr ? out.num_top : L.d_ntop.p,
+				out.pair_fail, st);
+		if (rc < 0) return rc;
+		if (pe_signal) CU(cudaEventRecord(pe_signal, st));
+	} else {
+		batch_select_top1_kernel<<<blocks_r, 256, 0, st>>>(n, in.cb, in.cb_base, out.scores, fuse, strata, out.best_pair, out.mapq, out.num_top);
+		c->launches += 1;
+	}
+	batch_gather_kernel<<<blocks_r, 256, 0, st>>>(n, in.cb, in.cb_base, L.d_rp.as<PairDesc>(), out.best_pair, out.scores, fuse, L.d_wp.as<PairDesc>(),
+			L.d_wscores.as<float>());
+	c->launches += 1;
+	CU(cudaGetLastError());
+	int rc = run_align(c, m0, L.d_wp.as<PairDesc>(), n, rf, rr, rl, ref4, out.recs, out.strings, out.str_cap, out.cursor, st,
+			fuse ? nullptr : L.d_wscores.as<float>(), fuse ? L.d_obest.as<float>() : nullptr);
+	if (rc) return rc;
+	if (fuse) {
+		batch_finalize_kernel<<<blocks_r, 256, 0, st>>>(n, in.cb, in.cb_base, L.d_obest.as<float>(), strata, out.scores, out.best_pair, out.mapq, out.num_top);
+		c->launches += 1;
+	}
+	CU(cudaGetLastError());
+	return NGM_B200_OK;
+}
+
+// install one sub-batch of reads (device pointers) in context c
+int install_reads(ngm_b200_ctx *c, int format, const void *d_reads, int n, int stride, const uint16_t *d_len, const ngm_b200_read_exc *d_exc, uint32_t n_exc,
+		uint32_t read_base, cudaStream_t st) {
+	if (format == NGM_B200_READS_ASCII) return pack_reads_device(c, static_cast<const uint8_t *>(d_reads), n, stride, st);
+	if (format != NGM_B200_READS_PACKED2) return fail(NGM_B200_EINVAL, "unknown read format %d", format);
+	if (stride <= 0 || (stride & 3)) return fail(NGM_B200_EINVAL, "PACKED2 rows must be a multiple of 4 bytes (got %d)", stride);
+	if (d_len == nullptr) return fail(NGM_B200_EINVAL, "PACKED2 reads need read_len");
+	const int RW = c->dp.read_words;
+	CU(c->d_rfwd.ensure((size_t) n * RW * 4));
+	CU(c->d_rrev.ensure((size_t) n * RW * 4));
+	CU(c->d_rrlen.ensure((size_t) n * 2));
+	const long long tot = (long long) n * RW;
+	expand_packed2_kernel<<<(unsigned) ((tot + 255) / 256), 256, 0, st>>>(static_cast<const uint32_t *>(d_reads), n, stride / 4, d_len, c->dp.qml,
+			c->d_rfwd.as<uint32_t>(), c->d_rrev.as<uint32_t>(), c->d_rrlen.as<uint16_t>(), RW);
+	c->launches += 1;
+	if (n_exc) {
+		patch_exceptions_kernel<<<(n_exc + 255) / 256, 256, 0, st>>>(d_exc, n_exc, read_base, n, c->d_rrlen.as<uint16_t>(), c->d_rfwd.as<uint32_t>(),
+				c->d_rrev.as<uint32_t>(), RW);
+		c->launches += 1;
+	}
+	CU(cudaGetLastError());
+	c->n_reads = n;
+	c->reads_stride = 0;
+	return NGM_B200_OK;
+}
+
+int sync_lanes(ngm_b200_ctx *c) {
+	if (c->batch == nullptr) c->batch = new BatchState();
+	BatchState *B = c->batch;
+	while ((int) B->lanes.size() < B->n_lanes) {
+		ngm_b200_params hp = c->hp;
+		ngm_b200_ctx *l = ngm_b200_create(&hp);
+		if (l == nullptr) return NGM_B200_ECUDA;
+		l->root = c;
+		B->lanes.push_back(l);
+		B->bufs.emplace_back();
+		CU(cudaEventCreateWithFlags(&B->bufs.back().done, cudaEventDisableTiming));
+		B->synced_epoch = ~0ull;
+	}
+	if (B->pe_chain == nullptr) CU(cudaEventCreateWithFlags(&B->pe_chain, cudaEventDisableTiming));
+	if (B->synced_epoch != c->epoch) {
+		for (ngm_b200_ctx *l : B->lanes) {
+			l->d_ref4.borrow(c->d_ref4);
+			l->concat_len = c->concat_len;
+			l->n_region_nib = c->n_region_nib;
+			l->have_ref = c->have_ref;
+			l->se_strata = c->se_strata;
+			int rc = cs_share_index(l, c);
+			if (rc) return rc;
+			rc = pe_share_state(l, c);
+			if (rc) return rc;
+		}
+		B->synced_epoch = c->epoch;
+	}
+	return NGM_B200_OK;
+}
+
+}  // namespace
+
+namespace ngm {
+// used by ngm_map.cu: the lanes of a root context, created / re-synchronised on demand
+int batch_lanes(ngm_b200_ctx *c, ngm_b200_ctx ***lanes, int *n_lanes, int *sub_batch) {
+	int rc = sync_lanes(c);
+	if (rc) return rc;
+	*lanes = c->batch->lanes.data();
+	*n_lanes = (int) c->batch->lanes.size();
+	*sub_batch = c->batch->sub_batch;
+	return NGM_B200_OK;
+}
+uint64_t batch_lane_launches(const ngm_b200_ctx *c) {
+	uint64_t n = 0;
+	if (c->batch)
+		for (const ngm_b200_ctx *l : c->batch->lanes) n += l->launches;
+	return n;
+}
+}  // namespace ngm
+
+extern "C" {
+
+int ngm_b200_set_pipeline(ngm_b200_ctx *c, int lanes, int sub_batch_reads) {
+	if (c == nullptr) return fail(NGM_B200_EINVAL, "ctx == NULL");
+	if (lanes < 1 || lanes > 8) return fail(NGM_B200_EINVAL, "lanes %d not in [1, 8]", lanes);
+	if (sub_batch_reads < 2 || (sub_batch_reads & 1)) return fail(NGM_B200_EINVAL, "sub-batches hold an even number of reads (mates stay together), got %d", sub_batch_reads);
+	if (c->batch == nullptr) c->batch = new BatchState();
+	if ((int) c->batch->lanes.size() > lanes) return fail(NGM_B200_ESTATE, "the pipeline already runs %zu lanes", c->batch->lanes.size());
+	c->batch->n_lanes = lanes;
+	c->batch->sub_batch = sub_batch_reads;
+	return NGM_B200_OK;
+}
+
+int ngm_b200_se_configure(ngm_b200_ctx *c, int strata) {
+	if (c == nullptr) return fail(NGM_B200_EINVAL, "ctx == NULL");
+	c->se_strata = strata ? 1 : 0;
+	c->epoch += 1;
+	return NGM_B200_OK;
+}
+
+void *ngm_b200_host_alloc(size_t bytes) {
+	void *p = nullptr;
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+		fail(NGM_B200_ECUDA, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(cudaGetLastError()));
+		return nullptr;
+	}
+	return p;
+}
+
+void ngm_b200_host_free(void *p) {
+	if (p) cudaFreeHost(p);
+}
+
+int ngm_b200_host_register(void *p, size_t bytes) {
+	if (p == nullptr || bytes == 0) return fail(NGM_B200_EINVAL, "NULL / empty range");
+	CU(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+	return NGM_B200_OK;
+}
+
+int ngm_b200_host_unregister(void *p) {
+	if (p == nullptr) return fail(NGM_B200_EINVAL, "NULL");
+	CU(cudaHostUnregister(p));
+	return NGM_B200_OK;
+}
+
+int ngm_b200_pack_reads(const char *ascii, int n_reads, int stride, void *packed, int row_bytes, uint16_t *read_len, ngm_b200_read_exc *exceptions,
+		size_t exc_cap, size_t *n_exc, int threads) {
+	if (ascii == nullptr || packed == nullptr || read_len == nullptr || n_reads < 0 || stride <= 0) return fail(NGM_B200_EINVAL, "bad argument");
+	if ((row_bytes & 3) || row_bytes < 4 * ((stride + 15) / 16)) return fail(NGM_B200_EINVAL, "row_bytes %d too small for %d bases", row_bytes, stride);
+	if (stride > 65535) return fail(NGM_B200_EINVAL, "rows longer than 65535 bases");
+	int nt = threads > 0 ? threads : (int) std::thread::hardware_concurrency();
+	nt = std::max(1, std::min(nt, std::max(1, n_reads / 4096)));
+	// pass 1: pack + count the exceptions of every slice; pass 2 (only when there are any): write them in order
+	std::vector<size_t> cnt((size_t) nt + 1, 0);
+	auto pack_slice = [&](int t, bool emit, size_t off) {
+		const int lo = (int) ((long long) n_reads * t / nt), hi = (int) ((long long) n_reads * (t + 1) / nt);
+		size_t k = 0;
+		for (int r = lo; r < hi; ++r) {
+			const unsigned char *s = reinterpret_cast<const unsigned char *>(ascii) + (size_t) r * stride;
+			uint32_t *o = reinterpret_cast<uint32_t *>(static_cast<char *>(packed) + (size_t) r * row_bytes);
+			int len = stride;
+			while (len > 0 && s[len - 1] == 0) --len;              // MappedRead::length: index of the last non-NUL byte + 1
+			if (!emit) {
+				for (int w = 0; w < row_bytes / 4; ++w) {
+					uint32_t v = 0;
+					const int i0 = 16 * w;
+					for (int i = 0; i < 16 && i0 + i < len; ++i) {
+						const unsigned char ch = s[i0 + i];
+						uint32_t code;
+						switch (ch) {
+							case 'A': case 'a': code = 0; break;
+							case 'C': case 'c': code = 1; break;
+							case 'G': case 'g': code = 2; break;
+							case 'T': case 't': code = 3; break;
+							default: code = 0; ++k; break;
+						}
+						v |= code << (2 * i);
+					}
+					o[w] = v;
+				}
+				read_len[r] = (uint16_t) len;
+			} else {
+				for (int i = 0; i < len; ++i) {
+					const unsigned char u = s[i] & 0xDF;
+					if (!(u == 'A' || u == 'C' || u == 'G' || u == 'T')) {
+						if (off + k < exc_cap) {
+							ngm_b200_read_exc x;
+							x.read_index = (uint32_t) r;
+							x.pos = (uint16_t) i;
+							x.ch = s[i];
+							x.pad = 0;
+							exceptions[off + k] = x;
+						}
+						++k;
+					}
+				}
+			}
+		}
+		if (!emit) cnt[(size_t) t + 1] = k;
+	};
+	{
+		std::vector<std::thread> th;
+		for (int t = 1; t < nt; ++t) th.emplace_back(pack_slice, t, false, (size_t) 0);
+		pack_slice(0, false, 0);
+		for (auto &x : th) x.join();
+	}
+	for (int t = 0; t < nt; ++t) cnt[(size_t) t + 1] += cnt[t];
+	const size_t total = cnt[nt];
+	if (n_exc) *n_exc = total;
+	if (total == 0) return n_reads;
+	if (exceptions == nullptr || total > exc_cap) return fail(NGM_B200_ERANGE, "exception list too small: %zu entries needed", total);
+	{
+		std::vector<std::thread> th;
+		for (int t = 1; t < nt; ++t)
+			if (cnt[(size_t) t + 1] != cnt[t]) th.emplace_back(pack_slice, t, true, cnt[t]);
+		if (cnt[1] != cnt[0]) pack_slice(0, true, 0);
+		for (auto &x : th) x.join();
+	}
+	return n_reads;
+}
+
+int ngm_b200_dev_run_batch(ngm_b200_ctx *c, const ngm_b200_batch_in *in, ngm_b200_batch_out *out, void *stream) {
+	if (c == nullptr || in == nullptr || out == nullptr) return fail(NGM_B200_EINVAL, "NULL argument");
+	if (in->n_reads <= 0) return 0;
+	if (in->reads == nullptr || in->cand_begin == nullptr || out->best_pair == nullptr || out->mapq == nullptr || out->recs == nullptr ||
+			out->strings == nullptr || out->d_str_cursor == nullptr || (in->paired && out->pair_fail == nullptr))
+		return fail(NGM_B200_EINVAL, "NULL array");
+	if (in->paired && (in->n_reads & 1)) return fail(NGM_B200_EINVAL, "paired batches hold the mates in rows 2f and 2f + 1: %d rows", in->n_reads);
+	if (out->str_capacity > 0xFFFFFFFFull) return fail(NGM_B200_EINVAL, "string heap beyond 32 bits");
+	CU(cudaSetDevice(c->device));
+	if (c->batch == nullptr) c->batch = new BatchState();
+	LaneBuf &L = c->batch->own;
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	// the number of candidates sizes the staging: it is the caller's (reserved > 0) or read back once
+	int np = (int) in->n_desc;
+	if (np <= 0) {
+		CU(cudaMemcpyAsync(&np, in->cand_begin + in->n_reads, 4, cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+	}
+	if (np > 0 && in->desc == nullptr) return fail(NGM_B200_EINVAL, "NULL descriptor array");
+	int rc = install_reads(c, in->read_format, in->reads, in->n_reads, in->read_stride, in->read_len, in->exceptions, in->n_exceptions, 0, st);
+	if (rc) return rc;
+	float *scores = out->scores;
+	if (scores == nullptr) {
+		CU(L.d_scores.ensure(std::max<size_t>(np, 1) * 4));
+		scores = L.d_scores.as<float>();
+	}
+	if (out->num_top == nullptr) CU(L.d_ntop.ensure((size_t) in->n_reads * 4));
+	batch_set_u32_kernel<<<1, 1, 0, st>>>(out->d_str_cursor, 0u, nullptr);
+	DevIn di = { in->n_reads, in->mode, in->paired, in->desc_format, in->cand_begin, 0, in->desc, np };
+	DevOut dn = { scores, out->best_pair, out->mapq, out->num_top, out->pair_fail, out->recs, out->strings, (uint32_t) out->str_capacity, out->d_str_cursor };
+	rc = batch_enqueue(c, L, di, dn, c->se_strata, st, nullptr, nullptr);
+	return rc ? rc : in->n_reads;
+}
+
+int ngm_b200_run_batch(ngm_b200_ctx *c, const ngm_b200_batch_in *in, ngm_b200_batch_out *out) {
+	if (c == nullptr || in == nullptr || out == nullptr) return fail(NGM_B200_EINVAL, "NULL argument");
+	const int n = in->n_reads;
+	if (n <= 0) return 0;
+	if (in->reads == nullptr || in->cand_begin == nullptr || out->best_pair == nullptr || out->mapq == nullptr || out->recs == nullptr ||
+			(out->str_capacity && out->strings == nullptr) || (in->paired && out->pair_fail == nullptr))
+		return fail(NGM_B200_EINVAL, "NULL array");
+	if (in->paired && (n & 1)) return fail(NGM_B200_EINVAL, "paired batches hold the mates in rows 2f and 2f + 1: %d rows", n);
+	if (in->read_format == NGM_B200_READS_PACKED2 && in->read_len == nullptr) return fail(NGM_B200_EINVAL, "PACKED2 reads need read_len");
+	if (in->read_stride <= 0) return fail(NGM_B200_EINVAL, "read_stride %d", in->read_stride);
+	const int32_t *cb = in->cand_begin;
+	const long long total_pairs = (long long) cb[n] - cb[0];
+	if (total_pairs < 0 || (total_pairs > 0 && in->desc == nullptr)) return fail(NGM_B200_EINVAL, "bad candidate lists");
+	CU(cudaSetDevice(c->device));
+	int rc = sync_lanes(c);
+	if (rc) return rc;
+	BatchState *B = c->batch;
+	const int SB = B->sub_batch;
+	const int n_sub = (n + SB - 1) / SB;
+	const size_t slot = (out->str_capacity / (size_t) n_sub) & ~(size_t) 15;
+	if ((slot + 16) * (size_t) n_sub > 0xFFFFFFF0ull) return fail(NGM_B200_EINVAL, "string heap beyond 32 bits");
+	CU(B->h_used.ensure((size_t) n_sub * 4));
+	uint32_t *h_used = B->h_used.as<uint32_t>();
+	const size_t desc_bytes = in->desc_format == NGM_B200_DESC_U64 ? 8 : sizeof(ngm_b200_pair);
+	const int n_lanes = std::min((int) B->lanes.size(), std::max(1, n_sub));
+	int64_t pe_sum = 0, pe_count = 0;
+	if (in->paired && (rc = ngm_b200_pe_insert_stats(c, &pe_sum, &pe_count)) < 0) return rc;
+	size_t worst_used = 0, total_used = 0;
+	bool overflow = false;
+	int err = NGM_B200_OK;
+	auto finish = [&](int li) -> int {                              // fetch the strings of the lane's previous sub-batch
+		LaneBuf &L = B->bufs[li];
+		if (L.pending < 0) return NGM_B200_OK;
+		const int k = L.pending;
+		L.pending = -1;
+		CU(cudaEventSynchronize(L.done));
+		const size_t base = slot * (size_t) k;
+		const size_t used = (size_t) h_used[k] - base;
+		worst_used = std::max(worst_used, used);
+		total_used += used;
+		if (used > slot) {
+			overflow = true;
+			return NGM_B200_OK;
+		}
+		if (used) CU(cudaMemcpyAsync(out->strings + base, L.d_strings.p, used, cudaMemcpyDeviceToHost, B->lanes[li]->stream));
+		return NGM_B200_OK;
+	};
+	const ngm_b200_read_exc *exc = in->exceptions;
+	size_t exc_at = 0;
+	for (int k = 0; k < n_sub && err == NGM_B200_OK; ++k) {
+		const int li = k % n_lanes;
+		ngm_b200_ctx *l = B->lanes[li];
+		LaneBuf &L = B->bufs[li];
+		cudaStream_t st = l->stream;
+		if ((err = finish(li)) != NGM_B200_OK) break;
+		const int r0 = k * SB, m = std::min(SB, n - r0);
+		const int p0 = cb[r0], mp = cb[r0 + m] - p0;
+		// ---- host -> device
+		const size_t rbytes = (size_t) m * in->read_stride;
+		if (cudaSuccess != L.d_in_reads.ensure(rbytes) || cudaSuccess != L.d_cb.ensure(((size_t) m + 1) * 4) ||
+				cudaSuccess != L.d_desc.ensure(std::max<size_t>(mp, 1) * desc_bytes) || cudaSuccess != L.d_scores.ensure(std::max<size_t>(mp, 1) * 4) ||
+				cudaSuccess != L.d_best.ensure((size_t) m * 4) || cudaSuccess != L.d_mapq.ensure((size_t) m * 4) || cudaSuccess != L.d_ntop.ensure((size_t) m * 4) ||
+				cudaSuccess != L.d_pfail.ensure((size_t) m * 4) || cudaSuccess != L.d_recs.ensure((size_t) m * sizeof(ngm_b200_align_rec)) ||
+				cudaSuccess != L.d_strings.ensure(std::max<size_t>(slot, 16)) || cudaSuccess != L.d_cursor.ensure(4)) {
+			err = fail(NGM_B200_ECUDA, "lane staging: %s", cudaGetErrorString(cudaGetLastError()));
+			break;
+		}
+		cudaError_t e = cudaMemcpyAsync(L.d_in_reads.p, static_cast<const char *>(in->reads) + (size_t) r0 * in->read_stride, rbytes, cudaMemcpyHostToDevice, st);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(L.d_cb.p, cb + r0, ((size_t) m + 1) * 4, cudaMemcpyHostToDevice, st);
+		if (e == cudaSuccess && mp) e = cudaMemcpyAsync(L.d_desc.p, static_cast<const char *>(in->desc) + (size_t) (p0 - cb[0]) * desc_bytes, (size_t) mp * desc_bytes, cudaMemcpyHostToDevice, st);
+		uint32_t n_exc = 0;
+		if (e == cudaSuccess && in->read_format == NGM_B200_READS_PACKED2) {
+			if (cudaSuccess != L.d_in_len.ensure((size_t) m * 2)) e = cudaErrorMemoryAllocation;
+			if (e == cudaSuccess) e = cudaMemcpyAsync(L.d_in_len.p, in->read_len + r0, (size_t) m * 2, cudaMemcpyHostToDevice, st);
+			if (exc != nullptr) {
+				while (exc_at < in->n_exceptions && exc[exc_at].read_index < (uint32_t) r0) ++exc_at;
+				size_t hi = exc_at;
+				while (hi < in->n_exceptions && exc[hi].read_index < (uint32_t) (r0 + m)) ++hi;
+				n_exc = (uint32_t) (hi - exc_at);
+				if (n_exc) {
+					if (cudaSuccess != L.d_in_exc.ensure((size_t) n_exc * sizeof(ngm_b200_read_exc))) e = cudaErrorMemoryAllocation;
+					if (e == cudaSuccess) e = cudaMemcpyAsync(L.d_in_exc.p, exc + exc_at, (size_t) n_exc * sizeof(ngm_b200_read_exc), cudaMemcpyHostToDevice, st);
+				}
+			}
+		}
+		if (e != cudaSuccess) {
+			err = fail(NGM_B200_ECUDA, "host -> device copy: %s", cudaGetErrorString(e));
+			break;
+		}
+		// ---- kernels
+		if ((err = install_reads(l, in->read_format, L.d_in_reads.p, m, in->read_stride, L.d_in_len.as<uint16_t>(), L.d_in_exc.as<ngm_b200_read_exc>(), n_exc,
+				(uint32_t) r0, st)) != NGM_B200_OK)
+			break;
+		const uint32_t base = (uint32_t) (slot * (size_t) k);
+		batch_set_u32_kernel<<<1, 1, 0, st>>>(L.d_cursor.as<uint32_t>(), base, nullptr);
+		if (p0) batch_rebase_kernel<<<(m + 1 + 255) / 256, 256, 0, st>>>(m + 1, L.d_cb.as<int>(), p0);      // offsets into the sub-batch's own arrays
+		DevIn di = { m, in->mode, in->paired, in->desc_format, L.d_cb.as<int>(), 0, L.d_desc.p, mp };
+		DevOut dn = { L.d_scores.as<float>(), L.d_best.as<int>(), L.d_mapq.as<int>(), L.d_ntop.as<int>(), L.d_pfail.as<int>(), L.d_recs.as<ngm_b200_align_rec>(),
+				L.d_strings.as<char>() - base, (uint32_t) (base + slot), L.d_cursor.as<uint32_t>() };
+		if ((err = batch_enqueue(l, L, di, dn, c->se_strata, st, (in->paired && k > 0) ? B->pe_chain : nullptr, in->paired ? B->pe_chain : nullptr)) != NGM_B200_OK) break;
+		// candidate indices of the caller's arrays, not of the sub-batch
+		if (p0 - cb[0] != 0) batch_add_base_kernel<<<(m + 255) / 256, 256, 0, st>>>(m, L.d_best.as<int>(), p0 - cb[0]);
+		l->launches += 2;
+		// ---- device -> host
+		e = cudaMemcpyAsync(out->best_pair + r0, L.d_best.p, (size_t) m * 4, cudaMemcpyDeviceToHost, st);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(out->mapq + r0, L.d_mapq.p, (size_t) m * 4, cudaMemcpyDeviceToHost, st);
+		if (e == cudaSuccess && out->num_top) e = cudaMemcpyAsync(out->num_top + r0, L.d_ntop.p, (size_t) m * 4, cudaMemcpyDeviceToHost, st);
+		if (e == cudaSuccess && in->paired) e = cudaMemcpyAsync(out->pair_fail + r0, L.d_pfail.p, (size_t) m * 4, cudaMemcpyDeviceToHost, st);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(out->recs + r0, L.d_recs.p, (size_t) m * sizeof(ngm_b200_align_rec), cudaMemcpyDeviceToHost, st);
+		if (e == cudaSuccess && out->scores && mp) e = cudaMemcpyAsync(out->scores + (p0 - cb[0]), L.d_scores.p, (size_t) mp * 4, cudaMemcpyDeviceToHost, st);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(h_used + k, L.d_cursor.p, 4, cudaMemcpyDeviceToHost, st);
+		if (e == cudaSuccess) e = cudaEventRecord(L.done, st);
+		if (e != cudaSuccess) {
+			err = fail(NGM_B200_ECUDA, "device -> host copy: %s", cudaGetErrorString(e));
+			break;
+		}
+		L.pending = k;
+	}
+	for (int li = 0; li < n_lanes; ++li) {
+		const int rc2 = finish(li);
+		if (err == NGM_B200_OK) err = rc2;
+	}
+	for (int li = 0; li < n_lanes; ++li) {
+		const cudaError_t e = cudaStreamSynchronize(B->lanes[li]->stream);
+		if (e != cudaSuccess && err == NGM_B200_OK) err = fail(NGM_B200_ECUDA, "lane %d: %s", li, cudaGetErrorString(e));
+	}
+	if (err != NGM_B200_OK) {
+		if (in->paired) ngm_b200_pe_set_insert_stats(c, pe_sum, pe_count);
+		return err;
+	}
+	out->str_used = total_used;
+	if (overflow) {
+		if (in->paired) ngm_b200_pe_set_insert_stats(c, pe_sum, pe_count);
+		out->str_used = (worst_used + 64) * (size_t) n_sub;
+		return fail(NGM_B200_ERANGE, "string heap too small: a sub-batch needed %zu bytes, its slot holds %zu", worst_used, slot);
+	}
+	return n;
+}
+
+}  // extern "C"

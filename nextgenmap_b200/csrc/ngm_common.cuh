@@ -50,6 +50,8 @@ struct DevParams {
 	int silent_clip;
 	int read_words;        // words per packed read row
 	int rows_cap;          // pointer rows per alignment in the scratch matrix
+	uint32_t c_four;       // 4 and -1 as run-time values: multipliers of the tag IMADs, which ptxas must not fold back onto the ALU pipe
+	uint32_t c_neg1;
 	uint2 lut[16];         // [dir * 8 + rc] -> signed score bytes for fc = 0..7
 	uint2 lut4[16];        // same rows holding 4*S + 2 (diag candidate of the tagged s16x2 align kernel)
 };
@@ -57,6 +59,13 @@ struct DevParams {
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 	uint32_t d;
 	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+	return d;
+}
+
+// a * b + c on the FMA pipe (IMAD); with b taken from the kernel parameters ptxas cannot turn it into LEA / LOP3 / IADD3 (ALU pipe)
+__device__ __forceinline__ uint32_t imad_u32(uint32_t a, uint32_t b, uint32_t c) {
+	uint32_t d;
+	asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
 	return d;
 }
 

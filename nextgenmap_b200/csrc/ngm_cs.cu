@@ -46,6 +46,30 @@ void cs_release(CsState *cs) {
 	delete cs;
 }
 
+int cs_share_index(ngm_b200_ctx *lane, const ngm_b200_ctx *root) {
+	const CsState *r = root->cs;
+	if (r == nullptr || !r->ready) {
+		if (lane->cs) lane->cs->ready = false;
+		return NGM_B200_OK;
+	}
+	if (lane->cs == nullptr) lane->cs = new CsState();
+	CsState *s = lane->cs;
+	s->hp = r->hp;
+	s->k = r->k;
+	s->step = r->step;
+	s->bin_shift = r->bin_shift;
+	s->n_prefix = r->n_prefix;
+	s->table_len = r->table_len;
+	s->max_kfreq = r->max_kfreq;
+	s->d_tabu.borrow(r->d_tabu);
+	s->d_table.borrow(r->d_table);
+	s->d_weight.borrow(r->d_weight);
+	s->d_both.borrow(r->d_both);
+	s->d_table2.borrow(r->d_table2);
+	s->ready = true;
+	return NGM_B200_OK;
+}
+
 }  // namespace ngm
 
 namespace {
@@ -67,6 +91,7 @@ CsState *fresh_state(ngm_b200_ctx *c, const ngm_b200_cs_params *p) {
 	c->cs->step = p->kmer_skip + 1;
 	c->cs->bin_shift = p->bin_size;
 	c->cs->n_prefix = 1u << (2 * p->kmer);
+	c->epoch += 1;
 	return c->cs;
 }
 
@@ -153,6 +178,7 @@ int finish_index(ngm_b200_ctx *c, CsState *cs, unsigned long long s1, unsigned l
 	d_off2.release();
 	d_tmp.release();
 	cs->ready = true;
+	c->epoch += 1;
 	return NGM_B200_OK;
 }
 
@@ -491,6 +517,7 @@ int ngm_b200_cs_set_sensitivity(ngm_b200_ctx *c, float sensitivity) {
 	if (c == nullptr || c->cs == nullptr || !c->cs->ready) return fail(NGM_B200_ESTATE, "no candidate-search index");
 	if (!(sensitivity >= 0.0f && sensitivity <= 1.0f)) return fail(NGM_B200_EINVAL, "sensitivity %g not in [0, 1]", sensitivity);
 	c->cs->hp.sensitivity = sensitivity;
+	c->epoch += 1;
 	return NGM_B200_OK;
 }
 

@@ -22,8 +22,16 @@ int fail(int code, const char *fmt, ...);      // records the message for ngm_b2
 struct DevBuf {
 	void *p = nullptr;
 	size_t cap = 0;
+	bool borrowed = false;     // alias of another context's buffer (lanes share the reference and the index): never freed or resized here
+	void borrow(const DevBuf &o) {
+		release();
+		p = o.p;
+		cap = o.cap;
+		borrowed = true;
+	}
 	cudaError_t ensure(size_t bytes) {
 		if (bytes <= cap) return cudaSuccess;
+		if (borrowed) return cudaErrorInvalidValue;
 		if (p) cudaFree(p);
 		p = nullptr;
 		cap = 0;
@@ -33,9 +41,10 @@ struct DevBuf {
 		return e;
 	}
 	void release() {
-		if (p) cudaFree(p);
+		if (p && !borrowed) cudaFree(p);
 		p = nullptr;
 		cap = 0;
+		borrowed = false;
 	}
 	template <typename T> T *as() const { return static_cast<T *>(p); }
 };
@@ -61,12 +70,26 @@ struct HostBuf {   // pinned
 	template <typename T> T *as() const { return static_cast<T *>(p); }
 };
 
+struct ScoreArgs;
+int mode_of(int mode);                          // mode & 0xFF -> 0 / 1, or -1
+// (implemented in ngm_b200.cu; used by the batch engine in ngm_batch.cu)
+int pack_reads_device(ngm_b200_ctx *c, const uint8_t *d_ascii, int n_reads, int stride, cudaStream_t st);
+int run_score(ngm_b200_ctx *c, int mode, const ScoreArgs &a, cudaStream_t st);
+int run_align(ngm_b200_ctx *c, int mode, const PairDesc *pairs, int n, const uint32_t *rf, const uint32_t *rr, const uint16_t *rl, const uint32_t *ref4,
+		ngm_b200_align_rec *recs, char *strings, uint32_t str_cap, uint32_t *cursor, cudaStream_t st, const float *known_user, float *out_best);
+
 struct CsState;                                 // candidate search: index + scratch (ngm_cs.cu)
 void cs_release(CsState *cs);
 struct PeState;                                 // paired-end selection: parameters, running insert-size sums, scratch (ngm_select.cu)
 void pe_release(PeState *pe);
 struct MapState;                                // scratch of ngm_b200_map_batch (ngm_map.cu)
 void map_release(MapState *m);
+struct BatchState;                              // lanes + staging of ngm_b200_run_batch (ngm_batch.cu)
+void batch_release(BatchState *b);
+uint64_t batch_lane_launches(const ngm_b200_ctx *c);
+int batch_lanes(ngm_b200_ctx *c, ngm_b200_ctx ***lanes, int *n_lanes, int *sub_batch);      // created / re-synchronised on demand
+int cs_share_index(ngm_b200_ctx *lane, const ngm_b200_ctx *root);      // lane->cs aliases root's index (own search scratch)
+int pe_share_state(ngm_b200_ctx *lane, const ngm_b200_ctx *root);      // lane->pe: root's parameters + an alias of its running insert-size sums
 
 }  // namespace ngm
 
@@ -98,4 +121,8 @@ struct ngm_b200_ctx {
 	ngm::CsState *cs = nullptr;
 	ngm::PeState *pe = nullptr;
 	ngm::MapState *map = nullptr;
+	ngm::BatchState *batch = nullptr;
+	int se_strata = 0;         // "strata" for single-end top-1 selection (ScoreBuffer.cpp:259)
+	uint64_t epoch = 0;        // bumped whenever the reference / index / selection parameters change: lanes re-sync their aliases
+	ngm_b200_ctx *root = nullptr;      // set in a lane: the context whose resident data it borrows
 };

@@ -62,13 +62,15 @@ __device__ __forceinline__ bool load_pair(const DevParams &P, const PairDesc *__
 template <int W, int LO, int MODE>
 __global__ void __launch_bounds__(128) score_i32_kernel(const __grid_constant__ DevParams P, const PairDesc *__restrict__ pairs, int n,
 		const uint32_t *__restrict__ reads_fwd, const uint32_t *__restrict__ reads_rev, const uint16_t *__restrict__ rlen,
-		const uint32_t *__restrict__ ref4, float *__restrict__ out) {
+		const uint32_t *__restrict__ ref4, float *__restrict__ out, const int *__restrict__ sel, const int *__restrict__ n_dev) {
 	using G = BandGeom<W>;
 	__shared__ uint2 s_lut[16];
 	if (threadIdx.x < 16) s_lut[threadIdx.x] = P.lut[threadIdx.x];
 	__syncthreads();
-	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= n) return;
+	if (n_dev != nullptr) n = min(n, *n_dev);
+	const int slot_i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (slot_i >= n) return;
+	const int idx = sel != nullptr ? sel[slot_i] : slot_i;
 	constexpr int SENT = MODE == 0 ? 0 : kEndFreeMin;
 	PairCtx c;
 	uint32_t flags;

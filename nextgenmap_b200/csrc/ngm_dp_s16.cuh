@@ -33,16 +33,17 @@ __device__ __forceinline__ uint32_t pack2(int lo, int hi) { return ((uint32_t) h
 template <int W, int LO, int MODE>
 __global__ void __launch_bounds__(128) score_s16_kernel(const __grid_constant__ DevParams P, const PairDesc *__restrict__ pairs, int n,
 		const uint32_t *__restrict__ reads_fwd, const uint32_t *__restrict__ reads_rev, const uint16_t *__restrict__ rlen,
-		const uint32_t *__restrict__ ref4, float *__restrict__ out) {
+		const uint32_t *__restrict__ ref4, float *__restrict__ out, const int *__restrict__ sel, const int *__restrict__ n_dev) {
 	using G = BandGeom<W>;
 	__shared__ uint2 s_lut[16];
 	if (threadIdx.x < 16) s_lut[threadIdx.x] = P.lut[threadIdx.x];
 	__syncthreads();
+	if (n_dev != nullptr) n = min(n, *n_dev);
 	const int t2 = blockIdx.x * blockDim.x + threadIdx.x;
-	const int ia = 2 * t2;
-	if (ia >= n) return;
-	const bool has_b = ia + 1 < n;
-	const int ib = has_b ? ia + 1 : ia;
+	if (2 * t2 >= n) return;
+	const bool has_b = 2 * t2 + 1 < n;
+	const int ia = sel != nullptr ? sel[2 * t2] : 2 * t2;
+	const int ib = has_b ? (sel != nullptr ? sel[2 * t2 + 1] : ia + 1) : ia;
 	constexpr int SENT = MODE == 0 ? 0 : kEndFreeMin;
 	const uint32_t SENT2 = pack2(SENT, SENT);
 	PairCtx ca, cb;
@@ -120,10 +121,11 @@ __global__ void __launch_bounds__(128) score_s16_kernel(const __grid_constant__ 
 	const float inactive = MODE == 0 ? -1.0f : (float) kEndFreeMin;
 	const float ra = act_a ? (float) (int) (short) (best & 0xFFFFu) : inactive;
 	const float rb = act_b ? (float) (int) (short) (best >> 16) : inactive;
-	if (has_b) {
+	if (has_b && sel == nullptr) {
 		*reinterpret_cast<float2 *>(out + ia) = make_float2(ra, rb);
 	} else {
 		out[ia] = ra;
+		if (has_b) out[ib] = rb;
 	}
 }
 

@@ -15,7 +15,7 @@ template <int W, int LO, int MODE>
 __global__ void __launch_bounds__(128) align_i32_kernel(const __grid_constant__ DevParams P, const PairDesc *__restrict__ pairs, int n,
 		const uint32_t *__restrict__ reads_fwd, const uint32_t *__restrict__ reads_rev, const uint16_t *__restrict__ rlen,
 		const uint32_t *__restrict__ ref4, uint32_t *__restrict__ ptr_scratch, uint16_t *__restrict__ ops_scratch, int stride, int ops_cap,
-		ngm_b200_align_rec *__restrict__ recs, char *__restrict__ strings, uint32_t str_cap, uint32_t *__restrict__ cursor) {
+		ngm_b200_align_rec *__restrict__ recs, char *__restrict__ strings, uint32_t str_cap, uint32_t *__restrict__ cursor, float *__restrict__ out_best) {
 	__shared__ uint2 s_lut[16];
 	if (threadIdx.x < 16) s_lut[threadIdx.x] = P.lut[threadIdx.x];
 	__syncthreads();
@@ -40,11 +40,14 @@ __global__ void __launch_bounds__(128) align_i32_kernel(const __grid_constant__ 
 	uint16_t *ops = ops_scratch + slot;
 	if (valid) {
 		uint32_t flags;
+		float bs = MODE == 0 ? -1.0f : (float) kEndFreeMin;
 		if (load_pair(P, pairs, idx, reads_fwd, reads_rev, rlen, ref4, c, flags)) {
 			int best_read, best_ref, best_score, read_count;
 			forward_i32<W, LO, MODE>(P, s_lut, c, S, slot, best_read, best_ref, best_score, read_count);
+			bs = (float) best_score;
 			t = backtrace_u16<W, MODE>(P, s_lut, c, S, slot, best_read, best_ref, best_score, read_count);
 		}
+		if (out_best != nullptr) out_best[idx] = bs;
 	}
 	FormatOut f;
 	f.cigar_len = f.md_len = f.match = f.mismatch = f.total = f.read_index = 0;

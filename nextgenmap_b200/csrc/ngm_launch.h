@@ -34,6 +34,10 @@ struct ScoreArgs {
 	const uint16_t *rlen;
 	const uint32_t *ref4;
 	float *out;
+	// optional work list: pair i of the launch is pairs[sel[i]] and its result goes to out[sel[i]]; the number of entries is read on the
+	// device (*n_dev <= n) so that a list compacted on the device needs no host round trip.  sel == nullptr: pairs[0..n) in order.
+	const int *sel = nullptr;
+	const int *n_dev = nullptr;
 };
 
 struct AlignArgs {
@@ -47,6 +51,7 @@ struct AlignArgs {
 	uint16_t *ops_scratch;
 	int4 *best_scratch;          // per alignment {best_read, best_ref, best_score, read_count} (s16 path)
 	const float *known;          // local maxima of the pairs (score kernel output) or nullptr
+	float *out_best = nullptr;   // optional, per alignment: the forward pass's maximum = what BatchScore returns for the pair in this mode
 	int stride, ops_cap;
 	ngm_b200_align_rec *recs;
 	char *strings;

@@ -126,6 +126,65 @@ __global__ void __launch_bounds__(256) revcomp_words_kernel(const uint32_t *__re
 	rev[gid] = out;
 }
 
+// The three kernels above in one pass (descriptor path, `set_reads`): one warp per read row.  Every lane packs eight bytes into
+// a code word, the row's length falls out of a warp maximum, and the reverse complement is assembled from the row's words in
+// shared memory -- the ASCII row is read once and nothing is re-read from HBM (the three-kernel form moves ~4 GB per 10 M reads,
+// this one 3.2 GB: 152 B in, 2 x 84 B out).
+__device__ __forceinline__ uint32_t revcomp_word(const uint32_t *f, int hi) {
+	// output nibble k = complement of source index hi - k; indices < 0 read as NUL (only possible above the row's length: masked by the caller)
+	const int wi = hi >> 3;
+	const uint32_t a = f[wi];
+	const uint32_t b = wi > 0 ? f[wi - 1] : kNulWord;
+	const uint32_t x = __funnelshift_rc(b, a, 4 * ((hi & 7) + 1));   // nibble 7 = index hi ... nibble 0 = hi - 7
+	uint32_t y = __byte_perm(x, 0, 0x0123);
+	y = ((y >> 4) & 0x0F0F0F0Fu) | ((y & 0x0F0F0F0Fu) << 4);           // nibble k = index hi - k
+	const uint32_t m = (~y >> 2) & 0x11111111u;                        // codes 0..3 (A C G T): complement = code ^ 3
+	return y ^ (m * 3u);
+}
+
+constexpr int kPackRowsPerBlock = 8;
+
+__global__ void __launch_bounds__(32 * kPackRowsPerBlock) pack_reads_fused_kernel(const uint8_t *__restrict__ src, int rows, int width, int src_stride,
+		uint32_t *__restrict__ fwd, uint32_t *__restrict__ rev, uint16_t *__restrict__ rlen, int words) {
+	__shared__ uint8_t s_code[256];
+	extern __shared__ uint32_t s_rows[];                              // [kPackRowsPerBlock][words]
+	s_code[threadIdx.x] = (uint8_t) ascii_code(threadIdx.x);
+	__syncthreads();
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int row = blockIdx.x * kPackRowsPerBlock + warp;
+	if (row >= rows) return;
+	uint32_t *buf = s_rows + warp * words;
+	const uint8_t *s = src + (size_t) row * src_stride;
+	const bool wide = ((src_stride & 7) == 0) && ((reinterpret_cast<uintptr_t>(src) & 7) == 0);
+	int last = 0;
+	for (int w = lane; w < words; w += 32) {
+		const int i0 = 8 * w;
+		uint32_t word;
+		if (wide && i0 + 8 <= width) {
+			const uint2 v = *reinterpret_cast<const uint2 *>(s + i0);
+			word = (uint32_t) s_code[v.x & 0xFF] | (uint32_t) s_code[(v.x >> 8) & 0xFF] << 4 | (uint32_t) s_code[(v.x >> 16) & 0xFF] << 8 |
+					(uint32_t) s_code[v.x >> 24] << 12 | (uint32_t) s_code[v.y & 0xFF] << 16 | (uint32_t) s_code[(v.y >> 8) & 0xFF] << 20 |
+					(uint32_t) s_code[(v.y >> 16) & 0xFF] << 24 | (uint32_t) s_code[v.y >> 24] << 28;
+		} else {
+			word = 0;
+#pragma unroll
+			for (int k = 0; k < 8; ++k) word |= (uint32_t) s_code[i0 + k < width ? s[i0 + k] : 0] << (4 * k);
+		}
+		buf[w] = word;
+		fwd[(size_t) row * words + w] = word;
+		const uint32_t x = word ^ kNulWord;                          // non-zero nibble <=> code != NUL
+		if (x != 0) last = max(last, i0 + (31 - __clz(x)) / 4 + 1);
+	}
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, d));
+	__syncwarp();
+	if (lane == 0) rlen[row] = (uint16_t) last;
+	for (int w = lane; w < words; w += 32) {
+		const int hi = last - 1 - 8 * w;                             // source index of output nibble 0
+		rev[(size_t) row * words + w] = hi >= 0 ? revcomp_word(buf, hi) : kNulWord;
+	}
+}
+
 // strict path: pair i uses read row i and the window packed at word i * win_words
 __global__ void strict_pairs_kernel(PairDesc *__restrict__ pairs, const uint8_t *__restrict__ flags, int n, int win_words) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -224,7 +283,7 @@ __global__ void gather_winners_kernel(int n_reads, const ngm_b200_pair *__restri
 
 // ScoreBuffer::top1SE + computeMQ (ScoreBuffer.cpp:34-40,228-277); one thread per read.
 __global__ void select_top1_kernel(int n_reads, const int *__restrict__ cand_begin, const float *__restrict__ scores,
-		int *__restrict__ best_pair, int *__restrict__ mapq, int *__restrict__ num_top) {
+		int *__restrict__ best_pair, int *__restrict__ mapq, int *__restrict__ num_top, int strata) {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= n_reads) return;
 	const int b = cand_begin[r], e = cand_begin[r + 1];
@@ -248,10 +307,16 @@ __global__ void select_top1_kernel(int n_reads, const int *__restrict__ cand_beg
 			++nbest;
 		}
 	}
-	if (num_top != nullptr) num_top[r] = nbest;
 	int mq = 0;
 	if (best > 0.0f && second >= 0.0f) mq = (int) ceilf(60.0f * (best - second) / best);
-	best_pair[r] = e > b ? b + besti : -1;
+	int bp = e > b ? b + besti : -1;
+	if (strata && nbest != 1 && e > b) {                       // "too many equal scoring positions": unmapped (ScoreBuffer.cpp:259-276)
+		bp = -1;
+		mq = 0;
+		nbest = 1;
+	}
+	if (num_top != nullptr) num_top[r] = nbest;
+	best_pair[r] = bp;
 	mapq[r] = mq;
 }
 

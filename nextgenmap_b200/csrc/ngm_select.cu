@@ -427,6 +427,19 @@ void pe_release(PeState *pe) {
 	delete pe;
 }
 
+int pe_share_state(ngm_b200_ctx *lane, const ngm_b200_ctx *root) {
+	const PeState *r = root->pe;
+	if (r == nullptr || !r->have_state) {
+		if (lane->pe) lane->pe->have_state = false;
+		return NGM_B200_OK;
+	}
+	if (lane->pe == nullptr) lane->pe = new PeState();
+	lane->pe->hp = r->hp;
+	lane->pe->d_state.borrow(r->d_state);                          // the running insert-size sums are the root's: one sequence over all lanes
+	lane->pe->have_state = true;
+	return NGM_B200_OK;
+}
+
 }  // namespace ngm
 
 using namespace ngm;
@@ -442,6 +455,7 @@ int ngm_b200_pe_configure(ngm_b200_ctx *c, const ngm_b200_pe_params *params) {
 	const long long init[2] = {0, 1};                             // ScoreBuffer.h:90: pairDistCount(1), pairDistSum(0)
 	CU(cudaMemcpy(c->pe->d_state.p, init, sizeof(init), cudaMemcpyHostToDevice));
 	c->pe->have_state = true;
+	c->epoch += 1;
 	return NGM_B200_OK;
 }
 

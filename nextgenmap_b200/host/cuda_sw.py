@@ -66,6 +66,30 @@ class MapResult(C.Structure):
                 ("recs", C.c_void_p), ("strings", C.c_void_p), ("str_capacity", C.c_size_t), ("str_used", C.c_size_t)]
 
 
+class BatchIn(C.Structure):
+    """ngm_b200_batch_in (include/ngm_b200.h)."""
+    _fields_ = [("n_reads", C.c_int32), ("mode", C.c_int32), ("paired", C.c_int32), ("read_format", C.c_int32), ("reads", C.c_void_p), ("read_stride", C.c_int32),
+                ("desc_format", C.c_int32), ("read_len", C.c_void_p), ("exceptions", C.c_void_p), ("n_exceptions", C.c_uint32), ("n_desc", C.c_uint32),
+                ("cand_begin", C.c_void_p), ("desc", C.c_void_p)]
+
+
+class BatchOut(C.Structure):
+    """ngm_b200_batch_out (include/ngm_b200.h)."""
+    _fields_ = [("scores", C.c_void_p), ("best_pair", C.c_void_p), ("mapq", C.c_void_p), ("num_top", C.c_void_p), ("pair_fail", C.c_void_p), ("recs", C.c_void_p),
+                ("strings", C.c_void_p), ("str_capacity", C.c_size_t), ("str_used", C.c_size_t), ("d_str_cursor", C.c_void_p)]
+
+
+READ_EXC = np.dtype([("read_index", "<u4"), ("pos", "<u2"), ("ch", "u1"), ("pad", "u1")])
+READS_ASCII, READS_PACKED2 = 0, 1
+DESC_PAIR16, DESC_U64 = 0, 1
+
+
+def make_desc_u64(window_start, flags) -> np.ndarray:
+    """NGM_B200_DESC(): window start saturated to 56 bits, flags in the top byte."""
+    ws = np.minimum(np.asarray(window_start, dtype=np.uint64), np.uint64(0x00FFFFFFFFFFFFFF))
+    return ws | (np.asarray(flags, dtype=np.uint64) << np.uint64(56))
+
+
 class _CContigRec(C.Structure):
     _fields_ = [("start", C.c_uint64), ("length", C.c_uint32), ("name_len", C.c_uint32), ("name", C.c_char * 100)]
 
@@ -162,6 +186,16 @@ def load_library() -> C.CDLL:
     lib.ngm_b200_free_ht_file.argtypes = [C.POINTER(_CHtFile)]
     lib.ngm_b200_write_ht_file.argtypes = [C.c_char_p, C.POINTER(_CHtFile)]
     lib.ngm_b200_dev_select_top1.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ngm_b200_run_batch.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.POINTER(BatchOut)]
+    lib.ngm_b200_dev_run_batch.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.POINTER(BatchOut), C.c_void_p]
+    lib.ngm_b200_set_pipeline.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.ngm_b200_se_configure.argtypes = [C.c_void_p, C.c_int]
+    lib.ngm_b200_host_alloc.restype = C.c_void_p
+    lib.ngm_b200_host_alloc.argtypes = [C.c_size_t]
+    lib.ngm_b200_host_free.argtypes = [C.c_void_p]
+    lib.ngm_b200_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    lib.ngm_b200_host_unregister.argtypes = [C.c_void_p]
+    lib.ngm_b200_pack_reads.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_int]
     _lib = lib
     return lib
 
@@ -303,6 +337,76 @@ class CudaSW:
             self._check(rc)
             break
         return recs, heap[: used.value]
+
+    # -- whole batches: ScoreBuffer::DoRun + AlignmentBuffer::DoRun in one pipelined call --------------
+    def set_pipeline(self, lanes: int = 3, sub_batch_reads: int = 1 << 20) -> None:
+        self._check(self.lib.ngm_b200_set_pipeline(self.ctx, lanes, sub_batch_reads))
+
+    def se_configure(self, strata: int = 0) -> None:
+        self._check(self.lib.ngm_b200_se_configure(self.ctx, strata))
+
+    def pack_reads(self, reads: np.ndarray, threads: int = 0):
+        """ASCII rows -> (packed2 uint8 [n, row_bytes], read_len uint16 [n], exceptions READ_EXC [k]) on the host (ngm_b200_pack_reads)."""
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        n, stride = reads.shape
+        row_bytes = 4 * ((stride + 15) // 16)
+        packed = np.zeros((n, row_bytes), np.uint8)
+        lens = np.zeros(n, np.uint16)
+        cap = 1024
+        need = C.c_size_t(0)
+        for _ in range(2):
+            exc = np.zeros(cap, dtype=READ_EXC)
+            rc = self.lib.ngm_b200_pack_reads(reads.ctypes.data, n, stride, packed.ctypes.data, row_bytes, lens.ctypes.data, exc.ctypes.data, cap, C.byref(need), threads)
+            if rc == -3 and need.value > cap:
+                cap = need.value
+                continue
+            self._check(rc)
+            break
+        return packed, lens, exc[: need.value]
+
+    def run_batch(self, mode: int, reads: np.ndarray, cand_begin: np.ndarray, pairs: np.ndarray, paired: bool = False, packed: bool = False,
+                  desc_u64: bool = False, str_capacity: Optional[int] = None, want_scores: bool = True) -> dict:
+        """ngm_b200_run_batch on host arrays.  reads: ASCII rows; packed=True sends them 2-bit packed (ngm_b200_pack_reads);
+        pairs: PAIR records (read_index is ignored); desc_u64=True sends 64-bit descriptors."""
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        cand_begin = np.ascontiguousarray(cand_begin, dtype=np.int32)
+        pairs = np.ascontiguousarray(pairs, dtype=PAIR)
+        n = reads.shape[0]
+        npairs = int(cand_begin[-1] - cand_begin[0])
+        keep = []
+        bi = BatchIn()
+        bi.n_reads, bi.mode, bi.paired = n, mode, 1 if paired else 0
+        if packed:
+            pk, lens, exc = self.pack_reads(reads)
+            keep += [pk, lens, exc]
+            bi.read_format, bi.reads, bi.read_stride = READS_PACKED2, pk.ctypes.data, pk.shape[1]
+            bi.read_len, bi.exceptions, bi.n_exceptions = lens.ctypes.data, (exc.ctypes.data if len(exc) else None), len(exc)
+        else:
+            bi.read_format, bi.reads, bi.read_stride = READS_ASCII, reads.ctypes.data, reads.shape[1]
+        if desc_u64:
+            d = np.ascontiguousarray(make_desc_u64(pairs["window_start"], pairs["flags"]))
+            keep.append(d)
+            bi.desc_format, bi.desc = DESC_U64, d.ctypes.data
+        else:
+            bi.desc_format, bi.desc = DESC_PAIR16, pairs.ctypes.data
+        bi.cand_begin = cand_begin.ctypes.data
+        res = {"scores": np.full(max(npairs, 1), np.nan, np.float32), "best_pair": np.zeros(n, np.int32), "mapq": np.zeros(n, np.int32),
+               "num_top": np.zeros(n, np.int32), "pair_fail": np.zeros(n, np.int32), "recs": np.zeros(n, dtype=ALIGN_REC)}
+        cap = str_capacity if str_capacity is not None else max(4096, 96 * n)
+        for _ in range(2):
+            heap = np.zeros(max(cap, 1), np.uint8)
+            bo = BatchOut(res["scores"].ctypes.data if want_scores else None, res["best_pair"].ctypes.data, res["mapq"].ctypes.data, res["num_top"].ctypes.data,
+                          res["pair_fail"].ctypes.data if paired else None, res["recs"].ctypes.data, heap.ctypes.data, cap, 0, None)
+            rc = self.lib.ngm_b200_run_batch(self.ctx, C.byref(bi), C.byref(bo))
+            if rc == -3 and bo.str_used > cap:
+                cap = int(bo.str_used)
+                continue
+            self._check(rc)
+            break
+        res["scores"] = res["scores"][:npairs]
+        res["heap"] = heap
+        res["str_used"] = int(bo.str_used)
+        return res
 
     # -- candidate search (CS / CompactPrefixTable, SURVEY 8f #1) ---------------
     @staticmethod

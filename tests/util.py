@@ -6,6 +6,7 @@ from typing import Dict, List
 
 import numpy as np
 
+ROOT = Path(__file__).resolve().parents[1]
 GOLDEN = Path(__file__).resolve().parent / "golden"
 FIELDS = ("pos", "qstart", "qend", "nm", "identity", "ascore", "cigar", "md")
 
