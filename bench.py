@@ -53,8 +53,8 @@ def parse_args():
     ap.add_argument("--reads", type=int, default=int(os.environ.get("NGM_BENCH_READS", 10_000_000)))
     ap.add_argument("--contigs", type=int, default=int(os.environ.get("NGM_BENCH_CONTIGS", 24)))
     ap.add_argument("--contig-len", type=int, default=int(os.environ.get("NGM_BENCH_CONTIG_LEN", 125_000_000)))
-    ap.add_argument("--sub-batch", type=int, default=1_000_000, help="reads per e2e sub-batch")
-    ap.add_argument("--lanes", type=int, default=3, help="e2e: contexts/streams the sub-batches rotate over")
+    ap.add_argument("--sub-batch", type=int, default=524_288, help="reads per sub-batch inside ngm_b200_run_batch / ngm_b200_map_batch")
+    ap.add_argument("--lanes", type=int, default=4, help="lanes (stream + staging) the sub-batches rotate over inside the library")
     ap.add_argument("--read-len", type=int, default=READ_LEN, help="read length (BASELINE configs[4] sweep: 75/100/150/250/400); default 150")
     ap.add_argument("--corridor", type=int, default=0, help="override the band width (NGM -C n => 2n); 0 = int(5 + 0.15 L)")
     ap.add_argument("--sub-rate", type=float, default=0.01)
@@ -65,7 +65,16 @@ def parse_args():
     ap.add_argument("--no-cs", action="store_true", help="skip the candidate-search section (index build + k-mer vote on device)")
     ap.add_argument("--no-pe", action="store_true", help="skip the paired-end section (needs the candidate-search section)")
     ap.add_argument("--sensitivity", type=float, default=0.5, help="CS sensitivity (NGM -s; its own default when not estimated)")
-    return ap.parse_args()
+    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4],
+                    help="BASELINE.json configs[i]: 1 = 10 M x 150 bp SE (headline, default); 2 = paired-end 2 x 150 bp (10 M reads = 5 M fragments per GPU); "
+                         "3 = 5 M x 250 bp, 12 %% substitutions + 1.5 %% ins + 1.5 %% del, -C 40 (corridor 80); 4 = read-length sweep point, use with --read-len")
+    ap.add_argument("--no-numa", action="store_true", help="N > 1: do not bind the rank to the CPUs next to its GPU before the pinned staging is allocated")
+    args = ap.parse_args()
+    if args.config == 3:
+        args.read_len, args.corridor, args.sub_rate, args.indel_rate = 250, 80, 0.12, 0.03
+        if "NGM_BENCH_READS" not in os.environ and "--reads" not in sys.argv:
+            args.reads = 5_000_000
+    return args
 
 
 # ---------------------------------------------------------------------------
@@ -183,6 +192,28 @@ def run_cpu_reference(refs, qrys, n_align, n_reads, qml, corridor, threads, warm
     return {"value": n_reads * passes / dt, "kind": "port", "cores": 1, "wall_seconds": dt}
 
 
+def bind_to_gpu_numa_node(torch, local_rank: int):
+    """Pinned staging is first-touch: allocate it from the CPUs next to the rank's GPU (N > 1).  -> dict describing what was done."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = Path("/sys/bus/pci/devices") / bdf
+        node = int((base / "numa_node").read_text().strip())
+        cpus = set()
+        for part in (base / "local_cpulist").read_text().strip().split(","):
+            if part:
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if node < 0 or not use or use == allowed:
+            return {"pci": bdf, "numa_node": node, "bound": False}
+        os.sched_setaffinity(0, use)
+        return {"pci": bdf, "numa_node": node, "bound": True, "cpus": len(use)}
+    except Exception as e:  # noqa: BLE001
+        return {"bound": False, "error": str(e)}
+
+
 # ---------------------------------------------------------------------------
 _JSON_FD = None
 
@@ -231,6 +262,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if distributed and args.impl != "reference":
         dist.init_process_group("nccl", device_id=dev)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if (distributed and not args.no_numa and args.impl != "reference") else {"bound": False}
 
     # ---- workload ---------------------------------------------------------
     t_setup = time.perf_counter()
@@ -281,8 +313,13 @@ def main():
         return 0
 
     # ---- B200 arm ---------------------------------------------------------
+    import ctypes as C
     from nextgenmap_b200.host import CudaSW
-    from nextgenmap_b200.host.cuda_sw import ALIGN_REC
+    from nextgenmap_b200.host.cuda_sw import ALIGN_REC, BatchIn, BatchOut, READS_PACKED2, DESC_U64
+    paired = args.config == 2
+    if paired:                                       # BASELINE configs[2]: rows 2f / 2f + 1 are mates, insert ~ N(400, 40), FR
+        batch = workload.make_reads(ref, n_reads, L, qml, corridor, seed=20261018 + 2 + 16 * rank, sub_rate=args.sub_rate, indel_rate=args.indel_rate, paired=True)
+        cfg["workload"] = cfg["workload"].replace(" SE ", " paired-end (2 x, mates in adjacent rows) ")
     sw = CudaSW(qml, corridor, device=local_rank)
     lib, ctx = sw.lib, sw.ctx
     st = torch.cuda.current_stream().cuda_stream
@@ -293,27 +330,58 @@ def main():
         return rc
 
     check(lib.ngm_b200_dev_set_reference(ctx, ref.packed.data_ptr(), ref.concat_len, st))
+    if paired:
+        sw.pe_configure()
+    check(lib.ngm_b200_set_pipeline(ctx, max(1, args.lanes), min(args.sub_batch, max(2, batch.n_reads)) & ~1))
     n, npairs = batch.n_reads, batch.n_pairs
-    d_scores = torch.empty(npairs, dtype=torch.float32, device=dev)
-    d_best = torch.empty(n, dtype=torch.int32, device=dev)
-    d_mapq = torch.empty(n, dtype=torch.int32, device=dev)
-    d_wpairs = torch.empty((n, 16), dtype=torch.uint8, device=dev)
-    d_wscores = torch.empty(n, dtype=torch.float32, device=dev)
-    d_recs = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+    # The caller's staging format (north_star: packed sequences in pinned staging buffers): reads 2 bit / base + lengths, one 64-bit
+    # descriptor per (read, candidate), candidate offsets per read.  Packed on the host by the library's own ngm_b200_pack_reads.
+    t0 = time.perf_counter()
+    reads_np = batch.reads.cpu().numpy()
+    pk_np, len_np, exc_np = sw.pack_reads(reads_np)
+    pack_host_s = time.perf_counter() - t0
+    del reads_np
+    h_packed = torch.from_numpy(pk_np).pin_memory()
+    h_len = torch.from_numpy(len_np.view(np.int16)).pin_memory()
+    del pk_np, len_np
+    ws = batch.pairs[:, 0:8].contiguous().view(torch.int64).reshape(-1)
+    fl = batch.pairs[:, 12:16].contiguous().view(torch.int32).reshape(-1).long()
+    lim = (1 << 56) - 1
+    d_desc = (torch.where((ws < 0) | (ws > lim), torch.full_like(ws, lim), ws) | (fl << 56)).contiguous()      # NGM_B200_DESC()
+    del ws, fl
+    h_desc = d_desc.cpu().pin_memory()
+    h_cb = batch.cand_begin.cpu().pin_memory()
+    d_packed, d_len = h_packed.to(dev), h_len.to(dev)
+    row_bytes = h_packed.shape[1]
     STR_PER = 48 + int(L * args.sub_rate * 5) + (64 if args.indel_rate > 0.001 else 0)      # string-heap bytes per read
     str_cap = STR_PER * n
+    d_scores = torch.empty(max(npairs, 1), dtype=torch.float32, device=dev)
+    d_best = torch.empty(n, dtype=torch.int32, device=dev)
+    d_mapq = torch.empty(n, dtype=torch.int32, device=dev)
+    d_ntop = torch.empty(n, dtype=torch.int32, device=dev)
+    d_pfail = torch.empty(n, dtype=torch.int32, device=dev)
+    d_recs = torch.empty((n, 32), dtype=torch.uint8, device=dev)
     d_strings = torch.empty(str_cap, dtype=torch.uint8, device=dev)
     d_cursor = torch.zeros(1, dtype=torch.int32, device=dev)
+    exc_ptr = exc_np.ctypes.data if len(exc_np) else None
+    d_exc = torch.from_numpy(exc_np.view(np.uint8).reshape(-1, 8).copy()).to(dev) if len(exc_np) else None
+
+    def batch_in(reads_ptr, len_ptr, exc_p, cb_ptr, desc_ptr):
+        bi = BatchIn()
+        bi.n_reads, bi.mode, bi.paired, bi.read_format = n, MODE_LOCAL, 1 if paired else 0, READS_PACKED2
+        bi.reads, bi.read_stride, bi.desc_format, bi.read_len = reads_ptr, row_bytes, DESC_U64, len_ptr
+        bi.exceptions, bi.n_exceptions, bi.n_desc, bi.cand_begin, bi.desc = exc_p, len(exc_np), npairs, cb_ptr, desc_ptr
+        return bi
+
+    dev_in = batch_in(d_packed.data_ptr(), d_len.data_ptr(), d_exc.data_ptr() if d_exc is not None else None, batch.cand_begin.data_ptr(), d_desc.data_ptr())
+    dev_out = BatchOut(d_scores.data_ptr(), d_best.data_ptr(), d_mapq.data_ptr(), d_ntop.data_ptr(), d_pfail.data_ptr() if paired else None, d_recs.data_ptr(),
+                       d_strings.data_ptr(), str_cap, 0, d_cursor.data_ptr())
+    cfg["step"] = ("ngm_b200_dev_run_batch: expand 2-bit reads (+ reverse complements) -> resolve descriptors -> score the candidates of multi-candidate reads -> "
+                   + ("top1PE (select_pairs)" if paired else "top1 + MAPQ") + " -> align + backtrace + CIGAR/MD of every winner"
+                   + ("" if paired else " (single-candidate reads take their score from the alignment's forward pass)"))
 
     def resident_step():
-        check(lib.ngm_b200_dev_set_reads(ctx, batch.reads.data_ptr(), n, qml, st))
-        check(lib.ngm_b200_dev_score_pairs(ctx, MODE_LOCAL, npairs, batch.pairs.data_ptr(), d_scores.data_ptr(), st))
-        check(lib.ngm_b200_dev_select_top1(ctx, n, batch.cand_begin.data_ptr(), d_scores.data_ptr(), d_best.data_ptr(), d_mapq.data_ptr(), st))
-        check(lib.ngm_b200_dev_gather_winners_scored(ctx, n, batch.pairs.data_ptr(), d_scores.data_ptr(), d_best.data_ptr(), d_wpairs.data_ptr(),
-                                                     d_wscores.data_ptr(), st))
-        d_cursor.zero_()
-        check(lib.ngm_b200_dev_align_pairs_scored(ctx, MODE_LOCAL, n, d_wpairs.data_ptr(), d_wscores.data_ptr(), d_recs.data_ptr(), d_strings.data_ptr(),
-                                                  str_cap, d_cursor.data_ptr(), st))
+        check(lib.ngm_b200_dev_run_batch(ctx, C.byref(dev_in), C.byref(dev_out), st))
 
     def barrier():
         if distributed:
@@ -323,6 +391,8 @@ def main():
     clocks = ClockSampler(local_rank)
     clocks.start()
     for _ in range(max(args.warmup, 3)):
+        if paired:
+            sw.pe_configure()
         resident_step()
     barrier()
     if int(d_cursor.item()) > str_cap:
@@ -339,10 +409,20 @@ def main():
     barrier()
     clocks.mark_end()
     ms = e0.elapsed_time(e1)
-    launches = sw.launch_count() - launches0 + args.steps      # + one memset (cursor) per step issued by torch
+    launches = sw.launch_count() - launches0
     clk = clocks.stop()
+    if paired:                                       # leave the first-batch result in the buffers (the parity sample below starts from fresh sums)
+        sw.pe_configure()
+        resident_step()
+        torch.cuda.synchronize()
+    recs_all = d_recs.cpu().numpy().view(ALIGN_REC).reshape(-1)
+    best_all = d_best.cpu().numpy()
+    mapq_all = d_mapq.cpu().numpy()
+    mapped = int(np.count_nonzero(recs_all["score"] >= 0))
+    used_strings = int(d_cursor.item())
+    heap_res = d_strings[:used_strings].cpu().numpy()
 
-    # per-kernel timing of the two DP kernels on the launching stream (roofline)
+    # per-kernel timing on the launching stream (roofline): the classic device entry points on the same data
     def time_call(fn, reps=5):
         fn()
         torch.cuda.synchronize()
@@ -354,130 +434,101 @@ def main():
         torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
 
-    ms_score = time_call(lambda: check(lib.ngm_b200_dev_score_pairs(ctx, MODE_LOCAL, npairs, batch.pairs.data_ptr(), d_scores.data_ptr(), st)))
+    d_wpairs = torch.empty((n, 16), dtype=torch.uint8, device=dev)
+    d_wscores = torch.empty(n, dtype=torch.float32, device=dev)
+    d_scores_all = torch.empty(max(npairs, 1), dtype=torch.float32, device=dev)
+    d_best1 = torch.empty(n, dtype=torch.int32, device=dev)
+    d_mapq1 = torch.empty(n, dtype=torch.int32, device=dev)
+    ms_pack = time_call(lambda: check(lib.ngm_b200_dev_set_reads(ctx, batch.reads.data_ptr(), n, qml, st)))
+    ms_score = time_call(lambda: check(lib.ngm_b200_dev_score_pairs(ctx, MODE_LOCAL, npairs, batch.pairs.data_ptr(), d_scores_all.data_ptr(), st)))
+    check(lib.ngm_b200_dev_select_top1(ctx, n, batch.cand_begin.data_ptr(), d_scores_all.data_ptr(), d_best1.data_ptr(), d_mapq1.data_ptr(), st))
+    check(lib.ngm_b200_dev_gather_winners_scored(ctx, n, batch.pairs.data_ptr(), d_scores_all.data_ptr(), d_best1.data_ptr(), d_wpairs.data_ptr(), d_wscores.data_ptr(), st))
+    d_recs1 = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+    d_cursor1 = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def align_only():
-        d_cursor.zero_()
-        check(lib.ngm_b200_dev_align_pairs_scored(ctx, MODE_LOCAL, n, d_wpairs.data_ptr(), d_wscores.data_ptr(), d_recs.data_ptr(), d_strings.data_ptr(),
-                                                  str_cap, d_cursor.data_ptr(), st))
+        d_cursor1.zero_()
+        check(lib.ngm_b200_dev_align_pairs_scored(ctx, MODE_LOCAL, n, d_wpairs.data_ptr(), d_wscores.data_ptr(), d_recs1.data_ptr(), d_strings.data_ptr(),
+                                                  str_cap, d_cursor1.data_ptr(), st))
 
     def align_unscored():
-        d_cursor.zero_()
-        check(lib.ngm_b200_dev_align_pairs(ctx, MODE_LOCAL, n, d_wpairs.data_ptr(), d_recs.data_ptr(), d_strings.data_ptr(), str_cap, d_cursor.data_ptr(), st))
+        d_cursor1.zero_()
+        check(lib.ngm_b200_dev_align_pairs(ctx, MODE_LOCAL, n, d_wpairs.data_ptr(), d_recs1.data_ptr(), d_strings.data_ptr(), str_cap, d_cursor1.data_ptr(), st))
 
     ms_align_unscored = time_call(align_unscored, reps=2)
-
     ms_align = time_call(align_only)
-    ms_pack = time_call(lambda: check(lib.ngm_b200_dev_set_reads(ctx, batch.reads.data_ptr(), n, qml, st)))
+    # forward / backtrace split of one align pass (events recorded inside the library between the two kernels of every launch set)
+    lib.ngm_b200_profile.argtypes = [C.c_void_p, C.c_int]
+    lib.ngm_b200_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.ngm_b200_alu_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    check(lib.ngm_b200_profile(ctx, 1))
+    align_only()
+    f_ms, b_ms = C.c_float(0), C.c_float(0)
+    launch_sets = check(lib.ngm_b200_profile_read(ctx, C.byref(f_ms), C.byref(b_ms)))
+    check(lib.ngm_b200_profile(ctx, 0))
+    ms_fwd, ms_bt = float(f_ms.value), float(b_ms.value)
+    pa, pi_, pm = C.c_double(0), C.c_double(0), C.c_double(0)
+    check(lib.ngm_b200_alu_peak(ctx, C.byref(pa), C.byref(pi_), C.byref(pm)))
+    alu_rate, imad_rate, mixed_rate = float(pa.value), float(pi_.value), float(pm.value)
+    # the separate-call pipeline must agree with the fused batch (single-end: same winners, same records)
+    classic_equal = None
+    if not paired:
+        r1 = d_recs1.cpu().numpy().view(ALIGN_REC).reshape(-1)
+        classic_equal = bool(np.array_equal(d_best1.cpu().numpy(), best_all) and np.array_equal(d_mapq1.cpu().numpy(), mapq_all)
+                             and all(np.array_equal(r1[f], recs_all[f]) for f in ["position_offset", "qstart", "qend", "nm", "identity", "score", "cigar_len", "md_len"])
+                             and np.array_equal(d_scores_all.cpu().numpy(), d_scores.cpu().numpy()))
+    del d_recs1
 
-    recs_all = d_recs.cpu().numpy().view(ALIGN_REC).reshape(-1)
-    mapped = int(np.count_nonzero(recs_all["score"] >= 0))
-    used_strings = int(d_cursor.item())
-
-    # ---- end to end through the C ABI with host buffers ---------------------
+    # ---- end to end through the C ABI with host buffers: ONE ngm_b200_run_batch call per step ---------------
     e2e = None
     if not args.no_e2e:
-        SB = min(args.sub_batch, n)
-        cb_h = batch.cand_begin.cpu().numpy()
-        h_reads = batch.reads.cpu().pin_memory()
-        # descriptors as the caller would hand them over per sub-batch: read indices and candidate
-        # offsets relative to the sub-batch (prepared once, outside the timed region)
-        pdt = np.dtype([("window_start", "<u8"), ("read_index", "<u4"), ("flags", "<u4")])
-        pairs_np = batch.pairs.cpu().numpy().view(pdt).reshape(-1).copy()
-        cb_rel = []
-        for s in range(0, n, SB):
-            m = min(SB, n - s)
-            p0, p1 = int(cb_h[s]), int(cb_h[s + m])
-            pairs_np["read_index"][p0:p1] -= np.uint32(s)
-            cb_rel.append((cb_h[s: s + m + 1] - cb_h[s]).astype(np.int32))
-        h_pairs = torch.from_numpy(pairs_np.view(np.uint8).reshape(-1, 16)).pin_memory()
-        h_cbs = [torch.from_numpy(c).pin_memory() for c in cb_rel]
-        max_pairs = int(max(cb_h[min(s + SB, n)] - cb_h[s] for s in range(0, n, SB)))
-        h_recs = torch.empty((n, 32), dtype=torch.uint8).pin_memory()
-        h_mapq = torch.empty(n, dtype=torch.int32).pin_memory()
-        h_strings = torch.empty(str_cap, dtype=torch.uint8).pin_memory()
-        h_used = torch.zeros(((n + SB - 1) // SB,), dtype=torch.int32).pin_memory()
-        lanes = []
-        for _ in range(max(1, args.lanes)):
-            lane_sw = CudaSW(qml, corridor, device=local_rank)
-            s_ = torch.cuda.Stream(device=dev)
-            with torch.cuda.stream(s_):
-                check(lib.ngm_b200_dev_set_reference(lane_sw.ctx, ref.packed.data_ptr(), ref.concat_len, s_.cuda_stream))
-            lanes.append(dict(sw=lane_sw, stream=s_, reads=torch.empty((SB, qml), dtype=torch.uint8, device=dev),
-                              pairs=torch.empty((max_pairs, 16), dtype=torch.uint8, device=dev), cb=torch.empty(SB + 1, dtype=torch.int32, device=dev),
-                              scores=torch.empty(max_pairs, dtype=torch.float32, device=dev), best=torch.empty(SB, dtype=torch.int32, device=dev),
-                              mapq=torch.empty(SB, dtype=torch.int32, device=dev), wpairs=torch.empty((SB, 16), dtype=torch.uint8, device=dev),
-                              wscores=torch.empty(SB, dtype=torch.float32, device=dev),
-                              recs=torch.empty((SB, 32), dtype=torch.uint8, device=dev), strings=torch.empty(STR_PER * SB, dtype=torch.uint8, device=dev),
-                              cursor=torch.zeros(1, dtype=torch.int32, device=dev), pending=None))
-        torch.cuda.synchronize()
-        h2d = d2h = 0
-
-        def finish(lane):
-            """copy the strings of the lane's previous sub-batch once its cursor is known"""
-            nonlocal d2h
-            p = lane["pending"]
-            if p is None:
-                return
-            lane["stream"].synchronize()
-            used = int(h_used[p["k"]].item())
-            with torch.cuda.stream(lane["stream"]):
-                h_strings[p["soff"]: p["soff"] + used].copy_(lane["strings"][:used], non_blocking=True)
-            d2h += used
-            lane["pending"] = None
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+        h_scores, h_best, h_mapq, h_ntop, h_pfail = pin(max(npairs, 1), torch.float32), pin(n, torch.int32), pin(n, torch.int32), pin(n, torch.int32), pin(n, torch.int32)
+        h_recs, h_strings = pin((n, 32), torch.uint8), pin(str_cap, torch.uint8)
+        host_in = batch_in(h_packed.data_ptr(), h_len.data_ptr(), exc_ptr, h_cb.data_ptr(), h_desc.data_ptr())
+        host_out = BatchOut(h_scores.data_ptr(), h_best.data_ptr(), h_mapq.data_ptr(), h_ntop.data_ptr(), h_pfail.data_ptr() if paired else None, h_recs.data_ptr(),
+                            h_strings.data_ptr(), str_cap, 0, None)
 
         def e2e_step():
-            nonlocal h2d, d2h
-            for k, s in enumerate(range(0, n, SB)):
-                lane = lanes[k % len(lanes)]
-                finish(lane)
-                m = min(SB, n - s)
-                p0, p1 = int(cb_h[s]), int(cb_h[s + m])
-                mp = p1 - p0
-                c_, q_ = lane["sw"].ctx, lane["stream"].cuda_stream
-                with torch.cuda.stream(lane["stream"]):
-                    lane["reads"][:m].copy_(h_reads[s: s + m], non_blocking=True)
-                    lane["pairs"][:mp].copy_(h_pairs[p0:p1], non_blocking=True)
-                    lane["cb"][: m + 1].copy_(h_cbs[k], non_blocking=True)
-                    check(lib.ngm_b200_dev_set_reads(c_, lane["reads"].data_ptr(), m, qml, q_))
-                    check(lib.ngm_b200_dev_score_pairs(c_, MODE_LOCAL, mp, lane["pairs"].data_ptr(), lane["scores"].data_ptr(), q_))
-                    check(lib.ngm_b200_dev_select_top1(c_, m, lane["cb"].data_ptr(), lane["scores"].data_ptr(), lane["best"].data_ptr(), lane["mapq"].data_ptr(), q_))
-                    check(lib.ngm_b200_dev_gather_winners_scored(c_, m, lane["pairs"].data_ptr(), lane["scores"].data_ptr(), lane["best"].data_ptr(),
-                                                                 lane["wpairs"].data_ptr(), lane["wscores"].data_ptr(), q_))
-                    lane["cursor"].zero_()
-                    check(lib.ngm_b200_dev_align_pairs_scored(c_, MODE_LOCAL, m, lane["wpairs"].data_ptr(), lane["wscores"].data_ptr(), lane["recs"].data_ptr(),
-                                                              lane["strings"].data_ptr(), STR_PER * SB, lane["cursor"].data_ptr(), q_))
-                    h_recs[s: s + m].copy_(lane["recs"][:m], non_blocking=True)
-                    h_mapq[s: s + m].copy_(lane["mapq"][:m], non_blocking=True)
-                    h_used[k: k + 1].copy_(lane["cursor"], non_blocking=True)
-                h2d += m * qml + mp * 16 + (m + 1) * 4
-                d2h += m * 32 + m * 4 + 4
-                lane["pending"] = dict(k=k, soff=STR_PER * s)
-            for lane in lanes:
-                finish(lane)
-            for lane in lanes:
-                lane["stream"].synchronize()
+            check(lib.ngm_b200_run_batch(ctx, C.byref(host_in), C.byref(host_out)))
 
         for _ in range(2):
+            if paired:
+                sw.pe_configure()
             e2e_step()
         barrier()
-        h2d = d2h = 0
+        e2e_launch0 = sw.launch_count()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             e2e_step()
         barrier()
         e2e_s = time.perf_counter() - t0
-        e2e_launch = sum(l["sw"].launch_count() for l in lanes)
         e2e_ms = sharding.max_over_ranks(e2e_s * 1e3, dev)
-        e2e = {"value": world * n * args.steps / (e2e_ms / 1e3), "unit": "reads/s", "h2d_bytes_per_step": h2d // args.steps,
-               "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_ms / args.steps, "sub_batch_reads": SB, "streams": len(lanes),
-               "timer": "host wall clock around K steps (barrier + synchronize both sides), max over ranks"}
-        # the e2e path must reproduce the resident results bit for bit
+        used_e2e = int(host_out.str_used)
+        h2d = n * row_bytes + n * 2 + (n + 1) * 4 + npairs * 8 + len(exc_np) * 8
+        d2h = npairs * 4 + n * (4 + 4 + 4 + 32) + (n * 4 if paired else 0) + used_e2e + 4 * ((n + args.sub_batch - 1) // args.sub_batch)
+        e2e = {"value": world * n * args.steps / (e2e_ms / 1e3), "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": e2e_ms / args.steps, "sub_batch_reads": args.sub_batch, "lanes": args.lanes,
+               "h2d_gbs_per_gpu": h2d / (e2e_ms / args.steps * 1e-3) / 1e9, "d2h_gbs_per_gpu": d2h / (e2e_ms / args.steps * 1e-3) / 1e9,
+               "api": "one ngm_b200_run_batch call per step: pinned host reads (2 bit/base) + 64-bit descriptors + candidate offsets in; scores, winners, MAPQ, "
+                      "alignment records and CIGAR/MD strings back in pinned host memory; the library cuts the batch into sub-batches over its own lanes/streams",
+               "gpu_launches": sw.launch_count() - e2e_launch0, "numa": numa,
+               "timer": "host wall clock around K calls (barrier + synchronize both sides), max over ranks"}
+        if paired:                                   # compare a first batch after configure with the resident first batch
+            sw.pe_configure()
+            e2e_step()
         h_view = h_recs.numpy().view(ALIGN_REC).reshape(-1)
         fields = ["position_offset", "qstart", "qend", "nm", "identity", "score", "cigar_len", "md_len"]
-        e2e["matches_resident"] = bool(all(np.array_equal(h_view[f], recs_all[f]) for f in fields))
-        for lane in lanes:
-            lane["sw"].close()
+        same = all(np.array_equal(h_view[f], recs_all[f]) for f in fields) and np.array_equal(h_best.numpy(), best_all) and np.array_equal(h_mapq.numpy(), mapq_all)
+        same = same and np.array_equal(h_scores.numpy()[:npairs], d_scores.cpu().numpy()[:npairs])
+        # strings: the e2e heap is sparse (one slot per sub-batch), the resident heap dense; compare the text of a sample of reads
+        hs = h_strings.numpy()
+        for r in range(0, n, max(1, n // 50_000)):
+            a, b = h_view[r], recs_all[r]
+            if b["score"] >= 0:
+                la = int(a["cigar_len"]) + int(a["md_len"])
+                same = same and bytes(hs[int(a["str_off"]): int(a["str_off"]) + la]) == bytes(heap_res[int(b["str_off"]): int(b["str_off"]) + la])
+        e2e["matches_resident"] = bool(same)
 
     # ---- candidate search on device (SURVEY 8f #1): reads -> k-mer vote -> candidates -> score -> top1 -> align ----
     cs_info = None
@@ -764,13 +815,42 @@ def main():
         want = port.batch_score(refs_s, qrys_s, qml, corridor, MODE_LOCAL)
         got = d_scores[: int(cb[-1])].cpu().numpy()[order]
         parity = {"score_pairs_checked": int(len(order)), "score_mismatches": int(np.count_nonzero(want != got))}
+        # alignments of the sample's winners: position, QStart / QEnd, NM, identity, CIGAR and MD against the oracle's BatchAlign
+        # (windows the way AlignmentBuffer decodes them: refMaxLen of AlignmentBuffer.h:67)
+        inv = np.empty(len(order), np.int64)
+        inv[order] = np.arange(len(order))
+        win = best_all[:n_s]
+        sel_reads = np.nonzero(win >= 0)[0][:25_000]
+        abuf = (qml + corridor) | 2
+        refs_a = np.zeros((len(sel_reads), max(abuf, qml + corridor)), np.uint8)
+        for i, r in enumerate(sel_reads):
+            w = port.decode_window(packed_host, ref.concat_len, int(pairs_h["window_start"][win[r]]), abuf)
+            if w is not None:
+                refs_a[i, :abuf] = np.frombuffer(w, np.uint8)
+        qrys_a = qrys_s[inv[win[sel_reads]]]
+        wa = port.batch_align(refs_a, qrys_a, qml, corridor, MODE_LOCAL)
+        bad = 0
+        for i, r in enumerate(sel_reads):
+            g, a = recs_all[r], wa[i]
+            o = int(g["str_off"])
+            cig = bytes(heap_res[o: o + int(g["cigar_len"])])
+            md = bytes(heap_res[o + int(g["cigar_len"]): o + int(g["cigar_len"]) + int(g["md_len"])]).split(b"\0")[0]
+            if a.ascore == -1.0 and a.cigar == b"!!!":
+                ok = float(g["score"]) == -1.0
+            else:
+                ok = ((int(g["position_offset"]), int(g["qstart"]), int(g["qend"]), int(g["nm"]), np.float32(g["identity"]).tobytes(), float(g["score"]), cig, md)
+                      == (a.position_offset, a.qstart, a.qend, a.nm, np.float32(a.identity).tobytes(), a.ascore, a.cigar, a.md))
+            bad += 0 if ok else 1
+        parity.update({"alignments_checked": int(len(sel_reads)), "align_mismatches": int(bad),
+                       "align_fields": "PositionOffset, QStart, QEnd, NM, Identity (bit pattern), Align.Score, CIGAR, MD vs oracle/ngm_oracle.c BatchAlign"})
         if not args.no_cpu_baseline:
             res = run_cpu_reference(refs_s, qrys_s, n_align, n_s, qml, corridor, host_threads, 1, 3)
             cpu_baseline = {"value": res["value"], "unit": "reads/s", "cores": res["cores"], "kind": res["kind"],
                             "sample": f"{n_s} reads / {len(refs_s)} pairs of the same workload, 3 timed passes after 1 warm pass",
                             "score_pairs_per_s": res.get("score_pairs_per_s"), "align_pairs_per_s": res.get("align_pairs_per_s")}
     except Exception as e:  # noqa: BLE001
-        parity = {"error": str(e)}
+        import traceback
+        parity = {"error": str(e), "trace": traceback.format_exc()[-600:]}
 
     # ---- strict IAlignment path (char** in, struct Align out), one host thread, for the record ----
     strict = None
@@ -824,40 +904,58 @@ def main():
         cs_info["roofline"]["frac"] = cs_info["roofline"]["achieved"] / hbm_peak
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
     sm_mhz = clk.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
-    dominant = "score" if ms_score >= ms_align else "align"
-    dom_ms = max(ms_score, ms_align)
+    # The step's DP work: the score kernel runs on the candidates of multi-candidate reads only (single-end), the align launch set on every read.
+    multi_pairs = npairs if paired else int((batch.cand_begin[1:] - batch.cand_begin[:-1])[(batch.cand_begin[1:] - batch.cand_begin[:-1]) > 1].sum().item())
+    ms_score_step = ms_score * multi_pairs / max(npairs, 1)
+    dominant = "score" if ms_score_step >= ms_align else "align"
+    dom_ms = ms_score if dominant == "score" else ms_align
     dom_units = npairs if dominant == "score" else n
     alg_bytes = ALG_BYTES_SCORE * dom_units if dominant == "score" else (ALG_BYTES_SCORE + 8 + 2 * 4) * dom_units
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
     # DRAM traffic of the dominant launch set from the committed ncu capture (bytes per unit x units of this run)
-    traffic = None
-    tf = ROOT / "profiles" / "traffic_r1.json"
-    if tf.exists() and L == READ_LEN and not args.corridor:
-        tj = json.loads(tf.read_text())
-        per_unit = tj["score_s16_kernel"]["dram_bytes_per_unit"] if dominant == "score" else (
-            tj["align_s16_fwd_kernel"]["dram_bytes_per_unit"] + tj["backtrace_format_kernel"]["dram_bytes_per_unit"])
-        traffic = per_unit * dom_units
-    # integer-ALU roofline: SMs x 128 lanes x clock / 5 instr per cell, x2 for s16x2 lanes
-    alu_peak_gcups = sm_count * 128 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 5 / 1e9
+    traffic, traffic_src = None, None
+    for name in ("traffic_r2.json", "traffic_r1.json"):
+        tf = ROOT / "profiles" / name
+        if tf.exists() and L == READ_LEN and not args.corridor:
+            tj = json.loads(tf.read_text())
+            fwd_key = "align_s16_fwd2_kernel" if "align_s16_fwd2_kernel" in tj else "align_s16_fwd_kernel"
+            per_unit = tj["score_s16_kernel"]["dram_bytes_per_unit"] if dominant == "score" else (
+                tj[fwd_key]["dram_bytes_per_unit"] + tj["backtrace_format_kernel"]["dram_bytes_per_unit"])
+            traffic, traffic_src = per_unit * dom_units, f"profiles/{name}"
+            break
+    # Integer-ALU roofline against the MEASURED issue rate of the recurrence's own instruction (VIADDMNMX.S16x2, ngm_b200_alu_peak):
+    # one s16x2 instruction serves two cells.  Floors: score 4 ALU instructions per cell pair (substitution PRMT, diag VIADD, two VIADDMNMX);
+    # forward-with-pointers 5 (+ the LOP3 that strips the direction tag; the tag arithmetic itself runs on the FMA pipe).
     score_gcups = npairs * CELLS_PER_PAIR / (ms_score * 1e-3) / 1e9
     align_gcups = n * CELLS_PER_PAIR / (ms_align * 1e-3) / 1e9
+    fwd_gcups = n * CELLS_PER_PAIR / (max(ms_fwd, 1e-6) * 1e-3) / 1e9
+    peak_score_gcups = alu_rate * 2 / 4 / 1e9
+    peak_fwd_gcups = alu_rate * 2 / 5 / 1e9
+    survey_peak_gcups = 2 * sm_count * 128 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 5 / 1e9
     line = {
         "metric": "reads/sec aligned (150bp SE vs 3Gbp ref)", "value": total_reads * args.steps / (ms_max * 1e-3), "unit": "reads/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int16x2", "data": "synthetic", "config": cfg,
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
-        "roofline": {"kernel": "score_s16_kernel" if dominant == "score" else "align_s16_fwd_kernel + backtrace_format_kernel (one launch set per 262144 alignments)",
+        "roofline": {"kernel": "score_s16_kernel" if dominant == "score" else "align_s16_fwd2_kernel + backtrace_format_kernel (one launch set per 262144 alignments)",
                      "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": traffic, "traffic_note": "dram bytes for the units of one step, from the ncu capture in profiles/traffic_r1.json; the pointer matrix (1.3 KB/alignment) makes it ~11x the algorithmic bytes and still only ~12 % of HBM peak",
+                     "traffic": traffic, "traffic_note": f"dram bytes for the units of one launch set pass, from the ncu --set full capture summarised in {traffic_src}",
                      "peak_source": peak_src, "ms_per_launch_set": dom_ms, "units_per_launch_set": dom_units,
                      "algorithmic_bytes_per_unit": alg_bytes / dom_units,
                      "note": "integer DP: ~22 cells per algorithmic byte, so the HBM fraction is small by construction; the binding roofline is roofline_alu"},
-        "roofline_alu": {"bound": "int-alu issue", "score_gcups": score_gcups, "align_gcups": align_gcups, "peak_gcups_int32": alu_peak_gcups,
-                         "peak_gcups_s16x2": 2 * alu_peak_gcups, "score_frac_of_s16x2_peak": score_gcups / (2 * alu_peak_gcups),
-                         "align_frac_of_int32_peak": align_gcups / alu_peak_gcups, "sm_count": sm_count, "sm_mhz_under_load": sm_mhz,
-                         "definition": f"cells = L x corridor = {CELLS_PER_PAIR} per pair; peak = SMs x 128 lanes x max clock / 5 instr per cell (SURVEY 8d)"},
-        "kernel_ms": {"set_reads": ms_pack, "score": ms_score, "align": ms_align, "align_without_known_scores": ms_align_unscored, "score_share": ms_score / (ms_max / args.steps),
-                      "align_share": ms_align / (ms_max / args.steps)},
+        "roofline_alu": {"bound": "int-alu issue", "measured_viaddmnmx_s16x2_per_s": alu_rate, "measured_imad_per_s": imad_rate, "measured_mixed_per_s": mixed_rate,
+                         "score_gcups": score_gcups, "peak_score_gcups": peak_score_gcups, "score_frac": score_gcups / peak_score_gcups,
+                         "align_forward_gcups": fwd_gcups, "peak_forward_gcups": peak_fwd_gcups, "align_forward_frac": fwd_gcups / peak_fwd_gcups,
+                         "align_launch_set_gcups": align_gcups, "align_launch_set_frac": align_gcups / peak_fwd_gcups,
+                         "survey_model_peak_gcups_s16x2": survey_peak_gcups, "score_frac_of_survey_model": score_gcups / survey_peak_gcups,
+                         "align_launch_set_frac_of_survey_model": align_gcups / survey_peak_gcups,
+                         "sm_count": sm_count, "sm_mhz_under_load": sm_mhz,
+                         "definition": f"cells = L x corridor = {CELLS_PER_PAIR} per pair; peak = measured VIADDMNMX.S16x2 thread-instructions/s x 2 cells / (4 | 5) ALU "
+                                       "instructions per cell pair; the survey's model (SMs x 128 lanes x max clock / 5 instr per cell, x2) is kept beside it"},
+        "kernel_ms": {"set_reads_ascii": ms_pack, "score_all_pairs": ms_score, "score_in_step": ms_score_step, "align_launch_sets": ms_align, "align_forward": ms_fwd,
+                      "align_backtrace_format": ms_bt, "align_without_known_scores": ms_align_unscored, "launch_sets": launch_sets,
+                      "pairs_scored_in_step": multi_pairs, "score_share": ms_score_step / (ms_max / args.steps), "align_share": ms_align / (ms_max / args.steps),
+                      "classic_calls_equal_batch": classic_equal, "pack_reads_host_seconds": pack_host_s},
         "candidate_search": cs_info,
         "cpu_baseline": cpu_baseline, "parity_sample": parity, "strict_path": strict,
         "counters": {"reads": total_reads, "mapped": ctr["mapped"], "pairs_scored": ctr["pairs_scored"], "string_bytes": used_strings},

@@ -381,7 +381,7 @@ int ngm_b200_dev_cs_search(ngm_b200_ctx *ctx, const void *d_ascii_reads, int n_r
  * (a multiple of 4) holding 2 bits per base, base i in bits [2(i & 15), +2) of little-endian word i >> 4, A0 C1 G2 T3; read_len[r] =
  * bases in row r; every base that is not A/C/G/T is listed in `exceptions` (sorted by read, then position) with its ASCII byte.
  * 150 bp: 40 + 2 instead of 152 bytes per read cross PCIe.
- * Descriptor formats.  PAIR16: ngm_b200_pair (read_index is ignored: candidate lists are given by cand_begin).  U64: NGM_B200_DESC(). */
+ * Descriptor formats.  PAIR16: struct ngm_b200_pair -- its read_index is ignored, candidate lists are given by cand_begin.  U64: NGM_B200_DESC(). */
 typedef struct ngm_b200_read_exc {
 	uint32_t read_index;
 	uint16_t pos;
@@ -449,6 +449,15 @@ int ngm_b200_host_unregister(void *p);
 int ngm_b200_pack_reads(const char *ascii, int n_reads, int stride, void *packed, int row_bytes, uint16_t *read_len, ngm_b200_read_exc *exceptions,
 		size_t exc_cap, size_t *n_exc, int threads);
 
+/* -- measurement helpers (bench.py) ------------------------------------------------------------------------- */
+/* Issue rates measured on this device, in thread-level instructions per second: VIADDMNMX.S16x2 (the integer ALU pipe the DP
+ * recurrence runs on), IMAD (the FMA pipe the tag arithmetic is moved to) and both interleaved 1:1.  Denominators of bench.py's
+ * roofline_alu instead of a nominal lanes x clock model.  Synchronous, ~50 ms. */
+int ngm_b200_alu_peak(ngm_b200_ctx *ctx, double *viaddmnmx_per_s, double *imad_per_s, double *mixed_per_s);
+/* enable != 0: the following align launch sets on this context are bracketed by events (forward kernel | backtrace kernel);
+ * ngm_b200_profile_read synchronises, returns the number of launch sets and their summed durations in ms, and re-arms. */
+int ngm_b200_profile(ngm_b200_ctx *ctx, int enable);
+int ngm_b200_profile_read(ngm_b200_ctx *ctx, float *forward_ms, float *backtrace_ms);
 /* Number of kernels this context has launched since creation (bench.py gpu_launches). */
 uint64_t ngm_b200_launch_count(const ngm_b200_ctx *ctx);
 

@@ -14,8 +14,12 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
-OBJ = PKG / "build"
-LIB = PKG / "libngm_b200.so"
+# A/B builds: NGM_B200_DEFINES="-DNGM_FWD_ROW_UNROLL=8" NGM_B200_VARIANT=u8 python -m nextgenmap_b200.build  ->  libngm_b200_u8.so
+# (objects under build_u8/); load it with NGM_B200_LIB=<path>.  The product is the default build.
+VARIANT = os.environ.get("NGM_B200_VARIANT", "")
+EXTRA_DEFINES = os.environ.get("NGM_B200_DEFINES", "").split()
+OBJ = PKG / ("build_" + VARIANT if VARIANT else "build")
+LIB = PKG / ("libngm_b200_" + VARIANT + ".so" if VARIANT else "libngm_b200.so")
 NVCC = os.environ.get("NVCC", "nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CUFLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
@@ -36,7 +40,7 @@ def compile_one(src: Path, force: bool) -> Path:
     obj = OBJ / (src.name + ".o")
     deps = [src] + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list((PKG.parent / "include").glob("*.h"))
     if force or stale(obj, deps):
-        cmd = [NVCC] + ARCH + CUFLAGS + ["-DNGM_HAVE_S16" if (CSRC / "k_score_s16.cu").exists() else "-DNGM_NO_S16",
+        cmd = [NVCC] + ARCH + CUFLAGS + EXTRA_DEFINES + ["-DNGM_HAVE_S16" if (CSRC / "k_score_s16.cu").exists() else "-DNGM_NO_S16",
                                          "-I", str(PKG.parent / "include"), "-c", str(src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

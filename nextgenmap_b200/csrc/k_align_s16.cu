@@ -68,6 +68,7 @@ cudaError_t launch_align_s16(int capacity, int mode, const AlignArgs &a, cudaStr
 	if (!launched) return cudaErrorInvalidValue;
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return e;
+	if (a.ev_mid != nullptr) cudaEventRecord(a.ev_mid, st);
 	const dim3 b2(256), g2((a.n + 255) / 256);
 	if (mode == 0)
 		backtrace_format_kernel<0><<<g2, b2, 0, st>>>(a.P, a.pairs, a.n, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, a.ptr_scratch, capacity,

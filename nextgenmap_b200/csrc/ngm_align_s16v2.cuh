@@ -19,19 +19,29 @@
 
 #include "ngm_align_s16.cuh"
 
+// Rows per unrolled loop body.  Fully unrolled (8) the main loop alone is ~36 KB of SASS and the kernel 83 KB: ncu showed `no_instruction`
+// (instruction fetch) as the top stall reason at 16 resident warps per SM.  One row per body is ~4.5 KB; the shift amounts and the
+// read-code extraction simply take the row index from a register.
+#ifndef NGM_FWD_ROW_UNROLL
+#define NGM_FWD_ROW_UNROLL 2      /* measured on B200, 10 M x 150 bp: 8 rows 12.0 ms, 2 rows 10.1 ms, 1 row 10.6 ms */
+#endif
+#define NGM_PRAGMA_(x) _Pragma(#x)
+#define NGM_UNROLL_N(n) NGM_PRAGMA_(unroll n)
+
 namespace ngm {
 
 // One DP row for both halves.  PTR: accumulate + return the pointer words of the row.
 template <int W, int LO, int MODE, bool PTR>
 __device__ __forceinline__ void fwd2_row(uint32_t (&line)[W + 1], const uint32_t (&wa)[BandGeom<W>::kWin], const uint32_t (&wb)[BandGeom<W>::kWin],
-		const int t, const uint2 ta, const uint2 tb, const uint32_t gr2, const uint32_t gf2, const uint32_t SENT2, const int corridor,
-		const uint32_t c_four, const uint32_t c_neg1, uint32_t (&pw)[TagGeom<W>::kWords]) {
+		const int t, const uint2 ta, const uint2 tb, const uint32_t gr2, const uint32_t gf2, const uint32_t SENT2,
+		const uint32_t (&keepm)[W - LO + 1], const uint32_t (&fillm)[W - LO + 1], const uint32_t c_four, const uint32_t c_neg1,
+		uint32_t (&pw)[TagGeom<W>::kWords]) {
 	using G = BandGeom<W>;
 	uint32_t ala[G::kAligned], alb[G::kAligned];
 #pragma unroll
 	for (int k = 0; k < G::kAligned; ++k) {
-		ala[k] = t == 0 ? wa[k] : __funnelshift_r(wa[k], wa[k + 1], 4 * t);
-		alb[k] = t == 0 ? wb[k] : __funnelshift_r(wb[k], wb[k + 1], 4 * t);
+		ala[k] = __funnelshift_r(wa[k], wa[k + 1], 4 * t);          // t is a run-time value: the row loop is NOT fully unrolled (see NGM_FWD_ROW_UNROLL)
+		alb[k] = __funnelshift_r(wb[k], wb[k + 1], 4 * t);
 	}
 	uint32_t left = SENT2;
 	if (PTR) {
@@ -49,7 +59,8 @@ __device__ __forceinline__ void fwd2_row(uint32_t (&line)[W + 1], const uint32_t
 			const uint32_t d = __vadd2(line[j], s2);
 			const uint32_t u = __viaddmax_s16x2(line[j + 1], gr2, d);
 			uint32_t h = MODE == 0 ? __viaddmax_s16x2_relu(left, gf2, u) : __viaddmax_s16x2(left, gf2, u);
-			if (j >= LO) h = (j < corridor) ? h : SENT2;
+			// slots at or beyond the corridor are pinned to the sentinel: one LOP3 with loop-invariant masks instead of compare + select
+			if (j >= LO) h = (h & keepm[j - LO]) | (MODE == 0 ? 0u : fillm[j - LO]);
 			const uint32_t clean = h & 0xFFFCFFFCu;
 			if (PTR) {
 				const uint32_t tag = imad_u32(clean, c_neg1, h);          // h - clean, FMA pipe
@@ -102,6 +113,12 @@ __global__ void __launch_bounds__(128) align_s16_fwd2_kernel(const __grid_consta
 	uint32_t line[W + 1];
 #pragma unroll
 	for (int j = 0; j <= W; ++j) line[j] = (j < corridor) ? 0u : SENT2;
+	uint32_t keepm[W - LO + 1], fillm[W - LO + 1];
+#pragma unroll
+	for (int i = 0; i <= W - LO; ++i) {
+		keepm[i] = (LO + i < corridor) ? 0xFFFFFFFFu : 0u;
+		fillm[i] = (LO + i < corridor) ? 0u : SENT2;
+	}
 	uint32_t best = 0;
 	int rc_a = 0, rc_b = 0;
 	// checkpoint bookkeeping (local mode): per half the buffer, block and row count of the block of its last improvement
@@ -137,11 +154,11 @@ __global__ void __launch_bounds__(128) align_s16_fwd2_kernel(const __grid_consta
 #pragma unroll
 			for (int j = 0; j < W; ++j) *chk_at(cur_buf, j) = line[j];
 		}
-#pragma unroll
+NGM_UNROLL_N(NGM_FWD_ROW_UNROLL)
 		for (int t = 0; t < 8; ++t) {
 			const int rca = (rda >> (4 * t)) & 7, rcb = (rdb >> (4 * t)) & 7;
 			uint32_t pw[T::kWords];
-			fwd2_row<W, LO, MODE, true>(line, wa, wb, t, luta[rca], lutb[rcb], gr2, gf2, SENT2, corridor, c_four, c_neg1, pw);
+			fwd2_row<W, LO, MODE, true>(line, wa, wb, t, luta[rca], lutb[rcb], gr2, gf2, SENT2, keepm, fillm, c_four, c_neg1, pw);
 #pragma unroll
 			for (int k = 0; k < T::kWords; ++k) prow[(size_t) k * tstride] = pw[k];
 			prow += row_stride;
@@ -188,11 +205,11 @@ __global__ void __launch_bounds__(128) align_s16_fwd2_kernel(const __grid_consta
 		const uint32_t rdb = __funnelshift_l(pb, __ldg(cb.rp + blk_b), 4 * cb.sub);
 		bool found_a = false, found_b = false;
 		int brow_a = 0, brow_b = 0, rr_a = rc0_a, rr_b = rc0_b;
-#pragma unroll
+NGM_UNROLL_N(NGM_FWD_ROW_UNROLL)
 		for (int t = 0; t < 8; ++t) {
 			const int rca = (rda >> (4 * t)) & 7, rcb = (rdb >> (4 * t)) & 7;
 			uint32_t pw[T::kWords];
-			fwd2_row<W, LO, MODE, false>(line, wa, wb, t, luta[rca], lutb[rcb], gr2, gf2, SENT2, corridor, c_four, c_neg1, pw);
+			fwd2_row<W, LO, MODE, false>(line, wa, wb, t, luta[rca], lutb[rcb], gr2, gf2, SENT2, keepm, fillm, c_four, c_neg1, pw);
 			const uint32_t mx = band_max<W>(line, 0u);
 			const bool hit_a = !found_a && (int) (short) (mx & 0xFFFFu) == ma;
 			const bool hit_b = !found_b && (int) (short) (mx >> 16) == mb;

@@ -274,6 +274,13 @@ int run_align(ngm_b200_ctx *c, int mode, const PairDesc *pairs, int n, const uin
 			if (rc2) return rc2;
 			a.known = c->d_known.as<float>();
 		}
+		const bool prof = c->profile && c->align_s16[mode] && c->pev_used + 3 <= 3 * 64;
+		if (prof) {
+			for (int k = 0; k < 3; ++k)
+				if (c->pev[c->pev_used + k] == nullptr) CU(cudaEventCreate(&c->pev[c->pev_used + k]));
+			CU(cudaEventRecord(c->pev[c->pev_used], st));
+			a.ev_mid = c->pev[c->pev_used + 1];
+		}
 		a.stride = stride_pad;
 		a.ops_cap = 2 * c->dp.qml + c->dp.corridor + 2;
 		a.recs = recs + s;
@@ -290,6 +297,10 @@ int run_align(ngm_b200_ctx *c, int mode, const PairDesc *pairs, int n, const uin
 		e = launch_align_i32(c->capacity, mode, a, st);
 		c->launches += 1;
 		if (e != cudaSuccess) return fail(NGM_B200_ECUDA, "align kernel launch: %s", cudaGetErrorString(e));
+		if (prof) {
+			CU(cudaEventRecord(c->pev[c->pev_used + 2], st));
+			c->pev_used += 3;
+		}
 	}
 	return NGM_B200_OK;
 }
@@ -410,7 +421,9 @@ ngm_b200_ctx *ngm_b200_create(const ngm_b200_params *params) {
 	// words per packed strict window: the kernels read up to rows_cap + capacity + 16 nibbles
 	c->win_words = (dp.rows_cap + c->capacity + 16 + 7) / 8 + 2;
 	const size_t per_aln = (size_t) dp.rows_cap * ptr_words_for(c->capacity) * 4 + (2 * (size_t) dp.qml + dp.corridor + 2) * 2;
-	c->align_chunk = (int) std::max<size_t>(4096, std::min<size_t>(262144, (3ull << 30) / per_aln)) / 128 * 128;
+	// alignments per launch set: the pointer matrix of a launch set is scratch (2.5 KB per 150 bp alignment); 1 M alignments per set keep the
+	// grid at ~7 waves of 4 blocks per SM (a 262144-alignment set is 1.7 waves: the second wave runs 73 % full)
+	c->align_chunk = (int) std::max<size_t>(4096, std::min<size_t>(1 << 20, (6ull << 30) / per_aln)) / 128 * 128;
 	if (cudaSetDevice(c->device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
 		fail(NGM_B200_ECUDA, "cannot initialise device %d: %s", c->device, cudaGetErrorString(cudaGetLastError()));
 		delete c;
@@ -422,6 +435,8 @@ ngm_b200_ctx *ngm_b200_create(const ngm_b200_params *params) {
 void ngm_b200_destroy(ngm_b200_ctx *c) {
 	if (c == nullptr) return;
 	cudaSetDevice(c->device);
+	for (cudaEvent_t &e : c->pev)
+		if (e) cudaEventDestroy(e);
 	if (c->batch) batch_release(c->batch);                 // the lanes first: they borrow this context's buffers
 	c->batch = nullptr;
 	if (c->stream) {
@@ -438,6 +453,70 @@ void ngm_b200_destroy(ngm_b200_ctx *c) {
 	if (c->pe) pe_release(c->pe);
 	if (c->map) map_release(c->map);
 	delete c;
+}
+
+int ngm_b200_alu_peak(ngm_b200_ctx *c, double *viaddmnmx_per_s, double *imad_per_s, double *mixed_per_s) {
+	if (c == nullptr) return fail(NGM_B200_EINVAL, "ctx == NULL");
+	CU(cudaSetDevice(c->device));
+	int sms = 0;
+	CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+	const int blocks = sms * 8, iters = 4096;
+	DevBuf out;
+	CU(out.ensure((size_t) blocks * 256 * 4));
+	cudaEvent_t e0, e1;
+	CU(cudaEventCreate(&e0));
+	CU(cudaEventCreate(&e1));
+	double res[3] = {0, 0, 0};
+	for (int kind = 0; kind < 3; ++kind) {
+		float best = 1e30f;
+		for (int rep = 0; rep < 4; ++rep) {                    // the first repetition warms up
+			CU(cudaEventRecord(e0, c->stream));
+			if (kind == 0) alu_peak_kernel<0><<<blocks, 256, 0, c->stream>>>(out.as<uint32_t>(), iters, c->dp.c_neg1 << 2, c->dp.c_four | 1u);
+			else if (kind == 1) alu_peak_kernel<1><<<blocks, 256, 0, c->stream>>>(out.as<uint32_t>(), iters, c->dp.c_neg1 << 2, c->dp.c_four | 1u);
+			else alu_peak_kernel<2><<<blocks, 256, 0, c->stream>>>(out.as<uint32_t>(), iters, c->dp.c_neg1 << 2, c->dp.c_four | 1u);
+			CU(cudaEventRecord(e1, c->stream));
+			CU(cudaEventSynchronize(e1));
+			float ms = 0;
+			CU(cudaEventElapsedTime(&ms, e0, e1));
+			if (rep) best = std::min(best, ms);
+		}
+		c->launches += 4;
+		const double instr = (double) blocks * 256.0 * iters * 64.0 * (kind == 2 ? 2.0 : 1.0);      // thread-level instructions of the measured kind(s)
+		res[kind] = instr / (best * 1e-3);
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	out.release();
+	if (viaddmnmx_per_s) *viaddmnmx_per_s = res[0];
+	if (imad_per_s) *imad_per_s = res[1];
+	if (mixed_per_s) *mixed_per_s = res[2];
+	return NGM_B200_OK;
+}
+
+int ngm_b200_profile(ngm_b200_ctx *c, int enable) {
+	if (c == nullptr) return fail(NGM_B200_EINVAL, "ctx == NULL");
+	c->profile = enable ? 1 : 0;
+	c->pev_used = 0;
+	return NGM_B200_OK;
+}
+
+int ngm_b200_profile_read(ngm_b200_ctx *c, float *forward_ms, float *backtrace_ms) {
+	if (c == nullptr) return fail(NGM_B200_EINVAL, "ctx == NULL");
+	CU(cudaSetDevice(c->device));
+	float f = 0, b = 0;
+	for (int i = 0; i + 3 <= c->pev_used; i += 3) {
+		CU(cudaEventSynchronize(c->pev[i + 2]));
+		float x = 0, y = 0;
+		CU(cudaEventElapsedTime(&x, c->pev[i], c->pev[i + 1]));
+		CU(cudaEventElapsedTime(&y, c->pev[i + 1], c->pev[i + 2]));
+		f += x;
+		b += y;
+	}
+	const int sets = c->pev_used / 3;
+	c->pev_used = 0;
+	if (forward_ms) *forward_ms = f;
+	if (backtrace_ms) *backtrace_ms = b;
+	return sets;
 }
 
 int ngm_b200_score_batch_size(const ngm_b200_ctx *c) { return c ? c->score_batch : 0; }
@@ -641,7 +720,7 @@ static int pack_reads_device_impl(ngm_b200_ctx *c, const uint8_t *d_ascii, int n
 				c->d_rrev.as<uint32_t>());
 		c->launches += 3;
 	} else {
-		pack_reads_fused_kernel<<<(n_reads + kPackRowsPerBlock - 1) / kPackRowsPerBlock, 32 * kPackRowsPerBlock, (size_t) kPackRowsPerBlock * RW * 4, st>>>(
+		pack_reads_fused_kernel<<<(n_reads + kPackRowsPerBlock - 1) / kPackRowsPerBlock, 16 * kPackRowsPerBlock, (size_t) kPackRowsPerBlock * RW * 4, st>>>(
 				d_ascii, n_reads, width, stride, c->d_rfwd.as<uint32_t>(), c->d_rrev.as<uint32_t>(), c->d_rrlen.as<uint16_t>(), RW);
 		c->launches += 1;
 	}

@@ -40,38 +40,42 @@ __device__ __forceinline__ uint32_t spread2to4(uint32_t x16) {      // 8 two-bit
 
 __device__ __forceinline__ uint32_t nib_keep(int valid) { return valid >= 8 ? 0xFFFFFFFFu : (valid <= 0 ? 0u : ((1u << (4 * valid)) - 1u)); }
 
-// forward code word w (bases 8w .. 8w+7) of a PACKED2 row; positions >= len read as NUL
-__device__ __forceinline__ uint32_t packed2_word(const uint32_t *__restrict__ in, int in_words, int len, int w) {
-	if (w < 0 || 8 * w >= len) return kNulWord;
-	const int iw = w >> 1;
-	const uint32_t x = iw < in_words ? ((__ldg(in + iw) >> (16 * (w & 1))) & 0xFFFFu) : 0u;
-	const uint32_t keep = nib_keep(len - 8 * w);
-	return (spread2to4(x) & keep) | (kNulWord & ~keep);
-}
+// PACKED2 rows -> forward words, reverse-complement words (MappedRead::computeReverseSeq, MappedRead.cpp:36-67) and lengths in one
+// pass.  16 threads per row; a thread expands one 32-bit input word (16 bases) into two forward code words and assembles the two
+// reverse words of the same index from a 64-bit window of the (L1-resident) input row.  HBM-bound: 42 B in, 2 x 84 B out per 150 bp read.
+constexpr int kExpandRowsPerBlock = 16;
 
-// PACKED2 rows -> forward words, reverse-complement words (MappedRead::computeReverseSeq, MappedRead.cpp:36-67) and lengths.
-// One thread per output word; the 40-byte input row stays in L1 for the 21 threads that share it.
-__global__ void __launch_bounds__(256) expand_packed2_kernel(const uint32_t *__restrict__ in, int rows, int in_words, const uint16_t *__restrict__ len_in,
-		int max_len, uint32_t *__restrict__ fwd, uint32_t *__restrict__ rev, uint16_t *__restrict__ rlen, int words) {
-	const long long gid = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-	if (gid >= (long long) rows * words) return;
-	const int row = (int) (gid / words), w = (int) (gid - (long long) row * words);
+__global__ void __launch_bounds__(16 * kExpandRowsPerBlock) expand_packed2_kernel(const uint32_t *__restrict__ in, int rows, int in_words,
+		const uint16_t *__restrict__ len_in, int max_len, uint32_t *__restrict__ fwd, uint32_t *__restrict__ rev, uint16_t *__restrict__ rlen, int words) {
+	const int x = threadIdx.x & 15, row = blockIdx.x * kExpandRowsPerBlock + (threadIdx.x >> 4);
+	if (row >= rows) return;
 	const int len = min((int) len_in[row], max_len);
 	const uint32_t *r = in + (size_t) row * in_words;
-	fwd[gid] = packed2_word(r, in_words, len, w);
-	uint32_t out = kNulWord;
-	const int hi = len - 1 - 8 * w;                                // source index of output nibble 0; nibble k reads hi - k
-	if (hi >= 0) {
-		const int wi = hi >> 3;
-		const uint32_t a = packed2_word(r, in_words, len, wi), b = packed2_word(r, in_words, len, wi - 1);
-		const uint32_t x = __funnelshift_rc(b, a, 4 * ((hi & 7) + 1));
-		uint32_t y = __byte_perm(x, 0, 0x0123);
-		y = ((y >> 4) & 0x0F0F0F0Fu) | ((y & 0x0F0F0F0Fu) << 4);
-		const uint32_t m = (~y >> 2) & 0x11111111u;
-		out = y ^ (m * 3u);
+	auto word_at = [&](int q) -> uint32_t { return (q >= 0 && q < in_words) ? __ldg(r + q) : 0u; };
+	for (int w2 = x; 2 * w2 < words; w2 += 16) {
+		const uint32_t xin = word_at(w2);
+#pragma unroll
+		for (int h = 0; h < 2; ++h) {
+			const int w = 2 * w2 + h;
+			if (w >= words) break;
+			const uint32_t keep = nib_keep(len - 8 * w);
+			fwd[(size_t) row * words + w] = (spread2to4((xin >> (16 * h)) & 0xFFFFu) & keep) | (kNulWord & ~keep);
+			uint32_t out = kNulWord;
+			const int hi = len - 1 - 8 * w;                        // reverse word w: nibble k = complement of base hi - k
+			if (hi >= 0) {
+				const int lo = hi - 7;                                // may be negative: those nibbles are masked below
+				const int q = lo >> 4;                                // floor division (arithmetic shift)
+				const unsigned long long win = (unsigned long long) word_at(q) | ((unsigned long long) word_at(q + 1) << 32);
+				const uint32_t v = (uint32_t) (win >> (2 * (lo & 15))) & 0xFFFFu;      // bases lo .. hi
+				uint32_t y = __byte_perm(spread2to4(v), 0, 0x0123);
+				y = ((y >> 4) & 0x0F0F0F0Fu) | ((y & 0x0F0F0F0Fu) << 4);               // nibble k = base hi - k
+				const uint32_t kp = nib_keep(hi + 1);
+				out = ((y ^ 0x33333333u) & kp) | (kNulWord & ~kp);                     // A<->T, C<->G: code ^ 3
+			}
+			rev[(size_t) row * words + w] = out;
+		}
 	}
-	rev[gid] = out;
-	if (w == 0) rlen[row] = (uint16_t) len;
+	if (x == 0) rlen[row] = (uint16_t) len;
 }
 
 // bases that are not A/C/G/T: oclDefines.cl:64-80 classes (N 5, everything else 4; a NUL inside the row ends nothing here: lengths are explicit)
@@ -399,8 +403,7 @@ int install_reads(ngm_b200_ctx *c, int format, const void *d_reads, int n, int s
 	CU(c->d_rfwd.ensure((size_t) n * RW * 4));
 	CU(c->d_rrev.ensure((size_t) n * RW * 4));
 	CU(c->d_rrlen.ensure((size_t) n * 2));
-	const long long tot = (long long) n * RW;
-	expand_packed2_kernel<<<(unsigned) ((tot + 255) / 256), 256, 0, st>>>(static_cast<const uint32_t *>(d_reads), n, stride / 4, d_len, c->dp.qml,
+	expand_packed2_kernel<<<(n + kExpandRowsPerBlock - 1) / kExpandRowsPerBlock, 16 * kExpandRowsPerBlock, 0, st>>>(static_cast<const uint32_t *>(d_reads), n, stride / 4, d_len, c->dp.qml,
 			c->d_rfwd.as<uint32_t>(), c->d_rrev.as<uint32_t>(), c->d_rrlen.as<uint16_t>(), RW);
 	c->launches += 1;
 	if (n_exc) {

@@ -122,6 +122,9 @@ struct ngm_b200_ctx {
 	ngm::PeState *pe = nullptr;
 	ngm::MapState *map = nullptr;
 	ngm::BatchState *batch = nullptr;
+	int profile = 0;           // ngm_b200_profile: time the forward / backtrace kernels of the align launch sets with events
+	cudaEvent_t pev[3 * 64] = {};
+	int pev_used = 0;
 	int se_strata = 0;         // "strata" for single-end top-1 selection (ScoreBuffer.cpp:259)
 	uint64_t epoch = 0;        // bumped whenever the reference / index / selection parameters change: lanes re-sync their aliases
 	ngm_b200_ctx *root = nullptr;      // set in a lane: the context whose resident data it borrows

@@ -17,6 +17,13 @@
 #include "ngm_common.cuh"
 #include "ngm_dp_i32.cuh"
 
+// rows per unrolled loop body of the score kernel (8 = the whole read word; smaller bodies relieve the instruction cache)
+#ifndef NGM_SCORE_ROW_UNROLL
+#define NGM_SCORE_ROW_UNROLL 8
+#endif
+#define NGM_SPRAGMA_(x) _Pragma(#x)
+#define NGM_SUNROLL_N(n) NGM_SPRAGMA_(unroll n)
+
 namespace ngm {
 
 // byte I of a (low half) and byte I of b (high half), each sign-extended to 16 bits
@@ -72,15 +79,15 @@ __global__ void __launch_bounds__(128) score_s16_kernel(const __grid_constant__ 
 		prev_a = cur_a;
 		prev_b = cur_b;
 		const uint32_t next_a = __ldg(ca.wp + qw + G::kWin), next_b = __ldg(cb.wp + qw + G::kWin);
-#pragma unroll
+NGM_SUNROLL_N(NGM_SCORE_ROW_UNROLL)
 		for (int t = 0; t < 8; ++t) {
 			const uint2 ta = luta[(rda >> (4 * t)) & 7];
 			const uint2 tb = lutb[(rdb >> (4 * t)) & 7];
 			uint32_t ala[G::kAligned], alb[G::kAligned];
 #pragma unroll
 			for (int k = 0; k < G::kAligned; ++k) {
-				ala[k] = t == 0 ? wa[k] : __funnelshift_r(wa[k], wa[k + 1], 4 * t);
-				alb[k] = t == 0 ? wb[k] : __funnelshift_r(wb[k], wb[k + 1], 4 * t);
+				ala[k] = (NGM_SCORE_ROW_UNROLL == 8 && t == 0) ? wa[k] : __funnelshift_r(wa[k], wa[k + 1], 4 * t);
+				alb[k] = (NGM_SCORE_ROW_UNROLL == 8 && t == 0) ? wb[k] : __funnelshift_r(wb[k], wb[k + 1], 4 * t);
 			}
 			uint32_t left = SENT2;
 #pragma unroll

@@ -51,6 +51,7 @@ struct AlignArgs {
 	uint16_t *ops_scratch;
 	int4 *best_scratch;          // per alignment {best_read, best_ref, best_score, read_count} (s16 path)
 	const float *known;          // local maxima of the pairs (score kernel output) or nullptr
+	cudaEvent_t ev_mid = nullptr;   // optional: recorded between the forward and the backtrace kernel (ngm_b200_profile)
 	float *out_best = nullptr;   // optional, per alignment: the forward pass's maximum = what BatchScore returns for the pair in this mode
 	int stride, ops_cap;
 	ngm_b200_align_rec *recs;

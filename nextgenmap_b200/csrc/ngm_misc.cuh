@@ -142,44 +142,54 @@ __device__ __forceinline__ uint32_t revcomp_word(const uint32_t *f, int hi) {
 	return y ^ (m * 3u);
 }
 
-constexpr int kPackRowsPerBlock = 8;
+// four ASCII bytes -> four code nibbles (bits 0..15).  Fast path for plain A/C/G/T (either case): code = ((b >> 1) ^ (b >> 2)) & 3
+// for all four bytes at once, verified by mapping the codes back to letters with one PRMT; anything else takes the per-byte rule.
+__device__ __forceinline__ uint32_t ascii4_codes(uint32_t b) {
+	const uint32_t c = ((b >> 1) ^ (b >> 2)) & 0x03030303u;
+	uint32_t t = (c | (c >> 4)) & 0x00FF00FFu;
+	t = (t | (t >> 8)) & 0xFFFFu;
+	if ((b & 0xDFDFDFDFu) == prmt(0x54474341u, 0u, t)) return t;             // "ACGT" indexed by code
+	return ascii_code(b & 0xFFu) | ascii_code((b >> 8) & 0xFFu) << 4 | ascii_code((b >> 16) & 0xFFu) << 8 | ascii_code(b >> 24) << 12;
+}
 
-__global__ void __launch_bounds__(32 * kPackRowsPerBlock) pack_reads_fused_kernel(const uint8_t *__restrict__ src, int rows, int width, int src_stride,
+constexpr int kPackRowsPerBlock = 16;      // 16 threads per row, each packs 16 bytes into two code words
+
+__global__ void __launch_bounds__(16 * kPackRowsPerBlock) pack_reads_fused_kernel(const uint8_t *__restrict__ src, int rows, int width, int src_stride,
 		uint32_t *__restrict__ fwd, uint32_t *__restrict__ rev, uint16_t *__restrict__ rlen, int words) {
-	__shared__ uint8_t s_code[256];
 	extern __shared__ uint32_t s_rows[];                              // [kPackRowsPerBlock][words]
-	s_code[threadIdx.x] = (uint8_t) ascii_code(threadIdx.x);
-	__syncthreads();
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int row = blockIdx.x * kPackRowsPerBlock + warp;
-	if (row >= rows) return;
-	uint32_t *buf = s_rows + warp * words;
-	const uint8_t *s = src + (size_t) row * src_stride;
-	const bool wide = ((src_stride & 7) == 0) && ((reinterpret_cast<uintptr_t>(src) & 7) == 0);
+	const int x = threadIdx.x & 15, y = threadIdx.x >> 4;
+	const int row = blockIdx.x * kPackRowsPerBlock + y;
+	const bool live = row < rows;
+	uint32_t *buf = s_rows + y * words;
+	const uint8_t *s = src + (size_t) (live ? row : 0) * src_stride;
+	const bool wide = ((src_stride & 15) == 0 || (src_stride & 7) == 0) && ((reinterpret_cast<uintptr_t>(src) & 7) == 0);
 	int last = 0;
-	for (int w = lane; w < words; w += 32) {
-		const int i0 = 8 * w;
-		uint32_t word;
-		if (wide && i0 + 8 <= width) {
-			const uint2 v = *reinterpret_cast<const uint2 *>(s + i0);
-			word = (uint32_t) s_code[v.x & 0xFF] | (uint32_t) s_code[(v.x >> 8) & 0xFF] << 4 | (uint32_t) s_code[(v.x >> 16) & 0xFF] << 8 |
-					(uint32_t) s_code[v.x >> 24] << 12 | (uint32_t) s_code[v.y & 0xFF] << 16 | (uint32_t) s_code[(v.y >> 8) & 0xFF] << 20 |
-					(uint32_t) s_code[(v.y >> 16) & 0xFF] << 24 | (uint32_t) s_code[v.y >> 24] << 28;
-		} else {
-			word = 0;
+	for (int w2 = x; 2 * w2 < words; w2 += 16) {                      // code words 2 w2, 2 w2 + 1 = bytes 16 w2 .. 16 w2 + 15
 #pragma unroll
-			for (int k = 0; k < 8; ++k) word |= (uint32_t) s_code[i0 + k < width ? s[i0 + k] : 0] << (4 * k);
+		for (int h = 0; h < 2; ++h) {
+			const int w = 2 * w2 + h, i0 = 8 * w;
+			if (w >= words) break;
+			uint32_t word;
+			if (live && wide && i0 + 8 <= width) {
+				const uint2 v = *reinterpret_cast<const uint2 *>(s + i0);
+				word = ascii4_codes(v.x) | ascii4_codes(v.y) << 16;
+			} else {
+				word = 0;
+#pragma unroll
+				for (int k = 0; k < 8; ++k) word |= ascii_code((live && i0 + k < width) ? s[i0 + k] : 0u) << (4 * k);
+			}
+			buf[w] = word;
+			if (live) fwd[(size_t) row * words + w] = word;
+			const uint32_t nz = word ^ kNulWord;                      // non-zero nibble <=> code != NUL
+			if (nz != 0) last = max(last, i0 + (31 - __clz(nz)) / 4 + 1);
 		}
-		buf[w] = word;
-		fwd[(size_t) row * words + w] = word;
-		const uint32_t x = word ^ kNulWord;                          // non-zero nibble <=> code != NUL
-		if (x != 0) last = max(last, i0 + (31 - __clz(x)) / 4 + 1);
 	}
 #pragma unroll
-	for (int d = 16; d > 0; d >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, d));
+	for (int d = 8; d > 0; d >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, d, 16));
 	__syncwarp();
-	if (lane == 0) rlen[row] = (uint16_t) last;
-	for (int w = lane; w < words; w += 32) {
+	if (!live) return;
+	if (x == 0) rlen[row] = (uint16_t) last;
+	for (int w = x; w < words; w += 16) {
 		const int hi = last - 1 - 8 * w;                             // source index of output nibble 0
 		rev[(size_t) row * words + w] = hi >= 0 ? revcomp_word(buf, hi) : kNulWord;
 	}
@@ -279,6 +289,32 @@ __global__ void gather_winners_kernel(int n_reads, const ngm_b200_pair *__restri
 	}
 	out[r] = p;
 	if (out_scores != nullptr) out_scores[r] = s;
+}
+
+// Issue-rate microbenchmarks behind ngm_b200_alu_peak: what the roofline of the DP kernels is measured against.
+// KIND 0: VIADDMNMX.S16x2 (integer ALU pipe, the DP recurrence's instruction); 1: IMAD (FMA pipe); 2: both interleaved 1:1.
+template <int KIND>
+__global__ void __launch_bounds__(256) alu_peak_kernel(uint32_t *__restrict__ out, int iters, uint32_t g, uint32_t m) {
+	uint32_t a[8], b[8];
+#pragma unroll
+	for (int k = 0; k < 8; ++k) {
+		a[k] = threadIdx.x * 4u + k * 64u;
+		b[k] = blockIdx.x + k;
+	}
+	for (int i = 0; i < iters; ++i) {
+#pragma unroll
+		for (int u = 0; u < 8; ++u) {
+#pragma unroll
+			for (int k = 0; k < 8; ++k) {
+				if (KIND != 1) a[k] = __viaddmax_s16x2(a[k], g, b[k]);
+				if (KIND != 0) b[k] = imad_u32(b[k], m, a[k]);
+			}
+		}
+	}
+	uint32_t r = 0;
+#pragma unroll
+	for (int k = 0; k < 8; ++k) r ^= a[k] ^ b[k];
+	out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
 // ScoreBuffer::top1SE + computeMQ (ScoreBuffer.cpp:34-40,228-277); one thread per read.

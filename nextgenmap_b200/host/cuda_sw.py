@@ -11,6 +11,7 @@ CUDA device is missing, construction raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from pathlib import Path
 from typing import List, Optional, Sequence
@@ -18,7 +19,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 PKG = Path(__file__).resolve().parents[1]
-LIB_PATH = PKG / "libngm_b200.so"
+LIB_PATH = Path(os.environ["NGM_B200_LIB"]) if os.environ.get("NGM_B200_LIB") else PKG / "libngm_b200.so"      # (A/B builds: see build.py)
 
 
 class NgmB200Error(RuntimeError):
