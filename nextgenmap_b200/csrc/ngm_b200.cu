@@ -451,7 +451,6 @@ void ngm_b200_destroy(ngm_b200_ctx *c) {
 	for (DevBuf *b : db) b->release();
 	if (c->cs) cs_release(c->cs);
 	if (c->pe) pe_release(c->pe);
-	if (c->map) map_release(c->map);
 	delete c;
 }
 

@@ -265,15 +265,17 @@ __global__ void __launch_bounds__(256) batch_add_base_kernel(int n, int *__restr
 // ---------------------------------------------------------------------------------------------------------
 struct LaneBuf {
 	DevBuf d_in_reads, d_in_len, d_in_exc, d_cb, d_desc, d_rp, d_pairs16, d_sel, d_nsel, d_scores, d_best, d_mapq, d_ntop, d_pfail, d_wp, d_wscores, d_obest,
-			d_recs, d_strings, d_cursor;
+			d_recs, d_strings, d_cursor, d_maxhit;
+	cudaEvent_t searched = nullptr;                                // ngm_b200_map_batch: candidate search of the lane's sub-batch has finished
 	cudaEvent_t done = nullptr;
 	int pending = -1;                                              // sub-batch whose strings still have to be fetched
 	void release() {
 		DevBuf *all[] = { &d_in_reads, &d_in_len, &d_in_exc, &d_cb, &d_desc, &d_rp, &d_pairs16, &d_sel, &d_nsel, &d_scores, &d_best, &d_mapq, &d_ntop, &d_pfail,
-				&d_wp, &d_wscores, &d_obest, &d_recs, &d_strings, &d_cursor };
+				&d_wp, &d_wscores, &d_obest, &d_recs, &d_strings, &d_cursor, &d_maxhit };
 		for (DevBuf *b : all) b->release();
 		if (done) cudaEventDestroy(done);
-		done = nullptr;
+		if (searched) cudaEventDestroy(searched);
+		done = searched = nullptr;
 	}
 };
 
@@ -285,6 +287,7 @@ struct BatchState {
 	LaneBuf own;                                                   // staging of ngm_b200_dev_run_batch on the root context itself
 	uint64_t synced_epoch = ~0ull;
 	HostBuf h_used;                                                // pinned: heap cursor of every sub-batch
+	HostBuf h_count;                                               // pinned: candidates found in every sub-batch (ngm_b200_map_batch)
 	cudaEvent_t pe_chain = nullptr;                                // orders the paired-end selections of consecutive sub-batches
 };
 
@@ -294,6 +297,7 @@ void batch_release(BatchState *b) {
 	b->own.release();
 	for (ngm_b200_ctx *l : b->lanes) ngm_b200_destroy(l);
 	b->h_used.release();
+	b->h_count.release();
 	if (b->pe_chain) cudaEventDestroy(b->pe_chain);
 	delete b;
 }
@@ -336,10 +340,12 @@ int batch_enqueue(ngm_b200_ctx *c, LaneBuf &L, const DevIn &in, const DevOut &ou
 	CU(L.d_obest.ensure((size_t) n * 4));
 	CU(L.d_nsel.ensure(4));
 	if (fuse) CU(L.d_sel.ensure(std::max<size_t>(np, 1) * 4));
-	if (in.paired) CU(L.d_pairs16.ensure(std::max<size_t>(np, 1) * sizeof(ngm_b200_pair)));
+	const bool own_p16 = in.paired && in.desc_format != NGM_B200_DESC_PAIR16;      // top1PE reads ngm_b200_pair records: expand 64-bit descriptors
+	if (own_p16) CU(L.d_pairs16.ensure(std::max<size_t>(np, 1) * sizeof(ngm_b200_pair)));
 	batch_set_u32_kernel<<<1, 1, 0, st>>>(nullptr, 0, L.d_nsel.as<int>());
 	const int blocks_r = (n + 255) / 256;
-	ngm_b200_pair *p16 = in.paired ? L.d_pairs16.as<ngm_b200_pair>() : nullptr;
+	ngm_b200_pair *p16 = own_p16 ? L.d_pairs16.as<ngm_b200_pair>() : nullptr;
+	const ngm_b200_pair *pe_pairs = own_p16 ? p16 : static_cast<const ngm_b200_pair *>(in.desc);
 	if (in.desc_format == NGM_B200_DESC_PAIR16)
 		batch_plan_kernel<NGM_B200_DESC_PAIR16><<<blocks_r, 256, 0, st>>>(n, in.cb, in.cb_base, in.desc, L.d_rp.as<PairDesc>(), p16, (unsigned long long) c->concat_len,
 				(unsigned long long) c->n_region_nib, c->d_rrlen.as<uint16_t>(), fuse, L.d_sel.as<int>(), L.d_nsel.as<int>());
@@ -369,7 +375,7 @@ int batch_enqueue(ngm_b200_ctx *c, LaneBuf &L, const DevIn &in, const DevOut &ou
 	}
 	if (in.paired) {
 		if (pe_wait) CU(cudaStreamWaitEvent(st, pe_wait, 0));
-		int rc = ngm_b200_dev_select_pairs(c, n, in.cb, p16, out.scores, (uint32_t) np, out.best_pair, out.mapq, out.num_top != nullptr ? out.num_top : L.d_ntop.p,
+		int rc = ngm_b200_dev_select_pairs(c, n, in.cb, pe_pairs, out.scores, (uint32_t) np, out.best_pair, out.mapq, out.num_top != nullptr ? out.num_top : L.d_ntop.p,
 				out.pair_fail, st);
 		if (rc < 0) return rc;
 		if (pe_signal) CU(cudaEventRecord(pe_signal, st));
@@ -428,6 +434,7 @@ int sync_lanes(ngm_b200_ctx *c) {
 		B->lanes.push_back(l);
 		B->bufs.emplace_back();
 		CU(cudaEventCreateWithFlags(&B->bufs.back().done, cudaEventDisableTiming));
+		CU(cudaEventCreateWithFlags(&B->bufs.back().searched, cudaEventDisableTiming));
 		B->synced_epoch = ~0ull;
 	}
 	if (B->pe_chain == nullptr) CU(cudaEventCreateWithFlags(&B->pe_chain, cudaEventDisableTiming));
@@ -760,6 +767,162 @@ int ngm_b200_run_batch(ngm_b200_ctx *c, const ngm_b200_batch_in *in, ngm_b200_ba
 		return fail(NGM_B200_ERANGE, "string heap too small: a sub-batch needed %zu bytes, its slot holds %zu", worst_used, slot);
 	}
 	return n;
+}
+
+// CS::RunBatch -> ScoreBuffer::DoRun -> AlignmentBuffer::DoRun for a whole batch, host buffers in and out (CS.cpp:340-436,
+// ScoreBuffer.cpp:80-277,365-502, AlignmentBuffer.cpp:64-147).  Sub-batches rotate over the lanes in two phases: A = upload + candidate
+// search (the number of candidates comes back to the host), B = score + select + align + download at the sub-batch's offset in the
+// caller's candidate arrays.  A(k) is enqueued before the host waits for the count of k - 1, so the upload of k overlaps the search of k - 1.
+int ngm_b200_map_batch(ngm_b200_ctx *c, const char *reads, int n_reads, int stride, int mode, int paired, ngm_b200_map_result *res) {
+	if (c == nullptr || reads == nullptr || res == nullptr) return fail(NGM_B200_EINVAL, "NULL argument");
+	if (n_reads <= 0) return 0;
+	if (res->cand_begin == nullptr || res->best_pair == nullptr || res->mapq == nullptr || res->num_top == nullptr || res->max_hit == nullptr ||
+			res->recs == nullptr || (res->capacity && (res->pairs == nullptr || res->scores == nullptr)) || (res->str_capacity && res->strings == nullptr) ||
+			(paired && res->pair_fail == nullptr))
+		return fail(NGM_B200_EINVAL, "NULL result array");
+	if (paired && (n_reads & 1)) return fail(NGM_B200_EINVAL, "paired batches hold the mates in rows 2f and 2f + 1: %d rows", n_reads);
+	if (res->capacity > 0x7FFFFFFFull || res->str_capacity > 0xFFFFFFFFull) return fail(NGM_B200_EINVAL, "capacity beyond 32 bits");
+	if (c->cs == nullptr) return fail(NGM_B200_ESTATE, "cs_build_index / cs_load_index must precede ngm_b200_map_batch");
+	const int m0 = mode_of(mode);
+	if (m0 < 0) return fail(NGM_B200_EINVAL, "unsupported alignment mode %d", mode & 0xFF);
+	CU(cudaSetDevice(c->device));
+	int rc = sync_lanes(c);
+	if (rc) return rc;
+	BatchState *B = c->batch;
+	const int n = n_reads, SB = B->sub_batch;
+	const int n_sub = (n + SB - 1) / SB;
+	const int n_lanes = std::min((int) B->lanes.size(), std::max(1, n_sub));
+	const size_t slot = (res->str_capacity / (size_t) n_sub) & ~(size_t) 15;
+	const size_t cap = res->capacity;
+	const uint32_t lane_cap = (uint32_t) std::max<size_t>(cap, 1);
+	CU(B->h_used.ensure((size_t) n_sub * 4));
+	CU(B->h_count.ensure((size_t) n_sub * 4));
+	uint32_t *h_used = B->h_used.as<uint32_t>();
+	int *h_count = B->h_count.as<int>();
+	int64_t pe_sum = 0, pe_count = 0;
+	if (paired && (rc = ngm_b200_pe_insert_stats(c, &pe_sum, &pe_count)) < 0) return rc;
+	size_t total = 0, worst_used = 0, total_used = 0;
+	bool cand_overflow = false, str_overflow = false;
+	int err = NGM_B200_OK;
+	res->n_candidates = 0;
+	res->str_used = 0;
+	auto finish = [&](int li) -> int {
+		LaneBuf &L = B->bufs[li];
+		if (L.pending < 0) return NGM_B200_OK;
+		const int k = L.pending;
+		L.pending = -1;
+		CU(cudaEventSynchronize(L.done));
+		const size_t base = slot * (size_t) k, used = (size_t) h_used[k] - base;
+		worst_used = std::max(worst_used, used);
+		total_used += used;
+		if (used > slot) {
+			str_overflow = true;
+			return NGM_B200_OK;
+		}
+		if (used) CU(cudaMemcpyAsync(res->strings + base, L.d_strings.p, used, cudaMemcpyDeviceToHost, B->lanes[li]->stream));
+		return NGM_B200_OK;
+	};
+	auto phase_a = [&](int k) -> int {
+		const int li = k % n_lanes;
+		ngm_b200_ctx *l = B->lanes[li];
+		LaneBuf &L = B->bufs[li];
+		cudaStream_t st = l->stream;
+		const int r0 = k * SB, m = std::min(SB, n - r0);
+		CU(L.d_in_reads.ensure((size_t) m * stride));
+		CU(L.d_cb.ensure(((size_t) m + 1) * 4));
+		CU(L.d_desc.ensure((size_t) lane_cap * sizeof(ngm_b200_pair)));
+		CU(L.d_maxhit.ensure((size_t) m * 4));
+		CU(cudaMemcpyAsync(L.d_in_reads.p, reads + (size_t) r0 * stride, (size_t) m * stride, cudaMemcpyHostToDevice, st));
+		int rc2 = pack_reads_device(l, L.d_in_reads.as<uint8_t>(), m, stride, st);
+		if (rc2) return rc2;
+		l->reads_stride = stride;
+		rc2 = ngm_b200_dev_cs_search(l, L.d_in_reads.p, m, stride, 0, L.d_cb.p, L.d_desc.p, nullptr, lane_cap, L.d_maxhit.p, st);
+		if (rc2 < 0) return rc2;
+		CU(cudaMemcpyAsync(h_count + k, L.d_cb.as<int>() + m, 4, cudaMemcpyDeviceToHost, st));
+		CU(cudaEventRecord(L.searched, st));
+		return NGM_B200_OK;
+	};
+	auto phase_b = [&](int k) -> int {
+		const int li = k % n_lanes;
+		ngm_b200_ctx *l = B->lanes[li];
+		LaneBuf &L = B->bufs[li];
+		cudaStream_t st = l->stream;
+		const int r0 = k * SB, m = std::min(SB, n - r0);
+		CU(cudaEventSynchronize(L.searched));
+		const size_t mp = (size_t) h_count[k], p0 = total;
+		total += mp;
+		if (mp > lane_cap || total > cap) {
+			cand_overflow = true;
+			return NGM_B200_OK;
+		}
+		if (cand_overflow) return NGM_B200_OK;
+		CU(L.d_scores.ensure(std::max<size_t>(mp, 1) * 4));
+		CU(L.d_best.ensure((size_t) m * 4));
+		CU(L.d_mapq.ensure((size_t) m * 4));
+		CU(L.d_ntop.ensure((size_t) m * 4));
+		CU(L.d_pfail.ensure((size_t) m * 4));
+		CU(L.d_recs.ensure((size_t) m * sizeof(ngm_b200_align_rec)));
+		CU(L.d_strings.ensure(std::max<size_t>(slot, 16)));
+		CU(L.d_cursor.ensure(4));
+		const uint32_t base = (uint32_t) (slot * (size_t) k);
+		batch_set_u32_kernel<<<1, 1, 0, st>>>(L.d_cursor.as<uint32_t>(), base, nullptr);
+		DevIn di = { m, mode, paired, NGM_B200_DESC_PAIR16, L.d_cb.as<int>(), 0, L.d_desc.p, (int) mp };
+		DevOut dn = { L.d_scores.as<float>(), L.d_best.as<int>(), L.d_mapq.as<int>(), L.d_ntop.as<int>(), L.d_pfail.as<int>(), L.d_recs.as<ngm_b200_align_rec>(),
+				L.d_strings.as<char>() - base, (uint32_t) (base + slot), L.d_cursor.as<uint32_t>() };
+		int rc2 = batch_enqueue(l, L, di, dn, c->se_strata, st, (paired && k > 0) ? B->pe_chain : nullptr, paired ? B->pe_chain : nullptr);
+		if (rc2) return rc2;
+		if (p0) {
+			batch_add_base_kernel<<<(m + 255) / 256, 256, 0, st>>>(m, L.d_best.as<int>(), (int) p0);
+			batch_rebase_kernel<<<(m + 1 + 255) / 256, 256, 0, st>>>(m + 1, L.d_cb.as<int>(), -(int) p0);
+		}
+		l->launches += 3;
+		CU(cudaMemcpyAsync(res->cand_begin + r0, L.d_cb.p, (size_t) m * 4, cudaMemcpyDeviceToHost, st));
+		if (mp) {
+			CU(cudaMemcpyAsync(res->pairs + p0, L.d_desc.p, mp * sizeof(ngm_b200_pair), cudaMemcpyDeviceToHost, st));
+			CU(cudaMemcpyAsync(res->scores + p0, L.d_scores.p, mp * 4, cudaMemcpyDeviceToHost, st));
+		}
+		CU(cudaMemcpyAsync(res->best_pair + r0, L.d_best.p, (size_t) m * 4, cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpyAsync(res->mapq + r0, L.d_mapq.p, (size_t) m * 4, cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpyAsync(res->num_top + r0, L.d_ntop.p, (size_t) m * 4, cudaMemcpyDeviceToHost, st));
+		if (paired) CU(cudaMemcpyAsync(res->pair_fail + r0, L.d_pfail.p, (size_t) m * 4, cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpyAsync(res->max_hit + r0, L.d_maxhit.p, (size_t) m * 4, cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpyAsync(res->recs + r0, L.d_recs.p, (size_t) m * sizeof(ngm_b200_align_rec), cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpyAsync(h_used + k, L.d_cursor.p, 4, cudaMemcpyDeviceToHost, st));
+		CU(cudaEventRecord(L.done, st));
+		L.pending = k;
+		return NGM_B200_OK;
+	};
+	for (int k = 0; k <= n_sub && err == NGM_B200_OK; ++k) {
+		if (n_lanes == 1 && k >= 1) err = phase_b(k - 1);             // one lane: its previous sub-batch must be complete before the lane is reused
+		if (err == NGM_B200_OK && k < n_sub) {
+			err = finish(k % n_lanes);
+			if (err == NGM_B200_OK) err = phase_a(k);
+		}
+		if (err == NGM_B200_OK && n_lanes > 1 && k >= 1) err = phase_b(k - 1);
+	}
+	for (int li = 0; li < n_lanes; ++li) {
+		const int rc2 = finish(li);
+		if (err == NGM_B200_OK) err = rc2;
+	}
+	for (int li = 0; li < n_lanes; ++li) {
+		const cudaError_t e = cudaStreamSynchronize(B->lanes[li]->stream);
+		if (e != cudaSuccess && err == NGM_B200_OK) err = fail(NGM_B200_ECUDA, "lane %d: %s", li, cudaGetErrorString(e));
+	}
+	res->n_candidates = total;
+	if (err == NGM_B200_OK && cand_overflow) err = fail(NGM_B200_ERANGE, "candidate arrays too small: %zu entries needed", total);
+	if (err == NGM_B200_OK) {
+		res->cand_begin[n] = (int32_t) total;
+		res->str_used = total_used;
+		if (str_overflow) {
+			res->str_used = (worst_used + 64) * (size_t) n_sub;
+			err = fail(NGM_B200_ERANGE, "string heap too small: a sub-batch needed %zu bytes, its slot holds %zu", worst_used, slot);
+		}
+	}
+	if (err != NGM_B200_OK) {
+		if (paired) ngm_b200_pe_set_insert_stats(c, pe_sum, pe_count);      // a batch that has to be repeated starts from the same insert-size sums
+		return err;
+	}
+	return n_reads;
 }
 
 }  // extern "C"

@@ -82,8 +82,6 @@ struct CsState;                                 // candidate search: index + scr
 void cs_release(CsState *cs);
 struct PeState;                                 // paired-end selection: parameters, running insert-size sums, scratch (ngm_select.cu)
 void pe_release(PeState *pe);
-struct MapState;                                // scratch of ngm_b200_map_batch (ngm_map.cu)
-void map_release(MapState *m);
 struct BatchState;                              // lanes + staging of ngm_b200_run_batch (ngm_batch.cu)
 void batch_release(BatchState *b);
 uint64_t batch_lane_launches(const ngm_b200_ctx *c);
@@ -120,7 +118,6 @@ struct ngm_b200_ctx {
 	bool have_ref = false;
 	ngm::CsState *cs = nullptr;
 	ngm::PeState *pe = nullptr;
-	ngm::MapState *map = nullptr;
 	ngm::BatchState *batch = nullptr;
 	int profile = 0;           // ngm_b200_profile: time the forward / backtrace kernels of the align launch sets with events
 	cudaEvent_t pev[3 * 64] = {};

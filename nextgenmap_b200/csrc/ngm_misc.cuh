@@ -149,6 +149,7 @@ __device__ __forceinline__ uint32_t ascii4_codes(uint32_t b) {
 	uint32_t t = (c | (c >> 4)) & 0x00FF00FFu;
 	t = (t | (t >> 8)) & 0xFFFFu;
 	if ((b & 0xDFDFDFDFu) == prmt(0x54474341u, 0u, t)) return t;             // "ACGT" indexed by code
+	if (b == 0u) return 0x6666u;                                              // padding behind the read
 	return ascii_code(b & 0xFFu) | ascii_code((b >> 8) & 0xFFu) << 4 | ascii_code((b >> 16) & 0xFFu) << 8 | ascii_code(b >> 24) << 12;
 }
 
@@ -173,6 +174,8 @@ __global__ void __launch_bounds__(16 * kPackRowsPerBlock) pack_reads_fused_kerne
 			if (live && wide && i0 + 8 <= width) {
 				const uint2 v = *reinterpret_cast<const uint2 *>(s + i0);
 				word = ascii4_codes(v.x) | ascii4_codes(v.y) << 16;
+			} else if (!live || i0 >= width) {
+				word = kNulWord;
 			} else {
 				word = 0;
 #pragma unroll

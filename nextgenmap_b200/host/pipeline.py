@@ -160,12 +160,12 @@ def map_batch(sw: CudaSW, reads: np.ndarray, mode: int = 0, paired: bool = False
             scap = max(scap, int(res.str_used) + 16)
             continue
         sw._check(rc)
-        total, raw = int(res.n_candidates), heap[: int(res.str_used)].tobytes()
+        total, raw = int(res.n_candidates), heap.tobytes()      # (the heap is sparse: one slot per sub-batch of the library's pipeline)
 
         def strings(r: int):
             o, cl, ml = int(recs[r]["str_off"]), int(recs[r]["cigar_len"]), int(recs[r]["md_len"])
             return raw[o: o + cl], raw[o + cl: o + cl + ml]
-        return MappedBatch(begin, pairs[:total], scores[:total], mh, best, mq, nt, recs, heap[: int(res.str_used) + 1], strings, pf if paired else None)
+        return MappedBatch(begin, pairs[:total], scores[:total], mh, best, mq, nt, recs, heap, strings, pf if paired else None)
     raise RuntimeError("ngm_b200_map_batch: buffer sizing failed")
 
 

@@ -28,9 +28,10 @@ def available(which: str) -> bool:
 
 
 def write_inputs(d: Path, ref_len: int = 5_000_000, n_reads: int = 10_000, read_len: int = 100, seed: int = 20261017,
-                 sub_rate: float = 0.02, indel_reads: float = 0.05) -> None:
+                 sub_rate: float = 0.02, indel_reads: float = 0.05, ins_rate: float = 0.0, del_rate: float = 0.0) -> None:
     """Seeded synthetic reference (one contig) + reads: uniform start, both strands, 2 % substitutions,
-    a 1-3 bp indel in 5 % of the reads, constant qualities; truth in the read name."""
+    a 1-3 bp indel in 5 % of the reads, constant qualities; truth in the read name.
+    ins_rate / del_rate: additionally one-base insertions / deletions PER BASE (BASELINE configs[3]: 12 % substitutions + 1.5 % + 1.5 %)."""
     rng = np.random.default_rng(seed)
     acgt = np.frombuffer(b"ACGT", np.uint8)
     ref = acgt[rng.integers(0, 4, ref_len)]
@@ -41,7 +42,17 @@ def write_inputs(d: Path, ref_len: int = 5_000_000, n_reads: int = 10_000, read_
     with open(d / "reads.fq", "wb") as f:
         for r in range(n_reads):
             pos = int(rng.integers(0, ref_len - read_len - 8))
-            seq = ref[pos: pos + read_len + 4].copy()
+            seq = ref[pos: pos + read_len + 4 + (read_len // 8 if del_rate else 0)].copy()
+            if ins_rate or del_rate:
+                ev = rng.random(len(seq))
+                out = []
+                for i, b in enumerate(seq):
+                    if ev[i] < del_rate:
+                        continue
+                    out.append(b)
+                    if ev[i] > 1.0 - ins_rate:
+                        out.append(acgt[rng.integers(0, 4)])
+                seq = np.array(out, np.uint8)
             if rng.random() < indel_reads:
                 at, k = int(rng.integers(10, read_len - 10)), int(rng.integers(1, 4))
                 if rng.random() < 0.5:
