@@ -937,7 +937,7 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int16x2", "data": "synthetic", "config": cfg,
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
-        "roofline": {"kernel": "score_s16_kernel" if dominant == "score" else "align_s16_fwd2_kernel + backtrace_format_kernel (one launch set per 262144 alignments)",
+        "roofline": {"kernel": "score_s16_kernel" if dominant == "score" else "align_s16_fwd2_kernel + backtrace_format_kernel (one launch set per 1 Mi alignments)",
                      "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": traffic, "traffic_note": f"dram bytes for the units of one launch set pass, from the ncu --set full capture summarised in {traffic_src}",
                      "peak_source": peak_src, "ms_per_launch_set": dom_ms, "units_per_launch_set": dom_units,
