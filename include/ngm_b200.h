@@ -458,6 +458,10 @@ int ngm_b200_alu_peak(ngm_b200_ctx *ctx, double *viaddmnmx_per_s, double *imad_p
  * ngm_b200_profile_read synchronises, returns the number of launch sets and their summed durations in ms, and re-arms. */
 int ngm_b200_profile(ngm_b200_ctx *ctx, int enable);
 int ngm_b200_profile_read(ngm_b200_ctx *ctx, float *forward_ms, float *backtrace_ms);
+/* EXPERIMENT, not a product path: north_star's warp-per-tile skewed wavefront (shuffles between lanes) for the local score, timed
+ * against the production thread-per-pair kernel by bench.py (`design_ab`).  d_pairs: ngm_b200_pair descriptors as for
+ * ngm_b200_dev_score_pairs (set_reference / set_reads first); corridor <= 32, local mode. */
+int ngm_b200_exp_wavefront_score(ngm_b200_ctx *ctx, int n, const void *d_pairs, void *d_scores, void *stream);
 /* Number of kernels this context has launched since creation (bench.py gpu_launches). */
 uint64_t ngm_b200_launch_count(const ngm_b200_ctx *ctx);
 

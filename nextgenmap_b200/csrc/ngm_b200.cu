@@ -868,3 +868,7 @@ int ngm_b200_align_pairs(ngm_b200_ctx *c, int mode, int n, const ngm_b200_pair *
 namespace ngm {
 int pack_reads_device(ngm_b200_ctx *c, const uint8_t *d_ascii, int n_reads, int stride, cudaStream_t st) { return pack_reads_device_impl(c, d_ascii, n_reads, stride, st); }
 }  // namespace ngm
+
+namespace ngm {
+int resolve_pairs_for(ngm_b200_ctx *c, const void *d_pairs_user, int n, cudaStream_t st) { return resolve_pairs(c, d_pairs_user, n, st); }
+}  // namespace ngm

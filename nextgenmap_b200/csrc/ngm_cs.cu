@@ -161,7 +161,6 @@ int finish_index(ngm_b200_ctx *c, CsState *cs, unsigned long long s1, unsigned l
 	cudaStream_t st = c->stream;
 	DevBuf d_size, d_off2, d_tmp;
 	CU(cs->d_both.ensure((size_t) NP * sizeof(uint4)));
-	CU(cs->d_table2.ensure((size_t) cs->table_len * 4 + 4));
 	CU(d_size.ensure((size_t) NP * 4));
 	CU(d_off2.ensure((size_t) NP * 4));
 	cs_pair_size_kernel<<<(NP + 255) / 256, 256, 0, st>>>(cs->d_tabu.as<uint32_t>(), NP, cs->k, d_size.as<uint32_t>());
@@ -169,6 +168,13 @@ int finish_index(ngm_b200_ctx *c, CsState *cs, unsigned long long s1, unsigned l
 	CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_size.as<uint32_t>(), d_off2.as<uint32_t>(), (int) NP, st));
 	CU(d_tmp.ensure(tmp_bytes));
 	CU(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, d_size.as<uint32_t>(), d_off2.as<uint32_t>(), (int) NP, st));
+	uint32_t last_off = 0, last_size = 0;                      // the padded total sizes the search's copy of the positions
+	CU(cudaMemcpyAsync(&last_off, d_off2.as<uint32_t>() + (NP - 1), 4, cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(&last_size, d_size.as<uint32_t>() + (NP - 1), 4, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	const unsigned long long padded = (unsigned long long) last_off + last_size;
+	if (padded >= 0xFFFFFFF0ull) return fail(NGM_B200_ERANGE, "position table too large after padding (%llu entries)", padded);
+	CU(cs->d_table2.ensure((size_t) padded * 4 + 64));
 	cs_pair_copy_kernel<<<(NP + 255) / 256, 256, 0, st>>>(cs->d_tabu.as<uint32_t>(), NP, cs->k, d_off2.as<uint32_t>(), cs->d_table.as<uint32_t>(),
 			cs->d_table2.as<uint32_t>(), cs->d_both.as<uint4>());
 	c->launches += 4;
@@ -428,7 +434,17 @@ int ngm_b200_dev_cs_search(ngm_b200_ctx *c, const void *d_ascii_reads, int n_rea
 		const bool bins_fit = ((c->concat_len + 1024) >> cs->bin_shift) < (1ull << 30);      // two flag bits ride on every stored bin
 		const bool scan_fits = (uint64_t) std::max(1, stride - cs->k + 1) * (uint64_t) P.max_kfreq < (1ull << 20) && P.max_kfreq <= 65535;      // packed scan: hits in 20 bits; list lengths in 16
 		const int n_kmers_max = stride - cs->k + 1;
-		int config = (n_kmers_max <= 256 && expect <= 4250.0) ? 1 : (n_kmers_max <= 256 && expect <= 7700.0) ? 2 : (n_kmers_max <= 512 && expect <= 14000.0) ? 3 : 4;
+		// TMA variant (default): bulk copies into the hit array; its regions are padded to four slots, ~1.5 slots per k-mer
+		// NGM_B200_CS_STAGE: how the position lists reach shared memory.  0 (default) = per-lane loads inside the flat sweep; 1 = one bulk copy
+		// per k-mer region (cp.async.bulk / UBLKCP, completion on an mbarrier) + per-thread runs; 2 = 16-byte cp.async (LDGSTS) + per-thread runs.
+		// Measured on B200, 4 M x 150 bp vs 3 Gbp (profiles/r2_cs_staging.md): 49.5 / 44.5 / 35.9 M reads/s -- staging adds a second dependent
+		// DRAM round trip per read (index entry -> list) behind a block-wide barrier and ~1.4 k serialised UBLKCP issue instructions per read,
+		// which the cheaper sweep (12 instructions per hit) does not buy back.  The staged variants stay selectable and are covered by the tests.
+		static const int stage = [] { const char *e = getenv("NGM_B200_CS_STAGE"); return e == nullptr ? 0 : std::max(0, std::min(2, atoi(e))); }();
+		const bool use_tma = stage != 0;
+		const double pad = use_tma ? 1.5 * (double) std::max(1, stride - cs->k + 1) : 0.0;
+		int config = (n_kmers_max <= 256 && expect + pad <= 4500.0) ? 1 : (n_kmers_max <= 256 && expect + pad <= 8000.0) ? 2 : (n_kmers_max <= 512 && expect + pad <= 14500.0) ? 3 : 4;
+		if (!use_tma) config = (n_kmers_max <= 256 && expect <= 4250.0) ? 1 : (n_kmers_max <= 256 && expect <= 7700.0) ? 2 : (n_kmers_max <= 512 && expect <= 14000.0) ? 3 : 4;
 		if (const char *e = getenv("NGM_B200_CS_CONFIG")) {        // testing hook: run a small case through a larger configuration
 			const int want = atoi(e);
 			if (want > config && want <= 4) config = want;
@@ -436,10 +452,22 @@ int ngm_b200_dev_cs_search(ngm_b200_ctx *c, const void *d_ascii_reads, int n_rea
 		if (!bins_fit || !scan_fits) {
 			cs->exact_all = true;                                  // (bin_size 0/1 on > 1 Gbp: sequential kernel only)
 			exact_only_fallback = true;
+		} else if (use_tma) {
+			if (stage == 1) {
+				if (config == 1) CU(launch(cs_search_kernel<10, 256, 4864, 0, 1>, CsSmem<10, 256, 4864>::bytes_staged));                  // 150 bp on 3 Gbp: 5 blocks / SM
+				else if (config == 2) CU(launch(cs_search_kernel<11, 256, 8448, 4096, 1>, CsSmem<11, 256, 8448, 4096>::bytes_staged));      // 250 bp on 3 Gbp: 3 blocks / SM
+				else if (config == 3) CU(launch(cs_search_kernel<12, 512, 16384, 0, 1>, CsSmem<12, 512, 16384>::bytes_staged));
+				else CU(launch(cs_search_kernel<12, 1024, 36864, 0, 1>, CsSmem<12, 1024, 36864>::bytes_staged));
+			} else {
+				if (config == 1) CU(launch(cs_search_kernel<10, 256, 4864, 0, 2>, CsSmem<10, 256, 4864>::bytes_staged));
+				else if (config == 2) CU(launch(cs_search_kernel<11, 256, 8448, 4096, 2>, CsSmem<11, 256, 8448, 4096>::bytes_staged));
+				else if (config == 3) CU(launch(cs_search_kernel<12, 512, 16384, 0, 2>, CsSmem<12, 512, 16384>::bytes_staged));
+				else CU(launch(cs_search_kernel<12, 1024, 36864, 0, 2>, CsSmem<12, 1024, 36864>::bytes_staged));
+			}
 		} else if (config == 1) {
-			CU(launch(cs_search_kernel<10, 256, 4608>, CsSmem<10, 256, 4608>::bytes));                  // 150 bp on 3 Gbp: 5 blocks / SM
+			CU(launch(cs_search_kernel<10, 256, 4608>, CsSmem<10, 256, 4608>::bytes));
 		} else if (config == 2) {
-			CU(launch(cs_search_kernel<11, 256, 8192, 4096>, CsSmem<11, 256, 8192, 4096>::bytes));      // 250 bp on 3 Gbp: 3 blocks / SM
+			CU(launch(cs_search_kernel<11, 256, 8192, 4096>, CsSmem<11, 256, 8192, 4096>::bytes));
 		} else if (config == 3) {
 			CU(launch(cs_search_kernel<12, 512, 16384>, CsSmem<12, 512, 16384>::bytes));
 		} else {

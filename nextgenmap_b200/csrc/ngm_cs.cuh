@@ -283,7 +283,10 @@ __global__ void cs_pair_size_kernel(const uint32_t *__restrict__ tabu, uint32_t 
 	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= n_prefix) return;
 	const uint32_t c = cs_revcomp(p, k);
-	size[p] = p <= c ? cs_list_len(tabu, p) + (c != p ? cs_list_len(tabu, c) : 0u) : 0u;
+	const uint32_t n = p <= c ? cs_list_len(tabu, p) + (c != p ? cs_list_len(tabu, c) : 0u) : 0u;
+	// every pair region starts on a 64-byte boundary (16 positions): a region then costs exactly ceil(bytes / 64) DRAM fetches of 64 bytes
+	// instead of straddling one more, and it is a legal source of a bulk copy (cp.async.bulk: 16-byte aligned)
+	size[p] = (n + 15u) & ~15u;
 }
 
 __global__ void cs_pair_copy_kernel(const uint32_t *__restrict__ tabu, uint32_t n_prefix, int k, const uint32_t *__restrict__ off2,
@@ -306,7 +309,35 @@ __global__ void cs_pair_copy_kernel(const uint32_t *__restrict__ tabu, uint32_t 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// TMA (bulk asynchronous copy) helpers: cp.async.bulk global -> shared, completion on an mbarrier (SASS: UBLKCP + SYNCS)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cs_smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cs_mbar_init(uint64_t *bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cs_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void cs_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cs_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool cs_mbar_try_wait(uint64_t *bar, uint32_t parity) {
+	uint32_t ok;
+	asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+			: "=r"(ok) : "r"(cs_smem_u32(bar)), "r"(parity) : "memory");
+	return ok != 0;
+}
+__device__ __forceinline__ void cs_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+			::"r"(cs_smem_u32(dst)), "l"(src), "r"(bytes), "r"(cs_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cs_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------------
 // search: fast path, one 256-thread block per read
+//
+// TMA variant (template parameter TMA, the default on sm_100a): a k-mer's two position lists are ONE 64-byte aligned region of `table`,
+// so the thread that looked the k-mer up issues one bulk copy of that region straight into the k-mer's slots of the shared hit array;
+// all copies of the read complete on one mbarrier.  Sweep B then walks the hit array k-mer by k-mer (one warp per k-mer: offset and
+// strand are warp-uniform, no hit -> k-mer map, no per-lane global address arithmetic) and turns positions into bins in place.  Slots keep
+// the table's layout order; the reference's hit order, which only phase E and path J need, is recovered per slot by cs_seq_of().
 //
 // Almost all hits of a read are noise: bins that are hit exactly once (~4100 of ~4150 at 150 bp on 3 Gbp).  Only
 // bins hit at least twice can reach a threshold above one vote, so the hits are first run through a 64 Kbit
@@ -340,15 +371,43 @@ struct CsSmem {
 	static constexpr int T2 = 1 << T2_LOG;
 	static constexpr int SEENW = SEENW_ ? SEENW_ : (T2 > 2048 ? T2 : 2048);        // words of the "seen" bitmap (reused as per-slot first-hit array, >= T2)
 	static_assert(SEENW >= T2, "the first-hit array of path J lives in the bitmap");
-	static constexpr size_t bytes = (size_t) (SEENW + kCsRepWords) * 4 + (size_t) T2 * 8 + (size_t) MAXH * 4 + (size_t) MAXK * 16 +
-			(size_t) MAXK + 32 + ((size_t) MAXH / 32 + 2) * 2 + ((size_t) MAXH / 32 + 1) * 4;
+	static constexpr size_t bytes_staged = (size_t) (SEENW + kCsRepWords) * 4 + (size_t) T2 * 8 + (size_t) MAXH * 4 + (size_t) MAXK * 16 + (size_t) MAXK + 32;
+	static constexpr size_t bytes = bytes_staged + ((size_t) MAXH / 32 + 2) * 2 + ((size_t) MAXH / 32 + 1) * 4;      // + the chunk maps of the first-generation sweep
 };
 
-template <int T2_LOG, int MAXK, int MAXH, int SEENW_ = 0>
+constexpr uint32_t kHitPad = 0xFFFFFFFFu;                       // TMA variant: padding slot behind a k-mer's hits (regions are multiples of four slots)
+
+// TMA variant: km[rank] = {first slot, region start in `table`, first list's length | hits << 16, k-mer offset | palindrome << 30 | first list is the reverse one << 31}
+__device__ __forceinline__ int cs_rank_of(const uint4 *km, int n_km, uint32_t slot) {
+	int lo = 0, hi = n_km - 1;
+	while (lo < hi) {                                           // last k-mer whose first slot is <= slot
+		const int mid = (lo + hi + 1) >> 1;
+		if (km[mid].x <= slot) lo = mid; else hi = mid - 1;
+	}
+	return lo;
+}
+// slot (layout order: the list of the smaller prefix first) <-> number of the hit in the reference's order (forward list first)
+__device__ __forceinline__ uint32_t cs_seq_of(const uint4 *km, int n_km, uint32_t slot) {
+	const uint4 e = km[cs_rank_of(km, n_km, slot)];
+	if (!(e.w >> 31)) return slot;
+	const uint32_t o = slot - e.x, first = e.z & 0xFFFFu, total = e.z >> 16;
+	return o < first ? e.x + (total - first) + o : e.x + (o - first);
+}
+__device__ __forceinline__ uint32_t cs_slot_of(const uint4 *km, int n_km, uint32_t seq) {
+	const uint4 e = km[cs_rank_of(km, n_km, seq)];
+	if (!(e.w >> 31)) return seq;
+	const uint32_t o = seq - e.x, first = e.z & 0xFFFFu, total = e.z >> 16, fwd = total - first;
+	return o < fwd ? e.x + first + o : (o < total ? e.x + (o - fwd) : seq);      // (padding slots map to themselves)
+}
+
+template <int T2_LOG, int MAXK, int MAXH, int SEENW_ = 0, int STAGE = 0>
 __global__ void __launch_bounds__(256, NGM_CS_MIN_BLOCKS) cs_search_kernel(const CsDev P, const uint8_t *__restrict__ reads, int n_reads, int stride,
 		CsMeta *__restrict__ meta, CsCand *__restrict__ heap, uint32_t heap_cap, uint32_t *__restrict__ cursor, uint32_t *__restrict__ slow_list,
 		uint32_t *__restrict__ slow_count, float *__restrict__ max_hit) {
 	// slow_count[1 + reason]: why reads left the fast path (diagnostics, see CsExactReason)
+	// STAGE: how the position lists reach the shared hit array -- 0: per-lane loads in sweep B (first generation); 1: one bulk copy
+	// (cp.async.bulk, UBLKCP) per k-mer region, completion on an mbarrier; 2: 16-byte cp.async (LDGSTS) issued by the k-mer's own thread
+	constexpr bool TMA = STAGE != 0;
 	constexpr int T2 = 1 << T2_LOG;
 	constexpr uint32_t MASK = T2 - 1;
 	constexpr int NT = 256;
@@ -378,7 +437,8 @@ __global__ void __launch_bounds__(256, NGM_CS_MIN_BLOCKS) cs_search_kernel(const
 	__shared__ uint16_t s_queue[kCsQueue];                     // hit numbers (< MAXH)
 	static_assert(MAXH <= 65536, "queue entries are 16 bits wide");
 	__shared__ uint16_t s_multi[kCsMaxMulti];
-	__shared__ uint32_t s_nhits;
+	__shared__ uint32_t s_nhits, s_nkm, s_tx, s_npalin;
+	__shared__ __align__(8) uint64_t s_mbar;
 	__shared__ uint32_t s_max, s_maxm, s_slow, s_nmulti, s_nacc, s_ncand, s_nitems, s_nord, s_nq, s_nres;
 	__shared__ uint32_t s_res[2 * kCsMaxRes];                  // bins whose first vote is looked for (see sweep C)
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -387,11 +447,17 @@ __global__ void __launch_bounds__(256, NGM_CS_MIN_BLOCKS) cs_search_kernel(const
 	if (tid == 0) {
 		s_len = stride;
 		s_max = s_maxm = s_slow = s_nmulti = s_nacc = s_ncand = s_nitems = s_nord = s_nq = s_nres = 0;
+		s_tx = s_npalin = 0;
+		if (STAGE == 1) {
+			cs_mbar_init(&s_mbar, 1);
+			cs_fence_proxy_async();
+		}
 	}
 	{
 		uint4 *z4 = reinterpret_cast<uint4 *>(seen);               // both bitmaps
 		for (int i = tid; i < (SEENW + kCsRepWords) / 4; i += NT) z4[i] = make_uint4(0, 0, 0, 0);
-		for (int i = tid; i < MAXH / 32 + 1; i += NT) bstart[i] = 0;
+		if (!TMA)
+			for (int i = tid; i < MAXH / 32 + 1; i += NT) bstart[i] = 0;
 		uint4 *k4 = reinterpret_cast<uint4 *>(keys), *c4 = reinterpret_cast<uint4 *>(cnts);
 		for (int i = tid; i < T2 / 4; i += NT) {
 			k4[i] = make_uint4(kCsEmpty, kCsEmpty, kCsEmpty, kCsEmpty);
@@ -411,7 +477,7 @@ __global__ void __launch_bounds__(256, NGM_CS_MIN_BLOCKS) cs_search_kernel(const
 	const int n_kmers = max(0, len - k + 1);                   // <= MAXK (checked by the launcher: stride - k + 1 <= MAXK)
 
 	// ---- A: list descriptors + sequence numbers -----------------------------------------------------------
-	uint32_t mine[IPT], m_fs[IPT], m_rs[IPT], m_fc[IPT];
+	uint32_t mine[IPT], m_fs[IPT], m_rs[IPT], m_fc[IPT], m_rc[IPT];
 #pragma unroll
 	for (int q = 0; q < IPT; ++q) {
 		const int o = tid * IPT + q;                           // blocked layout so that the scan below is a plain prefix sum
@@ -431,7 +497,9 @@ __global__ void __launch_bounds__(256, NGM_CS_MIN_BLOCKS) cs_search_kernel(const
 		m_fs[q] = fs;
 		m_rs[q] = rs;
 		m_fc[q] = fc;
-		mine[q] = (fc + rc) | ((fc + rc) ? (1u << 20) : 0u);      // hits in bits 0..19, "has hits" counted in bits 20..31
+		m_rc[q] = rc;
+		// hits in bits 0..19 (TMA: slots, a multiple of four = 16 bytes, the granularity of a bulk copy), "has hits" counted in bits 20..31
+		mine[q] = (TMA ? ((fc + rc + 3u) & ~3u) : (fc + rc)) | ((fc + rc) ? (1u << 20) : 0u);
 	}
 	uint32_t tsum = 0;
 #pragma unroll
@@ -452,14 +520,49 @@ __global__ void __launch_bounds__(256, NGM_CS_MIN_BLOCKS) cs_search_kernel(const
 	for (int q = 0; q < IPT; ++q) {
 		const uint32_t start = run & 0xFFFFFu, cnt = mine[q] & 0xFFFFFu, rank = run >> 20;
 		if (cnt && start + cnt <= (uint32_t) MAXH) {            // (reads with more hits leave for the exact kernel below)
-			km[rank] = make_uint4(start, m_fs[q], m_rs[q], m_fc[q] | ((uint32_t) (tid * IPT + q) << 16));      // list lengths < max_kfreq <= 65535
-			if (start & 31u) atomicOr(&bstart[start >> 5], 1u << (start & 31u));
-			for (uint32_t ch = (start + 31u) >> 5; (ch << 5) < start + cnt; ++ch) rbase[ch] = (uint16_t) rank;
+			if (TMA) {
+				const uint32_t fc = m_fc[q], rc = m_rc[q], fs = m_fs[q], rs = m_rs[q];
+				const bool palin = fc && rc && fs == rs;            // the k-mer is its own reverse complement: one list, hit on both strands
+				const bool first_rev = rc && (!fc || rs < fs);      // layout: the list of the smaller prefix comes first
+				const uint32_t rstart = first_rev ? rs : fs;
+				km[rank] = make_uint4(start, rstart, (first_rev ? rc : fc) | ((fc + rc) << 16),
+						(uint32_t) (tid * IPT + q) | (palin ? 0x40000000u : 0u) | (first_rev ? 0x80000000u : 0u));
+				if (palin) {
+					// (positions of a palindromic k-mer are read from the table in the sweep: its one list is hit on both strands)
+				} else if (STAGE == 1) {
+					cs_bulk_g2s(bins + start, P.table + rstart, cnt * 4u, &s_mbar);      // region start: 64-byte aligned; cnt * 4: a multiple of 16
+					atomicAdd(&s_tx, cnt * 4u);
+				} else {
+					for (uint32_t e4 = 0; e4 < cnt; e4 += 4)                              // 16 bytes per copy, both sides 16-byte aligned
+						asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(cs_smem_u32(bins + start + e4)), "l"(P.table + rstart + e4) : "memory");
+				}
+			} else {
+				km[rank] = make_uint4(start, m_fs[q], m_rs[q], m_fc[q] | ((uint32_t) (tid * IPT + q) << 16));      // list lengths < max_kfreq <= 65535
+				if (start & 31u) atomicOr(&bstart[start >> 5], 1u << (start & 31u));
+				for (uint32_t ch = (start + 31u) >> 5; (ch << 5) < start + cnt; ++ch) rbase[ch] = (uint16_t) rank;
+			}
 		}
 		run += mine[q];
 	}
-	if (tid == NT - 1) s_nhits = run & 0xFFFFFu;
+	if (tid == NT - 1) {
+		s_nhits = run & 0xFFFFFu;
+		s_nkm = run >> 20;
+	}
 	__syncthreads();
+	// every copy issued above must have landed before this block may leave (or reuse) its shared memory, whatever path the read takes
+	if (STAGE == 1) {
+		if (tid == 0) {
+			cs_mbar_expect_tx(&s_mbar, s_tx);
+			uint32_t spin = 0;
+			while (!cs_mbar_try_wait(&s_mbar, 0u))
+				if (++spin > (1u << 24)) __trap();
+		}
+		__syncthreads();
+	} else if (STAGE == 2) {
+		asm volatile("cp.async.commit_group;" ::: "memory");
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+		__syncthreads();
+	}
 	const uint32_t n_hits = s_nhits;
 	auto to_exact = [&](int reason) {
 		if (tid == 0) {
@@ -518,7 +621,70 @@ __global__ void __launch_bounds__(256, NGM_CS_MIN_BLOCKS) cs_search_kernel(const
 	constexpr int U = 8;
 	const uint32_t n_chunks = (n_hits + 31u) >> 5;
 	const uint32_t lane_le = (2u << lane) - 1u;
-	for (uint32_t c0 = warp; c0 < n_chunks; c0 += (NT / 32) * U) {
+	const int n_km = (int) s_nkm;
+	if (TMA) {
+		// The positions are in bins[] already (layout order).  Every thread walks its own run of ceil(n_hits / 256) consecutive slots:
+		// perfectly balanced, conflict-free shared-memory strides, and the k-mer a slot belongs to (offset, strand) changes only every
+		// ~30 slots, so it is looked up once per thread (binary search over the region starts) and then advanced.  A hit costs about a
+		// dozen instructions.  (Measured alternatives: a warp per k-mer -- 10.9 k warp instructions per read for this sweep; a thread
+		// per list -- 7.5 k and a long wait for the last round at the barrier; the flat chunks of the first generation -- ~7 k.)
+		const uint32_t corr_r_base = (uint32_t) (len - k);
+		const uint32_t per = (n_hits + NT - 1) / NT;
+		uint32_t h = tid * per;
+		const uint32_t h_end = min(n_hits, h + per);
+		if (h < h_end) {
+			int rank = cs_rank_of(km, n_km, h);
+			uint32_t R = 0, first = 0, total = 0, r_end = 0, corr1 = 0, corr2 = 0, flag1 = 0, flag2 = 0, src = 0;
+			bool palin = false;
+			auto load_region = [&]() {
+				const uint4 e = km[rank];
+				R = e.x;
+				src = e.y;
+				first = e.z & 0xFFFFu;
+				total = e.z >> 16;
+				r_end = R + ((total + 3u) & ~3u);
+				const uint32_t j = e.w & 0xFFFFu;
+				const bool first_rev = (e.w >> 31) != 0;
+				palin = (e.w & 0x40000000u) != 0;
+				const uint32_t c_f = j, c_r = corr_r_base - j;
+				corr1 = first_rev ? c_r : c_f;
+				corr2 = first_rev ? c_f : c_r;
+				flag1 = first_rev ? kHitRev : 0u;
+				flag2 = first_rev ? 0u : kHitRev;
+			};
+			load_region();
+			for (; h < h_end; ++h) {
+				if (h >= r_end) {                                          // next k-mer (regions are contiguous)
+					++rank;
+					load_region();
+				}
+				const uint32_t o = h - R;
+				if (o >= total) {                                          // padding behind the k-mer's hits
+					bins[h] = kHitPad;
+					continue;
+				}
+				const bool in1 = o < first;
+				uint32_t loc = palin ? NGM_CS_LD(P.table + src + (in1 ? o : o - first)) : bins[h];
+				const uint32_t corr = in1 ? corr1 : corr2;
+				if (loc < corr) {                                          // the reference's 64-bit wrap-around: exact kernel
+					s_slow = 1;
+					loc = corr;
+				}
+				const uint32_t bin = (loc - corr) >> P.bin_shift;
+				const uint32_t hb = (bin * 0x85EBCA6Bu) >> SEEN_SHIFT;
+				const uint32_t bit = 1u << (hb & 31);
+				const uint32_t old = atomicOr(&seen[hb >> 5], bit);
+				uint32_t v = bin | (in1 ? flag1 : flag2);
+				if (old & bit) {
+					v |= kHitInserted;
+					const uint32_t at = atomicAdd(&s_nq, 1u);
+					if (at < (uint32_t) kCsQueue) s_queue[at] = (uint16_t) h;
+				}
+				bins[h] = v;
+			}
+		}
+	}
+	for (uint32_t c0 = warp; !TMA && c0 < n_chunks; c0 += (NT / 32) * U) {
 		uint32_t loc[U], meta_j[U];
 #pragma unroll
 		for (int u = 0; u < U; ++u) {
@@ -630,7 +796,7 @@ __global__ void __launch_bounds__(256, NGM_CS_MIN_BLOCKS) cs_search_kernel(const
 #pragma unroll
 			for (int e = 0; e < 4; ++e) {
 				const uint32_t t = tt[e];
-				if (h4 + e >= n_hits || (t & kHitInserted)) continue;
+				if (h4 + e >= n_hits || (t & kHitInserted)) continue;      // (padding slots carry every flag)
 				uint32_t word, bit;
 				rep_bit(t & kHitBin, word, bit);
 				if (!(rep[word] & bit)) continue;
@@ -718,15 +884,17 @@ __global__ void __launch_bounds__(256, NGM_CS_MIN_BLOCKS) cs_search_kernel(const
 		uint32_t *firsth = seen;                               // the bitmap is no longer needed: first hit per table slot
 		for (int sl = tid; sl < T2; sl += NT) firsth[sl] = 0xFFFFFFFFu;
 		__syncthreads();
+		// (TMA variant: h runs over the reference's hit numbers, cs_slot_of() gives the slot the hit is stored in)
 		for (uint32_t h = tid; h < n_hits; h += NT) {
 			const uint32_t t = bins[h];
-			if (t & kHitInserted) atomicMin(&firsth[find(t & kHitBin)], h);
+			if (t != kHitPad && (t & kHitInserted)) atomicMin(&firsth[find(t & kHitBin)], TMA ? cs_seq_of(km, n_km, h) : h);
 		}
 		__syncthreads();
 		const uint32_t chunk = (n_hits + NT - 1) / NT;
 		const uint32_t h0 = min(n_hits, tid * chunk), h1 = min(n_hits, h0 + chunk);
 		auto emits = [&](uint32_t h, uint32_t &f, uint32_t &rv, uint32_t &bin) -> uint32_t {
-			const uint32_t t = bins[h];
+			const uint32_t t = bins[TMA ? cs_slot_of(km, n_km, h) : h];
+			if (t == kHitPad) return 0u;
 			bin = t & kHitBin;
 			if (!(t & kHitInserted)) {                             // a bin with exactly one vote
 				f = (t & kHitRev) ? 0u : 1u;
@@ -821,13 +989,13 @@ __global__ void __launch_bounds__(256, NGM_CS_MIN_BLOCKS) cs_search_kernel(const
 		// ---- E: order of the list: replay the relevant hits in sequence ---------------------------------------
 		for (uint32_t h = tid; h < n_hits; h += NT) {
 			const uint32_t t = bins[h];
-			if (!(t & kHitInserted)) continue;                 // not in the table: a single-vote bin
+			if (!(t & kHitInserted) || t == kHitPad) continue;     // not in the table: a single-vote bin
 			const int slot = find(t & kHitBin);
 			const uint32_t c = cnts[slot];
 			if ((c & 0x8000u) || (c & 0x7FFFu) >= 2u || ((c >> 16) & 0x7FFFu) >= 2u) {
 				const uint32_t at = atomicAdd(&s_nitems, 1u);
 				if (at < kCsMaxItems) {
-					s_items_t[at] = h;                             // sequence number of the hit
+					s_items_t[at] = TMA ? cs_seq_of(km, n_km, h) : h;      // sequence number of the hit
 					s_items_s[at] = (uint32_t) slot | ((t & kHitRev) ? 0x80000000u : 0u);
 				}
 			}

@@ -73,6 +73,7 @@ struct HostBuf {   // pinned
 struct ScoreArgs;
 int mode_of(int mode);                          // mode & 0xFF -> 0 / 1, or -1
 // (implemented in ngm_b200.cu; used by the batch engine in ngm_batch.cu)
+int resolve_pairs_for(ngm_b200_ctx *c, const void *d_pairs_user, int n, cudaStream_t st);      // ngm_b200_pair -> c->d_rpairs (PairDesc)
 int pack_reads_device(ngm_b200_ctx *c, const uint8_t *d_ascii, int n_reads, int stride, cudaStream_t st);
 int run_score(ngm_b200_ctx *c, int mode, const ScoreArgs &a, cudaStream_t st);
 int run_align(ngm_b200_ctx *c, int mode, const PairDesc *pairs, int n, const uint32_t *rf, const uint32_t *rr, const uint16_t *rl, const uint32_t *ref4,
