@@ -112,6 +112,12 @@ int ngm_b200_device_count(void);
 const char *ngm_b200_last_error(void);
 ngm_b200_ctx *ngm_b200_create(const ngm_b200_params *params);
 void ngm_b200_destroy(ngm_b200_ctx *ctx);
+/* A context on the same device that borrows `root`'s resident data (packed reference, k-mer index, selection parameters) and owns
+ * only its stream, read batch and scratch.  NGM creates one IAlignment per CS thread (CS.cpp:455-461; the reference shares its OpenCL
+ * context the same way, OclHost.cpp:50,133): with this, sixteen threads hold ONE copy of a 3 Gbp reference.  Destroy it before the
+ * root.  ngm_b200_sync_shared re-borrows after the root's reference / index changed; the caller serialises it against those changes. */
+ngm_b200_ctx *ngm_b200_create_shared(ngm_b200_ctx *root);
+int ngm_b200_sync_shared(ngm_b200_ctx *ctx);
 /* IAlignment::GetScoreBatchSize / GetAlignBatchSize (IAlignment.h:53-54) */
 int ngm_b200_score_batch_size(const ngm_b200_ctx *ctx);
 int ngm_b200_align_batch_size(const ngm_b200_ctx *ctx);

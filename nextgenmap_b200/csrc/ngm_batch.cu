@@ -423,6 +423,21 @@ int install_reads(ngm_b200_ctx *c, int format, const void *d_reads, int n, int s
 	return NGM_B200_OK;
 }
 
+// a child context (lane / shared context) takes over the root's resident data: packed reference, k-mer index, selection parameters
+int borrow_from_root(ngm_b200_ctx *l, ngm_b200_ctx *root) {
+	l->d_ref4.borrow(root->d_ref4);
+	l->concat_len = root->concat_len;
+	l->n_region_nib = root->n_region_nib;
+	l->have_ref = root->have_ref;
+	l->se_strata = root->se_strata;
+	int rc = cs_share_index(l, root);
+	if (rc) return rc;
+	rc = pe_share_state(l, root);
+	if (rc) return rc;
+	l->root_epoch = root->epoch;
+	return NGM_B200_OK;
+}
+
 int sync_lanes(ngm_b200_ctx *c) {
 	if (c->batch == nullptr) c->batch = new BatchState();
 	BatchState *B = c->batch;
@@ -440,14 +455,7 @@ int sync_lanes(ngm_b200_ctx *c) {
 	if (B->pe_chain == nullptr) CU(cudaEventCreateWithFlags(&B->pe_chain, cudaEventDisableTiming));
 	if (B->synced_epoch != c->epoch) {
 		for (ngm_b200_ctx *l : B->lanes) {
-			l->d_ref4.borrow(c->d_ref4);
-			l->concat_len = c->concat_len;
-			l->n_region_nib = c->n_region_nib;
-			l->have_ref = c->have_ref;
-			l->se_strata = c->se_strata;
-			int rc = cs_share_index(l, c);
-			if (rc) return rc;
-			rc = pe_share_state(l, c);
+			int rc = borrow_from_root(l, c);
 			if (rc) return rc;
 		}
 		B->synced_epoch = c->epoch;
@@ -476,6 +484,28 @@ uint64_t batch_lane_launches(const ngm_b200_ctx *c) {
 }  // namespace ngm
 
 extern "C" {
+
+ngm_b200_ctx *ngm_b200_create_shared(ngm_b200_ctx *root) {
+	if (root == nullptr || root->root != nullptr) {
+		fail(NGM_B200_EINVAL, "ngm_b200_create_shared needs a root context");
+		return nullptr;
+	}
+	ngm_b200_params hp = root->hp;
+	ngm_b200_ctx *l = ngm_b200_create(&hp);
+	if (l == nullptr) return nullptr;
+	l->root = root;
+	if (borrow_from_root(l, root) != NGM_B200_OK) {
+		ngm_b200_destroy(l);
+		return nullptr;
+	}
+	return l;
+}
+
+int ngm_b200_sync_shared(ngm_b200_ctx *c) {
+	if (c == nullptr) return fail(NGM_B200_EINVAL, "ctx == NULL");
+	if (c->root == nullptr || c->root_epoch == c->root->epoch) return NGM_B200_OK;
+	return borrow_from_root(c, c->root);
+}
 
 int ngm_b200_set_pipeline(ngm_b200_ctx *c, int lanes, int sub_batch_reads) {
 	if (c == nullptr) return fail(NGM_B200_EINVAL, "ctx == NULL");

@@ -125,5 +125,6 @@ struct ngm_b200_ctx {
 	int pev_used = 0;
 	int se_strata = 0;         // "strata" for single-end top-1 selection (ScoreBuffer.cpp:259)
 	uint64_t epoch = 0;        // bumped whenever the reference / index / selection parameters change: lanes re-sync their aliases
-	ngm_b200_ctx *root = nullptr;      // set in a lane: the context whose resident data it borrows
+	ngm_b200_ctx *root = nullptr;      // set in a lane / shared context: the context whose resident data it borrows
+	uint64_t root_epoch = ~0ull;       // the root's epoch at the last borrow
 };

@@ -23,13 +23,16 @@ with tempfile.TemporaryDirectory(prefix="ngm_t_") as td:
     env["OPENCL_VENDOR_PATH"] = str(ocl / "vendor")
     env["LD_LIBRARY_PATH"] = str(ocl / "lib") + os.pathsep + env.get("LD_LIBRARY_PATH", "")
     subprocess.run([str(e2e.binary("ref")), "-r", str(d / "ref.fa"), "-t", str(threads), "--no-progress"], env=env, capture_output=True, cwd=d)  # index only
-    res = {}
-    for which in ("ref", "cuda", "ref", "cuda"):
+    res, done = {}, {}
+    for which in ("ref", "cuda", "cuda_strict", "ref", "cuda", "cuda_strict"):
         t0 = time.time()
         p = subprocess.run([str(e2e.binary(which)), "-r", str(d / "ref.fa"), "-q", str(d / "reads.fq"), "-o", str(d / f"{which}.sam"), "-t", str(threads),
                             "--no-progress"], env=env, capture_output=True, text=True, cwd=d)
         dt = time.time() - t0
         res.setdefault(which, []).append(dt)
+        import re
+        m = re.search(r"elapsed: ([0-9.]+)s", p.stdout + p.stderr)
+        done.setdefault(which, []).append(float(m.group(1)) if m else None)
     same = sorted(l for l in open(d / "ref.sam") if not l.startswith("@PG")) == sorted(l for l in open(d / "cuda.sam") if not l.startswith("@PG"))
-print(json.dumps({"reads": n_reads, "ref_len": ref_len, "threads": threads, "wall_s": res, "reads_per_s": {k: n_reads / min(v) for k, v in res.items()},
+print(json.dumps({"reads": n_reads, "ref_len": ref_len, "threads": threads, "wall_s": res, "ngm_done_elapsed_s": done, "reads_per_s": {k: n_reads / min(v) for k, v in res.items()},
                   "sam_identical": same}))

@@ -1,6 +1,8 @@
 """BASELINE configs[0] end to end: the UNMODIFIED NextGenMap, once with its own OpenCL backend (CPU device) and
 once with the CUDA backend swapped in at link time (nextgenmap_b200/link_seam, zero source changes), must write
-the same SAM: same positions, MAPQ, CIGAR, AS / NM / XI / MD tags for every read.
+the same SAM: same positions, MAPQ, CIGAR, AS / NM / XI / MD tags for every read.  Two CUDA builds: `ngm_cuda` with the
+re-plumbed ScoreBuffer / AlignmentBuffer (their window fetch submits descriptors against the reference resident in HBM, one
+shared copy for all CS threads; link_seam/replumb_shim.cpp) and `ngm_cuda_strict` (char** windows through IAlignment as they are).
 
 Both binaries are built by oracle/Makefile.ngm where /root/reference exists and travel to the GPU box in
 oracle/_ref/ (git-ignored); the test is skipped when they are absent.
@@ -21,6 +23,8 @@ def compare(extra, n_reads=10_000, read_len=100, threads=4):
         e2e.write_inputs(d, ref_len=5_000_000, n_reads=n_reads, read_len=read_len)
         want = e2e.run("ref", d, threads=threads, extra=extra, out_name="ref.sam")
         got = e2e.run("cuda", d, threads=threads, extra=extra, out_name="cuda.sam")
+        strict = e2e.run("cuda_strict", d, threads=threads, extra=extra, out_name="cuda_strict.sam") if e2e.available("cuda_strict") else got
+    assert strict == got
     assert len(want) == n_reads + 2                      # @HD, @SQ + one record per read
     mapped = sum(1 for ln in want if not ln.startswith("@") and ln.split("\t")[2] != "*")
     assert mapped > 0.98 * n_reads
