@@ -68,6 +68,8 @@ def parse_args():
     ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4],
                     help="BASELINE.json configs[i]: 1 = 10 M x 150 bp SE (headline, default); 2 = paired-end 2 x 150 bp (10 M reads = 5 M fragments per GPU); "
                          "3 = 5 M x 250 bp, 12 %% substitutions + 1.5 %% ins + 1.5 %% del, -C 40 (corridor 80); 4 = read-length sweep point, use with --read-len")
+    ap.add_argument("--no-ngm", action="store_true", help="skip the whole-program run of the unmodified ngm on the host cores (candidate_search.cpu_baseline_ngm)")
+    ap.add_argument("--ngm-sample", type=int, default=1_000_000, help="reads of the workload the unmodified ngm maps (SURVEY 8d)")
     ap.add_argument("--no-numa", action="store_true", help="N > 1: do not bind the rank to the CPUs next to its GPU before the pinned staging is allocated")
     args = ap.parse_args()
     if args.config == 3:
@@ -212,6 +214,80 @@ def bind_to_gpu_numa_node(torch, local_rank: int):
         return {"pci": bdf, "numa_node": node, "bound": True, "cpus": len(use)}
     except Exception as e:  # noqa: BLE001
         return {"bound": False, "error": str(e)}
+
+
+def run_ngm_whole(sw, ref, batch, n_sample, L, qml, contigs, sensitivity, threads, lib, tmp_root=None):
+    """SURVEY 8d "CPU timing beside it": the UNMODIFIED NextGenMap (oracle/_ref/ngm/ngm_ref: its own CS, OpenCL-on-CPU kernels, selection,
+    SAM writer) with `-t <threads>` on a sample of the same reads against the same 3 Gbp reference, with a warm index: the encoded
+    reference and the prefix table are written in NGM's own cache-file formats (the table is the one built on the device, byte-identical
+    to NGM's) so that NGM loads instead of rebuilding them.  -> reads/s from the wall clock of the mapping phase (a run with 1000 reads is
+    subtracted as start-up: index load, OpenCL initialisation)."""
+    import ctypes as C
+    import re
+    import shutil
+    import tempfile
+    from oracle import ngm_e2e as e2e
+    from nextgenmap_b200.host.cuda_sw import PrefixTableFile, _CContig, _CEncRef
+    if not e2e.available("ref"):
+        return {"unavailable": "oracle/_ref/ngm/ngm_ref not built"}
+    base = tmp_root or ("/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 12 << 30 else None)
+    d = Path(tempfile.mkdtemp(prefix="ngm_whole_", dir=base))
+    try:
+        t0 = time.perf_counter()
+        (d / "ref.fa").write_bytes(b">stub (NGM loads ref.fa-enc.2.ngm)\nACGT\n")
+        packed = ref.packed.cpu().numpy()
+        ctg = (_CContig * contigs)()
+        for i, s0 in enumerate(ref.contig_start):
+            nm = b"chr%d" % (i + 1)
+            ctg[i].start, ctg[i].length, ctg[i].name_len, ctg[i].name = int(s0), int(ref.contig_len), len(nm), nm
+        enc = _CEncRef()
+        enc.concat_len, enc.packed_bytes, enc.n_contigs = ref.concat_len - 1, packed.size, contigs      # GetConcatRefLen() = binRefIndex - 1
+        enc.packed = packed.ctypes.data_as(C.POINTER(C.c_uint8))
+        enc.contigs = C.cast(ctg, type(enc.contigs))
+        lib.ngm_b200_write_enc_ref.argtypes = [C.c_char_p, C.POINTER(_CEncRef)]
+        if lib.ngm_b200_write_enc_ref(str(d / "ref.fa-enc.2.ngm").encode(), C.byref(enc)) != 0:
+            return {"error": "cannot write the encoded reference"}
+        tab, weight, table = sw.cs_export_index()
+        PrefixTableFile.write(str(d / "ref.fa-ht-13-2.3.ngm"), 13, 2, tab, weight, table)
+        del tab, weight, table, packed
+        # FASTQ: fixed-width records, vectorised
+        rd = batch.reads[:n_sample, :L].cpu().numpy()
+        rec = np.empty((n_sample, 10 + L + 3 + L + 1), np.uint8)
+        names = np.char.zfill(np.arange(n_sample).astype("S8"), 8)
+        rec[:, 0] = ord("@")
+        rec[:, 1:9] = np.frombuffer(names.tobytes(), np.uint8).reshape(n_sample, 8)
+        rec[:, 9] = ord("\n")
+        rec[:, 10:10 + L] = rd
+        rec[:, 10 + L:13 + L] = np.frombuffer(b"\n+\n", np.uint8)
+        rec[:, 13 + L:13 + 2 * L] = ord("I")
+        rec[:, 13 + 2 * L] = ord("\n")
+        (d / "reads.fq").write_bytes(rec.tobytes())
+        (d / "warm.fq").write_bytes(rec[:1000].tobytes())
+        prep_s = time.perf_counter() - t0
+        env = dict(os.environ)
+        ocl = e2e.HERE / "_ref" / "ocl"
+        env["OPENCL_VENDOR_PATH"] = str(ocl / "vendor")
+        env["LD_LIBRARY_PATH"] = str(ocl / "lib") + os.pathsep + env.get("LD_LIBRARY_PATH", "")
+
+        def run(fq, out):
+            t = time.perf_counter()
+            p = subprocess.run([str(e2e.binary("ref")), "-r", str(d / "ref.fa"), "-q", str(d / fq), "-o", str(d / out), "-t", str(threads), "-s", str(sensitivity),
+                                "--no-progress"], env=env, capture_output=True, text=True, cwd=d, timeout=900)
+            wall = time.perf_counter() - t
+            log = p.stdout + p.stderr
+            m = re.search(r"Done \((\d+) reads mapped.*elapsed: ([0-9.]+)s", log)
+            if p.returncode != 0 or m is None:
+                raise RuntimeError("ngm failed: " + log[-600:])
+            return wall, int(m.group(1)), float(m.group(2)), ("Reading encoded reference" in log), ("Reading RefTable" in log or "eading" in log)
+        w0, _, e0, _, _ = run("warm.fq", "warm.sam")            # start-up: index load, OpenCL initialisation, 1000 reads
+        w1, mapped, e1, enc_loaded, _ = run("reads.fq", "out.sam")
+        map_s = max(w1 - w0, 1e-6)
+        return {"value": (n_sample - 1000) / map_s, "unit": "reads/s", "cores": threads, "kind": "reference (unmodified ngm, whole program)",
+                "sample": f"{n_sample} reads of the same workload, `ngm -t {threads} -s {sensitivity}`, warm index (NGM's own cache files: encoded reference + prefix table)",
+                "wall_seconds": w1, "startup_wall_seconds": w0, "ngm_elapsed_seconds": e1, "ngm_startup_elapsed_seconds": e0, "mapped": mapped,
+                "whole_run_reads_per_s_including_startup": n_sample / w1, "encoded_reference_loaded_from_cache": enc_loaded, "prepare_files_seconds": prep_s}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
 
 
 # ---------------------------------------------------------------------------
@@ -543,10 +619,14 @@ def main():
             csp = CsParams(K_MER, K_SKIP, BIN, 1, args.sensitivity, 0.0, 0, 0)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            check(lib.ngm_b200_cs_build_index(ctx, C.byref(csp), contig_arr, args.contigs))
+            if rank == 0 or not distributed:
+                check(lib.ngm_b200_cs_build_index(ctx, C.byref(csp), contig_arr, args.contigs))
             torch.cuda.synchronize()
             build_s = time.perf_counter() - t0
-            info = sw.cs_index_info()
+            t0 = time.perf_counter()
+            info = sharding.broadcast_index_device(sw, csp, dev, src=0)      # rank 0's prefix table goes to every GPU over NCCL
+            torch.cuda.synchronize()
+            index_bcast_s = time.perf_counter() - t0 if distributed else 0.0
             cap = 3 * n + 1024
             d_cb = torch.empty(n + 1, dtype=torch.int32, device=dev)
             d_cpairs = torch.empty((cap, 16), dtype=torch.uint8, device=dev)
@@ -601,7 +681,7 @@ def main():
             mean_list = info["table_len"] / float(4 ** K_MER)
             alg_bytes_read = n_kmers * 2 * 8 + n_kmers * 2 * mean_list * 4 + L
             cs_info = {"kmer": K_MER, "kmer_skip": K_SKIP, "bin_size": BIN, "sensitivity": args.sensitivity, "max_kfreq": info["max_kfreq"],
-                       "index_positions": info["table_len"], "index_build_seconds": build_s, "index_bytes": 4 * (4 ** K_MER + 1) + 4 * info["table_len"],
+                       "index_positions": info["table_len"], "index_build_seconds": build_s, "index_broadcast_seconds": index_bcast_s, "index_bytes": 4 * (4 ** K_MER + 1) + 4 * info["table_len"],
                        "cs_ms": ms_cs, "cs_reads_per_s": n / (ms_cs * 1e-3), "candidates": int(total_c), "candidates_per_read": total_c / n,
                        "pipeline_step": "set_reads -> cs_search (k-mer vote) -> score all candidates -> top1+MAPQ -> gather -> align+backtrace+CIGAR/MD",
                        "pipeline_ms": ms_pipe, "pipeline_reads_per_s": world * n / (ms_pipe * 1e-3),
@@ -700,6 +780,12 @@ def main():
                     del tab_h, weight_h, table_h, oix
                 except Exception as e:  # noqa: BLE001
                     cs_info["parity_sample"] = {"error": str(e)}
+            # the reference's whole program on the host cores beside the device pipeline, rank 0, single GPU runs only
+            if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.no_ngm and L == READ_LEN and not args.corridor:
+                try:
+                    cs_info["cpu_baseline_ngm"] = run_ngm_whole(sw, ref, batch, min(n, args.ngm_sample), L, qml, args.contigs, args.sensitivity, host_threads, lib)
+                except Exception as e:  # noqa: BLE001
+                    cs_info["cpu_baseline_ngm"] = {"error": str(e)[-400:]}
             # ---- paired-end (BASELINE configs[2] shape, per-GPU shard): the same run with mates in rows 2f / 2f + 1 and
             # ScoreBuffer::top1PE on the device (ngm_b200_dev_select_pairs) between scoring and alignment
             if not args.no_pe:

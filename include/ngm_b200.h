@@ -170,6 +170,8 @@ typedef struct ngm_b200_encref {
  * cookie 0x74656).  Host only (no CUDA call).  Free with ngm_b200_free_enc_ref. */
 int ngm_b200_read_enc_ref(const char *path, ngm_b200_encref *out);
 void ngm_b200_free_enc_ref(ngm_b200_encref *ref);
+/* Write such a file (SequenceProvider.cpp:189-208): NGM started on `<ref>` then loads `<ref>-enc.2.ngm` instead of encoding the FASTA. */
+int ngm_b200_write_enc_ref(const char *path, const ngm_b200_encref *ref);
 /* _SequenceProvider::convert (SequenceProvider.cpp:111-141): concatenated position -> (contig, position).
  * Returns 1, or 0 when the position lies in the 1000-N spacer in front of the next contig (reported as
  * unmapped by NGM). */
@@ -200,6 +202,12 @@ int ngm_b200_cs_index_info(const ngm_b200_ctx *ctx, uint32_t *index_len, uint32_
 /* Copy the device index back in the file's representation (tab: index_len entries, weight: index_len, table: table_len). */
 int ngm_b200_cs_export_index(ngm_b200_ctx *ctx, uint32_t *tab, int8_t *weight, uint32_t *table);
 
+/* Device-to-device forms for multi-GPU start-up (the index is broadcast over NCCL): the sender exports into device buffers
+ * (index_len x uint32, index_len x int8, table_len x uint32 -- sizes from ngm_b200_cs_index_info), the receivers install what arrived.
+ * params->max_kfreq must carry the sender's value.  Enqueued on `stream`; the load synchronises it. */
+int ngm_b200_dev_cs_export_index(ngm_b200_ctx *ctx, void *d_tab, void *d_weight, void *d_table, void *stream);
+int ngm_b200_dev_cs_load_index(ngm_b200_ctx *ctx, const ngm_b200_cs_params *params, const void *d_tab, const void *d_weight, uint32_t index_len,
+		const void *d_table, uint32_t table_len, void *stream);
 /* NGM's prefix-table cache file (CompactPrefixTable::saveToFile / readFromFile, PrefixTable.cpp:819-921). Host only. */
 typedef struct ngm_b200_htfile {
 	uint32_t kmer, kmer_skip, index_len, table_len;

@@ -61,6 +61,29 @@ extern "C" __attribute__((visibility("default"))) int ngm_b200_read_enc_ref(cons
 	return NGM_B200_OK;
 }
 
+// _SequenceProvider::writeEncRefToFile (SequenceProvider.cpp:189-208): the file NGM reads back instead of encoding the FASTA again
+extern "C" __attribute__((visibility("default"))) int ngm_b200_write_enc_ref(const char *path, const ngm_b200_encref *ref) {
+	if (path == nullptr || ref == nullptr || ref->packed == nullptr || (ref->n_contigs && ref->contigs == nullptr)) return NGM_B200_EINVAL;
+	FILE *fp = fopen(path, "wb");
+	if (fp == nullptr) return NGM_B200_EINVAL;
+	const uint32_t cookie = kRefEncCookie, ref_count = ref->n_contigs;
+	const uint64_t bin_ref_index = ref->concat_len + 1, enc_size = ref->packed_bytes;
+	bool ok = fwrite(&cookie, 4, 1, fp) == 1 && fwrite(&ref_count, 4, 1, fp) == 1 && fwrite(&bin_ref_index, 8, 1, fp) == 1 && fwrite(&enc_size, 8, 1, fp) == 1;
+	for (uint32_t i = 0; ok && i < ref_count; ++i) {
+		DiskRefIdx d;
+		memset(&d, 0, sizeof(d));
+		d.SeqId = i;
+		d.SeqStart = ref->contigs[i].start;
+		d.SeqLen = ref->contigs[i].length;
+		d.NameLen = ref->contigs[i].name_len > 100 ? 100 : ref->contigs[i].name_len;
+		memcpy(d.name, ref->contigs[i].name, 100);
+		ok = fwrite(&d, sizeof(d), 1, fp) == 1;
+	}
+	if (ok) ok = fwrite(ref->packed, 1, enc_size, fp) == enc_size;
+	ok = fclose(fp) == 0 && ok;
+	return ok ? NGM_B200_OK : NGM_B200_EINVAL;
+}
+
 extern "C" __attribute__((visibility("default"))) void ngm_b200_free_enc_ref(ngm_b200_encref *ref) {
 	if (ref == nullptr) return;
 	free(ref->packed);

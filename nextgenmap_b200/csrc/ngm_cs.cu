@@ -343,6 +343,46 @@ int ngm_b200_cs_load_index(ngm_b200_ctx *c, const ngm_b200_cs_params *params, co
 	return finish_index(c, cs, s1, s2);
 }
 
+// device-to-device forms: what a rank does with the prefix table it received over NCCL (the index is broadcast at start-up)
+int ngm_b200_dev_cs_export_index(ngm_b200_ctx *c, void *d_tab, void *d_weight, void *d_table, void *stream) {
+	if (c == nullptr || c->cs == nullptr || !c->cs->ready) return fail(NGM_B200_ESTATE, "no candidate-search index");
+	if (d_tab == nullptr || d_weight == nullptr || (d_table == nullptr && c->cs->table_len)) return fail(NGM_B200_EINVAL, "NULL argument");
+	CU(cudaSetDevice(c->device));
+	CsState *cs = c->cs;
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	const uint32_t NP = cs->n_prefix;
+	cs_export_tab_kernel<<<(NP + 1 + 255) / 256, 256, 0, st>>>(cs->d_tabu.as<uint32_t>(), NP, static_cast<uint32_t *>(d_tab));
+	c->launches += 1;
+	CU(cudaMemcpyAsync(d_weight, cs->d_weight.p, (size_t) NP + 1, cudaMemcpyDeviceToDevice, st));
+	if (cs->table_len) CU(cudaMemcpyAsync(d_table, cs->d_table.p, (size_t) cs->table_len * 4, cudaMemcpyDeviceToDevice, st));
+	CU(cudaGetLastError());
+	return NGM_B200_OK;
+}
+
+int ngm_b200_dev_cs_load_index(ngm_b200_ctx *c, const ngm_b200_cs_params *params, const void *d_tab, const void *d_weight, uint32_t index_len,
+		const void *d_table, uint32_t table_len, void *stream) {
+	if (c == nullptr || d_tab == nullptr || d_weight == nullptr || (d_table == nullptr && table_len)) return fail(NGM_B200_EINVAL, "NULL argument");
+	int rc = check_params(params);
+	if (rc) return rc;
+	if (params->max_kfreq <= 0) return fail(NGM_B200_EINVAL, "the device form takes max_kfreq from the sender (ngm_b200_cs_index_info)");
+	const uint32_t NP = 1u << (2 * params->kmer);
+	if (index_len != NP + 1) return fail(NGM_B200_EINVAL, "index length %u does not belong to kmer %d", index_len, params->kmer);
+	CU(cudaSetDevice(c->device));
+	CsState *cs = fresh_state(c, params);
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	CU(cs->d_weight.ensure((size_t) index_len));
+	CU(cs->d_tabu.ensure((size_t) index_len * 4));
+	CU(cs->d_table.ensure((size_t) table_len * 4 + 4));
+	CU(cudaMemcpyAsync(cs->d_weight.p, d_weight, (size_t) index_len, cudaMemcpyDeviceToDevice, st));
+	if (table_len) CU(cudaMemcpyAsync(cs->d_table.p, d_table, (size_t) table_len * 4, cudaMemcpyDeviceToDevice, st));
+	cs_tabu_from_file_kernel<<<(NP + 1 + 255) / 256, 256, 0, st>>>(static_cast<const uint32_t *>(d_tab), cs->d_weight.as<int8_t>(), NP, cs->d_tabu.as<uint32_t>());
+	c->launches += 1;
+	CU(cudaStreamSynchronize(st));
+	CU(cudaGetLastError());
+	cs->table_len = table_len;
+	return finish_index(c, cs, 0, 0);                              // (max_kfreq is given: the sums are not needed)
+}
+
 int ngm_b200_cs_index_info(const ngm_b200_ctx *c, uint32_t *index_len, uint32_t *table_len, int32_t *max_kfreq) {
 	if (c == nullptr || c->cs == nullptr || !c->cs->ready) return fail(NGM_B200_ESTATE, "no candidate-search index");
 	if (index_len) *index_len = c->cs->n_prefix + 1;

@@ -542,6 +542,12 @@ class EncodedReference:
         ok = self.lib.ngm_b200_convert(C.byref(self.c), concat_pos, C.byref(contig), C.byref(pos))
         return (int(contig.value), int(pos.value)) if ok else None
 
+    def write(self, path: str) -> None:
+        """writeEncRefToFile (SequenceProvider.cpp:189-208)."""
+        self.lib.ngm_b200_write_enc_ref.argtypes = [C.c_char_p, C.POINTER(_CEncRef)]
+        if self.lib.ngm_b200_write_enc_ref(str(path).encode(), C.byref(self.c)) != 0:
+            raise NgmB200Error(f"cannot write {path}")
+
     def close(self):
         if self.c.packed:
             self.lib.ngm_b200_free_enc_ref(C.byref(self.c))

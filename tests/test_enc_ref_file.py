@@ -39,6 +39,8 @@ def test_reader_matches_file_written_by_ngm():
         enc = d / "ref.fa-enc.2.ngm"
         assert enc.exists(), p.stdout + p.stderr
         ref = EncodedReference(str(enc))
+        ref.write(str(d / "copy-enc.2.ngm"))                          # ngm_b200_write_enc_ref: the same bytes NGM wrote
+        assert (d / "copy-enc.2.ngm").read_bytes() == enc.read_bytes()
     # layout: 1000 N, contig (+1 N if odd), 1000 N, ...
     expect = b"N" * 1000
     starts = []

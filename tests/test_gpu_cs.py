@@ -197,3 +197,39 @@ def test_sensitivity_estimate_matches_ngm_log_and_oracle(case):
     np.testing.assert_array_equal(mh, mh2)
     ix.close()
     sw.close()
+
+
+def test_device_to_device_index_transfer():
+    """What a rank does with a prefix table that arrived over NCCL: ngm_b200_dev_cs_export_index on the sender, ngm_b200_dev_cs_load_index on the
+    receiver.  The receiver's table and its candidate lists must equal the sender's."""
+    import ctypes as C
+    import torch
+    from nextgenmap_b200.host import CudaSW
+    from nextgenmap_b200.host.cuda_sw import CsParams
+    contigs = cs_cases.make_reference(21)
+    concat, ctg, concat_len = cs_port.layout(contigs)
+    reads = cs_cases.make_reads(22, concat, ctg, 400, 100, 102)
+    a, b = CudaSW(102, 20), CudaSW(102, 20)
+    packed = port.pack_ref(concat)
+    a.set_reference(packed, concat_len)
+    b.set_reference(packed, concat_len)
+    info = a.cs_build_index(ctg, a.cs_params(kmer=12))
+    dev = torch.device("cuda")
+    d_tab = torch.empty(info["index_len"], dtype=torch.int32, device=dev)
+    d_w = torch.empty(info["index_len"], dtype=torch.int8, device=dev)
+    d_t = torch.empty(max(info["table_len"], 1), dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    lib = a.lib
+    lib.ngm_b200_dev_cs_export_index.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ngm_b200_dev_cs_load_index.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+    a._check(lib.ngm_b200_dev_cs_export_index(a.ctx, d_tab.data_ptr(), d_w.data_ptr(), d_t.data_ptr(), st))
+    p = CsParams(12, 2, 2, 1, 0.5, 0.0, info["max_kfreq"], 0)
+    b._check(lib.ngm_b200_dev_cs_load_index(b.ctx, C.byref(p), d_tab.data_ptr(), d_w.data_ptr(), info["index_len"], d_t.data_ptr(), info["table_len"], st))
+    assert b.cs_index_info() == info
+    for x, y in zip(a.cs_export_index(), b.cs_export_index()):
+        np.testing.assert_array_equal(x, y)
+    ra, rb = a.cs_search(reads), b.cs_search(reads)
+    for x, y in zip(ra, rb):
+        np.testing.assert_array_equal(x, y)
+    a.close()
+    b.close()

@@ -19,6 +19,12 @@ def _worker(rank, world, port, out):
         packed = full.clone() if rank == 0 else torch.empty(0, dtype=torch.uint8)
         packed, concat_len = sharding.broadcast_reference(packed, 10001 if rank == 0 else 0, src=0)
         assert concat_len == 10001 and torch.equal(packed, full)
+        # the prefix table travels the same way (rank 0 read it from NGM's cache file / exported it from its device)
+        tab = rng.integers(0, 1 << 31, 1025, dtype=np.uint32)
+        weight = rng.integers(-5, 100, 1025).astype(np.int8)
+        table = rng.integers(0, 1 << 32, 7777, dtype=np.uint64).astype(np.uint32)
+        got = sharding.broadcast_index((tab, weight, table) if rank == 0 else None, "cpu", src=0)
+        assert all(np.array_equal(g, w) and g.dtype == w.dtype for g, w in zip(got, (tab, weight, table)))
         n_reads = 1001
         lo, hi = sharding.shard_range(n_reads, rank, world)
         # every rank "maps" its shard: pretend reads with an index divisible by 7 stay unmapped
