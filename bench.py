@@ -515,6 +515,9 @@ def main():
     d_scores_all = torch.empty(max(npairs, 1), dtype=torch.float32, device=dev)
     d_best1 = torch.empty(n, dtype=torch.int32, device=dev)
     d_mapq1 = torch.empty(n, dtype=torch.int32, device=dev)
+    lib.ngm_b200_dev_set_reads_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    ms_expand = time_call(lambda: check(lib.ngm_b200_dev_set_reads_packed(ctx, d_packed.data_ptr(), n, row_bytes, d_len.data_ptr(),
+                                                                       d_exc.data_ptr() if d_exc is not None else None, len(exc_np), st)))
     ms_pack = time_call(lambda: check(lib.ngm_b200_dev_set_reads(ctx, batch.reads.data_ptr(), n, qml, st)))
     ms_score = time_call(lambda: check(lib.ngm_b200_dev_score_pairs(ctx, MODE_LOCAL, npairs, batch.pairs.data_ptr(), d_scores_all.data_ptr(), st)))
     check(lib.ngm_b200_dev_select_top1(ctx, n, batch.cand_begin.data_ptr(), d_scores_all.data_ptr(), d_best1.data_ptr(), d_mapq1.data_ptr(), st))
@@ -1038,7 +1041,7 @@ def main():
                          "sm_count": sm_count, "sm_mhz_under_load": sm_mhz,
                          "definition": f"cells = L x corridor = {CELLS_PER_PAIR} per pair; peak = measured VIADDMNMX.S16x2 thread-instructions/s x 2 cells / (4 | 5) ALU "
                                        "instructions per cell pair; the survey's model (SMs x 128 lanes x max clock / 5 instr per cell, x2) is kept beside it"},
-        "kernel_ms": {"set_reads_ascii": ms_pack, "score_all_pairs": ms_score, "score_in_step": ms_score_step, "align_launch_sets": ms_align, "align_forward": ms_fwd,
+        "kernel_ms": {"set_reads_packed2": ms_expand, "set_reads_ascii": ms_pack, "score_all_pairs": ms_score, "score_in_step": ms_score_step, "align_launch_sets": ms_align, "align_forward": ms_fwd,
                       "align_backtrace_format": ms_bt, "align_without_known_scores": ms_align_unscored, "launch_sets": launch_sets,
                       "pairs_scored_in_step": multi_pairs, "score_share": ms_score_step / (ms_max / args.steps), "align_share": ms_align / (ms_max / args.steps),
                       "classic_calls_equal_batch": classic_equal, "pack_reads_host_seconds": pack_host_s},

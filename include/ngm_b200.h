@@ -245,7 +245,11 @@ int ngm_b200_cs_exact_reasons(const ngm_b200_ctx *ctx, uint32_t *out, int n);
 
 /* -- device-pointer entry points (resident pipelines, bench.py `value`) --- */
 /* All pointers are device pointers on ctx's device; work is enqueued on `stream`
- * (a cudaStream_t passed as void*) and NOT synchronised.  d_pairs as above;
+ * (a cudaStream_t passed as void*) and NOT synchronised.
+ * A CONTEXT IS SINGLE-STREAM AND SINGLE-THREAD: every entry point writes per-context scratch (resolved pairs, pointer matrices, op
+ * stacks, candidate-search heaps, the paired selector's state) and reads the read batch installed last.  Calls on one context must all
+ * use the same stream and must not overlap in time; concurrency comes from several contexts -- ngm_b200_create_shared gives each host
+ * thread / stream its own context over one resident reference, which is what ngm_b200_run_batch does internally with its lanes.  d_pairs as above;
  * d_scores: n floats; d_recs: n records; d_strings/d_str_cursor: heap + 1 uint32 cursor
  * (zeroed by the caller before the call). */
 int ngm_b200_dev_set_reference(ngm_b200_ctx *ctx, const void *d_packed, uint64_t concat_len, void *stream);
@@ -447,7 +451,10 @@ int ngm_b200_run_batch(ngm_b200_ctx *ctx, const ngm_b200_batch_in *in, ngm_b200_
 /* The same with every pointer of `in` / `out` on the device: one sub-batch, enqueued on `stream`, not synchronised (resident
  * pipelines; bench.py `value`).  out->str_used is not written; out->d_str_cursor receives the bytes used. */
 int ngm_b200_dev_run_batch(ngm_b200_ctx *ctx, const ngm_b200_batch_in *in, ngm_b200_batch_out *out, void *stream);
-/* Lanes (1..8, default 3) and reads per sub-batch (default 1 << 20) of ngm_b200_run_batch / ngm_b200_map_batch. */
+/* ngm_b200_dev_set_reads for PACKED2 rows (device pointers; see the formats above): installs the batch for the descriptor entry points. */
+int ngm_b200_dev_set_reads_packed(ngm_b200_ctx *ctx, const void *d_packed, int n_reads, int stride, const void *d_read_len, const void *d_exceptions,
+		uint32_t n_exceptions, void *stream);
+/* Lanes (1..8, default 4) and reads per sub-batch (default 1 << 19) of ngm_b200_run_batch / ngm_b200_map_batch. */
 int ngm_b200_set_pipeline(ngm_b200_ctx *ctx, int lanes, int sub_batch_reads);
 /* "strata" for single-end runs (ScoreBuffer::top1SE, ScoreBuffer.cpp:259-276): a read with several equally best candidates is reported
  * unmapped (best_pair -1, mapq 0).  Applies to ngm_b200_dev_select_top1[_ex], ngm_b200_run_batch and ngm_b200_map_batch. */

@@ -750,7 +750,7 @@ static int resolve_pairs(ngm_b200_ctx *c, const void *d_pairs_user, int n, cudaS
 	if (!c->have_ref || c->n_reads == 0) return fail(NGM_B200_ESTATE, "set_reference and set_reads must precede descriptor calls");
 	CU(c->d_rpairs.ensure((size_t) n * sizeof(PairDesc)));
 	resolve_pairs_kernel<<<(n + 255) / 256, 256, 0, st>>>(static_cast<const ngm_b200_pair *>(d_pairs_user), c->d_rpairs.as<PairDesc>(), n,
-			(unsigned long long) c->concat_len, (unsigned long long) c->n_region_nib, c->d_rrlen.as<uint16_t>());
+			(unsigned long long) c->concat_len, (unsigned long long) c->n_region_nib, c->d_rrlen.as<uint16_t>(), (unsigned int) c->n_reads);
 	c->launches += 1;
 	CU(cudaGetLastError());
 	return NGM_B200_OK;

@@ -316,6 +316,18 @@ int ngm_b200_cs_load_index(ngm_b200_ctx *c, const ngm_b200_cs_params *params, co
 	if (rc) return rc;
 	const uint32_t NP = 1u << (2 * params->kmer);
 	if (index_len != NP + 1) return fail(NGM_B200_EINVAL, "index length %u does not belong to kmer %d", index_len, params->kmer);
+	// a stale or damaged cache file must fail here, not as out-of-bounds reads in the search kernels: offsets (1-based in the file,
+	// PrefixTable.cpp:436-498) non-decreasing and ending at table_len, positions inside the reference this context holds
+	if (tab[0] < 1) return fail(NGM_B200_EINVAL, "prefix table: the first offset must be 1 (got %u)", tab[0]);
+	for (uint32_t j = 0; j < NP; ++j)
+		if (tab[j + 1] < tab[j]) return fail(NGM_B200_EINVAL, "prefix table: offsets decrease at k-mer %u", j);
+	if (tab[NP] - 1u != table_len) return fail(NGM_B200_EINVAL, "prefix table: the offsets end at %u, the table holds %u positions", tab[NP] - 1u, table_len);
+	if (c->have_ref) {
+		uint32_t top = 0;
+		for (uint32_t i = 0; i < table_len; ++i) top = std::max(top, table[i]);
+		if ((uint64_t) top >= c->concat_len) return fail(NGM_B200_EINVAL, "prefix table: position %u lies outside the reference (%llu bases): built for another reference?",
+				top, (unsigned long long) c->concat_len);
+	}
 	CU(cudaSetDevice(c->device));
 	CsState *cs = fresh_state(c, params);
 	cudaStream_t st = c->stream;

@@ -23,6 +23,19 @@ struct DevBuf {
 	void *p = nullptr;
 	size_t cap = 0;
 	bool borrowed = false;     // alias of another context's buffer (lanes share the reference and the index): never freed or resized here
+	DevBuf() = default;
+	DevBuf(const DevBuf &) = delete;
+	DevBuf &operator=(const DevBuf &) = delete;
+	DevBuf(DevBuf &&o) noexcept : p(o.p), cap(o.cap), borrowed(o.borrowed) { o.p = nullptr; o.cap = 0; o.borrowed = false; }
+	DevBuf &operator=(DevBuf &&o) noexcept {
+		if (this != &o) {
+			release();
+			p = o.p; cap = o.cap; borrowed = o.borrowed;
+			o.p = nullptr; o.cap = 0; o.borrowed = false;
+		}
+		return *this;
+	}
+	~DevBuf() { release(); }   // temporaries of the entry points are freed on every early return (CU()), too
 	void borrow(const DevBuf &o) {
 		release();
 		p = o.p;
@@ -52,6 +65,10 @@ struct DevBuf {
 struct HostBuf {   // pinned
 	void *p = nullptr;
 	size_t cap = 0;
+	HostBuf() = default;
+	HostBuf(const HostBuf &) = delete;
+	HostBuf &operator=(const HostBuf &) = delete;
+	~HostBuf() { release(); }
 	cudaError_t ensure(size_t bytes) {
 		if (bytes <= cap) return cudaSuccess;
 		if (p) cudaFreeHost(p);

@@ -263,15 +263,15 @@ __global__ void transcode_ref_kernel(const uint8_t *__restrict__ packed, unsigne
 // resident reference; starts >= concat_len (incl. the unsigned underflow of
 // loc - corridor/2) select the all-'N' region (ScoreBuffer.cpp:113-118).
 __global__ void resolve_pairs_kernel(const ngm_b200_pair *__restrict__ in, PairDesc *__restrict__ out, int n, unsigned long long concat_len,
-		unsigned long long n_region_nib, const uint16_t *__restrict__ rlen) {
+		unsigned long long n_region_nib, const uint16_t *__restrict__ rlen, unsigned int n_reads) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const ngm_b200_pair p = in[i];
 	PairDesc d;
 	d.win_nib = p.window_start < concat_len ? p.window_start : n_region_nib;
-	d.read_idx = p.read_index;
+	d.read_idx = p.read_index < n_reads ? p.read_index : 0u;
 	d.flags = p.flags & (PF_REVERSE | PF_DIR | PF_INACTIVE);
-	if (rlen[p.read_index] == 0) d.flags |= PF_INACTIVE;      // an empty read is its own quad leader
+	if (p.read_index >= n_reads || rlen[p.read_index] == 0) d.flags |= PF_INACTIVE;      // an empty read is its own quad leader; a row outside the batch is skipped
 	out[i] = d;
 }
 

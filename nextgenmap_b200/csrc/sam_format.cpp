@@ -8,6 +8,7 @@
 // (src/writer/SAMWriter.cpp:98-228,230-310,312-365).  topn 1, no bs-mapping, no hard / silent clipping of SEQ, no read group.
 // Lines come out in read order (mates: second mate's line first, like DoWritePair); NGM's own order depends on its thread timing.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -328,20 +329,31 @@ extern "C" __attribute__((visibility("default"))) int ngm_b200_format_sam(const 
 	const bool multi = b.topn > 1;
 	if (multi && (paired || b.sel == nullptr || b.n_sel == nullptr)) return NGM_B200_EINVAL;      // several alignments per read: single-end only, like the reference
 	if (paired && (b.n_reads & 1)) return NGM_B200_EINVAL;
+	// a mapped read dereferences its candidate, its score and its strings: refuse NULL arrays as soon as any read selects one
+	if (b.pairs == nullptr || b.scores == nullptr || b.strings == nullptr) {
+		for (int r = 0; r < b.n_reads; ++r)
+			if (multi ? b.n_sel[r] > 0 : b.best_pair[r] >= 0) return NGM_B200_EINVAL;
+	}
+	try {
 	const int units = paired ? b.n_reads / 2 : b.n_reads;
 	int threads = opts->threads > 0 ? opts->threads : (int) std::thread::hardware_concurrency();
 	threads = std::max(1, std::min(threads, std::max(1, units / 256)));
 	std::vector<std::string> parts((size_t) threads);
 	const Job job = { ref, opts, batch };
+	std::atomic<int> failed(0);                                    // an allocation failure inside a worker must not reach std::terminate
 	auto work = [&](int t) {
-		const int lo = (int) ((long long) units * t / threads), hi = (int) ((long long) units * (t + 1) / threads);
-		std::string &s = parts[(size_t) t];
-		s.reserve((size_t) (hi - lo) * (paired ? 2 : 1) * (size_t) (2 * b.stride + 160));
-		std::vector<char> scratch(4096);
-		for (int u = lo; u < hi; ++u) {
-			if (paired) fragment(job, u, s, scratch);
-			else if (multi) single_topn(job, u, s, scratch);
-			else single(job, u, s, scratch);
+		try {
+			const int lo = (int) ((long long) units * t / threads), hi = (int) ((long long) units * (t + 1) / threads);
+			std::string &s = parts[(size_t) t];
+			s.reserve((size_t) (hi - lo) * (paired ? 2 : 1) * (size_t) (2 * b.stride + 160));
+			std::vector<char> scratch(4096);
+			for (int u = lo; u < hi; ++u) {
+				if (paired) fragment(job, u, s, scratch);
+				else if (multi) single_topn(job, u, s, scratch);
+				else single(job, u, s, scratch);
+			}
+		} catch (...) {
+			failed.store(1);
 		}
 	};
 	auto run_all = [&](auto fn) {
@@ -354,6 +366,7 @@ extern "C" __attribute__((visibility("default"))) int ngm_b200_format_sam(const 
 		}
 	};
 	run_all(work);
+	if (failed.load()) return NGM_B200_EINVAL;
 	size_t total = 0;
 	std::vector<size_t> at((size_t) threads);
 	for (int t = 0; t < threads; ++t) {
@@ -364,4 +377,7 @@ extern "C" __attribute__((visibility("default"))) int ngm_b200_format_sam(const 
 	if (total > out_capacity) return NGM_B200_ERANGE;
 	run_all([&](int t) { memcpy(out + at[(size_t) t], parts[(size_t) t].data(), parts[(size_t) t].size()); });      // every thread places (and first-touches) its own part
 	return b.n_reads;
+	} catch (...) {                                                 // std::bad_alloc / std::system_error: no C++ exception crosses the C ABI
+		return NGM_B200_EINVAL;
+	}
 }
