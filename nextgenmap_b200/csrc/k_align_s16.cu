@@ -12,11 +12,11 @@ cudaError_t launch_align_s16(int capacity, int mode, const AlignArgs &a, cudaStr
 	if (a.n <= 0) return cudaSuccess;
 	const int threads = (a.n + 1) / 2;
 	const dim3 block(128), grid((threads + 127) / 128);
-	bool launched = false;
+	bool launched = a.phase == 2;
 	// second-generation forward pass (ngm_align_s16v2.cuh): narrow local bands and every end-free band.  NGM_B200_FWD=1 keeps the
 	// first-generation kernel (A/B measurements, tests of both).
 	static const bool use_v1 = [] { const char *e = getenv("NGM_B200_FWD"); return e != nullptr && atoi(e) == 1; }();
-	if (!use_v1) {
+	if (!use_v1 && !launched) {
 #define X(W, LO) \
 		if (capacity == W && !launched) { \
 			if constexpr (W <= kAlignS16MaxLocal) { \
@@ -25,14 +25,14 @@ cudaError_t launch_align_s16(int capacity, int mode, const AlignArgs &a, cudaStr
 					static const cudaError_t attr = cudaFuncSetAttribute(align_s16_fwd2_kernel<W, LO, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
 					if (attr != cudaSuccess) return attr; \
 					align_s16_fwd2_kernel<W, LO, 0><<<grid, block, smem, st>>>(a.P, a.pairs, a.n, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, \
-							a.ptr_scratch, a.stride, a.best_scratch); \
+							a.ptr_scratch, a.stride, a.best_scratch, a.range, a.range_m); \
 					launched = true; \
 				} \
 			} \
 			if constexpr (W <= kAlignS16MaxEndFree) { \
 				if (mode == 1) { \
 					align_s16_fwd2_kernel<W, LO, 1><<<grid, block, 0, st>>>(a.P, a.pairs, a.n, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, \
-							a.ptr_scratch, a.stride, a.best_scratch); \
+							a.ptr_scratch, a.stride, a.best_scratch, a.range, a.range_m); \
 					launched = true; \
 				} \
 			} \
@@ -68,14 +68,17 @@ cudaError_t launch_align_s16(int capacity, int mode, const AlignArgs &a, cudaStr
 	if (!launched) return cudaErrorInvalidValue;
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return e;
+	if (a.phase == 1) return cudaSuccess;
 	if (a.ev_mid != nullptr) cudaEventRecord(a.ev_mid, st);
-	const dim3 b2(256), g2((a.n + 255) / 256);
+	const int items = a.phase == 2 ? a.n_items : a.n;
+	const int ops_stride = a.ops_stride > 0 ? a.ops_stride : a.stride;
+	const dim3 b2(256), g2((items + 255) / 256);
 	if (mode == 0)
-		backtrace_format_kernel<0><<<g2, b2, 0, st>>>(a.P, a.pairs, a.n, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, a.ptr_scratch, capacity,
-				a.best_scratch, a.ops_scratch, a.stride, a.ops_cap, a.recs, a.strings, a.str_cap, a.cursor, a.out_best);
+		backtrace_format_kernel<0><<<g2, b2, 0, st>>>(a.P, a.pairs, items, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, a.ptr_scratch, capacity,
+				a.best_scratch, a.ops_scratch, a.stride, a.ops_cap, a.recs, a.strings, a.str_cap, a.cursor, a.out_best, a.slot_of, a.range, ops_stride);
 	else
-		backtrace_format_kernel<1><<<g2, b2, 0, st>>>(a.P, a.pairs, a.n, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, a.ptr_scratch, capacity,
-				a.best_scratch, a.ops_scratch, a.stride, a.ops_cap, a.recs, a.strings, a.str_cap, a.cursor, a.out_best);
+		backtrace_format_kernel<1><<<g2, b2, 0, st>>>(a.P, a.pairs, items, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, a.ptr_scratch, capacity,
+				a.best_scratch, a.ops_scratch, a.stride, a.ops_cap, a.recs, a.strings, a.str_cap, a.cursor, a.out_best, a.slot_of, a.range, ops_stride);
 	return cudaGetLastError();
 }
 

@@ -447,34 +447,40 @@ __global__ void __launch_bounds__(256) backtrace_format_kernel(const __grid_cons
 		const uint32_t *__restrict__ reads_fwd, const uint32_t *__restrict__ reads_rev, const uint16_t *__restrict__ rlen,
 		const uint32_t *__restrict__ ref4, const uint32_t *__restrict__ ptr_scratch, int capacity, const int4 *__restrict__ best_in,
 		uint16_t *__restrict__ ops_scratch, int stride, int ops_cap, ngm_b200_align_rec *__restrict__ recs, char *__restrict__ strings,
-		uint32_t str_cap, uint32_t *__restrict__ cursor, float *__restrict__ out_best) {
+		uint32_t str_cap, uint32_t *__restrict__ cursor, float *__restrict__ out_best, const int *__restrict__ slot_of,
+		const int *__restrict__ range, int ops_stride) {
 	__shared__ uint2 s_lut[16];
 	__shared__ uint32_t s_ring[kRing][256];
 	if (threadIdx.x < 16) s_lut[threadIdx.x] = P.lut[threadIdx.x];
 	__syncthreads();
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	const bool valid = idx < n;
-	const int id = valid ? idx : 0;
+	// slot_of != nullptr: thread idx writes the record of item idx (a read of the chunk) from the forward pass's slot slot_of[idx]
+	// (-1: nothing to align); the pair list starts at pairs[range[0]].  Otherwise item idx IS slot idx.
+	const bool in_range = idx < n;
+	const int slot = in_range ? (slot_of != nullptr ? slot_of[idx] : idx) : -1;
+	const bool valid = slot >= 0;
+	const int id = valid ? slot : 0;
+	if (range != nullptr) pairs += range[0];
 	PairCtx c;
 	uint32_t flags;
 	const bool active = load_pair(P, pairs, id, reads_fwd, reads_rev, rlen, ref4, c, flags);
 	// the forward pass's maximum is the pair's BatchScore result in this mode (oclSW / oclSW_Global compute the same recurrence)
-	if (out_best != nullptr && valid) out_best[idx] = active ? (float) best_in[id].z : (MODE == 0 ? -1.0f : (float) kEndFreeMin);
+	if (out_best != nullptr && in_range) out_best[idx] = active ? (float) best_in[id].z : (MODE == 0 ? -1.0f : (float) kEndFreeMin);
 	BandRt geo;
 	geo.cap = capacity;
 	geo.words = (capacity + 7) / 8;
 	geo.tstride = stride >> 1;
 	const size_t row_stride = (size_t) geo.tstride * geo.words;
 	const uint32_t *pbase = ptr_scratch + (size_t) (id >> 1);
-	uint16_t *ops = ops_scratch + id;
+	uint16_t *ops = ops_scratch + (in_range ? idx : 0);            // the op stack belongs to the item, not to the slot
 	TraceOut t;
 	t.ok = 0;
 	t.pos = 0;
 	t.qstart = t.qend = t.sp = 0;
-	if (valid) t = backtrace_tagged<MODE>(P, s_lut, c, pbase, row_stride, geo, id & 1, ops, stride, ops_cap, best_in[id], &s_ring[0][threadIdx.x], 256);
+	if (valid) t = backtrace_tagged<MODE>(P, s_lut, c, pbase, row_stride, geo, id & 1, ops, ops_stride, ops_cap, best_in[id], &s_ring[0][threadIdx.x], 256);
 	FormatOut f;
 	f.cigar_len = f.md_len = f.match = f.mismatch = f.total = f.read_index = 0;
-	if (t.ok) f = format_cigar_md<false>(P, c, ops, stride, t, nullptr, nullptr);
+	if (t.ok) f = format_cigar_md<false>(P, c, ops, ops_stride, t, nullptr, nullptr);
 	const uint32_t need = t.ok ? (uint32_t) (f.cigar_len + f.md_len) : 0u;
 	const int lane = threadIdx.x & 31;
 	uint32_t incl = need;
@@ -487,8 +493,8 @@ __global__ void __launch_bounds__(256) backtrace_format_kernel(const __grid_cons
 	if (lane == 31 && incl) base = atomicAdd(cursor, incl);      // one atomic per warp
 	base = __shfl_sync(0xffffffffu, base, 31);
 	const uint32_t off = base + incl - need;
-	if (!valid) return;
-	if (t.ok && (uint64_t) off + need <= (uint64_t) str_cap) format_cigar_md<true>(P, c, ops, stride, t, strings + off, strings + off + f.cigar_len);
+	if (!in_range) return;
+	if (t.ok && (uint64_t) off + need <= (uint64_t) str_cap) format_cigar_md<true>(P, c, ops, ops_stride, t, strings + off, strings + off + f.cigar_len);
 	ngm_b200_align_rec r;
 	fill_record(r, t, f, off);
 	store_record(recs, idx, r);

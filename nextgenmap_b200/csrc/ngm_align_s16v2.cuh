@@ -83,13 +83,21 @@ __device__ __forceinline__ uint32_t band_max(const uint32_t (&line)[W + 1], uint
 template <int W, int LO, int MODE>
 __global__ void __launch_bounds__(128) align_s16_fwd2_kernel(const __grid_constant__ DevParams P, const PairDesc *__restrict__ pairs, int n,
 		const uint32_t *__restrict__ reads_fwd, const uint32_t *__restrict__ reads_rev, const uint16_t *__restrict__ rlen,
-		const uint32_t *__restrict__ ref4, uint32_t *__restrict__ ptr_scratch, int stride, int4 *__restrict__ best_out) {
+		const uint32_t *__restrict__ ref4, uint32_t *__restrict__ ptr_scratch, int stride, int4 *__restrict__ best_out,
+		const int *__restrict__ range, int range_m) {
 	using G = BandGeom<W>;
 	using T = TagGeom<W>;
 	extern __shared__ uint32_t s_chk[];                           // local mode: [3][W][128] checkpoint words, one column per thread
 	__shared__ uint2 s_lut4[16];
 	if (threadIdx.x < 16) s_lut4[threadIdx.x] = P.lut4[threadIdx.x];
 	__syncthreads();
+	// range != nullptr: the launch covers pairs[range[0] .. range[range_m]) -- offsets that only the device knows (ngm_batch.cu: the
+	// forward pass over every candidate of a chunk of reads); slots, pointer words and best_out stay relative to the chunk
+	if (range != nullptr) {
+		const int base = range[0];
+		n = min(n, range[range_m] - base);
+		pairs += base;
+	}
 	const int t2 = blockIdx.x * blockDim.x + threadIdx.x;        // thread slot: pairs 2*t2, 2*t2 + 1
 	const int ia = 2 * t2;
 	if (ia >= n) return;

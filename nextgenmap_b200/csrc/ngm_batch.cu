@@ -21,6 +21,8 @@
 #include <thread>
 #include <vector>
 
+#include <cub/cub.cuh>
+
 #include "ngm_ctx.h"
 #include "ngm_launch.h"
 
@@ -245,6 +247,176 @@ __global__ void __launch_bounds__(256) batch_finalize_kernel(int n_reads, const 
 	if (num_top != nullptr) num_top[r] = nbest;
 }
 
+// ---- forward pass over EVERY candidate of reads with few candidates ("fwd-all") ---------------------------------------------------
+// Scoring a pair and then aligning the winner runs the DP twice for the winner.  The forward-with-pointers kernel costs ~1.3x the score
+// kernel per pair, so for a read with up to kFwdAllMax candidates it is cheaper to run the forward pass on all of them, pick the winner
+// from the forward maxima (the same numbers BatchScore returns) and backtrace only the winner: 1 candidate 104 instead of 104 (no score
+// pass either way), 2 candidates 208 instead of 264, 4 candidates 416 instead of 424 ALU instructions per row.  Reads with more candidates
+// keep score -> top-1 -> forward of the winner.
+constexpr int kFwdAllMax = 4;
+
+// per read: slots in the forward list (all candidates of a small read, one for the winner of a big one), and the score kernel's work list
+template <int FMT>
+__global__ void __launch_bounds__(256) batch_plan_all_kernel(int n_reads, const int *__restrict__ cb, const void *__restrict__ desc, PairDesc *__restrict__ rp,
+		unsigned long long concat_len, unsigned long long n_region_nib, const uint16_t *__restrict__ rlen, int *__restrict__ fcnt, int *__restrict__ sel,
+		int *__restrict__ n_sel) {
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool valid = r < n_reads;
+	int b = 0, e = 0;
+	if (valid) {
+		b = cb[r];
+		e = cb[r + 1];
+	}
+	const int cnt = e - b;
+	const bool empty = valid && rlen[r] == 0;
+	for (int i = b; i < e; ++i) {
+		unsigned long long ws;
+		uint32_t fl;
+		if (FMT == NGM_B200_DESC_PAIR16) {
+			const ngm_b200_pair p = static_cast<const ngm_b200_pair *>(desc)[i];
+			ws = p.window_start;
+			fl = p.flags;
+		} else {
+			const unsigned long long d = static_cast<const unsigned long long *>(desc)[i];
+			ws = d & 0x00FFFFFFFFFFFFFFull;
+			fl = (uint32_t) (d >> 56);
+		}
+		PairDesc d;
+		d.win_nib = ws < concat_len ? ws : n_region_nib;
+		d.read_idx = (uint32_t) r;
+		d.flags = (fl & (PF_REVERSE | PF_DIR | PF_INACTIVE)) | (empty ? PF_INACTIVE : 0u);
+		rp[i] = d;
+	}
+	if (valid) fcnt[r] = cnt <= kFwdAllMax ? cnt : 1;
+	if (r == n_reads) fcnt[r] = 0;
+	const int want = cnt > kFwdAllMax ? cnt : 0;
+	const int lane = threadIdx.x & 31;
+	int incl = want;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const int v = __shfl_up_sync(0xffffffffu, incl, d);
+		if (lane >= d) incl += v;
+	}
+	int base = 0;
+	if (lane == 31 && incl) base = atomicAdd(n_sel, incl);
+	base = __shfl_sync(0xffffffffu, base, 31);
+	const int at = base + incl - want;
+	for (int i = 0; i < want; ++i) sel[at + i] = b + i;
+}
+
+// top-1 of the reads with more than kFwdAllMax candidates (they were scored), and the forward list: F[fbegin[r] ..) = all candidates of a
+// small read / the winner of a big one
+__global__ void __launch_bounds__(256) batch_fill_fwd_kernel(int n_reads, const int *__restrict__ cb, const PairDesc *__restrict__ rp, const float *__restrict__ scores,
+		const int *__restrict__ fbegin, int strata, PairDesc *__restrict__ F, int *__restrict__ best_pair, int *__restrict__ mapq, int *__restrict__ num_top) {
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const int b = cb[r], e = cb[r + 1], f0 = fbegin[r];
+	if (e - b <= kFwdAllMax) {
+		for (int i = b; i < e; ++i) F[f0 + (i - b)] = rp[i];
+		if (e == b) {
+			best_pair[r] = -1;
+			mapq[r] = 0;
+			if (num_top != nullptr) num_top[r] = 0;
+		}
+		return;
+	}
+	float best = 0.0f, second = 0.0f;
+	int besti = 0, nbest = 0;
+	for (int j = b; j < e; ++j) {
+		const float s = scores[j];
+		if (s > second) {
+			if (s > best) {
+				second = best;
+				best = s;
+				besti = j - b;
+				nbest = 1;
+			} else if (s == best) {
+				++nbest;
+				second = best;
+			} else {
+				second = s;
+			}
+		} else if (s == best) {
+			++nbest;
+		}
+	}
+	int mq = 0;
+	if (best > 0.0f && second >= 0.0f) mq = (int) ceilf(60.0f * (best - second) / best);
+	int bp = b + besti;
+	if (strata && nbest != 1) {
+		bp = -1;
+		mq = 0;
+		nbest = 1;
+	}
+	best_pair[r] = bp;
+	mapq[r] = mq;
+	if (num_top != nullptr) num_top[r] = nbest;
+	PairDesc d;
+	if (bp >= 0) {
+		d = rp[bp];
+	} else {
+		d.win_nib = 0;
+		d.read_idx = (uint32_t) r;
+		d.flags = PF_INACTIVE;
+	}
+	F[f0] = d;
+}
+
+// after the forward pass of a chunk of reads: scores of the small reads' candidates (= forward maxima), their top-1 + MAPQ, and the
+// forward slot every read's alignment is backtraced from
+template <int MODE>
+__global__ void __launch_bounds__(256) batch_pick_kernel(int m, int r0, const int *__restrict__ cb, const int *__restrict__ fbegin, const PairDesc *__restrict__ F,
+		const int4 *__restrict__ best_in, int strata, float *__restrict__ scores, int *__restrict__ best_pair, int *__restrict__ mapq, int *__restrict__ num_top,
+		int *__restrict__ slot_of) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= m) return;
+	const int r = r0 + i;
+	const int b = cb[r], e = cb[r + 1], base = fbegin[r0], f0 = fbegin[r] - base;
+	if (e - b > kFwdAllMax) {
+		slot_of[i] = best_pair[r] >= 0 ? f0 : -1;
+		return;
+	}
+	if (e == b) {
+		slot_of[i] = -1;
+		return;
+	}
+	float best = 0.0f, second = 0.0f;
+	int besti = 0, nbest = 0;
+	for (int j = 0; j < e - b; ++j) {
+		const bool inactive = (F[base + f0 + j].flags & PF_INACTIVE) != 0;
+		const float s = inactive ? (MODE == 0 ? -1.0f : (float) kEndFreeMin) : (float) best_in[f0 + j].z;
+		scores[b + j] = s;
+		if (s > second) {
+			if (s > best) {
+				second = best;
+				best = s;
+				besti = j;
+				nbest = 1;
+			} else if (s == best) {
+				++nbest;
+				second = best;
+			} else {
+				second = s;
+			}
+		} else if (s == best) {
+			++nbest;
+		}
+	}
+	int mq = 0;
+	if (best > 0.0f && second >= 0.0f) mq = (int) ceilf(60.0f * (best - second) / best);
+	int bp = b + besti, sl = f0 + besti;
+	if (strata && nbest != 1) {
+		bp = -1;
+		sl = -1;
+		mq = 0;
+		nbest = 1;
+	}
+	best_pair[r] = bp;
+	mapq[r] = mq;
+	if (num_top != nullptr) num_top[r] = nbest;
+	slot_of[i] = sl;
+}
+
 __global__ void batch_set_u32_kernel(uint32_t *p, uint32_t v, int *q) {
 	if (p != nullptr) *p = v;
 	if (q != nullptr) *q = 0;
@@ -265,13 +437,13 @@ __global__ void __launch_bounds__(256) batch_add_base_kernel(int n, int *__restr
 // ---------------------------------------------------------------------------------------------------------
 struct LaneBuf {
 	DevBuf d_in_reads, d_in_len, d_in_exc, d_cb, d_desc, d_rp, d_pairs16, d_sel, d_nsel, d_scores, d_best, d_mapq, d_ntop, d_pfail, d_wp, d_wscores, d_obest,
-			d_recs, d_strings, d_cursor, d_maxhit;
+			d_recs, d_strings, d_cursor, d_maxhit, d_fcnt, d_fbegin, d_F, d_slot, d_scan_tmp;
 	cudaEvent_t searched = nullptr;                                // ngm_b200_map_batch: candidate search of the lane's sub-batch has finished
 	cudaEvent_t done = nullptr;
 	int pending = -1;                                              // sub-batch whose strings still have to be fetched
 	void release() {
 		DevBuf *all[] = { &d_in_reads, &d_in_len, &d_in_exc, &d_cb, &d_desc, &d_rp, &d_pairs16, &d_sel, &d_nsel, &d_scores, &d_best, &d_mapq, &d_ntop, &d_pfail,
-				&d_wp, &d_wscores, &d_obest, &d_recs, &d_strings, &d_cursor, &d_maxhit };
+				&d_wp, &d_wscores, &d_obest, &d_recs, &d_strings, &d_cursor, &d_maxhit, &d_fcnt, &d_fbegin, &d_F, &d_slot, &d_scan_tmp };
 		for (DevBuf *b : all) b->release();
 		if (done) cudaEventDestroy(done);
 		if (searched) cudaEventDestroy(searched);
@@ -323,6 +495,105 @@ struct DevOut {
 	uint32_t *cursor;               // already holds str_base
 };
 
+// single-end batches on the s16x2 second-generation kernels: forward pass over every candidate of reads with <= kFwdAllMax candidates
+int enqueue_fwd_all(ngm_b200_ctx *c, LaneBuf &L, const DevIn &in, const DevOut &out, int m0, int strata, cudaStream_t st) {
+	const int n = in.n_reads, np = in.n_pairs;
+	CU(L.d_rp.ensure(std::max<size_t>(np, 1) * sizeof(PairDesc)));
+	CU(L.d_F.ensure(std::max<size_t>(np, 1) * sizeof(PairDesc)));
+	CU(L.d_sel.ensure(std::max<size_t>(np, 1) * 4));
+	CU(L.d_nsel.ensure(4));
+	CU(L.d_fcnt.ensure(((size_t) n + 1) * 4));
+	CU(L.d_fbegin.ensure(((size_t) n + 1) * 4));
+	batch_set_u32_kernel<<<1, 1, 0, st>>>(nullptr, 0, L.d_nsel.as<int>());
+	const int blocks_r = (n + 255) / 256, blocks_r1 = (n + 1 + 255) / 256;
+	if (in.desc_format == NGM_B200_DESC_PAIR16)
+		batch_plan_all_kernel<NGM_B200_DESC_PAIR16><<<blocks_r1, 256, 0, st>>>(n, in.cb, in.desc, L.d_rp.as<PairDesc>(), (unsigned long long) c->concat_len,
+				(unsigned long long) c->n_region_nib, c->d_rrlen.as<uint16_t>(), L.d_fcnt.as<int>(), L.d_sel.as<int>(), L.d_nsel.as<int>());
+	else
+		batch_plan_all_kernel<NGM_B200_DESC_U64><<<blocks_r1, 256, 0, st>>>(n, in.cb, in.desc, L.d_rp.as<PairDesc>(), (unsigned long long) c->concat_len,
+				(unsigned long long) c->n_region_nib, c->d_rrlen.as<uint16_t>(), L.d_fcnt.as<int>(), L.d_sel.as<int>(), L.d_nsel.as<int>());
+	size_t tmp_bytes = 0;
+	CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, L.d_fcnt.as<int>(), L.d_fbegin.as<int>(), n + 1, st));
+	CU(L.d_scan_tmp.ensure(tmp_bytes));
+	CU(cub::DeviceScan::ExclusiveSum(L.d_scan_tmp.p, tmp_bytes, L.d_fcnt.as<int>(), L.d_fbegin.as<int>(), n + 1, st));
+	c->launches += 3;
+	CU(cudaGetLastError());
+	const uint32_t *rf = c->d_rfwd.as<uint32_t>(), *rr = c->d_rrev.as<uint32_t>(), *ref4 = c->d_ref4.as<uint32_t>();
+	const uint16_t *rl = c->d_rrlen.as<uint16_t>();
+	if (np > 0) {                                                  // reads with many candidates: BatchScore first (the work list may be empty)
+		ScoreArgs a;
+		a.P = c->dp;
+		a.pairs = L.d_rp.as<PairDesc>();
+		a.n = np;
+		a.reads_fwd = rf;
+		a.reads_rev = rr;
+		a.rlen = rl;
+		a.ref4 = ref4;
+		a.out = out.scores;
+		a.sel = L.d_sel.as<int>();
+		a.n_dev = L.d_nsel.as<int>();
+		int rc = run_score(c, m0, a, st);
+		if (rc) return rc;
+	}
+	batch_fill_fwd_kernel<<<blocks_r, 256, 0, st>>>(n, in.cb, L.d_rp.as<PairDesc>(), out.scores, L.d_fbegin.as<int>(), strata, L.d_F.as<PairDesc>(), out.best_pair,
+			out.mapq, out.num_top);
+	c->launches += 1;
+	CU(cudaGetLastError());
+	// chunks of G reads: at most kFwdAllMax * G forward slots, whose pointer matrix is the launch set's scratch
+	const size_t per_slot = (size_t) c->dp.rows_cap * ptr_words_for(c->capacity) * 4 + sizeof(int4);
+	size_t slots_budget = std::max<size_t>((size_t) kFwdAllMax * 4096, std::min<size_t>((size_t) 4 << 20, ((size_t) 11 << 30) / per_slot));
+	const int G = (int) std::min<size_t>((size_t) n, slots_budget / kFwdAllMax);
+	const int C = (kFwdAllMax * G + 255) / 256 * 256;
+	const int Gpad = (G + 127) / 128 * 128;
+	const int ops_cap = 2 * c->dp.qml + c->dp.corridor + 2;
+	CU(c->d_ptr.ensure((size_t) c->dp.rows_cap * C * ptr_words_for(c->capacity) * sizeof(uint32_t)));
+	CU(c->d_best.ensure((size_t) C * sizeof(int4)));
+	CU(c->d_ops.ensure((size_t) ops_cap * Gpad * sizeof(uint16_t)));
+	CU(L.d_slot.ensure((size_t) Gpad * 4));
+	for (int r0 = 0; r0 < n; r0 += G) {
+		const int m = std::min(G, n - r0);
+		AlignArgs a;
+		a.P = c->dp;
+		a.pairs = L.d_F.as<PairDesc>();
+		a.n = std::min(C, kFwdAllMax * m);
+		a.reads_fwd = rf;
+		a.reads_rev = rr;
+		a.rlen = rl;
+		a.ref4 = ref4;
+		a.ptr_scratch = c->d_ptr.as<uint32_t>();
+		a.ops_scratch = c->d_ops.as<uint16_t>();
+		a.best_scratch = c->d_best.as<int4>();
+		a.known = nullptr;
+		a.stride = C;
+		a.ops_cap = ops_cap;
+		a.recs = out.recs + r0;
+		a.strings = out.strings;
+		a.str_cap = out.str_cap;
+		a.cursor = out.cursor;
+		a.range = L.d_fbegin.as<int>() + r0;
+		a.range_m = m;
+		a.phase = 1;
+		cudaError_t e = launch_align_s16(c->capacity, m0, a, st);
+		if (e != cudaSuccess) return fail(NGM_B200_ECUDA, "forward kernel launch: %s", cudaGetErrorString(e));
+		if (m0 == 0)
+			batch_pick_kernel<0><<<(m + 255) / 256, 256, 0, st>>>(m, r0, in.cb, L.d_fbegin.as<int>(), L.d_F.as<PairDesc>(), c->d_best.as<int4>(), strata, out.scores,
+					out.best_pair, out.mapq, out.num_top, L.d_slot.as<int>());
+		else
+			batch_pick_kernel<1><<<(m + 255) / 256, 256, 0, st>>>(m, r0, in.cb, L.d_fbegin.as<int>(), L.d_F.as<PairDesc>(), c->d_best.as<int4>(), strata, out.scores,
+					out.best_pair, out.mapq, out.num_top, L.d_slot.as<int>());
+		a.phase = 2;
+		a.n = m;
+		a.n_items = m;
+		a.slot_of = L.d_slot.as<int>();
+		a.ops_stride = Gpad;
+		e = launch_align_s16(c->capacity, m0, a, st);
+		if (e != cudaSuccess) return fail(NGM_B200_ECUDA, "backtrace kernel launch: %s", cudaGetErrorString(e));
+		c->launches += 3;
+	}
+	CU(cudaGetLastError());
+	return NGM_B200_OK;
+}
+
 // enqueue score -> select -> align of one sub-batch whose reads are installed in `c` (d_rfwd / d_rrev / d_rrlen)
 int batch_enqueue(ngm_b200_ctx *c, LaneBuf &L, const DevIn &in, const DevOut &out, int strata, cudaStream_t st, cudaEvent_t pe_wait, cudaEvent_t pe_signal) {
 	const int n = in.n_reads, np = in.n_pairs;
@@ -334,6 +605,11 @@ int batch_enqueue(ngm_b200_ctx *c, LaneBuf &L, const DevIn &in, const DevOut &ou
 	const bool wide_local = m0 == 0 && c->align_s16[0] && c->capacity > kAlignS16MaxLocal;
 	static const bool no_fuse = [] { const char *e = getenv("NGM_B200_NO_FUSE"); return e != nullptr && atoi(e) == 1; }();
 	const int fuse = (!in.paired && !wide_local && !no_fuse) ? 1 : 0;
+	// NGM_B200_FWD_ALL=0 keeps score -> top-1 -> forward of the winner for every multi-candidate read (A/B measurements)
+	static const bool fwd_all_on = [] { const char *e = getenv("NGM_B200_FWD_ALL"); return e == nullptr || atoi(e) != 0; }();
+	static const bool fwd_v1 = [] { const char *e = getenv("NGM_B200_FWD"); return e != nullptr && atoi(e) == 1; }();
+	const bool s16_fwd2 = c->align_s16[m0] && c->capacity <= (m0 == 1 ? kAlignS16MaxEndFree : kAlignS16MaxLocal);
+	if (fuse && fwd_all_on && !fwd_v1 && s16_fwd2 && in.cb_base == 0) return enqueue_fwd_all(c, L, in, out, m0, strata, st);
 	CU(L.d_rp.ensure(std::max<size_t>(np, 1) * sizeof(PairDesc)));
 	CU(L.d_wp.ensure((size_t) n * sizeof(PairDesc)));
 	CU(L.d_wscores.ensure((size_t) n * 4));
@@ -512,7 +788,6 @@ int ngm_b200_set_pipeline(ngm_b200_ctx *c, int lanes, int sub_batch_reads) {
 	if (lanes < 1 || lanes > 8) return fail(NGM_B200_EINVAL, "lanes %d not in [1, 8]", lanes);
 	if (sub_batch_reads < 2 || (sub_batch_reads & 1)) return fail(NGM_B200_EINVAL, "sub-batches hold an even number of reads (mates stay together), got %d", sub_batch_reads);
 	if (c->batch == nullptr) c->batch = new BatchState();
-	if ((int) c->batch->lanes.size() > lanes) return fail(NGM_B200_ESTATE, "the pipeline already runs %zu lanes", c->batch->lanes.size());
 	c->batch->n_lanes = lanes;
 	c->batch->sub_batch = sub_batch_reads;
 	return NGM_B200_OK;
@@ -693,7 +968,7 @@ int ngm_b200_run_batch(ngm_b200_ctx *c, const ngm_b200_batch_in *in, ngm_b200_ba
 	CU(B->h_used.ensure((size_t) n_sub * 4));
 	uint32_t *h_used = B->h_used.as<uint32_t>();
 	const size_t desc_bytes = in->desc_format == NGM_B200_DESC_U64 ? 8 : sizeof(ngm_b200_pair);
-	const int n_lanes = std::min((int) B->lanes.size(), std::max(1, n_sub));
+	const int n_lanes = std::min(std::min(B->n_lanes, (int) B->lanes.size()), std::max(1, n_sub));
 	int64_t pe_sum = 0, pe_count = 0;
 	if (in->paired && (rc = ngm_b200_pe_insert_stats(c, &pe_sum, &pe_count)) < 0) return rc;
 	size_t worst_used = 0, total_used = 0;
@@ -830,7 +1105,7 @@ int ngm_b200_map_batch(ngm_b200_ctx *c, const char *reads, int n_reads, int stri
 	BatchState *B = c->batch;
 	const int n = n_reads, SB = B->sub_batch;
 	const int n_sub = (n + SB - 1) / SB;
-	const int n_lanes = std::min((int) B->lanes.size(), std::max(1, n_sub));
+	const int n_lanes = std::min(std::min(B->n_lanes, (int) B->lanes.size()), std::max(1, n_sub));
 	const size_t slot = (res->str_capacity / (size_t) n_sub) & ~(size_t) 15;
 	const size_t cap = res->capacity;
 	const uint32_t lane_cap = (uint32_t) std::max<size_t>(cap, 1);

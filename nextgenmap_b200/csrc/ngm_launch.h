@@ -52,6 +52,13 @@ struct AlignArgs {
 	int4 *best_scratch;          // per alignment {best_read, best_ref, best_score, read_count} (s16 path)
 	const float *known;          // local maxima of the pairs (score kernel output) or nullptr
 	cudaEvent_t ev_mid = nullptr;   // optional: recorded between the forward and the backtrace kernel (ngm_b200_profile)
+	// forward pass over every candidate of a chunk of reads (ngm_batch.cu), s16x2 second-generation kernels only:
+	int phase = 0;                  // 0 = forward + backtrace of pairs[0..n); 1 = forward only; 2 = backtrace only
+	const int *range = nullptr;     // device: the launch covers pairs[range[0] .. range[range_m]) (at most n of them)
+	int range_m = 0;
+	const int *slot_of = nullptr;   // phase 2: item i (one of n_items reads) is aligned from forward slot slot_of[i], -1 = none
+	int n_items = 0;
+	int ops_stride = 0;             // items per op-stack row (0: = stride)
 	float *out_best = nullptr;   // optional, per alignment: the forward pass's maximum = what BatchScore returns for the pair in this mode
 	int stride, ops_cap;
 	ngm_b200_align_rec *recs;
