@@ -30,8 +30,20 @@
 
 namespace ngm {
 
-// One DP row for both halves.  PTR: accumulate + return the pointer words of the row.
-template <int W, int LO, int MODE, bool PTR>
+// Window alignment on the FMA pipe (experiment, -DNGM_FUNNEL_FMA=1): (lo >> s) | (hi << (32 - s)) = mulhi(lo, 2^(32-s)) + hi * 2^(32-s), two
+// FMA-pipe instructions instead of one ALU-pipe SHF; the multiplier comes from a run-time table so that ptxas keeps the multiplies.
+#ifndef NGM_FUNNEL_FMA
+#define NGM_FUNNEL_FMA 0
+#endif
+__device__ __forceinline__ uint32_t funnel_fma(uint32_t lo, uint32_t hi, uint32_t mult) {
+	uint32_t a, d;
+	asm("mul.hi.u32 %0, %1, %2;" : "=r"(a) : "r"(lo), "r"(mult));
+	asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(mult), "r"(a));
+	return d;
+}
+
+// One DP row for both halves.  PTR: accumulate + return the pointer words of the row.  MAYBE0: t may be 0 (no shift).
+template <int W, int LO, int MODE, bool PTR, bool MAYBE0 = true>
 __device__ __forceinline__ void fwd2_row(uint32_t (&line)[W + 1], const uint32_t (&wa)[BandGeom<W>::kWin], const uint32_t (&wb)[BandGeom<W>::kWin],
 		const int t, const uint2 ta, const uint2 tb, const uint32_t gr2, const uint32_t gf2, const uint32_t SENT2,
 		const uint32_t (&keepm)[W - LO + 1], const uint32_t (&fillm)[W - LO + 1], const uint32_t c_four, const uint32_t c_neg1,
@@ -40,8 +52,14 @@ __device__ __forceinline__ void fwd2_row(uint32_t (&line)[W + 1], const uint32_t
 	uint32_t ala[G::kAligned], alb[G::kAligned];
 #pragma unroll
 	for (int k = 0; k < G::kAligned; ++k) {
+#if NGM_FUNNEL_FMA
+		const uint32_t mult = c_four << ((30 - 4 * t) & 31);         // 2^(32 - 4t) for t >= 1 (c_four = 4, a run-time value)
+		ala[k] = (MAYBE0 && t == 0) ? wa[k] : funnel_fma(wa[k], wa[k + 1], mult);
+		alb[k] = (MAYBE0 && t == 0) ? wb[k] : funnel_fma(wb[k], wb[k + 1], mult);
+#else
 		ala[k] = __funnelshift_r(wa[k], wa[k + 1], 4 * t);          // t is a run-time value: the row loop is NOT fully unrolled (see NGM_FWD_ROW_UNROLL)
 		alb[k] = __funnelshift_r(wb[k], wb[k + 1], 4 * t);
+#endif
 	}
 	uint32_t left = SENT2;
 	if (PTR) {
@@ -50,8 +68,18 @@ __device__ __forceinline__ void fwd2_row(uint32_t (&line)[W + 1], const uint32_t
 	}
 #pragma unroll
 	for (int m = 0; m < G::kGroups; ++m) {
+#if NGM_FUNNEL_FMA
+		uint32_t hia = 0, hib = 0;
+		if (m & 1) {                                                   // x >> 16 = mulhi(x, 2^16): FMA pipe
+			asm("mul.hi.u32 %0, %1, %2;" : "=r"(hia) : "r"(ala[m >> 1]), "r"(c_four << 14));
+			asm("mul.hi.u32 %0, %1, %2;" : "=r"(hib) : "r"(alb[m >> 1]), "r"(c_four << 14));
+		}
+		const uint32_t sa = prmt(ta.x, ta.y, (m & 1) ? hia : ala[m >> 1]);
+		const uint32_t sb = prmt(tb.x, tb.y, (m & 1) ? hib : alb[m >> 1]);
+#else
 		const uint32_t sa = prmt(ta.x, ta.y, (m & 1) ? (ala[m >> 1] >> 16) : ala[m >> 1]);
 		const uint32_t sb = prmt(tb.x, tb.y, (m & 1) ? (alb[m >> 1] >> 16) : alb[m >> 1]);
+#endif
 #pragma unroll
 		for (int i = 0; i < 4; ++i) {
 			const int j = 4 * m + i;
@@ -162,6 +190,25 @@ __global__ void __launch_bounds__(128) align_s16_fwd2_kernel(const __grid_consta
 #pragma unroll
 			for (int j = 0; j < W; ++j) *chk_at(cur_buf, j) = line[j];
 		}
+#if NGM_FUNNEL_FMA
+#pragma unroll 1
+		for (int tt = 0; tt < 8; tt += 2) {
+#pragma unroll
+			for (int h2 = 0; h2 < 2; ++h2) {
+				const int t = tt + h2;
+				const int rca = (rda >> (4 * t)) & 7, rcb = (rdb >> (4 * t)) & 7;
+				uint32_t pw[T::kWords];
+				if (h2 == 0) fwd2_row<W, LO, MODE, true, true>(line, wa, wb, t, luta[rca], lutb[rcb], gr2, gf2, SENT2, keepm, fillm, c_four, c_neg1, pw);
+				else fwd2_row<W, LO, MODE, true, false>(line, wa, wb, t, luta[rca], lutb[rcb], gr2, gf2, SENT2, keepm, fillm, c_four, c_neg1, pw);
+#pragma unroll
+				for (int k = 0; k < T::kWords; ++k) prow[(size_t) k * tstride] = pw[k];
+				prow += row_stride;
+				if (MODE == 0) best = band_max<W>(line, best);
+				rc_a += (rca != kCodeNul);
+				rc_b += (rcb != kCodeNul);
+			}
+		}
+#else
 NGM_UNROLL_N(NGM_FWD_ROW_UNROLL)
 		for (int t = 0; t < 8; ++t) {
 			const int rca = (rda >> (4 * t)) & 7, rcb = (rdb >> (4 * t)) & 7;
@@ -174,6 +221,7 @@ NGM_UNROLL_N(NGM_FWD_ROW_UNROLL)
 			rc_a += (rca != kCodeNul);
 			rc_b += (rcb != kCodeNul);
 		}
+#endif
 		if (MODE == 0) {
 			const uint32_t imp = best ^ best_before;
 			if (imp & 0xFFFFu) {
