@@ -330,6 +330,10 @@ typedef struct ngm_b200_map_result {
 	char *strings;              /* string heap of `str_capacity` bytes */
 	size_t str_capacity;
 	size_t str_used;            /* out: bytes needed (> str_capacity: NGM_B200_ERANGE) */
+	/* ngm_b200_se_configure_topn(topn > 1), single-end: recs then holds n x topn records (record r * topn + j = candidate sel[r * topn + j],
+	 * j < n_sel[r]; score -1 beyond), best_pair[r] = sel[r * topn].  Not read for topn 1 (may be NULL). */
+	int32_t *sel;               /* n x topn */
+	int32_t *n_sel;             /* n */
 } ngm_b200_map_result;
 /* CS::RunBatch -> ScoreBuffer::DoRun (BatchScore, top1SE or top1PE) -> AlignmentBuffer::DoRun (BatchAlign) for one batch of reads, from
  * host buffers to host buffers (CS.cpp:340-436, ScoreBuffer.cpp:80-277,365-502, AlignmentBuffer.cpp:64-147).  Needs ngm_b200_set_reference
@@ -443,6 +447,11 @@ typedef struct ngm_b200_batch_out {
 	size_t str_used;            /* out: bytes of CIGAR / MD text.  NGM_B200_ERANGE: a sub-batch needed more than its slot; str_used then holds a
 	                             * sufficient total capacity for a repeat of the call */
 	uint32_t *d_str_cursor;     /* ngm_b200_dev_run_batch only: device word that receives the heap bytes used (dense heap, one sub-batch) */
+	/* ngm_b200_se_configure_topn(topn > 1), single-end batches (ScoreBuffer::topNSE): every candidate is scored, the list sorted, up to topn
+	 * candidates per read aligned.  recs then holds n_reads x topn records (record r * topn + j = candidate sel[r * topn + j], j < n_sel[r];
+	 * score -1 beyond), best_pair[r] = sel[r * topn], mapq / num_top as ngm_b200_dev_select_topn.  Not read for topn 1 (may be NULL). */
+	int32_t *sel;               /* n_reads x topn */
+	int32_t *n_sel;             /* n_reads */
 } ngm_b200_batch_out;
 
 /* Host buffers in, host buffers out; returns n_reads.  For copies that overlap with the kernels the buffers must be page-locked:
@@ -459,6 +468,9 @@ int ngm_b200_set_pipeline(ngm_b200_ctx *ctx, int lanes, int sub_batch_reads);
 /* "strata" for single-end runs (ScoreBuffer::top1SE, ScoreBuffer.cpp:259-276): a read with several equally best candidates is reported
  * unmapped (best_pair -1, mapq 0).  Applies to ngm_b200_dev_select_top1[_ex], ngm_b200_run_batch and ngm_b200_map_batch. */
 int ngm_b200_se_configure(ngm_b200_ctx *ctx, int strata);
+/* "topn" (NGM -n, 1..1000; default 1) of the single-end batches of ngm_b200_run_batch / ngm_b200_dev_run_batch / ngm_b200_map_batch:
+ * > 1 switches them from top1SE to topNSE (ScoreBuffer.cpp:279-330; `strata` as configured above) -- see sel / n_sel of the result structs. */
+int ngm_b200_se_configure_topn(ngm_b200_ctx *ctx, int topn);
 /* Page-locked host memory for the staging buffers (cudaHostAlloc / cudaHostRegister). */
 void *ngm_b200_host_alloc(size_t bytes);
 void ngm_b200_host_free(void *p);
@@ -483,6 +495,10 @@ int ngm_b200_profile_read(ngm_b200_ctx *ctx, float *forward_ms, float *backtrace
  * against the production thread-per-pair kernel by bench.py (`design_ab`).  d_pairs: ngm_b200_pair descriptors as for
  * ngm_b200_dev_score_pairs (set_reference / set_reads first); corridor <= 32, local mode. */
 int ngm_b200_exp_wavefront_score(ngm_b200_ctx *ctx, int n, const void *d_pairs, void *d_scores, void *stream);
+/* MEASUREMENT, not a product path (csrc/exp_issue.cu, scripts/issue_rates.py): issue rates, in thread-level instructions per second, of the
+ * instructions the DP kernels are made of, alone (op_b = -1) and interleaved 1:1 in pairs -- which of them share the integer ALU pipe.
+ * Writes up to `cap` cases, returns their number. */
+int ngm_b200_exp_issue_rates(ngm_b200_ctx *ctx, int cap, int *op_a, int *op_b, double *per_s);
 /* Number of kernels this context has launched since creation (bench.py gpu_launches). */
 uint64_t ngm_b200_launch_count(const ngm_b200_ctx *ctx);
 

@@ -35,6 +35,24 @@ namespace ngm {
 #ifndef NGM_FUNNEL_FMA
 #define NGM_FUNNEL_FMA 0
 #endif
+// The odd nibble groups' `>> 16` alone as IMAD.HI (x >> 16 = mulhi(x, 2^16)): -DNGM_HI16_FMA=1
+#ifndef NGM_HI16_FMA
+#define NGM_HI16_FMA NGM_FUNNEL_FMA
+#endif
+// Offset-binary band (EXPERIMENT, local mode, -DNGM_FWD_OFFSET=1): every band value is kept as true + 0x8000 per half and compared
+// UNSIGNED.  A 32-bit IMAD that adds a negative per-half constant to such a word then ALWAYS carries out of the low half (the stored low
+// half is >= 0x8000 > |4 * gap|), so the carry is a constant that the addend's high half absorbs (c - 0x10000): the up and left candidates
+// become IMADs and the floor of local alignment the third operand of one VIMNMX3.U16x2 -- VIADDMNMX.U16x2 + VIMNMX3.U16x2 + 2 IMAD instead
+// of VIADD.16x2 + 2 x VIADDMNMX.S16x2.  Bit-identical results (all GPU tests pass), but measured SLOWER on B200 (10 M x 150 bp: forward pass
+// 10.42 vs 9.99 ms): scripts/issue_rates.py shows why -- VIADD.16x2 already issues on the FMA pipe, and VIMNMX3 costs the integer pipe the same
+// slot as VIADDMNMX, so the variant only adds FMA-pipe work (profiles/r2_issue_rates.md).  Off by default.
+#ifndef NGM_FWD_OFFSET
+#define NGM_FWD_OFFSET 0
+#endif
+constexpr uint32_t kOfs2 = 0x80008000u;
+// per-half constant c (two's complement) as the addend of an always-carrying 32-bit add
+__device__ __forceinline__ uint32_t carry_addend(int c) { return pack2(c, c) - 0x10000u; }
+
 __device__ __forceinline__ uint32_t funnel_fma(uint32_t lo, uint32_t hi, uint32_t mult) {
 	uint32_t a, d;
 	asm("mul.hi.u32 %0, %1, %2;" : "=r"(a) : "r"(lo), "r"(mult));
@@ -49,6 +67,8 @@ __device__ __forceinline__ void fwd2_row(uint32_t (&line)[W + 1], const uint32_t
 		const uint32_t (&keepm)[W - LO + 1], const uint32_t (&fillm)[W - LO + 1], const uint32_t c_four, const uint32_t c_neg1,
 		uint32_t (&pw)[TagGeom<W>::kWords]) {
 	using G = BandGeom<W>;
+	constexpr bool OFS = MODE == 0 && NGM_FWD_OFFSET != 0;        // gr2 / gf2 then hold carry_addend()s and SENT2 = kOfs2 (see above)
+	const uint32_t c_one = c_four >> 2;
 	uint32_t ala[G::kAligned], alb[G::kAligned];
 #pragma unroll
 	for (int k = 0; k < G::kAligned; ++k) {
@@ -68,7 +88,7 @@ __device__ __forceinline__ void fwd2_row(uint32_t (&line)[W + 1], const uint32_t
 	}
 #pragma unroll
 	for (int m = 0; m < G::kGroups; ++m) {
-#if NGM_FUNNEL_FMA
+#if NGM_HI16_FMA
 		uint32_t hia = 0, hib = 0;
 		if (m & 1) {                                                   // x >> 16 = mulhi(x, 2^16): FMA pipe
 			asm("mul.hi.u32 %0, %1, %2;" : "=r"(hia) : "r"(ala[m >> 1]), "r"(c_four << 14));
@@ -84,11 +104,19 @@ __device__ __forceinline__ void fwd2_row(uint32_t (&line)[W + 1], const uint32_t
 		for (int i = 0; i < 4; ++i) {
 			const int j = 4 * m + i;
 			const uint32_t s2 = i == 0 ? sbyte2<0>(sa, sb) : i == 1 ? sbyte2<1>(sa, sb) : i == 2 ? sbyte2<2>(sa, sb) : sbyte2<3>(sa, sb);
-			const uint32_t d = __vadd2(line[j], s2);
-			const uint32_t u = __viaddmax_s16x2(line[j + 1], gr2, d);
-			uint32_t h = MODE == 0 ? __viaddmax_s16x2_relu(left, gf2, u) : __viaddmax_s16x2(left, gf2, u);
+			uint32_t h;
+			if (OFS) {
+				const uint32_t up = imad_u32(line[j + 1], c_one, gr2);    // FMA pipe
+				const uint32_t lf = imad_u32(left, c_one, gf2);           // FMA pipe
+				const uint32_t u = __viaddmax_u16x2(line[j], s2, up);
+				h = __vimax3_u16x2(u, lf, kOfs2);
+			} else {
+				const uint32_t d = __vadd2(line[j], s2);
+				const uint32_t u = __viaddmax_s16x2(line[j + 1], gr2, d);
+				h = MODE == 0 ? __viaddmax_s16x2_relu(left, gf2, u) : __viaddmax_s16x2(left, gf2, u);
+			}
 			// slots at or beyond the corridor are pinned to the sentinel: one LOP3 with loop-invariant masks instead of compare + select
-			if (j >= LO) h = (h & keepm[j - LO]) | (MODE == 0 ? 0u : fillm[j - LO]);
+			if (j >= LO) h = (h & keepm[j - LO]) | ((MODE == 0 && !OFS) ? 0u : fillm[j - LO]);
 			const uint32_t clean = h & 0xFFFCFFFCu;
 			if (PTR) {
 				const uint32_t tag = imad_u32(clean, c_neg1, h);          // h - clean, FMA pipe
@@ -100,11 +128,11 @@ __device__ __forceinline__ void fwd2_row(uint32_t (&line)[W + 1], const uint32_t
 	}
 }
 
-template <int W>
+template <int W, bool OFS = false>
 __device__ __forceinline__ uint32_t band_max(const uint32_t (&line)[W + 1], uint32_t acc) {
 #pragma unroll
-	for (int j = 0; j + 1 < W; j += 2) acc = __vimax3_s16x2(acc, line[j], line[j + 1]);
-	if (W & 1) acc = __vmaxs2(acc, line[W - 1]);
+	for (int j = 0; j + 1 < W; j += 2) acc = OFS ? __vimax3_u16x2(acc, line[j], line[j + 1]) : __vimax3_s16x2(acc, line[j], line[j + 1]);
+	if (W & 1) acc = OFS ? __vmaxu2(acc, line[W - 1]) : __vmaxs2(acc, line[W - 1]);
 	return acc;
 }
 
@@ -131,14 +159,19 @@ __global__ void __launch_bounds__(128) align_s16_fwd2_kernel(const __grid_consta
 	if (ia >= n) return;
 	const bool vb = ia + 1 < n;
 	const int ib = vb ? ia + 1 : ia;
+	constexpr bool OFS = MODE == 0 && NGM_FWD_OFFSET != 0;
 	constexpr int SENT = MODE == 0 ? 0 : 4 * kEndFreeMinS16;
-	const uint32_t SENT2 = pack2(SENT, SENT);
+	const uint32_t SENT2 = OFS ? kOfs2 : pack2(SENT, SENT);
+	const uint32_t ZERO2 = OFS ? kOfs2 : 0u;                      // a cell value of 0 as stored
+	auto half_lo = [](uint32_t v) { return OFS ? (int) (v & 0xFFFFu) - 0x8000 : (int) (short) (v & 0xFFFFu); };
+	auto half_hi = [](uint32_t v) { return OFS ? (int) (v >> 16) - 0x8000 : (int) (short) (v >> 16); };
 	PairCtx ca, cb;
 	uint32_t fa, fb;
 	const bool act_a = load_pair(P, pairs, ia, reads_fwd, reads_rev, rlen, ref4, ca, fa);
 	const bool act_b = load_pair(P, pairs, ib, reads_fwd, reads_rev, rlen, ref4, cb, fb) && vb;
 	const int corridor = P.corridor;
-	const uint32_t gr2 = pack2(4 * P.gap_read + 1, 4 * P.gap_read + 1), gf2 = pack2(4 * P.gap_ref, 4 * P.gap_ref);
+	const uint32_t gr2 = OFS ? carry_addend(4 * P.gap_read + 1) : pack2(4 * P.gap_read + 1, 4 * P.gap_read + 1);
+	const uint32_t gf2 = OFS ? carry_addend(4 * P.gap_ref) : pack2(4 * P.gap_ref, 4 * P.gap_ref);
 	const uint32_t c_four = P.c_four, c_neg1 = P.c_neg1;
 	const int tstride = stride >> 1;
 	const size_t row_stride = (size_t) tstride * T::kWords;
@@ -148,14 +181,14 @@ __global__ void __launch_bounds__(128) align_s16_fwd2_kernel(const __grid_consta
 
 	uint32_t line[W + 1];
 #pragma unroll
-	for (int j = 0; j <= W; ++j) line[j] = (j < corridor) ? 0u : SENT2;
+	for (int j = 0; j <= W; ++j) line[j] = (j < corridor) ? ZERO2 : SENT2;
 	uint32_t keepm[W - LO + 1], fillm[W - LO + 1];
 #pragma unroll
 	for (int i = 0; i <= W - LO; ++i) {
 		keepm[i] = (LO + i < corridor) ? 0xFFFFFFFFu : 0u;
 		fillm[i] = (LO + i < corridor) ? 0u : SENT2;
 	}
-	uint32_t best = 0;
+	uint32_t best = ZERO2;
 	int rc_a = 0, rc_b = 0;
 	// checkpoint bookkeeping (local mode): per half the buffer, block and row count of the block of its last improvement
 	int own_a = 0, own_b = 0, blk_a = 0, blk_b = 0, rc0_a = 0, rc0_b = 0;
@@ -203,7 +236,7 @@ __global__ void __launch_bounds__(128) align_s16_fwd2_kernel(const __grid_consta
 #pragma unroll
 				for (int k = 0; k < T::kWords; ++k) prow[(size_t) k * tstride] = pw[k];
 				prow += row_stride;
-				if (MODE == 0) best = band_max<W>(line, best);
+				if (MODE == 0) best = band_max<W, OFS>(line, best);
 				rc_a += (rca != kCodeNul);
 				rc_b += (rcb != kCodeNul);
 			}
@@ -217,7 +250,7 @@ NGM_UNROLL_N(NGM_FWD_ROW_UNROLL)
 #pragma unroll
 			for (int k = 0; k < T::kWords; ++k) prow[(size_t) k * tstride] = pw[k];
 			prow += row_stride;
-			if (MODE == 0) best = band_max<W>(line, best);
+			if (MODE == 0) best = band_max<W, OFS>(line, best);
 			rc_a += (rca != kCodeNul);
 			rc_b += (rcb != kCodeNul);
 		}
@@ -247,7 +280,7 @@ NGM_UNROLL_N(NGM_FWD_ROW_UNROLL)
 	ba.read_count = rc_a | ((spec_a & 0x44444444u) ? kSpecialFlag : 0);
 	bb.read_count = rc_b | ((spec_b & 0x44444444u) ? kSpecialFlag : 0);
 	if (MODE == 0) {
-		const int ma = (int) (short) (best & 0xFFFFu), mb = (int) (short) (best >> 16);
+		const int ma = half_lo(best), mb = half_hi(best);
 		// ---- replay: the block of each half's last improvement, from its checkpoint, until the half reaches its maximum ----
 #pragma unroll
 		for (int j = 0; j < W; ++j) line[j] = prmt(*chk_at(own_a, j), *chk_at(own_b, j), 0x7610u);
@@ -266,9 +299,9 @@ NGM_UNROLL_N(NGM_FWD_ROW_UNROLL)
 			const int rca = (rda >> (4 * t)) & 7, rcb = (rdb >> (4 * t)) & 7;
 			uint32_t pw[T::kWords];
 			fwd2_row<W, LO, MODE, false>(line, wa, wb, t, luta[rca], lutb[rcb], gr2, gf2, SENT2, keepm, fillm, c_four, c_neg1, pw);
-			const uint32_t mx = band_max<W>(line, 0u);
-			const bool hit_a = !found_a && (int) (short) (mx & 0xFFFFu) == ma;
-			const bool hit_b = !found_b && (int) (short) (mx >> 16) == mb;
+			const uint32_t mx = band_max<W, OFS>(line, ZERO2);
+			const bool hit_a = !found_a && half_lo(mx) == ma;
+			const bool hit_b = !found_b && half_hi(mx) == mb;
 			// the band of the row in which a half first reaches its maximum goes to a (by now free) checkpoint buffer
 			if (hit_a) {
 #pragma unroll
@@ -289,8 +322,8 @@ NGM_UNROLL_N(NGM_FWD_ROW_UNROLL)
 		bool fa_ = false, fb_ = false;
 #pragma unroll
 		for (int j = 0; j < W; ++j) {
-			const bool ha = !fa_ && j < corridor && (int) (short) (*chk_at(0, j) & 0xFFFFu) == ma;
-			const bool hb = !fb_ && j < corridor && (int) (short) (*chk_at(1, j) >> 16) == mb;
+			const bool ha = !fa_ && j < corridor && half_lo(*chk_at(0, j)) == ma;
+			const bool hb = !fb_ && j < corridor && half_hi(*chk_at(1, j)) == mb;
 			ra = ha ? j : ra;
 			rb = hb ? j : rb;
 			fa_ = fa_ || ha;

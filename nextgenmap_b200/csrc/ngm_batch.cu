@@ -227,6 +227,28 @@ __global__ void __launch_bounds__(256) batch_gather_kernel(int n_reads, const in
 	wscores[r] = s;
 }
 
+// topn > 1 (ScoreBuffer::topNSE): row r * topn + j of the align batch = the j-th selected candidate of read r (inactive beyond n_sel[r])
+__global__ void __launch_bounds__(256) batch_gather_topn_kernel(int n_reads, int topn, const PairDesc *__restrict__ rp, const int *__restrict__ sel,
+		const float *__restrict__ scores, PairDesc *__restrict__ wp, float *__restrict__ wscores, int *__restrict__ best_pair) {
+	const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= (long long) n_reads * topn) return;
+	const int r = (int) (i / topn), j = (int) (i - (long long) r * topn);
+	const int s = sel[i];
+	PairDesc d;
+	float sc = 0.0f;
+	if (s >= 0) {
+		d = rp[s];
+		sc = scores[s];
+	} else {
+		d.win_nib = 0;
+		d.read_idx = (uint32_t) r;
+		d.flags = PF_INACTIVE;
+	}
+	wp[i] = d;
+	wscores[i] = sc;
+	if (j == 0) best_pair[r] = s;
+}
+
 // fused batches: the score of a single-candidate read is the maximum its alignment's forward pass found; then top1SE over that one score
 __global__ void __launch_bounds__(256) batch_finalize_kernel(int n_reads, const int *__restrict__ cb, int cb_base, const float *__restrict__ out_best,
 		int strata, float *__restrict__ scores, int *__restrict__ best_pair, int *__restrict__ mapq, int *__restrict__ num_top) {
@@ -437,13 +459,13 @@ __global__ void __launch_bounds__(256) batch_add_base_kernel(int n, int *__restr
 // ---------------------------------------------------------------------------------------------------------
 struct LaneBuf {
 	DevBuf d_in_reads, d_in_len, d_in_exc, d_cb, d_desc, d_rp, d_pairs16, d_sel, d_nsel, d_scores, d_best, d_mapq, d_ntop, d_pfail, d_wp, d_wscores, d_obest,
-			d_recs, d_strings, d_cursor, d_maxhit, d_fcnt, d_fbegin, d_F, d_slot, d_scan_tmp;
+			d_recs, d_strings, d_cursor, d_maxhit, d_fcnt, d_fbegin, d_F, d_slot, d_scan_tmp, d_tsel, d_tnsel;
 	cudaEvent_t searched = nullptr;                                // ngm_b200_map_batch: candidate search of the lane's sub-batch has finished
 	cudaEvent_t done = nullptr;
 	int pending = -1;                                              // sub-batch whose strings still have to be fetched
 	void release() {
 		DevBuf *all[] = { &d_in_reads, &d_in_len, &d_in_exc, &d_cb, &d_desc, &d_rp, &d_pairs16, &d_sel, &d_nsel, &d_scores, &d_best, &d_mapq, &d_ntop, &d_pfail,
-				&d_wp, &d_wscores, &d_obest, &d_recs, &d_strings, &d_cursor, &d_maxhit, &d_fcnt, &d_fbegin, &d_F, &d_slot, &d_scan_tmp };
+				&d_wp, &d_wscores, &d_obest, &d_recs, &d_strings, &d_cursor, &d_maxhit, &d_fcnt, &d_fbegin, &d_F, &d_slot, &d_scan_tmp, &d_tsel, &d_tnsel };
 		for (DevBuf *b : all) b->release();
 		if (done) cudaEventDestroy(done);
 		if (searched) cudaEventDestroy(searched);
@@ -493,6 +515,8 @@ struct DevOut {
 	char *strings;                  // heap pointer such that strings + offset is valid for offsets in [str_base, str_cap)
 	uint32_t str_cap;
 	uint32_t *cursor;               // already holds str_base
+	int topn = 1;                   // > 1 (single-end): recs holds n_reads x topn records, sel n_reads x topn candidate indices, n_sel n_reads counts
+	int *sel = nullptr, *n_sel = nullptr;
 };
 
 // single-end batches on the s16x2 second-generation kernels: forward pass over every candidate of reads with <= kFwdAllMax candidates
@@ -594,12 +618,53 @@ int enqueue_fwd_all(ngm_b200_ctx *c, LaneBuf &L, const DevIn &in, const DevOut &
 	return NGM_B200_OK;
 }
 
+// single-end batches with topn > 1 (NGM -n / --strata; ScoreBuffer::topNSE, ScoreBuffer.cpp:279-330): BatchScore of every candidate, the
+// sorted selection, BatchAlign of up to topn candidates per read
+int enqueue_topn(ngm_b200_ctx *c, LaneBuf &L, const DevIn &in, const DevOut &out, int m0, int strata, cudaStream_t st) {
+	const int n = in.n_reads, np = in.n_pairs, topn = out.topn;
+	if (in.cb_base != 0) return fail(NGM_B200_EINVAL, "topn batches take candidate offsets relative to the sub-batch");
+	if ((long long) n * topn > 0x7FFFFFFFll) return fail(NGM_B200_EINVAL, "n_reads x topn beyond 31 bits");
+	const size_t items = (size_t) n * topn;
+	CU(L.d_rp.ensure(std::max<size_t>(np, 1) * sizeof(PairDesc)));
+	CU(L.d_wp.ensure(items * sizeof(PairDesc)));
+	CU(L.d_wscores.ensure(items * 4));
+	CU(L.d_nsel.ensure(4));
+	const int blocks_r = (n + 255) / 256;
+	if (in.desc_format == NGM_B200_DESC_PAIR16)
+		batch_plan_kernel<NGM_B200_DESC_PAIR16><<<blocks_r, 256, 0, st>>>(n, in.cb, 0, in.desc, L.d_rp.as<PairDesc>(), nullptr, (unsigned long long) c->concat_len,
+				(unsigned long long) c->n_region_nib, c->d_rrlen.as<uint16_t>(), 0, nullptr, nullptr);
+	else
+		batch_plan_kernel<NGM_B200_DESC_U64><<<blocks_r, 256, 0, st>>>(n, in.cb, 0, in.desc, L.d_rp.as<PairDesc>(), nullptr, (unsigned long long) c->concat_len,
+				(unsigned long long) c->n_region_nib, c->d_rrlen.as<uint16_t>(), 0, nullptr, nullptr);
+	c->launches += 1;
+	CU(cudaGetLastError());
+	const uint32_t *rf = c->d_rfwd.as<uint32_t>(), *rr = c->d_rrev.as<uint32_t>(), *ref4 = c->d_ref4.as<uint32_t>();
+	const uint16_t *rl = c->d_rrlen.as<uint16_t>();
+	if (np > 0) {
+		ScoreArgs a = score_args(c, L.d_rp.as<PairDesc>(), np, rf, rr, rl, ref4, out.scores);
+		int rc = run_score(c, m0, a, st);
+		if (rc) return rc;
+	}
+	int rc = ngm_b200_dev_select_topn(c, n, in.cb, out.scores, (uint32_t) np, topn, strata, out.sel, out.n_sel, out.mapq, out.num_top != nullptr ? out.num_top : L.d_ntop.p, st);
+	if (rc < 0) return rc;
+	batch_gather_topn_kernel<<<(unsigned) ((items + 255) / 256), 256, 0, st>>>(n, topn, L.d_rp.as<PairDesc>(), out.sel, out.scores, L.d_wp.as<PairDesc>(),
+			L.d_wscores.as<float>(), out.best_pair);
+	c->launches += 1;
+	CU(cudaGetLastError());
+	return run_align(c, m0, L.d_wp.as<PairDesc>(), (int) items, rf, rr, rl, ref4, out.recs, out.strings, out.str_cap, out.cursor, st, L.d_wscores.as<float>(), nullptr);
+}
+
 // enqueue score -> select -> align of one sub-batch whose reads are installed in `c` (d_rfwd / d_rrev / d_rrlen)
 int batch_enqueue(ngm_b200_ctx *c, LaneBuf &L, const DevIn &in, const DevOut &out, int strata, cudaStream_t st, cudaEvent_t pe_wait, cudaEvent_t pe_signal) {
 	const int n = in.n_reads, np = in.n_pairs;
 	const int m0 = mode_of(in.mode);
 	if (m0 < 0) return fail(NGM_B200_EINVAL, "unsupported alignment mode %d", in.mode & 0xFF);
 	if (!c->have_ref) return fail(NGM_B200_ESTATE, "set_reference must precede ngm_b200_run_batch");
+	if (out.topn > 1) {
+		if (in.paired) return fail(NGM_B200_EINVAL, "topn %d: paired runs report one alignment per mate (ScoreBuffer.cpp:365-502)", out.topn);
+		if (out.sel == nullptr || out.n_sel == nullptr) return fail(NGM_B200_EINVAL, "topn %d needs the sel / n_sel arrays", out.topn);
+		return enqueue_topn(c, L, in, out, m0, strata, st);
+	}
 	// single-candidate reads skip BatchScore when the alignment kernel of this configuration reports its forward maximum and does not
 	// need the score beforehand (wide local bands locate their best cell by it)
 	const bool wide_local = m0 == 0 && c->align_s16[0] && c->capacity > kAlignS16MaxLocal;
@@ -706,6 +771,7 @@ int borrow_from_root(ngm_b200_ctx *l, ngm_b200_ctx *root) {
 	l->n_region_nib = root->n_region_nib;
 	l->have_ref = root->have_ref;
 	l->se_strata = root->se_strata;
+	l->se_topn = root->se_topn;
 	int rc = cs_share_index(l, root);
 	if (rc) return rc;
 	rc = pe_share_state(l, root);
@@ -796,6 +862,14 @@ int ngm_b200_set_pipeline(ngm_b200_ctx *c, int lanes, int sub_batch_reads) {
 int ngm_b200_se_configure(ngm_b200_ctx *c, int strata) {
 	if (c == nullptr) return fail(NGM_B200_EINVAL, "ctx == NULL");
 	c->se_strata = strata ? 1 : 0;
+	c->epoch += 1;
+	return NGM_B200_OK;
+}
+
+int ngm_b200_se_configure_topn(ngm_b200_ctx *c, int topn) {
+	if (c == nullptr) return fail(NGM_B200_EINVAL, "ctx == NULL");
+	if (topn < 1 || topn > 1000) return fail(NGM_B200_EINVAL, "topn %d not in [1, 1000]", topn);      // GenericReadWriter.h:79 MAX_PASSED
+	c->se_topn = topn;
 	c->epoch += 1;
 	return NGM_B200_OK;
 }
@@ -940,6 +1014,11 @@ int ngm_b200_dev_run_batch(ngm_b200_ctx *c, const ngm_b200_batch_in *in, ngm_b20
 	batch_set_u32_kernel<<<1, 1, 0, st>>>(out->d_str_cursor, 0u, nullptr);
 	DevIn di = { in->n_reads, in->mode, in->paired, in->desc_format, in->cand_begin, 0, in->desc, np };
 	DevOut dn = { scores, out->best_pair, out->mapq, out->num_top, out->pair_fail, out->recs, out->strings, (uint32_t) out->str_capacity, out->d_str_cursor };
+	if (!in->paired && c->se_topn > 1) {
+		dn.topn = c->se_topn;
+		dn.sel = out->sel;
+		dn.n_sel = out->n_sel;
+	}
 	rc = batch_enqueue(c, L, di, dn, c->se_strata, st, nullptr, nullptr);
 	return rc ? rc : in->n_reads;
 }
@@ -954,6 +1033,8 @@ int ngm_b200_run_batch(ngm_b200_ctx *c, const ngm_b200_batch_in *in, ngm_b200_ba
 	if (in->paired && (n & 1)) return fail(NGM_B200_EINVAL, "paired batches hold the mates in rows 2f and 2f + 1: %d rows", n);
 	if (in->read_format == NGM_B200_READS_PACKED2 && in->read_len == nullptr) return fail(NGM_B200_EINVAL, "PACKED2 reads need read_len");
 	if (in->read_stride <= 0) return fail(NGM_B200_EINVAL, "read_stride %d", in->read_stride);
+	const int topn = in->paired ? 1 : c->se_topn;
+	if (topn > 1 && (out->sel == nullptr || out->n_sel == nullptr)) return fail(NGM_B200_EINVAL, "topn %d needs the sel / n_sel arrays", topn);
 	const int32_t *cb = in->cand_begin;
 	const long long total_pairs = (long long) cb[n] - cb[0];
 	if (total_pairs < 0 || (total_pairs > 0 && in->desc == nullptr)) return fail(NGM_B200_EINVAL, "bad candidate lists");
@@ -1006,8 +1087,9 @@ int ngm_b200_run_batch(ngm_b200_ctx *c, const ngm_b200_batch_in *in, ngm_b200_ba
 		if (cudaSuccess != L.d_in_reads.ensure(rbytes) || cudaSuccess != L.d_cb.ensure(((size_t) m + 1) * 4) ||
 				cudaSuccess != L.d_desc.ensure(std::max<size_t>(mp, 1) * desc_bytes) || cudaSuccess != L.d_scores.ensure(std::max<size_t>(mp, 1) * 4) ||
 				cudaSuccess != L.d_best.ensure((size_t) m * 4) || cudaSuccess != L.d_mapq.ensure((size_t) m * 4) || cudaSuccess != L.d_ntop.ensure((size_t) m * 4) ||
-				cudaSuccess != L.d_pfail.ensure((size_t) m * 4) || cudaSuccess != L.d_recs.ensure((size_t) m * sizeof(ngm_b200_align_rec)) ||
-				cudaSuccess != L.d_strings.ensure(std::max<size_t>(slot, 16)) || cudaSuccess != L.d_cursor.ensure(4)) {
+				cudaSuccess != L.d_pfail.ensure((size_t) m * 4) || cudaSuccess != L.d_recs.ensure((size_t) m * topn * sizeof(ngm_b200_align_rec)) ||
+				cudaSuccess != L.d_strings.ensure(std::max<size_t>(slot, 16)) || cudaSuccess != L.d_cursor.ensure(4) ||
+				(topn > 1 && (cudaSuccess != L.d_tsel.ensure((size_t) m * topn * 4) || cudaSuccess != L.d_tnsel.ensure((size_t) m * 4)))) {
 			err = fail(NGM_B200_ECUDA, "lane staging: %s", cudaGetErrorString(cudaGetLastError()));
 			break;
 		}
@@ -1043,16 +1125,26 @@ int ngm_b200_run_batch(ngm_b200_ctx *c, const ngm_b200_batch_in *in, ngm_b200_ba
 		DevIn di = { m, in->mode, in->paired, in->desc_format, L.d_cb.as<int>(), 0, L.d_desc.p, mp };
 		DevOut dn = { L.d_scores.as<float>(), L.d_best.as<int>(), L.d_mapq.as<int>(), L.d_ntop.as<int>(), L.d_pfail.as<int>(), L.d_recs.as<ngm_b200_align_rec>(),
 				L.d_strings.as<char>() - base, (uint32_t) (base + slot), L.d_cursor.as<uint32_t>() };
+		if (topn > 1) {
+			dn.topn = topn;
+			dn.sel = L.d_tsel.as<int>();
+			dn.n_sel = L.d_tnsel.as<int>();
+		}
 		if ((err = batch_enqueue(l, L, di, dn, c->se_strata, st, (in->paired && k > 0) ? B->pe_chain : nullptr, in->paired ? B->pe_chain : nullptr)) != NGM_B200_OK) break;
 		// candidate indices of the caller's arrays, not of the sub-batch
-		if (p0 - cb[0] != 0) batch_add_base_kernel<<<(m + 255) / 256, 256, 0, st>>>(m, L.d_best.as<int>(), p0 - cb[0]);
+		if (p0 - cb[0] != 0) {
+			batch_add_base_kernel<<<(m + 255) / 256, 256, 0, st>>>(m, L.d_best.as<int>(), p0 - cb[0]);
+			if (topn > 1) batch_add_base_kernel<<<(unsigned) (((size_t) m * topn + 255) / 256), 256, 0, st>>>(m * topn, L.d_tsel.as<int>(), p0 - cb[0]);
+		}
 		l->launches += 2;
 		// ---- device -> host
 		e = cudaMemcpyAsync(out->best_pair + r0, L.d_best.p, (size_t) m * 4, cudaMemcpyDeviceToHost, st);
 		if (e == cudaSuccess) e = cudaMemcpyAsync(out->mapq + r0, L.d_mapq.p, (size_t) m * 4, cudaMemcpyDeviceToHost, st);
 		if (e == cudaSuccess && out->num_top) e = cudaMemcpyAsync(out->num_top + r0, L.d_ntop.p, (size_t) m * 4, cudaMemcpyDeviceToHost, st);
 		if (e == cudaSuccess && in->paired) e = cudaMemcpyAsync(out->pair_fail + r0, L.d_pfail.p, (size_t) m * 4, cudaMemcpyDeviceToHost, st);
-		if (e == cudaSuccess) e = cudaMemcpyAsync(out->recs + r0, L.d_recs.p, (size_t) m * sizeof(ngm_b200_align_rec), cudaMemcpyDeviceToHost, st);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(out->recs + (size_t) r0 * topn, L.d_recs.p, (size_t) m * topn * sizeof(ngm_b200_align_rec), cudaMemcpyDeviceToHost, st);
+		if (e == cudaSuccess && topn > 1) e = cudaMemcpyAsync(out->sel + (size_t) r0 * topn, L.d_tsel.p, (size_t) m * topn * 4, cudaMemcpyDeviceToHost, st);
+		if (e == cudaSuccess && topn > 1) e = cudaMemcpyAsync(out->n_sel + r0, L.d_tnsel.p, (size_t) m * 4, cudaMemcpyDeviceToHost, st);
 		if (e == cudaSuccess && out->scores && mp) e = cudaMemcpyAsync(out->scores + (p0 - cb[0]), L.d_scores.p, (size_t) mp * 4, cudaMemcpyDeviceToHost, st);
 		if (e == cudaSuccess) e = cudaMemcpyAsync(h_used + k, L.d_cursor.p, 4, cudaMemcpyDeviceToHost, st);
 		if (e == cudaSuccess) e = cudaEventRecord(L.done, st);
@@ -1099,6 +1191,8 @@ int ngm_b200_map_batch(ngm_b200_ctx *c, const char *reads, int n_reads, int stri
 	if (c->cs == nullptr) return fail(NGM_B200_ESTATE, "cs_build_index / cs_load_index must precede ngm_b200_map_batch");
 	const int m0 = mode_of(mode);
 	if (m0 < 0) return fail(NGM_B200_EINVAL, "unsupported alignment mode %d", mode & 0xFF);
+	const int topn = paired ? 1 : c->se_topn;
+	if (topn > 1 && (res->sel == nullptr || res->n_sel == nullptr)) return fail(NGM_B200_EINVAL, "topn %d needs the sel / n_sel arrays", topn);
 	CU(cudaSetDevice(c->device));
 	int rc = sync_lanes(c);
 	if (rc) return rc;
@@ -1175,7 +1269,7 @@ int ngm_b200_map_batch(ngm_b200_ctx *c, const char *reads, int n_reads, int stri
 		CU(L.d_mapq.ensure((size_t) m * 4));
 		CU(L.d_ntop.ensure((size_t) m * 4));
 		CU(L.d_pfail.ensure((size_t) m * 4));
-		CU(L.d_recs.ensure((size_t) m * sizeof(ngm_b200_align_rec)));
+		CU(L.d_recs.ensure((size_t) m * topn * sizeof(ngm_b200_align_rec)));
 		CU(L.d_strings.ensure(std::max<size_t>(slot, 16)));
 		CU(L.d_cursor.ensure(4));
 		const uint32_t base = (uint32_t) (slot * (size_t) k);
@@ -1183,10 +1277,18 @@ int ngm_b200_map_batch(ngm_b200_ctx *c, const char *reads, int n_reads, int stri
 		DevIn di = { m, mode, paired, NGM_B200_DESC_PAIR16, L.d_cb.as<int>(), 0, L.d_desc.p, (int) mp };
 		DevOut dn = { L.d_scores.as<float>(), L.d_best.as<int>(), L.d_mapq.as<int>(), L.d_ntop.as<int>(), L.d_pfail.as<int>(), L.d_recs.as<ngm_b200_align_rec>(),
 				L.d_strings.as<char>() - base, (uint32_t) (base + slot), L.d_cursor.as<uint32_t>() };
+		if (topn > 1) {
+			CU(L.d_tsel.ensure((size_t) m * topn * 4));
+			CU(L.d_tnsel.ensure((size_t) m * 4));
+			dn.topn = topn;
+			dn.sel = L.d_tsel.as<int>();
+			dn.n_sel = L.d_tnsel.as<int>();
+		}
 		int rc2 = batch_enqueue(l, L, di, dn, c->se_strata, st, (paired && k > 0) ? B->pe_chain : nullptr, paired ? B->pe_chain : nullptr);
 		if (rc2) return rc2;
 		if (p0) {
 			batch_add_base_kernel<<<(m + 255) / 256, 256, 0, st>>>(m, L.d_best.as<int>(), (int) p0);
+			if (topn > 1) batch_add_base_kernel<<<(unsigned) (((size_t) m * topn + 255) / 256), 256, 0, st>>>(m * topn, L.d_tsel.as<int>(), (int) p0);
 			batch_rebase_kernel<<<(m + 1 + 255) / 256, 256, 0, st>>>(m + 1, L.d_cb.as<int>(), -(int) p0);
 		}
 		l->launches += 3;
@@ -1200,7 +1302,11 @@ int ngm_b200_map_batch(ngm_b200_ctx *c, const char *reads, int n_reads, int stri
 		CU(cudaMemcpyAsync(res->num_top + r0, L.d_ntop.p, (size_t) m * 4, cudaMemcpyDeviceToHost, st));
 		if (paired) CU(cudaMemcpyAsync(res->pair_fail + r0, L.d_pfail.p, (size_t) m * 4, cudaMemcpyDeviceToHost, st));
 		CU(cudaMemcpyAsync(res->max_hit + r0, L.d_maxhit.p, (size_t) m * 4, cudaMemcpyDeviceToHost, st));
-		CU(cudaMemcpyAsync(res->recs + r0, L.d_recs.p, (size_t) m * sizeof(ngm_b200_align_rec), cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpyAsync(res->recs + (size_t) r0 * topn, L.d_recs.p, (size_t) m * topn * sizeof(ngm_b200_align_rec), cudaMemcpyDeviceToHost, st));
+		if (topn > 1) {
+			CU(cudaMemcpyAsync(res->sel + (size_t) r0 * topn, L.d_tsel.p, (size_t) m * topn * 4, cudaMemcpyDeviceToHost, st));
+			CU(cudaMemcpyAsync(res->n_sel + r0, L.d_tnsel.p, (size_t) m * 4, cudaMemcpyDeviceToHost, st));
+		}
 		CU(cudaMemcpyAsync(h_used + k, L.d_cursor.p, 4, cudaMemcpyDeviceToHost, st));
 		CU(cudaEventRecord(L.done, st));
 		L.pending = k;

@@ -93,6 +93,7 @@ int mode_of(int mode);                          // mode & 0xFF -> 0 / 1, or -1
 int resolve_pairs_for(ngm_b200_ctx *c, const void *d_pairs_user, int n, cudaStream_t st);      // ngm_b200_pair -> c->d_rpairs (PairDesc)
 int pack_reads_device(ngm_b200_ctx *c, const uint8_t *d_ascii, int n_reads, int stride, cudaStream_t st);
 int run_score(ngm_b200_ctx *c, int mode, const ScoreArgs &a, cudaStream_t st);
+ScoreArgs score_args(ngm_b200_ctx *c, const PairDesc *pairs, int n, const uint32_t *rf, const uint32_t *rr, const uint16_t *rl, const uint32_t *ref4, float *out);
 int run_align(ngm_b200_ctx *c, int mode, const PairDesc *pairs, int n, const uint32_t *rf, const uint32_t *rr, const uint16_t *rl, const uint32_t *ref4,
 		ngm_b200_align_rec *recs, char *strings, uint32_t str_cap, uint32_t *cursor, cudaStream_t st, const float *known_user, float *out_best);
 
@@ -141,6 +142,7 @@ struct ngm_b200_ctx {
 	cudaEvent_t pev[3 * 64] = {};
 	int pev_used = 0;
 	int se_strata = 0;         // "strata" for single-end top-1 selection (ScoreBuffer.cpp:259)
+	int se_topn = 1;           // "topn": alignments reported per single-end read (ScoreBuffer.cpp:279-330); batch entry points
 	uint64_t epoch = 0;        // bumped whenever the reference / index / selection parameters change: lanes re-sync their aliases
 	ngm_b200_ctx *root = nullptr;      // set in a lane / shared context: the context whose resident data it borrows
 	uint64_t root_epoch = ~0ull;       // the root's epoch at the last borrow

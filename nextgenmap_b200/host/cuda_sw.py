@@ -64,7 +64,7 @@ class MapResult(C.Structure):
     """ngm_b200_map_result (include/ngm_b200.h)."""
     _fields_ = [("cand_begin", C.c_void_p), ("pairs", C.c_void_p), ("scores", C.c_void_p), ("capacity", C.c_size_t), ("n_candidates", C.c_size_t),
                 ("best_pair", C.c_void_p), ("mapq", C.c_void_p), ("num_top", C.c_void_p), ("pair_fail", C.c_void_p), ("max_hit", C.c_void_p),
-                ("recs", C.c_void_p), ("strings", C.c_void_p), ("str_capacity", C.c_size_t), ("str_used", C.c_size_t)]
+                ("recs", C.c_void_p), ("strings", C.c_void_p), ("str_capacity", C.c_size_t), ("str_used", C.c_size_t), ("sel", C.c_void_p), ("n_sel", C.c_void_p)]
 
 
 class BatchIn(C.Structure):
@@ -77,7 +77,8 @@ class BatchIn(C.Structure):
 class BatchOut(C.Structure):
     """ngm_b200_batch_out (include/ngm_b200.h)."""
     _fields_ = [("scores", C.c_void_p), ("best_pair", C.c_void_p), ("mapq", C.c_void_p), ("num_top", C.c_void_p), ("pair_fail", C.c_void_p), ("recs", C.c_void_p),
-                ("strings", C.c_void_p), ("str_capacity", C.c_size_t), ("str_used", C.c_size_t), ("d_str_cursor", C.c_void_p)]
+                ("strings", C.c_void_p), ("str_capacity", C.c_size_t), ("str_used", C.c_size_t), ("d_str_cursor", C.c_void_p), ("sel", C.c_void_p),
+                ("n_sel", C.c_void_p)]
 
 
 READ_EXC = np.dtype([("read_index", "<u4"), ("pos", "<u2"), ("ch", "u1"), ("pad", "u1")])
@@ -191,6 +192,7 @@ def load_library() -> C.CDLL:
     lib.ngm_b200_dev_run_batch.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.POINTER(BatchOut), C.c_void_p]
     lib.ngm_b200_set_pipeline.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.ngm_b200_se_configure.argtypes = [C.c_void_p, C.c_int]
+    lib.ngm_b200_se_configure_topn.argtypes = [C.c_void_p, C.c_int]
     lib.ngm_b200_host_alloc.restype = C.c_void_p
     lib.ngm_b200_host_alloc.argtypes = [C.c_size_t]
     lib.ngm_b200_host_free.argtypes = [C.c_void_p]
@@ -343,8 +345,11 @@ class CudaSW:
     def set_pipeline(self, lanes: int = 3, sub_batch_reads: int = 1 << 20) -> None:
         self._check(self.lib.ngm_b200_set_pipeline(self.ctx, lanes, sub_batch_reads))
 
-    def se_configure(self, strata: int = 0) -> None:
+    def se_configure(self, strata: int = 0, topn: int = 1) -> None:
+        """`strata` and `topn` (NGM --strata / -n) of the single-end batch entry points; topn > 1: ScoreBuffer::topNSE."""
         self._check(self.lib.ngm_b200_se_configure(self.ctx, strata))
+        self._check(self.lib.ngm_b200_se_configure_topn(self.ctx, topn))
+        self.se_topn = topn
 
     def pack_reads(self, reads: np.ndarray, threads: int = 0):
         """ASCII rows -> (packed2 uint8 [n, row_bytes], read_len uint16 [n], exceptions READ_EXC [k]) on the host (ngm_b200_pack_reads)."""
@@ -368,7 +373,9 @@ class CudaSW:
     def run_batch(self, mode: int, reads: np.ndarray, cand_begin: np.ndarray, pairs: np.ndarray, paired: bool = False, packed: bool = False,
                   desc_u64: bool = False, str_capacity: Optional[int] = None, want_scores: bool = True) -> dict:
         """ngm_b200_run_batch on host arrays.  reads: ASCII rows; packed=True sends them 2-bit packed (ngm_b200_pack_reads);
-        pairs: PAIR records (read_index is ignored); desc_u64=True sends 64-bit descriptors."""
+        pairs: PAIR records (read_index is ignored); desc_u64=True sends 64-bit descriptors.  After se_configure(topn > 1) a single-end
+        batch returns recs [n, topn], sel [n, topn] and n_sel [n]."""
+        topn = 1 if paired else getattr(self, "se_topn", 1)
         reads = np.ascontiguousarray(reads, dtype=np.uint8)
         cand_begin = np.ascontiguousarray(cand_begin, dtype=np.int32)
         pairs = np.ascontiguousarray(pairs, dtype=PAIR)
@@ -392,12 +399,15 @@ class CudaSW:
             bi.desc_format, bi.desc = DESC_PAIR16, pairs.ctypes.data
         bi.cand_begin = cand_begin.ctypes.data
         res = {"scores": np.full(max(npairs, 1), np.nan, np.float32), "best_pair": np.zeros(n, np.int32), "mapq": np.zeros(n, np.int32),
-               "num_top": np.zeros(n, np.int32), "pair_fail": np.zeros(n, np.int32), "recs": np.zeros(n, dtype=ALIGN_REC)}
-        cap = str_capacity if str_capacity is not None else max(4096, 96 * n)
+               "num_top": np.zeros(n, np.int32), "pair_fail": np.zeros(n, np.int32), "recs": np.zeros((n, topn) if topn > 1 else n, dtype=ALIGN_REC)}
+        if topn > 1:
+            res["sel"], res["n_sel"] = np.zeros((n, topn), np.int32), np.zeros(n, np.int32)
+        cap = str_capacity if str_capacity is not None else max(4096, 96 * n * topn)
         for _ in range(2):
             heap = np.zeros(max(cap, 1), np.uint8)
             bo = BatchOut(res["scores"].ctypes.data if want_scores else None, res["best_pair"].ctypes.data, res["mapq"].ctypes.data, res["num_top"].ctypes.data,
-                          res["pair_fail"].ctypes.data if paired else None, res["recs"].ctypes.data, heap.ctypes.data, cap, 0, None)
+                          res["pair_fail"].ctypes.data if paired else None, res["recs"].ctypes.data, heap.ctypes.data, cap, 0, None,
+                          res["sel"].ctypes.data if topn > 1 else None, res["n_sel"].ctypes.data if topn > 1 else None)
             rc = self.lib.ngm_b200_run_batch(self.ctx, C.byref(bi), C.byref(bo))
             if rc == -3 and bo.str_used > cap:
                 cap = int(bo.str_used)

@@ -140,20 +140,24 @@ def map_reads_topn(sw: CudaSW, reads: np.ndarray, topn: int, strata: bool = Fals
                            num_top=d_nt.cpu().numpy(), recs=recs, strings=strings, heap=heap)
 
 
-def map_batch(sw: CudaSW, reads: np.ndarray, mode: int = 0, paired: bool = False, capacity: int = 0, heap_bytes: int = 0) -> MappedBatch:
-    """The same as ``map_reads`` / ``map_pairs`` through the one-call entry point ``ngm_b200_map_batch`` (host buffers in, host buffers
-    out; candidates, scores and winners never leave the device in between)."""
+def map_batch(sw: CudaSW, reads: np.ndarray, mode: int = 0, paired: bool = False, capacity: int = 0, heap_bytes: int = 0):
+    """The same as ``map_reads`` / ``map_pairs`` / ``map_reads_topn`` through the one-call entry point ``ngm_b200_map_batch`` (host buffers
+    in, host buffers out; candidates, scores and winners never leave the device in between).  After ``sw.se_configure(topn > 1)`` a
+    single-end batch comes back in the shape ``map_reads_topn`` returns (recs [n, topn], sel, n_sel)."""
     reads = np.ascontiguousarray(reads, dtype=np.uint8)
     n, stride = reads.shape
-    cap, scap = capacity or max(1024, 4 * n), heap_bytes or n * 64 + 4096
+    topn = 1 if paired else getattr(sw, "se_topn", 1)
+    cap, scap = capacity or max(1024, 4 * n), heap_bytes or n * 64 * topn + 4096
     for _ in range(4):
         begin = np.zeros(n + 1, np.int32)
         pairs, scores = np.zeros(cap, dtype=PAIR), np.zeros(cap, np.float32)
         best, mq, nt, pf = (np.zeros(n, np.int32) for _ in range(4))
         mh = np.zeros(n, np.float32)
-        recs, heap = np.zeros(n, dtype=ALIGN_REC), np.zeros(scap, np.uint8)
+        recs, heap = np.zeros((n, topn) if topn > 1 else n, dtype=ALIGN_REC), np.zeros(scap, np.uint8)
+        sel, n_sel = (np.zeros((n, topn), np.int32), np.zeros(n, np.int32)) if topn > 1 else (None, None)
         res = MapResult(begin.ctypes.data, pairs.ctypes.data, scores.ctypes.data, cap, 0, best.ctypes.data, mq.ctypes.data, nt.ctypes.data,
-                        pf.ctypes.data if paired else None, mh.ctypes.data, recs.ctypes.data, heap.ctypes.data, scap, 0)
+                        pf.ctypes.data if paired else None, mh.ctypes.data, recs.ctypes.data, heap.ctypes.data, scap, 0,
+                        sel.ctypes.data if topn > 1 else None, n_sel.ctypes.data if topn > 1 else None)
         rc = sw.lib.ngm_b200_map_batch(sw.ctx, reads.ctypes.data, n, stride, mode, 1 if paired else 0, C.byref(res))
         if rc == -3:                                 # (the library puts the insert-size sums of a paired run back before it reports this)
             cap = max(cap, int(res.n_candidates) + 16)
@@ -161,6 +165,14 @@ def map_batch(sw: CudaSW, reads: np.ndarray, mode: int = 0, paired: bool = False
             continue
         sw._check(rc)
         total, raw = int(res.n_candidates), heap.tobytes()      # (the heap is sparse: one slot per sub-batch of the library's pipeline)
+        if topn > 1:
+            from types import SimpleNamespace
+
+            def strings_n(r: int, j: int):
+                o, cl, ml = int(recs[r, j]["str_off"]), int(recs[r, j]["cigar_len"]), int(recs[r, j]["md_len"])
+                return raw[o: o + cl], raw[o + cl: o + cl + ml]
+            return SimpleNamespace(cand_begin=begin, pairs=pairs[:total], scores=scores[:total], max_hit=mh, sel=sel, n_sel=n_sel, mapq=mq, num_top=nt,
+                                   recs=recs, strings=strings_n, heap=heap, best_pair=best)
 
         def strings(r: int):
             o, cl, ml = int(recs[r]["str_off"]), int(recs[r]["cigar_len"]), int(recs[r]["md_len"])

@@ -155,5 +155,23 @@ def test_topn_sam_identical_to_ngm(extra, topn, strata, seed):
     bad = [(g, w) for g, w in zip(got, want) if g != w]
     assert not bad, f"{len(bad)} of {len(want)} SAM lines differ, first:\n{bad[0][0]}\n{bad[0][1]}"
     assert sum(1 for ln in want if int(ln.split("\t")[1]) & 0x100) > (5 if strata else 100)
+    # the same run through the one-call entry points (ngm_b200_se_configure_topn): several sub-batches over the lanes
+    sw.se_configure(strata=1 if strata else 0, topn=topn)
+    sw.set_pipeline(3, 256)
+    one_call = pipeline.map_batch(sw, reads)
+    assert np.array_equal(one_call.sel, batch.sel) and np.array_equal(one_call.n_sel, batch.n_sel) and np.array_equal(one_call.best_pair, batch.sel[:, 0])
+    assert sorted(pipeline.format_sam(one_call, reads, names, quals, ref, False).decode().splitlines()) == got
+    rb = sw.run_batch(0, reads, batch.cand_begin, batch.pairs, packed=True, desc_u64=True)
+    assert np.array_equal(rb["sel"], batch.sel) and np.array_equal(rb["n_sel"], batch.n_sel) and np.array_equal(rb["best_pair"], batch.sel[:, 0])
+    assert np.array_equal(rb["mapq"], batch.mapq) and np.array_equal(rb["num_top"], batch.num_top)
+    assert np.array_equal(rb["scores"].view(np.uint32), batch.scores.view(np.uint32))
+    taken = batch.sel >= 0
+    assert np.all(rb["recs"]["score"][~taken] == -1.0)
+    for f in ("position_offset", "qstart", "qend", "nm", "score", "cigar_len", "md_len"):
+        assert np.array_equal(rb["recs"][f][taken], batch.recs[f][taken]), f
+    for r in range(len(reads)):
+        for j in range(int(batch.n_sel[r])):
+            assert sw.strings_of(rb["recs"][r], rb["heap"], j) == batch.strings(r, j)
+    sw.se_configure(0, 1)
     sw.close()
     ref.close()
