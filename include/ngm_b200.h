@@ -350,6 +350,9 @@ typedef struct ngm_b200_sam_opts {
 	int32_t max_insert_size;    /* "max_insert_size" (1000); <= 0 = INT_MAX */
 	int32_t threads;            /* host threads; 0 = all */
 	int32_t min_mq;             /* "min_mq" (0): reads below it are written as unmapped (AlignmentBuffer.cpp:46-49, GenericReadWriter.h:281-284) */
+	int32_t clip_seq;           /* "hard_clip" or "silent_clip" set: SEQ / QUAL of a mapped read lose the clipped ends (SAMWriter.cpp:104,146-160);
+	                             * the CIGAR's H ops (or none) come from the alignment itself (ngm_b200_params.hard_clip / silent_clip) */
+	const char *read_group;     /* "rg_id": RG:Z:<id> on every record (SAMWriter.cpp:166-168,358-360); NULL = none */
 } ngm_b200_sam_opts;
 /* One batch as the calls above leave it, all host pointers.  Paired runs: rows 2f / 2f + 1 are mates and pair_fail != NULL. */
 typedef struct ngm_b200_sam_batch {

@@ -53,7 +53,14 @@ struct HalfBest {
 // match cells carry their own tag (3 = diag & EQ, 2 = diag & X), so the common step needs no
 // sequence lookup at all.
 // ---------------------------------------------------------------------------
-constexpr int kRing = 16;       // rows in flight per thread (power of two)
+// Runs of matches in one step (-DNGM_BT_RUNS=0: one cell per loop iteration, the first form): a diagonal run stays on one band slot, so
+// the tags of the next eight rows sit at the same bit position of eight ring words; the walk takes all leading EQ cells of that window
+// at once and spends a full iteration only on X / I / D cells.
+#ifndef NGM_BT_RUNS
+#define NGM_BT_RUNS 0
+#endif
+constexpr int kRing = NGM_BT_RUNS ? 32 : 16;       // rows in flight per thread (power of two)
+constexpr int kRunRows = 8;                        // rows examined per iteration (NGM_BT_RUNS)
 constexpr int kSpecialFlag = 1 << 30;   // in HalfBest::read_count: sequences hold codes other than A/C/G/T
 
 __device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const uint32_t *gmem_src) {
@@ -120,6 +127,45 @@ __device__ __forceinline__ TraceOut backtrace_tagged(const DevParams &P, const u
 	while (row >= 0) {
 		int op;
 		bool up_row = true;
+#if NGM_BT_RUNS
+		// every row consumed was matched by one (possibly empty) copy group, so kRing groups are outstanding here and all but the
+		// kRing - kRunRows newest -- the rows row .. row - 7 -- have landed after this wait
+		cp_async_wait<kRing - kRunRows>();
+		w0 = ring[(row & (kRing - 1)) * ring_stride];
+		if (!border && fast_eq) {
+			uint32_t code = (w0 >> sh) & 3u;
+#pragma unroll
+			for (int k = 1; k < kRunRows; ++k) {
+				const uint32_t wk = ring[((row - k) & (kRing - 1)) * ring_stride];       // (stale for rows < 0: clamped below)
+				code |= ((wk >> sh) & 3u) << (2 * k);
+			}
+			const uint32_t eq = code & (code >> 1) & 0x5555u;                           // bit 2k: row - k carries tag 3
+			int lead = (__ffs((int) ((~eq & 0x5555u) | 0x10000u)) - 1) >> 1;            // leading EQ cells of the window
+			lead = min(lead, row + 1);
+			// the same as `lead` iterations of the single-cell fast path: local mode stops at h <= 0, checked before every cell
+			if (lead > 1 && (MODE != 0 || h - (lead - 1) * P.match > 0)) {
+				h -= lead * P.match;
+				abs_ref -= lead;
+				if (elem == OP_EQ) {
+					len += lead;
+				} else {
+					if (sp < ops_cap) ops[(size_t) sp * ops_stride] = (uint16_t) (len << 4 | elem);
+					sp += 1;
+					elem = OP_EQ;
+					len = lead;
+				}
+#pragma unroll
+				for (int k = 0; k < kRunRows; ++k) {
+					if (k < lead) {
+						fill(row - kRing - k, pf);                        // the window slides: row - 1 - k enters with row - 1 - k - (kRing - 1)
+						pf -= rs;
+					}
+				}
+				row -= lead;
+				continue;
+			}
+		}
+#endif
 		const uint32_t p = (w0 >> sh) & 3u;
 		if (!border && (MODE != 0 || h > 0) && p == 3u && fast_eq) {
 			op = OP_EQ;
@@ -184,8 +230,10 @@ __device__ __forceinline__ TraceOut backtrace_tagged(const DevParams &P, const u
 		if (up_row && row >= 0) {
 			fill(row - (kRing - 1), pf);                          // reuses the slot of the row just left
 			pf -= rs;
+#if !NGM_BT_RUNS
 			cp_async_wait<kRing - 1>();
 			w0 = ring[(row & (kRing - 1)) * ring_stride];
+#endif
 		}
 	}
 	cp_async_wait<0>();

@@ -98,7 +98,8 @@ struct Line {              // one output line is assembled in a scratch buffer t
 };
 
 size_t line_bound_at(const Job &j, int r, bool aligned, const ngm_b200_align_rec &rec) {       // name + FLAG..TLEN + SEQ + QUAL + tags + CIGAR + MD
-	return strlen(j.b->names[r]) + 2 * (size_t) j.b->stride + (aligned ? (size_t) rec.cigar_len + rec.md_len : 0) + 2 * 100 + 320;
+	return strlen(j.b->names[r]) + 2 * (size_t) j.b->stride + (aligned ? (size_t) rec.cigar_len + rec.md_len : 0) + 2 * 100 + 320 +
+			(j.o->read_group != nullptr ? strlen(j.o->read_group) + 8 : 0);
 }
 
 size_t line_bound(const Job &j, int r) { return line_bound_at(j, r, j.b->best_pair[r] >= 0, j.b->recs[r]); }
@@ -176,17 +177,26 @@ void mapped_line(const Job &j, const ReadView &v, int flags, const char *rnext, 
 	out.push_back('\t');
 	put_int(out, tlen);
 	out.push_back('\t');
+	// "hard_clip" / "silent_clip": SEQ and QUAL lose the clipped ends of the oriented read (SAMWriter.cpp:104,146-160)
+	const int skip = j.o->clip_seq ? rec.qstart : 0;
+	const int keep = std::max(0, j.o->clip_seq ? v.length - rec.qstart - rec.qend : v.length);
 	char *dst = out.p;
-	out.p += 2 * (size_t) v.length + 1;
+	out.p += 2 * (size_t) keep + 1;
 	if (v.reverse) {                                            // RevSeq, reversed qualities (SAMWriter.cpp:120-126)
-		const unsigned char *sq = reinterpret_cast<const unsigned char *>(v.seq) + v.length;
-		for (int i = 0; i < v.length; ++i) dst[i] = (char) kComp.t[*--sq];
-		dst[v.length] = '\t';
-		std::reverse_copy(v.qual, v.qual + v.length, dst + v.length + 1);
+		const unsigned char *sq = reinterpret_cast<const unsigned char *>(v.seq) + v.length - skip;
+		for (int i = 0; i < keep; ++i) dst[i] = (char) kComp.t[*--sq];
+		dst[keep] = '\t';
+		// (a quality string that starts with '*' counts as "no qualities" and stays as it is, SAMWriter.cpp:122)
+		if (v.qual[0] == '*') memcpy(dst + keep + 1, v.qual + skip, (size_t) keep);
+		else std::reverse_copy(v.qual + v.length - skip - keep, v.qual + v.length - skip, dst + keep + 1);
 	} else {
-		memcpy(dst, v.seq, (size_t) v.length);
-		dst[v.length] = '\t';
-		memcpy(dst + v.length + 1, v.qual, (size_t) v.length);
+		memcpy(dst, v.seq + skip, (size_t) keep);
+		dst[keep] = '\t';
+		memcpy(dst + keep + 1, v.qual + skip, (size_t) keep);
+	}
+	if (j.o->read_group != nullptr) {                            // SAMWriter.cpp:166-168
+		out.append("\tRG:Z:");
+		out.append(j.o->read_group);
 	}
 	const int ntop = b.num_top[v.r];
 	tag_int(out, "\tAS:i:", (int) b.scores[v.bp]);
@@ -203,7 +213,7 @@ void mapped_line(const Job &j, const ReadView &v, int flags, const char *rnext, 
 	out.push_back('\n');
 }
 
-void unmapped_line(const ReadView &v, int flags, const ngm_b200_contig *rname, int64_t loc, char rnext, int64_t pnext, Line &out) {
+void unmapped_line(const Job &j, const ReadView &v, int flags, const ngm_b200_contig *rname, int64_t loc, char rnext, int64_t pnext, Line &out) {
 	out.append(v.name);                                         // SAMWriter::DoWriteUnmappedReadGeneric
 	out.push_back('\t');
 	put_int(out, flags | 0x4);
@@ -220,6 +230,10 @@ void unmapped_line(const ReadView &v, int flags, const ngm_b200_contig *rname, i
 	out.append(v.seq, (size_t) v.length);
 	out.push_back('\t');
 	out.append(v.qual, (size_t) v.length);
+	if (j.o->read_group != nullptr) {                            // SAMWriter.cpp:358-360
+		out.append("\tRG:Z:");
+		out.append(j.o->read_group);
+	}
 	out.push_back('\n');
 }
 
@@ -229,7 +243,7 @@ void single(const Job &j, int r, std::string &text, std::vector<char> &scratch) 
 	scratch.resize(std::max(scratch.size(), line_bound(j, r)));
 	Line out = { scratch.data() };
 	if (v.has && v.converted && passes(j, v)) mapped_line(j, v, 0, "*", nullptr, -1, 0, out);
-	else unmapped_line(v, 0, nullptr, -1, '*', -1, out);
+	else unmapped_line(j, v, 0, nullptr, -1, '*', -1, out);
 	text.append(scratch.data(), (size_t) (out.p - scratch.data()));
 }
 
@@ -268,7 +282,7 @@ void single_topn(const Job &j, int r, std::string &text, std::vector<char> &scra
 	}
 	if (written == 0) {
 		if (ns == 0) collect_at(j, r, -1, &b.recs[(size_t) r * topn], views[0]);
-		unmapped_line(views[0], 0, nullptr, -1, '*', -1, out);
+		unmapped_line(j, views[0], 0, nullptr, -1, '*', -1, out);
 	}
 	text.append(scratch.data(), (size_t) (out.p - scratch.data()));
 }
@@ -291,13 +305,13 @@ void fragment(const Job &j, int f, std::string &text, std::vector<char> &scratch
 	int fa = 0x1 | 0x40, fb = 0x1 | 0x80;
 	const ngm_b200_contig *ca = &j.ref->contigs[a.contig], *cb = &j.ref->contigs[b.contig];
 	if (!a.has && !b.has) {
-		unmapped_line(b, fb | 0x8, nullptr, -1, '*', -1, out);
-		unmapped_line(a, fa | 0x8, nullptr, -1, '*', -1, out);
+		unmapped_line(j, b, fb | 0x8, nullptr, -1, '*', -1, out);
+		unmapped_line(j, a, fa | 0x8, nullptr, -1, '*', -1, out);
 	} else if (!a.has) {
 		mapped_line(j, b, fb | 0x8, "=", nullptr, (int64_t) b.loc, 0, out);
-		unmapped_line(a, fa, cb, (int64_t) b.loc, '=', (int64_t) b.loc, out);
+		unmapped_line(j, a, fa, cb, (int64_t) b.loc, '=', (int64_t) b.loc, out);
 	} else if (!b.has) {
-		unmapped_line(b, fb, ca, (int64_t) a.loc, '=', (int64_t) a.loc, out);
+		unmapped_line(j, b, fb, ca, (int64_t) a.loc, '=', (int64_t) a.loc, out);
 		mapped_line(j, a, fa | 0x8, "=", nullptr, (int64_t) a.loc, 0, out);
 	} else if (!fail) {
 		fa |= 0x2;

@@ -238,7 +238,7 @@ def _mapped_line(batch, rd: _Read, encref, flags: int, rnext: str, pnext: int, t
     s, q = rd.seq, rd.qual
     if rd.reverse:
         s = rd.seq.translate(COMP)[::-1]
-        q = rd.qual[::-1]
+        q = rd.qual if rd.qual[:1] == b"*" else rd.qual[::-1]      # SAMWriter.cpp:122: a quality string starting with "*" is left alone
         flags |= 0x10
     ntop = int(batch.num_top[rd.r])
     qstart, qend = int(rec["qstart"]), int(rec["qend"])
@@ -363,7 +363,8 @@ def sam_lines_paired(batch, reads: np.ndarray, names: Sequence[str], quals: Sequ
 
 
 def format_sam(batch, reads: np.ndarray, names: Sequence[str], quals: Sequence[bytes], encref, paired: bool, min_identity: float = 0.65,
-               min_residues: float = 0.5, min_insert_size: int = 0, max_insert_size: int = 1000, threads: int = 0, min_mq: int = 0) -> bytes:
+               min_residues: float = 0.5, min_insert_size: int = 0, max_insert_size: int = 1000, threads: int = 0, min_mq: int = 0,
+               clip_seq: bool = False, read_group: Optional[str] = None) -> bytes:
     """The same lines as ``sam_lines`` / ``sam_lines_paired`` from the library's multi-threaded formatter (``ngm_b200_format_sam``): what a
     C / C++ host calls.  ``encref``: an ``EncodedReference`` (the C struct is handed over as it is).  ``batch.recs`` / ``batch.heap`` as
     ``ngm_b200_align_pairs`` returned them."""
@@ -386,7 +387,7 @@ def format_sam(batch, reads: np.ndarray, names: Sequence[str], quals: Sequence[b
     n_sel = np.ascontiguousarray(batch.n_sel, dtype=np.int32) if topn else None
     sb = SamBatch(n, stride, reads.ctypes.data, q.ctypes.data, name_arr, ptr(keep[0]), ptr(keep[1]), ptr(keep[2]), ptr(keep[3]), ptr(keep[4]), ptr(keep[5]),
                   ptr(keep[6]), ptr(keep[7]), ptr(keep[8]), topn if topn > 1 else 0, ptr(sel), ptr(n_sel))
-    so = SamOpts(min_identity, min_residues, min_insert_size, max_insert_size, threads, min_mq)
+    so = SamOpts(min_identity, min_residues, min_insert_size, max_insert_size, threads, min_mq, 1 if clip_seq else 0, read_group.encode() if read_group else None)
     used = C.c_size_t(0)
     cap = n * max(topn, 1) * (2 * stride + 256) + 4096
     for _ in range(2):

@@ -175,3 +175,55 @@ def test_topn_sam_identical_to_ngm(extra, topn, strata, seed):
     sw.se_configure(0, 1)
     sw.close()
     ref.close()
+
+
+@pytest.mark.parametrize("flag,paired", [("--hard-clip", False), ("--silent-clip", False), ("--hard-clip", True)])
+def test_clipping_and_read_group_identical_to_ngm(flag, paired):
+    """`--hard-clip` / `--silent-clip` (H ops or none in the CIGAR, SEQ / QUAL without the clipped ends) and `--rg-id` (RG:Z on every record,
+    mapped or not): SAMWriter.cpp:104,146-168,358-360 -- the library's formatter (ngm_b200_sam_opts.clip_seq / read_group) against ngm."""
+    from nextgenmap_b200.host import CudaSW, EncodedReference
+    from nextgenmap_b200.host import pipeline
+    from tests.test_mapper_oracle import read_fastq as read_fastq_pe, rows
+    hard = flag == "--hard-clip"
+    with tempfile.TemporaryDirectory(prefix="pipe_clip_") as td:
+        d = Path(td)
+        if paired:
+            e2e.write_paired_inputs(d, ref_len=500_000, n_frags=1000, read_len=100, seed=77)
+        else:
+            e2e.write_inputs(d, ref_len=900_000, n_reads=3000, read_len=150, seed=78, sub_rate=0.06, indel_reads=0.2)
+        lines = (d / "reads.fq").read_bytes().split(b"\n")          # position-dependent qualities: clipping QUAL at the wrong end must show
+        for i in range(3, len(lines), 4):
+            lines[i] = bytes(40 + (i + 3 * k) % 33 for k in range(len(lines[i])))
+        (d / "reads.fq").write_bytes(b"\n".join(lines))
+        args = ["-s", "0.5", flag, "--rg-id", "lane7"] + (["-p"] if paired else [])
+        want = [ln for ln in e2e.run("ref", d, threads=1 if paired else 4, extra=args) if not ln.startswith("@")]
+        ref = EncodedReference(str(d / "ref.fa-enc.2.ngm"))
+        if paired:
+            names, seqs, quals = read_fastq_pe(d / "reads.fq", True)
+        else:
+            names, seqs, quals = read_fastq(d / "reads.fq")
+    read_len = max(len(x) for x in seqs)
+    qml, cor = (read_len | 1) + 1, int(5 + 0.15 * read_len)
+    reads = np.zeros((len(seqs), qml), np.uint8)
+    for i, x in enumerate(seqs):
+        reads[i, : len(x)] = np.frombuffer(x, np.uint8)
+    sw = CudaSW(qml, cor, hard_clip=1 if hard else 0, silent_clip=0 if hard else 1)
+    sw.set_reference(ref.packed, ref.concat_len)
+    sw.cs_build_index([(c[1], c[2]) for c in ref.contigs], sw.cs_params(kmer=13, sensitivity=0.5))
+    if paired:
+        sw.pe_configure()
+    batch = pipeline.map_batch(sw, reads, 0, paired=paired)
+    got = pipeline.format_sam(batch, reads, names, quals, ref, paired, clip_seq=True, read_group="lane7").decode().splitlines()
+    got.sort()
+    assert len(got) == len(want)
+    bad = [(g, w) for g, w in zip(got, want) if g != w]
+    assert not bad, f"{len(bad)} of {len(want)} SAM lines differ, first:\n{bad[0][0]}\n{bad[0][1]}"
+    assert all("RG:Z:lane7" in ln for ln in want)
+    clipped = [ln for ln in want if ln.split("\t")[1] != "4" and len(ln.split("\t")[9]) < read_len]
+    assert len(clipped) > 20                                  # reads that really lost bases
+    if hard:
+        assert any("H" in ln.split("\t")[5] for ln in clipped)
+    else:
+        assert not any("H" in ln.split("\t")[5] or "S" in ln.split("\t")[5] for ln in want)
+    sw.close()
+    ref.close()
