@@ -6,6 +6,10 @@
 #include "ngm_align_s16.cuh"
 #include "ngm_align_s16v2.cuh"
 
+#ifndef NGM_EXACT_LIST
+#define NGM_EXACT_LIST(X) X(24, 23) X(28, 27) X(36, 35) X(44, 42)
+#endif
+
 namespace ngm {
 
 cudaError_t launch_align_s16(int capacity, int mode, const AlignArgs &a, cudaStream_t st) {
@@ -16,6 +20,33 @@ cudaError_t launch_align_s16(int capacity, int mode, const AlignArgs &a, cudaStr
 	// second-generation forward pass (ngm_align_s16v2.cuh): narrow local bands and every end-free band.  NGM_B200_FWD=1 keeps the
 	// first-generation kernel (A/B measurements, tests of both).
 	static const bool use_v1 = [] { const char *e = getenv("NGM_B200_FWD"); return e != nullptr && atoi(e) == 1; }();
+	// corridors NGM derives from common read lengths (5 + 0.15 x length: 125 bp -> 23, 150 bp -> 27, 200 bp -> 35, 250 bp -> 42) get
+	// instantiations that know the corridor at compile time: no slot beyond it is computed, no run-time corridor mask
+	if (!use_v1 && !launched) {
+#define XE(W, C) \
+		if (capacity == W && a.P.corridor == C && !launched) { \
+			if constexpr (W <= kAlignS16MaxLocal) { \
+				if (mode == 0) { \
+					constexpr int smem = 3 * W * 128 * 4; \
+					static const cudaError_t attr = cudaFuncSetAttribute(align_s16_fwd2_kernel<W, C, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+					if (attr != cudaSuccess) return attr; \
+					align_s16_fwd2_kernel<W, C, 0, true><<<grid, block, smem, st>>>(a.P, a.pairs, a.n, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, \
+							a.ptr_scratch, a.stride, a.best_scratch, a.range, a.range_m); \
+					launched = true; \
+				} \
+			} \
+			if (mode == 1) { \
+				align_s16_fwd2_kernel<W, C, 1, true><<<grid, block, 0, st>>>(a.P, a.pairs, a.n, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, \
+						a.ptr_scratch, a.stride, a.best_scratch, a.range, a.range_m); \
+				launched = true; \
+			} \
+		}
+		static const bool no_exact = [] { const char *e = getenv("NGM_B200_FWD_EXACT"); return e != nullptr && atoi(e) == 0; }();
+		if (!no_exact) {
+			NGM_EXACT_LIST(XE)
+		}
+#undef XE
+	}
 	if (!use_v1 && !launched) {
 #define X(W, LO) \
 		if (capacity == W && !launched) { \

@@ -61,7 +61,9 @@ __device__ __forceinline__ uint32_t funnel_fma(uint32_t lo, uint32_t hi, uint32_
 }
 
 // One DP row for both halves.  PTR: accumulate + return the pointer words of the row.  MAYBE0: t may be 0 (no shift).
-template <int W, int LO, int MODE, bool PTR, bool MAYBE0 = true>
+// EXACT: the corridor is LO exactly (a compile-time constant): slots >= LO are never computed (they keep the sentinel; their pointer tags
+// are zero shifts of the pointer word) and no slot needs the run-time corridor mask.
+template <int W, int LO, int MODE, bool PTR, bool MAYBE0 = true, bool EXACT = false>
 __device__ __forceinline__ void fwd2_row(uint32_t (&line)[W + 1], const uint32_t (&wa)[BandGeom<W>::kWin], const uint32_t (&wb)[BandGeom<W>::kWin],
 		const int t, const uint2 ta, const uint2 tb, const uint32_t gr2, const uint32_t gf2, const uint32_t SENT2,
 		const uint32_t (&keepm)[W - LO + 1], const uint32_t (&fillm)[W - LO + 1], const uint32_t c_four, const uint32_t c_neg1,
@@ -103,6 +105,10 @@ __device__ __forceinline__ void fwd2_row(uint32_t (&line)[W + 1], const uint32_t
 #pragma unroll
 		for (int i = 0; i < 4; ++i) {
 			const int j = 4 * m + i;
+			if (EXACT && j >= LO) {
+				if (PTR) pw[j >> 3] = imad_u32(pw[j >> 3], c_four, 0u);
+				continue;
+			}
 			const uint32_t s2 = i == 0 ? sbyte2<0>(sa, sb) : i == 1 ? sbyte2<1>(sa, sb) : i == 2 ? sbyte2<2>(sa, sb) : sbyte2<3>(sa, sb);
 			uint32_t h;
 			if (OFS) {
@@ -116,7 +122,7 @@ __device__ __forceinline__ void fwd2_row(uint32_t (&line)[W + 1], const uint32_t
 				h = MODE == 0 ? __viaddmax_s16x2_relu(left, gf2, u) : __viaddmax_s16x2(left, gf2, u);
 			}
 			// slots at or beyond the corridor are pinned to the sentinel: one LOP3 with loop-invariant masks instead of compare + select
-			if (j >= LO) h = (h & keepm[j - LO]) | ((MODE == 0 && !OFS) ? 0u : fillm[j - LO]);
+			if (!EXACT && j >= LO) h = (h & keepm[j - LO]) | ((MODE == 0 && !OFS) ? 0u : fillm[j - LO]);
 			const uint32_t clean = h & 0xFFFCFFFCu;
 			if (PTR) {
 				const uint32_t tag = imad_u32(clean, c_neg1, h);          // h - clean, FMA pipe
@@ -128,15 +134,15 @@ __device__ __forceinline__ void fwd2_row(uint32_t (&line)[W + 1], const uint32_t
 	}
 }
 
-template <int W, bool OFS = false>
+template <int W, bool OFS = false, int N = W>             // N: slots that can hold a value
 __device__ __forceinline__ uint32_t band_max(const uint32_t (&line)[W + 1], uint32_t acc) {
 #pragma unroll
-	for (int j = 0; j + 1 < W; j += 2) acc = OFS ? __vimax3_u16x2(acc, line[j], line[j + 1]) : __vimax3_s16x2(acc, line[j], line[j + 1]);
-	if (W & 1) acc = OFS ? __vmaxu2(acc, line[W - 1]) : __vmaxs2(acc, line[W - 1]);
+	for (int j = 0; j + 1 < N; j += 2) acc = OFS ? __vimax3_u16x2(acc, line[j], line[j + 1]) : __vimax3_s16x2(acc, line[j], line[j + 1]);
+	if (N & 1) acc = OFS ? __vmaxu2(acc, line[N - 1]) : __vmaxs2(acc, line[N - 1]);
 	return acc;
 }
 
-template <int W, int LO, int MODE>
+template <int W, int LO, int MODE, bool EXACT = false>
 __global__ void __launch_bounds__(128) align_s16_fwd2_kernel(const __grid_constant__ DevParams P, const PairDesc *__restrict__ pairs, int n,
 		const uint32_t *__restrict__ reads_fwd, const uint32_t *__restrict__ reads_rev, const uint16_t *__restrict__ rlen,
 		const uint32_t *__restrict__ ref4, uint32_t *__restrict__ ptr_scratch, int stride, int4 *__restrict__ best_out,
@@ -160,6 +166,7 @@ __global__ void __launch_bounds__(128) align_s16_fwd2_kernel(const __grid_consta
 	const bool vb = ia + 1 < n;
 	const int ib = vb ? ia + 1 : ia;
 	constexpr bool OFS = MODE == 0 && NGM_FWD_OFFSET != 0;
+	constexpr int WE = EXACT ? LO : W;                            // slots that are ever computed
 	constexpr int SENT = MODE == 0 ? 0 : 4 * kEndFreeMinS16;
 	const uint32_t SENT2 = OFS ? kOfs2 : pack2(SENT, SENT);
 	const uint32_t ZERO2 = OFS ? kOfs2 : 0u;                      // a cell value of 0 as stored
@@ -221,7 +228,7 @@ __global__ void __launch_bounds__(128) align_s16_fwd2_kernel(const __grid_consta
 		if (MODE == 0) {
 			cur_buf = (own_a != 0 && own_b != 0) ? 0 : ((own_a != 1 && own_b != 1) ? 1 : 2);
 #pragma unroll
-			for (int j = 0; j < W; ++j) *chk_at(cur_buf, j) = line[j];
+			for (int j = 0; j < WE; ++j) *chk_at(cur_buf, j) = line[j];
 		}
 #if NGM_FUNNEL_FMA
 #pragma unroll 1
@@ -231,12 +238,12 @@ __global__ void __launch_bounds__(128) align_s16_fwd2_kernel(const __grid_consta
 				const int t = tt + h2;
 				const int rca = (rda >> (4 * t)) & 7, rcb = (rdb >> (4 * t)) & 7;
 				uint32_t pw[T::kWords];
-				if (h2 == 0) fwd2_row<W, LO, MODE, true, true>(line, wa, wb, t, luta[rca], lutb[rcb], gr2, gf2, SENT2, keepm, fillm, c_four, c_neg1, pw);
-				else fwd2_row<W, LO, MODE, true, false>(line, wa, wb, t, luta[rca], lutb[rcb], gr2, gf2, SENT2, keepm, fillm, c_four, c_neg1, pw);
+				if (h2 == 0) fwd2_row<W, LO, MODE, true, true, EXACT>(line, wa, wb, t, luta[rca], lutb[rcb], gr2, gf2, SENT2, keepm, fillm, c_four, c_neg1, pw);
+				else fwd2_row<W, LO, MODE, true, false, EXACT>(line, wa, wb, t, luta[rca], lutb[rcb], gr2, gf2, SENT2, keepm, fillm, c_four, c_neg1, pw);
 #pragma unroll
 				for (int k = 0; k < T::kWords; ++k) prow[(size_t) k * tstride] = pw[k];
 				prow += row_stride;
-				if (MODE == 0) best = band_max<W, OFS>(line, best);
+				if (MODE == 0) best = band_max<W, OFS, WE>(line, best);
 				rc_a += (rca != kCodeNul);
 				rc_b += (rcb != kCodeNul);
 			}
@@ -246,11 +253,11 @@ NGM_UNROLL_N(NGM_FWD_ROW_UNROLL)
 		for (int t = 0; t < 8; ++t) {
 			const int rca = (rda >> (4 * t)) & 7, rcb = (rdb >> (4 * t)) & 7;
 			uint32_t pw[T::kWords];
-			fwd2_row<W, LO, MODE, true>(line, wa, wb, t, luta[rca], lutb[rcb], gr2, gf2, SENT2, keepm, fillm, c_four, c_neg1, pw);
+			fwd2_row<W, LO, MODE, true, true, EXACT>(line, wa, wb, t, luta[rca], lutb[rcb], gr2, gf2, SENT2, keepm, fillm, c_four, c_neg1, pw);
 #pragma unroll
 			for (int k = 0; k < T::kWords; ++k) prow[(size_t) k * tstride] = pw[k];
 			prow += row_stride;
-			if (MODE == 0) best = band_max<W, OFS>(line, best);
+			if (MODE == 0) best = band_max<W, OFS, WE>(line, best);
 			rc_a += (rca != kCodeNul);
 			rc_b += (rcb != kCodeNul);
 		}
@@ -283,7 +290,7 @@ NGM_UNROLL_N(NGM_FWD_ROW_UNROLL)
 		const int ma = half_lo(best), mb = half_hi(best);
 		// ---- replay: the block of each half's last improvement, from its checkpoint, until the half reaches its maximum ----
 #pragma unroll
-		for (int j = 0; j < W; ++j) line[j] = prmt(*chk_at(own_a, j), *chk_at(own_b, j), 0x7610u);
+		for (int j = 0; j < WE; ++j) line[j] = prmt(*chk_at(own_a, j), *chk_at(own_b, j), 0x7610u);
 #pragma unroll
 		for (int k = 0; k < G::kWin; ++k) {
 			wa[k] = __ldg(ca.wp + blk_a + k);
@@ -298,19 +305,19 @@ NGM_UNROLL_N(NGM_FWD_ROW_UNROLL)
 		for (int t = 0; t < 8; ++t) {
 			const int rca = (rda >> (4 * t)) & 7, rcb = (rdb >> (4 * t)) & 7;
 			uint32_t pw[T::kWords];
-			fwd2_row<W, LO, MODE, false>(line, wa, wb, t, luta[rca], lutb[rcb], gr2, gf2, SENT2, keepm, fillm, c_four, c_neg1, pw);
-			const uint32_t mx = band_max<W, OFS>(line, ZERO2);
+			fwd2_row<W, LO, MODE, false, true, EXACT>(line, wa, wb, t, luta[rca], lutb[rcb], gr2, gf2, SENT2, keepm, fillm, c_four, c_neg1, pw);
+			const uint32_t mx = band_max<W, OFS, WE>(line, ZERO2);
 			const bool hit_a = !found_a && half_lo(mx) == ma;
 			const bool hit_b = !found_b && half_hi(mx) == mb;
 			// the band of the row in which a half first reaches its maximum goes to a (by now free) checkpoint buffer
 			if (hit_a) {
 #pragma unroll
-				for (int j = 0; j < W; ++j) *chk_at(0, j) = line[j];
+				for (int j = 0; j < WE; ++j) *chk_at(0, j) = line[j];
 				brow_a = rr_a;
 			}
 			if (hit_b) {
 #pragma unroll
-				for (int j = 0; j < W; ++j) *chk_at(1, j) = line[j];
+				for (int j = 0; j < WE; ++j) *chk_at(1, j) = line[j];
 				brow_b = rr_b;
 			}
 			found_a = found_a || hit_a;
@@ -321,7 +328,7 @@ NGM_UNROLL_N(NGM_FWD_ROW_UNROLL)
 		int ra = 0, rb = 0;
 		bool fa_ = false, fb_ = false;
 #pragma unroll
-		for (int j = 0; j < W; ++j) {
+		for (int j = 0; j < WE; ++j) {
 			const bool ha = !fa_ && j < corridor && half_lo(*chk_at(0, j)) == ma;
 			const bool hb = !fb_ && j < corridor && half_hi(*chk_at(1, j)) == mb;
 			ra = ha ? j : ra;

@@ -43,41 +43,42 @@ __device__ __forceinline__ uint32_t spread2to4(uint32_t x16) {      // 8 two-bit
 __device__ __forceinline__ uint32_t nib_keep(int valid) { return valid >= 8 ? 0xFFFFFFFFu : (valid <= 0 ? 0u : ((1u << (4 * valid)) - 1u)); }
 
 // PACKED2 rows -> forward words, reverse-complement words (MappedRead::computeReverseSeq, MappedRead.cpp:36-67) and lengths in one
-// pass.  16 threads per row; a thread expands one 32-bit input word (16 bases) into two forward code words and assembles the two
-// reverse words of the same index from a 64-bit window of the (L1-resident) input row.  HBM-bound: 42 B in, 2 x 84 B out per 150 bp read.
-constexpr int kExpandRowsPerBlock = 16;
+// pass.  One thread per output word index (row, w): it writes forward word w and reverse word w, so a warp's stores are two runs of 32
+// consecutive words and the 40-byte input row stays in L1 for the ~21 threads that read it.  HBM-bound by design: 42 B in, 2 x 84 B out
+// per 150 bp read.  (The first form -- 16 threads per row, two words each, bounds-checked 64-bit windows -- issued 116 warp instructions
+// per row and was issue-bound at 1.29 ms per 10 M reads, profiles/r2_hot_path.md.)
+constexpr int kExpandThreads = 256;
 
-__global__ void __launch_bounds__(16 * kExpandRowsPerBlock) expand_packed2_kernel(const uint32_t *__restrict__ in, int rows, int in_words,
-		const uint16_t *__restrict__ len_in, int max_len, uint32_t *__restrict__ fwd, uint32_t *__restrict__ rev, uint16_t *__restrict__ rlen, int words) {
-	const int x = threadIdx.x & 15, row = blockIdx.x * kExpandRowsPerBlock + (threadIdx.x >> 4);
-	if (row >= rows) return;
+__global__ void __launch_bounds__(kExpandThreads) expand_packed2_kernel(const uint32_t *__restrict__ in, int rows, int in_words,
+		const uint16_t *__restrict__ len_in, int max_len, uint32_t *__restrict__ fwd, uint32_t *__restrict__ rev, uint16_t *__restrict__ rlen, int words,
+		uint32_t words_magic) {
+	const uint32_t idx = blockIdx.x * kExpandThreads + threadIdx.x;
+	const uint32_t row = __umulhi(idx, words_magic);                // idx / words (words_magic = ceil(2^32 / words); the launcher keeps idx in the exact range)
+	const int w = (int) (idx - row * (uint32_t) words);
+	if (row >= (uint32_t) rows) return;
 	const int len = min((int) len_in[row], max_len);
 	const uint32_t *r = in + (size_t) row * in_words;
-	auto word_at = [&](int q) -> uint32_t { return (q >= 0 && q < in_words) ? __ldg(r + q) : 0u; };
-	for (int w2 = x; 2 * w2 < words; w2 += 16) {
-		const uint32_t xin = word_at(w2);
-#pragma unroll
-		for (int h = 0; h < 2; ++h) {
-			const int w = 2 * w2 + h;
-			if (w >= words) break;
-			const uint32_t keep = nib_keep(len - 8 * w);
-			fwd[(size_t) row * words + w] = (spread2to4((xin >> (16 * h)) & 0xFFFFu) & keep) | (kNulWord & ~keep);
-			uint32_t out = kNulWord;
-			const int hi = len - 1 - 8 * w;                        // reverse word w: nibble k = complement of base hi - k
-			if (hi >= 0) {
-				const int lo = hi - 7;                                // may be negative: those nibbles are masked below
-				const int q = lo >> 4;                                // floor division (arithmetic shift)
-				const unsigned long long win = (unsigned long long) word_at(q) | ((unsigned long long) word_at(q + 1) << 32);
-				const uint32_t v = (uint32_t) (win >> (2 * (lo & 15))) & 0xFFFFu;      // bases lo .. hi
-				uint32_t y = __byte_perm(spread2to4(v), 0, 0x0123);
-				y = ((y >> 4) & 0x0F0F0F0Fu) | ((y & 0x0F0F0F0Fu) << 4);               // nibble k = base hi - k
-				const uint32_t kp = nib_keep(hi + 1);
-				out = ((y ^ 0x33333333u) & kp) | (kNulWord & ~kp);                     // A<->T, C<->G: code ^ 3
-			}
-			rev[(size_t) row * words + w] = out;
-		}
+	// forward word w: bases 8w .. 8w + 7 = half (w & 1) of input word w >> 1
+	const int qf = w >> 1;
+	const uint32_t xin = qf < in_words ? __ldg(r + qf) : 0u;
+	const uint32_t keep = nib_keep(len - 8 * w);
+	fwd[(size_t) idx] = (spread2to4((xin >> (16 * (w & 1))) & 0xFFFFu) & keep) | (kNulWord & ~keep);
+	// reverse word w: nibble k = complement of base hi - k
+	uint32_t out = kNulWord;
+	const int hi = len - 1 - 8 * w;
+	if (hi >= 0) {
+		const int lo = hi - 7;                                    // may be negative: those nibbles are masked below
+		const int q = lo >> 4;                                    // floor division (arithmetic shift)
+		const uint32_t w0 = (q >= 0) ? __ldg(r + q) : 0u;
+		const uint32_t w1 = (q + 1 < in_words) ? __ldg(r + q + 1) : 0u;
+		const uint32_t v = __funnelshift_r(w0, w1, 2 * (lo & 15)) & 0xFFFFu;      // bases lo .. hi
+		uint32_t y = __byte_perm(spread2to4(v), 0, 0x0123);
+		y = ((y >> 4) & 0x0F0F0F0Fu) | ((y & 0x0F0F0F0Fu) << 4);                   // nibble k = base hi - k
+		const uint32_t kp = nib_keep(hi + 1);
+		out = ((y ^ 0x33333333u) & kp) | (kNulWord & ~kp);                         // A<->T, C<->G: code ^ 3
 	}
-	if (x == 0) rlen[row] = (uint16_t) len;
+	rev[(size_t) idx] = out;
+	if (w == 0) rlen[row] = (uint16_t) len;
 }
 
 // bases that are not A/C/G/T: oclDefines.cl:64-80 classes (N 5, everything else 4; a NUL inside the row ends nothing here: lengths are explicit)
@@ -750,8 +751,16 @@ int install_reads(ngm_b200_ctx *c, int format, const void *d_reads, int n, int s
 	CU(c->d_rfwd.ensure((size_t) n * RW * 4));
 	CU(c->d_rrev.ensure((size_t) n * RW * 4));
 	CU(c->d_rrlen.ensure((size_t) n * 2));
-	expand_packed2_kernel<<<(n + kExpandRowsPerBlock - 1) / kExpandRowsPerBlock, 16 * kExpandRowsPerBlock, 0, st>>>(static_cast<const uint32_t *>(d_reads), n, stride / 4, d_len, c->dp.qml,
-			c->d_rfwd.as<uint32_t>(), c->d_rrev.as<uint32_t>(), c->d_rrlen.as<uint16_t>(), RW);
+	// idx / RW as mulhi(idx, ceil(2^32 / RW)) is exact while idx * e < 2^32, e = RW - 2^32 mod RW: launches of at most that many words
+	const uint32_t magic = (uint32_t) ((0x100000000ull + (unsigned long long) RW - 1) / (unsigned long long) RW);
+	const unsigned long long e = (unsigned long long) RW - (0x100000000ull % (unsigned long long) RW);
+	const int rows_per = (int) std::min<unsigned long long>(0x7FFFFFFFull / RW, (0xFFFFFFFFull / e) / RW);
+	for (int r0 = 0; r0 < n; r0 += rows_per) {
+		const int m = std::min(rows_per, n - r0);
+		expand_packed2_kernel<<<(unsigned) (((size_t) m * RW + kExpandThreads - 1) / kExpandThreads), kExpandThreads, 0, st>>>(
+				static_cast<const uint32_t *>(d_reads) + (size_t) r0 * (stride / 4), m, stride / 4, d_len + r0, c->dp.qml, c->d_rfwd.as<uint32_t>() + (size_t) r0 * RW,
+				c->d_rrev.as<uint32_t>() + (size_t) r0 * RW, c->d_rrlen.as<uint16_t>() + r0, RW, magic);
+	}
 	c->launches += 1;
 	if (n_exc) {
 		patch_exceptions_kernel<<<(n_exc + 255) / 256, 256, 0, st>>>(d_exc, n_exc, read_base, n, c->d_rrlen.as<uint16_t>(), c->d_rfwd.as<uint32_t>(),
