@@ -134,6 +134,71 @@ __device__ __forceinline__ void fwd2_row(uint32_t (&line)[W + 1], const uint32_t
 	}
 }
 
+// Row pairs on one window alignment (-DNGM_FWD_PAIR_ROWS=0: every row aligns its own window).  Rows t (even) and t + 1 read the same
+// reference nibbles, one slot apart: slot j of row t + OFF is nibble j + OFF of the window aligned for row t.  The pair therefore shares the
+// funnel shifts and the `>> 16` of the odd groups (12 ALU-pipe instructions per row at W = 28); the odd row pays with one more PRMT group.
+#ifndef NGM_FWD_PAIR_ROWS
+#define NGM_FWD_PAIR_ROWS 1
+#endif
+template <int W>
+struct PairGeom {
+	static constexpr int kNibbles = W + 1;                       // nibbles the two rows touch
+	static constexpr int kWords = (kNibbles + 7) / 8;            // aligned words
+	static constexpr int kSel = (kNibbles + 3) / 4;              // 16-bit PRMT selectors (groups of four nibbles)
+};
+
+// selectors of the window aligned for row t: sel[g] carries nibbles 4g .. 4g + 3 in its low 16 bits
+template <int W>
+__device__ __forceinline__ void fwd2_selectors(const uint32_t (&w)[BandGeom<W>::kWin], int t, uint32_t (&sel)[PairGeom<W>::kSel]) {
+	using PG = PairGeom<W>;
+#pragma unroll
+	for (int k = 0; k < PG::kWords; ++k) {
+		const uint32_t hi = k + 1 < BandGeom<W>::kWin ? w[k + 1] : 0u;      // (only the low nibbles of the last word are used)
+		const uint32_t al = __funnelshift_r(w[k], hi, 4 * t);
+		sel[2 * k] = al;
+		if (2 * k + 1 < PG::kSel) sel[2 * k + 1] = al >> 16;
+	}
+}
+
+// fwd2_row on shared selectors; OFF = 0 / 1: the row's distance from the row the window was aligned for
+template <int W, int LO, int MODE, bool PTR, bool EXACT, int OFF>
+__device__ __forceinline__ void fwd2_row_sel(uint32_t (&line)[W + 1], const uint32_t (&sela)[PairGeom<W>::kSel], const uint32_t (&selb)[PairGeom<W>::kSel],
+		const uint2 ta, const uint2 tb, const uint32_t gr2, const uint32_t gf2, const uint32_t SENT2, const uint32_t (&keepm)[W - LO + 1],
+		const uint32_t (&fillm)[W - LO + 1], const uint32_t c_four, const uint32_t c_neg1, uint32_t (&pw)[TagGeom<W>::kWords]) {
+	constexpr int NSLOT = EXACT ? LO : W;
+	uint32_t left = SENT2;
+	if (PTR) {
+#pragma unroll
+		for (int k = 0; k < TagGeom<W>::kWords; ++k) pw[k] = 0;
+	}
+#pragma unroll
+	for (int g = 0; g <= (NSLOT - 1 + OFF) / 4; ++g) {
+		const uint32_t sa = prmt(ta.x, ta.y, sela[g]);
+		const uint32_t sb = prmt(tb.x, tb.y, selb[g]);
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			const int j = 4 * g + i - OFF;
+			if (j < 0 || j >= NSLOT) continue;
+			const uint32_t s2 = i == 0 ? sbyte2<0>(sa, sb) : i == 1 ? sbyte2<1>(sa, sb) : i == 2 ? sbyte2<2>(sa, sb) : sbyte2<3>(sa, sb);
+			const uint32_t d = __vadd2(line[j], s2);
+			const uint32_t u = __viaddmax_s16x2(line[j + 1], gr2, d);
+			uint32_t h = MODE == 0 ? __viaddmax_s16x2_relu(left, gf2, u) : __viaddmax_s16x2(left, gf2, u);
+			if (!EXACT && j >= LO) h = (h & keepm[j - LO]) | (MODE == 0 ? 0u : fillm[j - LO]);
+			const uint32_t clean = h & 0xFFFCFFFCu;
+			if (PTR) {
+				const uint32_t tag = imad_u32(clean, c_neg1, h);          // h - clean, FMA pipe
+				pw[j >> 3] = imad_u32(pw[j >> 3], c_four, tag);           // 4 * pw + tag, FMA pipe
+			}
+			left = clean;
+			line[j] = clean;
+		}
+	}
+	if (PTR && EXACT) {                                           // slots LO .. W - 1 are never computed: their tags are zero shifts
+#pragma unroll
+		for (int j = LO; j < W; ++j) pw[j >> 3] = imad_u32(pw[j >> 3], c_four, 0u);
+	}
+}
+
 template <int W, bool OFS = false, int N = W>             // N: slots that can hold a value
 __device__ __forceinline__ uint32_t band_max(const uint32_t (&line)[W + 1], uint32_t acc) {
 #pragma unroll
@@ -240,6 +305,27 @@ __global__ void __launch_bounds__(128) align_s16_fwd2_kernel(const __grid_consta
 				uint32_t pw[T::kWords];
 				if (h2 == 0) fwd2_row<W, LO, MODE, true, true, EXACT>(line, wa, wb, t, luta[rca], lutb[rcb], gr2, gf2, SENT2, keepm, fillm, c_four, c_neg1, pw);
 				else fwd2_row<W, LO, MODE, true, false, EXACT>(line, wa, wb, t, luta[rca], lutb[rcb], gr2, gf2, SENT2, keepm, fillm, c_four, c_neg1, pw);
+#pragma unroll
+				for (int k = 0; k < T::kWords; ++k) prow[(size_t) k * tstride] = pw[k];
+				prow += row_stride;
+				if (MODE == 0) best = band_max<W, OFS, WE>(line, best);
+				rc_a += (rca != kCodeNul);
+				rc_b += (rcb != kCodeNul);
+			}
+		}
+#elif NGM_FWD_PAIR_ROWS && !NGM_FWD_OFFSET
+#pragma unroll 1
+		for (int tt = 0; tt < 8; tt += 2) {
+			uint32_t sela[PairGeom<W>::kSel], selb[PairGeom<W>::kSel];
+			fwd2_selectors<W>(wa, tt, sela);
+			fwd2_selectors<W>(wb, tt, selb);
+#pragma unroll
+			for (int h2 = 0; h2 < 2; ++h2) {
+				const int t = tt + h2;
+				const int rca = (rda >> (4 * t)) & 7, rcb = (rdb >> (4 * t)) & 7;
+				uint32_t pw[T::kWords];
+				if (h2 == 0) fwd2_row_sel<W, LO, MODE, true, EXACT, 0>(line, sela, selb, luta[rca], lutb[rcb], gr2, gf2, SENT2, keepm, fillm, c_four, c_neg1, pw);
+				else fwd2_row_sel<W, LO, MODE, true, EXACT, 1>(line, sela, selb, luta[rca], lutb[rcb], gr2, gf2, SENT2, keepm, fillm, c_four, c_neg1, pw);
 #pragma unroll
 				for (int k = 0; k < T::kWords; ++k) prow[(size_t) k * tstride] = pw[k];
 				prow += row_stride;

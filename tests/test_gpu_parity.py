@@ -48,7 +48,7 @@ def test_golden_fixtures(name, lane_mode):
 
 
 SHAPES = [(32, 10, 3000), (76, 16, 3000), (102, 20, 4000), (152, 27, 6000), (252, 42, 1500), (252, 80, 1000), (402, 65, 600),
-          (20, 5, 500), (60, 12, 1000), (152, 25, 1000), (152, 28, 1000), (1000, 155, 40)]
+          (20, 5, 500), (60, 12, 1000), (152, 25, 1000), (152, 28, 1000), (1000, 155, 40), (127, 23, 1500), (202, 35, 1000)]       # (23, 27, 35, 42: the exact-corridor forward kernels)
 
 
 @pytest.mark.parametrize("lane_mode", [1, 0])
