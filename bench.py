@@ -452,9 +452,10 @@ def main():
     dev_in = batch_in(d_packed.data_ptr(), d_len.data_ptr(), d_exc.data_ptr() if d_exc is not None else None, batch.cand_begin.data_ptr(), d_desc.data_ptr())
     dev_out = BatchOut(d_scores.data_ptr(), d_best.data_ptr(), d_mapq.data_ptr(), d_ntop.data_ptr(), d_pfail.data_ptr() if paired else None, d_recs.data_ptr(),
                        d_strings.data_ptr(), str_cap, 0, d_cursor.data_ptr())
-    cfg["step"] = ("ngm_b200_dev_run_batch: expand 2-bit reads (+ reverse complements) -> resolve descriptors -> score the candidates of multi-candidate reads -> "
-                   + ("top1PE (select_pairs)" if paired else "top1 + MAPQ") + " -> align + backtrace + CIGAR/MD of every winner"
-                   + ("" if paired else " (single-candidate reads take their score from the alignment's forward pass)"))
+    cfg["step"] = ("ngm_b200_dev_run_batch: expand 2-bit reads (+ reverse complements) -> resolve descriptors -> "
+                   + ("BatchScore of every candidate -> top1PE (select_pairs) -> forward pass + backtrace + CIGAR/MD of every winner" if paired else
+                      "forward pass with pointers over every candidate of reads with <= 4 candidates (BatchScore first for the others) -> top1 + MAPQ from the "
+                      "forward maxima -> backtrace + CIGAR/MD of the winner"))
 
     def resident_step():
         check(lib.ngm_b200_dev_run_batch(ctx, C.byref(dev_in), C.byref(dev_out), st))
@@ -546,6 +547,19 @@ def main():
     launch_sets = check(lib.ngm_b200_profile_read(ctx, C.byref(f_ms), C.byref(b_ms)))
     check(lib.ngm_b200_profile(ctx, 0))
     ms_fwd, ms_bt = float(f_ms.value), float(b_ms.value)
+    # the same split inside one resident step (single-end: the forward pass runs over EVERY candidate of reads with <= 4 candidates, the
+    # winner is picked from the forward maxima, only the winner is traced back)
+    step_fwd_ms = step_bt_ms = None
+    step_fwd_pairs = 0
+    if not paired:
+        check(lib.ngm_b200_profile(ctx, 1))
+        resident_step()
+        chunks = check(lib.ngm_b200_profile_read(ctx, C.byref(f_ms), C.byref(b_ms)))
+        check(lib.ngm_b200_profile(ctx, 0))
+        if chunks > 0:
+            step_fwd_ms, step_bt_ms = float(f_ms.value), float(b_ms.value)
+            cnt = batch.cand_begin[1:] - batch.cand_begin[:-1]
+            step_fwd_pairs = int(cnt[cnt <= 4].sum().item())
     pa, pi_, pm = C.c_double(0), C.c_double(0), C.c_double(0)
     check(lib.ngm_b200_alu_peak(ctx, C.byref(pa), C.byref(pi_), C.byref(pm)))
     alu_rate, imad_rate, mixed_rate = float(pa.value), float(pi_.value), float(pm.value)
@@ -1036,6 +1050,9 @@ def main():
                          "score_gcups": score_gcups, "peak_score_gcups": peak_score_gcups, "score_frac": score_gcups / peak_score_gcups,
                          "align_forward_gcups": fwd_gcups, "peak_forward_gcups": peak_fwd_gcups, "align_forward_frac": fwd_gcups / peak_fwd_gcups,
                          "align_launch_set_gcups": align_gcups, "align_launch_set_frac": align_gcups / peak_fwd_gcups,
+                         "step_forward_gcups": (step_fwd_pairs * CELLS_PER_PAIR / (step_fwd_ms * 1e-3) / 1e9) if step_fwd_ms else None,
+                         "issue_model": "profiles/r2_issue_rates.md: measured issue rates of every instruction of the inner loop; the forward kernel's loop needs "
+                                        "6.1 integer-pipe instructions per slot (two cells) and runs at 86 % of that bound",
                          "survey_model_peak_gcups_s16x2": survey_peak_gcups, "score_frac_of_survey_model": score_gcups / survey_peak_gcups,
                          "align_launch_set_frac_of_survey_model": align_gcups / survey_peak_gcups,
                          "sm_count": sm_count, "sm_mhz_under_load": sm_mhz,
@@ -1044,7 +1061,9 @@ def main():
         "kernel_ms": {"set_reads_packed2": ms_expand, "set_reads_ascii": ms_pack, "score_all_pairs": ms_score, "score_in_step": ms_score_step, "align_launch_sets": ms_align, "align_forward": ms_fwd,
                       "align_backtrace_format": ms_bt, "align_without_known_scores": ms_align_unscored, "launch_sets": launch_sets,
                       "pairs_scored_in_step": multi_pairs, "score_share": ms_score_step / (ms_max / args.steps), "align_share": ms_align / (ms_max / args.steps),
-                      "classic_calls_equal_batch": classic_equal, "pack_reads_host_seconds": pack_host_s},
+                      "classic_calls_equal_batch": classic_equal, "pack_reads_host_seconds": pack_host_s,
+                      "step_forward_all": step_fwd_ms, "step_pick_backtrace": step_bt_ms, "step_forward_pairs": step_fwd_pairs,
+                      "note": "score_* / align_* time the classic entry points on the same data (one kernel each); step_* are the kernels of one resident step"},
         "candidate_search": cs_info,
         "cpu_baseline": cpu_baseline, "parity_sample": parity, "strict_path": strict,
         "counters": {"reads": total_reads, "mapped": ctr["mapped"], "pairs_scored": ctr["pairs_scored"], "string_bytes": used_strings},

@@ -598,8 +598,16 @@ int enqueue_fwd_all(ngm_b200_ctx *c, LaneBuf &L, const DevIn &in, const DevOut &
 		a.range = L.d_fbegin.as<int>() + r0;
 		a.range_m = m;
 		a.phase = 1;
+		// ngm_b200_profile: forward kernel | pick + backtrace kernel of every chunk between events (bench.py's in-step kernel split)
+		const bool prof = c->profile && c->pev_used + 3 <= 3 * 64;
+		if (prof) {
+			for (int k = 0; k < 3; ++k)
+				if (c->pev[c->pev_used + k] == nullptr) CU(cudaEventCreate(&c->pev[c->pev_used + k]));
+			CU(cudaEventRecord(c->pev[c->pev_used], st));
+		}
 		cudaError_t e = launch_align_s16(c->capacity, m0, a, st);
 		if (e != cudaSuccess) return fail(NGM_B200_ECUDA, "forward kernel launch: %s", cudaGetErrorString(e));
+		if (prof) CU(cudaEventRecord(c->pev[c->pev_used + 1], st));
 		if (m0 == 0)
 			batch_pick_kernel<0><<<(m + 255) / 256, 256, 0, st>>>(m, r0, in.cb, L.d_fbegin.as<int>(), L.d_F.as<PairDesc>(), c->d_best.as<int4>(), strata, out.scores,
 					out.best_pair, out.mapq, out.num_top, L.d_slot.as<int>());
@@ -613,6 +621,10 @@ int enqueue_fwd_all(ngm_b200_ctx *c, LaneBuf &L, const DevIn &in, const DevOut &
 		a.ops_stride = Gpad;
 		e = launch_align_s16(c->capacity, m0, a, st);
 		if (e != cudaSuccess) return fail(NGM_B200_ECUDA, "backtrace kernel launch: %s", cudaGetErrorString(e));
+		if (prof) {
+			CU(cudaEventRecord(c->pev[c->pev_used + 2], st));
+			c->pev_used += 3;
+		}
 		c->launches += 3;
 	}
 	CU(cudaGetLastError());
