@@ -6,10 +6,6 @@
 #include "ngm_align_s16.cuh"
 #include "ngm_align_s16v2.cuh"
 
-#ifndef NGM_EXACT_LIST
-#define NGM_EXACT_LIST(X) X(24, 23) X(28, 27) X(36, 35) X(44, 42)
-#endif
-
 namespace ngm {
 
 cudaError_t launch_align_s16(int capacity, int mode, const AlignArgs &a, cudaStream_t st) {

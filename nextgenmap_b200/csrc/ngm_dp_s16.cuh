@@ -37,7 +37,15 @@ __device__ __forceinline__ uint32_t sbyte2(uint32_t a, uint32_t b) {
 
 __device__ __forceinline__ uint32_t pack2(int lo, int hi) { return ((uint32_t) hi << 16) | ((uint32_t) lo & 0xFFFFu); }
 
-template <int W, int LO, int MODE>
+// Shared selectors (-DNGM_SCORE_SHARED_SEL=0: every row aligns its own window).  With the eight rows of a window word unrolled, row t reads
+// nibble j + t of the window as it sits in the registers: the rows share the sixteen-bit selector halves of the window words, no row needs a
+// funnel shift, and slot j of row t takes byte (j + t) & 3 of group (j + t) >> 2.  EXACT: the corridor is LO exactly (compile-time): slots
+// >= LO are never computed and no slot carries the run-time corridor select.
+#ifndef NGM_SCORE_SHARED_SEL
+#define NGM_SCORE_SHARED_SEL (NGM_SCORE_ROW_UNROLL == 8)
+#endif
+
+template <int W, int LO, int MODE, bool EXACT = false>
 __global__ void __launch_bounds__(128) score_s16_kernel(const __grid_constant__ DevParams P, const PairDesc *__restrict__ pairs, int n,
 		const uint32_t *__restrict__ reads_fwd, const uint32_t *__restrict__ reads_rev, const uint16_t *__restrict__ rlen,
 		const uint32_t *__restrict__ ref4, float *__restrict__ out, const int *__restrict__ sel, const int *__restrict__ n_dev) {
@@ -79,6 +87,44 @@ __global__ void __launch_bounds__(128) score_s16_kernel(const __grid_constant__ 
 		prev_a = cur_a;
 		prev_b = cur_b;
 		const uint32_t next_a = __ldg(ca.wp + qw + G::kWin), next_b = __ldg(cb.wp + qw + G::kWin);
+#if NGM_SCORE_SHARED_SEL
+		constexpr int NSLOT = EXACT ? LO : W;
+		constexpr int NSEL = (NSLOT + 7 + 3) / 4;                  // selectors the eight rows touch (nibbles 0 .. NSLOT + 6)
+		uint32_t sela[NSEL], selb[NSEL];
+#pragma unroll
+		for (int g = 0; g < NSEL; ++g) {
+			sela[g] = (g & 1) ? (wa[g >> 1] >> 16) : wa[g >> 1];
+			selb[g] = (g & 1) ? (wb[g >> 1] >> 16) : wb[g >> 1];
+		}
+#pragma unroll
+		for (int t = 0; t < 8; ++t) {
+			const uint2 ta = luta[(rda >> (4 * t)) & 7];
+			const uint2 tb = lutb[(rdb >> (4 * t)) & 7];
+			uint32_t left = SENT2;
+#pragma unroll
+			for (int g = t / 4; g <= (NSLOT - 1 + t) / 4; ++g) {
+				const uint32_t sa = prmt(ta.x, ta.y, sela[g]);
+				const uint32_t sb = prmt(tb.x, tb.y, selb[g]);
+#pragma unroll
+				for (int i = 0; i < 4; ++i) {
+					const int j = 4 * g + i - t;
+					if (j < 0 || j >= NSLOT) continue;
+					const uint32_t s2 = i == 0 ? sbyte2<0>(sa, sb) : i == 1 ? sbyte2<1>(sa, sb) : i == 2 ? sbyte2<2>(sa, sb) : sbyte2<3>(sa, sb);
+					const uint32_t d = __vadd2(line[j], s2);
+					const uint32_t u = __viaddmax_s16x2(line[j + 1], gr2, d);
+					uint32_t h = MODE == 0 ? __viaddmax_s16x2_relu(left, gf2, u) : __viaddmax_s16x2(left, gf2, u);
+					if (!EXACT && j >= LO) h = (j < corridor) ? h : SENT2;
+					left = h;
+					line[j] = h;
+				}
+			}
+			if (MODE == 0) {
+#pragma unroll
+				for (int j = 0; j + 1 < NSLOT; j += 2) best = __vimax3_s16x2(best, line[j], line[j + 1]);
+				if (NSLOT & 1) best = __vmaxs2(best, line[NSLOT - 1]);
+			}
+		}
+#else
 NGM_SUNROLL_N(NGM_SCORE_ROW_UNROLL)
 		for (int t = 0; t < 8; ++t) {
 			const uint2 ta = luta[(rda >> (4 * t)) & 7];
@@ -112,6 +158,7 @@ NGM_SUNROLL_N(NGM_SCORE_ROW_UNROLL)
 				if (W & 1) best = __vmaxs2(best, line[W - 1]);
 			}
 		}
+#endif
 #pragma unroll
 		for (int k = 0; k + 1 < G::kWin; ++k) {
 			wa[k] = wa[k + 1];

@@ -17,6 +17,12 @@ namespace ngm {
 	X(12, 1) X(16, 13) X(20, 17) X(24, 21) X(28, 25) X(32, 29) X(36, 33) X(40, 37) X(44, 41) X(48, 45) \
 	X(56, 49) X(64, 57) X(72, 65) X(80, 73) X(96, 81) X(112, 97) X(128, 113) X(160, 129)
 
+// (capacity, corridor) pairs with kernels that know the corridor at compile time: the corridors NGM derives from common read lengths
+// (5 + 0.15 x length: 125 bp -> 23, 150 bp -> 27, 200 bp -> 35, 250 bp -> 42)
+#ifndef NGM_EXACT_LIST
+#define NGM_EXACT_LIST(X) X(24, 23) X(28, 27) X(36, 35) X(44, 42)
+#endif
+
 constexpr int kMaxCorridor = 160;
 // the tagged s16x2 align kernel keeps band + snapshot in registers: beyond these capacities it would spill
 constexpr int kAlignS16MaxLocal = 48;
