@@ -34,6 +34,12 @@
 namespace ngm {
 
 constexpr int kEndFreeMinS16 = -7900;
+// rows per loop body of the first-generation forward kernel on wide bands (capacity > 48).  Measured on B200: 250 bp / corridor 80 (5 M
+// alignments) 8 rows 48.2 ms, 4 rows 39.4, 2 rows 28.3, 1 row 26.4; 400 bp / corridor 65 (capacity 72) 90.0 / 85.9 / 68.5 / 70.5 ms.
+// ncu on the eight-row body: `no_instruction` 3.4 stalls per issue, integer pipe 40 % busy -- ~100 KB of SASS per body.
+#ifndef NGM_FWD1_WIDE_UNROLL
+#define NGM_FWD1_WIDE_UNROLL(W) ((W) >= 80 ? 1 : 2)
+#endif
 
 template <int W>
 struct TagGeom {
@@ -349,7 +355,9 @@ __global__ void __launch_bounds__(128) align_s16_fwd_kernel(const __grid_constan
 			const uint32_t next_a = __ldg(ca.wp + qw + G::kWin), next_b = __ldg(cb.wp + qw + G::kWin);
 			spec_a |= (next_a & nib_mask(wend_a - 8 * (qw + G::kWin))) | (cur_a & nib_mask(ca.len - 8 * qw));
 			spec_b |= (next_b & nib_mask(wend_b - 8 * (qw + G::kWin))) | (cur_b & nib_mask(cb.len - 8 * qw));
-#pragma unroll
+			// wide bands: the fully unrolled eight-row body is ~100 KB of SASS at W = 80 (instruction fetch)
+			constexpr int kUnroll = W > kAlignS16MaxLocal ? NGM_FWD1_WIDE_UNROLL(W) : 8;
+#pragma unroll kUnroll
 			for (int t = 0; t < 8; ++t) {
 				const int rca = (rda >> (4 * t)) & 7, rcb = (rdb >> (4 * t)) & 7;
 				const uint2 ta = luta[rca];
@@ -357,8 +365,8 @@ __global__ void __launch_bounds__(128) align_s16_fwd_kernel(const __grid_constan
 				uint32_t ala[G::kAligned], alb[G::kAligned];
 #pragma unroll
 				for (int k = 0; k < G::kAligned; ++k) {
-					ala[k] = t == 0 ? wa[k] : __funnelshift_r(wa[k], wa[k + 1], 4 * t);
-					alb[k] = t == 0 ? wb[k] : __funnelshift_r(wb[k], wb[k + 1], 4 * t);
+					ala[k] = (kUnroll == 8 && t == 0) ? wa[k] : __funnelshift_r(wa[k], wa[k + 1], 4 * t);
+					alb[k] = (kUnroll == 8 && t == 0) ? wb[k] : __funnelshift_r(wb[k], wb[k + 1], 4 * t);
 				}
 				uint32_t left = SENT2;
 				uint32_t pw[T::kWords];

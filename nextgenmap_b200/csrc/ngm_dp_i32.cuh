@@ -33,6 +33,14 @@ struct BandGeom {
 	static constexpr int kPtrWords = (W + 15) / 16;       // 2 bits per cell
 };
 
+// Rows per unrolled loop body of the int32 kernels: eight on narrow bands; wide bands (capacity > 48) would not fit the instruction cache
+// (the s16x2 kernels measured 1.7x on this, see NGM_FWD1_WIDE_UNROLL).  -DNGM_I32_WIDE_UNROLL=8 restores the full unroll.
+#ifndef NGM_I32_WIDE_UNROLL
+#define NGM_I32_WIDE_UNROLL 2
+#endif
+template <int W>
+constexpr int kUnrollI32 = W > 48 ? NGM_I32_WIDE_UNROLL : 8;
+
 // Everything the row loop needs about one pair.
 struct PairCtx {
 	const uint32_t *rp;      // packed read row
@@ -94,12 +102,12 @@ __global__ void __launch_bounds__(128) score_i32_kernel(const __grid_constant__ 
 		const uint32_t rdw = __funnelshift_l(prev, cur, 4 * c.sub);
 		prev = cur;
 		const uint32_t nextw = __ldg(c.wp + qw + G::kWin);
-#pragma unroll
+#pragma unroll kUnrollI32<W>
 		for (int t = 0; t < 8; ++t) {
 			const uint2 tab = lut[(rdw >> (4 * t)) & 7];
 			uint32_t al[G::kAligned];
 #pragma unroll
-			for (int k = 0; k < G::kAligned; ++k) al[k] = t == 0 ? win[k] : __funnelshift_r(win[k], win[k + 1], 4 * t);
+			for (int k = 0; k < G::kAligned; ++k) al[k] = (kUnrollI32<W> == 8 && t == 0) ? win[k] : __funnelshift_r(win[k], win[k + 1], 4 * t);
 			int left = SENT;
 #pragma unroll
 			for (int m = 0; m < G::kGroups; ++m) {
@@ -179,13 +187,13 @@ __device__ __forceinline__ void forward_i32(const DevParams &P, const uint2 *s_l
 		const uint32_t rdw = __funnelshift_l(prev, cur, 4 * c.sub);
 		prev = cur;
 		const uint32_t nextw = __ldg(c.wp + qw + G::kWin);
-#pragma unroll
+#pragma unroll kUnrollI32<W>
 		for (int t = 0; t < 8; ++t) {
 			const int rc = (rdw >> (4 * t)) & 7;
 			const uint2 tab = lut[rc];
 			uint32_t al[G::kAligned];
 #pragma unroll
-			for (int k = 0; k < G::kAligned; ++k) al[k] = t == 0 ? win[k] : __funnelshift_r(win[k], win[k + 1], 4 * t);
+			for (int k = 0; k < G::kAligned; ++k) al[k] = (kUnrollI32<W> == 8 && t == 0) ? win[k] : __funnelshift_r(win[k], win[k + 1], 4 * t);
 			int left = SENT;
 			int rowbest = 0;
 			uint32_t pw[G::kPtrWords];

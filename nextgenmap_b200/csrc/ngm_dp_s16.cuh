@@ -41,6 +41,10 @@ __device__ __forceinline__ uint32_t pack2(int lo, int hi) { return ((uint32_t) h
 // nibble j + t of the window as it sits in the registers: the rows share the sixteen-bit selector halves of the window words, no row needs a
 // funnel shift, and slot j of row t takes byte (j + t) & 3 of group (j + t) >> 2.  EXACT: the corridor is LO exactly (compile-time): slots
 // >= LO are never computed and no slot carries the run-time corridor select.
+// rows per loop body on wide bands (capacity > 48): 250 bp / corridor 80 24.7 ms (8 rows) -> 22.4 ms (2 rows); 400 bp 66.5 -> 61.8 ms
+#ifndef NGM_SCORE_WIDE_UNROLL
+#define NGM_SCORE_WIDE_UNROLL 2
+#endif
 #ifndef NGM_SCORE_SHARED_SEL
 #define NGM_SCORE_SHARED_SEL (NGM_SCORE_ROW_UNROLL == 8)
 #endif
@@ -87,7 +91,9 @@ __global__ void __launch_bounds__(128) score_s16_kernel(const __grid_constant__ 
 		prev_a = cur_a;
 		prev_b = cur_b;
 		const uint32_t next_a = __ldg(ca.wp + qw + G::kWin), next_b = __ldg(cb.wp + qw + G::kWin);
-#if NGM_SCORE_SHARED_SEL
+		// wide bands: the eight-row body no longer fits the instruction cache (W = 80: ~50 KB); NGM_SCORE_WIDE_UNROLL rows per body there
+		constexpr int kUnrollS = W > 48 ? NGM_SCORE_WIDE_UNROLL : NGM_SCORE_ROW_UNROLL;
+		if constexpr (NGM_SCORE_SHARED_SEL && kUnrollS == 8) {
 		constexpr int NSLOT = EXACT ? LO : W;
 		constexpr int NSEL = (NSLOT + 7 + 3) / 4;                  // selectors the eight rows touch (nibbles 0 .. NSLOT + 6)
 		uint32_t sela[NSEL], selb[NSEL];
@@ -124,16 +130,16 @@ __global__ void __launch_bounds__(128) score_s16_kernel(const __grid_constant__ 
 				if (NSLOT & 1) best = __vmaxs2(best, line[NSLOT - 1]);
 			}
 		}
-#else
-NGM_SUNROLL_N(NGM_SCORE_ROW_UNROLL)
+		} else {
+#pragma unroll kUnrollS
 		for (int t = 0; t < 8; ++t) {
 			const uint2 ta = luta[(rda >> (4 * t)) & 7];
 			const uint2 tb = lutb[(rdb >> (4 * t)) & 7];
 			uint32_t ala[G::kAligned], alb[G::kAligned];
 #pragma unroll
 			for (int k = 0; k < G::kAligned; ++k) {
-				ala[k] = (NGM_SCORE_ROW_UNROLL == 8 && t == 0) ? wa[k] : __funnelshift_r(wa[k], wa[k + 1], 4 * t);
-				alb[k] = (NGM_SCORE_ROW_UNROLL == 8 && t == 0) ? wb[k] : __funnelshift_r(wb[k], wb[k + 1], 4 * t);
+				ala[k] = (kUnrollS == 8 && t == 0) ? wa[k] : __funnelshift_r(wa[k], wa[k + 1], 4 * t);
+				alb[k] = (kUnrollS == 8 && t == 0) ? wb[k] : __funnelshift_r(wb[k], wb[k + 1], 4 * t);
 			}
 			uint32_t left = SENT2;
 #pragma unroll
@@ -158,7 +164,7 @@ NGM_SUNROLL_N(NGM_SCORE_ROW_UNROLL)
 				if (W & 1) best = __vmaxs2(best, line[W - 1]);
 			}
 		}
-#endif
+		}
 #pragma unroll
 		for (int k = 0; k + 1 < G::kWin; ++k) {
 			wa[k] = wa[k + 1];
