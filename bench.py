@@ -559,7 +559,9 @@ def main():
         if chunks > 0:
             step_fwd_ms, step_bt_ms = float(f_ms.value), float(b_ms.value)
             cnt = batch.cand_begin[1:] - batch.cand_begin[:-1]
-            step_fwd_pairs = int(cnt[cnt <= 4].sum().item())
+            # narrow local bands: forward pass over every candidate of reads with <= 4 candidates; wide bands (capacity > 48) score every
+            # candidate first and run the forward pass (maximum known) on the winners only
+            step_fwd_pairs = int(cnt[cnt <= 4].sum().item()) + int((cnt > 4).sum().item()) if corridor <= 48 else n
     pa, pi_, pm = C.c_double(0), C.c_double(0), C.c_double(0)
     check(lib.ngm_b200_alu_peak(ctx, C.byref(pa), C.byref(pi_), C.byref(pm)))
     alu_rate, imad_rate, mixed_rate = float(pa.value), float(pi_.value), float(pm.value)
