@@ -102,10 +102,10 @@ cudaError_t launch_align_s16(int capacity, int mode, const AlignArgs &a, cudaStr
 	const dim3 b2(256), g2((items + 255) / 256);
 	if (mode == 0)
 		backtrace_format_kernel<0><<<g2, b2, 0, st>>>(a.P, a.pairs, items, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, a.ptr_scratch, capacity,
-				a.best_scratch, a.ops_scratch, a.stride, a.ops_cap, a.recs, a.strings, a.str_cap, a.cursor, a.out_best, a.slot_of, a.range, ops_stride);
+				a.best_scratch, a.ops_scratch, a.stride, a.ops_cap, a.recs, a.strings, a.str_cap, a.cursor, a.out_best, a.slot_of, a.range, ops_stride, a.items_dev, a.rec_of);
 	else
 		backtrace_format_kernel<1><<<g2, b2, 0, st>>>(a.P, a.pairs, items, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, a.ptr_scratch, capacity,
-				a.best_scratch, a.ops_scratch, a.stride, a.ops_cap, a.recs, a.strings, a.str_cap, a.cursor, a.out_best, a.slot_of, a.range, ops_stride);
+				a.best_scratch, a.ops_scratch, a.stride, a.ops_cap, a.recs, a.strings, a.str_cap, a.cursor, a.out_best, a.slot_of, a.range, ops_stride, a.items_dev, a.rec_of);
 	return cudaGetLastError();
 }
 

@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(256) backtrace_format_kernel(const __grid_cons
 		const uint32_t *__restrict__ ref4, const uint32_t *__restrict__ ptr_scratch, int capacity, const int4 *__restrict__ best_in,
 		uint16_t *__restrict__ ops_scratch, int stride, int ops_cap, ngm_b200_align_rec *__restrict__ recs, char *__restrict__ strings,
 		uint32_t str_cap, uint32_t *__restrict__ cursor, float *__restrict__ out_best, const int *__restrict__ slot_of,
-		const int *__restrict__ range, int ops_stride) {
+		const int *__restrict__ range, int ops_stride, const int *__restrict__ items_dev, const int *__restrict__ rec_of) {
 	__shared__ uint2 s_lut[16];
 	__shared__ uint32_t s_ring[kRing][256];
 	if (threadIdx.x < 16) s_lut[threadIdx.x] = P.lut[threadIdx.x];
@@ -512,6 +512,8 @@ __global__ void __launch_bounds__(256) backtrace_format_kernel(const __grid_cons
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	// slot_of != nullptr: thread idx writes the record of item idx (a read of the chunk) from the forward pass's slot slot_of[idx]
 	// (-1: nothing to align); the pair list starts at pairs[range[0]].  Otherwise item idx IS slot idx.
+	// items_dev: the number of items is only known on the device; rec_of: item idx writes recs[rec_of[idx]].
+	if (items_dev != nullptr) n = min(n, *items_dev);
 	const bool in_range = idx < n;
 	const int slot = in_range ? (slot_of != nullptr ? slot_of[idx] : idx) : -1;
 	const bool valid = slot >= 0;
@@ -553,7 +555,7 @@ __global__ void __launch_bounds__(256) backtrace_format_kernel(const __grid_cons
 	if (t.ok && (uint64_t) off + need <= (uint64_t) str_cap) format_cigar_md<true>(P, c, ops, ops_stride, t, strings + off, strings + off + f.cigar_len);
 	ngm_b200_align_rec r;
 	fill_record(r, t, f, off);
-	store_record(recs, idx, r);
+	store_record(recs, rec_of != nullptr ? rec_of[idx] : idx, r);
 }
 
 }  // namespace ngm

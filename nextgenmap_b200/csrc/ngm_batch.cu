@@ -282,7 +282,7 @@ constexpr int kFwdAllMax = 4;
 template <int FMT>
 __global__ void __launch_bounds__(256) batch_plan_all_kernel(int n_reads, const int *__restrict__ cb, const void *__restrict__ desc, PairDesc *__restrict__ rp,
 		unsigned long long concat_len, unsigned long long n_region_nib, const uint16_t *__restrict__ rlen, int *__restrict__ fcnt, int *__restrict__ sel,
-		int *__restrict__ n_sel) {
+		int *__restrict__ n_sel, ngm_b200_pair *__restrict__ pairs16) {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	const bool valid = r < n_reads;
 	int b = 0, e = 0;
@@ -309,6 +309,13 @@ __global__ void __launch_bounds__(256) batch_plan_all_kernel(int n_reads, const 
 		d.read_idx = (uint32_t) r;
 		d.flags = (fl & (PF_REVERSE | PF_DIR | PF_INACTIVE)) | (empty ? PF_INACTIVE : 0u);
 		rp[i] = d;
+		if (pairs16 != nullptr) {                                  // top1PE reads ngm_b200_pair records
+			ngm_b200_pair p;
+			p.window_start = ws;
+			p.read_index = (uint32_t) r;
+			p.flags = fl;
+			pairs16[i] = p;
+		}
 	}
 	if (valid) fcnt[r] = cnt <= kFwdAllMax ? cnt : 1;
 	if (r == n_reads) fcnt[r] = 0;
@@ -330,17 +337,26 @@ __global__ void __launch_bounds__(256) batch_plan_all_kernel(int n_reads, const 
 // top-1 of the reads with more than kFwdAllMax candidates (they were scored), and the forward list: F[fbegin[r] ..) = all candidates of a
 // small read / the winner of a big one
 __global__ void __launch_bounds__(256) batch_fill_fwd_kernel(int n_reads, const int *__restrict__ cb, const PairDesc *__restrict__ rp, const float *__restrict__ scores,
-		const int *__restrict__ fbegin, int strata, PairDesc *__restrict__ F, int *__restrict__ best_pair, int *__restrict__ mapq, int *__restrict__ num_top) {
+		const int *__restrict__ fbegin, int strata, PairDesc *__restrict__ F, int *__restrict__ best_pair, int *__restrict__ mapq, int *__restrict__ num_top,
+		int paired) {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= n_reads) return;
 	const int b = cb[r], e = cb[r + 1], f0 = fbegin[r];
 	if (e - b <= kFwdAllMax) {
 		for (int i = b; i < e; ++i) F[f0 + (i - b)] = rp[i];
-		if (e == b) {
+		if (e == b && !paired) {
 			best_pair[r] = -1;
 			mapq[r] = 0;
 			if (num_top != nullptr) num_top[r] = 0;
 		}
+		return;
+	}
+	if (paired) {                                                 // the winner is only known after top1PE: an idle slot for now
+		PairDesc d;
+		d.win_nib = 0;
+		d.read_idx = (uint32_t) r;
+		d.flags = PF_INACTIVE;
+		F[f0] = d;
 		return;
 	}
 	float best = 0.0f, second = 0.0f;
@@ -390,11 +406,17 @@ __global__ void __launch_bounds__(256) batch_fill_fwd_kernel(int n_reads, const 
 template <int MODE>
 __global__ void __launch_bounds__(256) batch_pick_kernel(int m, int r0, const int *__restrict__ cb, const int *__restrict__ fbegin, const PairDesc *__restrict__ F,
 		const int4 *__restrict__ best_in, int strata, float *__restrict__ scores, int *__restrict__ best_pair, int *__restrict__ mapq, int *__restrict__ num_top,
-		int *__restrict__ slot_of) {
+		int *__restrict__ slot_of, int paired) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= m) return;
 	const int r = r0 + i;
 	const int b = cb[r], e = cb[r + 1], base = fbegin[r0], f0 = fbegin[r] - base;
+	if (paired) {                                                 // scores only: the selection is top1PE's (batch_slot_pairs_kernel follows it)
+		if (e - b <= kFwdAllMax)
+			for (int j = 0; j < e - b; ++j)
+				scores[b + j] = (F[base + f0 + j].flags & PF_INACTIVE) ? (MODE == 0 ? -1.0f : (float) kEndFreeMin) : (float) best_in[f0 + j].z;
+		return;
+	}
 	if (e - b > kFwdAllMax) {
 		slot_of[i] = best_pair[r] >= 0 ? f0 : -1;
 		return;
@@ -440,6 +462,27 @@ __global__ void __launch_bounds__(256) batch_pick_kernel(int m, int r0, const in
 	slot_of[i] = sl;
 }
 
+// paired batches after top1PE of a chunk: the forward slot of every small read's winner; the winners of big reads (scored, not yet
+// forwarded) go to the late list and are aligned in a second, usually empty, pass
+__global__ void __launch_bounds__(256) batch_slot_pairs_kernel(int m, int r0, const int *__restrict__ cb, const int *__restrict__ fbegin, const PairDesc *__restrict__ rp,
+		const int *__restrict__ best_pair, int *__restrict__ slot_of, PairDesc *__restrict__ late_pairs, int *__restrict__ late_item, int *__restrict__ late_range) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= m) return;
+	const int r = r0 + i;
+	const int b = cb[r], e = cb[r + 1], bp = best_pair[r];
+	int sl = -1;
+	if (bp >= 0) {
+		if (e - b <= kFwdAllMax) {
+			sl = fbegin[r] - fbegin[r0] + (bp - b);
+		} else {
+			const int k = atomicAdd(late_range + 1, 1);            // late_range = {0, number of late winners}
+			late_pairs[k] = rp[bp];
+			late_item[k] = i;
+		}
+	}
+	slot_of[i] = sl;
+}
+
 __global__ void batch_set_u32_kernel(uint32_t *p, uint32_t v, int *q) {
 	if (p != nullptr) *p = v;
 	if (q != nullptr) *q = 0;
@@ -460,13 +503,13 @@ __global__ void __launch_bounds__(256) batch_add_base_kernel(int n, int *__restr
 // ---------------------------------------------------------------------------------------------------------
 struct LaneBuf {
 	DevBuf d_in_reads, d_in_len, d_in_exc, d_cb, d_desc, d_rp, d_pairs16, d_sel, d_nsel, d_scores, d_best, d_mapq, d_ntop, d_pfail, d_wp, d_wscores, d_obest,
-			d_recs, d_strings, d_cursor, d_maxhit, d_fcnt, d_fbegin, d_F, d_slot, d_scan_tmp, d_tsel, d_tnsel;
+			d_recs, d_strings, d_cursor, d_maxhit, d_fcnt, d_fbegin, d_F, d_slot, d_scan_tmp, d_tsel, d_tnsel, d_late_pairs, d_late_item, d_late_range;
 	cudaEvent_t searched = nullptr;                                // ngm_b200_map_batch: candidate search of the lane's sub-batch has finished
 	cudaEvent_t done = nullptr;
 	int pending = -1;                                              // sub-batch whose strings still have to be fetched
 	void release() {
 		DevBuf *all[] = { &d_in_reads, &d_in_len, &d_in_exc, &d_cb, &d_desc, &d_rp, &d_pairs16, &d_sel, &d_nsel, &d_scores, &d_best, &d_mapq, &d_ntop, &d_pfail,
-				&d_wp, &d_wscores, &d_obest, &d_recs, &d_strings, &d_cursor, &d_maxhit, &d_fcnt, &d_fbegin, &d_F, &d_slot, &d_scan_tmp, &d_tsel, &d_tnsel };
+				&d_wp, &d_wscores, &d_obest, &d_recs, &d_strings, &d_cursor, &d_maxhit, &d_fcnt, &d_fbegin, &d_F, &d_slot, &d_scan_tmp, &d_tsel, &d_tnsel, &d_late_pairs, &d_late_item, &d_late_range };
 		for (DevBuf *b : all) b->release();
 		if (done) cudaEventDestroy(done);
 		if (searched) cudaEventDestroy(searched);
@@ -521,8 +564,16 @@ struct DevOut {
 };
 
 // single-end batches on the s16x2 second-generation kernels: forward pass over every candidate of reads with <= kFwdAllMax candidates
-int enqueue_fwd_all(ngm_b200_ctx *c, LaneBuf &L, const DevIn &in, const DevOut &out, int m0, int strata, cudaStream_t st) {
+// Paired batches take the same route: BatchScore results of every candidate = forward maxima, top1PE per chunk of reads (the running
+// insert-size sums see the fragments in input order either way), backtrace of the winners; winners of reads with more than kFwdAllMax
+// candidates are aligned in a second, usually empty, pass over a late list.
+int enqueue_fwd_all(ngm_b200_ctx *c, LaneBuf &L, const DevIn &in, const DevOut &out, int m0, int strata, cudaStream_t st, cudaEvent_t pe_wait, cudaEvent_t pe_signal) {
 	const int n = in.n_reads, np = in.n_pairs;
+	const int paired = in.paired ? 1 : 0;
+	const bool own_p16 = paired && in.desc_format != NGM_B200_DESC_PAIR16;
+	if (own_p16) CU(L.d_pairs16.ensure(std::max<size_t>(np, 1) * sizeof(ngm_b200_pair)));
+	ngm_b200_pair *p16 = own_p16 ? L.d_pairs16.as<ngm_b200_pair>() : nullptr;
+	const ngm_b200_pair *pe_pairs = own_p16 ? p16 : static_cast<const ngm_b200_pair *>(in.desc);
 	CU(L.d_rp.ensure(std::max<size_t>(np, 1) * sizeof(PairDesc)));
 	CU(L.d_F.ensure(std::max<size_t>(np, 1) * sizeof(PairDesc)));
 	CU(L.d_sel.ensure(std::max<size_t>(np, 1) * 4));
@@ -533,10 +584,10 @@ int enqueue_fwd_all(ngm_b200_ctx *c, LaneBuf &L, const DevIn &in, const DevOut &
 	const int blocks_r = (n + 255) / 256, blocks_r1 = (n + 1 + 255) / 256;
 	if (in.desc_format == NGM_B200_DESC_PAIR16)
 		batch_plan_all_kernel<NGM_B200_DESC_PAIR16><<<blocks_r1, 256, 0, st>>>(n, in.cb, in.desc, L.d_rp.as<PairDesc>(), (unsigned long long) c->concat_len,
-				(unsigned long long) c->n_region_nib, c->d_rrlen.as<uint16_t>(), L.d_fcnt.as<int>(), L.d_sel.as<int>(), L.d_nsel.as<int>());
+				(unsigned long long) c->n_region_nib, c->d_rrlen.as<uint16_t>(), L.d_fcnt.as<int>(), L.d_sel.as<int>(), L.d_nsel.as<int>(), p16);
 	else
 		batch_plan_all_kernel<NGM_B200_DESC_U64><<<blocks_r1, 256, 0, st>>>(n, in.cb, in.desc, L.d_rp.as<PairDesc>(), (unsigned long long) c->concat_len,
-				(unsigned long long) c->n_region_nib, c->d_rrlen.as<uint16_t>(), L.d_fcnt.as<int>(), L.d_sel.as<int>(), L.d_nsel.as<int>());
+				(unsigned long long) c->n_region_nib, c->d_rrlen.as<uint16_t>(), L.d_fcnt.as<int>(), L.d_sel.as<int>(), L.d_nsel.as<int>(), p16);
 	size_t tmp_bytes = 0;
 	CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, L.d_fcnt.as<int>(), L.d_fbegin.as<int>(), n + 1, st));
 	CU(L.d_scan_tmp.ensure(tmp_bytes));
@@ -561,13 +612,14 @@ int enqueue_fwd_all(ngm_b200_ctx *c, LaneBuf &L, const DevIn &in, const DevOut &
 		if (rc) return rc;
 	}
 	batch_fill_fwd_kernel<<<blocks_r, 256, 0, st>>>(n, in.cb, L.d_rp.as<PairDesc>(), out.scores, L.d_fbegin.as<int>(), strata, L.d_F.as<PairDesc>(), out.best_pair,
-			out.mapq, out.num_top);
+			out.mapq, out.num_top, paired);
 	c->launches += 1;
 	CU(cudaGetLastError());
 	// chunks of G reads: at most kFwdAllMax * G forward slots, whose pointer matrix is the launch set's scratch
 	const size_t per_slot = (size_t) c->dp.rows_cap * ptr_words_for(c->capacity) * 4 + sizeof(int4);
 	size_t slots_budget = std::max<size_t>((size_t) kFwdAllMax * 4096, std::min<size_t>((size_t) 4 << 20, ((size_t) 11 << 30) / per_slot));
-	const int G = (int) std::min<size_t>((size_t) n, slots_budget / kFwdAllMax);
+	int G = (int) std::min<size_t>((size_t) n, slots_budget / kFwdAllMax);
+	if (paired && (G & 1)) G = std::max(2, G - 1);                 // mates stay in one chunk
 	const int C = (kFwdAllMax * G + 255) / 256 * 256;
 	const int Gpad = (G + 127) / 128 * 128;
 	const int ops_cap = 2 * c->dp.qml + c->dp.corridor + 2;
@@ -575,6 +627,18 @@ int enqueue_fwd_all(ngm_b200_ctx *c, LaneBuf &L, const DevIn &in, const DevOut &
 	CU(c->d_best.ensure((size_t) C * sizeof(int4)));
 	CU(c->d_ops.ensure((size_t) ops_cap * Gpad * sizeof(uint16_t)));
 	CU(L.d_slot.ensure((size_t) Gpad * 4));
+	if (paired) {
+		CU(L.d_late_pairs.ensure((size_t) Gpad * sizeof(PairDesc)));
+		CU(L.d_late_item.ensure((size_t) Gpad * 4));
+		CU(L.d_late_range.ensure(8));
+		if (out.num_top == nullptr) CU(L.d_ntop.ensure((size_t) n * 4));
+		// The previous sub-batch's selections come first.  Waiting HERE (before this sub-batch's forward pass, not just before its first
+		// top1PE) keeps the lanes staggered: lane k + 1 runs its forward pass while lane k traces back and copies out.  With the wait in
+		// front of the selection only, all lanes ran their forward passes interleaved and finished together: e2e 370 -> 336 M reads/s.
+		if (pe_wait) CU(cudaStreamWaitEvent(st, pe_wait, 0));
+	} else if (pe_wait) {
+		CU(cudaStreamWaitEvent(st, pe_wait, 0));                   // single-end: the same staggering of the lanes (pe_signal follows the forward passes)
+	}
 	for (int r0 = 0; r0 < n; r0 += G) {
 		const int m = std::min(G, n - r0);
 		AlignArgs a;
@@ -608,12 +672,23 @@ int enqueue_fwd_all(ngm_b200_ctx *c, LaneBuf &L, const DevIn &in, const DevOut &
 		cudaError_t e = launch_align_s16(c->capacity, m0, a, st);
 		if (e != cudaSuccess) return fail(NGM_B200_ECUDA, "forward kernel launch: %s", cudaGetErrorString(e));
 		if (prof) CU(cudaEventRecord(c->pev[c->pev_used + 1], st));
+		if (!paired && pe_signal && r0 + G >= n) CU(cudaEventRecord(pe_signal, st));      // the next lane's forward pass may start
 		if (m0 == 0)
 			batch_pick_kernel<0><<<(m + 255) / 256, 256, 0, st>>>(m, r0, in.cb, L.d_fbegin.as<int>(), L.d_F.as<PairDesc>(), c->d_best.as<int4>(), strata, out.scores,
-					out.best_pair, out.mapq, out.num_top, L.d_slot.as<int>());
+					out.best_pair, out.mapq, out.num_top, L.d_slot.as<int>(), paired);
 		else
 			batch_pick_kernel<1><<<(m + 255) / 256, 256, 0, st>>>(m, r0, in.cb, L.d_fbegin.as<int>(), L.d_F.as<PairDesc>(), c->d_best.as<int4>(), strata, out.scores,
-					out.best_pair, out.mapq, out.num_top, L.d_slot.as<int>());
+					out.best_pair, out.mapq, out.num_top, L.d_slot.as<int>(), paired);
+		if (paired) {
+			// top1PE of the chunk's fragments (mates stay together: G is even), then the winners' slots
+			int *ntop = out.num_top != nullptr ? out.num_top : L.d_ntop.as<int>();
+			int rc = ngm_b200_dev_select_pairs(c, m, in.cb + r0, pe_pairs, out.scores, (uint32_t) np, out.best_pair + r0, out.mapq + r0, ntop + r0, out.pair_fail + r0, st);
+			if (rc < 0) return rc;
+			batch_set_u32_kernel<<<1, 1, 0, st>>>(L.d_late_range.as<uint32_t>(), 0u, L.d_late_range.as<int>() + 1);
+			batch_slot_pairs_kernel<<<(m + 255) / 256, 256, 0, st>>>(m, r0, in.cb, L.d_fbegin.as<int>(), L.d_rp.as<PairDesc>(), out.best_pair, L.d_slot.as<int>(),
+					L.d_late_pairs.as<PairDesc>(), L.d_late_item.as<int>(), L.d_late_range.as<int>());
+			c->launches += 2;
+		}
 		a.phase = 2;
 		a.n = m;
 		a.n_items = m;
@@ -626,7 +701,28 @@ int enqueue_fwd_all(ngm_b200_ctx *c, LaneBuf &L, const DevIn &in, const DevOut &
 			c->pev_used += 3;
 		}
 		c->launches += 3;
+		if (paired) {
+			// the late list: winners of reads with more than kFwdAllMax candidates; same scratch (the chunk's backtrace has been enqueued),
+			// the number of entries is only known on the device
+			AlignArgs b = a;
+			b.pairs = L.d_late_pairs.as<PairDesc>();
+			b.n = m;
+			b.range = L.d_late_range.as<int>();
+			b.range_m = 1;
+			b.phase = 1;
+			e = launch_align_s16(c->capacity, m0, b, st);
+			if (e != cudaSuccess) return fail(NGM_B200_ECUDA, "forward kernel launch (late list): %s", cudaGetErrorString(e));
+			b.phase = 2;
+			b.n_items = m;
+			b.items_dev = L.d_late_range.as<int>() + 1;
+			b.slot_of = nullptr;
+			b.rec_of = L.d_late_item.as<int>();
+			e = launch_align_s16(c->capacity, m0, b, st);
+			if (e != cudaSuccess) return fail(NGM_B200_ECUDA, "backtrace kernel launch (late list): %s", cudaGetErrorString(e));
+			c->launches += 2;
+		}
 	}
+	if (paired && pe_signal) CU(cudaEventRecord(pe_signal, st));
 	CU(cudaGetLastError());
 	return NGM_B200_OK;
 }
@@ -687,7 +783,9 @@ int batch_enqueue(ngm_b200_ctx *c, LaneBuf &L, const DevIn &in, const DevOut &ou
 	static const bool fwd_all_on = [] { const char *e = getenv("NGM_B200_FWD_ALL"); return e == nullptr || atoi(e) != 0; }();
 	static const bool fwd_v1 = [] { const char *e = getenv("NGM_B200_FWD"); return e != nullptr && atoi(e) == 1; }();
 	const bool s16_fwd2 = c->align_s16[m0] && c->capacity <= (m0 == 1 ? kAlignS16MaxEndFree : kAlignS16MaxLocal);
-	if (fuse && fwd_all_on && !fwd_v1 && s16_fwd2 && in.cb_base == 0) return enqueue_fwd_all(c, L, in, out, m0, strata, st);
+	static const bool pe_fwd_all = [] { const char *e = getenv("NGM_B200_PE_FWD_ALL"); return e == nullptr || atoi(e) != 0; }();
+	if ((fuse || (in.paired && pe_fwd_all && !wide_local && !no_fuse)) && fwd_all_on && !fwd_v1 && s16_fwd2 && in.cb_base == 0)
+		return enqueue_fwd_all(c, L, in, out, m0, strata, st, pe_wait, pe_signal);
 	CU(L.d_rp.ensure(std::max<size_t>(np, 1) * sizeof(PairDesc)));
 	CU(L.d_wp.ensure((size_t) n * sizeof(PairDesc)));
 	CU(L.d_wscores.ensure((size_t) n * 4));
@@ -1151,7 +1249,9 @@ int ngm_b200_run_batch(ngm_b200_ctx *c, const ngm_b200_batch_in *in, ngm_b200_ba
 			dn.sel = L.d_tsel.as<int>();
 			dn.n_sel = L.d_tnsel.as<int>();
 		}
-		if ((err = batch_enqueue(l, L, di, dn, c->se_strata, st, (in->paired && k > 0) ? B->pe_chain : nullptr, in->paired ? B->pe_chain : nullptr)) != NGM_B200_OK) break;
+		static const bool stagger = [] { const char *e = getenv("NGM_B200_STAGGER"); return e == nullptr || atoi(e) != 0; }();
+		const bool chain = in->paired || stagger;
+		if ((err = batch_enqueue(l, L, di, dn, c->se_strata, st, (chain && k > 0) ? B->pe_chain : nullptr, chain ? B->pe_chain : nullptr)) != NGM_B200_OK) break;
 		// candidate indices of the caller's arrays, not of the sub-batch
 		if (p0 - cb[0] != 0) {
 			batch_add_base_kernel<<<(m + 255) / 256, 256, 0, st>>>(m, L.d_best.as<int>(), p0 - cb[0]);

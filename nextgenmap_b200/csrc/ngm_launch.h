@@ -64,6 +64,8 @@ struct AlignArgs {
 	int range_m = 0;
 	const int *slot_of = nullptr;   // phase 2: item i (one of n_items reads) is aligned from forward slot slot_of[i], -1 = none
 	int n_items = 0;
+	const int *items_dev = nullptr; // phase 2, optional (device): only the first min(n_items, *items_dev) items exist
+	const int *rec_of = nullptr;    // phase 2, optional (device): item i writes recs[rec_of[i]] instead of recs[i]
 	int ops_stride = 0;             // items per op-stack row (0: = stride)
 	float *out_best = nullptr;   // optional, per alignment: the forward pass's maximum = what BatchScore returns for the pair in this mode
 	int stride, ops_cap;

@@ -235,6 +235,23 @@ def test_run_batch_paired_is_independent_of_sub_batching():
     np.testing.assert_array_equal(base["best_pair"], want["best"])
     np.testing.assert_array_equal(base["mapq"], want["mapq"])
     np.testing.assert_array_equal(base["pair_fail"], want["paired_fail"])
+    # the records are those of the classic align entry point for every winner -- including the winners of reads with more than four candidates,
+    # which the batch aligns in a second pass over a late list
+    counts = begin[1:] - begin[:-1]
+    has = base["best_pair"] >= 0
+    assert np.count_nonzero(has & (counts > 4)) >= 5 and np.count_nonzero(has & (counts <= 4)) > 1000
+    sw0.set_reads(reads)
+    winners = pairs[base["best_pair"][has]].copy()
+    winners["read_index"] = np.nonzero(has)[0]
+    recs, heap = sw0.align_pairs(0, winners)
+    got = base["recs"][has]
+    for f in ("position_offset", "qstart", "qend", "nm", "score", "cigar_len", "md_len"):
+        np.testing.assert_array_equal(got[f], recs[f], err_msg=f)
+    rows = np.nonzero(has)[0]
+    for i in range(len(rows)):
+        if recs[i]["score"] >= 0:
+            assert sw0.strings_of(base["recs"], base["heap"], int(rows[i])) == sw0.strings_of(recs, heap, i), i
+    assert np.all(base["recs"]["score"][~has] == -1.0)
     for _, _, sw in out:
         sw.close()
 
