@@ -55,6 +55,13 @@ cudaError_t launch_align_s16(int capacity, int mode, const AlignArgs &a, cudaStr
 							a.ptr_scratch, a.stride, a.best_scratch, a.range, a.range_m); \
 					launched = true; \
 				} \
+			} else if constexpr (W <= kAlignS16MaxKnown) { \
+				/* wide local band whose maxima are not known yet: the second-generation kernel with its checkpoints in local memory */ \
+				if (mode == 0 && a.known == nullptr) { \
+					align_s16_fwd2_kernel<W, LO, 0><<<grid, block, 0, st>>>(a.P, a.pairs, a.n, a.reads_fwd, a.reads_rev, a.rlen, a.ref4, \
+							a.ptr_scratch, a.stride, a.best_scratch, a.range, a.range_m); \
+					launched = true; \
+				} \
 			} \
 			if constexpr (W <= kAlignS16MaxEndFree) { \
 				if (mode == 1) { \

@@ -249,7 +249,11 @@ __global__ void __launch_bounds__(128) align_s16_fwd2_kernel(const __grid_consta
 	const size_t row_stride = (size_t) tstride * T::kWords;
 	uint32_t *prow = ptr_scratch + (size_t) t2;
 	uint32_t *chk = s_chk + threadIdx.x;
-	auto chk_at = [&](int buf, int j) -> uint32_t * { return chk + (buf * W + j) * 128; };
+	// wide local bands (capacity > 48): three checkpoints of W words per thread do not fit shared memory at a useful occupancy; they live in
+	// local memory instead (L1 / L2 resident: 3 x W x 4 bytes per thread, written once per eight rows)
+	constexpr bool CHK_LOCAL = MODE == 0 && W > kAlignS16MaxLocal;
+	uint32_t chk_local[CHK_LOCAL ? 3 : 1][CHK_LOCAL ? W : 1];
+	auto chk_at = [&](int buf, int j) -> uint32_t * { return CHK_LOCAL ? &chk_local[CHK_LOCAL ? buf : 0][CHK_LOCAL ? j : 0] : chk + (buf * W + j) * 128; };
 
 	uint32_t line[W + 1];
 #pragma unroll

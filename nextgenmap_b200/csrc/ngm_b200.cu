@@ -242,6 +242,11 @@ int ensure_align_scratch(ngm_b200_ctx *c, int stride) {
 }
 
 // Launch the align kernel over n resolved pairs in slices of align_chunk.
+bool wide_v2_enabled() {
+	static const bool on = [] { const char *e = getenv("NGM_B200_WIDE_V2"); return e == nullptr || atoi(e) != 0; }();
+	return on;
+}
+
 int run_align(ngm_b200_ctx *c, int mode, const PairDesc *pairs, int n, const uint32_t *rf, const uint32_t *rr, const uint16_t *rl,
 		const uint32_t *ref4, ngm_b200_align_rec *recs, char *strings, uint32_t str_cap, uint32_t *cursor, cudaStream_t st,
 		const float *known_user, float *out_best) {
@@ -267,8 +272,9 @@ int run_align(ngm_b200_ctx *c, int mode, const PairDesc *pairs, int n, const uin
 			// wide band and the caller already holds the pairs' local maxima (the resident pipeline: BatchScore ran first).
 			// Narrow bands keep the snapshot kernel: measured faster there (19.5 vs 17.8 ms per 10 M x 150 bp, profiles/r1b).
 			a.known = known_user + s;
-		} else if (mode == 0 && c->align_s16[0] && c->capacity > kAlignS16MaxLocal) {
-			// wide band: get the local maxima from the (cheap) score kernel first, then run the snapshot-free forward pass
+		} else if (mode == 0 && c->align_s16[0] && c->capacity > kAlignS16MaxLocal && !wide_v2_enabled()) {
+			// wide band (NGM_B200_WIDE_V2=0): get the local maxima from the (cheap) score kernel first, then run the snapshot-free forward pass;
+			// the default is the second-generation kernel with local-memory checkpoints, which needs no score pass
 			ScoreArgs sa = score_args(c, a.pairs, a.n, rf, rr, rl, ref4, c->d_known.as<float>());
 			int rc2 = run_score(c, 0, sa, st);
 			if (rc2) return rc2;

@@ -776,13 +776,13 @@ int batch_enqueue(ngm_b200_ctx *c, LaneBuf &L, const DevIn &in, const DevOut &ou
 	}
 	// single-candidate reads skip BatchScore when the alignment kernel of this configuration reports its forward maximum and does not
 	// need the score beforehand (wide local bands locate their best cell by it)
-	const bool wide_local = m0 == 0 && c->align_s16[0] && c->capacity > kAlignS16MaxLocal;
+	const bool wide_local = m0 == 0 && c->align_s16[0] && c->capacity > kAlignS16MaxLocal && !wide_v2_enabled();
 	static const bool no_fuse = [] { const char *e = getenv("NGM_B200_NO_FUSE"); return e != nullptr && atoi(e) == 1; }();
 	const int fuse = (!in.paired && !wide_local && !no_fuse) ? 1 : 0;
 	// NGM_B200_FWD_ALL=0 keeps score -> top-1 -> forward of the winner for every multi-candidate read (A/B measurements)
 	static const bool fwd_all_on = [] { const char *e = getenv("NGM_B200_FWD_ALL"); return e == nullptr || atoi(e) != 0; }();
 	static const bool fwd_v1 = [] { const char *e = getenv("NGM_B200_FWD"); return e != nullptr && atoi(e) == 1; }();
-	const bool s16_fwd2 = c->align_s16[m0] && c->capacity <= (m0 == 1 ? kAlignS16MaxEndFree : kAlignS16MaxLocal);
+	const bool s16_fwd2 = c->align_s16[m0] && c->capacity <= (m0 == 1 ? kAlignS16MaxEndFree : (wide_v2_enabled() ? kAlignS16MaxKnown : kAlignS16MaxLocal));
 	static const bool pe_fwd_all = [] { const char *e = getenv("NGM_B200_PE_FWD_ALL"); return e == nullptr || atoi(e) != 0; }();
 	if ((fuse || (in.paired && pe_fwd_all && !wide_local && !no_fuse)) && fwd_all_on && !fwd_v1 && s16_fwd2 && in.cb_base == 0)
 		return enqueue_fwd_all(c, L, in, out, m0, strata, st, pe_wait, pe_signal);

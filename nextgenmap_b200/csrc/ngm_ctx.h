@@ -93,6 +93,7 @@ int mode_of(int mode);                          // mode & 0xFF -> 0 / 1, or -1
 int resolve_pairs_for(ngm_b200_ctx *c, const void *d_pairs_user, int n, cudaStream_t st);      // ngm_b200_pair -> c->d_rpairs (PairDesc)
 int pack_reads_device(ngm_b200_ctx *c, const uint8_t *d_ascii, int n_reads, int stride, cudaStream_t st);
 int run_score(ngm_b200_ctx *c, int mode, const ScoreArgs &a, cudaStream_t st);
+bool wide_v2_enabled();                         // wide local bands without a score pass first (NGM_B200_WIDE_V2, default on)
 ScoreArgs score_args(ngm_b200_ctx *c, const PairDesc *pairs, int n, const uint32_t *rf, const uint32_t *rr, const uint16_t *rl, const uint32_t *ref4, float *out);
 int run_align(ngm_b200_ctx *c, int mode, const PairDesc *pairs, int n, const uint32_t *rf, const uint32_t *rr, const uint16_t *rl, const uint32_t *ref4,
 		ngm_b200_align_rec *recs, char *strings, uint32_t str_cap, uint32_t *cursor, cudaStream_t st, const float *known_user, float *out_best);
