@@ -282,3 +282,44 @@ np.savez(sys.argv[1], scores=g["scores"], best=g["best_pair"], recs=g["recs"].vi
         np.testing.assert_array_equal(a[f], b[f], err_msg=f)
     np.testing.assert_array_equal(res[0]["scores"], res[1]["scores"])
     assert int(res[0]["used"]) == int(res[1]["used"])
+
+
+@pytest.mark.parametrize("qml,cor,paired,switch", [(152, 27, False, "NGM_B200_FWD_EXACT"), (152, 27, False, "NGM_B200_FWD_ALL"), (152, 27, True, "NGM_B200_PE_FWD_ALL"),
+                                                  (252, 80, False, "NGM_B200_WIDE_V2"), (252, 80, True, "NGM_B200_WIDE_V2"), (152, 27, False, "NGM_B200_STAGGER")])
+def test_routes_agree(qml, cor, paired, switch):
+    """Every A/B switch of the batch engine selects another route to the SAME results: exact-corridor kernels, forward pass over every
+    candidate (single-end and paired), the second-generation kernel on wide bands, staggered lanes.  <switch>=0 against the default."""
+    code = r'''
+import numpy as np, sys
+sys.path.insert(0, %r)
+from tests.test_gpu_batch import make_batch
+from nextgenmap_b200.host import CudaSW
+qml, cor, paired = int(sys.argv[2]), int(sys.argv[3]), sys.argv[4] == "1"
+concat, packed, reads, pairs, begin = make_batch(57, 1600, qml, cor)
+sw = CudaSW(qml, cor); sw.set_reference(packed, len(concat))
+if paired:
+    sw.pe_configure()
+sw.set_pipeline(3, 300)
+g = sw.run_batch(0, reads, begin, pairs, paired=paired, packed=True, desc_u64=True)
+strings = [sw.strings_of(g["recs"], g["heap"], r) for r in range(len(reads)) if g["recs"][r]["score"] >= 0]
+np.savez(sys.argv[1], scores=g["scores"], best=g["best_pair"], mapq=g["mapq"], ntop=g["num_top"], pf=g["pair_fail"], recs=g["recs"].view(np.uint8),
+         strings=np.frombuffer(b"\n".join(c + b"\t" + m for c, m in strings), np.uint8))
+''' % (str(util.ROOT),)
+    import tempfile
+    res = []
+    with tempfile.TemporaryDirectory() as td:
+        for v in (None, "0"):
+            env = dict(os.environ)
+            env.pop(switch, None)
+            if v is not None:
+                env[switch] = v
+            path = os.path.join(td, f"o{v}.npz")
+            subprocess.run([sys.executable, "-c", code, path, str(qml), str(cor), "1" if paired else "0"], check=True, env=env, cwd=str(util.ROOT))
+            res.append(dict(np.load(path)))
+    from nextgenmap_b200.host.cuda_sw import ALIGN_REC
+    a, b = (r["recs"].view(ALIGN_REC).reshape(-1) for r in res)
+    for f in ("position_offset", "qstart", "qend", "nm", "score", "cigar_len", "md_len"):
+        np.testing.assert_array_equal(a[f], b[f], err_msg=f)
+    for f in ("scores", "best", "mapq", "ntop", "strings") + (("pf",) if paired else ()):
+        np.testing.assert_array_equal(res[0][f], res[1][f], err_msg=f)
+    assert np.count_nonzero(a["score"] >= 0) > 1000
