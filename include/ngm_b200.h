@@ -445,9 +445,9 @@ typedef struct ngm_b200_batch_out {
 	int32_t *pair_fail;         /* n_reads, paired batches only */
 	ngm_b200_align_rec *recs;   /* n_reads: alignment of the selected candidate (score -1 when there is none) */
 	char *strings;              /* CIGAR / MD heap; recs[].str_off are offsets into it.  The heap is filled per sub-batch, so it is sparse:
-	                             * sub-batch k owns [k * slot, (k + 1) * slot), slot = str_capacity / number of sub-batches (16-byte aligned) */
+	                             * every sub-batch owns the part of the heap that corresponds to its share of the reads (16-byte aligned) */
 	size_t str_capacity;
-	size_t str_used;            /* out: bytes of CIGAR / MD text.  NGM_B200_ERANGE: a sub-batch needed more than its slot; str_used then holds a
+	size_t str_used;            /* out: bytes of CIGAR / MD text.  NGM_B200_ERANGE: a sub-batch needed more than its part; str_used then holds a
 	                             * sufficient total capacity for a repeat of the call */
 	uint32_t *d_str_cursor;     /* ngm_b200_dev_run_batch only: device word that receives the heap bytes used (dense heap, one sub-batch) */
 	/* ngm_b200_se_configure_topn(topn > 1), single-end batches (ScoreBuffer::topNSE): every candidate is scored, the list sorted, up to topn

@@ -672,7 +672,8 @@ int enqueue_fwd_all(ngm_b200_ctx *c, LaneBuf &L, const DevIn &in, const DevOut &
 		cudaError_t e = launch_align_s16(c->capacity, m0, a, st);
 		if (e != cudaSuccess) return fail(NGM_B200_ECUDA, "forward kernel launch: %s", cudaGetErrorString(e));
 		if (prof) CU(cudaEventRecord(c->pev[c->pev_used + 1], st));
-		if (!paired && pe_signal && r0 + G >= n) CU(cudaEventRecord(pe_signal, st));      // the next lane's forward pass may start
+		static const int stagger_mode = [] { const char *e = getenv("NGM_B200_STAGGER"); return e == nullptr ? 1 : atoi(e); }();
+		if (!paired && pe_signal && r0 + G >= n && stagger_mode != 2) CU(cudaEventRecord(pe_signal, st));      // the next lane's forward pass may start
 		if (m0 == 0)
 			batch_pick_kernel<0><<<(m + 255) / 256, 256, 0, st>>>(m, r0, in.cb, L.d_fbegin.as<int>(), L.d_F.as<PairDesc>(), c->d_best.as<int4>(), strata, out.scores,
 					out.best_pair, out.mapq, out.num_top, L.d_slot.as<int>(), paired);
@@ -723,6 +724,11 @@ int enqueue_fwd_all(ngm_b200_ctx *c, LaneBuf &L, const DevIn &in, const DevOut &
 		}
 	}
 	if (paired && pe_signal) CU(cudaEventRecord(pe_signal, st));
+	{
+		// NGM_B200_STAGGER=2 (experiment): the next lane's kernels start only after this lane's backtrace
+		static const int stagger_mode2 = [] { const char *e = getenv("NGM_B200_STAGGER"); return e == nullptr ? 1 : atoi(e); }();
+		if (!paired && pe_signal && stagger_mode2 == 2) CU(cudaEventRecord(pe_signal, st));
+	}
 	CU(cudaGetLastError());
 	return NGM_B200_OK;
 }
@@ -1162,16 +1168,47 @@ int ngm_b200_run_batch(ngm_b200_ctx *c, const ngm_b200_batch_in *in, ngm_b200_ba
 	if (rc) return rc;
 	BatchState *B = c->batch;
 	const int SB = B->sub_batch;
-	const int n_sub = (n + SB - 1) / SB;
-	const size_t slot = (out->str_capacity / (size_t) n_sub) & ~(size_t) 15;
-	if ((slot + 16) * (size_t) n_sub > 0xFFFFFFF0ull) return fail(NGM_B200_EINVAL, "string heap beyond 32 bits");
+	// Sub-batches: full ones in the middle, a ramp at both ends (SB/4, SB/2 ... SB/2, SB/4).  The first upload and the last download are
+	// the only copies nothing overlaps with; small sub-batches there cut the pipeline's fill and drain (NGM_B200_RAMP=0: equal sizes).
+	static const bool ramp = [] { const char *e = getenv("NGM_B200_RAMP"); return e == nullptr || atoi(e) != 0; }();
+	std::vector<int> sub_r0;                                        // first read of every sub-batch, and n at the end
+	{
+		const int q = std::max(2, (SB / 4) & ~1), h = std::max(2, (SB / 2) & ~1);
+		int at = 0;
+		sub_r0.push_back(0);
+		if (ramp && n > 2 * SB + 2 * (q + h)) {
+			at += q;
+			sub_r0.push_back(at);
+			at += h;
+			sub_r0.push_back(at);
+			while (n - at > SB + h + q) {
+				at += SB;
+				sub_r0.push_back(at);
+			}
+			const int rest = n - at - h - q;                        // in (0, SB]
+			at += (rest + 1) & ~1;
+			sub_r0.push_back(at);
+			at += h;
+			sub_r0.push_back(at);
+		} else {
+			for (at = SB; at < n; at += SB) sub_r0.push_back(at);
+		}
+		if (sub_r0.back() != n) sub_r0.push_back(n);
+	}
+	const int n_sub = (int) sub_r0.size() - 1;
+	// string heap: sub-batch k owns the part of the heap that corresponds to its share of the reads (16-byte aligned)
+	if (out->str_capacity > 0xFFFFFFF0ull) return fail(NGM_B200_EINVAL, "string heap beyond 32 bits");
+	std::vector<size_t> heap_at((size_t) n_sub + 1);
+	for (int k = 0; k <= n_sub; ++k) heap_at[k] = (size_t) ((unsigned long long) out->str_capacity * (unsigned long long) sub_r0[k] / (unsigned long long) n) & ~(size_t) 15;
+	size_t slot = 0;                                                // the largest part: sizes the lanes' staging
+	for (int k = 0; k < n_sub; ++k) slot = std::max(slot, heap_at[k + 1] - heap_at[k]);
 	CU(B->h_used.ensure((size_t) n_sub * 4));
 	uint32_t *h_used = B->h_used.as<uint32_t>();
 	const size_t desc_bytes = in->desc_format == NGM_B200_DESC_U64 ? 8 : sizeof(ngm_b200_pair);
 	const int n_lanes = std::min(std::min(B->n_lanes, (int) B->lanes.size()), std::max(1, n_sub));
 	int64_t pe_sum = 0, pe_count = 0;
 	if (in->paired && (rc = ngm_b200_pe_insert_stats(c, &pe_sum, &pe_count)) < 0) return rc;
-	size_t worst_used = 0, total_used = 0;
+	size_t worst_used = 0, total_used = 0, need_capacity = 0;
 	bool overflow = false;
 	int err = NGM_B200_OK;
 	auto finish = [&](int li) -> int {                              // fetch the strings of the lane's previous sub-batch
@@ -1180,11 +1217,13 @@ int ngm_b200_run_batch(ngm_b200_ctx *c, const ngm_b200_batch_in *in, ngm_b200_ba
 		const int k = L.pending;
 		L.pending = -1;
 		CU(cudaEventSynchronize(L.done));
-		const size_t base = slot * (size_t) k;
+		const size_t base = heap_at[k], part = heap_at[k + 1] - heap_at[k];
 		const size_t used = (size_t) h_used[k] - base;
 		worst_used = std::max(worst_used, used);
 		total_used += used;
-		if (used > slot) {
+		// capacity with which this sub-batch's share would have held its strings
+		need_capacity = std::max(need_capacity, (size_t) ((unsigned long long) (used + 32) * (unsigned long long) n / (unsigned long long) (sub_r0[k + 1] - sub_r0[k])) + 64);
+		if (used > part) {
 			overflow = true;
 			return NGM_B200_OK;
 		}
@@ -1199,7 +1238,7 @@ int ngm_b200_run_batch(ngm_b200_ctx *c, const ngm_b200_batch_in *in, ngm_b200_ba
 		LaneBuf &L = B->bufs[li];
 		cudaStream_t st = l->stream;
 		if ((err = finish(li)) != NGM_B200_OK) break;
-		const int r0 = k * SB, m = std::min(SB, n - r0);
+		const int r0 = sub_r0[k], m = sub_r0[k + 1] - r0;
 		const int p0 = cb[r0], mp = cb[r0 + m] - p0;
 		// ---- host -> device
 		const size_t rbytes = (size_t) m * in->read_stride;
@@ -1238,12 +1277,12 @@ int ngm_b200_run_batch(ngm_b200_ctx *c, const ngm_b200_batch_in *in, ngm_b200_ba
 		if ((err = install_reads(l, in->read_format, L.d_in_reads.p, m, in->read_stride, L.d_in_len.as<uint16_t>(), L.d_in_exc.as<ngm_b200_read_exc>(), n_exc,
 				(uint32_t) r0, st)) != NGM_B200_OK)
 			break;
-		const uint32_t base = (uint32_t) (slot * (size_t) k);
+		const uint32_t base = (uint32_t) heap_at[k], part = (uint32_t) (heap_at[k + 1] - heap_at[k]);
 		batch_set_u32_kernel<<<1, 1, 0, st>>>(L.d_cursor.as<uint32_t>(), base, nullptr);
 		if (p0) batch_rebase_kernel<<<(m + 1 + 255) / 256, 256, 0, st>>>(m + 1, L.d_cb.as<int>(), p0);      // offsets into the sub-batch's own arrays
 		DevIn di = { m, in->mode, in->paired, in->desc_format, L.d_cb.as<int>(), 0, L.d_desc.p, mp };
 		DevOut dn = { L.d_scores.as<float>(), L.d_best.as<int>(), L.d_mapq.as<int>(), L.d_ntop.as<int>(), L.d_pfail.as<int>(), L.d_recs.as<ngm_b200_align_rec>(),
-				L.d_strings.as<char>() - base, (uint32_t) (base + slot), L.d_cursor.as<uint32_t>() };
+				L.d_strings.as<char>() - base, (uint32_t) (base + part), L.d_cursor.as<uint32_t>() };
 		if (topn > 1) {
 			dn.topn = topn;
 			dn.sel = L.d_tsel.as<int>();
@@ -1290,8 +1329,8 @@ int ngm_b200_run_batch(ngm_b200_ctx *c, const ngm_b200_batch_in *in, ngm_b200_ba
 	out->str_used = total_used;
 	if (overflow) {
 		if (in->paired) ngm_b200_pe_set_insert_stats(c, pe_sum, pe_count);
-		out->str_used = (worst_used + 64) * (size_t) n_sub;
-		return fail(NGM_B200_ERANGE, "string heap too small: a sub-batch needed %zu bytes, its slot holds %zu", worst_used, slot);
+		out->str_used = need_capacity;
+		return fail(NGM_B200_ERANGE, "string heap too small: a sub-batch needed %zu bytes, more than its share of the heap; %zu bytes would do", worst_used, need_capacity);
 	}
 	return n;
 }
