@@ -199,6 +199,11 @@ __device__ __forceinline__ void fwd2_row_sel(uint32_t (&line)[W + 1], const uint
 	}
 }
 
+// resident blocks per SM the register allocation must allow (1 = no constraint beyond the 255-register limit)
+#ifndef NGM_FWD2_MIN_BLOCKS
+#define NGM_FWD2_MIN_BLOCKS(W) 1
+#endif
+
 template <int W, bool OFS = false, int N = W>             // N: slots that can hold a value
 __device__ __forceinline__ uint32_t band_max(const uint32_t (&line)[W + 1], uint32_t acc) {
 #pragma unroll
@@ -208,7 +213,7 @@ __device__ __forceinline__ uint32_t band_max(const uint32_t (&line)[W + 1], uint
 }
 
 template <int W, int LO, int MODE, bool EXACT = false>
-__global__ void __launch_bounds__(128) align_s16_fwd2_kernel(const __grid_constant__ DevParams P, const PairDesc *__restrict__ pairs, int n,
+__global__ void __launch_bounds__(128, NGM_FWD2_MIN_BLOCKS(W)) align_s16_fwd2_kernel(const __grid_constant__ DevParams P, const PairDesc *__restrict__ pairs, int n,
 		const uint32_t *__restrict__ reads_fwd, const uint32_t *__restrict__ reads_rev, const uint16_t *__restrict__ rlen,
 		const uint32_t *__restrict__ ref4, uint32_t *__restrict__ ptr_scratch, int stride, int4 *__restrict__ best_out,
 		const int *__restrict__ range, int range_m) {
