@@ -221,7 +221,7 @@ void ngm_b200_free_ht_file(ngm_b200_htfile *ht);
 int ngm_b200_write_ht_file(const char *path, const ngm_b200_htfile *ht);
 
 /* Candidate search for n_reads rows of `stride` ASCII bytes (NUL padded, like MappedRead::Seq): CS::RunBatch without
- * the bs-mapping k-mer mutation (CS.cpp:340-436).  cand_begin: n_reads + 1 offsets; pairs[cand_begin[r] .. cand_begin[r+1])
+ * the bs-mapping k-mer mutation unless ngm_b200_cs_configure_mutation switched it on (CS.cpp:340-436).  cand_begin: n_reads + 1 offsets; pairs[cand_begin[r] .. cand_begin[r+1])
  * are read r's candidates in the reference's order as descriptors for ngm_b200_score_pairs (window_start =
  * Location - corridor/2, flags = REVERSE|DIR for minus-strand candidates, ScoreBuffer.cpp:92-114); votes = LocationScore
  * Score.f; max_hit (optional) = MappedRead::s.  *total receives the number of candidates; if it exceeds `capacity` the
@@ -236,6 +236,15 @@ int ngm_b200_cs_search(ngm_b200_ctx *ctx, const char *reads, int n_reads, int st
  * mode_flags bit 1 of the search calls selects the vote count used here (both strands added) for max_hit[]. */
 int ngm_b200_cs_estimate_sensitivity(ngm_b200_ctx *ctx, const char *sampled_reads, int n, int stride, float *sensitivity);
 int ngm_b200_cs_set_sensitivity(ngm_b200_ctx *ctx, float sensitivity);
+/* bs-mapping / SLAMseq candidate search (CS::PrefixMutateSearch, CS.cpp:53-112; CS::RunBatch, CS.cpp:341-380).  bs_mapping = "bs_mapping" (1: every
+ * read k-mer is also looked up with every subset of its T -- second mate: A -- replaced by C -- G --; k-mers with more than bs_cutoff = "bs_cutoff" (6)
+ * such bases are skipped; read k-mers are taken every read_kmer_skip + 1 positions -- under bs_mapping the "kmer_skip" key (2) thins the READ's k-mers,
+ * CS.cpp:556-560, and the index must have been built with ngm_b200_cs_params.kmer_skip 0 as CompactPrefixTable does, PrefixTable.cpp:204-207).  slam_seq = "slam_seq" (bit 2 set: the k-mer votes with weight 1, each single
+ * C -> T -- second mate: G -> A -- replacement with weight 1 / (replaceable bases + 1), so votes become fractional).  paired = "paired": odd rows of
+ * a read batch are second mates.  Both zero switches the mutation off.  With mutation on, every read is searched by the sequential kernel in the
+ * table of CS::RunBatch's last overflow retry (2^20 slots, CS.cpp:404-428); a read that overflows it keeps no candidates, as in the reference.
+ * Call after cs_build_index / cs_load_index; applies to cs_search, dev_cs_search and map_batch (sub-batches must hold whole pairs). */
+int ngm_b200_cs_configure_mutation(ngm_b200_ctx *ctx, int bs_mapping, int slam_seq, int bs_cutoff, int paired, int read_kmer_skip);
 /* Reads the last ngm_b200_cs_search call routed to the exact kernel. */
 uint64_t ngm_b200_cs_exact_reads(const ngm_b200_ctx *ctx);
 /* Why they left the block-per-read kernel (diagnostics): out[0..n) = counts per reason -- 0 more hits than the kernel's
@@ -353,6 +362,8 @@ typedef struct ngm_b200_sam_opts {
 	int32_t clip_seq;           /* "hard_clip" or "silent_clip" set: SEQ / QUAL of a mapped read lose the clipped ends (SAMWriter.cpp:104,146-160);
 	                             * the CIGAR's H ops (or none) come from the alignment itself (ngm_b200_params.hard_clip / silent_clip) */
 	const char *read_group;     /* "rg_id": RG:Z:<id> on every record (SAMWriter.cpp:166-168,358-360); NULL = none */
+	int32_t bs_mapping;         /* "bs_mapping" (1): ZS:Z:++ / -+ (first mate or single read, forward / reverse) or -- / +- (second mate) after NH:i
+	                             * (SAMWriter.cpp:173-187) */
 } ngm_b200_sam_opts;
 /* One batch as the calls above leave it, all host pointers.  Paired runs: rows 2f / 2f + 1 are mates and pair_fail != NULL. */
 typedef struct ngm_b200_sam_batch {

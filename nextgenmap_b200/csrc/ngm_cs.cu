@@ -30,9 +30,12 @@ struct CsState {
 	DevBuf d_tabu, d_table, d_weight, d_both, d_table2;
 	// search scratch
 	DevBuf d_meta, d_heap, d_cursor, d_slow_list, d_slow_count, d_counts, d_begin, d_scan_tmp, d_pairs, d_votes;
-	DevBuf d_ex_tables, d_ex_rlists, d_ex_gens;
+	DevBuf d_ex_tables, d_ex_rlists, d_ex_gens, d_heap_votes;
 	HostBuf h_total;
 	int ex_blocks = 0;
+	int ex_bits = 0;               // table size the exact kernel's scratch was allocated for
+	// bs-mapping / SLAMseq k-mer mutation (ngm_b200_cs_configure_mutation)
+	int mut_mode = 0, mut_cutoff = 6, mut_paired = 0, mut_read_skip = 0;
 	uint64_t exact_reads = 0;      // reads the last search sent to the exact kernel
 	bool exact_all = false;
 };
@@ -40,7 +43,7 @@ struct CsState {
 void cs_release(CsState *cs) {
 	if (cs == nullptr) return;
 	DevBuf *db[] = { &cs->d_tabu, &cs->d_table, &cs->d_weight, &cs->d_both, &cs->d_table2, &cs->d_meta, &cs->d_heap, &cs->d_cursor, &cs->d_slow_list, &cs->d_slow_count,
-			&cs->d_counts, &cs->d_begin, &cs->d_scan_tmp, &cs->d_pairs, &cs->d_votes, &cs->d_ex_tables, &cs->d_ex_rlists, &cs->d_ex_gens };
+			&cs->d_counts, &cs->d_begin, &cs->d_scan_tmp, &cs->d_pairs, &cs->d_votes, &cs->d_ex_tables, &cs->d_ex_rlists, &cs->d_ex_gens, &cs->d_heap_votes };
 	for (DevBuf *b : db) b->release();
 	cs->h_total.release();
 	delete cs;
@@ -61,6 +64,10 @@ int cs_share_index(ngm_b200_ctx *lane, const ngm_b200_ctx *root) {
 	s->n_prefix = r->n_prefix;
 	s->table_len = r->table_len;
 	s->max_kfreq = r->max_kfreq;
+	s->mut_mode = r->mut_mode;
+	s->mut_cutoff = r->mut_cutoff;
+	s->mut_paired = r->mut_paired;
+	s->mut_read_skip = r->mut_read_skip;
 	s->d_tabu.borrow(r->d_tabu);
 	s->d_table.borrow(r->d_table);
 	s->d_weight.borrow(r->d_weight);
@@ -442,6 +449,16 @@ int ngm_b200_dev_cs_search(ngm_b200_ctx *c, const void *d_ascii_reads, int n_rea
 	P.sensitivity = cs->hp.sensitivity;
 	P.kmer_min = cs->hp.kmer_min;
 	P.merged = (mode_flags & 2) ? 1 : 0;
+	P.mut_mode = cs->mut_mode;
+	P.mut_cutoff = cs->mut_cutoff;
+	P.mut_paired = cs->mut_paired;
+	P.read_skip = cs->mut_mode == 1 ? cs->mut_read_skip : 0;
+	P.ex_bits = cs->mut_mode != 0 ? 20 : kCsExactBits;
+	P.heap_votes = nullptr;
+	if (cs->mut_mode == 2) {
+		CU(cs->d_heap_votes.ensure((size_t) capacity * sizeof(float) + 8));
+		P.heap_votes = cs->d_heap_votes.as<float>();
+	}
 	CU(cs->d_meta.ensure((size_t) n_reads * sizeof(CsMeta)));
 	CU(cs->d_heap.ensure((size_t) capacity * sizeof(CsCand) + 8));
 	CU(cs->d_cursor.ensure(4));
@@ -450,11 +467,12 @@ int ngm_b200_dev_cs_search(ngm_b200_ctx *c, const void *d_ascii_reads, int n_rea
 	CU(cs->d_counts.ensure(((size_t) n_reads + 1) * 4));
 	CU(cudaMemsetAsync(cs->d_cursor.p, 0, 4, st));
 	CU(cudaMemsetAsync(cs->d_slow_count.p, 0, 64, st));
-	if (cs->ex_blocks == 0) {
+	if (cs->ex_blocks == 0 || cs->ex_bits != P.ex_bits) {
 		int sms = 0;
 		CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
 		cs->ex_blocks = std::max(8, 2 * sms);
-		const size_t tl = (size_t) 1 << kCsExactBits;
+		cs->ex_bits = P.ex_bits;
+		const size_t tl = (size_t) 1 << P.ex_bits;
 		CU(cs->d_ex_tables.ensure(tl * sizeof(CsExactEntry) * cs->ex_blocks));
 		CU(cs->d_ex_rlists.ensure(tl * 4 * cs->ex_blocks));
 		CU(cs->d_ex_gens.ensure((size_t) cs->ex_blocks * 4));
@@ -466,7 +484,7 @@ int ngm_b200_dev_cs_search(ngm_b200_ctx *c, const void *d_ascii_reads, int n_rea
 	CsCand *heap = cs->d_heap.as<CsCand>();
 	uint32_t *cursor = cs->d_cursor.as<uint32_t>();
 	float *max_hit = static_cast<float *>(d_max_hit);
-	const bool exact_only = (mode_flags & 1) != 0;
+	const bool exact_only = (mode_flags & 1) != 0 || cs->mut_mode != 0;      // the mutated k-mers are enumerated by the sequential kernel only
 	bool exact_only_fallback = false;
 	cs->exact_all = exact_only;
 	cs->exact_reads = (uint64_t) n_reads;
@@ -539,7 +557,8 @@ int ngm_b200_dev_cs_search(ngm_b200_ctx *c, const void *d_ascii_reads, int n_rea
 	CU(cs->d_scan_tmp.ensure(tmp_bytes));
 	CU(cub::DeviceScan::ExclusiveSum(cs->d_scan_tmp.p, tmp_bytes, cs->d_counts.as<int>(), static_cast<int *>(d_cand_begin), n_reads + 1, st));
 	cs_gather_kernel<<<(n_reads + 255) / 256, 256, 0, st>>>(meta, heap, capacity, static_cast<const int *>(d_cand_begin), n_reads, cs->bin_shift,
-			c->dp.corridor, capacity, static_cast<ngm_b200_pair *>(d_pairs), static_cast<float *>(d_votes));
+			c->dp.corridor, capacity, static_cast<ngm_b200_pair *>(d_pairs), static_cast<float *>(d_votes), P.heap_votes,
+			cs->mut_mode != 0 && cs->mut_paired);
 	c->launches += 3;
 	CU(cudaGetLastError());
 	return n_reads;
@@ -591,6 +610,19 @@ uint64_t ngm_b200_cs_exact_reads(const ngm_b200_ctx *c) {
 			cudaMemcpy(&slow, c->cs->d_slow_count.p, 4, cudaMemcpyDeviceToHost) != cudaSuccess)
 		return 0;
 	return slow;
+}
+
+// CS::RunBatch's choice of k-mer callback (CS.cpp:341-343) and of the mutated base (:362-380)
+int ngm_b200_cs_configure_mutation(ngm_b200_ctx *c, int bs_mapping, int slam_seq, int bs_cutoff, int paired, int read_kmer_skip) {
+	if (c == nullptr || c->cs == nullptr || !c->cs->ready) return fail(NGM_B200_ESTATE, "no candidate-search index");
+	if (bs_mapping == 1 && slam_seq != 0) return fail(NGM_B200_EINVAL, "bs_mapping and slam_seq exclude each other (Config.cpp:454-457)");
+	if (bs_cutoff < 0 || read_kmer_skip < 0) return fail(NGM_B200_EINVAL, "bs_cutoff %d / read_kmer_skip %d < 0", bs_cutoff, read_kmer_skip);
+	c->cs->mut_mode = bs_mapping == 1 ? 1 : ((slam_seq & 4) ? 2 : 0);
+	c->cs->mut_cutoff = bs_cutoff;
+	c->cs->mut_paired = paired ? 1 : 0;
+	c->cs->mut_read_skip = read_kmer_skip;
+	c->epoch += 1;
+	return NGM_B200_OK;
 }
 
 int ngm_b200_cs_set_sensitivity(ngm_b200_ctx *c, float sensitivity) {

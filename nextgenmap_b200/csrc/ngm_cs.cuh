@@ -42,6 +42,13 @@ struct CsDev {
 	int k, bin_shift, max_kfreq, max_cmrs;
 	float sensitivity, kmer_min;
 	int merged;               // max_hit[] receives the best vote with both strands added (ReadProvider's estimate) instead of MappedRead::s
+	// bs-mapping / SLAMseq k-mer mutation (CS::PrefixMutateSearch, CS.cpp:53-112); served by cs_search_exact_kernel only
+	int mut_mode;             // 0 off, 1 "bs_mapping", 2 "slam_seq" & 4
+	int mut_cutoff;           // "bs_cutoff" (6): read k-mers with more replaceable bases are skipped (bs_mapping)
+	int mut_paired;           // "paired": odd reads are second mates and mutate the complementary base (CS.cpp:362-380)
+	int read_skip;            // m_PrefixBaseSkip: "kmer_skip" under bs_mapping, else 0 (CS.cpp:556-560)
+	int ex_bits;              // log2 slots of the exact kernel's table (kCsExactBits; 20 with mutation = the largest table CS::RunBatch tries)
+	float *heap_votes;        // mut_mode 2: the candidates' fractional votes, parallel to the heap (CsCand::votes holds integers)
 };
 
 struct CsRun {                // one N-free stretch of a contig as CS::PrefixIteration walks it
@@ -1100,75 +1107,191 @@ struct CsExactEntry {         // CSTableEntry (LocationScore.h:9-14)
 	float fscore, rscore;
 };
 
+// One lane's search state (CS members rTable, rList, currentState, maxHitNumber, currentThresh, hpoc)
+struct CsExactState {
+	CsExactEntry *tab;
+	uint32_t *rlist;
+	uint32_t gen, rlen, tmask;
+	int bits;
+	float maxhit, thresh, maxmerged;
+	uint32_t hpoc;            // probe steps left before the reference gives up (CS.cpp:176-178); 0 = unlimited
+	bool overflow;
+};
+
+// CS::PrefixSearch + AddLocationStd (CS.cpp:114-213) for one k-mer at read offset o
+__device__ __forceinline__ void cs_exact_vote(const CsDev &P, CsExactState &S, uint32_t prefix, int o, int len, float weight) {
+	CsLists L;
+	if (S.overflow || !cs_lookup(P, prefix, L)) return;
+	const uint64_t corr_r = (uint64_t) len - ((uint64_t) o + (uint64_t) P.k);
+	const uint32_t total = L.fc + L.rc;
+	for (uint32_t i = 0; i < total; ++i) {
+		const bool rev = i >= L.fc;
+		const uint64_t loc = P.table[rev ? L.rs + (i - L.fc) : L.fs + i];
+		const uint64_t bin = (loc - (rev ? corr_r : (uint64_t) o)) >> P.bin_shift;      // GetBin on 64 bits
+		uint32_t e = (uint32_t) ((bin * 11400714819323199488ull) >> (64 - S.bits));      // CS::Hash
+		bool found;
+		uint32_t probes = 0;
+		while ((found = ((S.tab[e].state & 0x7FFFFFFFu) == S.gen)) && !((uint64_t) S.tab[e].loc == bin)) {
+			e = (e + 1) & S.tmask;
+			if (++probes > S.tmask || (S.hpoc != 0 && --S.hpoc == 0)) {
+				S.overflow = true;
+				return;
+			}
+		}
+		float score = weight;
+		if (!found) {
+			S.tab[e].loc = (uint32_t) bin;
+			S.tab[e].state = S.gen;
+			S.tab[e].fscore = rev ? 0.0f : weight;
+			S.tab[e].rscore = rev ? weight : 0.0f;
+		} else if (rev) {
+			score = (S.tab[e].rscore = __fadd_rn(S.tab[e].rscore, weight));
+		} else {
+			score = (S.tab[e].fscore = __fadd_rn(S.tab[e].fscore, weight));
+		}
+		if (score > S.maxhit) {
+			S.maxhit = score;
+			S.thresh = __fmul_rn(S.maxhit, P.sensitivity);
+		}
+		S.maxmerged = fmaxf(S.maxmerged, S.tab[e].fscore + S.tab[e].rscore);
+		if (!(S.tab[e].state & 0x80000000u) && score >= S.thresh) {
+			S.tab[e].state |= 0x80000000u;
+			S.rlist[S.rlen++] = e;
+		}
+	}
+}
+
+// CS::PrefixMutateSearch (CS.cpp:53-112) for one read k-mer.  bs_mapping: the k-mer and, depth first, every k-mer with a subset of its
+// `from` bases replaced (PrefixMutateSearchEx: the subsets of the replaceable positions in lexicographic order of their sorted index lists,
+// positions counted from the k-mer's last base); k-mers with more than `cutoff` such bases are skipped.  slam_seq: the k-mer with weight 1,
+// then its single replacements with weight 1 / (replaceable bases + 1) (PrefixMutateSearchSlamSeq).
+__device__ void cs_exact_mutate(const CsDev &P, CsExactState &S, uint32_t prefix, int o, int len, uint32_t from, uint32_t to) {
+	int pos[16];
+	int c = 0;
+	for (int i = 0; i < P.k; ++i)
+		if (((prefix >> (2 * i)) & 3u) == from) pos[c++] = i;
+	if (P.mut_mode == 2) {
+		cs_exact_vote(P, S, prefix, o, len, 1.0f);
+		const float w = __fdiv_rn(1.0f, (float) (c + 1));
+		for (int j = 0; j < c; ++j) cs_exact_vote(P, S, (prefix & ~(3u << (2 * pos[j]))) | (to << (2 * pos[j])), o, len, w);
+		return;
+	}
+	if (c > P.mut_cutoff) return;
+	int sub[16];
+	int d = 0;
+	for (;;) {
+		uint32_t p = prefix;
+		for (int j = 0; j < d; ++j) p = (p & ~(3u << (2 * pos[sub[j]]))) | (to << (2 * pos[sub[j]]));
+		cs_exact_vote(P, S, p, o, len, 1.0f);
+		if (S.overflow) return;
+		const int last = d ? sub[d - 1] : -1;
+		if (last + 1 < c) {
+			sub[d++] = last + 1;
+		} else {
+			--d;                                               // (d >= 1 here unless c == 0)
+			if (d <= 0) return;
+			sub[d - 1] += 1;
+		}
+	}
+}
+
+// CS::PrefixIteration (CSstatic.cpp:26-76) as a loop, with the read-side k-mer skip: fn(prefix, offset) for every emitted k-mer
+template <typename F>
+__device__ void cs_exact_iterate(const uint8_t *seq, int length, int k, uint32_t prefixskip, F fn) {
+	const uint32_t mask = k < 16 ? (1u << (2 * k)) - 1u : 0xFFFFFFFFu;
+	int offset = 0;
+	for (;;) {
+		if (length < k) return;
+		if (*seq == 'N') {
+			int n_skip = 1;
+			while (n_skip < length && seq[n_skip] == 'N') ++n_skip;
+			seq += n_skip;
+			if (n_skip >= length - k) return;
+			length -= n_skip;
+			offset += n_skip;
+		}
+		uint32_t prefix = 0;
+		bool restart = false;
+		int i;
+		for (i = 0; i < k - 1; ++i) {
+			if (seq[i] == 'N') {
+				restart = true;
+				break;
+			}
+			prefix = (prefix << 2) | cs_enc2(seq[i]);
+		}
+		if (!restart) {
+			uint32_t skipcount = prefixskip;
+			for (i = k - 1; i < length; ++i) {
+				if (seq[i] == 'N') {
+					restart = true;
+					break;
+				}
+				prefix = ((prefix << 2) | cs_enc2(seq[i])) & mask;
+				if (skipcount == prefixskip) {
+					fn(prefix, offset + i + 1 - k);
+					skipcount = 0;
+				} else {
+					++skipcount;
+				}
+			}
+		}
+		if (!restart) return;
+		seq += i + 1;
+		length -= i + 1;
+		offset += i + 1;
+	}
+}
+
 __global__ void __launch_bounds__(32) cs_search_exact_kernel(const CsDev P, const uint8_t *__restrict__ reads, int n_reads, int stride,
 		CsMeta *__restrict__ meta, CsCand *__restrict__ heap, uint32_t heap_cap, uint32_t *__restrict__ cursor, const uint32_t *__restrict__ work_list,
 		const uint32_t *__restrict__ work_count, CsExactEntry *__restrict__ tables, uint32_t *__restrict__ rlists, uint32_t *__restrict__ gens,
 		float *__restrict__ max_hit) {
 	if (threadIdx.x != 0) return;
-	constexpr uint32_t TLEN = 1u << kCsExactBits;
-	CsExactEntry *tab = tables + (size_t) blockIdx.x * TLEN;
-	uint32_t *rlist = rlists + (size_t) blockIdx.x * TLEN;
-	uint32_t gen = gens[blockIdx.x];
+	const uint32_t TLEN = 1u << P.ex_bits;
+	CsExactState S;
+	S.tab = tables + (size_t) blockIdx.x * TLEN;
+	S.rlist = rlists + (size_t) blockIdx.x * TLEN;
+	S.tmask = TLEN - 1;
+	S.bits = P.ex_bits;
+	S.gen = gens[blockIdx.x];
 	const uint32_t n_work = work_list != nullptr ? *work_count : (uint32_t) n_reads;
 	for (uint32_t w = blockIdx.x; w < n_work; w += gridDim.x) {
 		const int r = work_list != nullptr ? (int) work_list[w] : (int) w;
 		const uint8_t *seq = reads + (size_t) r * stride;
 		int len = 0;
 		while (len < stride && seq[len] != 0) ++len;
-		gen = (gen + 1) & 0x7FFFFFFFu;                         // CS::RunBatch, CS.cpp:351-356
-		if (gen == 0x7FFFFFFFu) gen = 1;
-		uint32_t rlen = 0;
-		float maxhit = 0.0f, thresh = 0.0f, maxmerged = 0.0f;
-		bool overflow = false;
-		for (int o = 0; o + P.k <= len && !overflow; ++o) {
-			uint32_t prefix;
-			if (!cs_read_kmer(seq, len, o, P.k, prefix)) continue;
-			CsLists L;
-			if (!cs_lookup(P, prefix, L)) continue;
-			const uint64_t corr_r = (uint64_t) len - ((uint64_t) o + (uint64_t) P.k);
-			const uint32_t total = L.fc + L.rc;
-			for (uint32_t i = 0; i < total; ++i) {
-				const bool rev = i >= L.fc;
-				const uint64_t loc = P.table[rev ? L.rs + (i - L.fc) : L.fs + i];
-				const uint64_t bin = (loc - (rev ? corr_r : (uint64_t) o)) >> P.bin_shift;      // GetBin on 64 bits
-				uint32_t e = (uint32_t) ((bin * 11400714819323199488ull) >> (64 - kCsExactBits));      // CS::Hash
-				bool found;
-				uint32_t probes = 0;
-				while ((found = ((tab[e].state & 0x7FFFFFFFu) == gen)) && !((uint64_t) tab[e].loc == bin)) {
-					e = (e + 1) & (TLEN - 1);
-					if (++probes >= TLEN) {
-						overflow = true;
-						break;
-					}
-				}
-				if (overflow) break;
-				float score = 1.0f;
-				if (!found) {
-					tab[e].loc = (uint32_t) bin;
-					tab[e].state = gen;
-					tab[e].fscore = rev ? 0.0f : 1.0f;
-					tab[e].rscore = rev ? 1.0f : 0.0f;
-				} else if (rev) {
-					score = (tab[e].rscore += 1.0f);
-				} else {
-					score = (tab[e].fscore += 1.0f);
-				}
-				if (score > maxhit) {
-					maxhit = score;
-					thresh = __fmul_rn(maxhit, P.sensitivity);
-				}
-				maxmerged = fmaxf(maxmerged, tab[e].fscore + tab[e].rscore);
-				if (!(tab[e].state & 0x80000000u) && score >= thresh) {
-					tab[e].state |= 0x80000000u;
-					rlist[rlen++] = e;
-				}
+		S.gen = (S.gen + 1) & 0x7FFFFFFFu;                     // CS::RunBatch, CS.cpp:351-356
+		if (S.gen == 0x7FFFFFFFu) S.gen = 1;
+		S.rlen = 0;
+		S.maxhit = 0.0f;
+		S.thresh = 0.0f;
+		S.maxmerged = 0.0f;
+		S.overflow = false;
+		S.hpoc = 0;
+		if (P.mut_mode == 0) {
+			for (int o = 0; o + P.k <= len && !S.overflow; ++o) {
+				uint32_t prefix;
+				if (!cs_read_kmer(seq, len, o, P.k, prefix)) continue;
+				cs_exact_vote(P, S, prefix, o, len, 1.0f);
 			}
+		} else {
+			// the table of CS::RunBatch's last retry (2^20 slots, 0.777 x slots probe steps, CS.cpp:404-428): a read that fits a smaller
+			// table gets the same list from this one, a read that overflows this one keeps no candidates
+			S.hpoc = (uint32_t) __fmul_rn((float) (int) TLEN, 0.777f);
+			const bool second = P.mut_paired && (r & 1);
+			const uint32_t from = P.mut_mode == 2 ? (second ? 3u : 1u) : (second ? 0u : 2u);
+			const uint32_t to = P.mut_mode == 2 ? (second ? 0u : 2u) : (second ? 3u : 1u);
+			cs_exact_iterate(seq, len, P.k, P.mut_mode == 1 ? (uint32_t) P.read_skip : 0u,
+					[&](uint32_t prefix, int o) { cs_exact_mutate(P, S, prefix, o, len, from, to); });
 		}
-		if (max_hit != nullptr) max_hit[r] = P.merged ? maxmerged : maxhit;
-		const float thr = fmaxf(P.kmer_min, thresh);
+		const bool overflow = S.overflow;
+		const uint32_t rlen = S.rlen;
+		if (max_hit != nullptr) max_hit[r] = P.merged ? S.maxmerged : S.maxhit;
+		const float thr = fmaxf(P.kmer_min, S.thresh);
 		uint32_t n = 0;
 		for (uint32_t i = 0; i < rlen && !overflow; ++i) {
-			const CsExactEntry t = tab[rlist[i]];
+			const CsExactEntry t = S.tab[S.rlist[i]];
 			n += (t.fscore >= thr) + (t.rscore >= thr);
 		}
 		if (overflow || !((long long) n < (long long) P.max_cmrs)) n = 0;
@@ -1178,12 +1301,13 @@ __global__ void __launch_bounds__(32) cs_search_exact_kernel(const CsDev P, cons
 			if ((unsigned long long) off + n <= heap_cap) {
 				uint32_t at = off;
 				for (uint32_t i = 0; i < rlen; ++i) {
-					const CsExactEntry t = tab[rlist[i]];
+					const CsExactEntry t = S.tab[S.rlist[i]];
 					if (t.fscore >= thr) {
 						CsCand cd;
 						cd.bin = t.loc;
 						cd.votes = (uint16_t) t.fscore;
 						cd.rev = 0;
+						if (P.heap_votes != nullptr) P.heap_votes[at] = t.fscore;
 						heap[at++] = cd;
 					}
 					if (t.rscore >= thr) {
@@ -1191,6 +1315,7 @@ __global__ void __launch_bounds__(32) cs_search_exact_kernel(const CsDev P, cons
 						cd.bin = t.loc;
 						cd.votes = (uint16_t) t.rscore;
 						cd.rev = 1;
+						if (P.heap_votes != nullptr) P.heap_votes[at] = t.rscore;
 						heap[at++] = cd;
 					}
 				}
@@ -1199,7 +1324,7 @@ __global__ void __launch_bounds__(32) cs_search_exact_kernel(const CsDev P, cons
 		meta[r].off = off;
 		meta[r].count = overflow ? 0u : n;
 	}
-	gens[blockIdx.x] = gen;
+	gens[blockIdx.x] = S.gen;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1214,7 +1339,8 @@ __global__ void cs_counts_kernel(const CsMeta *__restrict__ meta, int n_reads, i
 // LocationScore -> (read, window) descriptor: Location = ResolveBin(bin) (CS.h:170-175); ScoreBuffer fetches the
 // window at Location - corridor/2 and uses RevSeq for reverse candidates (ScoreBuffer.cpp:92-114)
 __global__ void cs_gather_kernel(const CsMeta *__restrict__ meta, const CsCand *__restrict__ heap, uint32_t heap_cap, const int *__restrict__ begin,
-		int n_reads, int bin_shift, int corridor, uint32_t out_cap, ngm_b200_pair *__restrict__ pairs, float *__restrict__ votes) {
+		int n_reads, int bin_shift, int corridor, uint32_t out_cap, ngm_b200_pair *__restrict__ pairs, float *__restrict__ votes,
+		const float *__restrict__ heap_votes, int second_mates) {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= n_reads) return;
 	const CsMeta m = meta[r];
@@ -1226,9 +1352,11 @@ __global__ void cs_gather_kernel(const CsMeta *__restrict__ meta, const CsCand *
 		ngm_b200_pair p;
 		p.window_start = (((unsigned long long) c.bin << bin_shift) + half) - (unsigned long long) (corridor >> 1);
 		p.read_index = (uint32_t) r;
-		p.flags = c.rev ? (NGM_B200_PAIR_REVERSE | NGM_B200_PAIR_DIR) : 0u;
+		// the bs / SLAMseq direction flag ScoreBuffer hands to BatchScore: the strand, inverted for second mates (ScoreBuffer.cpp:92-110)
+		const bool dir = (c.rev != 0) != (second_mates && (r & 1));
+		p.flags = (c.rev ? NGM_B200_PAIR_REVERSE : 0u) | (dir ? NGM_B200_PAIR_DIR : 0u);
 		pairs[b + i] = p;
-		if (votes != nullptr) votes[b + i] = (float) c.votes;
+		if (votes != nullptr) votes[b + i] = heap_votes != nullptr ? heap_votes[m.off + i] : (float) c.votes;
 	}
 }
 

@@ -5,7 +5,7 @@
 // (src/AlignmentBuffer.cpp:129), AlignmentBuffer::WriteRead (convert() to contig coordinates :166-176; for pairs the check of the
 // aligned positions :176-200), the output filters of GenericReadWriter::WriteRead / WritePair (src/writer/GenericReadWriter.h:190-312:
 // min_identity, min_residues) and SAMWriter::DoWriteReadGeneric / DoWriteUnmappedReadGeneric / DoWritePair
-// (src/writer/SAMWriter.cpp:98-228,230-310,312-365).  topn 1, no bs-mapping, no hard / silent clipping of SEQ, no read group.
+// (src/writer/SAMWriter.cpp:98-228,230-310,312-365).  bs-mapping adds ZS:Z (ngm_b200_sam_opts.bs_mapping).
 // Lines come out in read order (mates: second mate's line first, like DoWritePair); NGM's own order depends on its thread timing.
 #include <algorithm>
 #include <atomic>
@@ -202,6 +202,10 @@ void mapped_line(const Job &j, const ReadView &v, int flags, const char *rnext, 
 	tag_int(out, "\tAS:i:", (int) b.scores[v.bp]);
 	tag_int(out, "\tNM:i:", rec.nm);
 	tag_int(out, "\tNH:i:", ntop);
+	if (j.o->bs_mapping == 1) {                                  // SAMWriter.cpp:173-187: which converted strand the read matches
+		const bool second = b.pair_fail != nullptr && (v.r & 1); // !(ReadId & 1) || Paired == 0
+		out.append(second ? (v.reverse ? "\tZS:Z:+-" : "\tZS:Z:--") : (v.reverse ? "\tZS:Z:-+" : "\tZS:Z:++"));
+	}
 	out.append("\tXI:f:");
 	put_xi(out, rec.identity);
 	tag_int(out, "\tX0:i:", ntop);

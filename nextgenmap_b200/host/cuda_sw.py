@@ -50,7 +50,7 @@ class PeParams(C.Structure):
 class SamOpts(C.Structure):
     """ngm_b200_sam_opts (include/ngm_b200.h); defaults = src/config/Config.cpp:405-410,430-431."""
     _fields_ = [("min_identity", C.c_float), ("min_residues", C.c_float), ("min_insert_size", C.c_int32), ("max_insert_size", C.c_int32), ("threads", C.c_int32),
-                ("min_mq", C.c_int32), ("clip_seq", C.c_int32), ("read_group", C.c_char_p)]
+                ("min_mq", C.c_int32), ("clip_seq", C.c_int32), ("read_group", C.c_char_p), ("bs_mapping", C.c_int32)]
 
 
 class SamBatch(C.Structure):
@@ -182,6 +182,7 @@ def load_library() -> C.CDLL:
                                               C.c_void_p, C.c_void_p]
     lib.ngm_b200_cs_estimate_sensitivity.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
     lib.ngm_b200_cs_set_sensitivity.argtypes = [C.c_void_p, C.c_float]
+    lib.ngm_b200_cs_configure_mutation.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.ngm_b200_dev_cs_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                            C.c_void_p, C.c_void_p]
     lib.ngm_b200_read_ht_file.argtypes = [C.c_char_p, C.POINTER(_CHtFile)]
@@ -486,6 +487,10 @@ class CudaSW:
         if install:
             self._check(self.lib.ngm_b200_cs_set_sensitivity(self.ctx, sens))
         return float(sens.value)
+
+    def cs_configure_mutation(self, bs_mapping: int = 0, slam_seq: int = 0, bs_cutoff: int = 6, paired: bool = False, read_kmer_skip: int = 2) -> None:
+        """CS::RunBatch under --bs-mapping / --slam-seq 4|x (CS::PrefixMutateSearch, CS.cpp:53-112,341-380); both 0 = off."""
+        self._check(self.lib.ngm_b200_cs_configure_mutation(self.ctx, bs_mapping, slam_seq, bs_cutoff, 1 if paired else 0, read_kmer_skip))
 
     def pe_configure(self, pair_score_cutoff: float = 0.9, min_insert_size: int = 0, max_insert_size: int = 1000, strata: int = 0,
                      fast_pairing: int = 0) -> None:

@@ -242,9 +242,13 @@ def _mapped_line(batch, rd: _Read, encref, flags: int, rnext: str, pnext: int, t
         flags |= 0x10
     ntop = int(batch.num_top[rd.r])
     qstart, qend = int(rec["qstart"]), int(rec["qend"])
+    zs = []
+    if getattr(batch, "bs_mapping", 0) == 1:                    # SAMWriter.cpp:173-187 (set ``batch.bs_mapping = 1`` for a --bs-mapping run)
+        second = getattr(batch, "pair_fail", None) is not None and (rd.r & 1)
+        zs = ["ZS:Z:" + (("+-" if rd.reverse else "--") if second else ("-+" if rd.reverse else "++"))]
     return "\t".join([rd.name, str(flags), encref.contigs[rd.contig][0], str((rd.loc + 1) & 0xFFFFFFFF), str(int(batch.mapq[rd.r])), cigar.decode(),
                       rnext, str((pnext + 1) & 0xFFFFFFFF), str(tlen), s.decode(), q.decode(), "AS:i:%d" % int(batch.scores[rd.bp]),
-                      "NM:i:%d" % int(rec["nm"]), "NH:i:%d" % ntop, "XI:f:" + _xi(float(rec["identity"])), "X0:i:%d" % ntop,
+                      "NM:i:%d" % int(rec["nm"]), "NH:i:%d" % ntop, *zs, "XI:f:" + _xi(float(rec["identity"])), "X0:i:%d" % ntop,
                       "XE:i:%d" % int(batch.max_hit[rd.r]), "XR:i:%d" % (rd.length - qstart - qend), "MD:Z:" + md.split(b"\0")[0].decode()])
 
 
@@ -364,7 +368,7 @@ def sam_lines_paired(batch, reads: np.ndarray, names: Sequence[str], quals: Sequ
 
 def format_sam(batch, reads: np.ndarray, names: Sequence[str], quals: Sequence[bytes], encref, paired: bool, min_identity: float = 0.65,
                min_residues: float = 0.5, min_insert_size: int = 0, max_insert_size: int = 1000, threads: int = 0, min_mq: int = 0,
-               clip_seq: bool = False, read_group: Optional[str] = None) -> bytes:
+               clip_seq: bool = False, read_group: Optional[str] = None, bs_mapping: int = 0) -> bytes:
     """The same lines as ``sam_lines`` / ``sam_lines_paired`` from the library's multi-threaded formatter (``ngm_b200_format_sam``): what a
     C / C++ host calls.  ``encref``: an ``EncodedReference`` (the C struct is handed over as it is).  ``batch.recs`` / ``batch.heap`` as
     ``ngm_b200_align_pairs`` returned them."""
@@ -387,7 +391,8 @@ def format_sam(batch, reads: np.ndarray, names: Sequence[str], quals: Sequence[b
     n_sel = np.ascontiguousarray(batch.n_sel, dtype=np.int32) if topn else None
     sb = SamBatch(n, stride, reads.ctypes.data, q.ctypes.data, name_arr, ptr(keep[0]), ptr(keep[1]), ptr(keep[2]), ptr(keep[3]), ptr(keep[4]), ptr(keep[5]),
                   ptr(keep[6]), ptr(keep[7]), ptr(keep[8]), topn if topn > 1 else 0, ptr(sel), ptr(n_sel))
-    so = SamOpts(min_identity, min_residues, min_insert_size, max_insert_size, threads, min_mq, 1 if clip_seq else 0, read_group.encode() if read_group else None)
+    so = SamOpts(min_identity, min_residues, min_insert_size, max_insert_size, threads, min_mq, 1 if clip_seq else 0, read_group.encode() if read_group else None,
+                 bs_mapping)
     used = C.c_size_t(0)
     cap = n * max(topn, 1) * (2 * stride + 256) + 4096
     for _ in range(2):

@@ -236,6 +236,16 @@ typedef struct {
 	uint32_t *rlist;
 	int rlist_len;
 	float max_hit, cur_thresh;
+	/* bs-mapping / SLAMseq (CS::PrefixMutateSearch, CS.cpp:53-112) */
+	int mutate_mode;            /* 0 none, 1 bs_mapping, 2 slam_seq & 4 */
+	uint64_t mutate_from, mutate_to;
+	int bs_cutoff;
+	float weight;               /* 1 / m_CurrentMutLocs (CS.cpp:136-138) */
+	/* the reference's overflow test (hpoc, CS.cpp:176-178): only when probe_budget_on */
+	int probe_budget_on;
+	uint32_t hpoc;
+	int overflow;
+	unsigned read_skip;         /* m_PrefixBaseSkip: "kmer_skip" under bs_mapping, else 0 (CS.cpp:556-560) */
 } search_state;
 
 static inline uint32_t cs_hash(uint64_t n, int bits) {             /* CS::Hash, CS.h:94-102 */
@@ -243,11 +253,16 @@ static inline uint32_t cs_hash(uint64_t n, int bits) {             /* CS::Hash, 
 }
 
 static void add_location(search_state *s, uint64_t loc, int reverse, float freq) {     /* CS::AddLocationStd, CS.cpp:164-213 */
+	if (s->overflow) return;                                        /* (the exception has left PrefixIteration) */
 	uint32_t e = cs_hash(loc, s->table_bits);
 	int found;
 	while ((found = ((s->rtable[e].state & 0x7FFFFFFFu) == s->cur_state)) && !((uint64_t) s->rtable[e].loc == loc)) {
 		++e;
 		if (e >= s->table_len) e = 0;
+		if (s->probe_budget_on && --s->hpoc == 0) {                 /* throw 1, CS.cpp:176-178 */
+			s->overflow = 1;
+			return;
+		}
 	}
 	cs_entry *en = &s->rtable[e];
 	float score = freq;
@@ -292,12 +307,42 @@ static void prefix_search(uint64_t prefix, uint64_t pos, void *data) {     /* CS
 	if (!((int) (fcount + rcount) < s->max_kfreq)) return;         /* cur->refTotal < maxPrefixFreq, CS.cpp:122 */
 	for (uint32_t i = 0; i < fcount; ++i) {
 		const uint64_t loc = ix->table[fstart + i];
-		add_location(s, (loc - pos) >> ix->bin_shift, 0, 1.0f);
+		add_location(s, (loc - pos) >> ix->bin_shift, 0, s->weight);
 	}
 	const uint64_t corr = (uint64_t) s->read_len - (pos + (uint64_t) ix->k);
 	for (uint32_t i = 0; i < rcount; ++i) {
 		const uint64_t loc = ix->table[rstart + i];
-		add_location(s, (loc - corr) >> ix->bin_shift, 1, 1.0f);
+		add_location(s, (loc - corr) >> ix->bin_shift, 1, s->weight);
+	}
+}
+
+/* CS::PrefixMutateSearchEx (CS.cpp:95-112): the k-mer itself, then, depth first, every k-mer that has a subset of its
+ * `mutate_from` bases replaced by `mutate_to` (positions counted from the k-mer's LAST base, i = 0) */
+static void prefix_mutate_search_ex(search_state *s, uint64_t prefix, uint64_t pos, int mpos) {
+	prefix_search(prefix, pos, s);
+	for (int i = mpos; i < s->ix->k; ++i) {
+		if (((prefix >> (2 * i)) & 3u) == s->mutate_from) {
+			const uint64_t p = (prefix & ~((uint64_t) 3 << (2 * i))) | (s->mutate_to << (2 * i));
+			prefix_mutate_search_ex(s, p, pos, i + 1);
+		}
+	}
+}
+
+static void prefix_mutate_search(uint64_t prefix, uint64_t pos, void *data) {     /* CS::PrefixMutateSearch, CS.cpp:53-80 */
+	search_state *s = (search_state *) data;
+	int locs = 0;
+	for (int i = 0; i < s->ix->k; ++i) locs += ((prefix >> (2 * i)) & 3u) == s->mutate_from;
+	if (s->mutate_mode == 2) {
+		s->weight = 1.0f;                                           /* m_CurrentMutLocs = 1 */
+		prefix_search(prefix, pos, s);
+		s->weight = 1.0f / (float) (locs + 1);                      /* 1.0f / cs->m_CurrentMutLocs, CS.cpp:137 */
+		for (int i = 0; i < s->ix->k; ++i) {                        /* PrefixMutateSearchSlamSeq, CS.cpp:82-93: single replacements only */
+			if (((prefix >> (2 * i)) & 3u) == s->mutate_from)
+				prefix_search((prefix & ~((uint64_t) 3 << (2 * i))) | (s->mutate_to << (2 * i)), pos, s);
+		}
+	} else if (locs <= s->bs_cutoff) {
+		s->weight = 1.0f;
+		prefix_mutate_search_ex(s, prefix, pos, 0);
 	}
 }
 
@@ -329,7 +374,11 @@ static int search_one(search_state *s, const char *read, int read_len, float kme
 	s->rlist_len = 0;
 	s->max_hit = 0.0f;
 	s->cur_thresh = 0.0f;
-	prefix_iteration(read, (uint64_t) read_len, prefix_search, s, 0, 0, (unsigned) ix->k);
+	s->overflow = 0;
+	s->weight = 1.0f;
+	prefix_iteration(read, (uint64_t) read_len, s->mutate_mode ? prefix_mutate_search : prefix_search, s, s->mutate_mode == 1 ? s->read_skip : 0, 0,
+			(unsigned) ix->k);
+	if (s->overflow) return -1;
 	/* CollectResultsStd, CS.cpp:263-313 */
 	const float thr = kmer_min > s->cur_thresh ? kmer_min : s->cur_thresh;
 	int index = 0;
@@ -388,6 +437,57 @@ long long cs_oracle_search_batch(const cs_oracle_index *ix, const char *reads, i
 		cand_begin[r] = (int) total;
 		const long long room = out_cap - total;
 		const int n = search_one(&s, read, len, kmer_min, max_cmrs, out + total, room > 0x7fffffff ? 0x7fffffff : (room < 0 ? 0 : (int) room), max_hit ? max_hit + r : 0);
+		total += n;
+	}
+	cand_begin[n_reads] = (int) total;
+	free(s.rtable);
+	free(s.rlist);
+	return total;
+}
+
+/* CS::RunBatch with bs_mapping / slam_seq (CS.cpp:340-436): the mutated base by mode and mate, the search in a table of 2^table_bits
+ * slots with a budget of 0.333 x slots probe steps, after an overflow again with table_bits + 2, + 3, ... <= 20 and 0.777 x slots; a read
+ * that overflows every table keeps no candidates. */
+long long cs_oracle_search_batch_mut(const cs_oracle_index *ix, const char *reads, int n_reads, int stride, float sensitivity, float kmer_min,
+		int max_kfreq, int max_cmrs, int mutate_mode, int bs_cutoff, int paired, int read_skip, int table_bits, int *cand_begin,
+		cs_oracle_cand *out, long long out_cap, float *max_hit) {
+	search_state s;
+	memset(&s, 0, sizeof(s));
+	s.ix = ix;
+	s.max_kfreq = max_kfreq;
+	s.sensitivity = sensitivity;
+	s.mutate_mode = mutate_mode;
+	s.bs_cutoff = bs_cutoff;
+	s.read_skip = (unsigned) read_skip;
+	s.probe_budget_on = 1;
+	state_alloc(&s, 20);
+	long long total = 0;
+	for (int r = 0; r < n_reads; ++r) {
+		const char *read = reads + (size_t) r * stride;
+		int len = 0;
+		while (len < stride && read[len] != '\0') ++len;
+		cand_begin[r] = (int) total;
+		const int second = paired && (r & 1);                       /* ReadId & 1, CS.cpp:362-380 */
+		if (mutate_mode == 2) {
+			s.mutate_from = second ? 3 : 1;
+			s.mutate_to = second ? 0 : 2;
+		} else {
+			s.mutate_from = second ? 0 : 2;
+			s.mutate_to = second ? 3 : 1;
+		}
+		const long long room = out_cap - total;
+		const int cap = room > 0x7fffffff ? 0x7fffffff : (room < 0 ? 0 : (int) room);
+		int n = -1, x = 2, bits = table_bits, tries = 0;
+		while (n < 0 && bits <= 20) {
+			s.table_bits = bits;
+			s.table_len = (uint32_t) 1 << bits;
+			s.hpoc = (uint32_t) ((float) (int) s.table_len * (tries == 0 ? 0.333f : 0.777f));      /* CS.cpp:392,418 */
+			n = search_one(&s, read, len, kmer_min, max_cmrs, out + total, cap, max_hit ? max_hit + r : 0);
+			bits = table_bits + x;
+			x += 1;
+			++tries;
+		}
+		if (n < 0) n = 0;
 		total += n;
 	}
 	cand_begin[n_reads] = (int) total;

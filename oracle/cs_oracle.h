@@ -49,6 +49,14 @@ int cs_oracle_search(const cs_oracle_index *ix, const char *read, int read_len, 
 long long cs_oracle_search_batch(const cs_oracle_index *ix, const char *reads, int n_reads, int stride, float sensitivity, float kmer_min,
 		int max_kfreq, int max_cmrs, int *cand_begin, cs_oracle_cand *out, long long out_cap, float *max_hit);
 
+/* CS::RunBatch under bs_mapping (mutate_mode 1: every subset of the read k-mer's T -- second mate: A -- replaced by C -- G --, k-mers with more
+ * than bs_cutoff such bases skipped, read k-mers taken every read_skip + 1 positions) or slam_seq & 4 (mutate_mode 2: the k-mer with weight 1, its
+ * single replacements C -> T -- second mate: G -> A -- with weight 1 / (replaceable bases + 1)); CS.cpp:53-112,340-436 incl. the table-overflow
+ * retries (table_bits = "search_table_length", 16).  paired: odd rows are second mates. */
+long long cs_oracle_search_batch_mut(const cs_oracle_index *ix, const char *reads, int n_reads, int stride, float sensitivity, float kmer_min,
+		int max_kfreq, int max_cmrs, int mutate_mode, int bs_cutoff, int paired, int read_skip, int table_bits, int *cand_begin,
+		cs_oracle_cand *out, long long out_cap, float *max_hit);
+
 /* The sensitivity NGM estimates when -s is absent (ReadProvider::init, ReadProvider.cpp:236-251,310-325 with the static PrefixSearch
  * :81-123 and CollectResultsFallback :53-79).  `sampled`: the reads number 1000, 2000, ... of the input.  Returns the number of reads
  * that contributed; *sensitivity = min(max(0.3, mean), 0.9) (no --fast / --sensitive modifier). */

@@ -90,6 +90,25 @@ class Index:
                 return begin, out[:total], mh
             cap = int(total) + 16
 
+    def search_mut(self, reads: np.ndarray, sensitivity: float, mutate_mode: int, bs_cutoff: int = 6, paired: bool = False, read_skip: int = 0,
+                   table_bits: int = 16, kmer_min: float = 0.0, max_kfreq: int = 0, max_cmrs: int = 2 ** 31 - 1):
+        """CS::RunBatch under --bs-mapping (mutate_mode 1) / --slam-seq 4 (mutate_mode 2); same outputs as `search`."""
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        n, stride = reads.shape
+        begin = np.zeros(n + 1, np.int32)
+        mh = np.zeros(n, np.float32)
+        cap = max(1024, 64 * n)
+        self.lib.cs_oracle_search_batch_mut.restype = C.c_longlong
+        while True:
+            out = np.zeros(cap, dtype=CAND)
+            total = self.lib.cs_oracle_search_batch_mut(C.byref(self.c), reads.ctypes.data_as(C.c_void_p), n, stride, C.c_float(sensitivity),
+                                                        C.c_float(kmer_min), max_kfreq or self.max_kfreq, max_cmrs, mutate_mode, bs_cutoff,
+                                                        1 if paired else 0, read_skip, table_bits, begin.ctypes.data_as(C.c_void_p),
+                                                        out.ctypes.data_as(C.c_void_p), C.c_longlong(cap), mh.ctypes.data_as(C.c_void_p))
+            if total <= cap:
+                return begin, out[:total], mh
+            cap = int(total) + 16
+
     def estimate_sensitivity(self, reads: np.ndarray, max_kfreq: int = 0):
         """ReadProvider::init's estimate over the whole input (every 1000th read of the first 10 M) -> (sensitivity, contributing reads);
         (0.5, 0) for fewer than 1000 reads (ReadProvider.cpp:310,372-379)."""

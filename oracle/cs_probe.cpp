@@ -7,6 +7,7 @@
 // NGM_main.cpp:123-138 and the per-read reset of CS::RunBatch (CS.cpp:346-392), which cannot be called itself because
 // it hands the reads on to the score buffer.
 //
+// With --bs-mapping / --slam-seq the callback is CS::PrefixMutateSearch, as in CS::RunBatch.
 // usage: ngm_cs_probe <ngm options: -r ref -q reads -s sens ...>      (candidates go to stdout, NGM's log to stderr)
 // line format: <ReadId> <name> <length> <maxHit> <n> {<location>:<strand>:<votes>}
 #include <stdio.h>
@@ -45,8 +46,7 @@ public:
 	Probe() : CS(false) {
 	}
 	void Run(FILE * out) {
-		int const tableBits = 20;              // large enough never to overflow; the table size does not influence the result
-		int const len = 1 << 24;
+		int const len = 1 << 20;               // the largest table CS::RunBatch ever switches to (CS.cpp:406-407)
 		rTable = new CSTableEntry[len];        // CS::DoRun, CS.cpp:466-474
 		rList = new int[len];
 		for (int i = 0; i < len; ++i) {
@@ -54,7 +54,6 @@ public:
 			rTable[i].state = -1;
 			rList[i] = -1;
 		}
-		SetSearchTableBitLen(tableBits);
 		m_CsSensitivity = Config.GetFloat("sensitivity", 0, 1);
 		m_RefProvider = NGM.GetRefProvider(0);
 		AllocRefEntryChain();
@@ -63,15 +62,42 @@ public:
 			for (size_t i = 0; i < m_CurrentBatch.size(); ++i) {
 				MappedRead * read = m_CurrentBatch[i];
 				m_CurrentSeq = read->ReadId;
-				currentState++;                // CS::RunBatch, CS.cpp:351-357
-				rListLength = 0;
-				maxHitNumber = 0.0f;
-				currentThresh = 0.0f;
-				kCount = 0;
+				// CS::RunBatch, CS.cpp:341-431, without SendToBuffer: the k-mer callback and the mutated base by mode and mate, the
+				// per-read reset, the search in the configured table and its retries in larger ones after an overflow
+				PrefixIterationFn pFunc = (m_EnableBS || m_EnableSlamSeq) ? &CS::PrefixMutateSearch : &CS::PrefixSearch;
+				ulong mutateFrom, mutateTo;
+				if (Config.GetInt("paired") > 0 && (read->ReadId & 1)) {
+					mutateFrom = m_EnableSlamSeq ? 0x3 : 0x0;
+					mutateTo = m_EnableSlamSeq ? 0x0 : 0x3;
+				} else {
+					mutateFrom = m_EnableSlamSeq ? 0x1 : 0x2;
+					mutateTo = m_EnableSlamSeq ? 0x2 : 0x1;
+				}
 				m_CurrentReadLength = read->length;
-				hpoc = c_SrchTableLen * 0.333f;
-				PrefixIteration(read->Seq, read->length, &CS::PrefixSearch, 0x2, 0x1, this, m_PrefixBaseSkip);
-				CollectResultsStd(read);
+				int const bitsConfigured = c_SrchTableBitLen;
+				int bits = bitsConfigured;
+				int x = 2;
+				bool done = false;
+				int tries = 0;
+				while (!done && bits <= 20) {
+					SetSearchTableBitLen(bits);
+					currentState++;
+					rListLength = 0;
+					maxHitNumber = 0.0f;
+					currentThresh = 0.0f;
+					if (tries == 0) kCount = 0;
+					hpoc = c_SrchTableLen * (tries == 0 ? 0.333f : 0.777f);
+					try {
+						PrefixIteration(read->Seq, read->length, pFunc, mutateFrom, mutateTo, this, m_PrefixBaseSkip);
+						CollectResultsStd(read);
+						done = true;
+					} catch (int overflow) {
+						bits = bitsConfigured + x;
+						x += 1;
+					}
+					++tries;
+				}
+				SetSearchTableBitLen(bitsConfigured);
 				fprintf(out, "%d %s %d %.9g %d", read->ReadId, read->name, read->length, maxHitNumber, read->numScores());
 				for (int j = 0; j < read->numScores(); ++j) {
 					fprintf(out, " %llu:%d:%.9g", (unsigned long long) read->Scores[j].Location.m_Location, read->Scores[j].Location.isReverse() ? 1 : 0,

@@ -141,16 +141,28 @@ def map_batch_topn(packed: np.ndarray, concat_len: int, ix: cs_port.Index, reads
 
 
 def map_batch(packed: np.ndarray, concat_len: int, ix: cs_port.Index, reads: np.ndarray, qml: int, corridor: int, mode: int, sensitivity: float,
-              selector: Optional[Selector] = None, paired: bool = False):
+              selector: Optional[Selector] = None, paired: bool = False, mutate: Optional[dict] = None, scoring: Optional[port.Scoring] = None):
+    """mutate: {"mode": 1 (--bs-mapping) | 2 (--slam-seq 4), "bs_cutoff": 6, "read_skip": 2} -> candidate search with CS::PrefixMutateSearch
+    and the direction flag of ScoreBuffer / AlignmentBuffer (strand, inverted for second mates; ScoreBuffer.cpp:92-110, AlignmentBuffer.cpp:84-97)
+    handed to BatchScore / BatchAlign; scoring: the run's scoring scheme (Config.cpp:463-469 under bs_mapping)."""
     reads = np.ascontiguousarray(reads, dtype=np.uint8)
     n = reads.shape[0]
-    begin, cands, max_hit = ix.search(reads, sensitivity)
+    sc = scoring or port.Scoring()
+    if mutate:
+        begin, cands, max_hit = ix.search_mut(reads, sensitivity, mutate["mode"], bs_cutoff=mutate.get("bs_cutoff", 6), paired=paired,
+                                              read_skip=mutate.get("read_skip", 2 if mutate["mode"] == 1 else 0))
+    else:
+        begin, cands, max_hit = ix.search(reads, sensitivity)
     pairs = np.zeros(len(cands), dtype=PAIR)
     pairs["window_start"] = (cands["location"].astype(np.uint64) - np.uint64(corridor >> 1))
     pairs["read_index"] = np.repeat(np.arange(n, dtype=np.uint32), np.diff(begin))
-    pairs["flags"] = np.where(cands["reverse"] != 0, 3, 0)
+    rev = cands["reverse"] != 0
+    second = (pairs["read_index"] & 1).astype(bool) if (mutate and paired) else np.zeros(len(cands), bool)
+    pairs["flags"] = np.where(rev, 1, 0) | np.where(rev ^ second, 2, 0)
+    use_dirs = sc.bs_mapping == 1 or sc.slam_seq != 0           # ScoreBuffer.cpp:127: the direction buffer is only handed over in these modes
+    dirs = ((pairs["flags"] >> 1) & 1).astype(np.uint8) if use_dirs else None
     refs, qrys = _windows(packed, concat_len, reads, pairs, qml, corridor, ((qml + corridor) | 1) + 1, True)
-    scores = port.batch_score(refs, qrys, qml, corridor, mode) if len(pairs) else np.zeros(0, np.float32)
+    scores = port.batch_score(refs, qrys, qml, corridor, mode, sc, dirs) if len(pairs) else np.zeros(0, np.float32)
     selector = selector or Selector()
     read_len = np.array([len(reads[r].tobytes().split(b"\0")[0]) for r in range(n)], np.int32)
     if paired:
@@ -166,9 +178,10 @@ def map_batch(packed: np.ndarray, concat_len: int, ix: cs_port.Index, reads: np.
     strings = {}
     if len(has):
         refs, qrys = _windows(packed, concat_len, reads, winners, qml, corridor, (qml + corridor) | 2, False)
-        for r, a in zip(has, port.batch_align(refs, qrys, qml, corridor, mode)):
+        wdirs = ((winners["flags"] >> 1) & 1).astype(np.uint8) if use_dirs else None
+        for r, a in zip(has, port.batch_align(refs, qrys, qml, corridor, mode, sc, wdirs)):
             recs[r] = (a.position_offset, a.qstart, a.qend, a.nm, a.identity, a.ascore)
             strings[int(r)] = (a.cigar, a.md_raw)
     return SimpleNamespace(cand_begin=begin, pairs=pairs, scores=scores, max_hit=max_hit, best_pair=best, mapq=sel["mapq"].astype(np.int32),
                            num_top=sel["num_top"].astype(np.int32), recs=recs, heap=None, strings=lambda r: strings[int(r)],
-                           pair_fail=sel["paired_fail"].astype(np.int32), insert=sel["insert"].astype(np.int32))
+                           pair_fail=sel["paired_fail"].astype(np.int32) if paired else None, insert=sel["insert"].astype(np.int32))

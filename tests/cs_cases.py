@@ -56,6 +56,24 @@ def make_reads(seed: int, concat: bytes, contigs: List[Tuple[int, int]], n_reads
     return out
 
 
+def convert_bases(reads: np.ndarray, seed: int, mode: int, paired: bool = False) -> np.ndarray:
+    """Chemistry of the mutated searches: mode 1 (bisulfite) turns ~80 % of the C into T -- second mates: G into A --, mode 2 (SLAMseq) ~5 % of the
+    T into C -- second mates: A into G; the k-mer mutation of CS::PrefixMutateSearch undoes exactly these."""
+    rng = np.random.default_rng(seed)
+    out = reads.copy()
+    second = np.zeros(out.shape, bool)
+    if paired:
+        second[1::2] = True
+    draw = rng.random(out.shape)
+    if mode == 1:
+        out[(reads == ord("C")) & ~second & (draw < 0.8)] = ord("T")
+        out[(reads == ord("G")) & second & (draw < 0.8)] = ord("A")
+    else:
+        out[(reads == ord("T")) & ~second & (draw < 0.05)] = ord("C")
+        out[(reads == ord("A")) & second & (draw < 0.05)] = ord("G")
+    return out
+
+
 def write_fasta(path, contig_seqs: List[bytes]) -> None:
     with open(path, "wb") as f:
         for i, s in enumerate(contig_seqs):

@@ -108,3 +108,64 @@ def test_sensitivity_estimate_needs_1000_reads():
     ix = cs_port.Index(port.pack_ref(concat), concat_len, ctg, k=13)
     assert ix.estimate_sensitivity(cs_cases.make_reads(6, concat, ctg, 999, 100, 102)) == (0.5, 0)
     ix.close()
+
+
+# -- bs-mapping / SLAMseq: CS::PrefixMutateSearch (CS.cpp:53-112) ------------------------------------------------------------------
+GOLD_MUT = GOLD.parent / "cs_mut"
+NAMES_MUT = sorted(p.stem for p in GOLD_MUT.glob("*.npz"))
+
+
+def load_mut(name):
+    with np.load(GOLD_MUT / f"{name}.npz") as z:
+        return {k: z[k] for k in z.files}
+
+
+def oracle_lists_mut(ix, g, paired=None):
+    begin, cands, mh = ix.search_mut(g["reads"], float(g["sensitivity"]), int(g["mode"]), bs_cutoff=int(g["bs_cutoff"]),
+                                     paired=bool(g["paired"]) if paired is None else paired, read_skip=int(g["read_skip"]), max_kfreq=int(g["max_kfreq"]))
+    return {r: (float(mh[r]), [(int(c["location"]), int(c["reverse"]), float(c["score"])) for c in cands[begin[r]: begin[r + 1]]])
+            for r in range(g["reads"].shape[0])}
+
+
+@pytest.mark.parametrize("name", NAMES_MUT)
+def test_mutated_search_matches_reference_fixture(name):
+    """Fixtures made by tests/golden/make_cs_mut_golden.py from the reference's own CS code under --bs-mapping / --slam-seq 4."""
+    g = load_mut(name)
+    concat = g["concat"].tobytes()
+    ctg = [(int(a), int(b)) for a, b in g["contigs"]]
+    ix = cs_port.Index(port.pack_ref(concat), len(concat) - 1, ctg, k=int(g["k"]), ref_skip=int(g["ref_skip"]))
+    want = golden_lists(g)
+    got = oracle_lists_mut(ix, g)
+    bad = [(r, want[r], got[r]) for r in want if want[r] != got[r]]
+    assert not bad, f"{len(bad)} reads differ, first {bad[0]}"
+    # the fixture must exercise what it claims: the mutation changes the lists, and the mates mutate different bases
+    plain = oracle_lists(ix, g["reads"], float(g["sensitivity"]), int(g["max_kfreq"]))
+    assert sum(1 for r in want if want[r] != plain[r]) > 20
+    if int(g["paired"]):
+        single = oracle_lists_mut(ix, g, paired=False)
+        assert sum(1 for r in want if (r & 1) and want[r] != single[r]) > 10
+    if int(g["mode"]) == 2:
+        assert sum(1 for r in want for c in want[r][1] if c[2] != int(c[2])) > 50          # fractional votes (weight 1 / m_CurrentMutLocs)
+    ix.close()
+
+
+@pytest.mark.skipif(not cs_port.probe_available(), reason="oracle/_ref/ngm/ngm_cs_probe not built")
+@pytest.mark.parametrize("seed,k,read_len,sens,mode,paired", [(17, 11, 90, 0.5, 1, False), (18, 13, 120, 0.4, 2, True)])
+def test_fresh_mutated_differential_run_against_reference(seed, k, read_len, sens, mode, paired):
+    contigs = cs_cases.make_reference(seed)
+    concat, ctg, concat_len = cs_port.layout(contigs)
+    reads = cs_cases.convert_bases(cs_cases.make_reads(seed + 1, concat, ctg, 300, read_len, (read_len | 1) + 1), seed + 2, mode, paired)
+    extra = (["--bs-mapping"] if mode == 1 else ["--slam-seq", "4"]) + (["-p", "--skip-mate-check"] if paired else [])
+    with tempfile.TemporaryDirectory(prefix="csmutdiff_") as td:
+        d = Path(td)
+        cs_cases.write_fasta(d / "ref.fa", contigs)
+        cs_cases.write_fastq(d / "reads.fq", reads)
+        head, rows = cs_port.run_probe(d, "ref.fa", "reads.fq", sens, k=k, extra=extra)
+    ix = cs_port.Index(port.pack_ref(concat), concat_len, ctg, k=k, ref_skip=0 if mode == 1 else 2)
+    begin, cands, mh = ix.search_mut(reads, sens, mode, paired=paired, read_skip=2 if mode == 1 else 0, max_kfreq=head["max_kfreq"])
+    f32 = lambda x: float(np.float32(x))
+    for (rid, name, ln, m, cl) in rows:
+        r = int(name[1:])
+        got = (float(mh[r]), [(int(c["location"]), int(c["reverse"]), float(c["score"])) for c in cands[begin[r]: begin[r + 1]]])
+        assert got == (f32(m), [(a, b, f32(v)) for a, b, v in cl]), (r, got, (m, cl))
+    ix.close()

@@ -233,3 +233,74 @@ def test_device_to_device_index_transfer():
         np.testing.assert_array_equal(x, y)
     a.close()
     b.close()
+
+
+# -- bs-mapping / SLAMseq candidate search (CS::PrefixMutateSearch, CS.cpp:53-112) ---------------------------------
+GOLD_MUT = GOLD.parent / "cs_mut"
+NAMES_MUT = sorted(p.stem for p in GOLD_MUT.glob("*.npz"))
+
+
+def _mut_context(g_or_none, concat, ctg, concat_len, k, read_len, sens, mode, paired, bs_cutoff, max_kfreq=0):
+    from nextgenmap_b200.host import CudaSW
+    qml, cor = shapes_for(read_len)
+    sw = CudaSW(qml, cor, bs_mapping=1 if mode == 1 else 0, slam_seq=4 if mode == 2 else 0)
+    sw.set_reference(port.pack_ref(concat), concat_len)
+    # CompactPrefixTable indexes every reference position under bs_mapping (PrefixTable.cpp:204-207); the reads' k-mers are thinned instead
+    info = sw.cs_build_index(ctg, sw.cs_params(kmer=k, kmer_skip=0 if mode == 1 else 2, sensitivity=sens, max_kfreq=max_kfreq))
+    sw.cs_configure_mutation(bs_mapping=1 if mode == 1 else 0, slam_seq=4 if mode == 2 else 0, bs_cutoff=bs_cutoff, paired=paired, read_kmer_skip=2)
+    return sw, cor, info
+
+
+@pytest.mark.parametrize("name", NAMES_MUT)
+def test_mutated_search_matches_reference_fixture(name):
+    """tests/golden/cs_mut: what the reference's own CS code produced under --bs-mapping / --slam-seq 4 (single-end and paired)."""
+    with np.load(GOLD_MUT / f"{name}.npz") as z:
+        g = {k: z[k] for k in z.files}
+    concat = g["concat"].tobytes()
+    ctg = [(int(a), int(b)) for a, b in g["contigs"]]
+    sw, cor, info = _mut_context(g, concat, ctg, len(concat) - 1, int(g["k"]), int(g["read_len"]), float(g["sensitivity"]), int(g["mode"]), bool(g["paired"]),
+                                 int(g["bs_cutoff"]))
+    assert info["max_kfreq"] == int(g["max_kfreq"])
+    want = {}
+    for i, r in enumerate(g["read_index"]):
+        b, e = int(g["cand_begin"][i]), int(g["cand_begin"][i + 1])
+        want[int(r)] = (float(g["max_hit"][i]), [(int(g["cand_loc"][j]), int(g["cand_rev"][j]), float(g["cand_votes"][j])) for j in range(b, e)])
+    begin, pairs, votes, mh = sw.cs_search(g["reads"])
+    got = lists_from_device(begin, pairs, votes, mh, cor)
+    bad = [(r, want[r], got[r]) for r in want if want[r] != got[r]]
+    assert not bad, f"{len(bad)} reads differ, first {bad[0]}"
+    assert sw.cs_exact_reads() == len(want)                      # the mutated k-mers are enumerated by the sequential kernel
+    # the direction flag ScoreBuffer would hand to BatchScore (ScoreBuffer.cpp:92-110): the strand, inverted for second mates
+    rd = np.repeat(np.arange(len(begin) - 1), np.diff(begin))
+    rev = (pairs["flags"] & 1).astype(bool)
+    second = (rd & 1).astype(bool) if int(g["paired"]) else np.zeros(len(rd), bool)
+    np.testing.assert_array_equal(((pairs["flags"] >> 1) & 1).astype(bool), rev ^ second)
+    # switching the mutation off again gives the plain search
+    sw.cs_configure_mutation()
+    ix = cs_port.Index(port.pack_ref(concat), len(concat) - 1, ctg, k=int(g["k"]), ref_skip=int(g["ref_skip"]))
+    b2, c2, m2 = ix.search(g["reads"], float(g["sensitivity"]), max_kfreq=int(g["max_kfreq"]))
+    plain = {r: (float(m2[r]), [(int(c["location"]), int(c["reverse"]), float(c["score"])) for c in c2[b2[r]: b2[r + 1]]]) for r in range(g["reads"].shape[0])}
+    assert lists_from_device(*sw.cs_search(g["reads"]), cor) == plain
+    ix.close()
+    sw.close()
+
+
+@pytest.mark.parametrize("seed,k,read_len,sens,mode,paired,cutoff", [(61, 13, 150, 0.5, 1, False, 6), (62, 11, 100, 0.4, 1, True, 4), (63, 13, 150, 0.5, 2, False, 6),
+                                                                      (64, 12, 250, 0.7, 2, True, 6), (65, 10, 60, 0.5, 1, False, 8)])
+def test_mutated_search_fresh_cases_against_oracle(seed, k, read_len, sens, mode, paired, cutoff):
+    contigs = cs_cases.make_reference(seed, 2)
+    concat, ctg, concat_len = cs_port.layout(contigs)
+    qml, cor = shapes_for(read_len)
+    reads = cs_cases.convert_bases(cs_cases.make_reads(seed + 1, concat, ctg, 500, read_len, qml), seed + 2, mode, paired)
+    ix = cs_port.Index(port.pack_ref(concat), concat_len, ctg, k=k, ref_skip=0 if mode == 1 else 2)
+    sw, cor, info = _mut_context(None, concat, ctg, concat_len, k, read_len, sens, mode, paired, cutoff)
+    assert info["table_len"] == ix.table_len and info["max_kfreq"] == ix.max_kfreq
+    begin, cands, mh = ix.search_mut(reads, sens, mode, bs_cutoff=cutoff, paired=paired, read_skip=2 if mode == 1 else 0)
+    want = {r: (float(mh[r]), [(int(c["location"]), int(c["reverse"]), float(c["score"])) for c in cands[begin[r]: begin[r + 1]]])
+            for r in range(reads.shape[0])}
+    got = lists_from_device(*sw.cs_search(reads), cor)
+    bad = [(r, want[r], got[r]) for r in want if want[r] != got[r]]
+    assert not bad, f"{len(bad)} reads differ, first {bad[0]}"
+    assert sum(len(v[1]) for v in want.values()) > 300
+    ix.close()
+    sw.close()

@@ -227,3 +227,69 @@ def test_clipping_and_read_group_identical_to_ngm(flag, paired):
         assert not any("H" in ln.split("\t")[5] or "S" in ln.split("\t")[5] for ln in want)
     sw.close()
     ref.close()
+
+
+def _bisulfite(path, seed, paired):
+    """Directional bisulfite chemistry on the reads of a FASTQ file: ~90 % of the C of a first mate / single read become T, ~90 % of the
+    G of a second mate become A (what CS::PrefixMutateSearch undoes: T -> C, second mate A -> G; CS.cpp:362-380)."""
+    lines = Path(path).read_bytes().split(b"\n")
+    rng = np.random.default_rng(seed)
+    for i in range(1, len(lines), 4):
+        s = np.frombuffer(lines[i], np.uint8).copy()
+        second = paired and ((i // 4) & 1)
+        m = (s == ord("G" if second else "C")) & (rng.random(len(s)) < 0.9)
+        s[m] = ord("A" if second else "T")
+        lines[i] = s.tobytes()
+    Path(path).write_bytes(b"\n".join(lines))
+
+
+@pytest.mark.parametrize("paired,seed", [(False, 71), (True, 72)])
+def test_bs_mapping_sam_identical_to_ngm(paired, seed):
+    """`ngm --bs-mapping` (single-end and `-p`): candidate search with mutated k-mers on an every-position index (CS::PrefixMutateSearch),
+    the bs scoring scheme (match 4, mismatch 2, gaps 10 / 10, T-C pairs by direction; Config.cpp:463-469, SWOcl.cpp:228-242) with the
+    direction flag per candidate, X-op accounting of computeCigarMD under bs_mapping, ZS:Z in the SAM record (SAMWriter.cpp:173-187)."""
+    from nextgenmap_b200.host import CudaSW, EncodedReference
+    from nextgenmap_b200.host import pipeline
+    from tests.test_mapper_oracle import read_fastq as read_fastq_pe, rows
+    read_len = 100
+    with tempfile.TemporaryDirectory(prefix="pipe_bs_") as td:
+        d = Path(td)
+        if paired:
+            e2e.write_paired_inputs(d, ref_len=300_000, n_frags=600, read_len=read_len, seed=seed)
+        else:
+            e2e.write_inputs(d, ref_len=400_000, n_reads=1_500, read_len=read_len, seed=seed, indel_reads=0.15)
+        _bisulfite(d / "reads.fq", seed, paired)
+        want = [ln for ln in e2e.run("ref", d, threads=1, extra=["--bs-mapping", "-s", "0.5"] + (["-p"] if paired else [])) if not ln.startswith("@")]
+        ref = EncodedReference(str(d / "ref.fa-enc.2.ngm"))
+        names, seqs, quals = read_fastq_pe(d / "reads.fq", paired)
+    qml, cor = (read_len | 1) + 1, int(5 + 0.15 * read_len)
+    reads = rows(seqs, qml)
+    sw = CudaSW(qml, cor, match_bonus=4, mismatch_penalty=2, gap_read_penalty=10, gap_ref_penalty=10, match_bonus_tt=4, match_bonus_tc=4, bs_mapping=1)
+    sw.set_reference(ref.packed, ref.concat_len)
+    sw.cs_build_index([(c[1], c[2]) for c in ref.contigs], sw.cs_params(kmer=13, kmer_skip=0, sensitivity=0.5))
+    sw.cs_configure_mutation(bs_mapping=1, bs_cutoff=6, paired=paired, read_kmer_skip=2)
+    if paired:
+        sw.pe_configure()
+        batch = pipeline.map_pairs(sw, reads, 0)
+        batch.bs_mapping = 1
+        got = pipeline.sam_lines_paired(batch, reads, names, quals, ref, cor)
+    else:
+        batch = pipeline.map_reads(sw, reads, 0)
+        batch.bs_mapping = 1
+        got = pipeline.sam_lines(sw, batch, reads, names, quals, ref, cor)
+    native = pipeline.format_sam(batch, reads, names, quals, ref, paired, bs_mapping=1).decode().splitlines()
+    assert native == got
+    if paired:
+        sw.pe_configure()
+    sw.set_pipeline(3, 256)                                        # several lanes, sub-batches of whole pairs
+    one_call = pipeline.map_batch(sw, reads, 0, paired=paired)
+    assert pipeline.format_sam(one_call, reads, names, quals, ref, paired, bs_mapping=1).decode().splitlines() == got
+    got.sort()
+    assert len(got) == len(want)
+    bad = [(g, w) for g, w in zip(got, want) if g != w]
+    assert not bad, f"{len(bad)} of {len(want)} SAM lines differ, first:\n{bad[0][0]}\n{bad[0][1]}"
+    zs = {f for ln in want for f in ln.split("\t")[11:] if f.startswith("ZS:Z:")}
+    assert zs == ({"ZS:Z:++", "ZS:Z:-+", "ZS:Z:--", "ZS:Z:+-"} if paired else {"ZS:Z:++", "ZS:Z:-+"})
+    assert sum(1 for ln in want if not int(ln.split("\t")[1]) & 4) > 0.8 * len(want)
+    sw.close()
+    ref.close()

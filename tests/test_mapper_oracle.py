@@ -12,7 +12,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from oracle import cs_port, mapper_port, ngm_e2e as e2e
+from oracle import cs_port, mapper_port, ngm_e2e as e2e, port
 
 GOLD = Path(__file__).resolve().parent / "golden"
 
@@ -81,7 +81,7 @@ class LaidOutReference:
         pass
 
 
-def oracle_sam(d: Path, read_len: int, mode: int, sens: float, paired: bool, batches: int = 1, sel=None, limits=None):
+def oracle_sam(d: Path, read_len: int, mode: int, sens: float, paired: bool, batches: int = 1, sel=None, limits=None, mutate=None, scoring=None):
     from nextgenmap_b200.host import EncodedReference        # host-only reader of <ref>-enc.2.ngm (no CUDA call)
     from nextgenmap_b200.host import pipeline
     enc = d / "ref.fa-enc.2.ngm"
@@ -89,13 +89,21 @@ def oracle_sam(d: Path, read_len: int, mode: int, sens: float, paired: bool, bat
     names, seqs, quals = read_fastq(d / "reads.fq", paired)
     qml, cor = (read_len | 1) + 1, int(5 + 0.15 * read_len)
     reads = rows(seqs, qml)
-    ix = cs_port.Index(ref.packed, ref.concat_len, [(c[1], c[2]) for c in ref.contigs], k=13)
+    ix = cs_port.Index(ref.packed, ref.concat_len, [(c[1], c[2]) for c in ref.contigs], k=13, ref_skip=0 if (mutate and mutate["mode"] == 1) else 2)
     sel = sel or mapper_port.Selector()
     got, n = [], len(names)
     step = (n // batches + 1) & ~1
     for lo in range(0, n, step):                             # the insert-size sums carry over the batches
         hi = min(n, lo + step)
-        batch = mapper_port.map_batch(ref.packed, ref.concat_len, ix, reads[lo:hi], qml, cor, mode, sens, sel, paired=paired)
+        batch = mapper_port.map_batch(ref.packed, ref.concat_len, ix, reads[lo:hi], qml, cor, mode, sens, sel, paired=paired, mutate=mutate, scoring=scoring)
+        if scoring is not None and scoring.bs_mapping == 1:
+            batch.bs_mapping = 1                             # ZS:Z in the SAM record
+        if mutate is not None and batch.best_pair.size:      # the native formatter gives the same lines (host only)
+            fmt = pipeline.format_sam(with_heap(batch), reads[lo:hi], names[lo:hi], quals[lo:hi],
+                                      ref if enc.exists() else ref.as_encoded_reference(), paired, bs_mapping=getattr(batch, "bs_mapping", 0),
+                                      **(limits or {})).decode().splitlines()
+            assert fmt == (pipeline.sam_lines_paired(batch, reads[lo:hi], names[lo:hi], quals[lo:hi], ref, cor, **(limits or {})) if paired
+                           else pipeline.sam_lines(None, batch, reads[lo:hi], names[lo:hi], quals[lo:hi], ref, cor))
         if paired:
             got += pipeline.sam_lines_paired(batch, reads[lo:hi], names[lo:hi], quals[lo:hi], ref, cor, **(limits or {}))
         else:
@@ -289,3 +297,38 @@ def test_min_mq_identical_to_ngm(paired):
     diff(sorted(got), want)
     assert sum(1 for ln in want if int(ln.split("\t")[1]) & 4) > 300
     ref.close()
+
+
+def bisulfite(path, seed, paired):
+    """Directional bisulfite chemistry on the reads of a FASTQ file: ~90 % of the C of a first mate / single read become T, ~90 % of the
+    G of a second mate become A (what CS::PrefixMutateSearch undoes: T -> C, second mate A -> G; CS.cpp:362-380)."""
+    lines = Path(path).read_bytes().split(b"\n")
+    rng = np.random.default_rng(seed)
+    for i in range(1, len(lines), 4):
+        s = np.frombuffer(lines[i], np.uint8).copy()
+        second = paired and ((i // 4) & 1)
+        m = (s == ord("G" if second else "C")) & (rng.random(len(s)) < 0.9)
+        s[m] = ord("A" if second else "T")
+        lines[i] = s.tobytes()
+    Path(path).write_bytes(b"\n".join(lines))
+
+
+@pytest.mark.skipif(not e2e.available("ref"), reason="oracle/_ref/ngm/ngm_ref not built")
+@pytest.mark.parametrize("paired,seed", [(False, 71), (True, 72)])
+def test_bs_mapping_sam_identical_to_ngm(paired, seed):
+    """`ngm --bs-mapping` against the chain of restatements: mutated candidate search on an every-position index, the bs scoring scheme with the
+    per-candidate direction flag, X-op accounting under bs_mapping, ZS:Z -- pins the direction rule for second mates and the SAM tag."""
+    with tempfile.TemporaryDirectory(prefix="bs_") as td:
+        d = Path(td)
+        if paired:
+            e2e.write_paired_inputs(d, ref_len=300_000, n_frags=600, read_len=100, seed=seed)
+        else:
+            e2e.write_inputs(d, ref_len=400_000, n_reads=1_500, read_len=100, seed=seed, indel_reads=0.15)
+        bisulfite(d / "reads.fq", seed, paired)
+        want = [ln for ln in e2e.run("ref", d, threads=1, extra=["--bs-mapping", "-s", "0.5"] + (["-p"] if paired else [])) if not ln.startswith("@")]
+        sc = port.Scoring(match=4, mismatch=2, gap_read=10, gap_ref=10, bs_mapping=1, match_tt=4, match_tc=4)      # Config.cpp:463-469
+        got, _ = oracle_sam(d, 100, 0, 0.5, paired, mutate={"mode": 1, "bs_cutoff": 6, "read_skip": 2}, scoring=sc)
+    diff(got, want)
+    zs = {f for ln in want for f in ln.split("\t")[11:] if f.startswith("ZS:Z:")}
+    assert zs == ({"ZS:Z:++", "ZS:Z:-+", "ZS:Z:--", "ZS:Z:+-"} if paired else {"ZS:Z:++", "ZS:Z:-+"})
+    assert sum(1 for ln in want if not int(ln.split("\t")[1]) & 4) > 0.8 * len(want)
