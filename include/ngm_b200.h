@@ -364,6 +364,10 @@ typedef struct ngm_b200_sam_opts {
 	const char *read_group;     /* "rg_id": RG:Z:<id> on every record (SAMWriter.cpp:166-168,358-360); NULL = none */
 	int32_t bs_mapping;         /* "bs_mapping" (1): ZS:Z:++ / -+ (first mate or single read, forward / reverse) or -- / +- (second mate) after NH:i
 	                             * (SAMWriter.cpp:173-187) */
+	int32_t slam_seq;           /* "slam_seq" (!= 0): TC:i (T>C conversions; A>G for reverse reads), RA:Z (the 25 reference-base x read-base counts over
+	                             * the aligned columns) and MP:Z (type:read position:reference position of every mismatch) behind MD:Z -- what
+	                             * computeSlaSeqTags makes of Align::ExtendedData (GenericReadWriter.h:87-181, SAMWriter.cpp:203-222), derived here from
+	                             * CIGAR + MD + the read */
 } ngm_b200_sam_opts;
 /* One batch as the calls above leave it, all host pointers.  Paired runs: rows 2f / 2f + 1 are mates and pair_fail != NULL. */
 typedef struct ngm_b200_sam_batch {

@@ -13,6 +13,7 @@
 
 #include "../../include/ngm_b200.h"
 #include "../../include/ngm_plugin_abi.h"
+#include "slam_tags.h"
 
 #define NGM_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -40,7 +41,7 @@ inline bool is_descriptor(char const *window) { return window != 0 && memcmp(win
 
 class CudaSW : public IAlignment {
 public:
-	CudaSW(ngm_b200_ctx *c, int dev) : ctx(c), device(dev), h_rows(0), h_rows_cap(0) {}
+	CudaSW(ngm_b200_ctx *c, int dev, int slam) : ctx(c), device(dev), slam_seq(slam), h_rows(0), h_rows_cap(0) {}
 	virtual ~CudaSW() {
 		ngm_b200_destroy(ctx);
 		if (h_rows) ngm_b200_host_free(h_rows);
@@ -70,10 +71,31 @@ public:
 			log_msg(2, "BatchAlign failed: %s", ngm_b200_last_error());
 			return 0;
 		}
+		if (slam_seq != 0) keep_columns(got, qry, results);
 		return got;
 	}
 
 private:
+	// Align::ExtendedData under slam_seq: one AlignmentPosition per aligned column, closed by the default-constructed entry (type -1), which
+	// SAMWriter / BAMWriter turn into the TC / RA / MP tags (SWOclCigar.cpp:443-447,484-497,523-535; GenericReadWriter.h:87-181).  The host
+	// frees it with delete[] (MappedRead.cpp:97-99).  Rebuilt from the CIGAR / MD strings just written and the read as it was aligned.
+	void keep_columns(int n, char const *const *qry, Align *results) {
+		std::vector<ngm::SlamPos> pos;
+		for (int i = 0; i < n; ++i) {
+			Align &o = results[i];
+			if (o.Score < 0.0f || o.pBuffer1 == 0 || o.pBuffer2 == 0 || qry[i] == 0) continue;
+			if (!ngm::slam_positions(o.pBuffer1, strlen(o.pBuffer1), o.pBuffer2, strlen(o.pBuffer2), qry[i], (int) strlen(qry[i]), o.QStart, pos)) pos.clear();
+			AlignmentPosition *ap = new AlignmentPosition[pos.size() + 1];
+			for (size_t k = 0; k < pos.size(); ++k) {
+				ap[k].type = pos[k].type;
+				ap[k].readPosition = pos[k].read_pos;
+				ap[k].refPosition = pos[k].ref_pos;
+				ap[k].match = pos[k].match;
+			}
+			o.ExtendedData = ap;
+		}
+	}
+
 	// The descriptor path behind the IAlignment calls of the re-plumbed ScoreBuffer / AlignmentBuffer: the read rows of the batch (each
 	// distinct row once: consecutive candidates of a read share their qry pointer) go to the device as they are -- the caller already
 	// chose Seq or RevSeq (ScoreBuffer.cpp:92-110) --, the windows as {start, row, direction} descriptors.
@@ -167,6 +189,7 @@ private:
 
 	ngm_b200_ctx *ctx;
 	int device;
+	int slam_seq;                       // "slam_seq" != 0: BatchAlign also leaves Align::ExtendedData
 	char *h_rows;                       // pinned staging of the batch's read rows
 	size_t h_rows_cap;
 	std::vector<ngm_b200_pair> desc;
@@ -240,7 +263,7 @@ NGM_EXPORT IAlignment *CreateAlignment(int const mode) {
 		log_msg(2, "CreateAlignment: %s", ngm_b200_last_error());
 		return 0;
 	}
-	return new CudaSW(ctx, p.device);
+	return new CudaSW(ctx, p.device, p.slam_seq);
 }
 
 // -- the two hooks of link_seam/replumb_shim.cpp ---------------------------------------------------------------

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/ngm_b200.h"
+#include "slam_tags.h"
 
 namespace {
 
@@ -99,7 +100,7 @@ struct Line {              // one output line is assembled in a scratch buffer t
 
 size_t line_bound_at(const Job &j, int r, bool aligned, const ngm_b200_align_rec &rec) {       // name + FLAG..TLEN + SEQ + QUAL + tags + CIGAR + MD
 	return strlen(j.b->names[r]) + 2 * (size_t) j.b->stride + (aligned ? (size_t) rec.cigar_len + rec.md_len : 0) + 2 * 100 + 320 +
-			(j.o->read_group != nullptr ? strlen(j.o->read_group) + 8 : 0);
+			(j.o->read_group != nullptr ? strlen(j.o->read_group) + 8 : 0) + (j.o->slam_seq != 0 ? 20 * (size_t) j.b->stride + 192 : 0);
 }
 
 size_t line_bound(const Job &j, int r) { return line_bound_at(j, r, j.b->best_pair[r] >= 0, j.b->recs[r]); }
@@ -213,7 +214,19 @@ void mapped_line(const Job &j, const ReadView &v, int flags, const char *rnext, 
 	tag_int(out, "\tXR:i:", v.length - rec.qstart - rec.qend);
 	out.append("\tMD:Z:");
 	const char *md = b.strings + rec.str_off + rec.cigar_len;
-	out.append(md, strnlen(md, rec.md_len));                    // printed with %s: stops at an embedded NUL (SURVEY 8a note 9)
+	const size_t md_len = strnlen(md, rec.md_len);
+	out.append(md, md_len);                                     // printed with %s: stops at an embedded NUL (SURVEY 8a note 9)
+	if (j.o->slam_seq != 0) {                                   // SAMWriter.cpp:203-222: TC:i / RA:Z / MP:Z from Align::ExtendedData
+		std::string oriented(v.seq, (size_t) v.length), tags;
+		if (v.reverse) {
+			for (int i = 0; i < v.length; ++i) oriented[(size_t) i] = (char) kComp.t[(unsigned char) v.seq[v.length - 1 - i]];
+		}
+		std::vector<ngm::SlamPos> pos;
+		if (ngm::slam_positions(b.strings + rec.str_off, rec.cigar_len, md, md_len, oriented.data(), v.length, rec.qstart, pos)) {
+			ngm::slam_sam_tags(pos, v.reverse, tags);
+			out.append(tags.data(), tags.size());
+		}
+	}
 	out.push_back('\n');
 }
 

@@ -50,7 +50,7 @@ class PeParams(C.Structure):
 class SamOpts(C.Structure):
     """ngm_b200_sam_opts (include/ngm_b200.h); defaults = src/config/Config.cpp:405-410,430-431."""
     _fields_ = [("min_identity", C.c_float), ("min_residues", C.c_float), ("min_insert_size", C.c_int32), ("max_insert_size", C.c_int32), ("threads", C.c_int32),
-                ("min_mq", C.c_int32), ("clip_seq", C.c_int32), ("read_group", C.c_char_p), ("bs_mapping", C.c_int32)]
+                ("min_mq", C.c_int32), ("clip_seq", C.c_int32), ("read_group", C.c_char_p), ("bs_mapping", C.c_int32), ("slam_seq", C.c_int32)]
 
 
 class SamBatch(C.Structure):

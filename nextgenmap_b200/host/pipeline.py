@@ -249,7 +249,53 @@ def _mapped_line(batch, rd: _Read, encref, flags: int, rnext: str, pnext: int, t
     return "\t".join([rd.name, str(flags), encref.contigs[rd.contig][0], str((rd.loc + 1) & 0xFFFFFFFF), str(int(batch.mapq[rd.r])), cigar.decode(),
                       rnext, str((pnext + 1) & 0xFFFFFFFF), str(tlen), s.decode(), q.decode(), "AS:i:%d" % int(batch.scores[rd.bp]),
                       "NM:i:%d" % int(rec["nm"]), "NH:i:%d" % ntop, *zs, "XI:f:" + _xi(float(rec["identity"])), "X0:i:%d" % ntop,
-                      "XE:i:%d" % int(batch.max_hit[rd.r]), "XR:i:%d" % (rd.length - qstart - qend), "MD:Z:" + md.split(b"\0")[0].decode()])
+                      "XE:i:%d" % int(batch.max_hit[rd.r]), "XR:i:%d" % (rd.length - qstart - qend), "MD:Z:" + md.split(b"\0")[0].decode(),
+                      *(_slam_tags(cigar, md.split(b"\0")[0], s, qstart, rd.reverse) if getattr(batch, "slam_seq", 0) else [])])
+
+
+_TRANS = {c: i for i, cs in enumerate((b"Aa", b"Cc", b"Gg", b"Tt")) for c in cs}
+
+
+def _slam_tags(cigar: bytes, md: bytes, oriented: bytes, qstart: int, reverse: bool) -> List[str]:
+    """TC:i / RA:Z / MP:Z of a --slam-seq run (set ``batch.slam_seq``): GenericReadWriter::computeSlaSeqTags (GenericReadWriter.h:87-181) over the
+    AlignmentPosition list computeCigarMD keeps (SWOclCigar.cpp:484-497,523-535), rebuilt from CIGAR + MD + the read as it was aligned."""
+    import re
+    rates = [0] * 25
+    mp = []
+    read_pos, ref_pos = qstart, 0
+    toks = re.findall(rb"\d+|\^[A-Za-z]+|[A-Za-z]", md)        # numbers, deletions, single mismatch letters
+    ti, eq = 0, 0
+    for ln, op in re.findall(rb"(\d+)([MIDSH=X])", cigar):
+        ln = int(ln)
+        if op in b"SH":
+            continue
+        if op == b"I":
+            read_pos += ln
+        elif op == b"D":
+            if ti < len(toks) and toks[ti].isdigit():
+                ti += 1
+            ti += 1                                              # the ^... token
+            ref_pos += ln
+        else:
+            for _ in range(ln):
+                q = _TRANS.get(oriented[read_pos], 4)
+                while eq == 0 and ti < len(toks) and toks[ti].isdigit():
+                    eq = int(toks[ti])
+                    ti += 1
+                if eq > 0:
+                    eq -= 1
+                    rates[5 * q + q] += 1
+                else:
+                    t = 5 * _TRANS.get(toks[ti][0], 4) + q
+                    ti += 1
+                    rates[t] += 1
+                    mp.append("%d:%d:%d" % (t, read_pos + 1, ref_pos + 1))
+                read_pos += 1
+                ref_pos += 1
+    out = ["TC:i:%d" % (rates[2] if reverse else rates[16]), "RA:Z:" + ",".join(str(v) for v in rates)]
+    if mp:
+        out.append("MP:Z:" + ",".join(mp))
+    return out
 
 
 def _i32(v: int) -> int:
@@ -368,7 +414,7 @@ def sam_lines_paired(batch, reads: np.ndarray, names: Sequence[str], quals: Sequ
 
 def format_sam(batch, reads: np.ndarray, names: Sequence[str], quals: Sequence[bytes], encref, paired: bool, min_identity: float = 0.65,
                min_residues: float = 0.5, min_insert_size: int = 0, max_insert_size: int = 1000, threads: int = 0, min_mq: int = 0,
-               clip_seq: bool = False, read_group: Optional[str] = None, bs_mapping: int = 0) -> bytes:
+               clip_seq: bool = False, read_group: Optional[str] = None, bs_mapping: int = 0, slam_seq: int = 0) -> bytes:
     """The same lines as ``sam_lines`` / ``sam_lines_paired`` from the library's multi-threaded formatter (``ngm_b200_format_sam``): what a
     C / C++ host calls.  ``encref``: an ``EncodedReference`` (the C struct is handed over as it is).  ``batch.recs`` / ``batch.heap`` as
     ``ngm_b200_align_pairs`` returned them."""
@@ -392,7 +438,7 @@ def format_sam(batch, reads: np.ndarray, names: Sequence[str], quals: Sequence[b
     sb = SamBatch(n, stride, reads.ctypes.data, q.ctypes.data, name_arr, ptr(keep[0]), ptr(keep[1]), ptr(keep[2]), ptr(keep[3]), ptr(keep[4]), ptr(keep[5]),
                   ptr(keep[6]), ptr(keep[7]), ptr(keep[8]), topn if topn > 1 else 0, ptr(sel), ptr(n_sel))
     so = SamOpts(min_identity, min_residues, min_insert_size, max_insert_size, threads, min_mq, 1 if clip_seq else 0, read_group.encode() if read_group else None,
-                 bs_mapping)
+                 bs_mapping, slam_seq)
     used = C.c_size_t(0)
     cap = n * max(topn, 1) * (2 * stride + 256) + 4096
     for _ in range(2):

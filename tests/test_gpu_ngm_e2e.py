@@ -17,10 +17,12 @@ from oracle import ngm_e2e as e2e
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not (e2e.available("ref") and e2e.available("cuda")), reason="oracle/_ref/ngm not built")]
 
 
-def compare(extra, n_reads=10_000, read_len=100, threads=4):
+def compare(extra, n_reads=10_000, read_len=100, threads=4, chemistry=None, ref_len=5_000_000):
     with tempfile.TemporaryDirectory(prefix="ngm_e2e_") as td:
         d = Path(td)
-        e2e.write_inputs(d, ref_len=5_000_000, n_reads=n_reads, read_len=read_len)
+        e2e.write_inputs(d, ref_len=ref_len, n_reads=n_reads, read_len=read_len)
+        if chemistry is not None:
+            chemistry(d / "reads.fq", 5, False)
         want = e2e.run("ref", d, threads=threads, extra=extra, out_name="ref.sam")
         got = e2e.run("cuda", d, threads=threads, extra=extra, out_name="cuda.sam")
         strict = e2e.run("cuda_strict", d, threads=threads, extra=extra, out_name="cuda_strict.sam") if e2e.available("cuda_strict") else got
@@ -43,3 +45,17 @@ def test_config0_end_to_end_mode_sam_identical():
 
 def test_150bp_single_thread_sam_identical():
     compare(extra=(), n_reads=4000, read_len=150, threads=1)
+
+
+def test_bs_mapping_sam_identical():
+    """`--bs-mapping`: NGM's own mutated candidate search feeds the backend the bs scoring scheme with a direction flag per candidate
+    (ScoreBuffer.cpp:92-110,127) -- through the descriptors of the re-plumbed callers and through the strict char** path."""
+    from tests.test_mapper_oracle import bisulfite
+    compare(extra=("--bs-mapping",), n_reads=3000, threads=2, chemistry=bisulfite, ref_len=1_000_000)
+
+
+def test_slam_seq_sam_identical():
+    """`--slam-seq 7`: T>C tolerant scoring, and BatchAlign leaves Align::ExtendedData (one AlignmentPosition per aligned column), from which
+    NGM's SAMWriter prints TC:i / RA:Z / MP:Z."""
+    from tests.test_mapper_oracle import slam_convert
+    compare(extra=("--slam-seq", "7"), n_reads=3000, threads=2, chemistry=slam_convert, ref_len=1_000_000)

@@ -293,3 +293,51 @@ def test_bs_mapping_sam_identical_to_ngm(paired, seed):
     assert sum(1 for ln in want if not int(ln.split("\t")[1]) & 4) > 0.8 * len(want)
     sw.close()
     ref.close()
+
+
+@pytest.mark.parametrize("paired,slam,seed", [(False, 6, 81), (True, 7, 82)])
+def test_slam_seq_sam_identical_to_ngm(paired, slam, seed):
+    """`ngm --slam-seq <bits>`: weighted k-mer mutation in candidate search (bit 2: fractional votes, XE:i is their integer part), the T>C
+    tolerant scoring scheme with the direction flag (bit 1), TC:i / RA:Z / MP:Z in the SAM record from CIGAR + MD + read."""
+    from nextgenmap_b200.host import CudaSW, EncodedReference
+    from nextgenmap_b200.host import pipeline
+    from tests.test_mapper_oracle import read_fastq as read_fastq_pe, rows, slam_convert
+    read_len = 100
+    with tempfile.TemporaryDirectory(prefix="pipe_slam_") as td:
+        d = Path(td)
+        if paired:
+            e2e.write_paired_inputs(d, ref_len=300_000, n_frags=500, read_len=read_len, seed=seed)
+        else:
+            e2e.write_inputs(d, ref_len=400_000, n_reads=1_200, read_len=read_len, seed=seed, indel_reads=0.2)
+        slam_convert(d / "reads.fq", seed, paired)
+        want = [ln for ln in e2e.run("ref", d, threads=1, extra=["--slam-seq", str(slam), "-s", "0.5"] + (["-p"] if paired else [])) if not ln.startswith("@")]
+        ref = EncodedReference(str(d / "ref.fa-enc.2.ngm"))
+        names, seqs, quals = read_fastq_pe(d / "reads.fq", paired)
+    qml, cor = (read_len | 1) + 1, int(5 + 0.15 * read_len)
+    reads = rows(seqs, qml)
+    sw = CudaSW(qml, cor, match_bonus_tt=10, match_bonus_tc=2, slam_seq=slam)                       # Config.cpp:446-447
+    sw.set_reference(ref.packed, ref.concat_len)
+    sw.cs_build_index([(c[1], c[2]) for c in ref.contigs], sw.cs_params(kmer=13, sensitivity=0.5))
+    sw.cs_configure_mutation(slam_seq=slam, paired=paired)
+    if paired:
+        sw.pe_configure()
+        batch = pipeline.map_pairs(sw, reads, 0)
+        batch.slam_seq = slam
+        got = pipeline.sam_lines_paired(batch, reads, names, quals, ref, cor)
+    else:
+        batch = pipeline.map_reads(sw, reads, 0)
+        batch.slam_seq = slam
+        got = pipeline.sam_lines(sw, batch, reads, names, quals, ref, cor)
+    assert pipeline.format_sam(batch, reads, names, quals, ref, paired, slam_seq=slam).decode().splitlines() == got
+    if paired:
+        sw.pe_configure()
+    sw.set_pipeline(3, 256)
+    one_call = pipeline.map_batch(sw, reads, 0, paired=paired)
+    assert pipeline.format_sam(one_call, reads, names, quals, ref, paired, slam_seq=slam).decode().splitlines() == got
+    got.sort()
+    assert len(got) == len(want)
+    bad = [(g, w) for g, w in zip(got, want) if g != w]
+    assert not bad, f"{len(bad)} of {len(want)} SAM lines differ, first:\n{bad[0][0]}\n{bad[0][1]}"
+    assert sum(1 for ln in want if "\tMP:Z:" in ln) > 0.5 * len(want)
+    sw.close()
+    ref.close()

@@ -98,10 +98,12 @@ def oracle_sam(d: Path, read_len: int, mode: int, sens: float, paired: bool, bat
         batch = mapper_port.map_batch(ref.packed, ref.concat_len, ix, reads[lo:hi], qml, cor, mode, sens, sel, paired=paired, mutate=mutate, scoring=scoring)
         if scoring is not None and scoring.bs_mapping == 1:
             batch.bs_mapping = 1                             # ZS:Z in the SAM record
-        if mutate is not None and batch.best_pair.size:      # the native formatter gives the same lines (host only)
+        if scoring is not None and scoring.slam_seq != 0:
+            batch.slam_seq = scoring.slam_seq                # TC:i / RA:Z / MP:Z
+        if scoring is not None and batch.best_pair.size:     # the native formatter gives the same lines (host only)
             fmt = pipeline.format_sam(with_heap(batch), reads[lo:hi], names[lo:hi], quals[lo:hi],
                                       ref if enc.exists() else ref.as_encoded_reference(), paired, bs_mapping=getattr(batch, "bs_mapping", 0),
-                                      **(limits or {})).decode().splitlines()
+                                      slam_seq=getattr(batch, "slam_seq", 0), **(limits or {})).decode().splitlines()
             assert fmt == (pipeline.sam_lines_paired(batch, reads[lo:hi], names[lo:hi], quals[lo:hi], ref, cor, **(limits or {})) if paired
                            else pipeline.sam_lines(None, batch, reads[lo:hi], names[lo:hi], quals[lo:hi], ref, cor))
         if paired:
@@ -332,3 +334,35 @@ def test_bs_mapping_sam_identical_to_ngm(paired, seed):
     zs = {f for ln in want for f in ln.split("\t")[11:] if f.startswith("ZS:Z:")}
     assert zs == ({"ZS:Z:++", "ZS:Z:-+", "ZS:Z:--", "ZS:Z:+-"} if paired else {"ZS:Z:++", "ZS:Z:-+"})
     assert sum(1 for ln in want if not int(ln.split("\t")[1]) & 4) > 0.8 * len(want)
+
+
+def slam_convert(path, seed, paired):
+    """SLAMseq chemistry: ~6 % of the T of a first mate / single read are read as C, ~6 % of the A of a second mate as G."""
+    lines = Path(path).read_bytes().split(b"\n")
+    rng = np.random.default_rng(seed)
+    for i in range(1, len(lines), 4):
+        s = np.frombuffer(lines[i], np.uint8).copy()
+        second = paired and ((i // 4) & 1)
+        m = (s == ord("A" if second else "T")) & (rng.random(len(s)) < 0.06)
+        s[m] = ord("G" if second else "C")
+        lines[i] = s.tobytes()
+    Path(path).write_bytes(b"\n".join(lines))
+
+
+@pytest.mark.skipif(not e2e.available("ref"), reason="oracle/_ref/ngm/ngm_ref not built")
+@pytest.mark.parametrize("paired,slam,seed", [(False, 6, 81), (True, 7, 82), (False, 1, 83)])
+def test_slam_seq_sam_identical_to_ngm(paired, slam, seed):
+    """`ngm --slam-seq <bits>`: bit 1 (2) the T>C tolerant scoring scheme with the per-candidate direction flag, bit 2 (4) the weighted k-mer
+    mutation in candidate search, any bit the per-column record behind the TC:i / RA:Z / MP:Z tags (Align::ExtendedData)."""
+    with tempfile.TemporaryDirectory(prefix="slam_") as td:
+        d = Path(td)
+        if paired:
+            e2e.write_paired_inputs(d, ref_len=300_000, n_frags=500, read_len=100, seed=seed)
+        else:
+            e2e.write_inputs(d, ref_len=400_000, n_reads=1_200, read_len=100, seed=seed, indel_reads=0.2)
+        slam_convert(d / "reads.fq", seed, paired)
+        want = [ln for ln in e2e.run("ref", d, threads=1, extra=["--slam-seq", str(slam), "-s", "0.5"] + (["-p"] if paired else [])) if not ln.startswith("@")]
+        sc = port.Scoring(slam_seq=slam, match_tt=10, match_tc=2)                                     # Config.cpp:446-447
+        got, _ = oracle_sam(d, 100, 0, 0.5, paired, mutate={"mode": 2} if slam & 4 else None, scoring=sc)
+    diff(got, want)
+    assert sum(1 for ln in want if "\tMP:Z:" in ln) > 0.5 * len(want) and sum(1 for ln in want if "\tTC:i:0" not in ln and "\tTC:i:" in ln) > 0.3 * len(want)
