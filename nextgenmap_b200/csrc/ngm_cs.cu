@@ -473,6 +473,16 @@ int ngm_b200_dev_cs_search(ngm_b200_ctx *c, const void *d_ascii_reads, int n_rea
 		cs->ex_blocks = std::max(8, 2 * sms);
 		cs->ex_bits = P.ex_bits;
 		const size_t tl = (size_t) 1 << P.ex_bits;
+		if (cs->mut_mode != 0) {
+			// every read of a mutated run is searched by one lane, a chain of dependent memory accesses: throughput is the number of lanes in
+			// flight.  Up to 16 per SM, as many as a fifth of the free device memory holds (20 MB of table + list per lane)
+			size_t free_b = 0, total_b = 0;
+			CU(cudaMemGetInfo(&free_b, &total_b));
+			const size_t per_lane = tl * (sizeof(CsExactEntry) + 4);
+			const size_t fit = (free_b / 5) / per_lane;
+			cs->ex_blocks = (int) std::max<size_t>((size_t) cs->ex_blocks, std::min<size_t>(fit, (size_t) 16 * sms));
+			if (const char *e = getenv("NGM_B200_CS_MUT_LANES")) cs->ex_blocks = std::max(1, atoi(e));
+		}
 		CU(cs->d_ex_tables.ensure(tl * sizeof(CsExactEntry) * cs->ex_blocks));
 		CU(cs->d_ex_rlists.ensure(tl * 4 * cs->ex_blocks));
 		CU(cs->d_ex_gens.ensure((size_t) cs->ex_blocks * 4));
