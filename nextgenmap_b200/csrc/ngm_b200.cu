@@ -323,18 +323,6 @@ int stage_strict(ngm_b200_ctx *c, int base, int m, const char *const *ref, const
 	CU(c->h_flags.ensure((size_t) m));
 	char *hr = c->h_reads.as<char>(), *hf = c->h_refs.as<char>();
 	uint8_t *fl = c->h_flags.as<uint8_t>();
-	for (int i = 0; i < m; ++i) {
-		memcpy(hr + (size_t) i * qml, qry[base + i], (size_t) qml);
-		memcpy(hf + (size_t) i * rw, ref[base + i], (size_t) rw);
-	}
-	for (int i = 0; i < m; ++i) {
-		// CPU-device quirk: only lane 0 of every quad is tested for an empty read
-		// (oclSwScore.cl:37,124; oclEndFreeScore.cl:20,74); base is a multiple of 4.
-		const int leader = i & ~3;
-		uint32_t f = hr[(size_t) leader * qml] == '\0' ? PF_INACTIVE : 0u;
-		if (dir != nullptr && (c->dp.alt || c->dp.acct_alt) && dir[base + i] != 0) f |= PF_DIR;
-		fl[i] = (uint8_t) f;
-	}
 	const int RW = c->dp.read_words, WW = c->win_words;
 	CU(c->d_areads.ensure((size_t) m * qml));
 	CU(c->d_arefs.ensure((size_t) m * rw));
@@ -345,9 +333,28 @@ int stage_strict(ngm_b200_ctx *c, int base, int m, const char *const *ref, const
 	CU(c->d_wins4.ensure(((size_t) m + 2) * WW * 4 + 4096));
 	CU(c->d_pairs.ensure((size_t) m * sizeof(PairDesc)));
 	cudaStream_t st = c->stream;
-	CU(cudaMemcpyAsync(c->d_areads.p, hr, (size_t) m * qml, cudaMemcpyHostToDevice, st));
-	CU(cudaMemcpyAsync(c->d_arefs.p, hf, (size_t) m * rw, cudaMemcpyHostToDevice, st));
-	CU(cudaMemcpyAsync(c->d_flags.p, fl, (size_t) m, cudaMemcpyHostToDevice, st));
+	// the rows are gathered piece by piece and every piece is sent while the next one is gathered (the reference overlaps the packing of
+	// one chunk with the kernel of the previous one the same way, SWOcl.cpp:435-444)
+	constexpr int kPiece = 8192;                               // a multiple of 4: quad leaders stay inside their piece
+	for (int p0 = 0; p0 < m; p0 += kPiece) {
+		const int p1 = std::min(m, p0 + kPiece);
+		for (int i = p0; i < p1; ++i) {
+			memcpy(hr + (size_t) i * qml, qry[base + i], (size_t) qml);
+			memcpy(hf + (size_t) i * rw, ref[base + i], (size_t) rw);
+		}
+		for (int i = p0; i < p1; ++i) {
+			// CPU-device quirk: only lane 0 of every quad is tested for an empty read
+			// (oclSwScore.cl:37,124; oclEndFreeScore.cl:20,74); base is a multiple of 4.
+			const int leader = i & ~3;
+			uint32_t f = hr[(size_t) leader * qml] == '\0' ? PF_INACTIVE : 0u;
+			if (dir != nullptr && (c->dp.alt || c->dp.acct_alt) && dir[base + i] != 0) f |= PF_DIR;
+			fl[i] = (uint8_t) f;
+		}
+		const size_t np = (size_t) (p1 - p0);
+		CU(cudaMemcpyAsync(c->d_areads.as<char>() + (size_t) p0 * qml, hr + (size_t) p0 * qml, np * qml, cudaMemcpyHostToDevice, st));
+		CU(cudaMemcpyAsync(c->d_arefs.as<char>() + (size_t) p0 * rw, hf + (size_t) p0 * rw, np * rw, cudaMemcpyHostToDevice, st));
+		CU(cudaMemcpyAsync(c->d_flags.as<char>() + p0, fl + p0, np, cudaMemcpyHostToDevice, st));
+	}
 	CU(cudaMemsetAsync(c->d_rlen32.p, 0, (size_t) m * 4, st));
 	CU(c->d_noncanon.ensure((size_t) m));
 	CU(cudaMemsetAsync(c->d_noncanon.p, 0, (size_t) m, st));

@@ -291,18 +291,28 @@ class CudaSW:
                              int(r["qend"]), float(r["score"]), float(r["identity"]), int(r["nm"])))
         return out
 
-    def batch_align_raw(self, mode: int, refs: np.ndarray, qrys: np.ndarray, extData=None):
-        """BatchAlign into numpy buffers: (struct Align array, CIGAR rows, MD rows); rows are 4*qry_max_len+ bytes
-        pre-filled with "!!!" like AlignmentBuffer.cpp:108-109."""
-        n = refs.shape[0]
+    def alloc_align_buffers(self, n: int):
+        """What AlignmentBuffer allocates ONCE per thread (AlignmentBuffer.h:63-90, AlignmentBuffer.cpp:106-109): the struct Align array and the
+        CIGAR / MD rows of 4*qry_max_len+ bytes its pBuffer1 / pBuffer2 point to.  -> (res, cig, md), touched, for ``batch_align_raw(buffers=)``."""
         stride = 4 * max(1, self.qml) + 2 * self.corridor + 64
         cig = np.zeros((n, stride), np.uint8)
         md = np.zeros((n, stride), np.uint8)
-        cig[:, :3] = 0x21
-        md[:, :3] = 0x21
         res = np.zeros(n, dtype=ALIGN_C)
         res["cigar"] = _row_pointers(cig)
         res["md"] = _row_pointers(md)
+        return res, cig, md
+
+    def batch_align_raw(self, mode: int, refs: np.ndarray, qrys: np.ndarray, extData=None, buffers=None):
+        """BatchAlign into numpy buffers: (struct Align array, CIGAR rows, MD rows); rows are 4*qry_max_len+ bytes
+        pre-filled with "!!!" like AlignmentBuffer.cpp:108-109.  buffers: the result of ``alloc_align_buffers`` (reused by a caller that,
+        like AlignmentBuffer, keeps its result buffers over the batches)."""
+        n = refs.shape[0]
+        res, cig, md = buffers if buffers is not None else self.alloc_align_buffers(n)
+        res, cig, md = res[:n], cig[:n], md[:n]
+        cig[:, :3] = 0x21
+        md[:, :3] = 0x21
+        cig[:, 3] = 0
+        md[:, 3] = 0
         rp, qp = _row_pointers(refs), _row_pointers(qrys)
         d = None if extData is None else np.ascontiguousarray(extData, dtype=np.uint8)
         got = self._check(self.lib.ngm_b200_batch_align(self.ctx, mode, n, rp.ctypes.data, qp.ctypes.data, qp.ctypes.data,
