@@ -467,27 +467,33 @@ int ngm_b200_dev_cs_search(ngm_b200_ctx *c, const void *d_ascii_reads, int n_rea
 	CU(cs->d_counts.ensure(((size_t) n_reads + 1) * 4));
 	CU(cudaMemsetAsync(cs->d_cursor.p, 0, 4, st));
 	CU(cudaMemsetAsync(cs->d_slow_count.p, 0, 64, st));
-	if (cs->ex_blocks == 0 || cs->ex_bits != P.ex_bits) {
+	{
 		int sms = 0;
 		CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-		cs->ex_blocks = std::max(8, 2 * sms);
-		cs->ex_bits = P.ex_bits;
+		int want = std::max(8, 2 * sms);
 		const size_t tl = (size_t) 1 << P.ex_bits;
-		if (cs->mut_mode != 0) {
+		if (cs->mut_mode != 0 && n_reads > want && cs->ex_blocks < std::min(n_reads, 16 * sms)) {
 			// every read of a mutated run is searched by one lane, a chain of dependent memory accesses: throughput is the number of lanes in
-			// flight.  Up to 16 per SM, as many as a fifth of the free device memory holds (20 MB of table + list per lane)
+			// flight.  One per read of the batch, up to 16 per SM, as many as a fifth of the free device memory holds (20 MB of table + list
+			// per lane); grown when a larger batch arrives
 			size_t free_b = 0, total_b = 0;
 			CU(cudaMemGetInfo(&free_b, &total_b));
 			const size_t per_lane = tl * (sizeof(CsExactEntry) + 4);
-			const size_t fit = (free_b / 5) / per_lane;
-			cs->ex_blocks = (int) std::max<size_t>((size_t) cs->ex_blocks, std::min<size_t>(fit, (size_t) 16 * sms));
-			if (const char *e = getenv("NGM_B200_CS_MUT_LANES")) cs->ex_blocks = std::max(1, atoi(e));
+			const size_t have = cs->ex_bits == P.ex_bits ? (size_t) cs->ex_blocks : 0;
+			const size_t fit = have + (free_b / 5) / per_lane;
+			want = (int) std::max<size_t>((size_t) want, std::min<size_t>(fit, (size_t) std::min(n_reads, 16 * sms)));
 		}
-		CU(cs->d_ex_tables.ensure(tl * sizeof(CsExactEntry) * cs->ex_blocks));
-		CU(cs->d_ex_rlists.ensure(tl * 4 * cs->ex_blocks));
-		CU(cs->d_ex_gens.ensure((size_t) cs->ex_blocks * 4));
-		CU(cudaMemsetAsync(cs->d_ex_tables.p, 0xFF, tl * sizeof(CsExactEntry) * cs->ex_blocks, st));
-		CU(cudaMemsetAsync(cs->d_ex_gens.p, 0, (size_t) cs->ex_blocks * 4, st));
+		if (cs->mut_mode != 0)
+			if (const char *e = getenv("NGM_B200_CS_MUT_LANES")) want = std::max(1, atoi(e));
+		if (cs->ex_blocks == 0 || cs->ex_bits != P.ex_bits || cs->ex_blocks < want) {
+			cs->ex_blocks = want;
+			cs->ex_bits = P.ex_bits;
+			CU(cs->d_ex_tables.ensure(tl * sizeof(CsExactEntry) * cs->ex_blocks));
+			CU(cs->d_ex_rlists.ensure(tl * 4 * cs->ex_blocks));
+			CU(cs->d_ex_gens.ensure((size_t) cs->ex_blocks * 4));
+			CU(cudaMemsetAsync(cs->d_ex_tables.p, 0xFF, tl * sizeof(CsExactEntry) * cs->ex_blocks, st));
+			CU(cudaMemsetAsync(cs->d_ex_gens.p, 0, (size_t) cs->ex_blocks * 4, st));
+		}
 	}
 	const uint8_t *reads = static_cast<const uint8_t *>(d_ascii_reads);
 	CsMeta *meta = cs->d_meta.as<CsMeta>();
