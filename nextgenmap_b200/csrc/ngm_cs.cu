@@ -659,7 +659,12 @@ int ngm_b200_cs_estimate_sensitivity(ngm_b200_ctx *c, const char *sampled_reads,
 	std::vector<float> best((size_t) n);
 	ngm_b200_pair dummy;
 	size_t total = 0;
+	// ReadProvider::init votes with its own plain PrefixSearch unless bs_mapping is set, and under bs_mapping it does not use the estimate at
+	// all (ReadProvider.cpp:194-197,326,378-384: 0.5 unless -s): the estimate never sees mutated k-mers
+	const int mut_mode = c->cs->mut_mode;
+	c->cs->mut_mode = 0;
 	int rc = ngm_b200_cs_search(c, sampled_reads, n, stride, 2, begin.data(), &dummy, nullptr, 0, &total, best.data());
+	c->cs->mut_mode = mut_mode;
 	if (rc < 0 && rc != NGM_B200_ERANGE) return rc;                 // the candidates themselves are not wanted
 	const int skip = c->cs->step;
 	float sum = 0.0f;

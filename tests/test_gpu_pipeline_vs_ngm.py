@@ -295,8 +295,8 @@ def test_bs_mapping_sam_identical_to_ngm(paired, seed):
     ref.close()
 
 
-@pytest.mark.parametrize("paired,slam,seed", [(False, 6, 81), (True, 7, 82)])
-def test_slam_seq_sam_identical_to_ngm(paired, slam, seed):
+@pytest.mark.parametrize("paired,slam,seed,estimate", [(False, 6, 81, False), (True, 7, 82, False), (False, 6, 84, True)])
+def test_slam_seq_sam_identical_to_ngm(paired, slam, seed, estimate):
     """`ngm --slam-seq <bits>`: weighted k-mer mutation in candidate search (bit 2: fractional votes, XE:i is their integer part), the T>C
     tolerant scoring scheme with the direction flag (bit 1), TC:i / RA:Z / MP:Z in the SAM record from CIGAR + MD + read."""
     from nextgenmap_b200.host import CudaSW, EncodedReference
@@ -310,7 +310,10 @@ def test_slam_seq_sam_identical_to_ngm(paired, slam, seed):
         else:
             e2e.write_inputs(d, ref_len=400_000, n_reads=1_200, read_len=read_len, seed=seed, indel_reads=0.2)
         slam_convert(d / "reads.fq", seed, paired)
-        want = [ln for ln in e2e.run("ref", d, threads=1, extra=["--slam-seq", str(slam), "-s", "0.5"] + (["-p"] if paired else [])) if not ln.startswith("@")]
+        # estimate: no -s -- NGM estimates the sensitivity with PLAIN k-mers (ReadProvider::init), the run itself mutates them
+        want = [ln for ln in e2e.run("ref", d, threads=1, extra=["--slam-seq", str(slam)] + ([] if estimate else ["-s", "0.5"]) + (["-p"] if paired else []))
+                if not ln.startswith("@")]
+        logged = e2e.logged_sensitivity() if estimate else None
         ref = EncodedReference(str(d / "ref.fa-enc.2.ngm"))
         names, seqs, quals = read_fastq_pe(d / "reads.fq", paired)
     qml, cor = (read_len | 1) + 1, int(5 + 0.15 * read_len)
@@ -319,6 +322,9 @@ def test_slam_seq_sam_identical_to_ngm(paired, slam, seed):
     sw.set_reference(ref.packed, ref.concat_len)
     sw.cs_build_index([(c[1], c[2]) for c in ref.contigs], sw.cs_params(kmer=13, sensitivity=0.5))
     sw.cs_configure_mutation(slam_seq=slam, paired=paired)
+    if estimate:
+        got_sens = sw.cs_estimate_sensitivity(reads)               # after the mutation was switched on: it must not take part
+        assert "%f" % got_sens == "%f" % logged and 0.3 < got_sens < 0.9
     if paired:
         sw.pe_configure()
         batch = pipeline.map_pairs(sw, reads, 0)

@@ -350,8 +350,8 @@ def slam_convert(path, seed, paired):
 
 
 @pytest.mark.skipif(not e2e.available("ref"), reason="oracle/_ref/ngm/ngm_ref not built")
-@pytest.mark.parametrize("paired,slam,seed", [(False, 6, 81), (True, 7, 82), (False, 1, 83)])
-def test_slam_seq_sam_identical_to_ngm(paired, slam, seed):
+@pytest.mark.parametrize("paired,slam,seed,estimate", [(False, 6, 81, False), (True, 7, 82, False), (False, 1, 83, False), (False, 6, 84, True)])
+def test_slam_seq_sam_identical_to_ngm(paired, slam, seed, estimate):
     """`ngm --slam-seq <bits>`: bit 1 (2) the T>C tolerant scoring scheme with the per-candidate direction flag, bit 2 (4) the weighted k-mer
     mutation in candidate search, any bit the per-column record behind the TC:i / RA:Z / MP:Z tags (Align::ExtendedData)."""
     with tempfile.TemporaryDirectory(prefix="slam_") as td:
@@ -361,8 +361,16 @@ def test_slam_seq_sam_identical_to_ngm(paired, slam, seed):
         else:
             e2e.write_inputs(d, ref_len=400_000, n_reads=1_200, read_len=100, seed=seed, indel_reads=0.2)
         slam_convert(d / "reads.fq", seed, paired)
-        want = [ln for ln in e2e.run("ref", d, threads=1, extra=["--slam-seq", str(slam), "-s", "0.5"] + (["-p"] if paired else [])) if not ln.startswith("@")]
+        want = [ln for ln in e2e.run("ref", d, threads=1, extra=["--slam-seq", str(slam)] + ([] if estimate else ["-s", "0.5"]) + (["-p"] if paired else []))
+                if not ln.startswith("@")]
+        sens = 0.5
+        if estimate:                                             # no -s: ReadProvider::init estimates with plain k-mers also under slam_seq
+            ref = LaidOutReference(d / "ref.fa")
+            ix = cs_port.Index(ref.packed, ref.concat_len, [(c[1], c[2]) for c in ref.contigs], k=13)
+            sens, _ = ix.estimate_sensitivity(rows(read_fastq(d / "reads.fq", paired)[1], 102))
+            ix.close()
+            assert "%f" % sens == "%f" % e2e.logged_sensitivity() and 0.3 < sens < 0.9
         sc = port.Scoring(slam_seq=slam, match_tt=10, match_tc=2)                                     # Config.cpp:446-447
-        got, _ = oracle_sam(d, 100, 0, 0.5, paired, mutate={"mode": 2} if slam & 4 else None, scoring=sc)
+        got, _ = oracle_sam(d, 100, 0, sens, paired, mutate={"mode": 2} if slam & 4 else None, scoring=sc)
     diff(got, want)
     assert sum(1 for ln in want if "\tMP:Z:" in ln) > 0.5 * len(want) and sum(1 for ln in want if "\tTC:i:0" not in ln and "\tTC:i:" in ln) > 0.3 * len(want)
