@@ -17,19 +17,23 @@ from oracle import ngm_e2e as e2e
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not (e2e.available("ref") and e2e.available("cuda")), reason="oracle/_ref/ngm not built")]
 
 
-def compare(extra, n_reads=10_000, read_len=100, threads=4, chemistry=None, ref_len=5_000_000):
+def compare(extra, n_reads=10_000, read_len=100, threads=4, chemistry=None, ref_len=5_000_000, paired=False):
     with tempfile.TemporaryDirectory(prefix="ngm_e2e_") as td:
         d = Path(td)
-        e2e.write_inputs(d, ref_len=ref_len, n_reads=n_reads, read_len=read_len)
+        if paired:                                         # n_reads mates = n_reads / 2 fragments; some fragments are unmappable by construction
+            e2e.write_paired_inputs(d, ref_len=ref_len, n_frags=n_reads // 2, read_len=read_len, seed=9)
+        else:
+            e2e.write_inputs(d, ref_len=ref_len, n_reads=n_reads, read_len=read_len)
         if chemistry is not None:
-            chemistry(d / "reads.fq", 5, False)
+            chemistry(d / "reads.fq", 5, paired)
         want = e2e.run("ref", d, threads=threads, extra=extra, out_name="ref.sam")
         got = e2e.run("cuda", d, threads=threads, extra=extra, out_name="cuda.sam")
         strict = e2e.run("cuda_strict", d, threads=threads, extra=extra, out_name="cuda_strict.sam") if e2e.available("cuda_strict") else got
     assert strict == got
-    assert len(want) == n_reads + 2                      # @HD, @SQ + one record per read
+    n_head = sum(1 for ln in want if ln.startswith("@"))
+    assert len(want) == n_reads + n_head                 # @HD, @SQ ... + one record per read
     mapped = sum(1 for ln in want if not ln.startswith("@") and ln.split("\t")[2] != "*")
-    assert mapped > 0.98 * n_reads
+    assert mapped > (0.8 if paired else 0.98) * n_reads
     diff = [(a, b) for a, b in zip(want, got) if a != b]
     assert len(want) == len(got) and not diff, f"{len(diff)} SAM lines differ, first:\n{diff[0][0]}\n{diff[0][1]}"
 
@@ -59,3 +63,10 @@ def test_slam_seq_sam_identical():
     NGM's SAMWriter prints TC:i / RA:Z / MP:Z."""
     from tests.test_mapper_oracle import slam_convert
     compare(extra=("--slam-seq", "7"), n_reads=3000, threads=2, chemistry=slam_convert, ref_len=1_000_000)
+
+
+def test_bs_mapping_paired_sam_identical():
+    """`-p --bs-mapping -t 1`: second mates mutate / score the complementary bases (CS.cpp:362-380) and carry the inverted direction flag
+    (ScoreBuffer.cpp:98-106, AlignmentBuffer.cpp:84-94); one CS thread, so that the insert-size tie-break sees the pairs in input order."""
+    from tests.test_mapper_oracle import bisulfite
+    compare(extra=("--bs-mapping", "-p"), n_reads=2000, threads=1, chemistry=bisulfite, ref_len=600_000, paired=True)
