@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -350,6 +351,12 @@ void fragment(const Job &j, int f, std::string &text, std::vector<char> &scratch
 
 }  // namespace
 
+namespace {
+std::mutex g_part_cache_mu;
+std::vector<std::string> g_part_cache;
+constexpr size_t kPartCacheBytes = (size_t) 1 << 30;
+}  // namespace
+
 extern "C" __attribute__((visibility("default"))) int ngm_b200_format_sam(const ngm_b200_encref *ref, const ngm_b200_sam_opts *opts,
 		const ngm_b200_sam_batch *batch, char *out, size_t out_capacity, size_t *out_used) {
 	if (ref == nullptr || opts == nullptr || batch == nullptr || out_used == nullptr || (out == nullptr && out_capacity)) return NGM_B200_EINVAL;
@@ -369,7 +376,24 @@ extern "C" __attribute__((visibility("default"))) int ngm_b200_format_sam(const 
 	const int units = paired ? b.n_reads / 2 : b.n_reads;
 	int threads = opts->threads > 0 ? opts->threads : (int) std::thread::hardware_concurrency();
 	threads = std::max(1, std::min(threads, std::max(1, units / 256)));
-	std::vector<std::string> parts((size_t) threads);
+	// The per-thread output parts are kept from call to call (grow-only, at most kPartCacheBytes in total): a fresh allocation of this size
+	// is unmapped memory whose first touch costs more than formatting the lines (measured: 1.2 -> 3.0 M reads/s per thread).  A call that
+	// finds the cache in use by another thread formats into parts of its own.
+	std::unique_lock<std::mutex> cache_lock(g_part_cache_mu, std::try_to_lock);
+	std::vector<std::string> own_parts;
+	std::vector<std::string> &parts = cache_lock.owns_lock() ? g_part_cache : own_parts;
+	if (parts.size() < (size_t) threads) parts.resize((size_t) threads);
+	for (int t = 0; t < threads; ++t) parts[(size_t) t].clear();
+	struct CacheTrim {                                             // runs on every way out, before the lock is released
+		std::vector<std::string> &p;
+		bool cached;
+		~CacheTrim() {
+			if (!cached) return;
+			size_t held = 0;
+			for (const std::string &x : p) held += x.capacity();
+			if (held > kPartCacheBytes) std::vector<std::string>().swap(p);
+		}
+	} trim = { parts, cache_lock.owns_lock() };
 	const Job job = { ref, opts, batch };
 	std::atomic<int> failed(0);                                    // an allocation failure inside a worker must not reach std::terminate
 	auto work = [&](int t) {
