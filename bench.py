@@ -412,9 +412,10 @@ def main():
     n, npairs = batch.n_reads, batch.n_pairs
     # The caller's staging format (north_star: packed sequences in pinned staging buffers): reads 2 bit / base + lengths, one 64-bit
     # descriptor per (read, candidate), candidate offsets per read.  Packed on the host by the library's own ngm_b200_pack_reads.
-    t0 = time.perf_counter()
     reads_np = batch.reads.cpu().numpy()
-    pk_np, len_np, exc_np = sw.pack_reads(reads_np)
+    sw.pack_reads(reads_np[: 1 << 16])
+    t0 = time.perf_counter()
+    pk_np, len_np, exc_np = sw.pack_reads(reads_np)            # (the call plus the wrapper's allocation of its three result arrays)
     pack_host_s = time.perf_counter() - t0
     del reads_np
     h_packed = torch.from_numpy(pk_np).pin_memory()
@@ -1122,7 +1123,7 @@ def main():
         "kernel_ms": {"set_reads_packed2": ms_expand, "set_reads_ascii": ms_pack, "score_all_pairs": ms_score, "score_in_step": ms_score_step, "align_launch_sets": ms_align, "align_forward": ms_fwd,
                       "align_backtrace_format": ms_bt, "align_without_known_scores": ms_align_unscored, "launch_sets": launch_sets,
                       "pairs_scored_in_step": multi_pairs, "score_share": ms_score_step / (ms_max / args.steps), "align_share": ms_align / (ms_max / args.steps),
-                      "classic_calls_equal_batch": classic_equal, "pack_reads_host_seconds": pack_host_s,
+                      "classic_calls_equal_batch": classic_equal, "pack_reads_host_seconds": pack_host_s, "pack_reads_host_reads_per_s": n / pack_host_s,
                       "step_forward_all": step_fwd_ms, "step_pick_backtrace": step_bt_ms, "step_forward_pairs": step_fwd_pairs,
                       "note": "score_* / align_* time the classic entry points on the same data (one kernel each); step_* are the kernels of one resident step"},
         "candidate_search": cs_info,

@@ -1031,36 +1031,66 @@ int ngm_b200_pack_reads(const char *ascii, int n_reads, int stride, void *packed
 	if (stride > 65535) return fail(NGM_B200_EINVAL, "rows longer than 65535 bases");
 	int nt = threads > 0 ? threads : (int) std::thread::hardware_concurrency();
 	nt = std::max(1, std::min(nt, std::max(1, n_reads / 4096)));
-	// pass 1: pack + count the exceptions of every slice; pass 2 (only when there are any): write them in order
+	// pass 1: pack + count the exceptions of every slice; pass 2 (only when there are any): write them in order, visiting the flagged reads only.
+	// Eight bases at a time: the code is bits 1 and 2 of the letter ((c >> 1 ^ c >> 2) & 3 = A 0, C 1, G 2, T 3, either case), a group of eight
+	// valid letters is folded into 16 bits with three shift-or steps; groups with any other byte and the tail of a read go base by base.
 	std::vector<size_t> cnt((size_t) nt + 1, 0);
+	std::vector<uint8_t> flagged;
+	try {
+		flagged.assign((size_t) n_reads, 0);
+	} catch (...) {
+		return fail(NGM_B200_EINVAL, "out of host memory");
+	}
+	constexpr uint64_t k01 = 0x0101010101010101ull, k7F = 0x7F7F7F7F7F7F7F7Full, k80 = 0x8080808080808080ull;
+	auto is_byte = [&](uint64_t u, unsigned char ch) -> uint64_t {      // 0x80 in every byte of u that equals ch
+		const uint64_t z = u ^ (k01 * ch);
+		return ~(((z & k7F) + k7F) | z | k7F);
+	};
+	auto all_acgt = [&](uint64_t x) -> bool {
+		const uint64_t u = x & 0xDFDFDFDFDFDFDFDFull;
+		return (is_byte(u, 'A') | is_byte(u, 'C') | is_byte(u, 'G') | is_byte(u, 'T')) == k80;
+	};
 	auto pack_slice = [&](int t, bool emit, size_t off) {
 		const int lo = (int) ((long long) n_reads * t / nt), hi = (int) ((long long) n_reads * (t + 1) / nt);
 		size_t k = 0;
 		for (int r = lo; r < hi; ++r) {
 			const unsigned char *s = reinterpret_cast<const unsigned char *>(ascii) + (size_t) r * stride;
-			uint32_t *o = reinterpret_cast<uint32_t *>(static_cast<char *>(packed) + (size_t) r * row_bytes);
-			int len = stride;
-			while (len > 0 && s[len - 1] == 0) --len;              // MappedRead::length: index of the last non-NUL byte + 1
 			if (!emit) {
-				for (int w = 0; w < row_bytes / 4; ++w) {
+				uint32_t *o = reinterpret_cast<uint32_t *>(static_cast<char *>(packed) + (size_t) r * row_bytes);
+				int len = stride;
+				while (len > 0 && s[len - 1] == 0) --len;              // MappedRead::length: index of the last non-NUL byte + 1
+				size_t bad = 0;
+				const int words = row_bytes / 4;
+				for (int w = 0; w < words; ++w) {
 					uint32_t v = 0;
-					const int i0 = 16 * w;
-					for (int i = 0; i < 16 && i0 + i < len; ++i) {
-						const unsigned char ch = s[i0 + i];
-						uint32_t code;
-						switch (ch) {
-							case 'A': case 'a': code = 0; break;
-							case 'C': case 'c': code = 1; break;
-							case 'G': case 'g': code = 2; break;
-							case 'T': case 't': code = 3; break;
-							default: code = 0; ++k; break;
+					for (int half = 0; half < 2; ++half) {
+						const int i0 = 16 * w + 8 * half;
+						if (i0 >= len) break;
+						uint32_t g = 0;
+						uint64_t x;
+						if (i0 + 8 <= len && (memcpy(&x, s + i0, 8), all_acgt(x))) {
+							uint64_t c2 = ((x >> 1) ^ (x >> 2)) & 0x0303030303030303ull;
+							c2 = (c2 | (c2 >> 6)) & 0x000F000F000F000Full;
+							c2 = (c2 | (c2 >> 12)) & 0x000000FF000000FFull;
+							g = (uint32_t) ((c2 | (c2 >> 24)) & 0xFFFFull);
+						} else {
+							for (int i = 0; i < 8 && i0 + i < len; ++i) {
+								const unsigned char ch = s[i0 + i], u = ch & 0xDF;
+								if (u == 'A' || u == 'C' || u == 'G' || u == 'T') g |= (uint32_t) (((ch >> 1) ^ (ch >> 2)) & 3u) << (2 * i);
+								else ++bad;                            // code 0; the byte itself travels in the exception list
+							}
 						}
-						v |= code << (2 * i);
+						v |= g << (16 * half);
 					}
 					o[w] = v;
 				}
 				read_len[r] = (uint16_t) len;
-			} else {
+				if (bad) {
+					flagged[(size_t) r] = 1;
+					k += bad;
+				}
+			} else if (flagged[(size_t) r]) {
+				const int len = (int) read_len[r];
 				for (int i = 0; i < len; ++i) {
 					const unsigned char u = s[i] & 0xDF;
 					if (!(u == 'A' || u == 'C' || u == 'G' || u == 'T')) {
