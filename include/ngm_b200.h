@@ -394,8 +394,10 @@ typedef struct ngm_b200_sam_batch {
 } ngm_b200_sam_batch;
 /* SAM body lines (no header) of the batch in read order, what AlignmentBuffer::WriteRead (AlignmentBuffer.cpp:166-200),
  * GenericReadWriter::WriteRead / WritePair (GenericReadWriter.h:190-312) and SAMWriter::DoWriteReadGeneric / DoWriteUnmappedReadGeneric /
- * DoWritePair (SAMWriter.cpp:98-228,230-365) produce for topn 1 without bs-mapping, clipping options or read group.  Host only,
- * multi-threaded.  *out_used receives the bytes needed; NGM_B200_ERANGE if that exceeds out_capacity (nothing is written then). */
+ * DoWritePair (SAMWriter.cpp:98-228,230-365) produce, incl. several alignments per read (topn), the clipping options, read group, and the
+ * bs-mapping / SLAMseq tags (ngm_b200_sam_opts).  Host only, multi-threaded.  *out_used receives the bytes needed; NGM_B200_ERANGE if that
+ * exceeds out_capacity (nothing is written then).  The library keeps its per-thread scratch (at most 1 GiB, about the size of the largest
+ * batch's text) from call to call; concurrent calls are allowed, all but one of them work in scratch of their own. */
 int ngm_b200_format_sam(const ngm_b200_encref *ref, const ngm_b200_sam_opts *opts, const ngm_b200_sam_batch *batch, char *out, size_t out_capacity,
 		size_t *out_used);
 /* Single-end selection with "topn" > 1 (ScoreBuffer::topNSE, ScoreBuffer.cpp:279-330; `-n`, `--strata`): the candidates are sorted by score
