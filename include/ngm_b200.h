@@ -243,7 +243,7 @@ int ngm_b200_cs_set_sensitivity(ngm_b200_ctx *ctx, float sensitivity);
  * C -> T -- second mate: G -> A -- replacement with weight 1 / (replaceable bases + 1), so votes become fractional).  paired = "paired": odd rows of
  * a read batch are second mates.  Both zero switches the mutation off.  With mutation on, every read is searched by the sequential kernel in the
  * table of CS::RunBatch's last overflow retry (2^20 slots, CS.cpp:404-428); a read that overflows it keeps no candidates, as in the reference.
- * Call after cs_build_index / cs_load_index; applies to cs_search, dev_cs_search and map_batch (sub-batches must hold whole pairs).  The sensitivity
+ * Call after cs_build_index / cs_load_index (a new index starts with the mutation off); applies to cs_search, dev_cs_search and map_batch (sub-batches must hold whole pairs).  The sensitivity
  * estimate is not affected: ReadProvider::init estimates with plain k-mers under slam_seq and, under bs_mapping, uses 0.5 unless -s is given
  * (ReadProvider.cpp:194-197,326,378-384). */
 int ngm_b200_cs_configure_mutation(ngm_b200_ctx *ctx, int bs_mapping, int slam_seq, int bs_cutoff, int paired, int read_kmer_skip);
