@@ -448,10 +448,16 @@ long long cs_oracle_search_batch(const cs_oracle_index *ix, const char *reads, i
 /* CS::RunBatch with bs_mapping / slam_seq (CS.cpp:340-436): the mutated base by mode and mate, the search in a table of 2^table_bits
  * slots with a budget of 0.333 x slots probe steps, after an overflow again with table_bits + 2, + 3, ... <= 20 and 0.777 x slots; a read
  * that overflows every table keeps no candidates. */
+static long long g_mut_retries = 0, g_mut_dropped = 0;
+/* diagnostics of the last cs_oracle_search_batch_mut call: searches repeated in a larger table, reads that overflowed every table */
+long long cs_oracle_last_retries(void) { return g_mut_retries; }
+long long cs_oracle_last_dropped(void) { return g_mut_dropped; }
+
 long long cs_oracle_search_batch_mut(const cs_oracle_index *ix, const char *reads, int n_reads, int stride, float sensitivity, float kmer_min,
 		int max_kfreq, int max_cmrs, int mutate_mode, int bs_cutoff, int paired, int read_skip, int table_bits, int *cand_begin,
 		cs_oracle_cand *out, long long out_cap, float *max_hit) {
 	search_state s;
+	g_mut_retries = g_mut_dropped = 0;
 	memset(&s, 0, sizeof(s));
 	s.ix = ix;
 	s.max_kfreq = max_kfreq;
@@ -487,7 +493,11 @@ long long cs_oracle_search_batch_mut(const cs_oracle_index *ix, const char *read
 			x += 1;
 			++tries;
 		}
-		if (n < 0) n = 0;
+		g_mut_retries += tries - 1;
+		if (n < 0) {
+			n = 0;
+			g_mut_dropped += 1;
+		}
 		total += n;
 	}
 	cand_begin[n_reads] = (int) total;

@@ -57,6 +57,10 @@ long long cs_oracle_search_batch_mut(const cs_oracle_index *ix, const char *read
 		int max_kfreq, int max_cmrs, int mutate_mode, int bs_cutoff, int paired, int read_skip, int table_bits, int *cand_begin,
 		cs_oracle_cand *out, long long out_cap, float *max_hit);
 
+/* diagnostics of the last cs_oracle_search_batch_mut call: searches repeated in a larger table, reads that overflowed every table */
+long long cs_oracle_last_retries(void);
+long long cs_oracle_last_dropped(void);
+
 /* The sensitivity NGM estimates when -s is absent (ReadProvider::init, ReadProvider.cpp:236-251,310-325 with the static PrefixSearch
  * :81-123 and CollectResultsFallback :53-79).  `sampled`: the reads number 1000, 2000, ... of the input.  Returns the number of reads
  * that contributed; *sensitivity = min(max(0.3, mean), 0.9) (no --fast / --sensitive modifier). */

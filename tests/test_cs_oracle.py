@@ -169,3 +169,41 @@ def test_fresh_mutated_differential_run_against_reference(seed, k, read_len, sen
         got = (float(mh[r]), [(int(c["location"]), int(c["reverse"]), float(c["score"])) for c in cands[begin[r]: begin[r + 1]]])
         assert got == (f32(m), [(a, b, f32(v)) for a, b, v in cl]), (r, got, (m, cl))
     ix.close()
+
+
+@pytest.mark.skipif(not cs_port.probe_available(), reason="oracle/_ref/ngm/ngm_cs_probe not built")
+def test_mutated_search_table_overflow_retries_match_reference():
+    """CS::RunBatch repeats a read's search in a larger table when the 2^16-slot table runs out of probe steps (CS.cpp:386-430): bs-mapping on
+    a 30 Mbp reference with k 10 gives a 250 bp read ~35 000 distinct bins (one retry, 2^18 slots) and a 900 bp read ~410 000 (three retries,
+    up to 2^20 slots).  The restatement must take the same decisions -- a search that is cut short or repeated once too often changes votes."""
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    ref_len, k = 30_000_000, 10
+    contigs = [acgt[rng.integers(0, 4, ref_len)].tobytes()]
+    concat, ctg, concat_len = cs_port.layout(contigs)
+    full = np.frombuffer(concat, np.uint8)
+    lens = [250] * 16 + [900] * 3
+    reads = np.zeros((len(lens), 902), np.uint8)
+    for r, ln in enumerate(lens):
+        pos = int(rng.integers(2000, ref_len - 2000))
+        s = full[pos: pos + ln].copy()
+        s[(s == ord("C")) & (rng.random(ln) < 0.9)] = ord("T")
+        reads[r, :ln] = s
+    with tempfile.TemporaryDirectory(prefix="csovf_") as td:
+        d = Path(td)
+        cs_cases.write_fasta(d / "ref.fa", contigs)
+        cs_cases.write_fastq(d / "reads.fq", reads)
+        head, rows = cs_port.run_probe(d, "ref.fa", "reads.fq", 0.5, k=k, extra=["--bs-mapping"])
+    ix = cs_port.Index(port.pack_ref(concat), concat_len, ctg, k=k, ref_skip=0)
+    begin, cands, mh = ix.search_mut(reads, 0.5, 1, read_skip=2, max_kfreq=head["max_kfreq"])
+    lib = port.lib()
+    lib.cs_oracle_last_retries.restype = C.c_longlong
+    lib.cs_oracle_last_dropped.restype = C.c_longlong
+    assert lib.cs_oracle_last_retries() >= 20 and lib.cs_oracle_last_dropped() == 0      # (24 here: nearly every read is searched again)
+    for (rid, name, ln, m, cl) in rows:
+        r = int(name[1:])
+        got = (float(mh[r]), [(int(c["location"]), int(c["reverse"]), float(c["score"])) for c in cands[begin[r]: begin[r + 1]]])
+        assert got == (m, cl), (r, got, (m, cl))
+        assert len(cl) >= 1 and cl[0][2] > 30
+    ix.close()
