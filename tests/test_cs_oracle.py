@@ -150,19 +150,26 @@ def test_mutated_search_matches_reference_fixture(name):
 
 
 @pytest.mark.skipif(not cs_port.probe_available(), reason="oracle/_ref/ngm/ngm_cs_probe not built")
-@pytest.mark.parametrize("seed,k,read_len,sens,mode,paired", [(17, 11, 90, 0.5, 1, False), (18, 13, 120, 0.4, 2, True)])
-def test_fresh_mutated_differential_run_against_reference(seed, k, read_len, sens, mode, paired):
+@pytest.mark.parametrize("seed,k,read_len,sens,mode,paired,opts", [(17, 11, 90, 0.5, 1, False, {}), (18, 13, 120, 0.4, 2, True, {}),
+                                                                   (19, 12, 100, 0.5, 1, True, {"kmer_skip": 1, "bs_cutoff": 2}),
+                                                                   (20, 10, 60, 0.7, 1, False, {"kmer_skip": 4, "bs_cutoff": 9})])
+def test_fresh_mutated_differential_run_against_reference(seed, k, read_len, sens, mode, paired, opts):
+    """opts: under --bs-mapping `--kmer-skip` thins the READ's k-mers (CS.cpp:556-560; the index keeps every position) and `--bs-cutoff`
+    bounds the replaceable bases per k-mer."""
     contigs = cs_cases.make_reference(seed)
     concat, ctg, concat_len = cs_port.layout(contigs)
     reads = cs_cases.convert_bases(cs_cases.make_reads(seed + 1, concat, ctg, 300, read_len, (read_len | 1) + 1), seed + 2, mode, paired)
     extra = (["--bs-mapping"] if mode == 1 else ["--slam-seq", "4"]) + (["-p", "--skip-mate-check"] if paired else [])
+    read_skip, cutoff = opts.get("kmer_skip", 2), opts.get("bs_cutoff", 6)
+    if opts:
+        extra += ["--kmer-skip", str(read_skip), "--bs-cutoff", str(cutoff)]
     with tempfile.TemporaryDirectory(prefix="csmutdiff_") as td:
         d = Path(td)
         cs_cases.write_fasta(d / "ref.fa", contigs)
         cs_cases.write_fastq(d / "reads.fq", reads)
         head, rows = cs_port.run_probe(d, "ref.fa", "reads.fq", sens, k=k, extra=extra)
     ix = cs_port.Index(port.pack_ref(concat), concat_len, ctg, k=k, ref_skip=0 if mode == 1 else 2)
-    begin, cands, mh = ix.search_mut(reads, sens, mode, paired=paired, read_skip=2 if mode == 1 else 0, max_kfreq=head["max_kfreq"])
+    begin, cands, mh = ix.search_mut(reads, sens, mode, bs_cutoff=cutoff, paired=paired, read_skip=read_skip if mode == 1 else 0, max_kfreq=head["max_kfreq"])
     f32 = lambda x: float(np.float32(x))
     for (rid, name, ln, m, cl) in rows:
         r = int(name[1:])
