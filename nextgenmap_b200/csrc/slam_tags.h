@@ -47,8 +47,9 @@ inline bool slam_positions(const char *cigar, size_t cigar_len, const char *md, 
 	size_t cp = 0;
 	while (cp < cigar_len && cigar[cp] != '\0') {
 		long len = 0;
+		const size_t digits_at = cp;
 		while (cp < cigar_len && cigar[cp] >= '0' && cigar[cp] <= '9') len = len * 10 + (cigar[cp++] - '0');
-		if (cp >= cigar_len) return false;
+		if (cp >= cigar_len || cp == digits_at || len > (1L << 24)) return false;      // an op needs a count
 		const char op = cigar[cp++];
 		if (op == 'S' || op == 'H') continue;                     // QStart / QEnd: already in read_pos
 		if (op == 'I') {
