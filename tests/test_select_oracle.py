@@ -117,6 +117,7 @@ def test_slam_tags_from_cigar_and_md_and_bad_strings():
     # the hand-checked one: 2S, then read[2..6) = G T T C against reference G T A C (MD "2A1"): one mismatch, reference A under read T
     # (type 5 * trans[A] + trans[T] = 3) at read position 5 and reference position 3 (1-based); MD's "4" counts the last column of this
     # run and the three of the next; "^GT" is the deletion; "1C2" puts a reference C under read[11]
+    tags = dict(f.split(":", 2)[::2] for f in lines[0].split("\t")[11:])
     assert tags["MP"].split(",")[0] == "3:5:3"
     assert tags["TC"] == "0" and sum(int(v) for v in tags["RA"].split(",")) == 11        # 4 + 3 + 4 aligned columns
     assert "MP" not in dict(f.split(":", 2)[::2] for f in lines[-1].split("\t")[11:])     # 14M / MD 14: no mismatch, no MP tag
